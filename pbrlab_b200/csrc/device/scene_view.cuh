@@ -1,0 +1,52 @@
+// Device-side view of a committed scene: every pointer is HBM-resident, read-only during rendering and identical
+// on every GPU (the scene is replicated).  Built by pbrgpu_commit() (csrc/pbrgpu.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pbr {
+
+// include/pbrgpu.h: pbrgpu_material (112 bytes)
+struct DeviceMaterial {
+  uint32_t type;        // 0 = CyclesPrincipledBsdfParameter, 1 = HairBsdfParameter (material-param.h:20-23)
+  uint32_t tex_id[2];
+  uint32_t reserved;
+  float p[24];
+};
+
+struct LightRec {        // one entry of LightManager::lights_ (light-manager.h:185-189) flattened
+  float choose_probability;
+  uint32_t prim_offset;  // first entry in the per-primitive light tables
+  uint32_t prim_count;
+  uint32_t pad;
+};
+
+struct SceneView {
+  // ---- traversal (see bvh_builder.h for the node format)
+  const float4* tri_nodes;     // 5 x float4 per 8-wide compressed node; root = node 0
+  const float4* tri_data;      // leaf-ordered, 3 x float4 per triangle: (v0, prim id) (e1=v0-v1, 0) (e2=v2-v0, 0)
+  const float4* curve_nodes;
+  const float4* curve_data;    // leaf-ordered, 4 x float4 (xyz, radius) per cubic Bezier segment
+  const uint32_t* curve_prim;  // leaf order -> curve primitive id
+  uint32_t num_tris, num_curves;
+  // ---- per-primitive shading tables (indexed by primitive id = order given to pbrgpu_set_*)
+  const uint4* tri_ids;        // instance_id, geom_id, prim_id inside the shape, material_id
+  const uint4* tri_nidx;       // 3 normal indices (0xFFFFFFFF = none), index into emissive[] or 0xFFFFFFFF
+  const uint4* tri_vidx;       // 3 vertex indices, unused
+  const uint4* tri_tidx;       // 3 texcoord indices (0xFFFFFFFF = none), unused
+  const float4* verts;         // xyzw
+  const float4* normals;       // xyzw
+  const float2* texcoords;
+  const uint4* curve_ids;      // instance_id, geom_id, segment id inside the shape, material_id
+  const DeviceMaterial* materials;
+  uint32_t num_materials;
+  // ---- lights (light-manager.h:172-193 flattened)
+  const float4* emissive;      // per emissive triangle: emission rgb, pdf = P(light) P(prim) / area   (ImplicitAreaLight)
+  const float* light_cdf;      // cumulative_probability_ over lights
+  const LightRec* lights;
+  uint32_t num_lights;
+  const float* lprim_cdf;      // per light primitive: AreaLight::cumulative_probability_
+  const float4* lprim_info;    // per light primitive: emission rgb, pdf = P(light) P(prim) / area
+  const uint32_t* lprim_tri;   // per light primitive: triangle primitive id
+};
+
+}  // namespace pbr

@@ -1,0 +1,477 @@
+// Per-vertex shading of one path, restating the reference's integrator pieces so that, given the same PCG32
+// stream, a path takes the same decisions in the same order:
+//   hit -> SurfaceInfo            src/shader/shader-utils.h:131-164, src/scene.cc:186-249, src/mesh/triangle-mesh.cc:62-184
+//   emission + MIS, roulette      src/render.cc:39-69
+//   area-light sampling / NEE     src/light-manager.h:37-170, src/shader/shader-utils.h:116-129,166-212
+//   Principled vertex             src/shader/cycles-principled-shader.cc:169-242,414-484
+//   random-walk subsurface        src/shader/random-walk-sss.h:111-405
+//   hair vertex                   src/shader/hair-shader.cc:153-229
+// Difference by design (wavefront): the NEE shadow ray is not traced here; the vertex returns it as a request with
+// the contribution it would add, and the any-hit kernel adds it when unoccluded.  No random number depends on the
+// outcome, so the draw order is unchanged.
+#pragma once
+#include "common.cuh"
+#include "hair.cuh"
+#include "principled.cuh"
+#include "rng.cuh"
+#include "sampling.cuh"
+#include "scene_view.cuh"
+#include "traverse.cuh"
+
+// g++ evaluates the two rng.Draw() arguments of UniformSampleSphere(rng.Draw(), rng.Draw())
+// (random-walk-sss.h:296) right to left: the FIRST draw becomes u2 (cos theta).  Checked against the compiled
+// reference by tests/test_shade_parity.py.
+#ifndef PBR_SSS_SPHERE_DRAW_RIGHT_TO_LEFT
+#define PBR_SSS_SPHERE_DRAW_RIGHT_TO_LEFT 1
+#endif
+
+namespace pbr {
+
+enum FaceDirection { kFront = 0, kBack = 1, kAmbiguous = 2 };
+
+struct Surface {                 // SurfaceInfo (shader-utils.h:18-41)
+  vec3 P, Ns, Ng;
+  float u, v, tex_u, tex_v;
+  uint32_t instance_id, geom_id, prim_id, material_id, light_entry;
+  int face;
+  bool is_curve;
+};
+
+PBR_HD vec3 NormalizeNoCheck(const vec3& v) {      // raytracer_impl.cc:213-219
+  const float inv_norm = 1.0f / sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+  return vec3(v.x * inv_norm, v.y * inv_norm, v.z * inv_norm);
+}
+
+// geometric normal Embree reports, normalised as EmbreeRayToTraceResult does (raytracer_impl.cc:221-243)
+PBR_HD vec3 HitGeometricNormal(const SceneView& s, const HitT& hit) {
+  if (hit.prim & kCurveFlag) {
+    const uint32_t i = hit.prim & ~kCurveFlag;
+    return NormalizeNoCheck(CurveTangent(s.curve_data[i * 4 + 0], s.curve_data[i * 4 + 1], s.curve_data[i * 4 + 2],
+                                         s.curve_data[i * 4 + 3], hit.u));
+  }
+  const vec3 e1 = from4(s.tri_data[hit.prim * 3 + 1]), e2 = from4(s.tri_data[hit.prim * 3 + 2]);
+  return NormalizeNoCheck(ecross(e2, e1));
+}
+
+PBR_HD Surface MakeSurface(const SceneView& s, const RayT& ray, const HitT& hit) {
+  Surface si;
+  si.u = hit.u;
+  si.v = hit.v;
+  si.P = ray.o + hit.t * ray.d;
+  si.Ng = HitGeometricNormal(s, hit);
+  si.light_entry = kInvalid;
+  if (hit.prim & kCurveFlag) {
+    const uint32_t prim = s.curve_prim[hit.prim & ~kCurveFlag];
+    const uint4 ids = s.curve_ids[prim];
+    si.instance_id = ids.x; si.geom_id = ids.y; si.prim_id = ids.z; si.material_id = ids.w;
+    si.is_curve = true;
+    si.Ns = si.Ng;                              // scene.cc:222-223
+    si.tex_u = 0.f; si.tex_v = 0.f;             // scene.cc:243-245
+  } else {
+    const uint32_t prim = f2u(s.tri_data[hit.prim * 3 + 0].w);
+    const uint4 ids = s.tri_ids[prim];
+    si.instance_id = ids.x; si.geom_id = ids.y; si.prim_id = ids.z; si.material_id = ids.w;
+    si.is_curve = false;
+    const uint4 ni = s.tri_nidx[prim];
+    si.light_entry = ni.w;
+    if (ni.x == kInvalid || ni.y == kInvalid || ni.z == kInvalid) {
+      // FetchGeometryNormal: normalize((p1-p0) x (p2-p1)) from the mesh vertices (triangle-mesh.cc:62-75,181-184)
+      const uint4 vi = s.tri_vidx[prim];
+      const vec3 p0 = from4(s.verts[vi.x]), p1 = from4(s.verts[vi.y]), p2 = from4(s.verts[vi.z]);
+      si.Ns = vnormalized(vcross(p1 - p0, p2 - p1));
+    } else {
+      si.Ns = vnormalized(Lerp3(from4(s.normals[ni.x]), from4(s.normals[ni.y]), from4(s.normals[ni.z]), hit.u, hit.v));
+    }
+    const uint4 ti = s.tri_tidx[prim];
+    if (ti.x == kInvalid || ti.y == kInvalid || ti.z == kInvalid) {
+      si.tex_u = hit.u; si.tex_v = hit.v;       // triangle-mesh.cc:131-135
+    } else {
+      const float2 t0 = s.texcoords[ti.x], t1 = s.texcoords[ti.y], t2 = s.texcoords[ti.z];
+      const float w = 1.0f - hit.u - hit.v;
+      si.tex_u = (w * t0.x + hit.u * t1.x) + hit.v * t2.x;
+      si.tex_v = (w * t0.y + hit.u * t1.y) + hit.v * t2.y;
+    }
+  }
+  const float dg = vdot(ray.d, si.Ng), ds = vdot(ray.d, si.Ns);
+  if (dg < 0.0f && ds < 0.0f) si.face = kFront;
+  else if (dg > 0.0f && ds > 0.0f) si.face = kBack;
+  else si.face = kAmbiguous;
+  return si;
+}
+
+// ---------------------------------------------------------------- lights
+struct LightSample {
+  bool valid;
+  vec3 pos, normal, emission;
+  float pdf;
+};
+
+// std::lower_bound(cdf, cdf+n, u) - cdf, clamped to n-1 (release builds of the reference index past the end when
+// rounding leaves the last CDF entry below u)
+PBR_HD uint32_t LowerBound(const float* cdf, uint32_t n, float u) {
+  uint32_t lo = 0, len = n;
+  while (len > 0) {
+    const uint32_t half = len >> 1;
+    if (cdf[lo + half] < u) { lo += half + 1; len -= half + 1; }
+    else len = half;
+  }
+  return lo < n ? lo : n - 1;
+}
+
+// LightManager::SampleAllLight (light-manager.h:79-170): 4 draws (light, primitive, u, v); none without lights
+PBR_HD LightSample SampleAllLight(const SceneView& s, Pcg32* rng) {
+  LightSample r;
+  r.valid = false;
+  r.pos = r.normal = r.emission = vec3(0.f);
+  r.pdf = 0.f;
+  if (s.num_lights == 0) return r;
+  const float u0 = Draw(rng);
+  const uint32_t li = LowerBound(s.light_cdf, s.num_lights, u0);
+  const LightRec L = s.lights[li];
+  const float u1 = Draw(rng);
+  const uint32_t pi = L.prim_offset + LowerBound(s.lprim_cdf + L.prim_offset, L.prim_count, u1);
+  const float4 info = s.lprim_info[pi];
+  const float u2 = Draw(rng), u3 = Draw(rng);
+  float bu, bv;
+  TriangleUniformSampler(u2, u3, &bu, &bv);
+  const uint4 vi = s.tri_vidx[s.lprim_tri[pi]];
+  const vec3 p0 = from4(s.verts[vi.x]), p1 = from4(s.verts[vi.y]), p2 = from4(s.verts[vi.z]);
+  r.pos = Lerp3(p0, p1, p2, bu, bv);                         // FetchLocalPosition, not transformed
+  r.normal = vnormalized(vcross(p1 - p0, p2 - p1));          // FetchGeometryNormal
+  r.emission = vec3(info.x, info.y, info.z);
+  r.pdf = info.w;                                            // P(light) * P(prim) * 1/area
+  r.valid = true;
+  return r;
+}
+
+struct ShadowRequest {
+  bool active;
+  RayT ray;
+  vec3 contribute;   // already includes f * Le * w / pdf, excludes the path throughput
+};
+
+// DirectIllumination (shader-utils.h:166-212) up to, but not including, the occlusion test.
+// eval(omega_l_local, &f, &pdf) is the closure's EvalFunc with omega_out bound.
+template <class Eval>
+PBR_HD void DirectIllumination(const SceneView& s, const vec3& P, const Frame& Rgl, const vec3& global_normal,
+                               Pcg32* rng, const Eval& eval, bool hemisphere, ShadowRequest* req) {
+  req->active = false;
+  const LightSample ls = SampleAllLight(s, rng);
+  if (!ls.valid) return;
+  const vec3 dir_to_light = vnormalized(ls.pos - P);
+  const float dist = vlength(P - ls.pos);
+  const float wl_dot_nl = -vdot(dir_to_light, ls.normal);
+  const float wl_dot_np = vdot(dir_to_light, global_normal);
+  const float pdf_sigma = fabsf(ls.pdf * dist * dist / (wl_dot_nl * wl_dot_np));
+  if ((!hemisphere) || (wl_dot_nl > 0.0f && wl_dot_np > 0.0f)) {
+    const vec3 omega_l = Rgl.ToLocal(dir_to_light);
+    vec3 f(0.0f);
+    float pdf = 0.f;
+    eval(omega_l, &f, &pdf);
+    const float weight = PowerHeuristicWeight(pdf_sigma, pdf);
+    req->contribute = f * ls.emission * weight / pdf_sigma;
+    req->ray.o = P;
+    req->ray.d = dir_to_light;
+    req->ray.tmin = kEps;                               // ShadowRay (shader-utils.h:116-129)
+    req->ray.tmax = fmaxf_(kEps, dist - kEps);
+    req->active = true;
+  }
+}
+
+// ---------------------------------------------------------------- result of one vertex
+struct VertexResult {
+  vec3 wi;          // next direction (world)
+  vec3 throughput;  // f * |cos| / pdf
+  float pdf;        // pdf of the BSDF sample (for emission MIS at the next vertex)
+  vec3 P;           // origin of the next ray (the SSS exit point after a walk)
+  ShadowRequest shadow[2];
+};
+
+PBR_HD void AbsorbVertex(const vec3& wo, const vec3& P, VertexResult* out) {
+  out->wi = wo;
+  out->throughput = vec3(0.f);
+  out->pdf = 0.f;
+  out->P = P;
+  out->shadow[0].active = false;
+  out->shadow[1].active = false;
+}
+
+struct PrincipledEval {
+  const PrincipledBsdf* bsdf;
+  vec3 wo;
+  PBR_HD void operator()(const vec3& wi, vec3* f, float* pdf) const { EvalBsdf(wi, wo, *bsdf, f, pdf); }
+};
+
+// SampleBsdf without the subsurface branch (cycles-principled-shader.cc:169-242); `select` already drawn.
+// Falls through to the clearcoat lobe when no weight catches the selector (quirk 9).
+PBR_HD void SampleBsdfLobes(const PrincipledBsdf& bsdf, const SampleWeight& w, float select, const vec3& wo,
+                            Pcg32* rng, vec3* wi, vec3* f, float* pdf) {
+  if (select < w.diffuse) {
+    const float u0 = Draw(rng), u1 = Draw(rng);
+    *wi = CosineSampleHemisphere(u0, u1);
+  } else if (select < w.diffuse + w.subsurface + w.specular) {
+    const float u0 = Draw(rng), u1 = Draw(rng);
+    float p = 0.f;
+    MicrofacetGGXSample(wo, bsdf.alpha_x, bsdf.alpha_y, u0, u1, 2, wi, &p);
+  } else {
+    const float u0 = Draw(rng), u1 = Draw(rng);
+    float p = 0.f;
+    MicrofacetGGXSample(wo, bsdf.clearcoat_alpha_x, bsdf.clearcoat_alpha_y, u0, u1, 1, wi, &p);
+  }
+  EvalBsdf(*wi, wo, bsdf, f, pdf);
+}
+
+PBR_HD void FinishPrincipled(const Frame& entry, const vec3& omega_in, const vec3& bsdf_f, float ret_pdf,
+                             VertexResult* out) {
+  out->wi = entry.ToWorld(omega_in);                  // entry-point frame even after SSS (quirk 13)
+  const float cos_i = fabsf(omega_in.z);
+  out->throughput = bsdf_f * cos_i / ret_pdf;
+  out->pdf = ret_pdf;
+  if (!IsFinite3(out->throughput) || !finitef_(out->pdf)) {
+    out->throughput = vec3(0.f);
+    out->pdf = 0.f;
+  }
+}
+
+PBR_HD PrincipledBsdf SurfaceBsdf(const SceneView& s, const Surface& si) {
+  const DeviceMaterial& m = s.materials[si.material_id];
+  PrincipledParams pp;
+  memcpy(&pp, m.p, 23 * sizeof(float));
+  pp.base_color_tex_id = m.tex_id[0];
+  pp.subsurface_color_tex_id = m.tex_id[1];
+  // textures: SURVEY §8(f)-4 (next row); ids other than "none" are rejected at pbrgpu_set_materials
+  return ParamToBsdf(pp, vec3(pp.base_color[0], pp.base_color[1], pp.base_color[2]),
+                     vec3(pp.subsurface_color[0], pp.subsurface_color[1], pp.subsurface_color[2]));
+}
+
+PBR_HD Frame PrincipledFrame(const Surface& si) {
+  Frame f;
+  f.ez = (si.face == kFront) ? si.Ns : -si.Ns;
+  BranchlessONB(f.ez, &f.ex, &f.ey);
+  return f;
+}
+
+// CyclesPrincipledShader (cycles-principled-shader.cc:414-484).  Returns true when the sampled closure is the
+// random walk: the caller then runs SubsurfaceVertex (possibly in another kernel); rng is left right after the
+// selector draw in that case.
+PBR_HD bool PrincipledVertex(const SceneView& s, const Surface& si, const vec3& wo_world, Pcg32* rng,
+                             VertexResult* out) {
+  if (si.face == kAmbiguous) {
+    AbsorbVertex(wo_world, si.P, out);
+    return false;
+  }
+  const Frame fr = PrincipledFrame(si);
+  const vec3 wo = fr.ToLocal(wo_world);
+  const PrincipledBsdf bsdf = SurfaceBsdf(s, si);
+  out->P = si.P;
+  out->shadow[1].active = false;
+  PrincipledEval ev = {&bsdf, wo};
+  DirectIllumination(s, si.P, fr, fr.ez, rng, ev, true, &out->shadow[0]);
+
+  const SampleWeight w = FetchClosureSampleWeight(wo, bsdf);
+  const float select = Draw(rng);
+  if (!(select < w.diffuse) && select < w.diffuse + w.subsurface) return true;
+  vec3 wi(0.f), f(0.f);
+  float pdf = 0.f;
+  SampleBsdfLobes(bsdf, w, select, wo, rng, &wi, &f, &pdf);
+  FinishPrincipled(fr, wi, f, pdf, out);
+  return false;
+}
+
+// ---------------------------------------------------------------- random-walk SSS (random-walk-sss.h)
+PBR_HD void ComputeScatteringCoefficientFromAlbedo(float A, float d, float* sigma_t, float* sigma_s) {   // :111-121
+  const float a = 1.0f - expf(A * (-5.09406f + A * (2.61188f - A * 4.31805f)));
+  const float sfit = 1.9f - A + 3.5f * Sqr(A - 0.8f);
+  *sigma_t = 1.0f / fmaxf_(d * sfit, 1e-16f);
+  *sigma_s = *sigma_t * a;
+}
+
+PBR_HD float SampleScatterDistance(const vec3& throughput, const vec3& sigma_s, const vec3& sigma_t, float u0,
+                                   float u1, vec3* channel_pdf) {                                          // :141-187
+  const vec3 albedo = SafeDivideSpectrum(sigma_s, sigma_t);
+  const float w0 = fabsf(throughput.x * albedo.x), w1 = fabsf(throughput.y * albedo.y),
+              w2 = fabsf(throughput.z * albedo.z);
+  const float sum = w0 + w1 + w2;
+  if (sum > 0.0f) *channel_pdf = vec3(w0 / sum, w1 / sum, w2 / sum);
+  else *channel_pdf = vec3(1.0f / 3.0f, 1.0f / 3.0f, 1.0f / 3.0f);
+  float sample_sigma_t;
+  if (u0 < channel_pdf->x) sample_sigma_t = sigma_t.x;
+  else if (u0 < channel_pdf->x + channel_pdf->y) sample_sigma_t = sigma_t.y;
+  else sample_sigma_t = sigma_t.z;
+  return -logf(1.0f - u1) / sample_sigma_t;
+}
+
+struct SssWalkState {     // what one in-flight random walk carries between bounces
+  vec3 sigma_t, sigma_s, throughput;
+  RayT ray;
+  uint32_t bounce;
+};
+
+// Steps 1-2 of RandomWalkSubsurface (:227-279): entry direction + coefficients.  false = walk rejected.
+PBR_HD bool SssBegin(const Surface& si, const Frame& entry, const PrincipledBsdf& bsdf, Pcg32* rng,
+                     SssWalkState* w) {
+  if (si.face != kFront) return false;
+  const float u0 = Draw(rng), u1 = Draw(rng);
+  const vec3 tmp = -CosineSampleHemisphere(u0, u1);
+  const vec3 global_dir = entry.ToWorld(tmp);
+  if (vdot(-si.Ng, global_dir) <= 0.0f) return false;
+  float st[3], ss[3];
+  ComputeScatteringCoefficientFromAlbedo(bsdf.subsurface_albedo.x, bsdf.subsurface_radius.x, &st[0], &ss[0]);
+  ComputeScatteringCoefficientFromAlbedo(bsdf.subsurface_albedo.y, bsdf.subsurface_radius.y, &st[1], &ss[1]);
+  ComputeScatteringCoefficientFromAlbedo(bsdf.subsurface_albedo.z, bsdf.subsurface_radius.z, &st[2], &ss[2]);
+  w->sigma_t = vec3(st[0], st[1], st[2]);
+  w->sigma_s = vec3(ss[0], ss[1], ss[2]);
+  w->throughput = SafeDivideSpectrum(bsdf.subsurface_weight, bsdf.subsurface_albedo);
+  w->ray.o = si.P;
+  w->ray.d = global_dir;
+  w->ray.tmin = 1e-3f;
+  w->ray.tmax = kInf;
+  w->bounce = 0;
+  return true;
+}
+
+enum SssStep { kSssContinue = 0, kSssHit = 1, kSssAbsorbed = 2 };
+
+// One iteration of the walk loop (:281-383).  On kSssHit, *hit holds the exit intersection along w->ray.
+PBR_HD SssStep SssBounce(const SceneView& s, Pcg32* rng, SssWalkState* w, HitT* hit, uint64_t* rays) {
+  if (w->bounce > 0) {
+#if PBR_SSS_SPHERE_DRAW_RIGHT_TO_LEFT
+    const float u2 = Draw(rng), u1 = Draw(rng);
+#else
+    const float u1 = Draw(rng), u2 = Draw(rng);
+#endif
+    w->ray.d = vnormalized(UniformSampleSphere(u1, u2));
+    w->ray.tmin = 0.f;
+  }
+  vec3 channel_pdf;
+  const float ua = Draw(rng), ub = Draw(rng);
+  const float t_scatter = SampleScatterDistance(w->throughput, w->sigma_s, w->sigma_t, ua, ub, &channel_pdf);
+  w->ray.tmax = t_scatter;
+  const bool is_hit = TraceClosest<false>(s, w->ray, hit, nullptr);
+  if (rays) ++*rays;
+  const float t = is_hit ? hit->t : t_scatter;
+  const vec3 tr(expf(-w->sigma_t.x * t), expf(-w->sigma_t.y * t), expf(-w->sigma_t.z * t));
+  if (is_hit) {
+    const float pdf = vdot(channel_pdf, tr);
+    w->throughput = w->throughput * tr / pdf;
+    return kSssHit;
+  }
+  const float pdf = vdot(channel_pdf, w->sigma_t * tr);
+  w->throughput = w->throughput * (w->sigma_s * tr) / pdf;
+  const float p = Saturatef(SpectrumNorm(w->throughput));
+  const float q = Draw(rng);
+  if (q >= p) return kSssAbsorbed;
+  w->throughput = w->throughput / p;
+  w->ray.o = w->ray.o + t * w->ray.d;
+  w->bounce++;
+  if (w->bounce > 8192u) return kSssAbsorbed;   // for (bounce = 0; bounce <= 8192; ++bounce)
+  return kSssContinue;
+}
+
+// After a surface hit (:385-404) + the success branch of SampleBsdf (cycles-principled-shader.cc:187-216).
+PBR_HD void SssFinish(const SceneView& s, const Surface& entry_si, const Frame& entry, const SssWalkState& w,
+                      const HitT& hit, Pcg32* rng, VertexResult* out) {
+  const Surface ex = MakeSurface(s, w.ray, hit);
+  if (ex.instance_id != entry_si.instance_id || ex.face != kBack) {
+    FinishPrincipled(entry, vec3(0.f), vec3(0.f), 0.f, out);   // omega_in = f = pdf = 0 -> throughput 0
+    return;
+  }
+  Frame xf;
+  xf.ez = ex.Ns;                                   // exit frame, normal not flipped
+  BranchlessONB(xf.ez, &xf.ex, &xf.ey);
+  const vec3 new_wo = xf.ToLocal(w.ray.d);
+  PrincipledBsdf nb;
+  InitBsdf(&nb);
+  nb.enable_diffuse = true;
+  nb.diffuse_weight = w.throughput;
+  PrincipledEval ev = {&nb, new_wo};
+  out->P = ex.P;
+  DirectIllumination(s, ex.P, xf, ex.Ns, rng, ev, true, &out->shadow[1]);
+  const SampleWeight sw = FetchClosureSampleWeight(new_wo, nb);
+  const float select = Draw(rng);
+  vec3 wi(0.f), f(0.f);
+  float pdf = 0.f;
+  SampleBsdfLobes(nb, sw, select, new_wo, rng, &wi, &f, &pdf);
+  FinishPrincipled(entry, wi, f, pdf, out);
+}
+
+// Whole subsurface branch for one path, run to completion by one thread (the wavefront's sss kernel refills idle
+// lanes between bounces instead; this form serves the host emulation and small test hooks).
+PBR_HD void SubsurfaceVertex(const SceneView& s, const Surface& si, Pcg32* rng, VertexResult* out, uint64_t* rays) {
+  const Frame fr = PrincipledFrame(si);
+  const PrincipledBsdf bsdf = SurfaceBsdf(s, si);
+  SssWalkState w;
+  if (!SssBegin(si, fr, bsdf, rng, &w)) {
+    FinishPrincipled(fr, vec3(0.f), vec3(0.f), 0.f, out);
+    return;
+  }
+  HitT hit;
+  for (;;) {
+    const SssStep st = SssBounce(s, rng, &w, &hit, rays);
+    if (st == kSssHit) { SssFinish(s, si, fr, w, hit, rng, out); return; }
+    if (st == kSssAbsorbed) { FinishPrincipled(fr, vec3(0.f), vec3(0.f), 0.f, out); return; }
+  }
+}
+
+// ---------------------------------------------------------------- hair vertex (hair-shader.cc:153-229)
+struct HairEval {
+  const hair::HairBsdf* bsdf;
+  vec3 wo;
+  PBR_HD void operator()(const vec3& wi, vec3* f, float* pdf) const {
+    const vec3 fc = hair::EnergyConservingHairBsdfCosPdf(wi, wo, *bsdf, pdf);
+    *f = fc / fabsf(wi.x);
+  }
+};
+
+PBR_HD void HairVertex(const SceneView& s, const Surface& si, const vec3& wo_world, Pcg32* rng, VertexResult* out) {
+  if (si.face == kAmbiguous) {
+    AbsorbVertex(wo_world, si.P, out);
+    return;
+  }
+  Frame fr;
+  fr.ex = si.Ns;
+  fr.ey = vnormalized(vcross(vcross(wo_world, fr.ex), fr.ex));
+  fr.ez = vcross(fr.ex, fr.ey);
+  const vec3 wo = fr.ToLocal(wo_world);
+  const hair::HairBsdf bsdf = hair::ParamToBsdf(s.materials[si.material_id].p, si.v);
+  out->P = si.P;
+  out->shadow[1].active = false;
+  HairEval ev = {&bsdf, wo};
+  DirectIllumination(s, si.P, fr, fr.ex, rng, ev, false, &out->shadow[0]);
+  float us[4];
+  us[0] = Draw(rng); us[1] = Draw(rng); us[2] = Draw(rng); us[3] = Draw(rng);
+  vec3 wi(0.f);
+  float pdf = 0.f;
+  const vec3 fc = hair::EnergyConservingHairSample(wo, bsdf, us, &wi, &pdf);
+  out->wi = fr.ToWorld(wi);
+  out->throughput = fc / pdf;
+  out->pdf = pdf;
+  if (!IsFinite3(out->throughput) || !finitef_(out->pdf)) {
+    out->throughput = vec3(0.f);
+    out->pdf = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------- emission + roulette (render.cc:39-69)
+// Returns false when the path ends at this vertex.  L and throughput are updated in place.
+PBR_HD bool EmissionAndRoulette(const SceneView& s, const RayT& ray, const HitT& hit, const Surface& si,
+                                uint32_t depth, float bsdf_pdf_prev, Pcg32* rng, vec3* L, vec3* throughput) {
+  if (si.face == kFront && si.light_entry != kInvalid) {
+    const float4 e = s.emissive[si.light_entry];
+    const float area_to_solid_angle = fabsf((hit.t * hit.t) / vdot(si.Ns, ray.d));
+    const float weight = (depth == 0) ? 1.0f : PowerHeuristicWeight(bsdf_pdf_prev, e.w * area_to_solid_angle);
+    *L = *L + weight * vec3(e.x, e.y, e.z) * (*throughput);
+  }
+  const float p = SpectrumNorm(*throughput);
+  if (p < Draw(rng)) return false;
+  *throughput = (*throughput) * vec3(1.0f / p);
+  return true;
+}
+
+// material dispatch of Shader() (shader.cc:8-34): 0 = absorbed here, 1 = principled, 2 = hair
+PBR_HD int MaterialKind(const SceneView& s, const Surface& si) {
+  if (si.material_id == kInvalid || si.material_id >= s.num_materials) return 0;
+  return s.materials[si.material_id].type == 0 ? 1 : 2;
+}
+
+}  // namespace pbr

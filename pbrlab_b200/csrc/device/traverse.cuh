@@ -1,0 +1,359 @@
+// Closest-hit / any-hit traversal of one ray through the compressed 8-wide BVH (Ylitie, Karras, Laine 2017 layout,
+// 80-byte nodes, see ../bvh_builder.h), with the primitive tests restating what the reference's ray engine does:
+//   * triangles: Moeller-Trumbore on precomputed (v0, e1 = v0-v1, e2 = v2-v0), Ng = e2 x e1, inclusive edges,
+//     no back-face culling, tnear < t <= tfar  (Embree kernels/geometry/triangle_intersector_moeller.h:69-110,
+//     kernels/geometry/triangle.h:40-41);
+//   * flat cubic Bezier curves: 4 ray-facing quads per segment in ray space, back-face culled quad test,
+//     tnear <= t <= tfar, self-intersection rejection t <= 2 r depth_scale, u = (i+U)/4, v in [-1,1],
+//     Ng = dB/du  (kernels/geometry/curve_intersector_ribbon.h:72-177, quad_intersector.h:15-74,
+//     curve_intersector_precalculations.h:20-26, kernels/subdiv/bezier_curve.h:12-51).
+// The reference reaches these through Scene::TraceFirstHit1 / AnyHit1 (src/scene.cc:261-268,
+// src/raytracer/raytracer_impl.cc:268-287).
+#pragma once
+#include "common.cuh"
+#include "scene_view.cuh"
+
+namespace pbr {
+
+struct RayT {
+  vec3 o, d;
+  float tmin, tmax;
+};
+struct HitT {
+  float t, u, v;
+  uint32_t prim;   // leaf-order index; bit 31 set = curve segment; kInvalid = miss
+};
+constexpr uint32_t kCurveFlag = 0x80000000u;
+constexpr int kStackSize = 32;
+
+struct TraverseStats { uint32_t nodes, prims; };
+
+// Embree's Vec3 dot/cross association on the SSE2 path (common/math/vec3.h:205-209, madd = a*b+c unfused)
+PBR_HD float edot(const vec3& a, const vec3& b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+PBR_HD vec3 ecross(const vec3& a, const vec3& b) {
+  return vec3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+PBR_HD bool IntersectTriangle(const vec3& O, const vec3& D, float tnear, float tfar, const vec3& v0, const vec3& e1,
+                              const vec3& e2, float* t, float* u, float* v) {
+  const vec3 Ng = ecross(e2, e1);
+  const vec3 C = v0 - O;
+  const vec3 R = ecross(C, D);
+  const float den = edot(Ng, D);
+  const float absDen = fabsf(den);
+  const uint32_t sgn = f2u(den) & 0x80000000u;
+  const float U = u2f(f2u(edot(R, e2)) ^ sgn);
+  const float V = u2f(f2u(edot(R, e1)) ^ sgn);
+  if (!((den != 0.0f) & (U >= 0.0f) & (V >= 0.0f) & (U + V <= absDen))) return false;
+  const float T = u2f(f2u(edot(Ng, C)) ^ sgn);
+  if (!((absDen * tnear < T) & (T <= absDen * tfar))) return false;
+  const float rcp = 1.0f / absDen;
+  *t = T * rcp;
+  *u = U * rcp;
+  *v = V * rcp;
+  return true;
+}
+
+// per-ray precalculation for curves (curve_intersector_precalculations.h:20-26, linearspace3.h:117-124)
+struct CurveRaySpace {
+  vec3 dx, dy, dz;   // rows of the transposed frame: p_ray = (dot(dx,p), dot(dy,p), dot(dz,p))
+  float depth_scale;
+};
+PBR_HD vec3 enormalize(const vec3& v) { return v * (1.0f / sqrtf(edot(v, v))); }
+PBR_HD CurveRaySpace MakeCurveRaySpace(const vec3& D) {
+  CurveRaySpace s;
+  s.depth_scale = 1.0f / sqrtf(edot(D, D));
+  const vec3 N = s.depth_scale * D;
+  const vec3 dx0(0.f, N.z, -N.y);
+  const vec3 dx1(-N.z, 0.f, N.x);
+  s.dx = enormalize(edot(dx0, dx0) > edot(dx1, dx1) ? dx0 : dx1);
+  s.dy = enormalize(ecross(N, s.dx));
+  s.dz = N * s.depth_scale;
+  return s;
+}
+// xfmVector(ray_space, p): p.x*col0 + (p.y*col1 + p.z*col2)
+PBR_HD vec3 ToRaySpace(const CurveRaySpace& s, const vec3& p) {
+  return vec3(p.x * s.dx.x + (p.y * s.dx.y + p.z * s.dx.z), p.x * s.dy.x + (p.y * s.dy.y + p.z * s.dy.z),
+              p.x * s.dz.x + (p.y * s.dz.y + p.z * s.dz.z));
+}
+
+struct vec4 { float x, y, z, w; };
+PBR_HD void BezierBasis(float u, float* b) {             // bezier_curve.h:16-26
+  const float t1 = u, t0 = 1.0f - t1;
+  b[0] = t0 * t0 * t0;
+  b[1] = 3.0f * t1 * (t0 * t0);
+  b[2] = 3.0f * (t1 * t1) * t0;
+  b[3] = t1 * t1 * t1;
+}
+PBR_HD void BezierDerivative(float u, float* b) {        // bezier_curve.h:28-38
+  const float t1 = u, t0 = 1.0f - t1;
+  b[0] = 3.0f * (-(t0 * t0));
+  b[1] = 3.0f * (-2.0f * (t0 * t1) + t0 * t0);
+  b[2] = 3.0f * (2.0f * (t0 * t1) - t1 * t1);
+  b[3] = 3.0f * (t1 * t1);
+}
+PBR_HD float bz(const float* b, float a0, float a1, float a2, float a3) {   // madd(b0,v0,madd(b1,v1,madd(b2,v2,b3*v3)))
+  return b[0] * a0 + (b[1] * a1 + (b[2] * a2 + b[3] * a3));
+}
+
+// tangent dB/du at u from the world-space control points (RibbonHit::Ng, curve_intersector_ribbon.h:35)
+PBR_HD vec3 CurveTangent(const float4& c0, const float4& c1, const float4& c2, const float4& c3, float u) {
+  float b[4];
+  BezierDerivative(u, b);
+  return vec3(bz(b, c0.x, c1.x, c2.x, c3.x), bz(b, c0.y, c1.y, c2.y, c3.y), bz(b, c0.z, c1.z, c2.z, c3.z));
+}
+
+// One cubic segment against the ray.  any_hit: return on the first accepted sub-segment.
+PBR_HD bool IntersectCurve(const vec3& O, const CurveRaySpace& rs, float tnear, float tfar, const float4& c0,
+                           const float4& c1, const float4& c2, const float4& c3, float* t_out, float* u_out,
+                           float* v_out) {
+  // control points in ray space (xfm_pr): position relative to the origin, radius carried in w
+  const vec3 q0 = ToRaySpace(rs, vec3(c0.x, c0.y, c0.z) - O);
+  const vec3 q1 = ToRaySpace(rs, vec3(c1.x, c1.y, c1.z) - O);
+  const vec3 q2 = ToRaySpace(rs, vec3(c2.x, c2.y, c2.z) - O);
+  const vec3 q3 = ToRaySpace(rs, vec3(c3.x, c3.y, c3.z) - O);
+  float m = 0.f;
+  m = fmaxf(m, fmaxf(fmaxf(fabsf(q0.x), fabsf(q0.y)), fabsf(q0.z)));
+  m = fmaxf(m, fmaxf(fmaxf(fabsf(q1.x), fabsf(q1.y)), fabsf(q1.z)));
+  m = fmaxf(m, fmaxf(fmaxf(fabsf(q2.x), fabsf(q2.y)), fabsf(q2.z)));
+  m = fmaxf(m, fmaxf(fmaxf(fabsf(q3.x), fabsf(q3.y)), fabsf(q3.z)));
+  const float eps = 4.0f * kFltEps * m;
+
+  bool found = false;
+  float best_t = 0.f, best_u = 0.f, best_v = 0.f;
+  for (int i = 0; i < 4; ++i) {
+    float b0[4], b1[4], d0[4], d1[4];
+    BezierBasis(float(i) / 4.0f, b0);
+    BezierBasis(float(i + 1) / 4.0f, b1);
+    const vec4 p0 = {bz(b0, q0.x, q1.x, q2.x, q3.x), bz(b0, q0.y, q1.y, q2.y, q3.y), bz(b0, q0.z, q1.z, q2.z, q3.z),
+                     bz(b0, c0.w, c1.w, c2.w, c3.w)};
+    const vec4 p1 = {bz(b1, q0.x, q1.x, q2.x, q3.x), bz(b1, q0.y, q1.y, q2.y, q3.y), bz(b1, q0.z, q1.z, q2.z, q3.z),
+                     bz(b1, c0.w, c1.w, c2.w, c3.w)};
+    {  // cylinder_culling_test(0, p0.xy, p1.xy, max(r0, r1))
+      const float ax = p1.x - p0.x, ay = p1.y - p0.y;
+      const float bx = p0.x - 0.f, by = p0.y - 0.f;
+      const float num = ax * by - ay * bx;
+      const float den2 = ax * ax + ay * ay;
+      const float r = fmaxf(p0.w, p1.w);
+      if (!(num * num <= r * r * den2)) continue;
+    }
+    BezierDerivative(float(i) / 4.0f, d0);
+    BezierDerivative(float(i + 1) / 4.0f, d1);
+    vec3 dp0(bz(d0, q0.x, q1.x, q2.x, q3.x), bz(d0, q0.y, q1.y, q2.y, q3.y), bz(d0, q0.z, q1.z, q2.z, q3.z));
+    vec3 dp1(bz(d1, q0.x, q1.x, q2.x, q3.x), bz(d1, q0.y, q1.y, q2.y, q3.y), bz(d1, q0.z, q1.z, q2.z, q3.z));
+    const vec3 chord(p1.x - p0.x, p1.y - p0.y, p1.z - p0.z);
+    if (fmaxf(fmaxf(fabsf(dp0.x), fabsf(dp0.y)), fabsf(dp0.z)) < eps) dp0 = chord;
+    if (fmaxf(fmaxf(fabsf(dp1.x), fabsf(dp1.y)), fabsf(dp1.z)) < eps) dp1 = chord;
+    const vec3 nn0 = enormalize(vec3(dp0.y, -dp0.x, 0.0f));
+    const vec3 nn1 = enormalize(vec3(dp1.y, -dp1.x, 0.0f));
+    const vec3 P0(p0.x, p0.y, p0.z), P1(p1.x, p1.y, p1.z);
+    const vec3 lp0 = p0.w * nn0 + P0, lp1 = p1.w * nn1 + P1;       // madd(w, nn, p)
+    const vec3 up0 = P0 - p0.w * nn0, up1 = P1 - p1.w * nn1;       // nmadd(w, nn, p)
+
+    // intersect_quad_backface_culling(O = 0, D = (0,0,1), quad = lp0, lp1, up1, up0)
+    const vec3 va = lp0, vb = lp1, vc = up1, vd = up0;
+    const vec3 edb = vb - vd;
+    const float WW = ecross(vd, edb).z;
+    const bool first = WW <= 0.0f;
+    const vec3 v0 = first ? va : vc;
+    const vec3 v1 = first ? vb : vd;
+    const vec3 v2 = first ? vd : vb;
+    const vec3 e0 = v2 - v0;
+    const vec3 e1 = v0 - v1;
+    const float U = ecross(v0, e0).z;
+    const float V = ecross(v1, e1).z;
+    if (!(fmaxf(U, V) <= 0.0f)) continue;
+    const vec3 Ng = ecross(e1, e0);
+    const float den = Ng.z;
+    const float rcpDen = 1.0f / den;
+    const float t = rcpDen * edot(v0, Ng);
+    if (!((tnear <= t) & (t <= tfar))) continue;
+    if (!(den != 0.0f)) continue;
+    float u = U * rcpDen, v = V * rcpDen;
+    u = first ? u : 1.0f - u;
+    v = first ? v : 1.0f - v;
+    // self-intersection avoidance (EMBREE_CURVE_SELF_INTERSECTION_AVOIDANCE_FACTOR 2.0)
+    const float r = u * (p1.w - p0.w) + p0.w;                        // lerp = madd(t, b-a, a)
+    if (!(t > 2.0f * r * rs.depth_scale)) continue;
+    if (!found || t < best_t) {   // select_min over the 4 lanes: lowest t, lowest lane on ties
+      found = true;
+      best_t = t;
+      best_u = (float(i) + u + 0.0f) * (1.0f / 4.0f);
+      best_v = 2.0f * v + -1.0f;
+    }
+  }
+  if (found) { *t_out = best_t; *u_out = best_u; *v_out = best_v; }
+  return found;
+}
+
+PBR_HD uint32_t extract_byte(uint32_t x, uint32_t i) { return (x >> (i * 8)) & 0xffu; }
+PBR_HD uint32_t sign_extend_s8x4(uint32_t x) {
+  // each byte: 0x80 -> 0xff, else 0x00 (only ever called with bytes in {0x00, 0x80})
+  return ((x >> 7) & 0x01010101u) * 0xffu;
+}
+PBR_HD uint32_t msb(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return 31u - uint32_t(__clz(int(x)));
+#else
+  return 31u - uint32_t(__builtin_clz(x));
+#endif
+}
+PBR_HD uint32_t popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return uint32_t(__popc(x));
+#else
+  return uint32_t(__builtin_popcount(x));
+#endif
+}
+
+// Slab-test the 8 quantised child boxes of one node; returns the hit mask: bits 24..31 = internal children in
+// octant-adjusted traversal order, bits 0..23 = primitives of hit leaf children (relative to the node's prim base).
+PBR_HD uint32_t NodeIntersect(const vec3& o_over_d, const vec3& inv_d, uint32_t oct_inv4, bool neg_x, bool neg_y,
+                              bool neg_z, float tmin, float tmax, const float4& n0, const float4& n1,
+                              const float4& n2, const float4& n3, const float4& n4) {
+  const uint32_t ew = f2u(n0.w);
+  const float sx = u2f(extract_byte(ew, 0) << 23) * inv_d.x;
+  const float sy = u2f(extract_byte(ew, 1) << 23) * inv_d.y;
+  const float sz = u2f(extract_byte(ew, 2) << 23) * inv_d.z;
+  const float ox = n0.x * inv_d.x - o_over_d.x;   // (p - o) / d
+  const float oy = n0.y * inv_d.y - o_over_d.y;
+  const float oz = n0.z * inv_d.z - o_over_d.z;
+  uint32_t hit_mask = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t meta4 = f2u(i == 0 ? n1.z : n1.w);
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const uint32_t q_lo_x = f2u(i == 0 ? n2.x : n2.y), q_lo_y = f2u(i == 0 ? n2.z : n2.w);
+    const uint32_t q_lo_z = f2u(i == 0 ? n3.x : n3.y), q_hi_x = f2u(i == 0 ? n3.z : n3.w);
+    const uint32_t q_hi_y = f2u(i == 0 ? n4.x : n4.y), q_hi_z = f2u(i == 0 ? n4.z : n4.w);
+    const uint32_t x_min = neg_x ? q_hi_x : q_lo_x, x_max = neg_x ? q_lo_x : q_hi_x;
+    const uint32_t y_min = neg_y ? q_hi_y : q_lo_y, y_max = neg_y ? q_lo_y : q_hi_y;
+    const uint32_t z_min = neg_z ? q_hi_z : q_lo_z, z_max = neg_z ? q_lo_z : q_hi_z;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 4; ++j) {
+      const float tlx = pbr_fma(float(extract_byte(x_min, j)), sx, ox);
+      const float tly = pbr_fma(float(extract_byte(y_min, j)), sy, oy);
+      const float tlz = pbr_fma(float(extract_byte(z_min, j)), sz, oz);
+      const float thx = pbr_fma(float(extract_byte(x_max, j)), sx, ox);
+      const float thy = pbr_fma(float(extract_byte(y_max, j)), sy, oy);
+      const float thz = pbr_fma(float(extract_byte(z_max, j)), sz, oz);
+      const float tn = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
+      const float tf = fminf(fminf(thx, thy), fminf(thz, tmax));
+      // a few ulps of slack keep the quantised-box test conservative under rounding
+      if (tn <= tf * 1.0000004f + 1e-30f) {
+        hit_mask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
+      }
+    }
+  }
+  return hit_mask;
+}
+
+// Generic traversal of one BVH.  CURVES selects the leaf test, ANY the early-out.
+template <bool CURVES, bool ANY, bool STATS>
+PBR_HD bool TraverseBvh(const float4* __restrict__ nodes, const float4* __restrict__ prims, const RayT& ray,
+                        float* tfar_io, HitT* hit, TraverseStats* st) {
+  const vec3 O = ray.o, D = ray.d;
+  // slab-test direction: zero components are nudged so 1/d stays finite (sign kept)
+  const float tiny = 1e-30f;
+  const vec3 ds(fabsf(D.x) < tiny ? copysignf(tiny, D.x) : D.x, fabsf(D.y) < tiny ? copysignf(tiny, D.y) : D.y,
+                fabsf(D.z) < tiny ? copysignf(tiny, D.z) : D.z);
+  const vec3 inv_d(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+  const vec3 o_over_d(O.x * inv_d.x, O.y * inv_d.y, O.z * inv_d.z);
+  const bool neg_x = ds.x < 0.f, neg_y = ds.y < 0.f, neg_z = ds.z < 0.f;
+  const uint32_t oct_inv4 = (neg_x ? 0u : 0x04040404u) | (neg_y ? 0u : 0x02020202u) | (neg_z ? 0u : 0x01010101u);
+  CurveRaySpace rs;
+  if (CURVES) rs = MakeCurveRaySpace(D);
+
+  float tfar = *tfar_io;
+  bool found = false;
+  uint2 stack[kStackSize];
+  int sp = 0;
+  uint2 group = make_uint2(0u, 0x80000000u);   // root: node base 0, one "child" at bit 31 -> slot 7^oct... see below
+  // The root is addressed as if it were child slot (7 ^ oct_inv) of a virtual parent whose only child it is:
+  // relative index = popc(imask below slot) = 0 because the low 8 bits (imask) are 0.
+  for (;;) {
+    uint2 pgroup;
+    if (group.y & 0xff000000u) {
+      const uint32_t hits_imask = group.y;
+      const uint32_t child_bit = msb(hits_imask);
+      group.y &= ~(1u << child_bit);
+      if (group.y & 0xff000000u) {
+        if (sp < kStackSize) stack[sp++] = group;
+      }
+      const uint32_t slot = (child_bit - 24u) ^ (oct_inv4 & 0xffu);
+      const uint32_t rel = popc(hits_imask & ~(0xffffffffu << slot));
+      const uint32_t node = group.x + rel;
+      const float4 n0 = nodes[node * 5 + 0], n1 = nodes[node * 5 + 1], n2 = nodes[node * 5 + 2];
+      const float4 n3 = nodes[node * 5 + 3], n4 = nodes[node * 5 + 4];
+      if (STATS) st->nodes++;
+      const uint32_t hitmask = NodeIntersect(o_over_d, inv_d, oct_inv4, neg_x, neg_y, neg_z, ray.tmin, tfar, n0, n1,
+                                             n2, n3, n4);
+      group.x = f2u(n1.x);
+      group.y = (hitmask & 0xff000000u) | extract_byte(f2u(n0.w), 3);
+      pgroup.x = f2u(n1.y);
+      pgroup.y = hitmask & 0x00ffffffu;
+    } else {
+      pgroup = group;
+      group = make_uint2(0u, 0u);
+    }
+    while (pgroup.y != 0u) {
+      const uint32_t bit = msb(pgroup.y);
+      pgroup.y &= ~(1u << bit);
+      const uint32_t idx = pgroup.x + bit;
+      if (STATS) st->prims++;
+      float t, u, v;
+      bool h;
+      if (CURVES) {
+        const float4 c0 = prims[idx * 4 + 0], c1 = prims[idx * 4 + 1], c2 = prims[idx * 4 + 2],
+                     c3 = prims[idx * 4 + 3];
+        h = IntersectCurve(O, rs, ray.tmin, tfar, c0, c1, c2, c3, &t, &u, &v);
+      } else {
+        const float4 a = prims[idx * 3 + 0], b = prims[idx * 3 + 1], c = prims[idx * 3 + 2];
+        h = IntersectTriangle(O, D, ray.tmin, tfar, from4(a), from4(b), from4(c), &t, &u, &v);
+      }
+      if (h) {
+        if (ANY) return true;
+        found = true;
+        tfar = t;
+        hit->t = t; hit->u = u; hit->v = v;
+        hit->prim = CURVES ? (idx | kCurveFlag) : idx;
+      }
+    }
+    if ((group.y & 0xff000000u) == 0u) {
+      if (sp == 0) break;
+      group = stack[--sp];
+    }
+  }
+  *tfar_io = tfar;
+  return found;
+}
+
+// Scene::TraceFirstHit1: triangles first, then curves against the shortened ray.
+template <bool STATS>
+PBR_HD bool TraceClosest(const SceneView& s, const RayT& ray, HitT* hit, TraverseStats* st) {
+  float tfar = ray.tmax;
+  hit->prim = kInvalid;
+  bool found = false;
+  if (s.num_tris) found |= TraverseBvh<false, false, STATS>(s.tri_nodes, s.tri_data, ray, &tfar, hit, st);
+  if (s.num_curves) found |= TraverseBvh<true, false, STATS>(s.curve_nodes, s.curve_data, ray, &tfar, hit, st);
+  return found;
+}
+
+// Scene::AnyHit1
+template <bool STATS>
+PBR_HD bool TraceAny(const SceneView& s, const RayT& ray, TraverseStats* st) {
+  float tfar = ray.tmax;
+  HitT hit;
+  if (s.num_tris && TraverseBvh<false, true, STATS>(s.tri_nodes, s.tri_data, ray, &tfar, &hit, st)) return true;
+  if (s.num_curves && TraverseBvh<true, true, STATS>(s.curve_nodes, s.curve_data, ray, &tfar, &hit, st)) return true;
+  return false;
+}
+
+}  // namespace pbr

@@ -1,0 +1,804 @@
+// Implementation of the C ABI in include/pbrgpu.h on CUDA (sm_100a): device memory management, scene upload,
+// the host loop that drives the wavefront kernels (wavefront.cuh), and the parity test hooks.
+//
+// There is no CPU path in this file: every entry point that computes anything launches kernels, and
+// pbrgpu_create() fails when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/pbrgpu.h"
+#include "kat.cuh"
+#include "scene_host.h"
+#include "wavefront.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+#define CUDA_TRY(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t err__ = (expr);                                                                  \
+    if (err__ != cudaSuccess) {                                                                  \
+      (ctx)->error = std::string(#expr) + ": " + cudaGetErrorString(err__);                      \
+      return PBRGPU_ERR_CUDA;                                                                    \
+    }                                                                                            \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* ptr = nullptr;
+  size_t count = 0;
+  cudaError_t Alloc(size_t n) {
+    if (n <= count && ptr) return cudaSuccess;
+    Free();
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), n * sizeof(T));
+    if (e == cudaSuccess) count = n;
+    return e;
+  }
+  cudaError_t Upload(const void* src, size_t n, cudaStream_t st) {
+    cudaError_t e = Alloc(n);
+    if (e != cudaSuccess || n == 0) return e;
+    return cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+  }
+  void Free() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+};
+
+// everything one GPU holds
+struct Device {
+  int id = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  // scene
+  DevBuf<float4> tri_nodes, tri_data, curve_nodes, curve_data, verts, normals, emissive, lprim_info;
+  DevBuf<float2> texcoords;
+  DevBuf<uint32_t> curve_prim, lprim_tri;
+  DevBuf<uint4> tri_ids, tri_nidx, tri_vidx, tri_tidx, curve_ids;
+  DevBuf<pbr::DeviceMaterial> materials;
+  DevBuf<float> light_cdf, lprim_cdf;
+  DevBuf<pbr::LightRec> lights;
+  pbr::SceneView view;
+  // wave
+  DevBuf<float4> ray_o, ray_d, hit, thr, rad, sh_o, sh_d, sh_c;
+  DevBuf<ulonglong2> rng;
+  DevBuf<uint32_t> q0, q1, q_surface, q_hair, q_sss, counters;
+  DevBuf<unsigned long long> stats;
+  pbr::WaveState wave;
+  uint32_t wave_capacity = 0;
+  // frame accumulators (device side of RenderLayer)
+  DevBuf<float4> rgba;
+  DevBuf<uint32_t> count;
+  // pinned host mirror of the counters
+  uint32_t* h_counters = nullptr;
+  unsigned long long* h_stats = nullptr;
+
+  void Release() {
+    tri_nodes.Free(); tri_data.Free(); curve_nodes.Free(); curve_data.Free(); verts.Free(); normals.Free();
+    emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); lprim_tri.Free(); tri_ids.Free();
+    tri_nidx.Free(); tri_vidx.Free(); tri_tidx.Free(); curve_ids.Free(); materials.Free(); light_cdf.Free();
+    lprim_cdf.Free(); lights.Free();
+    ray_o.Free(); ray_d.Free(); hit.Free(); thr.Free(); rad.Free(); sh_o.Free(); sh_d.Free(); sh_c.Free();
+    rng.Free(); q0.Free(); q1.Free(); q_surface.Free(); q_hair.Free(); q_sss.Free(); counters.Free(); stats.Free();
+    rgba.Free(); count.Free();
+    if (h_counters) cudaFreeHost(h_counters);
+    if (h_stats) cudaFreeHost(h_stats);
+    h_counters = nullptr; h_stats = nullptr;
+    for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
+}  // namespace
+
+struct pbrgpu_ctx {
+  std::vector<Device> devices;
+  pbrhost::HostScene host;
+  std::string error;
+  pbrgpu_stats stats;
+  uint32_t wave_spp = 0;
+  bool committed = false;
+};
+
+namespace {
+
+using pbr::SceneView;
+using pbr::WaveState;
+
+constexpr int kBlock = 128;
+int PersistentGrid(const Device& d, int blocks_per_sm) { return d.sm_count * blocks_per_sm; }
+
+int UploadScene(pbrgpu_ctx* ctx, Device& d) {
+  const pbrhost::HostScene& h = ctx->host;
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  cudaStream_t st = d.stream;
+  CUDA_TRY(ctx, d.tri_nodes.Upload(h.tri_bvh.nodes.data(), h.tri_bvh.nodes.size() / 4, st));
+  CUDA_TRY(ctx, d.tri_data.Upload(h.tri_data.data(), h.tri_data.size(), st));
+  CUDA_TRY(ctx, d.curve_nodes.Upload(h.curve_bvh.nodes.data(), h.curve_bvh.nodes.size() / 4, st));
+  CUDA_TRY(ctx, d.curve_data.Upload(h.curve_data.data(), h.curve_data.size(), st));
+  CUDA_TRY(ctx, d.curve_prim.Upload(h.curve_prim.data(), h.curve_prim.size(), st));
+  CUDA_TRY(ctx, d.tri_ids.Upload(h.tri_ids.data(), h.tri_ids.size(), st));
+  CUDA_TRY(ctx, d.tri_nidx.Upload(h.tri_nidx.data(), h.tri_nidx.size(), st));
+  CUDA_TRY(ctx, d.tri_vidx.Upload(h.tri_vidx.data(), h.tri_vidx.size(), st));
+  CUDA_TRY(ctx, d.tri_tidx.Upload(h.tri_tidx.data(), h.tri_tidx.size(), st));
+  CUDA_TRY(ctx, d.verts.Upload(h.verts.data(), h.verts.size(), st));
+  CUDA_TRY(ctx, d.normals.Upload(h.normals.data(), h.normals.size(), st));
+  CUDA_TRY(ctx, d.texcoords.Upload(h.texcoords.data(), h.texcoords.size(), st));
+  CUDA_TRY(ctx, d.curve_ids.Upload(h.curve_ids.data(), h.curve_ids.size(), st));
+  CUDA_TRY(ctx, d.materials.Upload(h.materials.data(), h.materials.size(), st));
+  CUDA_TRY(ctx, d.emissive.Upload(h.emissive.data(), h.emissive.size(), st));
+  CUDA_TRY(ctx, d.light_cdf.Upload(h.light_cdf.data(), h.light_cdf.size(), st));
+  CUDA_TRY(ctx, d.lights.Upload(h.lights.data(), h.lights.size(), st));
+  CUDA_TRY(ctx, d.lprim_cdf.Upload(h.lprim_cdf.data(), h.lprim_cdf.size(), st));
+  CUDA_TRY(ctx, d.lprim_info.Upload(h.lprim_info.data(), h.lprim_info.size(), st));
+  CUDA_TRY(ctx, d.lprim_tri.Upload(h.lprim_tri.data(), h.lprim_tri.size(), st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  SceneView& v = d.view;
+  memset(&v, 0, sizeof(v));
+  v.tri_nodes = d.tri_nodes.ptr; v.tri_data = d.tri_data.ptr;
+  v.curve_nodes = d.curve_nodes.ptr; v.curve_data = d.curve_data.ptr; v.curve_prim = d.curve_prim.ptr;
+  v.num_tris = h.num_tris(); v.num_curves = h.num_curves();
+  v.tri_ids = d.tri_ids.ptr; v.tri_nidx = d.tri_nidx.ptr; v.tri_vidx = d.tri_vidx.ptr; v.tri_tidx = d.tri_tidx.ptr;
+  v.verts = d.verts.ptr; v.normals = d.normals.ptr; v.texcoords = d.texcoords.ptr; v.curve_ids = d.curve_ids.ptr;
+  v.materials = d.materials.ptr; v.num_materials = uint32_t(h.materials.size());
+  v.emissive = d.emissive.ptr; v.light_cdf = d.light_cdf.ptr; v.lights = d.lights.ptr;
+  v.num_lights = uint32_t(h.lights.size());
+  v.lprim_cdf = d.lprim_cdf.ptr; v.lprim_info = d.lprim_info.ptr; v.lprim_tri = d.lprim_tri.ptr;
+  return PBRGPU_OK;
+}
+
+int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  if (capacity > d.wave_capacity) {
+    CUDA_TRY(ctx, d.ray_o.Alloc(capacity)); CUDA_TRY(ctx, d.ray_d.Alloc(capacity));
+    CUDA_TRY(ctx, d.hit.Alloc(capacity)); CUDA_TRY(ctx, d.thr.Alloc(capacity));
+    CUDA_TRY(ctx, d.rad.Alloc(capacity)); CUDA_TRY(ctx, d.rng.Alloc(capacity));
+    CUDA_TRY(ctx, d.q0.Alloc(capacity)); CUDA_TRY(ctx, d.q1.Alloc(capacity));
+    CUDA_TRY(ctx, d.q_surface.Alloc(capacity)); CUDA_TRY(ctx, d.q_hair.Alloc(capacity));
+    CUDA_TRY(ctx, d.q_sss.Alloc(capacity));
+    CUDA_TRY(ctx, d.sh_o.Alloc(size_t(2) * capacity)); CUDA_TRY(ctx, d.sh_d.Alloc(size_t(2) * capacity));
+    CUDA_TRY(ctx, d.sh_c.Alloc(size_t(2) * capacity));
+    d.wave_capacity = capacity;
+  }
+  CUDA_TRY(ctx, d.counters.Alloc(pbr::kCounterCount));
+  CUDA_TRY(ctx, d.stats.Alloc(pbr::kStatCount));
+  if (!d.h_counters) CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&d.h_counters), sizeof(uint32_t) * pbr::kCounterCount));
+  if (!d.h_stats) CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&d.h_stats), sizeof(unsigned long long) * pbr::kStatCount));
+  WaveState& w = d.wave;
+  w.ray_o = d.ray_o.ptr; w.ray_d = d.ray_d.ptr; w.hit = d.hit.ptr; w.thr = d.thr.ptr; w.rad = d.rad.ptr;
+  w.rng = d.rng.ptr; w.q_active[0] = d.q0.ptr; w.q_active[1] = d.q1.ptr; w.q_surface = d.q_surface.ptr;
+  w.q_hair = d.q_hair.ptr; w.q_sss = d.q_sss.ptr; w.sh_o = d.sh_o.ptr; w.sh_d = d.sh_d.ptr; w.sh_c = d.sh_c.ptr;
+  w.counters = d.counters.ptr; w.stats = d.stats.ptr; w.capacity = d.wave_capacity;
+  return PBRGPU_OK;
+}
+
+struct LoopTimers {
+  double closest_ms = 0, any_ms = 0, shade_ms = 0, sss_ms = 0;
+  uint64_t launches = 0;
+};
+
+// Runs bounce iterations until no path is alive.  n_active paths are in q_active[0].  max_iterations == 1 is the
+// single-vertex mode of pbrgpu_shade.
+int RunWave(pbrgpu_ctx* ctx, Device& d, uint32_t n_active, uint32_t max_iterations, pbr::ShadeFlags flags,
+            LoopTimers* tm, const volatile int* cancel) {
+  cudaStream_t st = d.stream;
+  const SceneView& s = d.view;
+  const WaveState& w = d.wave;
+  uint32_t parity = 0;
+  const int grid_trace = PersistentGrid(d, 8), grid_shade = PersistentGrid(d, 4);
+  for (uint32_t it = 0; n_active > 0 && it < max_iterations; ++it) {
+    if (cancel && *cancel) break;
+    const uint32_t next = parity ^ 1u;
+    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters);
+    pbr::TraceClosestKernel<<<grid_trace, kBlock, 0, st>>>(s, w, w.q_active[parity], n_active);
+    pbr::ShadeSurfaceKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
+    if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
+    pbr::SssWalkKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next);
+    pbr::TraceAnyKernel<<<grid_trace, kBlock, 0, st>>>(s, w);
+    tm->launches += s.num_curves ? 6 : 5;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d.h_counters, w.counters, sizeof(uint32_t) * pbr::kCounterCount,
+                                  cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    n_active = d.h_counters[pbr::kNumActiveNext];
+    parity = next;
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBRGPU_OK;
+}
+
+int FetchStats(pbrgpu_ctx* ctx, Device& d) {
+  CUDA_TRY(ctx, cudaMemcpyAsync(d.h_stats, d.stats.ptr, sizeof(unsigned long long) * pbr::kStatCount,
+                                cudaMemcpyDeviceToHost, d.stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  return PBRGPU_OK;
+}
+
+uint32_t ChooseWaveSpp(const pbrgpu_ctx* ctx, uint64_t npix, uint32_t local_spp) {
+  if (ctx->wave_spp) return std::max(1u, std::min(ctx->wave_spp, local_spp));
+  const uint64_t target_paths = 4ull << 20;   // ~4 Mi paths in flight: ~1 GB of wave state
+  uint64_t s = std::max<uint64_t>(1, target_paths / std::max<uint64_t>(1, npix));
+  return uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(s, local_spp)));
+}
+
+// the body of Render() on one device; result left in d.rgba / d.count
+int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed,
+                   uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, size_t* finish_pass,
+                   LoopTimers* tm) {
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  const uint64_t npix64 = uint64_t(width) * height;
+  if (npix64 == 0 || npix64 > 0x7fffffffull) { ctx->error = "pbrgpu_render: bad image size"; return PBRGPU_ERR_INVALID; }
+  const uint32_t npix = uint32_t(npix64);
+  const uint32_t local_spp = (spp > sample_offset) ? (spp - sample_offset + sample_stride - 1) / sample_stride : 0;
+  CUDA_TRY(ctx, d.rgba.Alloc(npix));
+  CUDA_TRY(ctx, d.count.Alloc(npix));
+  CUDA_TRY(ctx, cudaMemsetAsync(d.rgba.ptr, 0, sizeof(float4) * npix, d.stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(d.count.ptr, 0, sizeof(uint32_t) * npix, d.stream));
+  if (local_spp == 0) { CUDA_TRY(ctx, cudaStreamSynchronize(d.stream)); return PBRGPU_OK; }
+  const uint32_t wave_spp = ChooseWaveSpp(ctx, npix, local_spp);
+  if (uint64_t(wave_spp) * npix > 0x7fffffffull) { ctx->error = "pbrgpu_render: wave too large"; return PBRGPU_ERR_INVALID; }
+  int rc = EnsureWave(ctx, d, wave_spp * npix);
+  if (rc != PBRGPU_OK) return rc;
+  CUDA_TRY(ctx, cudaMemsetAsync(d.stats.ptr, 0, sizeof(unsigned long long) * pbr::kStatCount, d.stream));
+
+  pbr::CameraParams cam;
+  float c8[8];
+  pbrhost::MakeCamera(ctx->host.bmin, ctx->host.bmax, width, height, c8);
+  cam.eye[0] = c8[0]; cam.eye[1] = c8[1]; cam.eye[2] = c8[2];
+  cam.x_corner = c8[3]; cam.y_corner = c8[4]; cam.z_corner = c8[5]; cam.dx = c8[6]; cam.dy = c8[7];
+  cam.width = width; cam.height = height;
+
+  pbr::ShadeFlags flags;
+  flags.skip_emission_and_roulette = 0;
+  for (uint32_t done = 0; done < local_spp;) {
+    if (cancel && *cancel) break;
+    const uint32_t batch = std::min(wave_spp, local_spp - done);
+    const uint32_t n_paths = batch * npix;
+    const uint32_t first_sample = sample_offset + done * sample_stride;
+    pbr::GenCameraRaysKernel<<<(n_paths + 255) / 256, 256, 0, d.stream>>>(d.wave, cam, npix, n_paths, seed,
+                                                                          first_sample, sample_stride);
+    tm->launches++;
+    rc = RunWave(ctx, d, n_paths, 0xffffffffu, flags, tm, cancel);
+    if (rc != PBRGPU_OK) return rc;
+    if (cancel && *cancel) break;   // a cancelled wave is dropped: only whole passes are accumulated
+    pbr::AccumulateKernel<<<(npix + 255) / 256, 256, 0, d.stream>>>(d.wave, d.rgba.ptr, d.count.ptr, npix, batch);
+    tm->launches++;
+    done += batch;
+    if (finish_pass) {
+      const size_t global_done = std::min<size_t>(spp, size_t(sample_offset) + size_t(done) * sample_stride);
+      if (global_done > *finish_pass) *finish_pass = global_done;
+    }
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FetchStats(ctx, d);
+}
+
+__global__ void AddBuffersKernel(float4* dst, const float4* src, uint32_t* cdst, const uint32_t* csrc, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = dst[i];
+  const float4 b = src[i];
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  dst[i] = a;
+  cdst[i] += csrc[i];
+}
+
+__global__ void KatKernel(int op, const float* params, const float* in, uint32_t in_stride, uint64_t n, float* out,
+                          uint32_t out_stride) {
+  const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  pbr::KatEval(op, params, in + i * in_stride, out + i * out_stride, out_stride);
+}
+
+__global__ void SurfaceFaceKernel(pbr::SceneView s, pbr::WaveState w, uint32_t n, float* face_t) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float4 h4 = w.hit[p];
+  pbr::HitT hit;
+  hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
+  face_t[2 * p] = -1.f;
+  face_t[2 * p + 1] = 0.f;
+  if (hit.prim == pbr::kInvalid) return;
+  const pbr::RayT ray = pbr::LoadRay(w, p);
+  const pbr::Surface si = pbr::MakeSurface(s, ray, hit);
+  face_t[2 * p] = float(si.face);
+  face_t[2 * p + 1] = hit.t;
+}
+
+__global__ void MegaRadianceKernel(pbr::SceneView s, const float4* rays, const uint64_t* seeds, uint32_t n, float* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pbr::RayT ray;
+  const float4 o = rays[2 * i], d = rays[2 * i + 1];
+  ray.o = pbr::vec3(o.x, o.y, o.z); ray.tmin = o.w;
+  ray.d = pbr::vec3(d.x, d.y, d.z); ray.tmax = d.w;
+  pbr::Pcg32 rng;
+  pbr::pcg32_srandom(&rng, seeds[2 * i], seeds[2 * i + 1]);
+  const pbr::vec3 L = pbr::PathRadiance(s, ray, &rng, nullptr);
+  out[3 * i] = L.x; out[3 * i + 1] = L.y; out[3 * i + 2] = L.z;
+}
+
+bool CheckCommitted(pbrgpu_ctx* ctx, const char* who) {
+  if (!ctx) return false;
+  if (!ctx->committed) {
+    ctx->error = std::string(who) + ": scene not committed";
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pbrgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("pbrgpu_create: no CUDA device (") + cudaGetErrorString(e) +
+                     "); this backend has no CPU fallback";
+    return nullptr;
+  }
+  std::vector<int> ids;
+  if (device_ids && n_devices > 0) ids.assign(device_ids, device_ids + n_devices);
+  else {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    ids.push_back(cur);
+  }
+  pbrgpu_ctx* ctx = new pbrgpu_ctx();
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  for (int id : ids) {
+    if (id < 0 || id >= ndev) {
+      g_create_error = "pbrgpu_create: device id out of range";
+      delete ctx;
+      return nullptr;
+    }
+    Device d;
+    d.id = id;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(id) != cudaSuccess || cudaGetDeviceProperties(&prop, id) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&d.ev[0]) != cudaSuccess || cudaEventCreate(&d.ev[1]) != cudaSuccess) {
+      g_create_error = std::string("pbrgpu_create: cannot initialise device: ") + cudaGetErrorString(cudaGetLastError());
+      delete ctx;
+      return nullptr;
+    }
+    d.sm_count = prop.multiProcessorCount;
+    ctx->devices.push_back(d);
+  }
+  // peer access for the frame-end sum on multi-device contexts
+  for (size_t a = 1; a < ctx->devices.size(); ++a) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, ctx->devices[0].id, ctx->devices[a].id);
+    if (can) {
+      cudaSetDevice(ctx->devices[0].id);
+      cudaDeviceEnablePeerAccess(ctx->devices[a].id, 0);
+      cudaGetLastError();
+    }
+  }
+  cudaSetDevice(ctx->devices[0].id);
+  return ctx;
+}
+
+void pbrgpu_destroy(pbrgpu_ctx* ctx) {
+  if (!ctx) return;
+  for (Device& d : ctx->devices) {
+    cudaSetDevice(d.id);
+    d.Release();
+  }
+  delete ctx;
+}
+
+const char* pbrgpu_last_error(const pbrgpu_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int pbrgpu_set_triangles(pbrgpu_ctx* ctx, const float* xyzw, uint32_t nverts, const uint32_t* vidx, const float* nxyzw,
+                         uint32_t nnormals, const uint32_t* nidx, const float* uv, uint32_t nuv, const uint32_t* tidx,
+                         const uint32_t* material_id, const uint32_t* instance_id, const uint32_t* geom_id,
+                         const uint32_t* prim_id, uint64_t ntris) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  ctx->committed = false;
+  if (!ctx->host.SetTriangles(xyzw, nverts, vidx, nxyzw, nnormals, nidx, uv, nuv, tidx, material_id, instance_id,
+                              geom_id, prim_id, ntris)) {
+    ctx->error = ctx->host.error;
+    return PBRGPU_ERR_INVALID;
+  }
+  return PBRGPU_OK;
+}
+
+int pbrgpu_set_curves(pbrgpu_ctx* ctx, const float* xyzr, uint32_t nverts, const uint32_t* first_cp,
+                      const uint32_t* material_id, const uint32_t* instance_id, const uint32_t* geom_id,
+                      const uint32_t* prim_id, uint64_t nsegs) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  ctx->committed = false;
+  if (!ctx->host.SetCurves(xyzr, nverts, first_cp, material_id, instance_id, geom_id, prim_id, nsegs)) {
+    ctx->error = ctx->host.error;
+    return PBRGPU_ERR_INVALID;
+  }
+  return PBRGPU_OK;
+}
+
+int pbrgpu_set_materials(pbrgpu_ctx* ctx, const pbrgpu_material* materials, uint32_t n) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  if (!ctx->host.SetMaterials(materials, n)) {
+    ctx->error = ctx->host.error;
+    return PBRGPU_ERR_INVALID;
+  }
+  if (ctx->committed) {   // live edit: refresh the table in place
+    for (const auto& id : ctx->host.tri_ids)
+      if (id.w != PBRGPU_INVALID_ID && id.w >= n) { ctx->error = "pbrgpu_set_materials: table shrank below ids in use"; return PBRGPU_ERR_INVALID; }
+    for (const auto& id : ctx->host.curve_ids)
+      if (id.w != PBRGPU_INVALID_ID && id.w >= n) { ctx->error = "pbrgpu_set_materials: table shrank below ids in use"; return PBRGPU_ERR_INVALID; }
+    for (Device& d : ctx->devices) {
+      CUDA_TRY(ctx, cudaSetDevice(d.id));
+      CUDA_TRY(ctx, d.materials.Upload(ctx->host.materials.data(), ctx->host.materials.size(), d.stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+      d.view.materials = d.materials.ptr;
+      d.view.num_materials = n;
+    }
+  }
+  return PBRGPU_OK;
+}
+
+int pbrgpu_set_lights(pbrgpu_ctx* ctx, const pbrgpu_light_tables* tables) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  ctx->committed = false;
+  if (!ctx->host.SetLights(tables)) {
+    ctx->error = ctx->host.error;
+    return PBRGPU_ERR_INVALID;
+  }
+  return PBRGPU_OK;
+}
+
+int pbrgpu_commit(pbrgpu_ctx* ctx, const float* bmin, const float* bmax) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  if (!ctx->host.Commit(bmin, bmax)) {
+    ctx->error = ctx->host.error;
+    return PBRGPU_ERR_BUILD;
+  }
+  for (Device& d : ctx->devices) {
+    const int rc = UploadScene(ctx, d);
+    if (rc != PBRGPU_OK) return rc;
+  }
+  ctx->committed = true;
+  return PBRGPU_OK;
+}
+
+int pbrgpu_scene_bounds(const pbrgpu_ctx* ctx, float* bmin, float* bmax) {
+  if (!ctx || !ctx->committed) return PBRGPU_ERR_INVALID;
+  for (int k = 0; k < 3; ++k) { bmin[k] = ctx->host.bmin[k]; bmax[k] = ctx->host.bmax[k]; }
+  return PBRGPU_OK;
+}
+
+int pbrgpu_set_wave_spp(pbrgpu_ctx* ctx, uint32_t spp_per_wave) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  ctx->wave_spp = spp_per_wave;
+  return PBRGPU_OK;
+}
+
+int pbrgpu_get_stats(const pbrgpu_ctx* ctx, pbrgpu_stats* out) {
+  if (!ctx || !out) return PBRGPU_ERR_INVALID;
+  *out = ctx->stats;
+  return PBRGPU_OK;
+}
+
+static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed,
+                      uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, float* rgba_out,
+                      uint32_t* count_out, size_t* finish_pass, bool out_on_device) {
+  if (!CheckCommitted(ctx, "pbrgpu_render")) return PBRGPU_ERR_INVALID;
+  if (sample_stride == 0 || !rgba_out || !count_out) { ctx->error = "pbrgpu_render: bad arguments"; return PBRGPU_ERR_INVALID; }
+  const auto t0 = std::chrono::steady_clock::now();
+  const uint32_t ndev = uint32_t(ctx->devices.size());
+  const uint32_t npix = width * height;
+  if (finish_pass) *finish_pass = 0;
+  std::vector<LoopTimers> tms(ndev);
+  std::vector<int> rcs(ndev, PBRGPU_OK);
+  std::vector<size_t> progress(ndev, 0);
+  if (ndev == 1) {
+    rcs[0] = RenderOnDevice(ctx, ctx->devices[0], width, height, spp, seed, sample_offset, sample_stride, cancel,
+                            finish_pass, &tms[0]);
+  } else {
+    // one host thread per device; device k renders samples sample_offset + (k + j*ndev)*sample_stride
+    std::vector<std::thread> th;
+    for (uint32_t k = 0; k < ndev; ++k) {
+      th.emplace_back([&, k]() {
+        rcs[k] = RenderOnDevice(ctx, ctx->devices[k], width, height, spp, seed, sample_offset + k * sample_stride,
+                                sample_stride * ndev, cancel, &progress[k], &tms[k]);
+      });
+    }
+    for (auto& t : th) t.join();
+    if (finish_pass) {
+      size_t m = spp;
+      for (uint32_t k = 0; k < ndev; ++k) m = std::min(m, progress[k]);
+      *finish_pass = m;
+    }
+  }
+  for (uint32_t k = 0; k < ndev; ++k) if (rcs[k] != PBRGPU_OK) return rcs[k];
+
+  // frame-end sum of the per-device accumulators onto device 0 (peer copies over NVLink)
+  Device& d0 = ctx->devices[0];
+  CUDA_TRY(ctx, cudaSetDevice(d0.id));
+  if (ndev > 1) {
+    DevBuf<float4> tmp_rgba;
+    DevBuf<uint32_t> tmp_count;
+    CUDA_TRY(ctx, tmp_rgba.Alloc(npix));
+    CUDA_TRY(ctx, tmp_count.Alloc(npix));
+    for (uint32_t k = 1; k < ndev; ++k) {
+      Device& dk = ctx->devices[k];
+      CUDA_TRY(ctx, cudaMemcpyPeerAsync(tmp_rgba.ptr, d0.id, dk.rgba.ptr, dk.id, sizeof(float4) * npix, d0.stream));
+      CUDA_TRY(ctx, cudaMemcpyPeerAsync(tmp_count.ptr, d0.id, dk.count.ptr, dk.id, sizeof(uint32_t) * npix, d0.stream));
+      AddBuffersKernel<<<(npix + 255) / 256, 256, 0, d0.stream>>>(d0.rgba.ptr, tmp_rgba.ptr, d0.count.ptr, tmp_count.ptr, npix);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(d0.stream));
+    tmp_rgba.Free();
+    tmp_count.Free();
+  }
+  const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  CUDA_TRY(ctx, cudaMemcpyAsync(rgba_out, d0.rgba.ptr, sizeof(float4) * npix, kind, d0.stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(count_out, d0.count.ptr, sizeof(uint32_t) * npix, kind, d0.stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(d0.stream));
+
+  pbrgpu_stats& s = ctx->stats;
+  memset(&s, 0, sizeof(s));
+  for (uint32_t k = 0; k < ndev; ++k) {
+    const Device& d = ctx->devices[k];
+    if (d.h_stats) {
+      s.closest_rays += d.h_stats[pbr::kStatClosest];
+      s.shadow_rays += d.h_stats[pbr::kStatShadow];
+      s.sss_rays += d.h_stats[pbr::kStatSss];
+    }
+    s.kernel_launches += tms[k].launches;
+  }
+  uint64_t samples = 0;
+  for (uint32_t sidx = sample_offset; sidx < spp; sidx += sample_stride) ++samples;
+  s.paths = samples * npix;
+  s.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return PBRGPU_OK;
+}
+
+int pbrgpu_render(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed,
+                  uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, float* rgba_out,
+                  uint32_t* count_out, size_t* finish_pass) {
+  return RenderImpl(ctx, width, height, spp, seed, sample_offset, sample_stride, cancel, rgba_out, count_out,
+                    finish_pass, false);
+}
+
+int pbrgpu_render_device(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed,
+                         uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, float* d_rgba,
+                         uint32_t* d_count, size_t* finish_pass) {
+  return RenderImpl(ctx, width, height, spp, seed, sample_offset, sample_stride, cancel, d_rgba, d_count, finish_pass,
+                    true);
+}
+
+// ------------------------------------------------------------------------------------------------ test hooks
+int pbrgpu_trace_device(pbrgpu_ctx* ctx, const pbrgpu_ray* d_rays, uint64_t n, pbrgpu_hit* d_hits, int collect_stats) {
+  if (!CheckCommitted(ctx, "pbrgpu_trace_device")) return PBRGPU_ERR_INVALID;
+  if (n > 0xfffffff0ull) { ctx->error = "pbrgpu_trace_device: at most 2^32-16 rays per call"; return PBRGPU_ERR_INVALID; }
+  Device& d = ctx->devices[0];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  int rc = EnsureWave(ctx, d, 1);
+  if (rc != PBRGPU_OK) return rc;
+  DevBuf<float4> tuv, ng;
+  DevBuf<uint4> ids;
+  if (d_hits) {
+    CUDA_TRY(ctx, tuv.Alloc(n)); CUDA_TRY(ctx, ng.Alloc(n)); CUDA_TRY(ctx, ids.Alloc(n));
+  }
+  CUDA_TRY(ctx, cudaMemsetAsync(d.counters.ptr, 0, sizeof(uint32_t) * pbr::kCounterCount, d.stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(d.stats.ptr, 0, sizeof(unsigned long long) * pbr::kStatCount, d.stream));
+  CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
+  pbr::TraceBatchKernel<<<PersistentGrid(d, 8), kBlock, 0, d.stream>>>(
+      d.view, reinterpret_cast<const float4*>(d_rays), n, tuv.ptr, ids.ptr, ng.ptr, d.counters.ptr + pbr::kFetchTrace,
+      d.stats.ptr, collect_stats);
+  CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
+  if (d_hits) {
+    // interleave the three SoA outputs into the caller's array-of-structs (pbrgpu_hit = 9 words)
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(d_hits) + 0, sizeof(pbrgpu_hit), ng.ptr, sizeof(float4),
+                                    12, n, cudaMemcpyDeviceToDevice, d.stream));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(d_hits) + 12, sizeof(pbrgpu_hit), tuv.ptr, sizeof(float4),
+                                    12, n, cudaMemcpyDeviceToDevice, d.stream));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(d_hits) + 24, sizeof(pbrgpu_hit), ids.ptr, sizeof(uint4),
+                                    12, n, cudaMemcpyDeviceToDevice, d.stream));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  CUDA_TRY(ctx, cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]);
+  rc = FetchStats(ctx, d);
+  if (rc != PBRGPU_OK) return rc;
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.closest_rays = n;
+  ctx->stats.trace_closest_ms = ms;
+  ctx->stats.nodes_visited = d.h_stats[pbr::kStatNodes];
+  ctx->stats.prims_tested = d.h_stats[pbr::kStatPrims];
+  ctx->stats.kernel_launches = 1;
+  tuv.Free(); ng.Free(); ids.Free();
+  return PBRGPU_OK;
+}
+
+int pbrgpu_occluded_device(pbrgpu_ctx* ctx, const pbrgpu_ray* d_rays, uint64_t n, uint8_t* d_occluded) {
+  if (!CheckCommitted(ctx, "pbrgpu_occluded_device")) return PBRGPU_ERR_INVALID;
+  if (n > 0xfffffff0ull) { ctx->error = "pbrgpu_occluded_device: at most 2^32-16 rays per call"; return PBRGPU_ERR_INVALID; }
+  Device& d = ctx->devices[0];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  int rc = EnsureWave(ctx, d, 1);
+  if (rc != PBRGPU_OK) return rc;
+  CUDA_TRY(ctx, cudaMemsetAsync(d.counters.ptr, 0, sizeof(uint32_t) * pbr::kCounterCount, d.stream));
+  CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
+  pbr::OccludedBatchKernel<<<PersistentGrid(d, 8), kBlock, 0, d.stream>>>(
+      d.view, reinterpret_cast<const float4*>(d_rays), n, d_occluded, d.counters.ptr + pbr::kFetchShadow);
+  CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  CUDA_TRY(ctx, cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.shadow_rays = n;
+  ctx->stats.trace_any_ms = ms;
+  ctx->stats.kernel_launches = 1;
+  return PBRGPU_OK;
+}
+
+int pbrgpu_trace(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, uint64_t n, pbrgpu_hit* hits) {
+  if (!CheckCommitted(ctx, "pbrgpu_trace")) return PBRGPU_ERR_INVALID;
+  if (n == 0) return PBRGPU_OK;
+  Device& d = ctx->devices[0];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  DevBuf<pbrgpu_ray> dr;
+  DevBuf<pbrgpu_hit> dh;
+  CUDA_TRY(ctx, dr.Upload(rays, n, d.stream));
+  CUDA_TRY(ctx, dh.Alloc(n));
+  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  const int rc = pbrgpu_trace_device(ctx, dr.ptr, n, dh.ptr, 1);
+  if (rc == PBRGPU_OK) {
+    CUDA_TRY(ctx, cudaMemcpy(hits, dh.ptr, sizeof(pbrgpu_hit) * n, cudaMemcpyDeviceToHost));
+  }
+  dr.Free(); dh.Free();
+  return rc;
+}
+
+int pbrgpu_occluded(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, uint64_t n, uint8_t* occluded) {
+  if (!CheckCommitted(ctx, "pbrgpu_occluded")) return PBRGPU_ERR_INVALID;
+  if (n == 0) return PBRGPU_OK;
+  Device& d = ctx->devices[0];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  DevBuf<pbrgpu_ray> dr;
+  DevBuf<uint8_t> dout;
+  CUDA_TRY(ctx, dr.Upload(rays, n, d.stream));
+  CUDA_TRY(ctx, dout.Alloc(n));
+  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  const int rc = pbrgpu_occluded_device(ctx, dr.ptr, n, dout.ptr);
+  if (rc == PBRGPU_OK) CUDA_TRY(ctx, cudaMemcpy(occluded, dout.ptr, n, cudaMemcpyDeviceToHost));
+  dr.Free(); dout.Free();
+  return rc;
+}
+
+// mode: 0 = wavefront to termination (pbrgpu_radiance), 1 = single vertex (pbrgpu_shade), 2 = megakernel
+static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* seeds, uint64_t n, float* out, int mode) {
+  if (!CheckCommitted(ctx, "pbrgpu_radiance")) return PBRGPU_ERR_INVALID;
+  if (n == 0) return PBRGPU_OK;
+  if (n > 0x7fffffffull) { ctx->error = "path hook: too many paths"; return PBRGPU_ERR_INVALID; }
+  Device& d = ctx->devices[0];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  int rc = EnsureWave(ctx, d, uint32_t(n));
+  if (rc != PBRGPU_OK) return rc;
+  DevBuf<pbrgpu_ray> dr;
+  DevBuf<uint64_t> ds;
+  CUDA_TRY(ctx, dr.Upload(rays, n, d.stream));
+  CUDA_TRY(ctx, ds.Upload(seeds, 2 * n, d.stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(d.stats.ptr, 0, sizeof(unsigned long long) * pbr::kStatCount, d.stream));
+  const uint32_t n32 = uint32_t(n);
+  LoopTimers tm;
+  if (mode == 2) {
+    DevBuf<float> dout;
+    CUDA_TRY(ctx, dout.Alloc(3 * n));
+    MegaRadianceKernel<<<(n32 + 63) / 64, 64, 0, d.stream>>>(d.view, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32, dout.ptr);
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.ptr, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    dout.Free(); dr.Free(); ds.Free();
+    return PBRGPU_OK;
+  }
+  pbr::InitPathsFromRaysKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);
+  pbr::ShadeFlags flags;
+  flags.skip_emission_and_roulette = (mode == 1) ? 1u : 0u;
+  std::vector<float> face_t;
+  if (mode == 1) {
+    // the hook reports face direction and t of the first hit: run the closest-hit stage alone first
+    DevBuf<float> dface;
+    CUDA_TRY(ctx, dface.Alloc(2 * n));
+    pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters);
+    pbr::TraceClosestKernel<<<PersistentGrid(d, 8), kBlock, 0, d.stream>>>(d.view, d.wave, d.wave.q_active[0], n32);
+    SurfaceFaceKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.view, d.wave, n32, dface.ptr);
+    face_t.resize(2 * n);
+    CUDA_TRY(ctx, cudaMemcpyAsync(face_t.data(), dface.ptr, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+    dface.Free();
+  }
+  rc = RunWave(ctx, d, n32, mode == 1 ? 1u : 0xffffffffu, flags, &tm, nullptr);
+  if (rc != PBRGPU_OK) { dr.Free(); ds.Free(); return rc; }
+  std::vector<float4> rad(n), thr, ro, rdv;
+  CUDA_TRY(ctx, cudaMemcpyAsync(rad.data(), d.rad.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+  if (mode == 1) {
+    thr.resize(n); ro.resize(n); rdv.resize(n);
+    CUDA_TRY(ctx, cudaMemcpyAsync(thr.data(), d.thr.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ro.data(), d.ray_o.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(rdv.data(), d.ray_d.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  if (mode == 0) {
+    for (uint64_t i = 0; i < n; ++i) { out[3 * i] = rad[i].x; out[3 * i + 1] = rad[i].y; out[3 * i + 2] = rad[i].z; }
+  } else {
+    for (uint64_t i = 0; i < n; ++i) {
+      float* o = out + 16 * i;
+      for (int k = 0; k < 16; ++k) o[k] = 0.f;
+      if (face_t[2 * i] < 0.f) continue;
+      o[0] = 1.f;
+      o[1] = rdv[i].x; o[2] = rdv[i].y; o[3] = rdv[i].z;
+      o[4] = thr[i].x; o[5] = thr[i].y; o[6] = thr[i].z;
+      o[7] = rad[i].x; o[8] = rad[i].y; o[9] = rad[i].z;
+      o[10] = thr[i].w;
+      o[11] = ro[i].x; o[12] = ro[i].y; o[13] = ro[i].z;
+      o[14] = face_t[2 * i];
+      o[15] = face_t[2 * i + 1];
+    }
+  }
+  rc = FetchStats(ctx, d);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  ctx->stats.paths = n;
+  ctx->stats.closest_rays = d.h_stats[pbr::kStatClosest];
+  ctx->stats.shadow_rays = d.h_stats[pbr::kStatShadow];
+  ctx->stats.sss_rays = d.h_stats[pbr::kStatSss];
+  ctx->stats.kernel_launches = tm.launches;
+  dr.Free(); ds.Free();
+  return rc;
+}
+
+int pbrgpu_radiance(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* seeds, uint64_t n, float* radiance_out) {
+  return PathHook(ctx, rays, seeds, n, radiance_out, 0);
+}
+int pbrgpu_radiance_mega(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* seeds, uint64_t n, float* radiance_out) {
+  return PathHook(ctx, rays, seeds, n, radiance_out, 2);
+}
+int pbrgpu_shade(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* seeds, uint64_t n, float* out16) {
+  return PathHook(ctx, rays, seeds, n, out16, 1);
+}
+
+int pbrgpu_eval_closure(pbrgpu_ctx* ctx, int op, const float* params, const float* in, uint32_t in_stride, uint64_t n,
+                        float* out, uint32_t out_stride) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  if (n == 0) return PBRGPU_OK;
+  Device& d = ctx->devices[0];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  DevBuf<float> dp, din, dout;
+  float dummy[32] = {0};
+  CUDA_TRY(ctx, dp.Upload(params ? params : dummy, 32, d.stream));
+  if (in_stride) CUDA_TRY(ctx, din.Upload(in, size_t(in_stride) * n, d.stream));
+  CUDA_TRY(ctx, dout.Alloc(size_t(out_stride) * n));
+  KatKernel<<<unsigned((n + 127) / 128), 128, 0, d.stream>>>(op, dp.ptr, din.ptr, in_stride, n, dout.ptr, out_stride);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.ptr, sizeof(float) * out_stride * n, cudaMemcpyDeviceToHost, d.stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  CUDA_TRY(ctx, cudaGetLastError());
+  dp.Free(); din.Free(); dout.Free();
+  return PBRGPU_OK;
+}
+
+}  // extern "C"

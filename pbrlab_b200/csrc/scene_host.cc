@@ -1,0 +1,284 @@
+// See scene_host.h.
+#include "scene_host.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace pbrhost {
+
+bool HostScene::SetTriangles(const float* xyzw, uint32_t nverts, const uint32_t* vidx, const float* nxyzw,
+                             uint32_t nnormals, const uint32_t* nidx, const float* uv, uint32_t nuv,
+                             const uint32_t* tidx, const uint32_t* material_id, const uint32_t* instance_id,
+                             const uint32_t* geom_id, const uint32_t* prim_id, uint64_t ntris) {
+  committed = false;
+  if (ntris > 0x7fffffffull) { error = "pbrgpu_set_triangles: too many triangles"; return false; }
+  if (ntris && (!xyzw || !vidx || !instance_id || !geom_id || !prim_id)) {
+    error = "pbrgpu_set_triangles: null array";
+    return false;
+  }
+  verts.resize(nverts);
+  if (nverts) memcpy(verts.data(), xyzw, sizeof(F4) * nverts);
+  normals.resize(nxyzw ? nnormals : 0);
+  if (nxyzw && nnormals) memcpy(normals.data(), nxyzw, sizeof(F4) * nnormals);
+  texcoords.resize(uv ? nuv : 0);
+  if (uv && nuv) memcpy(texcoords.data(), uv, sizeof(F2) * nuv);
+  tri_vidx.resize(ntris); tri_nidx.resize(ntris); tri_tidx.resize(ntris); tri_ids.resize(ntris);
+  for (uint64_t i = 0; i < ntris; ++i) {
+    const uint32_t a = vidx[3 * i], b = vidx[3 * i + 1], c = vidx[3 * i + 2];
+    if (a >= nverts || b >= nverts || c >= nverts) { error = "pbrgpu_set_triangles: vertex index out of range"; return false; }
+    tri_vidx[i] = {a, b, c, 0u};
+    U4 n = {PBRGPU_INVALID_ID, PBRGPU_INVALID_ID, PBRGPU_INVALID_ID, PBRGPU_INVALID_ID};
+    if (nidx && !normals.empty()) {
+      n.x = nidx[3 * i]; n.y = nidx[3 * i + 1]; n.z = nidx[3 * i + 2];
+      if ((n.x != PBRGPU_INVALID_ID && n.x >= normals.size()) || (n.y != PBRGPU_INVALID_ID && n.y >= normals.size()) ||
+          (n.z != PBRGPU_INVALID_ID && n.z >= normals.size())) {
+        error = "pbrgpu_set_triangles: normal index out of range";
+        return false;
+      }
+    }
+    tri_nidx[i] = n;
+    U4 t = {PBRGPU_INVALID_ID, PBRGPU_INVALID_ID, PBRGPU_INVALID_ID, 0u};
+    if (tidx && !texcoords.empty()) {
+      t.x = tidx[3 * i]; t.y = tidx[3 * i + 1]; t.z = tidx[3 * i + 2];
+      if ((t.x != PBRGPU_INVALID_ID && t.x >= texcoords.size()) || (t.y != PBRGPU_INVALID_ID && t.y >= texcoords.size()) ||
+          (t.z != PBRGPU_INVALID_ID && t.z >= texcoords.size())) {
+        error = "pbrgpu_set_triangles: texcoord index out of range";
+        return false;
+      }
+    }
+    tri_tidx[i] = t;
+    tri_ids[i] = {instance_id[i], geom_id[i], prim_id[i], material_id ? material_id[i] : PBRGPU_INVALID_ID};
+  }
+  return true;
+}
+
+bool HostScene::SetCurves(const float* xyzr, uint32_t nverts, const uint32_t* first_cp, const uint32_t* material_id,
+                          const uint32_t* instance_id, const uint32_t* geom_id, const uint32_t* prim_id,
+                          uint64_t nsegs) {
+  committed = false;
+  if (nsegs > 0x7fffffffull) { error = "pbrgpu_set_curves: too many segments"; return false; }
+  if (nsegs && (!xyzr || !first_cp || !instance_id || !geom_id || !prim_id)) {
+    error = "pbrgpu_set_curves: null array";
+    return false;
+  }
+  curve_cps.resize(4 * nsegs);
+  curve_ids.resize(nsegs);
+  for (uint64_t i = 0; i < nsegs; ++i) {
+    const uint32_t f = first_cp[i];
+    if (uint64_t(f) + 3 >= nverts) { error = "pbrgpu_set_curves: control point index out of range"; return false; }
+    memcpy(&curve_cps[4 * i], xyzr + 4 * size_t(f), sizeof(F4) * 4);
+    curve_ids[i] = {instance_id[i], geom_id[i], prim_id[i], material_id ? material_id[i] : PBRGPU_INVALID_ID};
+  }
+  return true;
+}
+
+bool HostScene::SetMaterials(const pbrgpu_material* m, uint32_t n) {
+  if (n && !m) { error = "pbrgpu_set_materials: null array"; return false; }
+  for (uint32_t i = 0; i < n; ++i) {
+    if (m[i].type > 1) { error = "pbrgpu_set_materials: unknown material type"; return false; }
+    if (m[i].type == 0 && (m[i].tex_id[0] != PBRGPU_INVALID_ID || m[i].tex_id[1] != PBRGPU_INVALID_ID)) {
+      error = "pbrgpu_set_materials: textured materials are not supported by this backend yet";
+      return false;
+    }
+  }
+  materials.assign(m, m + n);
+  return true;
+}
+
+bool HostScene::SetLights(const pbrgpu_light_tables* t) {
+  committed = false;
+  light_cdf.clear(); lights.clear(); lprim_cdf.clear(); lprim_info.clear(); lprim_tri.clear();
+  if (!t || t->num_lights == 0) return true;
+  light_cdf.assign(t->light_cdf, t->light_cdf + t->num_lights);
+  lights.resize(t->num_lights);
+  for (uint32_t l = 0; l < t->num_lights; ++l) {
+    lights[l].choose_probability = t->light_probability[l];
+    lights[l].prim_offset = t->light_prim_offset[l];
+    lights[l].prim_count = t->light_prim_offset[l + 1] - t->light_prim_offset[l];
+    lights[l].pad = 0;
+    if (lights[l].prim_count == 0) { error = "pbrgpu_set_lights: light without primitives"; return false; }
+  }
+  const uint32_t np = t->num_light_prims;
+  lprim_cdf.assign(t->prim_cdf, t->prim_cdf + np);
+  lprim_tri.assign(t->prim_triangle, t->prim_triangle + np);
+  lprim_info.resize(np);
+  for (uint32_t l = 0; l < t->num_lights; ++l) {
+    for (uint32_t k = lights[l].prim_offset; k < lights[l].prim_offset + lights[l].prim_count; ++k) {
+      // pdf = choose_light * choose_prim * 1/area, multiplied in the reference's order (light-manager.h:59-62,151-152)
+      const float pdf = t->light_probability[l] * t->prim_probability[k] * t->prim_area_pdf[k];
+      lprim_info[k] = {t->prim_emission[3 * k], t->prim_emission[3 * k + 1], t->prim_emission[3 * k + 2], pdf};
+    }
+  }
+  // emissive entries are resolved against the triangles in Commit()
+  pending_emissive_.assign(t->prim_is_emissive, t->prim_is_emissive + np);
+  return true;
+}
+
+void MakeCamera(const float* bmin, const float* bmax, uint32_t width, uint32_t height, float* cam) {
+  float hs, vs;
+  if (bmax[0] - bmin[0] > bmax[1] - bmin[1]) {
+    hs = bmax[0] - bmin[0];
+    vs = hs * float(height) / float(width);
+  } else {
+    vs = bmax[1] - bmin[1];
+    hs = vs * float(width) / float(height);
+  }
+  cam[0] = (bmax[0] + bmin[0]) * 0.5f;
+  cam[1] = (bmax[1] + bmin[1]) * 0.5f;
+  cam[2] = bmax[2] + hs * 0.5f * sqrtf(3.f);
+  cam[3] = (bmax[0] + bmin[0]) * 0.5f - hs * 0.5f;
+  cam[4] = (bmax[1] + bmin[1]) * 0.5f + vs * 0.5f;
+  cam[5] = bmax[2];
+  cam[6] = hs / float(width);
+  cam[7] = vs / float(height);
+}
+
+namespace {
+inline void BezierBasisQuarter(int i, float* b) {   // Embree BezierBasis::eval(float(i)/4) (bezier_curve.h:16-26)
+  const float t1 = float(i) / 4.0f, t0 = 1.0f - t1;
+  b[0] = t0 * t0 * t0;
+  b[1] = 3.0f * t1 * (t0 * t0);
+  b[2] = 3.0f * (t1 * t1) * t0;
+  b[3] = t1 * t1 * t1;
+}
+}  // namespace
+
+bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const uint32_t nt = num_tris(), nc = num_curves();
+  if (nt == 0 && nc == 0) { error = "pbrgpu_commit: empty scene"; return false; }
+  for (auto& id : tri_ids) {
+    if (id.w != PBRGPU_INVALID_ID && id.w >= materials.size()) { error = "pbrgpu_commit: material id out of range"; return false; }
+  }
+  for (auto& id : curve_ids) {
+    if (id.w != PBRGPU_INVALID_ID && id.w >= materials.size()) { error = "pbrgpu_commit: material id out of range"; return false; }
+  }
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  pbrbvh::BuildParams prm;
+  const char* err = nullptr;
+
+  // ---- triangles: Embree's TriangleM stores v0, e1 = v0 - v1, e2 = v2 - v0 (kernels/geometry/triangle.h:40-41)
+  tri_data.clear();
+  if (nt) {
+    std::vector<pbrbvh::Aabb> boxes(nt);
+    for (uint32_t i = 0; i < nt; ++i) {
+      const F4 &a = verts[tri_vidx[i].x], &b = verts[tri_vidx[i].y], &c = verts[tri_vidx[i].z];
+      pbrbvh::Aabb& bx = boxes[i];
+      bx.lo[0] = std::min(a.x, std::min(b.x, c.x)); bx.hi[0] = std::max(a.x, std::max(b.x, c.x));
+      bx.lo[1] = std::min(a.y, std::min(b.y, c.y)); bx.hi[1] = std::max(a.y, std::max(b.y, c.y));
+      bx.lo[2] = std::min(a.z, std::min(b.z, c.z)); bx.hi[2] = std::max(a.z, std::max(b.z, c.z));
+      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], bx.lo[k]); hi[k] = std::max(hi[k], bx.hi[k]); }
+    }
+    if (!pbrbvh::BuildBvh8(boxes.data(), nt, prm, &tri_bvh, &err)) { error = err; return false; }
+    tri_data.resize(size_t(3) * nt);
+    for (uint32_t k = 0; k < nt; ++k) {
+      const uint32_t i = tri_bvh.prim_order[k];
+      const F4 &a = verts[tri_vidx[i].x], &b = verts[tri_vidx[i].y], &c = verts[tri_vidx[i].z];
+      float idbits;
+      memcpy(&idbits, &i, 4);
+      tri_data[3 * k + 0] = {a.x, a.y, a.z, idbits};
+      tri_data[3 * k + 1] = {a.x - b.x, a.y - b.y, a.z - b.z, 0.f};
+      tri_data[3 * k + 2] = {c.x - a.x, c.y - a.y, c.z - a.z, 0.f};
+    }
+  } else {
+    tri_bvh = pbrbvh::Bvh8();
+  }
+
+  // ---- curves: a segment's ribbon lies inside the union of balls (B(i/4), r(i/4)), i = 0..4
+  curve_data.clear(); curve_prim.clear();
+  if (nc) {
+    std::vector<pbrbvh::Aabb> boxes(nc);
+    for (uint32_t i = 0; i < nc; ++i) {
+      const F4* cp = &curve_cps[4 * size_t(i)];
+      pbrbvh::Aabb& bx = boxes[i];
+      for (int k = 0; k < 3; ++k) { bx.lo[k] = FLT_MAX; bx.hi[k] = -FLT_MAX; }
+      // Embree accurateFlatBounds(4): bbox of B(0), B(1/4), B(1/2), B(3/4) and v3, enlarged by the largest |r| of
+      // those points (kernels/subdiv/bezier_curve.h:631-640) — this is what feeds rtcGetSceneBounds, hence the camera
+      float ebl[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ebh[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, er = 0.f;
+      for (int j = 0; j <= 4; ++j) {
+        float p[4];
+        if (j < 4) {
+          float b[4];
+          BezierBasisQuarter(j, b);
+          const float* c0 = &cp[0].x; const float* c1 = &cp[1].x; const float* c2 = &cp[2].x; const float* c3 = &cp[3].x;
+          for (int k = 0; k < 4; ++k) p[k] = b[0] * c0[k] + (b[1] * c1[k] + (b[2] * c2[k] + b[3] * c3[k]));
+        } else {
+          p[0] = cp[3].x; p[1] = cp[3].y; p[2] = cp[3].z; p[3] = cp[3].w;
+        }
+        const float r = std::fabs(p[3]);
+        er = std::max(er, r);
+        for (int k = 0; k < 3; ++k) {
+          ebl[k] = std::min(ebl[k], p[k]); ebh[k] = std::max(ebh[k], p[k]);
+          // BVH box: small safety margin on top of the exact ball bound
+          bx.lo[k] = std::min(bx.lo[k], p[k] - r * 1.0001f);
+          bx.hi[k] = std::max(bx.hi[k], p[k] + r * 1.0001f);
+        }
+      }
+      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], ebl[k] - er); hi[k] = std::max(hi[k], ebh[k] + er); }
+    }
+    if (!pbrbvh::BuildBvh8(boxes.data(), nc, prm, &curve_bvh, &err)) { error = err; return false; }
+    curve_data.resize(size_t(4) * nc);
+    curve_prim.resize(nc);
+    for (uint32_t k = 0; k < nc; ++k) {
+      const uint32_t i = curve_bvh.prim_order[k];
+      memcpy(&curve_data[4 * size_t(k)], &curve_cps[4 * size_t(i)], sizeof(F4) * 4);
+      curve_prim[k] = i;
+    }
+  } else {
+    curve_bvh = pbrbvh::Bvh8();
+  }
+
+  // ---- emissive triangle entries (LightManager::ImplicitAreaLight)
+  emissive.clear();
+  for (auto& n : tri_nidx) n.w = PBRGPU_INVALID_ID;
+  for (size_t k = 0; k < lprim_tri.size(); ++k) {
+    if (lprim_tri[k] >= nt) { error = "pbrgpu_commit: light primitive refers to a missing triangle"; return false; }
+    if (k < pending_emissive_.size() && pending_emissive_[k]) {
+      tri_nidx[lprim_tri[k]].w = uint32_t(emissive.size());
+      emissive.push_back(lprim_info[k]);
+    }
+  }
+
+  for (int k = 0; k < 3; ++k) {
+    bmin[k] = bmin_in ? bmin_in[k] : lo[k];
+    bmax[k] = bmax_in ? bmax_in[k] : hi[k];
+  }
+  committed = true;
+  build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return true;
+}
+
+pbr::SceneView HostScene::HostView() const {
+  pbr::SceneView v;
+  memset(&v, 0, sizeof(v));
+  v.tri_nodes = reinterpret_cast<const float4*>(tri_bvh.nodes.data());
+  v.tri_data = reinterpret_cast<const float4*>(tri_data.data());
+  v.curve_nodes = reinterpret_cast<const float4*>(curve_bvh.nodes.data());
+  v.curve_data = reinterpret_cast<const float4*>(curve_data.data());
+  v.curve_prim = curve_prim.data();
+  v.num_tris = num_tris();
+  v.num_curves = num_curves();
+  v.tri_ids = reinterpret_cast<const uint4*>(tri_ids.data());
+  v.tri_nidx = reinterpret_cast<const uint4*>(tri_nidx.data());
+  v.tri_vidx = reinterpret_cast<const uint4*>(tri_vidx.data());
+  v.tri_tidx = reinterpret_cast<const uint4*>(tri_tidx.data());
+  v.verts = reinterpret_cast<const float4*>(verts.data());
+  v.normals = reinterpret_cast<const float4*>(normals.data());
+  v.texcoords = reinterpret_cast<const float2*>(texcoords.data());
+  v.curve_ids = reinterpret_cast<const uint4*>(curve_ids.data());
+  v.materials = reinterpret_cast<const pbr::DeviceMaterial*>(materials.data());
+  v.num_materials = uint32_t(materials.size());
+  v.emissive = reinterpret_cast<const float4*>(emissive.data());
+  v.light_cdf = light_cdf.data();
+  v.lights = lights.data();
+  v.num_lights = uint32_t(lights.size());
+  v.lprim_cdf = lprim_cdf.data();
+  v.lprim_info = reinterpret_cast<const float4*>(lprim_info.data());
+  v.lprim_tri = lprim_tri.data();
+  return v;
+}
+
+}  // namespace pbrhost

@@ -1,0 +1,153 @@
+// C door into the C++ host API (pbrlab::Scene / Render / loaders) for the Python tests, bench.py and the graft
+// entry points — ctypes cannot call C++.  Nothing here adds behaviour: every function forwards to the public
+// classes the reference's callers would use.
+#include <chrono>
+#include <cstring>
+#include <exception>
+#include <string>
+#include <vector>
+
+#include "../../include/pbrgpu.h"
+#include "io/curve-mesh-io.h"
+#include "io/triangle-mesh-io.h"
+#include "pc-common.h"
+#include "render.h"
+#include "scene.h"
+
+namespace {
+thread_local std::string g_error;
+}
+
+extern "C" {
+
+struct pbrhost_flat {   // views into Scene::Flat(); valid until the scene is destroyed or re-committed
+  const float* verts; uint32_t nverts;
+  const float* normals; uint32_t nnormals;
+  const float* texcoords; uint32_t ntexcoords;
+  const uint32_t *vidx, *nidx, *tidx, *tri_material, *tri_instance, *tri_geom, *tri_prim;
+  uint64_t ntris;
+  const float* curve_verts; uint32_t ncurve_verts;
+  const uint32_t *curve_first, *curve_material, *curve_instance, *curve_geom, *curve_prim;
+  uint64_t nsegs;
+  const float* materials; uint32_t nmaterials;
+  pbrgpu_light_tables lights;
+  float bmin[3], bmax[3];
+};
+
+const char* pbrhost_last_error(void) { return g_error.c_str(); }
+
+// CreateScene(argc, argv, &scene): argv[1..] = files.  commit_to_device = 0 stops after the host-side commit.
+void* pbrhost_scene_create(int nfiles, const char** files, int commit_to_device) {
+  std::vector<std::string> store;
+  store.emplace_back("pbrlab");
+  for (int i = 0; i < nfiles; ++i) store.emplace_back(files[i]);
+  std::vector<char*> argv;
+  for (auto& s : store) argv.push_back(const_cast<char*>(s.c_str()));
+  pbrlab::Scene* scene = new pbrlab::Scene();
+  try {
+    if (!CreateScene(int(argv.size()), argv.data(), scene, commit_to_device != 0)) {
+      g_error = "CreateScene failed";
+      delete scene;
+      return nullptr;
+    }
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    delete scene;
+    return nullptr;
+  }
+  return scene;
+}
+void pbrhost_scene_destroy(void* s) { delete static_cast<pbrlab::Scene*>(s); }
+
+void pbrhost_scene_flat(void* s, pbrhost_flat* o) {
+  const pbrlab::FlatScene& f = static_cast<pbrlab::Scene*>(s)->Flat();
+  memset(o, 0, sizeof(*o));
+  o->verts = f.verts.data(); o->nverts = uint32_t(f.verts.size() / 4);
+  o->normals = f.normals.data(); o->nnormals = uint32_t(f.normals.size() / 4);
+  o->texcoords = f.texcoords.data(); o->ntexcoords = uint32_t(f.texcoords.size() / 2);
+  o->vidx = f.vidx.data(); o->nidx = f.nidx.data(); o->tidx = f.tidx.data();
+  o->tri_material = f.tri_material.data(); o->tri_instance = f.tri_instance.data();
+  o->tri_geom = f.tri_geom.data(); o->tri_prim = f.tri_prim.data();
+  o->ntris = f.tri_prim.size();
+  o->curve_verts = f.curve_verts.data(); o->ncurve_verts = uint32_t(f.curve_verts.size() / 4);
+  o->curve_first = f.curve_first.data(); o->curve_material = f.curve_material.data();
+  o->curve_instance = f.curve_instance.data(); o->curve_geom = f.curve_geom.data(); o->curve_prim = f.curve_prim.data();
+  o->nsegs = f.curve_prim.size();
+  o->materials = f.materials.data(); o->nmaterials = uint32_t(f.materials.size() / 28);
+  o->lights.num_lights = uint32_t(f.lights.light_probability.size());
+  o->lights.light_probability = f.lights.light_probability.data();
+  o->lights.light_cdf = f.lights.light_cdf.data();
+  o->lights.light_prim_offset = f.lights.light_prim_offset.data();
+  o->lights.num_light_prims = uint32_t(f.lights.prim_probability.size());
+  o->lights.prim_probability = f.lights.prim_probability.data();
+  o->lights.prim_cdf = f.lights.prim_cdf.data();
+  o->lights.prim_area_pdf = f.lights.prim_area_pdf.data();
+  o->lights.prim_emission = f.lights.prim_emission.data();
+  o->lights.prim_is_emissive = f.lights.prim_is_emissive.data();
+  o->lights.prim_triangle = f.light_prim_triangle.data();
+  for (int k = 0; k < 3; ++k) { o->bmin[k] = f.bmin[k]; o->bmax[k] = f.bmax[k]; }
+}
+
+void* pbrhost_scene_ctx(void* s) { return static_cast<pbrlab::Scene*>(s)->DeviceContext(); }
+
+// pbrlab::Render() through the public C++ entry point.  Returns seconds inside Render(), < 0 on failure.
+double pbrhost_render(void* s, uint32_t w, uint32_t h, uint32_t spp, uint64_t seed, float* rgba, uint32_t* count) {
+  try {
+    pbrlab::SetRenderSeed(seed);
+    std::atomic_bool cancel(false);
+    std::atomic_size_t finish_pass(0);
+    pbrlab::RenderLayer layer;
+    const auto t0 = std::chrono::steady_clock::now();
+    pbrlab::Render(*static_cast<pbrlab::Scene*>(s), w, h, spp, cancel, &layer, &finish_pass);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (finish_pass.load() != spp) { g_error = "finish_pass != num_sample"; return -1.0; }
+    if (rgba) memcpy(rgba, layer.rgba.data(), sizeof(float) * layer.rgba.size());
+    if (count) memcpy(count, layer.count.data(), sizeof(uint32_t) * layer.count.size());
+    return std::chrono::duration<double>(t1 - t0).count();
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1.0;
+  }
+}
+
+// Scene::TraceFirstHit1 / AnyHit1 through the C++ API (single-ray entry points of the reference)
+int pbrhost_trace1(void* s, const float* ray8, float* out6, uint32_t* ids3) {
+  try {
+    pbrlab::Ray r;
+    r.ray_org = pbrlab::float3(ray8[0], ray8[1], ray8[2]); r.min_t = ray8[3];
+    r.ray_dir = pbrlab::float3(ray8[4], ray8[5], ray8[6]); r.max_t = ray8[7];
+    const pbrlab::TraceResult tr = static_cast<pbrlab::Scene*>(s)->TraceFirstHit1(r);
+    out6[0] = tr.t; out6[1] = tr.u; out6[2] = tr.v;
+    out6[3] = tr.normal_g[0]; out6[4] = tr.normal_g[1]; out6[5] = tr.normal_g[2];
+    ids3[0] = tr.instance_id; ids3[1] = tr.geom_id; ids3[2] = tr.prim_id;
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+int pbrhost_anyhit1(void* s, const float* ray8) {
+  try {
+    pbrlab::Ray r;
+    r.ray_org = pbrlab::float3(ray8[0], ray8[1], ray8[2]); r.min_t = ray8[3];
+    r.ray_dir = pbrlab::float3(ray8[4], ray8[5], ray8[6]); r.max_t = ray8[7];
+    return static_cast<pbrlab::Scene*>(s)->AnyHit1(r) ? 1 : 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
+// loader-level access (CyHair -> Bezier), two-call pattern: vt == nullptr returns the sizes
+int pbrhost_hair_load(const char* path, float* vt, uint64_t* nfloats, uint32_t* idx, uint64_t* nidx) {
+  std::vector<float> v;
+  std::vector<uint32_t> ind;
+  const bool ok = pbrlab::io::LoadCurveMeshAsCubicBezierCurve(path, false, &v, &ind);
+  *nfloats = v.size();
+  *nidx = ind.size();
+  if (vt) memcpy(vt, v.data(), sizeof(float) * v.size());
+  if (idx) memcpy(idx, ind.data(), sizeof(uint32_t) * ind.size());
+  return ok ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,303 @@
+#include "triangle-mesh-io.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <memory>
+
+namespace pbrlab {
+namespace io {
+namespace {
+
+bool ReadFile(const std::string& path, std::string* out) {
+  FILE* fp = fopen(path.c_str(), "rb");
+  if (!fp) return false;
+  fseek(fp, 0, SEEK_END);
+  const long n = ftell(fp);
+  fseek(fp, 0, SEEK_SET);
+  out->resize(size_t(n));
+  const size_t got = n > 0 ? fread(&(*out)[0], 1, size_t(n), fp) : 0;
+  fclose(fp);
+  out->push_back('\n');
+  return got == size_t(n);
+}
+
+inline bool IsSpace(char c) { return c == ' ' || c == '\t'; }
+inline bool IsEol(char c) { return c == '\n' || c == '\r' || c == '\0'; }
+inline void SkipSpace(const char** p) { while (IsSpace(**p)) ++*p; }
+
+// decimal -> float through double, like the reference's loader (real_t = float, parsed as double)
+inline float ParseFloat(const char** p) {
+  SkipSpace(p);
+  char* end = nullptr;
+  const double d = strtod(*p, &end);
+  if (end == *p) {   // not a number: skip the token
+    while (!IsSpace(**p) && !IsEol(**p)) ++*p;
+    return 0.f;
+  }
+  *p = end;
+  return static_cast<float>(d);
+}
+
+inline bool ParseInt(const char** p, int* v) {
+  char* end = nullptr;
+  const long x = strtol(*p, &end, 10);
+  if (end == *p) return false;
+  *p = end;
+  *v = int(x);
+  return true;
+}
+
+// OBJ index -> zero based (negative = relative to the elements read so far); 0 is invalid
+inline bool FixIndex(int idx, int n, int* out) {
+  if (idx > 0) { *out = idx - 1; return true; }
+  if (idx == 0) return false;
+  *out = n + idx;
+  return true;
+}
+
+struct Corner { int v, vt, vn; };
+
+std::string RestOfLine(const char* p) {
+  const char* e = p;
+  while (!IsEol(*e)) ++e;
+  while (e > p && IsSpace(e[-1])) --e;
+  return std::string(p, size_t(e - p));
+}
+
+struct RawMaterial {
+  std::string name;
+  std::map<std::string, std::string> keys;   // first occurrence wins
+};
+
+void LoadMtl(const std::string& path, std::vector<RawMaterial>* out, std::map<std::string, int>* index) {
+  std::string text;
+  if (!ReadFile(path, &text)) {
+    std::cerr << "warning : material file [" << path << "] not found" << std::endl;
+    return;
+  }
+  const char* p = text.c_str();
+  RawMaterial cur;
+  bool have = false;
+  while (*p) {
+    SkipSpace(&p);
+    const char* line = p;
+    while (!IsEol(*p)) ++p;
+    const char* eol = p;
+    while (*p == '\n' || *p == '\r') ++p;
+    if (line == eol || *line == '#') continue;
+    const char* sp = line;
+    while (sp < eol && !IsSpace(*sp)) ++sp;
+    const std::string key(line, size_t(sp - line));
+    const char* val = sp;
+    while (val < eol && IsSpace(*val)) ++val;
+    const char* vend = eol;
+    while (vend > val && IsSpace(vend[-1])) --vend;
+    const std::string value(val, size_t(vend - val));
+    if (key == "newmtl") {
+      if (have) {
+        index->insert(std::make_pair(cur.name, int(out->size())));
+        out->push_back(cur);
+      }
+      cur = RawMaterial();
+      cur.name = value;
+      have = true;
+      continue;
+    }
+    if (!have) continue;
+    cur.keys.insert(std::make_pair(key, value));
+  }
+  if (have) {
+    index->insert(std::make_pair(cur.name, int(out->size())));
+    out->push_back(cur);
+  }
+}
+
+bool GetFloat(const RawMaterial& m, const char* key, float* out) {
+  auto it = m.keys.find(key);
+  if (it == m.keys.end()) return false;
+  *out = float(atof(it->second.c_str()));   // reference: std::atof (triangle-mesh-io.cc:35-38)
+  return true;
+}
+bool GetFloat3(const RawMaterial& m, const char* key, float3* out) {
+  auto it = m.keys.find(key);
+  if (it == m.keys.end()) return false;
+  double x = 0.0, y = 0.0, z = 0.0;
+  sscanf(it->second.c_str(), "%lf %lf %lf", &x, &y, &z);   // reference :40-53
+  *out = float3(float(x), float(y), float(z));
+  return true;
+}
+
+MaterialParameter ToPrincipled(const RawMaterial& m) {
+  CyclesPrincipledBsdfParameter p;
+  GetFloat3(m, "base_color", &p.base_color);
+  GetFloat(m, "subsurface", &p.subsurface);
+  GetFloat3(m, "subsurface_radius", &p.subsurface_radius);
+  GetFloat3(m, "subsurface_color", &p.subsurface_color);
+  GetFloat(m, "metallic", &p.metallic);
+  GetFloat(m, "specular", &p.specular);
+  GetFloat(m, "specular_tint", &p.specular_tint);
+  GetFloat(m, "roughness", &p.roughness);
+  GetFloat(m, "anisotropic", &p.anisotropic);
+  GetFloat(m, "anisotropic_rotation", &p.anisotropic_rotation);
+  GetFloat(m, "sheen", &p.sheen);
+  GetFloat(m, "sheen_tint", &p.sheen_tint);
+  GetFloat(m, "clearcoat", &p.clearcoat);
+  GetFloat(m, "clearcoat_roughness", &p.clearcoat_roughness);
+  GetFloat(m, "ior", &p.ior);
+  GetFloat(m, "transmission", &p.transmission);
+  GetFloat(m, "transmission_roughness", &p.transmission_roughness);
+  for (const char* k : {"map_base_color", "map_subsurface_color"}) {
+    if (m.keys.count(k))
+      std::cerr << "warning : material [" << m.name << "] " << k
+                << " ignored (texture sampling is not implemented in the B200 backend)" << std::endl;
+  }
+  p.name = m.name;
+  return MaterialParameter(p);
+}
+
+struct ShapeBuild {
+  std::string name;
+  std::vector<uint32_t> v, vn, vt, mat;
+};
+
+}  // namespace
+
+bool LoadTriangleMeshFromObj(const std::string& filename, std::vector<TriangleMesh>* meshes,
+                             std::vector<MaterialParameter>* material_params, std::vector<Texture>* textures) {
+  (void)textures;
+  std::string text;
+  if (!ReadFile(filename, &text)) {
+    std::cerr << "error : cannot open [" << filename << "]" << std::endl;
+    return false;
+  }
+  const size_t slash = filename.find_last_of('/');
+  const std::string base_dir = (slash == std::string::npos) ? std::string("") : filename.substr(0, slash);
+  std::cerr << "base dir : " << base_dir << std::endl;
+
+  std::shared_ptr<Attribute> attr(new Attribute());
+  std::vector<RawMaterial> raw_materials;
+  std::map<std::string, int> material_index;
+  std::vector<ShapeBuild> shapes;
+  ShapeBuild cur;
+  int cur_material = -1;
+  std::vector<Corner> face;
+
+  auto flush = [&]() {
+    if (!cur.v.empty()) shapes.push_back(cur);
+    const std::string keep = cur.name;
+    cur = ShapeBuild();
+    cur.name = keep;
+  };
+
+  const char* p = text.c_str();
+  size_t line_no = 0;
+  while (*p) {
+    ++line_no;
+    SkipSpace(&p);
+    const char* line = p;
+    const char c0 = line[0], c1 = c0 ? line[1] : 0;
+    if (c0 == 'v' && IsSpace(c1)) {
+      p += 2;
+      const float x = ParseFloat(&p), y = ParseFloat(&p), z = ParseFloat(&p);
+      attr->vertices.push_back(x); attr->vertices.push_back(y); attr->vertices.push_back(z);
+      attr->vertices.push_back(1.0f);
+    } else if (c0 == 'v' && c1 == 'n' && IsSpace(line[2])) {
+      p += 3;
+      const float x = ParseFloat(&p), y = ParseFloat(&p), z = ParseFloat(&p);
+      attr->normals.push_back(x); attr->normals.push_back(y); attr->normals.push_back(z);
+      attr->normals.push_back(1.0f);
+    } else if (c0 == 'v' && c1 == 't' && IsSpace(line[2])) {
+      p += 3;
+      const float u = ParseFloat(&p), v = ParseFloat(&p);
+      attr->texcoords.push_back(u);
+      attr->texcoords.push_back(1.f - v);   // reference triangle-mesh-io.cc:286
+    } else if (c0 == 'f' && IsSpace(c1)) {
+      p += 2;
+      face.clear();
+      const int nv = int(attr->vertices.size() / 4), nn = int(attr->normals.size() / 4),
+                nt = int(attr->texcoords.size() / 2);
+      for (;;) {
+        SkipSpace(&p);
+        if (IsEol(*p)) break;
+        Corner c = {-1, -1, -1};
+        int raw;
+        if (!ParseInt(&p, &raw) || !FixIndex(raw, nv, &c.v)) {
+          std::cerr << "error : Failed to parse `f' line " << line_no << std::endl;
+          return false;
+        }
+        if (*p == '/') {
+          ++p;
+          if (*p == '/') {           // v//vn
+            ++p;
+            if (ParseInt(&p, &raw) && !FixIndex(raw, nn, &c.vn)) return false;
+          } else {
+            if (ParseInt(&p, &raw) && !FixIndex(raw, nt, &c.vt)) return false;
+            if (*p == '/') {
+              ++p;
+              if (ParseInt(&p, &raw) && !FixIndex(raw, nn, &c.vn)) return false;
+            }
+          }
+        }
+        face.push_back(c);
+      }
+      auto emit = [&](const Corner& a, const Corner& b, const Corner& c) {
+        cur.v.push_back(uint32_t(a.v)); cur.v.push_back(uint32_t(b.v)); cur.v.push_back(uint32_t(c.v));
+        cur.vn.push_back(uint32_t(a.vn)); cur.vn.push_back(uint32_t(b.vn)); cur.vn.push_back(uint32_t(c.vn));
+        cur.vt.push_back(uint32_t(a.vt)); cur.vt.push_back(uint32_t(b.vt)); cur.vt.push_back(uint32_t(c.vt));
+        cur.mat.push_back(uint32_t(cur_material));
+      };
+      const size_t n = face.size();
+      if (n == 3) {
+        emit(face[0], face[1], face[2]);
+      } else if (n == 4) {
+        // split along the shorter diagonal (reference src/io/tiny_obj_loader.h:1519-1575)
+        const float* V = attr->vertices.data();
+        auto d2 = [&](int a, int b) {
+          const float dx = V[4 * b] - V[4 * a], dy = V[4 * b + 1] - V[4 * a + 1], dz = V[4 * b + 2] - V[4 * a + 2];
+          return dx * dx + dy * dy + dz * dz;
+        };
+        if (d2(face[0].v, face[2].v) < d2(face[1].v, face[3].v)) {
+          emit(face[0], face[1], face[2]);
+          emit(face[0], face[2], face[3]);
+        } else {
+          emit(face[0], face[1], face[3]);
+          emit(face[1], face[2], face[3]);
+        }
+      } else if (n > 4) {
+        for (size_t k = 1; k + 1 < n; ++k) emit(face[0], face[k], face[k + 1]);
+      }
+    } else if (c0 == 'o' && IsSpace(c1)) {
+      flush();
+      cur.name = RestOfLine(line + 2);
+    } else if (c0 == 'g' && IsSpace(c1)) {
+      flush();
+      cur.name = RestOfLine(line + 2);
+    } else if (strncmp(line, "usemtl", 6) == 0) {
+      const char* q = line + 6;
+      SkipSpace(&q);
+      const std::string name = RestOfLine(q);
+      auto it = material_index.find(name);
+      cur_material = (it == material_index.end()) ? -1 : it->second;
+    } else if (strncmp(line, "mtllib", 6) == 0 && IsSpace(line[6])) {
+      const char* q = line + 7;
+      SkipSpace(&q);
+      const std::string name = RestOfLine(q);
+      LoadMtl(base_dir.empty() ? name : base_dir + "/" + name, &raw_materials, &material_index);
+    }
+    while (!IsEol(*p)) ++p;
+    while (*p == '\r') ++p;
+    if (*p == '\n') ++p;
+  }
+  flush();
+
+  meshes->clear();
+  for (const ShapeBuild& s : shapes) meshes->emplace_back(s.name, attr, s.v, s.vn, s.vt, s.mat);
+  for (const RawMaterial& m : raw_materials) material_params->push_back(ToPrincipled(m));
+  return true;
+}
+
+}  // namespace io
+}  // namespace pbrlab

@@ -1,0 +1,252 @@
+// TEST INFRASTRUCTURE ONLY — host emulation of the device code.
+// The per-ray / per-vertex routines of the CUDA path tracer (pbrlab_b200/csrc/device/*.cuh, kat.cuh) are plain
+// functions; this shim compiles them with g++ so their arithmetic can be checked against the compiled reference in
+// a container without a GPU.  It mirrors the pbrgpu_* entry points one to one (same argument meaning) but is never
+// built into, loaded by, or a fallback for the product: libpbrgpu.so has no CPU path.
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../pbrlab_b200/csrc/kat.cuh"
+#include "../../pbrlab_b200/csrc/scene_host.h"
+
+using namespace pbr;  // NOLINT
+
+namespace {
+struct Emul {
+  pbrhost::HostScene scene;
+  SceneView view;
+};
+
+template <typename F>
+void ParallelFor(uint64_t n, F f) {
+  const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+  std::atomic<uint64_t> next(0);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t)
+    th.emplace_back([&]() {
+      for (;;) {
+        const uint64_t b = next.fetch_add(1024);
+        if (b >= n) break;
+        const uint64_t e = std::min(n, b + 1024);
+        for (uint64_t i = b; i < e; ++i) f(i);
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
+RayT ToRay(const pbrgpu_ray& r) {
+  RayT ray;
+  ray.o = vec3(r.org[0], r.org[1], r.org[2]); ray.tmin = r.tmin;
+  ray.d = vec3(r.dir[0], r.dir[1], r.dir[2]); ray.tmax = r.tmax;
+  return ray;
+}
+}  // namespace
+
+extern "C" {
+
+void* emul_create() { return new Emul(); }
+void emul_destroy(void* h) { delete static_cast<Emul*>(h); }
+const char* emul_last_error(void* h) { return static_cast<Emul*>(h)->scene.error.c_str(); }
+
+int emul_set_triangles(void* h, const float* xyzw, uint32_t nverts, const uint32_t* vidx, const float* nxyzw,
+                       uint32_t nnormals, const uint32_t* nidx, const float* uv, uint32_t nuv, const uint32_t* tidx,
+                       const uint32_t* material_id, const uint32_t* instance_id, const uint32_t* geom_id,
+                       const uint32_t* prim_id, uint64_t ntris) {
+  return static_cast<Emul*>(h)->scene.SetTriangles(xyzw, nverts, vidx, nxyzw, nnormals, nidx, uv, nuv, tidx,
+                                                   material_id, instance_id, geom_id, prim_id, ntris) ? 0 : 1;
+}
+int emul_set_curves(void* h, const float* xyzr, uint32_t nverts, const uint32_t* first_cp, const uint32_t* material_id,
+                    const uint32_t* instance_id, const uint32_t* geom_id, const uint32_t* prim_id, uint64_t nsegs) {
+  return static_cast<Emul*>(h)->scene.SetCurves(xyzr, nverts, first_cp, material_id, instance_id, geom_id, prim_id,
+                                                nsegs) ? 0 : 1;
+}
+int emul_set_materials(void* h, const pbrgpu_material* m, uint32_t n) {
+  return static_cast<Emul*>(h)->scene.SetMaterials(m, n) ? 0 : 1;
+}
+int emul_set_lights(void* h, const pbrgpu_light_tables* t) { return static_cast<Emul*>(h)->scene.SetLights(t) ? 0 : 1; }
+int emul_commit(void* h, const float* bmin, const float* bmax) {
+  Emul* e = static_cast<Emul*>(h);
+  if (!e->scene.Commit(bmin, bmax)) return 3;
+  e->view = e->scene.HostView();
+  return 0;
+}
+int emul_scene_bounds(void* h, float* bmin, float* bmax) {
+  Emul* e = static_cast<Emul*>(h);
+  for (int k = 0; k < 3; ++k) { bmin[k] = e->scene.bmin[k]; bmax[k] = e->scene.bmax[k]; }
+  return 0;
+}
+// nodes, max depth, sah cost of the two BVHs: out[0..2] triangles, out[3..5] curves
+void emul_bvh_info(void* h, double* out6) {
+  Emul* e = static_cast<Emul*>(h);
+  out6[0] = e->scene.tri_bvh.num_nodes; out6[1] = e->scene.tri_bvh.max_depth; out6[2] = e->scene.tri_bvh.sah_cost;
+  out6[3] = e->scene.curve_bvh.num_nodes; out6[4] = e->scene.curve_bvh.max_depth; out6[5] = e->scene.curve_bvh.sah_cost;
+}
+
+int emul_trace(void* h, const pbrgpu_ray* rays, uint64_t n, pbrgpu_hit* hits, uint64_t* stats2) {
+  Emul* e = static_cast<Emul*>(h);
+  const SceneView& s = e->view;
+  std::atomic<uint64_t> nodes(0), prims(0);
+  ParallelFor(n, [&](uint64_t i) {
+    HitT hit;
+    TraverseStats st = {0, 0};
+    pbrgpu_hit out;
+    out.normal_g[0] = 1.f; out.normal_g[1] = 0.f; out.normal_g[2] = 0.f;
+    out.t = 1.f; out.u = 0.f; out.v = 0.f;
+    out.instance_id = out.geom_id = out.prim_id = kInvalid;
+    if (TraceClosest<true>(s, ToRay(rays[i]), &hit, &st)) {
+      const vec3 ng = HitGeometricNormal(s, hit);
+      out.normal_g[0] = ng.x; out.normal_g[1] = ng.y; out.normal_g[2] = ng.z;
+      out.t = hit.t; out.u = hit.u; out.v = hit.v;
+      uint4 ids;
+      if (hit.prim & kCurveFlag) ids = s.curve_ids[s.curve_prim[hit.prim & ~kCurveFlag]];
+      else ids = s.tri_ids[f2u(s.tri_data[hit.prim * 3].w)];
+      out.instance_id = ids.x; out.geom_id = ids.y; out.prim_id = ids.z;
+    }
+    hits[i] = out;
+    nodes += st.nodes;
+    prims += st.prims;
+  });
+  if (stats2) { stats2[0] = nodes; stats2[1] = prims; }
+  return 0;
+}
+
+int emul_occluded(void* h, const pbrgpu_ray* rays, uint64_t n, uint8_t* occ) {
+  Emul* e = static_cast<Emul*>(h);
+  ParallelFor(n, [&](uint64_t i) { occ[i] = TraceAny<false>(e->view, ToRay(rays[i]), nullptr) ? 1 : 0; });
+  return 0;
+}
+
+int emul_radiance(void* h, const pbrgpu_ray* rays, const uint64_t* seeds, uint64_t n, float* out, uint64_t* counts3) {
+  Emul* e = static_cast<Emul*>(h);
+  std::atomic<uint64_t> c0(0), c1(0), c2(0);
+  ParallelFor(n, [&](uint64_t i) {
+    Pcg32 rng;
+    pcg32_srandom(&rng, seeds[2 * i], seeds[2 * i + 1]);
+    uint64_t rc[3] = {0, 0, 0};
+    const vec3 L = PathRadiance(e->view, ToRay(rays[i]), &rng, rc);
+    out[3 * i] = L.x; out[3 * i + 1] = L.y; out[3 * i + 2] = L.z;
+    c0 += rc[0]; c1 += rc[1]; c2 += rc[2];
+  });
+  if (counts3) { counts3[0] = c0; counts3[1] = c1; counts3[2] = c2; }
+  return 0;
+}
+
+// one shading vertex, layout of pbrgpu_shade
+int emul_shade(void* h, const pbrgpu_ray* rays, const uint64_t* seeds, uint64_t n, float* out16) {
+  Emul* e = static_cast<Emul*>(h);
+  const SceneView& s = e->view;
+  ParallelFor(n, [&](uint64_t i) {
+    float* o = out16 + 16 * i;
+    for (int k = 0; k < 16; ++k) o[k] = 0.f;
+    const RayT ray = ToRay(rays[i]);
+    HitT hit;
+    if (!TraceClosest<false>(s, ray, &hit, nullptr)) return;
+    const Surface si = MakeSurface(s, ray, hit);
+    Pcg32 rng;
+    pcg32_srandom(&rng, seeds[2 * i], seeds[2 * i + 1]);
+    VertexResult vr;
+    const vec3 wo = -ray.d;
+    const int kind = MaterialKind(s, si);
+    if (kind == 1) {
+      if (PrincipledVertex(s, si, wo, &rng, &vr)) SubsurfaceVertex(s, si, &rng, &vr, nullptr);
+    } else if (kind == 2) {
+      HairVertex(s, si, wo, &rng, &vr);
+    } else {
+      AbsorbVertex(wo, si.P, &vr);
+    }
+    vec3 direct(0.f);
+    for (int k = 0; k < 2; ++k)
+      if (vr.shadow[k].active && !TraceAny<false>(s, vr.shadow[k].ray, nullptr)) direct = direct + vr.shadow[k].contribute;
+    o[0] = 1.f;
+    o[1] = vr.wi.x; o[2] = vr.wi.y; o[3] = vr.wi.z;
+    o[4] = vr.throughput.x; o[5] = vr.throughput.y; o[6] = vr.throughput.z;
+    o[7] = direct.x; o[8] = direct.y; o[9] = direct.z;
+    o[10] = vr.pdf;
+    o[11] = vr.P.x; o[12] = vr.P.y; o[13] = vr.P.z;
+    o[14] = float(si.face);
+    o[15] = hit.t;
+  });
+  return 0;
+}
+
+// hit -> SurfaceInfo: out n x 12: P(3) Ns(3) Ng(3) uv(2) face (-1 on miss)
+int emul_surface(void* h, const pbrgpu_ray* rays, uint64_t n, float* out12) {
+  Emul* e = static_cast<Emul*>(h);
+  const SceneView& s = e->view;
+  ParallelFor(n, [&](uint64_t i) {
+    float* o = out12 + 12 * i;
+    for (int k = 0; k < 12; ++k) o[k] = 0.f;
+    const RayT ray = ToRay(rays[i]);
+    HitT hit;
+    if (!TraceClosest<false>(s, ray, &hit, nullptr)) { o[11] = -1.f; return; }
+    const Surface si = MakeSurface(s, ray, hit);
+    o[0] = si.P.x; o[1] = si.P.y; o[2] = si.P.z;
+    o[3] = si.Ns.x; o[4] = si.Ns.y; o[5] = si.Ns.z;
+    o[6] = si.Ng.x; o[7] = si.Ng.y; o[8] = si.Ng.z;
+    o[9] = si.tex_u; o[10] = si.tex_v;
+    o[11] = float(si.face);
+  });
+  return 0;
+}
+
+// light sampling: out n x 10 (pos3, normal3, emission3, pdf)
+int emul_sample_light(void* h, const uint64_t* seeds, uint64_t n, float* out10) {
+  Emul* e = static_cast<Emul*>(h);
+  for (uint64_t i = 0; i < n; ++i) {
+    Pcg32 rng;
+    pcg32_srandom(&rng, seeds[2 * i], seeds[2 * i + 1]);
+    const LightSample ls = SampleAllLight(e->view, &rng);
+    float* o = out10 + 10 * i;
+    o[0] = ls.pos.x; o[1] = ls.pos.y; o[2] = ls.pos.z;
+    o[3] = ls.normal.x; o[4] = ls.normal.y; o[5] = ls.normal.z;
+    o[6] = ls.emission.x; o[7] = ls.emission.y; o[8] = ls.emission.z;
+    o[9] = ls.pdf;
+  }
+  return 0;
+}
+
+int emul_eval_closure(int op, const float* params, const float* in, uint32_t in_stride, uint64_t n, float* out,
+                      uint32_t out_stride) {
+  for (uint64_t i = 0; i < n; ++i) KatEval(op, params, in + size_t(i) * in_stride, out + size_t(i) * out_stride, out_stride);
+  return 0;
+}
+
+// Render() on the host cores with the GPU's path numbering: path (pixel p, sample s) = pcg32_srandom(seed + s, p)
+int emul_render(void* h, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed, uint32_t sample_offset,
+                uint32_t sample_stride, float* rgba, uint32_t* count, uint64_t* counts3) {
+  Emul* e = static_cast<Emul*>(h);
+  float cam[8];
+  pbrhost::MakeCamera(e->scene.bmin, e->scene.bmax, width, height, cam);
+  const uint64_t npix = uint64_t(width) * height;
+  memset(rgba, 0, sizeof(float) * 4 * npix);
+  memset(count, 0, sizeof(uint32_t) * npix);
+  std::atomic<uint64_t> c0(0), c1(0), c2(0);
+  ParallelFor(npix, [&](uint64_t pixel) {
+    const uint32_t x = uint32_t(pixel % width), y = uint32_t(pixel / width);
+    uint64_t rc[3] = {0, 0, 0};
+    for (uint32_t sidx = sample_offset; sidx < spp; sidx += sample_stride) {
+      Pcg32 rng;
+      pcg32_srandom(&rng, seed + sidx, pixel);
+      const float jx = Draw(&rng), jy = Draw(&rng);
+      const float tx = cam[3] + cam[6] * (float(x) + jx);
+      const float ty = cam[4] - cam[7] * (float(y) + jy);
+      float dx = tx - cam[0], dy = ty - cam[1], dz = cam[5] - cam[2];
+      const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+      RayT ray;
+      ray.o = vec3(cam[0], cam[1], cam[2]);
+      ray.d = vec3(dx * inv, dy * inv, dz * inv);
+      ray.tmin = 0.f;
+      ray.tmax = kInf;
+      const vec3 L = PathRadiance(e->view, ray, &rng, rc);
+      rgba[4 * pixel] += L.x; rgba[4 * pixel + 1] += L.y; rgba[4 * pixel + 2] += L.z; rgba[4 * pixel + 3] += 1.0f;
+      count[pixel]++;
+    }
+    c0 += rc[0]; c1 += rc[1]; c2 += rc[2];
+  });
+  if (counts3) { counts3[0] = c0; counts3[1] = c1; counts3[2] = c2; }
+  return 0;
+}
+
+}  // extern "C"
