@@ -72,9 +72,9 @@ struct Device {
   DevBuf<pbr::LightRec> lights;
   pbr::SceneView view;
   // wave
-  DevBuf<float4> ray_o, ray_d, hit, thr, rad, sh_o, sh_d, sh_c;
+  DevBuf<float4> ray_o, ray_d, hit, thr, rad, sh_o, sh_d, sh_c, walk_a, walk_b, walk_c, walk_d;
   DevBuf<ulonglong2> rng;
-  DevBuf<uint32_t> q0, q1, q_surface, q_hair, q_sss, counters;
+  DevBuf<uint32_t> q0, q1, q_surface, q_hair, q_sss, q_walk0, q_walk1, walk_n, q_done0, q_done1, pixel, counters;
   DevBuf<unsigned long long> stats;
   pbr::WaveState wave;
   uint32_t wave_capacity = 0;
@@ -92,6 +92,8 @@ struct Device {
     lprim_cdf.Free(); lights.Free();
     ray_o.Free(); ray_d.Free(); hit.Free(); thr.Free(); rad.Free(); sh_o.Free(); sh_d.Free(); sh_c.Free();
     rng.Free(); q0.Free(); q1.Free(); q_surface.Free(); q_hair.Free(); q_sss.Free(); counters.Free(); stats.Free();
+    walk_a.Free(); walk_b.Free(); walk_c.Free(); walk_d.Free(); q_walk0.Free(); q_walk1.Free(); walk_n.Free();
+    q_done0.Free(); q_done1.Free(); pixel.Free();
     rgba.Free(); count.Free();
     if (h_counters) cudaFreeHost(h_counters);
     if (h_stats) cudaFreeHost(h_stats);
@@ -119,6 +121,7 @@ using pbr::SceneView;
 using pbr::WaveState;
 
 constexpr int kBlock = 128;
+constexpr uint32_t kSssBouncesPerLaunch = 64;   // see SssWalkKernel
 int PersistentGrid(const Device& d, int blocks_per_sm) { return d.sm_count * blocks_per_sm; }
 
 int UploadScene(pbrgpu_ctx* ctx, Device& d) {
@@ -169,6 +172,12 @@ int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
     CUDA_TRY(ctx, d.q0.Alloc(capacity)); CUDA_TRY(ctx, d.q1.Alloc(capacity));
     CUDA_TRY(ctx, d.q_surface.Alloc(capacity)); CUDA_TRY(ctx, d.q_hair.Alloc(capacity));
     CUDA_TRY(ctx, d.q_sss.Alloc(capacity));
+    CUDA_TRY(ctx, d.q_walk0.Alloc(capacity)); CUDA_TRY(ctx, d.q_walk1.Alloc(capacity));
+    CUDA_TRY(ctx, d.walk_a.Alloc(capacity)); CUDA_TRY(ctx, d.walk_b.Alloc(capacity));
+    CUDA_TRY(ctx, d.walk_c.Alloc(capacity)); CUDA_TRY(ctx, d.walk_d.Alloc(capacity));
+    CUDA_TRY(ctx, d.walk_n.Alloc(capacity));
+    CUDA_TRY(ctx, d.q_done0.Alloc(capacity)); CUDA_TRY(ctx, d.q_done1.Alloc(capacity));
+    CUDA_TRY(ctx, d.pixel.Alloc(capacity));
     CUDA_TRY(ctx, d.sh_o.Alloc(size_t(2) * capacity)); CUDA_TRY(ctx, d.sh_d.Alloc(size_t(2) * capacity));
     CUDA_TRY(ctx, d.sh_c.Alloc(size_t(2) * capacity));
     d.wave_capacity = capacity;
@@ -180,7 +189,11 @@ int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
   WaveState& w = d.wave;
   w.ray_o = d.ray_o.ptr; w.ray_d = d.ray_d.ptr; w.hit = d.hit.ptr; w.thr = d.thr.ptr; w.rad = d.rad.ptr;
   w.rng = d.rng.ptr; w.q_active[0] = d.q0.ptr; w.q_active[1] = d.q1.ptr; w.q_surface = d.q_surface.ptr;
-  w.q_hair = d.q_hair.ptr; w.q_sss = d.q_sss.ptr; w.sh_o = d.sh_o.ptr; w.sh_d = d.sh_d.ptr; w.sh_c = d.sh_c.ptr;
+  w.q_hair = d.q_hair.ptr; w.q_sss = d.q_sss.ptr;
+  w.q_walk[0] = d.q_walk0.ptr; w.q_walk[1] = d.q_walk1.ptr; w.walk_a = d.walk_a.ptr; w.walk_b = d.walk_b.ptr;
+  w.walk_c = d.walk_c.ptr; w.walk_d = d.walk_d.ptr; w.walk_n = d.walk_n.ptr;
+  w.q_done[0] = d.q_done0.ptr; w.q_done[1] = d.q_done1.ptr; w.pixel = d.pixel.ptr;
+  w.sh_o = d.sh_o.ptr; w.sh_d = d.sh_d.ptr; w.sh_c = d.sh_c.ptr;
   w.counters = d.counters.ptr; w.stats = d.stats.ptr; w.capacity = d.wave_capacity;
   return PBRGPU_OK;
 }
@@ -190,29 +203,50 @@ struct LoopTimers {
   uint64_t launches = 0;
 };
 
-// Runs bounce iterations until no path is alive.  n_active paths are in q_active[0].  max_iterations == 1 is the
-// single-vertex mode of pbrgpu_shade.
-int RunWave(pbrgpu_ctx* ctx, Device& d, uint32_t n_active, uint32_t max_iterations, pbr::ShadeFlags flags,
-            LoopTimers* tm, const volatile int* cancel) {
+// Runs iterations on the slot pool until nothing is in flight and (when regenerating) the frame has no samples left.
+// Entry state: counters/queues set up by ResetPoolKernel (frame) or InitPathsFromRaysKernel (hooks).
+// max_iterations == 1 is the single-vertex mode of pbrgpu_shade.
+int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t max_iterations, pbr::ShadeFlags flags,
+            LoopTimers* tm, const volatile int* cancel, size_t* finish_pass, size_t pass_offset, size_t pass_stride,
+            size_t pass_cap) {
   cudaStream_t st = d.stream;
   const SceneView& s = d.view;
   const WaveState& w = d.wave;
   uint32_t parity = 0;
   const int grid_trace = PersistentGrid(d, 8), grid_shade = PersistentGrid(d, 4);
-  for (uint32_t it = 0; n_active > 0 && it < max_iterations; ++it) {
+  // state after the set-up kernel (host knows it): hooks start with n active slots, frames with N retired slots
+  bool have_active = (frame == nullptr), have_walk = false, have_done = (frame != nullptr);
+  for (uint32_t it = 0; (have_active || have_walk || have_done) && it < max_iterations; ++it) {
     if (cancel && *cancel) break;
     const uint32_t next = parity ^ 1u;
-    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters);
-    pbr::TraceClosestKernel<<<grid_trace, kBlock, 0, st>>>(s, w, w.q_active[parity], n_active);
+    // single-vertex mode lets the walk run to its end inside the one iteration
+    const uint32_t walk_budget = (max_iterations == 1u) ? 0x7fffffffu : kSssBouncesPerLaunch;
+    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, parity);
+    tm->launches += 1;
+    if (frame && have_done) {
+      pbr::RegenerateKernel<<<grid_shade, 256, 0, st>>>(w, *frame, parity);
+      tm->launches += 1;
+    }
+    pbr::TraceClosestKernel<<<grid_trace, kBlock, 0, st>>>(s, w, parity);
     pbr::ShadeSurfaceKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
     if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
-    pbr::SssWalkKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next);
+    pbr::SssWalkKernel<<<grid_shade, kBlock, 0, st>>>(s, w, parity, walk_budget);
     pbr::TraceAnyKernel<<<grid_trace, kBlock, 0, st>>>(s, w);
-    tm->launches += s.num_curves ? 6 : 5;
+    tm->launches += s.num_curves ? 5 : 4;
     CUDA_TRY(ctx, cudaMemcpyAsync(d.h_counters, w.counters, sizeof(uint32_t) * pbr::kCounterCount,
                                   cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d.h_stats, w.stats, sizeof(unsigned long long) * pbr::kStatCount,
+                                  cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    n_active = d.h_counters[pbr::kNumActiveNext];
+    have_active = d.h_counters[pbr::kNumActive0 + next] > 0;
+    have_walk = d.h_counters[pbr::kNumWalk0 + next] > 0;
+    // retired slots only matter while they can be accumulated (frame mode); hooks read rad[] directly
+    have_done = frame && d.h_counters[pbr::kNumDone0 + next] > 0;
+    if (frame && finish_pass) {
+      const size_t passes = size_t(d.h_stats[pbr::kStatRetired] / frame->npix);
+      const size_t global = std::min(pass_cap, pass_offset + passes * pass_stride);
+      if (global > *finish_pass) *finish_pass = global;
+    }
     parity = next;
   }
   CUDA_TRY(ctx, cudaGetLastError());
@@ -226,11 +260,13 @@ int FetchStats(pbrgpu_ctx* ctx, Device& d) {
   return PBRGPU_OK;
 }
 
-uint32_t ChooseWaveSpp(const pbrgpu_ctx* ctx, uint64_t npix, uint32_t local_spp) {
-  if (ctx->wave_spp) return std::max(1u, std::min(ctx->wave_spp, local_spp));
-  const uint64_t target_paths = 4ull << 20;   // ~4 Mi paths in flight: ~1 GB of wave state
-  uint64_t s = std::max<uint64_t>(1, target_paths / std::max<uint64_t>(1, npix));
-  return uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(s, local_spp)));
+// number of path slots kept in flight: enough to fill the GPU many times over (each iteration costs one host
+// round-trip), small enough that the SoA state (~300 B/slot) streams through HBM quickly
+uint32_t ChoosePoolSize(const pbrgpu_ctx* ctx, uint64_t npix, uint64_t total_samples) {
+  uint64_t n = ctx->wave_spp ? uint64_t(ctx->wave_spp) * npix : (4ull << 20);
+  n = std::min<uint64_t>(n, total_samples);
+  n = std::min<uint64_t>(n, 64ull << 20);
+  return uint32_t(std::max<uint64_t>(n, 1));
 }
 
 // the body of Render() on one device; result left in d.rgba / d.count
@@ -247,42 +283,34 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   CUDA_TRY(ctx, cudaMemsetAsync(d.rgba.ptr, 0, sizeof(float4) * npix, d.stream));
   CUDA_TRY(ctx, cudaMemsetAsync(d.count.ptr, 0, sizeof(uint32_t) * npix, d.stream));
   if (local_spp == 0) { CUDA_TRY(ctx, cudaStreamSynchronize(d.stream)); return PBRGPU_OK; }
-  const uint32_t wave_spp = ChooseWaveSpp(ctx, npix, local_spp);
-  if (uint64_t(wave_spp) * npix > 0x7fffffffull) { ctx->error = "pbrgpu_render: wave too large"; return PBRGPU_ERR_INVALID; }
-  int rc = EnsureWave(ctx, d, wave_spp * npix);
+  const uint64_t total = npix64 * local_spp;
+  const uint32_t n_slots = ChoosePoolSize(ctx, npix, total);
+  int rc = EnsureWave(ctx, d, n_slots);
   if (rc != PBRGPU_OK) return rc;
   CUDA_TRY(ctx, cudaMemsetAsync(d.stats.ptr, 0, sizeof(unsigned long long) * pbr::kStatCount, d.stream));
 
-  pbr::CameraParams cam;
+  pbr::FrameParams frame;
   float c8[8];
   pbrhost::MakeCamera(ctx->host.bmin, ctx->host.bmax, width, height, c8);
-  cam.eye[0] = c8[0]; cam.eye[1] = c8[1]; cam.eye[2] = c8[2];
-  cam.x_corner = c8[3]; cam.y_corner = c8[4]; cam.z_corner = c8[5]; cam.dx = c8[6]; cam.dy = c8[7];
-  cam.width = width; cam.height = height;
+  frame.cam.eye[0] = c8[0]; frame.cam.eye[1] = c8[1]; frame.cam.eye[2] = c8[2];
+  frame.cam.x_corner = c8[3]; frame.cam.y_corner = c8[4]; frame.cam.z_corner = c8[5];
+  frame.cam.dx = c8[6]; frame.cam.dy = c8[7];
+  frame.cam.width = width; frame.cam.height = height;
+  frame.npix = npix;
+  frame.total_samples = total;
+  frame.seed = seed;
+  frame.first_sample = sample_offset;
+  frame.sample_stride = sample_stride;
+  frame.rgba = d.rgba.ptr;
+  frame.count = d.count.ptr;
 
+  pbr::ResetPoolKernel<<<(std::max<uint32_t>(n_slots, 64) + 255) / 256, 256, 0, d.stream>>>(d.wave, n_slots);
+  tm->launches++;
   pbr::ShadeFlags flags;
   flags.skip_emission_and_roulette = 0;
-  for (uint32_t done = 0; done < local_spp;) {
-    if (cancel && *cancel) break;
-    const uint32_t batch = std::min(wave_spp, local_spp - done);
-    const uint32_t n_paths = batch * npix;
-    const uint32_t first_sample = sample_offset + done * sample_stride;
-    pbr::GenCameraRaysKernel<<<(n_paths + 255) / 256, 256, 0, d.stream>>>(d.wave, cam, npix, n_paths, seed,
-                                                                          first_sample, sample_stride);
-    tm->launches++;
-    rc = RunWave(ctx, d, n_paths, 0xffffffffu, flags, tm, cancel);
-    if (rc != PBRGPU_OK) return rc;
-    if (cancel && *cancel) break;   // a cancelled wave is dropped: only whole passes are accumulated
-    pbr::AccumulateKernel<<<(npix + 255) / 256, 256, 0, d.stream>>>(d.wave, d.rgba.ptr, d.count.ptr, npix, batch);
-    tm->launches++;
-    done += batch;
-    if (finish_pass) {
-      const size_t global_done = std::min<size_t>(spp, size_t(sample_offset) + size_t(done) * sample_stride);
-      if (global_done > *finish_pass) *finish_pass = global_done;
-    }
-  }
+  rc = RunPool(ctx, d, &frame, 0xffffffffu, flags, tm, cancel, finish_pass, sample_offset, sample_stride, spp);
+  if (rc != PBRGPU_OK) return rc;
   CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
-  CUDA_TRY(ctx, cudaGetLastError());
   return FetchStats(ctx, d);
 }
 
@@ -529,7 +557,7 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
     if (finish_pass) {
       size_t m = spp;
       for (uint32_t k = 0; k < ndev; ++k) m = std::min(m, progress[k]);
-      *finish_pass = m;
+      *finish_pass = m;   // every device finished at least this many of the interleaved passes
     }
   }
   for (uint32_t k = 0; k < ndev; ++k) if (rcs[k] != PBRGPU_OK) return rcs[k];
@@ -717,7 +745,7 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
     dout.Free(); dr.Free(); ds.Free();
     return PBRGPU_OK;
   }
-  pbr::InitPathsFromRaysKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);
+  pbr::InitPathsFromRaysKernel<<<(std::max(n32, 64u) + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);
   pbr::ShadeFlags flags;
   flags.skip_emission_and_roulette = (mode == 1) ? 1u : 0u;
   std::vector<float> face_t;
@@ -725,15 +753,17 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
     // the hook reports face direction and t of the first hit: run the closest-hit stage alone first
     DevBuf<float> dface;
     CUDA_TRY(ctx, dface.Alloc(2 * n));
-    pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters);
-    pbr::TraceClosestKernel<<<PersistentGrid(d, 8), kBlock, 0, d.stream>>>(d.view, d.wave, d.wave.q_active[0], n32);
+    pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters, 0u);
+    pbr::TraceClosestKernel<<<PersistentGrid(d, 8), kBlock, 0, d.stream>>>(d.view, d.wave, 0u);
     SurfaceFaceKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.view, d.wave, n32, dface.ptr);
+    // restore the entry state for the real iteration below
+    pbr::InitPathsFromRaysKernel<<<(std::max(n32, 64u) + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);
     face_t.resize(2 * n);
     CUDA_TRY(ctx, cudaMemcpyAsync(face_t.data(), dface.ptr, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, d.stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
     dface.Free();
   }
-  rc = RunWave(ctx, d, n32, mode == 1 ? 1u : 0xffffffffu, flags, &tm, nullptr);
+  rc = RunPool(ctx, d, nullptr, mode == 1 ? 1u : 0xffffffffu, flags, &tm, nullptr, nullptr, 0, 1, 0);
   if (rc != PBRGPU_OK) { dr.Free(); ds.Free(); return rc; }
   std::vector<float4> rad(n), thr, ro, rdv;
   CUDA_TRY(ctx, cudaMemcpyAsync(rad.data(), d.rad.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));

@@ -1,24 +1,34 @@
-// Wavefront path tracer kernels (sm_100a).  One launch of Render() is organised as waves of N paths whose state
-// lives in HBM as structure-of-arrays (every field a float4 / 16-byte record so each lane issues 128-bit loads and a
-// warp touches contiguous 512-byte spans when the queue is dense):
+// Wavefront path tracer kernels (sm_100a).
+//
+// Render() keeps a POOL of N path slots resident in HBM for the whole frame.  A slot's state is structure-of-arrays,
+// every field a 16-byte record so each lane issues one 128-bit load per field and a warp reading a dense queue
+// touches contiguous 512-byte spans:
 //
 //   ray_o[N]  (org.xyz, tmin)      ray_d[N]  (dir.xyz, tmax)      hit[N]  (t, u, v, leaf-order primitive | curve flag)
 //   thr[N]    (throughput.rgb, pdf of the last BSDF sample)       rad[N]  (radiance.rgb, depth)
-//   rng[N]    (PCG32 state, inc)
+//   rng[N]    (PCG32 state, inc)   pixel[N]  (u32)                walk_a..d[N], walk_n[N]  parked random walk
 //
-// and index queues (u32 path ids) compacted with warp ballots + one atomicAdd per warp:
+// Index queues (u32 slot ids) are compacted with warp ballots + one atomicAdd per warp:
 //
-//   q_active[2]  paths that still need a closest-hit query (ping-pong)
+//   q_active[2]  slots that need a closest-hit query (ping-pong between iterations)
 //   q_surface    hit a triangle-type material (or none): emission + roulette + Principled vertex
 //   q_hair       hit a hair material
-//   q_sss        Principled vertex selected the random-walk closure
-//   shadow queue (ray + contribution + path id): NEE any-hit queries
+//   q_sss        the Principled vertex selected the random-walk closure this iteration
+//   q_walk[2]    random walks that used up their bounce budget and continue next iteration (ping-pong)
+//   q_done[2]    paths that ended this iteration; consumed at the start of the next one (ping-pong)
+//   shadow queue (ray, contribution, slot): NEE any-hit queries
 //
-// One bounce iteration = trace_closest -> shade_surface, shade_hair -> sss_walk -> trace_any.  All kernels are
-// persistent: the grid is a fixed multiple of the SM count and warps pull 32-entry batches from the queue with an
-// atomic counter, so queue lengths never leave the device inside an iteration.
-// Replaces the per-pixel loop of the reference (src/render.cc:24-90,125-190) — see device/shade.cuh for the per-vertex
-// functions and their citations.
+// One iteration:
+//   begin -> regenerate -> trace_closest -> shade_surface, shade_hair -> sss_walk -> trace_any
+// `regenerate` retires every slot of q_done (adds its radiance to its pixel: rgba += (L,1), count += 1, the sums
+// RenderLayer holds) and immediately starts the next camera sample in the same slot, so the pool stays full until the
+// frame runs out of samples: long random walks and deep paths never leave the GPU idle, and the number of iterations
+// is (total rays) / N instead of (longest path).  Every kernel is persistent — a grid that is a fixed multiple of
+// the SM count, warps pulling 32-entry batches with an atomic counter — and reads its queue length from device
+// memory, so nothing but one small counter block crosses PCIe per iteration.
+//
+// Replaces the per-pixel loops of the reference (src/render.cc:24-90,125-190); the per-vertex functions and their
+// citations are in device/shade.cuh.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -26,13 +36,21 @@
 
 namespace pbr {
 
-// device-side counters, one cache line apart is not needed: touched once per warp
 enum Counter {
-  kNumActiveNext = 0, kNumSurface, kNumHair, kNumSss, kNumShadow,
-  kFetchTrace, kFetchSurface, kFetchHair, kFetchSss, kFetchShadow,
+  kNumActive0 = 0, kNumActive1,   // length of q_active[parity]
+  kNumWalk0, kNumWalk1,           // length of q_walk[parity]
+  kNumDone0, kNumDone1,           // length of q_done[parity]
+  kNumSurface, kNumHair, kNumSss, kNumShadow,
+  kFetchRegen, kFetchTrace, kFetchSurface, kFetchHair, kFetchSss, kFetchShadow,
   kCounterCount
 };
-enum Stat { kStatClosest = 0, kStatShadow, kStatSss, kStatNodes, kStatPrims, kStatCount };
+// 64-bit counters that live for a whole frame
+enum Stat {
+  kStatClosest = 0, kStatShadow, kStatSss, kStatNodes, kStatPrims,
+  kStatNextSample,      // next camera sample id to hand out
+  kStatRetired,         // camera samples accumulated into the frame so far
+  kStatCount
+};
 
 struct WaveState {
   float4* ray_o;
@@ -41,10 +59,18 @@ struct WaveState {
   float4* thr;
   float4* rad;
   ulonglong2* rng;
+  uint32_t* pixel;
   uint32_t* q_active[2];
+  uint32_t* q_walk[2];
+  uint32_t* q_done[2];
   uint32_t* q_surface;
   uint32_t* q_hair;
   uint32_t* q_sss;
+  float4* walk_a;                // parked walk: (sigma_t.xyz, throughput.x)
+  float4* walk_b;                //              (sigma_s.xyz, throughput.y)
+  float4* walk_c;                //              (ray.org.xyz, throughput.z)
+  float4* walk_d;                //              (ray.dir.xyz, tmin)
+  uint32_t* walk_n;              //              bounce count
   float4* sh_o;
   float4* sh_d;
   float4* sh_c;
@@ -53,7 +79,9 @@ struct WaveState {
   uint32_t capacity;
 };
 
-// ---- warp-aggregated queue append: one atomicAdd per warp
+constexpr uint32_t kNoPixel = 0xFFFFFFFFu;
+
+// ---- warp-aggregated queue append: one atomicAdd per warp.  Must be reached by all 32 lanes.
 __device__ __forceinline__ uint32_t WarpAppend(uint32_t* counter, bool pred) {
   const unsigned mask = __ballot_sync(0xffffffffu, pred);
   if (mask == 0u) return 0u;
@@ -81,10 +109,11 @@ __device__ __forceinline__ RayT LoadRay(const WaveState& w, uint32_t p) {
   r.d = vec3(d.x, d.y, d.z); r.tmax = d.w;
   return r;
 }
-__device__ __forceinline__ void StoreRay(const WaveState& w, uint32_t p, const vec3& o, const vec3& d, float tmin,
-                                         float tmax) {
-  w.ray_o[p] = make_float4(o.x, o.y, o.z, tmin);
-  w.ray_d[p] = make_float4(d.x, d.y, d.z, tmax);
+__device__ __forceinline__ HitT LoadHit(const WaveState& w, uint32_t p) {
+  const float4 h4 = w.hit[p];
+  HitT hit;
+  hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
+  return hit;
 }
 
 __device__ __forceinline__ void PushShadow(const WaveState& w, const ShadowRequest& req, const vec3& throughput,
@@ -98,39 +127,120 @@ __device__ __forceinline__ void PushShadow(const WaveState& w, const ShadowReque
   }
 }
 
-// ------------------------------------------------------------------------------------------------ camera
+// where a slot goes after its vertex: next closest-hit query, or retirement
+__device__ __forceinline__ void RouteSlot(const WaveState& w, uint32_t next_parity, uint32_t p, bool to_next,
+                                          bool to_done) {
+  const uint32_t a = WarpAppend(&w.counters[kNumActive0 + next_parity], to_next);
+  if (to_next) w.q_active[next_parity][a] = p;
+  const uint32_t b = WarpAppend(&w.counters[kNumDone0 + next_parity], to_done);
+  if (to_done) w.q_done[next_parity][b] = p;
+}
+
+// ------------------------------------------------------------------------------------------------ iteration set-up
+// zeroes every per-iteration counter; the three ping-pong lists keep the half that this iteration consumes
+__global__ void BeginIterationKernel(uint32_t* counters, uint32_t cur_parity) {
+  const uint32_t i = threadIdx.x;
+  if (i >= kCounterCount) return;
+  const uint32_t keep0 = kNumActive0 + cur_parity, keep1 = kNumWalk0 + cur_parity, keep2 = kNumDone0 + cur_parity;
+  if (i == keep0 || i == keep1 || i == keep2) return;
+  counters[i] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------ camera + retire
 // RenderingTile's ray generation (src/render.cc:160-171): target = corner + d*(pixel + xi); the two jitter draws
-// are the first two numbers of the path's stream.  cam: eye.xyz, x_corner, y_corner, z_corner, dx, dy.
+// are the first two numbers of the path's stream.
 struct CameraParams {
   float eye[3], x_corner, y_corner, z_corner, dx, dy;
   uint32_t width, height;
 };
+struct FrameParams {
+  CameraParams cam;
+  uint32_t npix;
+  unsigned long long total_samples;   // camera samples this device renders in this call = npix * local_spp
+  uint64_t seed;
+  uint32_t first_sample;      // global index of local sample 0
+  uint32_t sample_stride;     // global sample index = first_sample + local * stride
+  float4* rgba;               // frame accumulators (sums)
+  uint32_t* count;
+};
 
-__global__ void GenCameraRaysKernel(WaveState w, CameraParams cam, uint32_t npix, uint32_t n_paths,
-                                    uint64_t seed, uint32_t first_sample, uint32_t sample_stride) {
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_paths) return;
-  const uint32_t s_local = p / npix, pixel = p - s_local * npix;
-  const uint32_t x = pixel % cam.width, y = pixel / cam.width;
+__device__ __forceinline__ void StartCameraPath(const WaveState& w, const FrameParams& f, uint32_t p,
+                                                unsigned long long id) {
+  const uint32_t s_local = uint32_t(id / f.npix), pixel = uint32_t(id - (unsigned long long)s_local * f.npix);
+  const uint32_t x = pixel % f.cam.width, y = pixel / f.cam.width;
   Pcg32 rng;
-  pcg32_srandom(&rng, seed + uint64_t(first_sample + s_local * sample_stride), uint64_t(pixel));
+  pcg32_srandom(&rng, f.seed + uint64_t(f.first_sample) + uint64_t(s_local) * f.sample_stride, uint64_t(pixel));
   const float jx = Draw(&rng), jy = Draw(&rng);
-  const float tx = cam.x_corner + cam.dx * (float(x) + jx);
-  const float ty = cam.y_corner - cam.dy * (float(y) + jy);
-  float dx = tx - cam.eye[0], dy = ty - cam.eye[1], dz = cam.z_corner - cam.eye[2];
+  const float tx = f.cam.x_corner + f.cam.dx * (float(x) + jx);
+  const float ty = f.cam.y_corner - f.cam.dy * (float(y) + jy);
+  float dx = tx - f.cam.eye[0], dy = ty - f.cam.eye[1], dz = f.cam.z_corner - f.cam.eye[2];
   const float inv_norm = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);   // Normalize (render.cc:243-249)
   dx *= inv_norm; dy *= inv_norm; dz *= inv_norm;
-  w.ray_o[p] = make_float4(cam.eye[0], cam.eye[1], cam.eye[2], 0.0f);
+  w.ray_o[p] = make_float4(f.cam.eye[0], f.cam.eye[1], f.cam.eye[2], 0.0f);
   w.ray_d[p] = make_float4(dx, dy, dz, kInf);
   w.thr[p] = make_float4(1.f, 1.f, 1.f, 0.f);
   w.rad[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
   w.rng[p] = make_ulonglong2(rng.state, rng.inc);
-  w.q_active[0][p] = p;
+  w.pixel[p] = pixel;
 }
 
-// caller-supplied rays + seeds (pbrgpu_radiance / pbrgpu_shade hooks)
+// Retire the slots of q_done[cur] (render.cc:175-183: rgba += (L, 1), count += 1) and restart them on the next
+// camera samples.  Several samples of one pixel can retire in the same iteration, hence atomics.
+__global__ void __launch_bounds__(256) RegenerateKernel(WaveState w, FrameParams f, uint32_t cur_parity) {
+  const uint32_t n = w.counters[kNumDone0 + cur_parity];
+  unsigned long long retired = 0;
+  for (;;) {
+    const uint32_t i = WarpFetch(&w.counters[kFetchRegen]);
+    if (__all_sync(0xffffffffu, i >= n)) break;
+    const bool valid = i < n;
+    uint32_t p = 0;
+    if (valid) {
+      p = w.q_done[cur_parity][i];
+      const uint32_t pixel = w.pixel[p];
+      if (pixel != kNoPixel) {
+        const float4 r = w.rad[p];
+        float* dst = reinterpret_cast<float*>(&f.rgba[pixel]);
+        atomicAdd(dst + 0, r.x);
+        atomicAdd(dst + 1, r.y);
+        atomicAdd(dst + 2, r.z);
+        atomicAdd(dst + 3, 1.0f);
+        atomicAdd(&f.count[pixel], 1u);
+        w.pixel[p] = kNoPixel;
+        ++retired;
+      }
+    }
+    // hand out new sample ids, one atomic per warp
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (mask) {
+      const int leader = __ffs(mask) - 1;
+      if (lane == leader) base = atomicAdd(&w.stats[kStatNextSample], (unsigned long long)__popc(mask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+    }
+    const unsigned long long id = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+    const bool start = valid && id < f.total_samples;
+    if (start) StartCameraPath(w, f, p, id);
+    const uint32_t a = WarpAppend(&w.counters[kNumActive0 + cur_parity], start);
+    if (start) w.q_active[cur_parity][a] = p;
+  }
+  if (retired) atomicAdd(&w.stats[kStatRetired], retired);
+}
+
+// all slots idle and queued for (re)generation: the state a frame starts from
+__global__ void ResetPoolKernel(WaveState w, uint32_t n_slots) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_slots) {
+    w.pixel[p] = kNoPixel;
+    w.q_done[0][p] = p;
+  }
+  if (p < kCounterCount) w.counters[p] = (p == kNumDone0) ? n_slots : 0u;
+}
+
+// caller-supplied rays + seeds (pbrgpu_radiance / pbrgpu_shade hooks): slot i = path i = pixel i, no regeneration
 __global__ void InitPathsFromRaysKernel(WaveState w, const float4* rays, const uint64_t* seeds, uint32_t n) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < kCounterCount) w.counters[p] = (p == kNumActive0) ? n : 0u;
   if (p >= n) return;
   w.ray_o[p] = rays[2 * p];
   w.ray_d[p] = rays[2 * p + 1];
@@ -139,18 +249,16 @@ __global__ void InitPathsFromRaysKernel(WaveState w, const float4* rays, const u
   w.thr[p] = make_float4(1.f, 1.f, 1.f, 0.f);
   w.rad[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
   w.rng[p] = make_ulonglong2(rng.state, rng.inc);
+  w.pixel[p] = p;
   w.q_active[0][p] = p;
 }
 
-// ------------------------------------------------------------------------------------------------ iteration set-up
-__global__ void BeginIterationKernel(uint32_t* counters) {
-  if (threadIdx.x < kCounterCount) counters[threadIdx.x] = 0u;
-}
-
 // ------------------------------------------------------------------------------------------------ closest hit
-// Scene::TraceFirstHit1 for every active path; routes the path by the material kind of what it hit.
-__global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState w, const uint32_t* __restrict__ queue,
-                                                          uint32_t n) {
+// Scene::TraceFirstHit1 for every active slot; routes it by the material kind of what it hit, retires it on a miss.
+__global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState w, uint32_t cur_parity) {
+  const uint32_t n = w.counters[kNumActive0 + cur_parity];
+  const uint32_t* __restrict__ queue = w.q_active[cur_parity];
+  const uint32_t next_parity = cur_parity ^ 1u;
   unsigned long long rays = 0;
   for (;;) {
     const uint32_t slot = WarpFetch(&w.counters[kFetchTrace]);
@@ -159,13 +267,14 @@ __global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState
     uint32_t p = 0;
     HitT hit;
     hit.prim = kInvalid;
-    int kind = -1;   // -1 miss, 0/1 surface queue, 2 hair queue
+    int kind = -1;   // -1 nothing, 0 miss, 1 surface queue, 2 hair queue
     if (valid) {
       p = queue[slot];
       const RayT ray = LoadRay(w, p);
       TraceClosest<false>(s, ray, &hit, nullptr);
       ++rays;
       w.hit[p] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
+      kind = 0;
       if (hit.prim != kInvalid) {
         uint32_t mat;
         if (hit.prim & kCurveFlag) mat = s.curve_ids[s.curve_prim[hit.prim & ~kCurveFlag]].w;
@@ -177,6 +286,8 @@ __global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState
     if (kind == 1) w.q_surface[a] = p;
     const uint32_t b = WarpAppend(&w.counters[kNumHair], kind == 2);
     if (kind == 2) w.q_hair[b] = p;
+    const uint32_t c = WarpAppend(&w.counters[kNumDone0 + next_parity], kind == 0);
+    if (kind == 0) w.q_done[next_parity][c] = p;
   }
   if (rays) atomicAdd(&w.stats[kStatClosest], rays);
 }
@@ -186,13 +297,14 @@ struct ShadeFlags {
   uint32_t skip_emission_and_roulette;   // pbrgpu_shade hook: call Shader() only
 };
 
-__device__ __forceinline__ void CommitVertex(const WaveState& w, uint32_t p, const VertexResult& vr, vec3 throughput,
-                                             const vec3& L, uint32_t depth, const Pcg32& rng, uint32_t next_parity) {
+__device__ __forceinline__ void CommitVertex(const WaveState& w, uint32_t p, const VertexResult& vr,
+                                             const vec3& throughput, const vec3& L, uint32_t depth, const Pcg32& rng) {
   const vec3 new_thr = vr.throughput * throughput;                     // render.cc:80
   w.thr[p] = make_float4(new_thr.x, new_thr.y, new_thr.z, vr.pdf);
   w.rad[p] = make_float4(L.x, L.y, L.z, __uint_as_float(depth + 1u));
   w.rng[p] = make_ulonglong2(rng.state, rng.inc);
-  StoreRay(w, p, vr.P, vr.wi, 1e-3f, kInf);                            // render.cc:83-86
+  w.ray_o[p] = make_float4(vr.P.x, vr.P.y, vr.P.z, 1e-3f);             // render.cc:83-86
+  w.ray_d[p] = make_float4(vr.wi.x, vr.wi.y, vr.wi.z, kInf);
 }
 
 // emission + MIS, roulette, material dispatch, Principled vertex (everything but the random walk)
@@ -204,16 +316,14 @@ __global__ void __launch_bounds__(128) ShadeSurfaceKernel(SceneView s, WaveState
     if (__all_sync(0xffffffffu, slot >= n)) break;
     const bool valid = slot < n;
     uint32_t p = 0;
-    bool to_sss = false, to_next = false;
+    bool to_sss = false, to_next = false, to_done = false;
     ShadowRequest req;
     req.active = false;
     vec3 throughput(0.f);
     if (valid) {
       p = w.q_surface[slot];
       const RayT ray = LoadRay(w, p);
-      const float4 h4 = w.hit[p];
-      HitT hit;
-      hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
+      const HitT hit = LoadHit(w, p);
       const float4 t4 = w.thr[p];
       const float4 r4 = w.rad[p];
       throughput = vec3(t4.x, t4.y, t4.z);
@@ -228,16 +338,13 @@ __global__ void __launch_bounds__(128) ShadeSurfaceKernel(SceneView s, WaveState
         alive = EmissionAndRoulette(s, ray, hit, si, depth, t4.w, &rng, &L, &throughput);
       if (!alive) {
         w.rad[p] = make_float4(L.x, L.y, L.z, __uint_as_float(depth));
+        to_done = true;
       } else {
         const int kind = MaterialKind(s, si);
         VertexResult vr;
         const vec3 wo = -ray.d;
-        if (kind == 1) {
-          to_sss = PrincipledVertex(s, si, wo, &rng, &vr);
-        } else {
-          AbsorbVertex(wo, si.P, &vr);   // no material (shader.cc:11-17); hair on this queue cannot happen
-          vr.shadow[0].active = false;
-        }
+        if (kind == 1) to_sss = PrincipledVertex(s, si, wo, &rng, &vr);
+        else AbsorbVertex(wo, si.P, &vr);   // no material (shader.cc:11-17)
         req = vr.shadow[0];
         if (to_sss) {
           // the walk runs in its own kernel: park the path with the post-roulette throughput and the rng positioned
@@ -246,16 +353,16 @@ __global__ void __launch_bounds__(128) ShadeSurfaceKernel(SceneView s, WaveState
           w.rad[p] = make_float4(L.x, L.y, L.z, __uint_as_float(depth));
           w.rng[p] = make_ulonglong2(rng.state, rng.inc);
         } else {
-          CommitVertex(w, p, vr, throughput, L, depth, rng, next_parity);
+          CommitVertex(w, p, vr, throughput, L, depth, rng);
           to_next = !IsBlack(vr.throughput * throughput);               // render.cc:31
+          to_done = !to_next;
         }
       }
     }
     PushShadow(w, req, throughput, p);
     const uint32_t a = WarpAppend(&w.counters[kNumSss], to_sss);
     if (to_sss) w.q_sss[a] = p;
-    const uint32_t b = WarpAppend(&w.counters[kNumActiveNext], to_next);
-    if (to_next) w.q_active[next_parity][b] = p;
+    RouteSlot(w, next_parity, p, to_next, to_done);
   }
 }
 
@@ -267,16 +374,14 @@ __global__ void __launch_bounds__(128) ShadeHairKernel(SceneView s, WaveState w,
     if (__all_sync(0xffffffffu, slot >= n)) break;
     const bool valid = slot < n;
     uint32_t p = 0;
-    bool to_next = false;
+    bool to_next = false, to_done = false;
     ShadowRequest req;
     req.active = false;
     vec3 throughput(0.f);
     if (valid) {
       p = w.q_hair[slot];
       const RayT ray = LoadRay(w, p);
-      const float4 h4 = w.hit[p];
-      HitT hit;
-      hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
+      const HitT hit = LoadHit(w, p);
       const float4 t4 = w.thr[p];
       const float4 r4 = w.rad[p];
       throughput = vec3(t4.x, t4.y, t4.z);
@@ -291,39 +396,65 @@ __global__ void __launch_bounds__(128) ShadeHairKernel(SceneView s, WaveState w,
         alive = EmissionAndRoulette(s, ray, hit, si, depth, t4.w, &rng, &L, &throughput);
       if (!alive) {
         w.rad[p] = make_float4(L.x, L.y, L.z, __uint_as_float(depth));
+        to_done = true;
       } else {
         VertexResult vr;
         HairVertex(s, si, -ray.d, &rng, &vr);
         req = vr.shadow[0];
-        CommitVertex(w, p, vr, throughput, L, depth, rng, next_parity);
+        CommitVertex(w, p, vr, throughput, L, depth, rng);
         to_next = !IsBlack(vr.throughput * throughput);
+        to_done = !to_next;
       }
     }
     PushShadow(w, req, throughput, p);
-    const uint32_t b = WarpAppend(&w.counters[kNumActiveNext], to_next);
-    if (to_next) w.q_active[next_parity][b] = p;
+    RouteSlot(w, next_parity, p, to_next, to_done);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ random-walk SSS
-// RandomWalkSubsurface (random-walk-sss.h:227-405) for every parked path.  Walks have wildly different lengths
-// (1 .. 8192 bounces), so lanes are refilled from the queue as soon as their walk ends instead of waiting for the
-// longest walk of the warp: every loop trip runs at most one bounce (= one short closest-hit query) per lane.
-__global__ void __launch_bounds__(128) SssWalkKernel(SceneView s, WaveState w, uint32_t next_parity) {
-  const uint32_t n = w.counters[kNumSss];
+// RandomWalkSubsurface (random-walk-sss.h:227-405).  Walk lengths are wildly uneven (1 .. 8192 bounces; Lucy's red
+// channel has albedo ~1, so neither absorption nor roulette ends a walk early) and every bounce is a dependent
+// short closest-hit query (~10 us of latency), hence:
+//   * lanes are refilled from the queue the moment their walk ends — every loop trip runs at most one bounce per
+//     lane, no lane waits for the longest walk of its warp;
+//   * a walk gets at most `max_bounces` bounces per launch; if it is still inside the medium its 68-byte state is
+//     parked in HBM (walk_a..d, walk_n) and the slot goes to q_walk[next]: the next iteration resumes it first.
+//     A launch therefore never outlives its queue by more than max_bounces bounces, and because the pool is kept
+//     full by regeneration, long walks cost slots, not idle SMs.
+__device__ __forceinline__ void ParkWalk(const WaveState& w, uint32_t p, const SssWalkState& k) {
+  w.walk_a[p] = make_float4(k.sigma_t.x, k.sigma_t.y, k.sigma_t.z, k.throughput.x);
+  w.walk_b[p] = make_float4(k.sigma_s.x, k.sigma_s.y, k.sigma_s.z, k.throughput.y);
+  w.walk_c[p] = make_float4(k.ray.o.x, k.ray.o.y, k.ray.o.z, k.throughput.z);
+  w.walk_d[p] = make_float4(k.ray.d.x, k.ray.d.y, k.ray.d.z, k.ray.tmin);
+  w.walk_n[p] = k.bounce;
+}
+__device__ __forceinline__ void ResumeWalk(const WaveState& w, uint32_t p, SssWalkState* k) {
+  const float4 a = w.walk_a[p], b = w.walk_b[p], c = w.walk_c[p], d = w.walk_d[p];
+  k->sigma_t = vec3(a.x, a.y, a.z);
+  k->sigma_s = vec3(b.x, b.y, b.z);
+  k->throughput = vec3(a.w, b.w, c.w);
+  k->ray.o = vec3(c.x, c.y, c.z);
+  k->ray.d = vec3(d.x, d.y, d.z);
+  k->ray.tmin = d.w;
+  k->ray.tmax = kInf;
+  k->bounce = w.walk_n[p];
+}
+
+__global__ void __launch_bounds__(128) SssWalkKernel(SceneView s, WaveState w, uint32_t cur_parity,
+                                                     uint32_t max_bounces) {
+  const uint32_t next_parity = cur_parity ^ 1u;
+  const uint32_t n_resume = w.counters[kNumWalk0 + cur_parity];
+  const uint32_t n = n_resume + w.counters[kNumSss];
   const int lane = threadIdx.x & 31;
   bool active = false, exhausted = false;
-  uint32_t p = 0;
+  uint32_t p = 0, budget = 0;
   Pcg32 rng;
   SssWalkState walk;
-  Surface entry_si;
-  Frame entry_frame;
-  vec3 throughput(0.f), L(0.f);
-  uint32_t depth = 0;
   unsigned long long rays = 0;
 
   for (;;) {
     // ---- refill idle lanes
+    bool rejected = false;
     const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
     if (want) {
       uint32_t base = 0;
@@ -335,56 +466,72 @@ __global__ void __launch_bounds__(128) SssWalkKernel(SceneView s, WaveState w, u
         if (slot >= n) {
           exhausted = true;
         } else {
-          p = w.q_sss[slot];
-          const RayT ray = LoadRay(w, p);
-          const float4 h4 = w.hit[p];
-          HitT hit;
-          hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
-          const float4 t4 = w.thr[p];
-          const float4 r4 = w.rad[p];
-          throughput = vec3(t4.x, t4.y, t4.z);
-          L = vec3(r4.x, r4.y, r4.z);
-          depth = __float_as_uint(r4.w);
+          const bool resume = slot < n_resume;
+          p = resume ? w.q_walk[cur_parity][slot] : w.q_sss[slot - n_resume];
           const ulonglong2 rs = w.rng[p];
           rng.state = rs.x; rng.inc = rs.y;
-          entry_si = MakeSurface(s, ray, hit);
-          entry_frame = PrincipledFrame(entry_si);
-          const PrincipledBsdf bsdf = SurfaceBsdf(s, entry_si);
-          active = SssBegin(entry_si, entry_frame, bsdf, &rng, &walk);
-          if (!active) {   // walk rejected: the path's throughput becomes 0 and it ends
-            VertexResult vr;
-            vr.P = entry_si.P;
-            FinishPrincipled(entry_frame, vec3(0.f), vec3(0.f), 0.f, &vr);
-            CommitVertex(w, p, vr, throughput, L, depth, rng, next_parity);
+          budget = max_bounces;
+          if (resume) {
+            ResumeWalk(w, p, &walk);
+            active = true;
+          } else {
+            const RayT ray = LoadRay(w, p);
+            const Surface entry_si = MakeSurface(s, ray, LoadHit(w, p));
+            const Frame entry_frame = PrincipledFrame(entry_si);
+            const PrincipledBsdf bsdf = SurfaceBsdf(s, entry_si);
+            active = SssBegin(entry_si, entry_frame, bsdf, &rng, &walk);
+            if (!active) {   // walk rejected: the path's throughput becomes 0 and it ends
+              const float4 t4 = w.thr[p], r4 = w.rad[p];
+              VertexResult vr;
+              vr.P = entry_si.P;
+              FinishPrincipled(entry_frame, vec3(0.f), vec3(0.f), 0.f, &vr);
+              CommitVertex(w, p, vr, vec3(t4.x, t4.y, t4.z), vec3(r4.x, r4.y, r4.z), __float_as_uint(r4.w), rng);
+              rejected = true;
+            }
           }
         }
       }
     }
-    if (__all_sync(0xffffffffu, !active && exhausted)) break;
+    if (__all_sync(0xffffffffu, !active && exhausted && !rejected)) break;
 
     // ---- one bounce for every walking lane
-    bool to_next = false;
+    bool to_next = false, to_done = rejected, to_park = false;
     ShadowRequest req;
     req.active = false;
+    vec3 throughput(0.f);
     if (active) {
       HitT hit;
       const SssStep st = SssBounce(s, &rng, &walk, &hit, nullptr);
       ++rays;
+      --budget;
       if (st != kSssContinue) {
+        // the entry vertex is only needed now: rebuild it from the parked path's ray + hit
+        const RayT ray = LoadRay(w, p);
+        const Surface entry_si = MakeSurface(s, ray, LoadHit(w, p));
+        const Frame entry_frame = PrincipledFrame(entry_si);
+        const float4 t4 = w.thr[p], r4 = w.rad[p];
+        throughput = vec3(t4.x, t4.y, t4.z);
         VertexResult vr;
         vr.P = entry_si.P;
         vr.shadow[1].active = false;
         if (st == kSssHit) SssFinish(s, entry_si, entry_frame, walk, hit, &rng, &vr);
         else FinishPrincipled(entry_frame, vec3(0.f), vec3(0.f), 0.f, &vr);
         req = vr.shadow[1];
-        CommitVertex(w, p, vr, throughput, L, depth, rng, next_parity);
+        CommitVertex(w, p, vr, throughput, vec3(r4.x, r4.y, r4.z), __float_as_uint(r4.w), rng);
         to_next = !IsBlack(vr.throughput * throughput);
+        to_done = !to_next;
+        active = false;
+      } else if (budget == 0u) {
+        ParkWalk(w, p, walk);
+        w.rng[p] = make_ulonglong2(rng.state, rng.inc);
+        to_park = true;
         active = false;
       }
     }
     PushShadow(w, req, throughput, p);
-    const uint32_t b = WarpAppend(&w.counters[kNumActiveNext], to_next);
-    if (to_next) w.q_active[next_parity][b] = p;
+    RouteSlot(w, next_parity, p, to_next, to_done);
+    const uint32_t c = WarpAppend(&w.counters[kNumWalk0 + next_parity], to_park);
+    if (to_park) w.q_walk[next_parity][c] = p;
   }
   if (rays) atomicAdd(&w.stats[kStatSss], rays);
 }
@@ -413,20 +560,6 @@ __global__ void __launch_bounds__(128) TraceAnyKernel(SceneView s, WaveState w) 
     }
   }
   if (rays) atomicAdd(&w.stats[kStatShadow], rays);
-}
-
-// ------------------------------------------------------------------------------------------------ accumulation
-// rgba += (L, 1), count += 1 per sample (render.cc:175-183), samples of a pixel added in sample order.
-__global__ void AccumulateKernel(WaveState w, float4* rgba, uint32_t* count, uint32_t npix, uint32_t spp_wave) {
-  const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pixel >= npix) return;
-  float4 acc = rgba[pixel];
-  for (uint32_t sidx = 0; sidx < spp_wave; ++sidx) {
-    const float4 r = w.rad[sidx * npix + pixel];
-    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += 1.0f;
-  }
-  rgba[pixel] = acc;
-  count[pixel] += spp_wave;
 }
 
 // ------------------------------------------------------------------------------------------------ test hooks
