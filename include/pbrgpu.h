@@ -86,8 +86,12 @@ typedef struct pbrgpu_stats {
   uint64_t sss_rays;       /* closest-hit rays issued inside random-walk subsurface scattering */
   uint64_t kernel_launches;
   double   seconds;        /* wall time of the call, device work included */
-  double   trace_closest_ms, trace_any_ms, shade_ms, sss_ms;  /* CUDA-event sums per kernel family */
+  double   trace_closest_ms, trace_any_ms, shade_ms, sss_ms;  /* CUDA-event sums per kernel family (profiling mode) */
   uint64_t nodes_visited, prims_tested;   /* only filled by pbrgpu_trace* with stats enabled */
+  double   regen_ms;       /* retire + regenerate kernel (profiling mode) */
+  double   device_ms;      /* CUDA-event time from the first to the last kernel of the call on the launching stream
+                              (max over the context's devices) */
+  uint64_t trace_closest_launches;
 } pbrgpu_stats;
 
 /* ---- life cycle.  device_ids == NULL / n_devices == 0: the current device only. */
@@ -138,6 +142,9 @@ int pbrgpu_render_device(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint3
                          uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, float* d_rgba,
                          uint32_t* d_count, size_t* finish_pass);
 int pbrgpu_get_stats(const pbrgpu_ctx* ctx, pbrgpu_stats* out);
+/* profiling mode: every kernel family of every iteration is bracketed by CUDA events on the launching stream and the
+ * sums are reported in pbrgpu_stats (adds ~10 event records per iteration) */
+int pbrgpu_set_profiling(pbrgpu_ctx* ctx, int enabled);
 /* samples of one pixel traced concurrently per wave (0 = choose from free memory) */
 int pbrgpu_set_wave_spp(pbrgpu_ctx* ctx, uint32_t spp_per_wave);
 

@@ -41,7 +41,8 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("sss_rays", C.c_uint64), ("kernel_launches", C.c_uint64), ("seconds", C.c_double),
                 ("trace_closest_ms", C.c_double), ("trace_any_ms", C.c_double), ("shade_ms", C.c_double),
-                ("sss_ms", C.c_double), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64)]
+                ("sss_ms", C.c_double), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
+                ("regen_ms", C.c_double), ("device_ms", C.c_double), ("trace_closest_launches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -181,7 +182,7 @@ def gpu_lib():
         L.pbrgpu_destroy.argtypes = [C.c_void_p]
         for name in ("pbrgpu_set_triangles", "pbrgpu_set_curves", "pbrgpu_set_materials", "pbrgpu_set_lights",
                      "pbrgpu_commit", "pbrgpu_scene_bounds", "pbrgpu_render", "pbrgpu_render_device",
-                     "pbrgpu_get_stats", "pbrgpu_set_wave_spp", "pbrgpu_trace", "pbrgpu_occluded",
+                     "pbrgpu_get_stats", "pbrgpu_set_wave_spp", "pbrgpu_set_profiling", "pbrgpu_trace", "pbrgpu_occluded",
                      "pbrgpu_trace_device", "pbrgpu_occluded_device", "pbrgpu_radiance", "pbrgpu_radiance_mega",
                      "pbrgpu_shade", "pbrgpu_eval_closure"):
             getattr(L, name).restype = C.c_int
@@ -198,6 +199,8 @@ def host_lib():
         L = C.CDLL(HOST_LIB)
         L.pbrhost_scene_create.restype = C.c_void_p
         L.pbrhost_scene_create.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int]
+        L.pbrhost_scene_create_on.restype = C.c_void_p
+        L.pbrhost_scene_create_on.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.c_int]
         L.pbrhost_scene_destroy.argtypes = [C.c_void_p]
         L.pbrhost_scene_flat.argtypes = [C.c_void_p, C.POINTER(Flat)]
         L.pbrhost_scene_ctx.restype = C.c_void_p
@@ -247,6 +250,9 @@ class Context:
 
     def set_wave_spp(self, n):
         self._check(self.lib.pbrgpu_set_wave_spp(self.h, C.c_uint32(n)))
+
+    def set_profiling(self, on):
+        self._check(self.lib.pbrgpu_set_profiling(self.h, C.c_int(1 if on else 0)))
 
     def bounds(self):
         a = np.zeros(3, np.float32); b = np.zeros(3, np.float32)
@@ -326,10 +332,14 @@ class Context:
 class Scene:
     """pbrlab::Scene built by CreateScene() from .obj / .hair files (the reference CLI's path)."""
 
-    def __init__(self, files, commit_to_device=True):
+    def __init__(self, files, commit_to_device=True, device_ids=None):
         self.lib = host_lib()
         arr = (C.c_char_p * len(files))(*[f.encode() for f in files])
-        h = self.lib.pbrhost_scene_create(len(files), arr, 1 if commit_to_device else 0)
+        if device_ids:
+            ids = (C.c_int * len(device_ids))(*device_ids)
+            h = self.lib.pbrhost_scene_create_on(len(files), arr, 1 if commit_to_device else 0, ids, len(device_ids))
+        else:
+            h = self.lib.pbrhost_scene_create(len(files), arr, 1 if commit_to_device else 0)
         if not h:
             raise RuntimeError("CreateScene failed: " + self.lib.pbrhost_last_error().decode())
         self.h = C.c_void_p(h)

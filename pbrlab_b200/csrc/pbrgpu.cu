@@ -62,6 +62,7 @@ struct Device {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t kev[12] = {};   // per-kernel-family timing of one iteration (profiling mode)
   // scene
   DevBuf<float4> tri_nodes, tri_data, curve_nodes, curve_data, verts, normals, emissive, lprim_info;
   DevBuf<float2> texcoords;
@@ -99,6 +100,7 @@ struct Device {
     if (h_stats) cudaFreeHost(h_stats);
     h_counters = nullptr; h_stats = nullptr;
     for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : kev) { if (e) cudaEventDestroy(e); e = nullptr; }
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -113,6 +115,7 @@ struct pbrgpu_ctx {
   pbrgpu_stats stats;
   uint32_t wave_spp = 0;
   bool committed = false;
+  bool profile = false;   // time every kernel family with CUDA events (pbrgpu_set_profiling)
 };
 
 namespace {
@@ -121,7 +124,13 @@ using pbr::SceneView;
 using pbr::WaveState;
 
 constexpr int kBlock = 128;
-constexpr uint32_t kSssBouncesPerLaunch = 64;   // see SssWalkKernel
+// Bounce budget of one SssWalkKernel launch (see wavefront.cuh).  One bounce is a ~4k-instruction dependent chain
+// (tens of microseconds for a single warp), so a launch lasts at least budget x that: while the pool is busy a small
+// budget keeps the launch throughput-bound (more, shorter walk slices in flight); once only stragglers are left a
+// large budget saves host round-trips.
+constexpr uint32_t kSssBouncesBusy = 16;
+constexpr uint32_t kSssBouncesDrain = 1024;
+constexpr uint32_t kDrainThreshold = 1u << 16;   // slots in flight below which the pool counts as draining
 int PersistentGrid(const Device& d, int blocks_per_sm) { return d.sm_count * blocks_per_sm; }
 
 int UploadScene(pbrgpu_ctx* ctx, Device& d) {
@@ -199,8 +208,8 @@ int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
 }
 
 struct LoopTimers {
-  double closest_ms = 0, any_ms = 0, shade_ms = 0, sss_ms = 0;
-  uint64_t launches = 0;
+  double closest_ms = 0, any_ms = 0, shade_ms = 0, sss_ms = 0, regen_ms = 0, device_ms = 0;
+  uint64_t launches = 0, closest_launches = 0;
 };
 
 // Runs iterations on the slot pool until nothing is in flight and (when regenerating) the frame has no samples left.
@@ -216,32 +225,50 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
   const int grid_trace = PersistentGrid(d, 8), grid_shade = PersistentGrid(d, 4);
   // state after the set-up kernel (host knows it): hooks start with n active slots, frames with N retired slots
   bool have_active = (frame == nullptr), have_walk = false, have_done = (frame != nullptr);
+  uint64_t in_flight = ~0ull;   // slots that will trace or walk in the coming iteration (unknown before the first)
   for (uint32_t it = 0; (have_active || have_walk || have_done) && it < max_iterations; ++it) {
     if (cancel && *cancel) break;
     const uint32_t next = parity ^ 1u;
     // single-vertex mode lets the walk run to its end inside the one iteration
-    const uint32_t walk_budget = (max_iterations == 1u) ? 0x7fffffffu : kSssBouncesPerLaunch;
+    const uint32_t walk_budget =
+        (max_iterations == 1u) ? 0x7fffffffu : (in_flight < kDrainThreshold ? kSssBouncesDrain : kSssBouncesBusy);
+    const bool prof = ctx->profile;
+    auto mark = [&](int k) { if (prof) cudaEventRecord(d.kev[k], st); };
     pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, parity);
     tm->launches += 1;
+    mark(0);
     if (frame && have_done) {
       pbr::RegenerateKernel<<<grid_shade, 256, 0, st>>>(w, *frame, parity);
       tm->launches += 1;
     }
+    mark(1);
     pbr::TraceClosestKernel<<<grid_trace, kBlock, 0, st>>>(s, w, parity);
+    mark(2);
     pbr::ShadeSurfaceKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
     if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
+    mark(3);
     pbr::SssWalkKernel<<<grid_shade, kBlock, 0, st>>>(s, w, parity, walk_budget);
+    mark(4);
     pbr::TraceAnyKernel<<<grid_trace, kBlock, 0, st>>>(s, w);
+    mark(5);
     tm->launches += s.num_curves ? 5 : 4;
+    tm->closest_launches += 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(d.h_counters, w.counters, sizeof(uint32_t) * pbr::kCounterCount,
                                   cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(d.h_stats, w.stats, sizeof(unsigned long long) * pbr::kStatCount,
                                   cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (prof) {
+      float ms[5] = {0, 0, 0, 0, 0};
+      for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&ms[k], d.kev[k], d.kev[k + 1]);
+      tm->regen_ms += ms[0]; tm->closest_ms += ms[1]; tm->shade_ms += ms[2]; tm->sss_ms += ms[3]; tm->any_ms += ms[4];
+    }
     have_active = d.h_counters[pbr::kNumActive0 + next] > 0;
     have_walk = d.h_counters[pbr::kNumWalk0 + next] > 0;
     // retired slots only matter while they can be accumulated (frame mode); hooks read rad[] directly
     have_done = frame && d.h_counters[pbr::kNumDone0 + next] > 0;
+    in_flight = uint64_t(d.h_counters[pbr::kNumActive0 + next]) + d.h_counters[pbr::kNumWalk0 + next];
+    if (frame && d.h_stats[pbr::kStatNextSample] < frame->total_samples) in_flight += d.h_counters[pbr::kNumDone0 + next];
     if (frame && finish_pass) {
       const size_t passes = size_t(d.h_stats[pbr::kStatRetired] / frame->npix);
       const size_t global = std::min(pass_cap, pass_offset + passes * pass_stride);
@@ -263,7 +290,7 @@ int FetchStats(pbrgpu_ctx* ctx, Device& d) {
 // number of path slots kept in flight: enough to fill the GPU many times over (each iteration costs one host
 // round-trip), small enough that the SoA state (~300 B/slot) streams through HBM quickly
 uint32_t ChoosePoolSize(const pbrgpu_ctx* ctx, uint64_t npix, uint64_t total_samples) {
-  uint64_t n = ctx->wave_spp ? uint64_t(ctx->wave_spp) * npix : (4ull << 20);
+  uint64_t n = ctx->wave_spp ? uint64_t(ctx->wave_spp) * npix : (8ull << 20);
   n = std::min<uint64_t>(n, total_samples);
   n = std::min<uint64_t>(n, 64ull << 20);
   return uint32_t(std::max<uint64_t>(n, 1));
@@ -304,13 +331,18 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   frame.rgba = d.rgba.ptr;
   frame.count = d.count.ptr;
 
+  CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
   pbr::ResetPoolKernel<<<(std::max<uint32_t>(n_slots, 64) + 255) / 256, 256, 0, d.stream>>>(d.wave, n_slots);
   tm->launches++;
   pbr::ShadeFlags flags;
   flags.skip_emission_and_roulette = 0;
   rc = RunPool(ctx, d, &frame, 0xffffffffu, flags, tm, cancel, finish_pass, sample_offset, sample_stride, spp);
   if (rc != PBRGPU_OK) return rc;
+  CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]);
+  tm->device_ms = ms;
   return FetchStats(ctx, d);
 }
 
@@ -412,6 +444,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
       return nullptr;
     }
     d.sm_count = prop.multiProcessorCount;
+    for (auto& e : d.kev) cudaEventCreate(&e);
     ctx->devices.push_back(d);
   }
   // peer access for the frame-end sum on multi-device contexts
@@ -523,6 +556,12 @@ int pbrgpu_set_wave_spp(pbrgpu_ctx* ctx, uint32_t spp_per_wave) {
   return PBRGPU_OK;
 }
 
+int pbrgpu_set_profiling(pbrgpu_ctx* ctx, int enabled) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  ctx->profile = enabled != 0;
+  return PBRGPU_OK;
+}
+
 int pbrgpu_get_stats(const pbrgpu_ctx* ctx, pbrgpu_stats* out) {
   if (!ctx || !out) return PBRGPU_ERR_INVALID;
   *out = ctx->stats;
@@ -595,6 +634,10 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
       s.sss_rays += d.h_stats[pbr::kStatSss];
     }
     s.kernel_launches += tms[k].launches;
+    s.trace_closest_launches += tms[k].closest_launches;
+    s.trace_closest_ms += tms[k].closest_ms; s.trace_any_ms += tms[k].any_ms; s.shade_ms += tms[k].shade_ms;
+    s.sss_ms += tms[k].sss_ms; s.regen_ms += tms[k].regen_ms;
+    s.device_ms = std::max(s.device_ms, tms[k].device_ms);
   }
   uint64_t samples = 0;
   for (uint32_t sidx = sample_offset; sidx < spp; sidx += sample_stride) ++samples;

@@ -217,7 +217,13 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
           bx.hi[k] = std::max(bx.hi[k], p[k] + r * 1.0001f);
         }
       }
-      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], ebl[k] - er); hi[k] = std::max(hi[k], ebh[k] + er); }
+      float size = 0.f;   // enlarge_bounds: + 4 ulp of the largest coordinate (kernels/common/scene_curves.cpp:377-381)
+      for (int k = 0; k < 3; ++k) {
+        ebl[k] = ebl[k] - er; ebh[k] = ebh[k] + er;
+        size = std::max(size, std::max(std::fabs(ebl[k]), std::fabs(ebh[k])));
+      }
+      const float pad = 4.0f * FLT_EPSILON * size;
+      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], ebl[k] - pad); hi[k] = std::max(hi[k], ebh[k] + pad); }
     }
     if (!pbrbvh::BuildBvh8(boxes.data(), nc, prm, &curve_bvh, &err)) { error = err; return false; }
     curve_data.resize(size_t(4) * nc);

@@ -37,13 +37,22 @@ struct pbrhost_flat {   // views into Scene::Flat(); valid until the scene is de
 const char* pbrhost_last_error(void) { return g_error.c_str(); }
 
 // CreateScene(argc, argv, &scene): argv[1..] = files.  commit_to_device = 0 stops after the host-side commit.
+void* pbrhost_scene_create_on(int nfiles, const char** files, int commit_to_device, const int* device_ids,
+                              int n_devices);
 void* pbrhost_scene_create(int nfiles, const char** files, int commit_to_device) {
+  return pbrhost_scene_create_on(nfiles, files, commit_to_device, nullptr, 0);
+}
+// same, on explicit CUDA devices (one id per rank in a multi-process launch; several ids = one process driving
+// several GPUs, summed at frame end)
+void* pbrhost_scene_create_on(int nfiles, const char** files, int commit_to_device, const int* device_ids,
+                              int n_devices) {
   std::vector<std::string> store;
   store.emplace_back("pbrlab");
   for (int i = 0; i < nfiles; ++i) store.emplace_back(files[i]);
   std::vector<char*> argv;
   for (auto& s : store) argv.push_back(const_cast<char*>(s.c_str()));
   pbrlab::Scene* scene = new pbrlab::Scene();
+  if (device_ids && n_devices > 0) scene->SetDevices(std::vector<int>(device_ids, device_ids + n_devices));
   try {
     if (!CreateScene(int(argv.size()), argv.data(), scene, commit_to_device != 0)) {
       g_error = "CreateScene failed";

@@ -3,6 +3,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <stdexcept>
 
@@ -214,7 +215,14 @@ void Scene::CommitHostOnly(void) {
             rmax = std::max(rmax, std::fabs(q[3]));
             for (int c = 0; c < 3; ++c) { pl[c] = std::min(pl[c], q[c]); ph[c] = std::max(ph[c], q[c]); }
           }
-          for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], pl[c] - rmax); hi[c] = std::max(hi[c], ph[c] + rmax); }
+          // ... then padded by 4 ulp of the largest coordinate (enlarge_bounds, kernels/common/scene_curves.cpp:377-381)
+          float size = 0.f;
+          for (int c = 0; c < 3; ++c) {
+            pl[c] = pl[c] - rmax; ph[c] = ph[c] + rmax;
+            size = std::max(size, std::max(std::fabs(pl[c]), std::fabs(ph[c])));
+          }
+          const float pad = 4.0f * std::numeric_limits<float>::epsilon() * size;
+          for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], pl[c] - pad); hi[c] = std::max(hi[c], ph[c] + pad); }
         }
       }
     }

@@ -1,0 +1,111 @@
+"""The parity assertions, written once and applied to (a) the g++ emulation of the device code on CPU and (b) the
+CUDA path through the C ABI on a B200.  `impl` is anything with trace / occluded / shade / radiance / eval_closure
+(tests/emulbind.Emul or pbrlab_b200.Context)."""
+import numpy as np
+
+import common
+import pbrlab_b200 as pb
+
+REL = 1e-5   # north_star: BSDF eval/sample/pdf within 1e-5 relative given the same random numbers
+
+
+def close(a, b, rel=REL, abs_=1e-7):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    ok = np.abs(a - b) <= abs_ + rel * np.abs(b)
+    return ok | both_nan | both_inf
+
+
+def frac_close(a, b, rel=REL, abs_=1e-7):
+    return float(close(a, b, rel, abs_).mean())
+
+
+def check_kat(impl, g):
+    """closure-level known-answer vectors (tests/golden/kat_closures.npz)"""
+    ev = impl.eval_closure
+    # PCG32: bit exact
+    for (st, sq), want in zip(g["rng_seeds"], g["rng_draws"]):
+        words = np.array([[int(st) & 0xffffffff, int(st) >> 32, int(sq) & 0xffffffff, int(sq) >> 32]], np.uint32)
+        got = ev(0, None, words.view(np.float32), 64)[0]
+        assert np.array_equal(got, want), "PCG32 stream differs"
+    # fast_math polynomials: same operations -> bit exact except where libm differs; allow 1 ulp-ish
+    for key, fid, x in [("fm_sin", 0, g["fm_x"]), ("fm_cos", 1, g["fm_x"]), ("fm_exp2", 2, g["fm_xe"]),
+                        ("fm_exp", 3, g["fm_xe"]), ("fm_log2", 4, g["fm_xpos"]), ("fm_log", 5, g["fm_xpos"]),
+                        ("fm_asin", 7, g["fm_xu"]), ("fm_sincos_s", 8, g["fm_x"]), ("fm_sincos_c", 9, g["fm_x"])]:
+        got = ev(1, [fid], np.stack([x, x], 1), 1)[:, 0]
+        assert frac_close(got, g[key], 1e-6, 1e-9) == 1.0, key
+    got = ev(1, [6], np.stack([g["fm_x"], g["fm_y"]], 1), 1)[:, 0]
+    assert frac_close(got, g["fm_atan2"], 1e-6, 1e-9) == 1.0
+    assert frac_close(ev(2, None, g["u2"], 3), g["cosine_hemisphere"], REL, 1e-6) == 1.0
+    assert frac_close(ev(3, None, g["u2"], 3), g["uniform_sphere"], REL, 1e-6) == 1.0
+    assert frac_close(ev(4, None, np.stack([g["mis_a"], g["mis_b"]], 1), 1)[:, 0], g["mis_w"]) == 1.0
+    assert frac_close(ev(5, None, np.stack([g["fr_cos"], g["fr_eta"]], 1), 1)[:, 0], g["fr"], REL, 1e-7) == 1.0
+    wi, wo, u = g["wi"], g["wo"], g["u2"]
+    for k, (ax, ay, d) in enumerate(common.GGX_CASES):
+        e = ev(6, [ax, ay, d], np.concatenate([wi, wo], 1), 2)
+        assert frac_close(e, g["ggx"][k][:, 0:2]) == 1.0, ("ggx eval", ax, ay, d)
+        s = ev(7, [ax, ay, d], np.concatenate([wo, u], 1), 5)
+        want = g["ggx"][k][:, 2:7]
+        # the sampled direction is compared tightly; f and pdf of a near-delta lobe amplify the last ulp of wi by
+        # 1/alpha^2, so they are compared on the cases where the reference's own value is well conditioned
+        assert frac_close(s[:, 0:3], want[:, 0:3], REL, 1e-6) == 1.0, ("ggx sample dir", ax, ay, d)
+        tol = REL if min(ax, ay) >= 1e-2 else 2e-2
+        assert frac_close(s[:, 3:5], want[:, 3:5], tol, 1e-7) >= 0.999, ("ggx sample f/pdf", ax, ay, d)
+    for k, p in enumerate(common.PRINCIPLED_CASES):
+        assert frac_close(ev(10, p, np.zeros((1, 1), np.float32), 36)[0][:34], g["principled_bsdf"][k][:34], 1e-6, 1e-9) == 1.0
+        assert frac_close(ev(9, p, wo, 4), g["principled_w"][k]) == 1.0, ("principled weights", k)
+        assert frac_close(ev(8, p, np.concatenate([wi, wo], 1), 4), g["principled_eval"][k]) == 1.0, ("principled", k)
+    hwi, hwo, h, us = g["hair_wi"], g["hair_wo"], g["hair_h"], g["hair_us"]
+    for k, p in enumerate(common.HAIR_CASES):
+        assert frac_close(ev(13, p, np.zeros((1, 1), np.float32), 9)[0], g["hair_setup"][k], 1e-6, 1e-9) == 1.0
+        e = ev(11, p, np.concatenate([h[:, None], hwi, hwo], 1), 4)
+        assert frac_close(e, g["hair_eval"][k], REL, 1e-9) >= 0.9999, ("hair eval", k)
+        s = ev(12, p, np.concatenate([h[:, None], hwo, us], 1), 7)
+        assert frac_close(s, g["hair_sample"][k], REL, 1e-7) >= 0.999, ("hair sample", k)
+    assert frac_close(ev(14, None, g["sss_in"], 9), g["sss_coeff"], REL, 1e-9) == 1.0
+    assert frac_close(ev(15, None, g["sss_dist_in"], 4), g["sss_dist"], REL, 1e-9) == 1.0
+
+
+def check_rays(impl, g, min_agree=0.9999):
+    """hit / primID agreement with Embree >= 99.99 %, t within 1e-5 relative (north_star ray gate)"""
+    rays = common.rays_from_f8(g["rays"])
+    hits = impl.trace(rays)
+    ids = g["hit_ids"]; f = g["hit_f"]
+    same = (hits["instance_id"] == ids[:, 0]) & (hits["geom_id"] == ids[:, 1]) & (hits["prim_id"] == ids[:, 2])
+    assert same.mean() >= min_agree, "hit agreement %.6f" % same.mean()
+    hit = same & (ids[:, 0] != 0xFFFFFFFF)
+    assert hit.sum() > 1000
+    assert np.all(np.abs(hits["t"][hit] - f[hit, 0]) <= 1e-5 * np.abs(f[hit, 0]))
+    assert np.abs(hits["u"][hit] - f[hit, 1]).max() < 1e-4 and np.abs(hits["v"][hit] - f[hit, 2]).max() < 1e-4
+    assert np.abs(hits["normal_g"][hit] - f[hit, 3:6]).max() < 1e-4
+    occ = impl.occluded(rays)
+    assert (occ == g["occluded"]).mean() >= min_agree
+    return float(same.mean())
+
+
+def check_shade(impl, g, min_agree):
+    """one shading vertex = Shader(): wi, throughput, NEE contribution, pdf, next origin"""
+    rays = common.rays_from_f8(g["rays"])
+    a = impl.shade(rays, g["seeds"]); b = g["shade"]
+    assert np.array_equal(a[:, 0], b[:, 0]), "hit flags differ"
+    hit = b[:, 0] > 0
+    ok = np.ones(len(a), bool)
+    for sl in (slice(1, 4), slice(4, 7), slice(7, 10), slice(10, 11), slice(11, 14)):
+        scale = np.maximum(1.0, np.abs(b[:, sl]).max(axis=1))
+        ok &= np.abs(a[:, sl] - b[:, sl]).max(axis=1) <= 1e-4 * scale
+    frac = ok[hit].mean()
+    assert frac >= min_agree, "shading vertices agreeing: %.5f" % frac
+    return float(frac)
+
+
+def check_radiance(impl, g, min_agree):
+    """whole paths = GetRadiance() with the same PCG32 stream per path"""
+    rays = common.rays_from_f8(g["rays"])
+    a = impl.radiance(rays, g["seeds"])
+    frac = common.path_agreement(a, g["radiance"])
+    assert frac >= min_agree, "paths agreeing: %.5f" % frac
+    # the disagreeing paths are chaotic divergences, not bias: batch means agree to a few 1e-3
+    ma, mb = a.mean(axis=0), g["radiance"].mean(axis=0)
+    assert np.all(np.abs(ma - mb) <= 0.02 * mb), (ma, mb)
+    return frac

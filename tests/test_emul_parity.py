@@ -1,0 +1,124 @@
+"""CPU tests of the device code's arithmetic.  The per-ray / per-vertex functions of the CUDA path tracer are plain
+functions; tests/host_emul compiles them with g++ so that, in a container without a GPU, they can be checked against
+(a) the golden fixtures generated from the compiled reference and (b) the reference itself when oracle/_ref exists.
+The same assertions (tests/checks.py) run against the CUDA library on the GPU box (tests/test_gpu_parity.py)."""
+import numpy as np
+
+import checks
+import common
+import pbrlab_b200 as pb
+from conftest import golden
+
+
+class _EmulKat:
+    def __init__(self):
+        import emulbind
+        self.e = emulbind.Emul()
+
+    def eval_closure(self, *a):
+        return self.e.eval_closure(*a)
+
+
+def test_closure_known_answers(built):
+    checks.check_kat(_EmulKat(), golden("kat_closures.npz"))
+
+
+def test_rays_vs_embree_golden(cornell_emul):
+    agree = checks.check_rays(cornell_emul, golden("cornell_rays.npz"))
+    assert agree >= 0.9999
+
+
+def test_surface_info(cornell_emul):
+    g = golden("cornell_rays.npz")
+    rays = common.rays_from_f8(g["rays"])
+    a = cornell_emul.surface(rays); b = g["surface"]
+    assert np.array_equal(a[:, 11], b[:, 11])                       # face direction incl. miss flag
+    hit = b[:, 11] >= 0
+    assert np.abs(a[hit, 0:3] - b[hit, 0:3]).max() < 2e-5           # position
+    assert np.abs(a[hit, 3:9] - b[hit, 3:9]).max() < 1e-5           # Ns, Ng
+    assert np.abs(a[hit, 9:11] - b[hit, 9:11]).max() < 1e-5         # texcoord = (u, v) without vt
+
+
+def test_light_sampling(cornell_emul):
+    g = golden("cornell_paths.npz")
+    a = cornell_emul.sample_light(g["seeds"][:256])
+    assert np.allclose(a, g["light_samples"], rtol=1e-6, atol=1e-6)
+
+
+def test_shading_vertices(cornell_emul):
+    # Lucy's random walks and Suzanne's alpha = 1e-4 lobe amplify last-ulp differences of the hit point; everything
+    # else must agree
+    frac = checks.check_shade(cornell_emul, golden("cornell_paths.npz"), min_agree=0.995)
+    assert frac >= 0.995
+
+
+def test_sss_sphere_draw_order_is_right_to_left(cornell_emul):
+    """g++ evaluates UniformSampleSphere(rng.Draw(), rng.Draw()) right to left.  If the device
+    code drew in the other order, walks longer than one bounce would diverge: agreement on Lucy would collapse."""
+    g = golden("cornell_paths.npz")
+    rays = common.rays_from_f8(g["rays"])
+    hits = cornell_emul.trace(rays)
+    lucy = hits["instance_id"] == 0
+    a = cornell_emul.shade(rays[lucy], g["seeds"][lucy]); b = g["shade"][lucy]
+    moved = np.abs(b[:, 11:14] - (rays["org"][lucy] + hits["t"][lucy, None] * rays["dir"][lucy])).max(axis=1) > 1e-4
+    assert moved.sum() > 500                                         # walks that left the entry point
+    ok = np.abs(a[moved, 11:14] - b[moved, 11:14]).max(axis=1) < 1e-3
+    assert ok.mean() > 0.97
+
+
+def test_paths(cornell_emul):
+    frac = checks.check_radiance(cornell_emul, golden("cornell_paths.npz"), min_agree=0.995)
+    assert frac >= 0.995
+
+
+def test_hair_rays_and_vertices(hair_emul):
+    g = golden("hair_scene.npz")
+    rays = common.rays_from_f8(g["rays"])
+    hits = hair_emul.trace(rays)
+    ids = g["hit_ids"]
+    same = (hits["instance_id"] == ids[:, 0]) & (hits["prim_id"] == ids[:, 2])
+    assert same.mean() >= 0.999, same.mean()
+    curve = same & (ids[:, 0] == 9)
+    assert curve.sum() > 3000
+    f = g["hit_f"]
+    assert np.all(np.abs(hits["t"][curve] - f[curve, 0]) <= 2e-5 * np.abs(f[curve, 0]))
+    assert np.abs(hits["u"][curve] - f[curve, 1]).max() < 1e-3          # position along the segment
+    assert np.abs(hits["v"][curve] - f[curve, 2]).max() < 2e-3          # h across the ribbon, feeds the hair BSDF
+    assert np.abs(hits["normal_g"][curve] - f[curve, 3:6]).max() < 1e-3  # tangent
+    assert (hair_emul.occluded(rays) == g["occluded"]).mean() >= 0.999
+    a = hair_emul.shade(rays, g["seeds"]); b = g["shade"]
+    ok = np.ones(len(a), bool)
+    for sl in (slice(1, 4), slice(4, 7), slice(7, 10), slice(10, 11)):
+        scale = np.maximum(1.0, np.abs(b[:, sl]).max(axis=1))
+        ok &= np.abs(a[:, sl] - b[:, sl]).max(axis=1) <= 2e-3 * scale
+    assert ok[curve].mean() >= 0.98, ok[curve].mean()
+    frac = common.path_agreement(hair_emul.radiance(rays, g["seeds"]), g["radiance"], rel=1e-3)
+    assert frac >= 0.97, frac
+
+
+def test_live_reference_when_available(cornell_emul, ref):
+    """fresh random rays / seeds against oracle/_ref itself (skipped where the library did not travel)"""
+    import pytest
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from pbrlab_b200 import scenes
+    S = ref.scene([scenes.cornell()])
+    rng = np.random.default_rng(77)
+    rays = common.camera_rays(S.camera(512, 512), 50000, rng)
+    hits = cornell_emul.trace(rays)
+    f, ids = S.trace(pb.rays_to_f8(rays))
+    same = (hits["instance_id"] == ids[:, 0]) & (hits["prim_id"] == ids[:, 2])
+    assert same.mean() >= 0.9999
+    seeds = np.stack([rng.integers(0, 2**62, len(rays), dtype=np.uint64)] * 2, 1)
+    frac = common.path_agreement(cornell_emul.radiance(rays, seeds), S.radiance(pb.rays_to_f8(rays), seeds))
+    assert frac >= 0.995
+
+
+def test_render_sample_split_is_additive(cornell_emul):
+    """the multi-GPU decomposition: samples s = r (mod R) rendered separately sum to the full frame"""
+    full, cfull, _ = cornell_emul.render(32, 32, 6, seed=5)
+    a, ca, _ = cornell_emul.render(32, 32, 6, seed=5, sample_offset=0, sample_stride=2)
+    b, cb, _ = cornell_emul.render(32, 32, 6, seed=5, sample_offset=1, sample_stride=2)
+    assert np.array_equal(ca + cb, cfull) and np.all(cfull == 6)
+    assert np.allclose(a + b, full, rtol=1e-5, atol=1e-6)
+    assert np.all(full[..., 3] == 6.0)
