@@ -286,14 +286,19 @@ PBR_HD void ComputeScatteringCoefficientFromAlbedo(float A, float d, float* sigm
   *sigma_s = *sigma_t * a;
 }
 
-PBR_HD float SampleScatterDistance(const vec3& throughput, const vec3& sigma_s, const vec3& sigma_t, float u0,
-                                   float u1, vec3* channel_pdf) {                                          // :141-187
+// SampleChannel's pdf (:141-172): proportional to |throughput * albedo|, uniform when that is black
+PBR_HD vec3 SssChannelPdf(const vec3& throughput, const vec3& sigma_s, const vec3& sigma_t) {
   const vec3 albedo = SafeDivideSpectrum(sigma_s, sigma_t);
   const float w0 = fabsf(throughput.x * albedo.x), w1 = fabsf(throughput.y * albedo.y),
               w2 = fabsf(throughput.z * albedo.z);
   const float sum = w0 + w1 + w2;
-  if (sum > 0.0f) *channel_pdf = vec3(w0 / sum, w1 / sum, w2 / sum);
-  else *channel_pdf = vec3(1.0f / 3.0f, 1.0f / 3.0f, 1.0f / 3.0f);
+  if (sum > 0.0f) return vec3(w0 / sum, w1 / sum, w2 / sum);
+  return vec3(1.0f / 3.0f, 1.0f / 3.0f, 1.0f / 3.0f);
+}
+
+PBR_HD float SampleScatterDistance(const vec3& throughput, const vec3& sigma_s, const vec3& sigma_t, float u0,
+                                   float u1, vec3* channel_pdf) {                                          // :141-187
+  *channel_pdf = SssChannelPdf(throughput, sigma_s, sigma_t);
   float sample_sigma_t;
   if (u0 < channel_pdf->x) sample_sigma_t = sigma_t.x;
   else if (u0 < channel_pdf->x + channel_pdf->y) sample_sigma_t = sigma_t.y;
@@ -332,8 +337,12 @@ PBR_HD bool SssBegin(const Surface& si, const Frame& entry, const PrincipledBsdf
 
 enum SssStep { kSssContinue = 0, kSssHit = 1, kSssAbsorbed = 2 };
 
-// One iteration of the walk loop (:281-383).  On kSssHit, *hit holds the exit intersection along w->ray.
-PBR_HD SssStep SssBounce(const SceneView& s, Pcg32* rng, SssWalkState* w, HitT* hit, uint64_t* rays) {
+// One iteration of the walk loop (:281-383), split at the ray query so that the wavefront's walk kernel can run the
+// query in its warp traversal engine:
+//   SssPrepareSegment: new direction (bounces > 0) + scatter distance -> w->ray (tmax = scatter distance)
+//   SssFinishSegment:  transmittance / throughput update, roulette, advance.  On kSssHit the caller holds the exit
+//                      intersection along w->ray.
+PBR_HD void SssPrepareSegment(Pcg32* rng, SssWalkState* w) {
   if (w->bounce > 0) {
 #if PBR_SSS_SPHERE_DRAW_RIGHT_TO_LEFT
     const float u2 = Draw(rng), u1 = Draw(rng);
@@ -345,11 +354,12 @@ PBR_HD SssStep SssBounce(const SceneView& s, Pcg32* rng, SssWalkState* w, HitT* 
   }
   vec3 channel_pdf;
   const float ua = Draw(rng), ub = Draw(rng);
-  const float t_scatter = SampleScatterDistance(w->throughput, w->sigma_s, w->sigma_t, ua, ub, &channel_pdf);
-  w->ray.tmax = t_scatter;
-  const bool is_hit = TraceClosest<false>(s, w->ray, hit, nullptr);
-  if (rays) ++*rays;
-  const float t = is_hit ? hit->t : t_scatter;
+  w->ray.tmax = SampleScatterDistance(w->throughput, w->sigma_s, w->sigma_t, ua, ub, &channel_pdf);
+}
+
+PBR_HD SssStep SssFinishSegment(bool is_hit, float hit_t, Pcg32* rng, SssWalkState* w) {
+  const vec3 channel_pdf = SssChannelPdf(w->throughput, w->sigma_s, w->sigma_t);   // same value as in Prepare
+  const float t = is_hit ? hit_t : w->ray.tmax;
   const vec3 tr(expf(-w->sigma_t.x * t), expf(-w->sigma_t.y * t), expf(-w->sigma_t.z * t));
   if (is_hit) {
     const float pdf = vdot(channel_pdf, tr);
@@ -366,6 +376,13 @@ PBR_HD SssStep SssBounce(const SceneView& s, Pcg32* rng, SssWalkState* w, HitT* 
   w->bounce++;
   if (w->bounce > 8192u) return kSssAbsorbed;   // for (bounce = 0; bounce <= 8192; ++bounce)
   return kSssContinue;
+}
+
+PBR_HD SssStep SssBounce(const SceneView& s, Pcg32* rng, SssWalkState* w, HitT* hit, uint64_t* rays) {
+  SssPrepareSegment(rng, w);
+  const bool is_hit = TraceClosest<false>(s, w->ray, hit, nullptr);
+  if (rays) ++*rays;
+  return SssFinishSegment(is_hit, hit->t, rng, w);
 }
 
 // After a surface hit (:385-404) + the success branch of SampleBsdf (cycles-principled-shader.cc:187-216).

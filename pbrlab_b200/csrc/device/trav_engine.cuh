@@ -1,0 +1,168 @@
+// Warp-level traversal engine (device only): the same closest-hit / any-hit walk of the compressed 8-wide BVH as
+// TraverseBvh (traverse.cuh) — same node test, same primitive tests, same visiting order, hence the same hits — but
+// written as a RESUMABLE per-lane state machine so that a persistent warp can replace a finished ray by a new one
+// while its neighbours are still traversing.
+//
+// Why: measured on B200 (profiles/r1a_*.txt) the one-ray-per-lane-until-all-32-finish form executed its node step
+// with 7.0 and its triangle test with 3.0 of 32 lanes active: path-tracing rays have wildly different traversal
+// lengths (2 nodes for a wall, 40 for Lucy) and the warp waits for its slowest lane.  Here a lane that finishes goes
+// idle only until `refill_min_idle` lanes are idle; then the warp runs one converged section that consumes the
+// finished results and fetches new rays (one atomicAdd per warp), and traversal resumes with a full warp.
+//
+// Replaces Scene::TraceFirstHit1 / AnyHit1 -> rtcIntersect1 / rtcOccluded1 (reference src/scene.cc:261-268,
+// src/raytracer/raytracer_impl.cc:268-287); hit semantics are Embree's, see traverse.cuh.
+#pragma once
+#include "traverse.cuh"
+
+#if defined(__CUDACC__)
+namespace pbr {
+
+struct Trav {
+  vec3 O, D, inv_d, ood;   // origin, direction, 1/d (zero components nudged), o/d
+  float tmin, tfar;
+  uint32_t oct_inv4;       // octant-inversion mask replicated in 4 bytes (bit 2 = +x, 1 = +y, 0 = +z)
+  uint2 group;             // current node group: (child base, hit mask << 24 | imask)
+  int sp;                  // stack entries in use
+  bool active;             // still traversing
+  bool curves;             // walking the curve BVH (after the triangle BVH)
+  HitT hit;                // closest hit so far (prim == kInvalid: none)
+  uint32_t n_nodes, n_prims;   // STATS only
+};
+
+__device__ __forceinline__ void TravBegin(const SceneView& s, const RayT& ray, Trav& t) {
+  t.O = ray.o; t.D = ray.d;
+  t.tmin = ray.tmin; t.tfar = ray.tmax;
+  const float tiny = 1e-30f;
+  const vec3 ds(fabsf(ray.d.x) < tiny ? copysignf(tiny, ray.d.x) : ray.d.x,
+                fabsf(ray.d.y) < tiny ? copysignf(tiny, ray.d.y) : ray.d.y,
+                fabsf(ray.d.z) < tiny ? copysignf(tiny, ray.d.z) : ray.d.z);
+  t.inv_d = vec3(1.0f / ds.x, 1.0f / ds.y, 1.0f / ds.z);
+  t.ood = vec3(ray.o.x * t.inv_d.x, ray.o.y * t.inv_d.y, ray.o.z * t.inv_d.z);
+  t.oct_inv4 = (ds.x < 0.f ? 0u : 0x04040404u) | (ds.y < 0.f ? 0u : 0x02020202u) | (ds.z < 0.f ? 0u : 0x01010101u);
+  t.hit.prim = kInvalid;
+  t.hit.t = 0.f; t.hit.u = 0.f; t.hit.v = 0.f;
+  t.sp = 0;
+  t.curves = (s.num_tris == 0u);
+  t.group = make_uint2(0u, 0x80000000u);   // the root as the only child of a virtual parent (see TraverseBvh)
+  t.active = (s.num_tris | s.num_curves) != 0u;
+}
+
+// One trip of TraverseBvh's loop: at most one node test, then every primitive of the leaves it produced.
+template <bool ANY, bool HAS_CURVES, bool STATS>
+__device__ __forceinline__ void TravStep(const SceneView& s, Trav& t, uint2* __restrict__ stack) {
+  const bool in_curves = HAS_CURVES && t.curves;
+  const float4* __restrict__ nodes = in_curves ? s.curve_nodes : s.tri_nodes;
+  uint2 pgroup;
+  if (t.group.y & 0xff000000u) {
+    const uint32_t hits_imask = t.group.y;
+    const uint32_t child_bit = msb(hits_imask);
+    t.group.y &= ~(1u << child_bit);
+    if (t.group.y & 0xff000000u) {
+      if (t.sp < kStackSize) stack[t.sp++] = t.group;
+    }
+    const uint32_t slot = (child_bit - 24u) ^ (t.oct_inv4 & 0xffu);
+    const uint32_t rel = popc(hits_imask & ~(0xffffffffu << slot));
+    const uint32_t node = t.group.x + rel;
+    const float4 n0 = nodes[node * 5 + 0], n1 = nodes[node * 5 + 1], n2 = nodes[node * 5 + 2];
+    const float4 n3 = nodes[node * 5 + 3], n4 = nodes[node * 5 + 4];
+    if (STATS) t.n_nodes++;
+    const bool neg_x = !(t.oct_inv4 & 0x04u), neg_y = !(t.oct_inv4 & 0x02u), neg_z = !(t.oct_inv4 & 0x01u);
+    const uint32_t hitmask = NodeIntersect(t.ood, t.inv_d, t.oct_inv4, neg_x, neg_y, neg_z, t.tmin, t.tfar, n0, n1,
+                                           n2, n3, n4);
+    t.group.x = f2u(n1.x);
+    t.group.y = (hitmask & 0xff000000u) | extract_byte(f2u(n0.w), 3);
+    pgroup.x = f2u(n1.y);
+    pgroup.y = hitmask & 0x00ffffffu;
+  } else {
+    pgroup = t.group;
+    t.group = make_uint2(0u, 0u);
+  }
+  if (pgroup.y != 0u) {
+    if (in_curves) {
+      const CurveRaySpace rs = MakeCurveRaySpace(t.D);
+      const float4* __restrict__ prims = s.curve_data;
+      do {
+        const uint32_t bit = msb(pgroup.y);
+        pgroup.y &= ~(1u << bit);
+        const uint32_t idx = pgroup.x + bit;
+        if (STATS) t.n_prims++;
+        float ht, hu, hv;
+        const float4 c0 = prims[idx * 4 + 0], c1 = prims[idx * 4 + 1], c2 = prims[idx * 4 + 2],
+                     c3 = prims[idx * 4 + 3];
+        if (IntersectCurve(t.O, rs, t.tmin, t.tfar, c0, c1, c2, c3, &ht, &hu, &hv)) {
+          t.hit.t = ht; t.hit.u = hu; t.hit.v = hv;
+          t.hit.prim = idx | kCurveFlag;
+          t.tfar = ht;
+          if (ANY) { t.active = false; return; }
+        }
+      } while (pgroup.y != 0u);
+    } else {
+      const float4* __restrict__ prims = s.tri_data;
+      do {
+        const uint32_t bit = msb(pgroup.y);
+        pgroup.y &= ~(1u << bit);
+        const uint32_t idx = pgroup.x + bit;
+        if (STATS) t.n_prims++;
+        float ht, hu, hv;
+        const float4 a = prims[idx * 3 + 0], b = prims[idx * 3 + 1], c = prims[idx * 3 + 2];
+        if (IntersectTriangle(t.O, t.D, t.tmin, t.tfar, from4(a), from4(b), from4(c), &ht, &hu, &hv)) {
+          t.hit.t = ht; t.hit.u = hu; t.hit.v = hv;
+          t.hit.prim = idx;
+          t.tfar = ht;
+          if (ANY) { t.active = false; return; }
+        }
+      } while (pgroup.y != 0u);
+    }
+  }
+  if ((t.group.y & 0xff000000u) == 0u) {
+    if (t.sp == 0) {
+      if (HAS_CURVES && !t.curves && s.num_curves) {   // triangles done: the shortened ray goes through the curves
+        t.curves = true;
+        t.group = make_uint2(0u, 0x80000000u);
+      } else {
+        t.active = false;
+      }
+    } else {
+      t.group = stack[--t.sp];
+    }
+  }
+}
+
+// The engine loop.  `Client` supplies the converged section:
+//   bool Wants(const Trav& t, bool exhausted)  — per lane, for idle lanes: could a Refill give this lane work
+//        (a finished walk segment to continue, or a work source that is not dry yet)?
+//   bool Refill(Trav& t, bool exhausted)  — called by ALL 32 lanes, converged, so warp collectives are allowed.
+//        A lane with !t.active (1) consumes the result of the ray it just finished, if any, and (2) tries to obtain
+//        its next ray: on success it calls TravBegin (t.active == true).  Returns true when this lane found the
+//        work source empty.
+//   void End(const Trav& t)  — after the loop.
+// A Refill happens when at least `refill_min_idle` idle lanes want one, or when nobody is traversing.  The loop ends
+// when no lane is active after a Refill and the source is dry.
+template <bool ANY, bool HAS_CURVES, bool STATS, class Client>
+__device__ __forceinline__ void TravEngine(const SceneView& s, Client& client, uint32_t refill_min_idle) {
+  uint2 stack[kStackSize];
+  Trav t;
+  t.active = false;
+  t.n_nodes = 0; t.n_prims = 0;
+  bool exhausted = false;   // warp-uniform: the work source ran dry
+  for (;;) {
+    const unsigned act = __ballot_sync(0xffffffffu, t.active);
+    const unsigned want = __ballot_sync(0xffffffffu, !t.active && client.Wants(t, exhausted));
+    if (act == 0u || uint32_t(__popc(want)) >= refill_min_idle) {
+      const bool dry = client.Refill(t, exhausted);
+      exhausted = __any_sync(0xffffffffu, dry) || exhausted;
+      if (__ballot_sync(0xffffffffu, t.active) == 0u) {
+        if (exhausted) break;
+        continue;
+      }
+    }
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+      if (t.active) TravStep<ANY, HAS_CURVES, STATS>(s, t, stack);
+    }
+  }
+  client.End(t);
+}
+
+}  // namespace pbr
+#endif

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -116,6 +117,10 @@ struct pbrgpu_ctx {
   uint32_t wave_spp = 0;
   bool committed = false;
   bool profile = false;   // time every kernel family with CUDA events (pbrgpu_set_profiling)
+  // launch tuning (defaults measured on B200; PBRGPU_* environment variables override for sweeps)
+  uint32_t tune_refill = 16;       // idle lanes that trigger a refill in the traversal engine
+  uint32_t tune_refill_sss = 24;   // same for the random-walk kernel (its converged section is the bounce itself)
+  int tune_trace_blocks = 8, tune_shade_blocks = 4, tune_walk_blocks = 4;   // resident 128-thread blocks per SM
 };
 
 namespace {
@@ -222,7 +227,10 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
   const SceneView& s = d.view;
   const WaveState& w = d.wave;
   uint32_t parity = 0;
-  const int grid_trace = PersistentGrid(d, 8), grid_shade = PersistentGrid(d, 4);
+  const int grid_trace = PersistentGrid(d, ctx->tune_trace_blocks), grid_shade = PersistentGrid(d, ctx->tune_shade_blocks);
+  const int grid_walk = PersistentGrid(d, ctx->tune_walk_blocks);
+  const bool curves = s.num_curves != 0u;
+  const uint32_t refill = ctx->tune_refill;
   // state after the set-up kernel (host knows it): hooks start with n active slots, frames with N retired slots
   bool have_active = (frame == nullptr), have_walk = false, have_done = (frame != nullptr);
   uint64_t in_flight = ~0ull;   // slots that will trace or walk in the coming iteration (unknown before the first)
@@ -242,14 +250,17 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
       tm->launches += 1;
     }
     mark(1);
-    pbr::TraceClosestKernel<<<grid_trace, kBlock, 0, st>>>(s, w, parity);
+    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill);
+    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill);
     mark(2);
     pbr::ShadeSurfaceKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
     if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
     mark(3);
-    pbr::SssWalkKernel<<<grid_shade, kBlock, 0, st>>>(s, w, parity, walk_budget);
+    if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss);
+    else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss);
     mark(4);
-    pbr::TraceAnyKernel<<<grid_trace, kBlock, 0, st>>>(s, w);
+    if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, refill);
+    else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, refill);
     mark(5);
     tm->launches += s.num_curves ? 5 : 4;
     tm->closest_launches += 1;
@@ -427,6 +438,12 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   }
   pbrgpu_ctx* ctx = new pbrgpu_ctx();
   memset(&ctx->stats, 0, sizeof(ctx->stats));
+  auto env_int = [](const char* name, int def) { const char* v = getenv(name); return v && *v ? atoi(v) : def; };
+  ctx->tune_refill = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_REFILL", int(ctx->tune_refill)))));
+  ctx->tune_refill_sss = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_REFILL_SSS", int(ctx->tune_refill_sss)))));
+  ctx->tune_trace_blocks = std::max(1, env_int("PBRGPU_TRACE_BLOCKS", ctx->tune_trace_blocks));
+  ctx->tune_shade_blocks = std::max(1, env_int("PBRGPU_SHADE_BLOCKS", ctx->tune_shade_blocks));
+  ctx->tune_walk_blocks = std::max(1, env_int("PBRGPU_WALK_BLOCKS", ctx->tune_walk_blocks));
   for (int id : ids) {
     if (id < 0 || id >= ndev) {
       g_create_error = "pbrgpu_create: device id out of range";
@@ -676,9 +693,20 @@ int pbrgpu_trace_device(pbrgpu_ctx* ctx, const pbrgpu_ray* d_rays, uint64_t n, p
   CUDA_TRY(ctx, cudaMemsetAsync(d.counters.ptr, 0, sizeof(uint32_t) * pbr::kCounterCount, d.stream));
   CUDA_TRY(ctx, cudaMemsetAsync(d.stats.ptr, 0, sizeof(unsigned long long) * pbr::kStatCount, d.stream));
   CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
-  pbr::TraceBatchKernel<<<PersistentGrid(d, 8), kBlock, 0, d.stream>>>(
-      d.view, reinterpret_cast<const float4*>(d_rays), n, tuv.ptr, ids.ptr, ng.ptr, d.counters.ptr + pbr::kFetchTrace,
-      d.stats.ptr, collect_stats);
+  {
+    const int grid = PersistentGrid(d, ctx->tune_trace_blocks);
+    const float4* r4 = reinterpret_cast<const float4*>(d_rays);
+    uint32_t* fetch = d.counters.ptr + pbr::kFetchTrace;
+    const bool curves = d.view.num_curves != 0u;
+#define PBR_LAUNCH_BATCH(C, S)                                                                                    \
+    pbr::TraceBatchKernel<C, S><<<grid, kBlock, 0, d.stream>>>(d.view, r4, n, tuv.ptr, ids.ptr, ng.ptr, fetch,   \
+                                                                d.stats.ptr, ctx->tune_refill)
+    if (curves && collect_stats) PBR_LAUNCH_BATCH(true, true);
+    else if (curves) PBR_LAUNCH_BATCH(true, false);
+    else if (collect_stats) PBR_LAUNCH_BATCH(false, true);
+    else PBR_LAUNCH_BATCH(false, false);
+#undef PBR_LAUNCH_BATCH
+  }
   CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
   if (d_hits) {
     // interleave the three SoA outputs into the caller's array-of-structs (pbrgpu_hit = 9 words)
@@ -714,8 +742,14 @@ int pbrgpu_occluded_device(pbrgpu_ctx* ctx, const pbrgpu_ray* d_rays, uint64_t n
   if (rc != PBRGPU_OK) return rc;
   CUDA_TRY(ctx, cudaMemsetAsync(d.counters.ptr, 0, sizeof(uint32_t) * pbr::kCounterCount, d.stream));
   CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
-  pbr::OccludedBatchKernel<<<PersistentGrid(d, 8), kBlock, 0, d.stream>>>(
-      d.view, reinterpret_cast<const float4*>(d_rays), n, d_occluded, d.counters.ptr + pbr::kFetchShadow);
+  if (d.view.num_curves)
+    pbr::OccludedBatchKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(
+        d.view, reinterpret_cast<const float4*>(d_rays), n, d_occluded, d.counters.ptr + pbr::kFetchShadow,
+        ctx->tune_refill);
+  else
+    pbr::OccludedBatchKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(
+        d.view, reinterpret_cast<const float4*>(d_rays), n, d_occluded, d.counters.ptr + pbr::kFetchShadow,
+        ctx->tune_refill);
   CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
   CUDA_TRY(ctx, cudaGetLastError());
@@ -797,7 +831,10 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
     DevBuf<float> dface;
     CUDA_TRY(ctx, dface.Alloc(2 * n));
     pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters, 0u);
-    pbr::TraceClosestKernel<<<PersistentGrid(d, 8), kBlock, 0, d.stream>>>(d.view, d.wave, 0u);
+    if (d.view.num_curves)
+      pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill);
+    else
+      pbr::TraceClosestKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill);
     SurfaceFaceKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.view, d.wave, n32, dface.ptr);
     // restore the entry state for the real iteration below
     pbr::InitPathsFromRaysKernel<<<(std::max(n32, 64u) + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);

@@ -33,6 +33,7 @@
 #include <cuda_runtime.h>
 
 #include "device/shade.cuh"
+#include "device/trav_engine.cuh"
 
 namespace pbr {
 
@@ -255,24 +256,25 @@ __global__ void InitPathsFromRaysKernel(WaveState w, const float4* rays, const u
 
 // ------------------------------------------------------------------------------------------------ closest hit
 // Scene::TraceFirstHit1 for every active slot; routes it by the material kind of what it hit, retires it on a miss.
-__global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState w, uint32_t cur_parity) {
-  const uint32_t n = w.counters[kNumActive0 + cur_parity];
-  const uint32_t* __restrict__ queue = w.q_active[cur_parity];
-  const uint32_t next_parity = cur_parity ^ 1u;
+// Runs in the warp traversal engine (device/trav_engine.cuh): lanes are refilled from q_active while others traverse.
+struct ClosestClient {
+  const SceneView& s;
+  const WaveState& w;
+  const uint32_t* __restrict__ queue;
+  uint32_t n, next_parity;
+  uint32_t p = 0;
+  bool has_result = false;
   unsigned long long rays = 0;
-  for (;;) {
-    const uint32_t slot = WarpFetch(&w.counters[kFetchTrace]);
-    if (__all_sync(0xffffffffu, slot >= n)) break;
-    const bool valid = slot < n;
-    uint32_t p = 0;
-    HitT hit;
-    hit.prim = kInvalid;
+
+  __device__ __forceinline__ ClosestClient(const SceneView& s_, const WaveState& w_, uint32_t cur_parity)
+      : s(s_), w(w_), queue(w_.q_active[cur_parity]), n(w_.counters[kNumActive0 + cur_parity]),
+        next_parity(cur_parity ^ 1u) {}
+  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
+  __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     int kind = -1;   // -1 nothing, 0 miss, 1 surface queue, 2 hair queue
-    if (valid) {
-      p = queue[slot];
-      const RayT ray = LoadRay(w, p);
-      TraceClosest<false>(s, ray, &hit, nullptr);
-      ++rays;
+    if (!t.active && has_result) {
+      has_result = false;
+      const HitT hit = t.hit;
       w.hit[p] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
       kind = 0;
       if (hit.prim != kInvalid) {
@@ -282,14 +284,40 @@ __global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState
         kind = (mat < s.num_materials && s.materials[mat].type == 1u) ? 2 : 1;
       }
     }
+    const uint32_t done_p = p;
     const uint32_t a = WarpAppend(&w.counters[kNumSurface], kind == 1);
-    if (kind == 1) w.q_surface[a] = p;
+    if (kind == 1) w.q_surface[a] = done_p;
     const uint32_t b = WarpAppend(&w.counters[kNumHair], kind == 2);
-    if (kind == 2) w.q_hair[b] = p;
+    if (kind == 2) w.q_hair[b] = done_p;
     const uint32_t c = WarpAppend(&w.counters[kNumDone0 + next_parity], kind == 0);
-    if (kind == 0) w.q_done[next_parity][c] = p;
+    if (kind == 0) w.q_done[next_parity][c] = done_p;
+    bool dry = false;
+    if (!exhausted) {
+      const bool need = !t.active;
+      const uint32_t slot = WarpAppend(&w.counters[kFetchTrace], need);
+      if (need) {
+        if (slot < n) {
+          p = queue[slot];
+          TravBegin(s, LoadRay(w, p), t);
+          has_result = true;
+          ++rays;
+        } else {
+          dry = true;
+        }
+      }
+    }
+    return dry;
   }
-  if (rays) atomicAdd(&w.stats[kStatClosest], rays);
+  __device__ __forceinline__ void End(const Trav&) {
+    if (rays) atomicAdd(&w.stats[kStatClosest], rays);
+  }
+};
+
+template <bool HAS_CURVES>
+__global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState w, uint32_t cur_parity,
+                                                          uint32_t refill_min_idle) {
+  ClosestClient client(s, w, cur_parity);
+  TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle);
 }
 
 // ------------------------------------------------------------------------------------------------ shading
@@ -440,68 +468,40 @@ __device__ __forceinline__ void ResumeWalk(const WaveState& w, uint32_t p, SssWa
   k->bounce = w.walk_n[p];
 }
 
-__global__ void __launch_bounds__(128) SssWalkKernel(SceneView s, WaveState w, uint32_t cur_parity,
-                                                     uint32_t max_bounces) {
-  const uint32_t next_parity = cur_parity ^ 1u;
-  const uint32_t n_resume = w.counters[kNumWalk0 + cur_parity];
-  const uint32_t n = n_resume + w.counters[kNumSss];
-  const int lane = threadIdx.x & 31;
-  bool active = false, exhausted = false;
+struct SssClient {
+  const SceneView& s;
+  const WaveState& w;
+  uint32_t cur_parity, next_parity, n_resume, n, max_bounces;
   uint32_t p = 0, budget = 0;
+  bool has_walk = false;
   Pcg32 rng;
-  SssWalkState walk;
+  SssWalkState walk;    // walk.ray is rebuilt from the traversal state after every segment
   unsigned long long rays = 0;
 
-  for (;;) {
-    // ---- refill idle lanes
-    bool rejected = false;
-    const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
-    if (want) {
-      uint32_t base = 0;
-      const int leader = __ffs(want) - 1;
-      if (lane == leader) base = atomicAdd(&w.counters[kFetchSss], uint32_t(__popc(want)));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (!active && !exhausted) {
-        const uint32_t slot = base + uint32_t(__popc(want & ((1u << lane) - 1u)));
-        if (slot >= n) {
-          exhausted = true;
-        } else {
-          const bool resume = slot < n_resume;
-          p = resume ? w.q_walk[cur_parity][slot] : w.q_sss[slot - n_resume];
-          const ulonglong2 rs = w.rng[p];
-          rng.state = rs.x; rng.inc = rs.y;
-          budget = max_bounces;
-          if (resume) {
-            ResumeWalk(w, p, &walk);
-            active = true;
-          } else {
-            const RayT ray = LoadRay(w, p);
-            const Surface entry_si = MakeSurface(s, ray, LoadHit(w, p));
-            const Frame entry_frame = PrincipledFrame(entry_si);
-            const PrincipledBsdf bsdf = SurfaceBsdf(s, entry_si);
-            active = SssBegin(entry_si, entry_frame, bsdf, &rng, &walk);
-            if (!active) {   // walk rejected: the path's throughput becomes 0 and it ends
-              const float4 t4 = w.thr[p], r4 = w.rad[p];
-              VertexResult vr;
-              vr.P = entry_si.P;
-              FinishPrincipled(entry_frame, vec3(0.f), vec3(0.f), 0.f, &vr);
-              CommitVertex(w, p, vr, vec3(t4.x, t4.y, t4.z), vec3(r4.x, r4.y, r4.z), __float_as_uint(r4.w), rng);
-              rejected = true;
-            }
-          }
-        }
-      }
-    }
-    if (__all_sync(0xffffffffu, !active && exhausted && !rejected)) break;
+  __device__ __forceinline__ SssClient(const SceneView& s_, const WaveState& w_, uint32_t cur, uint32_t max_b)
+      : s(s_), w(w_), cur_parity(cur), next_parity(cur ^ 1u), n_resume(w_.counters[kNumWalk0 + cur]),
+        n(w_.counters[kNumWalk0 + cur] + w_.counters[kNumSss]), max_bounces(max_b) {}
+  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_walk || !exhausted; }
 
-    // ---- one bounce for every walking lane
-    bool to_next = false, to_done = rejected, to_park = false;
+  __device__ __forceinline__ void StartSegment(Trav& t) {
+    SssPrepareSegment(&rng, &walk);
+    TravBegin(s, walk.ray, t);
+    if (!t.active) {   // empty scene: the segment ends without a hit
+      t.hit.prim = kInvalid;
+    }
+  }
+
+  __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
+    // ---- (1) walks whose segment query finished: scatter / exit / absorb
+    bool to_next = false, to_done = false, to_park = false;
     ShadowRequest req;
     req.active = false;
     vec3 throughput(0.f);
-    if (active) {
-      HitT hit;
-      const SssStep st = SssBounce(s, &rng, &walk, &hit, nullptr);
+    uint32_t routed_p = p;
+    if (!t.active && has_walk) {
+      walk.ray.o = t.O; walk.ray.d = t.D; walk.ray.tmin = t.tmin;   // tmax untouched: the scatter distance
+      const bool is_hit = t.hit.prim != kInvalid;
+      const SssStep st = SssFinishSegment(is_hit, t.hit.t, &rng, &walk);
       ++rays;
       --budget;
       if (st != kSssContinue) {
@@ -514,107 +514,216 @@ __global__ void __launch_bounds__(128) SssWalkKernel(SceneView s, WaveState w, u
         VertexResult vr;
         vr.P = entry_si.P;
         vr.shadow[1].active = false;
-        if (st == kSssHit) SssFinish(s, entry_si, entry_frame, walk, hit, &rng, &vr);
+        if (st == kSssHit) SssFinish(s, entry_si, entry_frame, walk, t.hit, &rng, &vr);
         else FinishPrincipled(entry_frame, vec3(0.f), vec3(0.f), 0.f, &vr);
         req = vr.shadow[1];
         CommitVertex(w, p, vr, throughput, vec3(r4.x, r4.y, r4.z), __float_as_uint(r4.w), rng);
         to_next = !IsBlack(vr.throughput * throughput);
         to_done = !to_next;
-        active = false;
+        has_walk = false;
       } else if (budget == 0u) {
         ParkWalk(w, p, walk);
         w.rng[p] = make_ulonglong2(rng.state, rng.inc);
         to_park = true;
-        active = false;
+        has_walk = false;
+      } else {
+        StartSegment(t);
       }
     }
-    PushShadow(w, req, throughput, p);
-    RouteSlot(w, next_parity, p, to_next, to_done);
+    PushShadow(w, req, throughput, routed_p);
+    RouteSlot(w, next_parity, routed_p, to_next, to_done);
     const uint32_t c = WarpAppend(&w.counters[kNumWalk0 + next_parity], to_park);
-    if (to_park) w.q_walk[next_parity][c] = p;
+    if (to_park) w.q_walk[next_parity][c] = routed_p;
+
+    // ---- (2) lanes without a walk take the next one: parked walks first, then this iteration's new ones
+    bool dry = false, rejected = false;
+    if (!exhausted) {
+      const bool need = !t.active && !has_walk;
+      const uint32_t slot = WarpAppend(&w.counters[kFetchSss], need);
+      if (need) {
+        if (slot >= n) {
+          dry = true;
+        } else {
+          const bool resume = slot < n_resume;
+          p = resume ? w.q_walk[cur_parity][slot] : w.q_sss[slot - n_resume];
+          const ulonglong2 rs = w.rng[p];
+          rng.state = rs.x; rng.inc = rs.y;
+          budget = max_bounces;
+          if (resume) {
+            ResumeWalk(w, p, &walk);
+            has_walk = true;
+          } else {
+            const RayT ray = LoadRay(w, p);
+            const Surface entry_si = MakeSurface(s, ray, LoadHit(w, p));
+            const Frame entry_frame = PrincipledFrame(entry_si);
+            const PrincipledBsdf bsdf = SurfaceBsdf(s, entry_si);
+            has_walk = SssBegin(entry_si, entry_frame, bsdf, &rng, &walk);
+            if (!has_walk) {   // walk rejected: the path's throughput becomes 0 and it ends
+              const float4 t4 = w.thr[p], r4 = w.rad[p];
+              VertexResult vr;
+              vr.P = entry_si.P;
+              FinishPrincipled(entry_frame, vec3(0.f), vec3(0.f), 0.f, &vr);
+              CommitVertex(w, p, vr, vec3(t4.x, t4.y, t4.z), vec3(r4.x, r4.y, r4.z), __float_as_uint(r4.w), rng);
+              rejected = true;
+            }
+          }
+          if (has_walk) StartSegment(t);
+        }
+      }
+      RouteSlot(w, next_parity, p, false, rejected);
+    }
+    return dry;
   }
-  if (rays) atomicAdd(&w.stats[kStatSss], rays);
+  __device__ __forceinline__ void End(const Trav&) {
+    if (rays) atomicAdd(&w.stats[kStatSss], rays);
+  }
+};
+
+template <bool HAS_CURVES>
+__global__ void __launch_bounds__(128) SssWalkKernel(SceneView s, WaveState w, uint32_t cur_parity,
+                                                     uint32_t max_bounces, uint32_t refill_min_idle) {
+  SssClient client(s, w, cur_parity, max_bounces);
+  TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle);
 }
 
 // ------------------------------------------------------------------------------------------------ shadow rays
 // Scene::AnyHit1 for every NEE request; unoccluded contributions are added to their path's radiance.  A path can
 // have two requests in flight in one iteration (entry + SSS exit), hence the atomics (never contended).
-__global__ void __launch_bounds__(128) TraceAnyKernel(SceneView s, WaveState w) {
-  const uint32_t n = w.counters[kNumShadow];
+struct ShadowClient {
+  const SceneView& s;
+  const WaveState& w;
+  uint32_t n;
+  float4 c;
+  bool has_result = false;
   unsigned long long rays = 0;
-  for (;;) {
-    const uint32_t slot = WarpFetch(&w.counters[kFetchShadow]);
-    if (__all_sync(0xffffffffu, slot >= n)) break;
-    if (slot < n) {
-      const float4 o = w.sh_o[slot], d = w.sh_d[slot], c = w.sh_c[slot];
-      RayT ray;
-      ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
-      ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
-      ++rays;
-      if (!TraceAny<false>(s, ray, nullptr)) {
+
+  __device__ __forceinline__ ShadowClient(const SceneView& s_, const WaveState& w_)
+      : s(s_), w(w_), n(w_.counters[kNumShadow]) {}
+  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
+  __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
+    if (!t.active && has_result) {
+      has_result = false;
+      if (t.hit.prim == kInvalid) {
         float* dst = reinterpret_cast<float*>(&w.rad[__float_as_uint(c.w)]);
         atomicAdd(dst + 0, c.x);
         atomicAdd(dst + 1, c.y);
         atomicAdd(dst + 2, c.z);
       }
     }
+    bool dry = false;
+    if (!exhausted) {
+      const bool need = !t.active;
+      const uint32_t slot = WarpAppend(&w.counters[kFetchShadow], need);
+      if (need) {
+        if (slot < n) {
+          const float4 o = w.sh_o[slot], d = w.sh_d[slot];
+          c = w.sh_c[slot];
+          RayT ray;
+          ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
+          ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
+          TravBegin(s, ray, t);
+          has_result = true;
+          ++rays;
+        } else {
+          dry = true;
+        }
+      }
+    }
+    return dry;
   }
-  if (rays) atomicAdd(&w.stats[kStatShadow], rays);
+  __device__ __forceinline__ void End(const Trav&) {
+    if (rays) atomicAdd(&w.stats[kStatShadow], rays);
+  }
+};
+
+template <bool HAS_CURVES>
+__global__ void __launch_bounds__(128) TraceAnyKernel(SceneView s, WaveState w, uint32_t refill_min_idle) {
+  ShadowClient client(s, w);
+  TravEngine<true, HAS_CURVES, false>(s, client, refill_min_idle);
 }
 
 // ------------------------------------------------------------------------------------------------ test hooks
-__global__ void __launch_bounds__(128) TraceBatchKernel(SceneView s, const float4* __restrict__ rays, uint64_t n,
-                                                        float4* hits_tuv, uint4* hits_ids, float4* hits_ng,
-                                                        uint32_t* fetch, unsigned long long* stats, int collect) {
-  TraverseStats st;
-  st.nodes = 0; st.prims = 0;
-  for (;;) {
-    const uint64_t slot = uint64_t(WarpFetch(fetch));
-    if (__all_sync(0xffffffffu, slot >= n)) break;
-    if (slot < n) {
-      const float4 o = rays[2 * slot], d = rays[2 * slot + 1];
-      RayT ray;
-      ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
-      ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
-      HitT hit;
-      if (collect) TraceClosest<true>(s, ray, &hit, &st);
-      else TraceClosest<false>(s, ray, &hit, nullptr);
+// pbrgpu_trace / pbrgpu_occluded: caller-supplied ray batches through the same engine as the render kernels
+struct BatchClient {
+  const SceneView& s;
+  const float4* __restrict__ rays;
+  uint64_t n;
+  float4* hits_tuv;
+  uint4* hits_ids;
+  float4* hits_ng;
+  uint8_t* occluded;
+  uint32_t* fetch;
+  unsigned long long* stats;
+  uint64_t slot_of_result = 0;
+  bool has_result = false;
+
+  __device__ __forceinline__ BatchClient(const SceneView& s_, const float4* r, uint64_t n_, float4* tuv, uint4* ids,
+                                         float4* ng, uint8_t* occ, uint32_t* f, unsigned long long* st)
+      : s(s_), rays(r), n(n_), hits_tuv(tuv), hits_ids(ids), hits_ng(ng), occluded(occ), fetch(f), stats(st) {}
+  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
+  __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
+    if (!t.active && has_result) {
+      has_result = false;
+      const HitT hit = t.hit;
+      const uint64_t slot = slot_of_result;
+      if (occluded) occluded[slot] = (hit.prim != kInvalid) ? 1 : 0;
       if (hits_tuv) {
         uint4 ids = make_uint4(kInvalid, kInvalid, kInvalid, kInvalid);
         vec3 ng(1.f, 0.f, 0.f);
-        float t = 1.0f, u = 0.f, v = 0.f;
+        float ht = 1.0f, hu = 0.f, hv = 0.f;
         if (hit.prim != kInvalid) {
           ng = HitGeometricNormal(s, hit);
-          t = hit.t; u = hit.u; v = hit.v;
+          ht = hit.t; hu = hit.u; hv = hit.v;
           if (hit.prim & kCurveFlag) ids = s.curve_ids[s.curve_prim[hit.prim & ~kCurveFlag]];
           else ids = s.tri_ids[__float_as_uint(s.tri_data[hit.prim * 3].w)];
         }
-        hits_tuv[slot] = make_float4(t, u, v, 0.f);
+        hits_tuv[slot] = make_float4(ht, hu, hv, 0.f);
         hits_ids[slot] = ids;
         hits_ng[slot] = make_float4(ng.x, ng.y, ng.z, 0.f);
       }
     }
+    bool dry = false;
+    if (!exhausted) {
+      const bool need = !t.active;
+      const uint64_t slot = uint64_t(WarpAppend(fetch, need));
+      if (need) {
+        if (slot < n) {
+          const float4 o = rays[2 * slot], d = rays[2 * slot + 1];
+          RayT ray;
+          ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
+          ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
+          TravBegin(s, ray, t);
+          slot_of_result = slot;
+          has_result = true;
+        } else {
+          dry = true;
+        }
+      }
+    }
+    return dry;
   }
-  if (collect) {
-    atomicAdd(&stats[kStatNodes], (unsigned long long)st.nodes);
-    atomicAdd(&stats[kStatPrims], (unsigned long long)st.prims);
-  }
-}
-
-__global__ void __launch_bounds__(128) OccludedBatchKernel(SceneView s, const float4* __restrict__ rays, uint64_t n,
-                                                           uint8_t* out, uint32_t* fetch) {
-  for (;;) {
-    const uint64_t slot = uint64_t(WarpFetch(fetch));
-    if (__all_sync(0xffffffffu, slot >= n)) break;
-    if (slot < n) {
-      const float4 o = rays[2 * slot], d = rays[2 * slot + 1];
-      RayT ray;
-      ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
-      ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
-      const bool occ = TraceAny<false>(s, ray, nullptr);
-      if (out) out[slot] = occ ? 1 : 0;
+  __device__ __forceinline__ void End(const Trav& t) {
+    if (stats) {
+      atomicAdd(&stats[kStatNodes], (unsigned long long)t.n_nodes);
+      atomicAdd(&stats[kStatPrims], (unsigned long long)t.n_prims);
     }
   }
+};
+
+template <bool HAS_CURVES, bool STATS>
+__global__ void __launch_bounds__(128) TraceBatchKernel(SceneView s, const float4* __restrict__ rays, uint64_t n,
+                                                        float4* hits_tuv, uint4* hits_ids, float4* hits_ng,
+                                                        uint32_t* fetch, unsigned long long* stats,
+                                                        uint32_t refill_min_idle) {
+  BatchClient client(s, rays, n, hits_tuv, hits_ids, hits_ng, nullptr, fetch, STATS ? stats : nullptr);
+  TravEngine<false, HAS_CURVES, STATS>(s, client, refill_min_idle);
+}
+
+template <bool HAS_CURVES>
+__global__ void __launch_bounds__(128) OccludedBatchKernel(SceneView s, const float4* __restrict__ rays, uint64_t n,
+                                                           uint8_t* out, uint32_t* fetch, uint32_t refill_min_idle) {
+  BatchClient client(s, rays, n, nullptr, nullptr, nullptr, out, fetch, nullptr);
+  TravEngine<true, HAS_CURVES, false>(s, client, refill_min_idle);
 }
 
 }  // namespace pbr
