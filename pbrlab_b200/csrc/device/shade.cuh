@@ -252,10 +252,11 @@ PBR_HD Frame PrincipledFrame(const Surface& si) {
 }
 
 // CyclesPrincipledShader (cycles-principled-shader.cc:414-484).  Returns true when the sampled closure is the
-// random walk: the caller then runs SubsurfaceVertex (possibly in another kernel); rng is left right after the
-// selector draw in that case.
+// random walk: the caller then runs the walk (SubsurfaceVertex, or SssBegin + the wavefront's walk kernels); rng is
+// left right after the selector draw in that case.  fr_out / bsdf_out: the shading frame and closure set of the
+// vertex, for the caller that continues with the walk.
 PBR_HD bool PrincipledVertex(const SceneView& s, const Surface& si, const vec3& wo_world, Pcg32* rng,
-                             VertexResult* out) {
+                             VertexResult* out, Frame* fr_out, PrincipledBsdf* bsdf_out) {
   if (si.face == kAmbiguous) {
     AbsorbVertex(wo_world, si.P, out);
     return false;
@@ -270,12 +271,22 @@ PBR_HD bool PrincipledVertex(const SceneView& s, const Surface& si, const vec3& 
 
   const SampleWeight w = FetchClosureSampleWeight(wo, bsdf);
   const float select = Draw(rng);
-  if (!(select < w.diffuse) && select < w.diffuse + w.subsurface) return true;
+  if (!(select < w.diffuse) && select < w.diffuse + w.subsurface) {
+    *fr_out = fr;
+    *bsdf_out = bsdf;
+    return true;
+  }
   vec3 wi(0.f), f(0.f);
   float pdf = 0.f;
   SampleBsdfLobes(bsdf, w, select, wo, rng, &wi, &f, &pdf);
   FinishPrincipled(fr, wi, f, pdf, out);
   return false;
+}
+PBR_HD bool PrincipledVertex(const SceneView& s, const Surface& si, const vec3& wo_world, Pcg32* rng,
+                             VertexResult* out) {
+  Frame fr;
+  PrincipledBsdf bsdf;
+  return PrincipledVertex(s, si, wo_world, rng, out, &fr, &bsdf);
 }
 
 // ---------------------------------------------------------------- random-walk SSS (random-walk-sss.h)

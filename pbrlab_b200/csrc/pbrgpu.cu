@@ -74,9 +74,8 @@ struct Device {
   DevBuf<pbr::LightRec> lights;
   pbr::SceneView view;
   // wave
-  DevBuf<float4> ray_o, ray_d, hit, thr, rad, sh_o, sh_d, sh_c, walk_a, walk_b, walk_c, walk_d;
-  DevBuf<ulonglong2> rng;
-  DevBuf<uint32_t> q0, q1, q_surface, q_hair, q_sss, q_walk0, q_walk1, walk_n, q_done0, q_done1, pixel, counters;
+  DevBuf<float4> slot, walk, sh_o, sh_d, sh_c;
+  DevBuf<uint32_t> q0, q1, q_surface, q_hair, q_sss, q_exit, q_walk0, q_walk1, q_done0, q_done1, counters;
   DevBuf<unsigned long long> stats;
   pbr::WaveState wave;
   uint32_t wave_capacity = 0;
@@ -92,10 +91,9 @@ struct Device {
     emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); lprim_tri.Free(); tri_ids.Free();
     tri_nidx.Free(); tri_vidx.Free(); tri_tidx.Free(); curve_ids.Free(); materials.Free(); light_cdf.Free();
     lprim_cdf.Free(); lights.Free();
-    ray_o.Free(); ray_d.Free(); hit.Free(); thr.Free(); rad.Free(); sh_o.Free(); sh_d.Free(); sh_c.Free();
-    rng.Free(); q0.Free(); q1.Free(); q_surface.Free(); q_hair.Free(); q_sss.Free(); counters.Free(); stats.Free();
-    walk_a.Free(); walk_b.Free(); walk_c.Free(); walk_d.Free(); q_walk0.Free(); q_walk1.Free(); walk_n.Free();
-    q_done0.Free(); q_done1.Free(); pixel.Free();
+    slot.Free(); walk.Free(); sh_o.Free(); sh_d.Free(); sh_c.Free();
+    q0.Free(); q1.Free(); q_surface.Free(); q_hair.Free(); q_sss.Free(); q_exit.Free(); counters.Free(); stats.Free();
+    q_walk0.Free(); q_walk1.Free(); q_done0.Free(); q_done1.Free();
     rgba.Free(); count.Free();
     if (h_counters) cudaFreeHost(h_counters);
     if (h_stats) cudaFreeHost(h_stats);
@@ -120,7 +118,8 @@ struct pbrgpu_ctx {
   // launch tuning (defaults measured on B200; PBRGPU_* environment variables override for sweeps)
   uint32_t tune_refill = 16;       // idle lanes that trigger a refill in the traversal engine
   uint32_t tune_refill_sss = 24;   // same for the random-walk kernel (its converged section is the bounce itself)
-  int tune_trace_blocks = 8, tune_shade_blocks = 4, tune_walk_blocks = 4;   // resident 128-thread blocks per SM
+  uint32_t tune_prim_lanes = 1, tune_prim_lanes_sss = 1;   // lanes with pending primitives that trigger a primitive phase
+  int tune_trace_blocks = 8, tune_shade_blocks = 4, tune_walk_blocks = 6;   // resident 128-thread blocks per SM
 };
 
 namespace {
@@ -180,18 +179,13 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
 int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
   CUDA_TRY(ctx, cudaSetDevice(d.id));
   if (capacity > d.wave_capacity) {
-    CUDA_TRY(ctx, d.ray_o.Alloc(capacity)); CUDA_TRY(ctx, d.ray_d.Alloc(capacity));
-    CUDA_TRY(ctx, d.hit.Alloc(capacity)); CUDA_TRY(ctx, d.thr.Alloc(capacity));
-    CUDA_TRY(ctx, d.rad.Alloc(capacity)); CUDA_TRY(ctx, d.rng.Alloc(capacity));
+    CUDA_TRY(ctx, d.slot.Alloc(size_t(capacity) * pbr::kSlotStride));
+    CUDA_TRY(ctx, d.walk.Alloc(size_t(capacity) * pbr::kWalkStride));
     CUDA_TRY(ctx, d.q0.Alloc(capacity)); CUDA_TRY(ctx, d.q1.Alloc(capacity));
     CUDA_TRY(ctx, d.q_surface.Alloc(capacity)); CUDA_TRY(ctx, d.q_hair.Alloc(capacity));
-    CUDA_TRY(ctx, d.q_sss.Alloc(capacity));
+    CUDA_TRY(ctx, d.q_sss.Alloc(capacity)); CUDA_TRY(ctx, d.q_exit.Alloc(capacity));
     CUDA_TRY(ctx, d.q_walk0.Alloc(capacity)); CUDA_TRY(ctx, d.q_walk1.Alloc(capacity));
-    CUDA_TRY(ctx, d.walk_a.Alloc(capacity)); CUDA_TRY(ctx, d.walk_b.Alloc(capacity));
-    CUDA_TRY(ctx, d.walk_c.Alloc(capacity)); CUDA_TRY(ctx, d.walk_d.Alloc(capacity));
-    CUDA_TRY(ctx, d.walk_n.Alloc(capacity));
     CUDA_TRY(ctx, d.q_done0.Alloc(capacity)); CUDA_TRY(ctx, d.q_done1.Alloc(capacity));
-    CUDA_TRY(ctx, d.pixel.Alloc(capacity));
     CUDA_TRY(ctx, d.sh_o.Alloc(size_t(2) * capacity)); CUDA_TRY(ctx, d.sh_d.Alloc(size_t(2) * capacity));
     CUDA_TRY(ctx, d.sh_c.Alloc(size_t(2) * capacity));
     d.wave_capacity = capacity;
@@ -201,12 +195,11 @@ int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
   if (!d.h_counters) CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&d.h_counters), sizeof(uint32_t) * pbr::kCounterCount));
   if (!d.h_stats) CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&d.h_stats), sizeof(unsigned long long) * pbr::kStatCount));
   WaveState& w = d.wave;
-  w.ray_o = d.ray_o.ptr; w.ray_d = d.ray_d.ptr; w.hit = d.hit.ptr; w.thr = d.thr.ptr; w.rad = d.rad.ptr;
-  w.rng = d.rng.ptr; w.q_active[0] = d.q0.ptr; w.q_active[1] = d.q1.ptr; w.q_surface = d.q_surface.ptr;
-  w.q_hair = d.q_hair.ptr; w.q_sss = d.q_sss.ptr;
-  w.q_walk[0] = d.q_walk0.ptr; w.q_walk[1] = d.q_walk1.ptr; w.walk_a = d.walk_a.ptr; w.walk_b = d.walk_b.ptr;
-  w.walk_c = d.walk_c.ptr; w.walk_d = d.walk_d.ptr; w.walk_n = d.walk_n.ptr;
-  w.q_done[0] = d.q_done0.ptr; w.q_done[1] = d.q_done1.ptr; w.pixel = d.pixel.ptr;
+  w.slot = d.slot.ptr; w.walk = d.walk.ptr;
+  w.q_active[0] = d.q0.ptr; w.q_active[1] = d.q1.ptr; w.q_surface = d.q_surface.ptr;
+  w.q_hair = d.q_hair.ptr; w.q_sss = d.q_sss.ptr; w.q_exit = d.q_exit.ptr;
+  w.q_walk[0] = d.q_walk0.ptr; w.q_walk[1] = d.q_walk1.ptr;
+  w.q_done[0] = d.q_done0.ptr; w.q_done[1] = d.q_done1.ptr;
   w.sh_o = d.sh_o.ptr; w.sh_d = d.sh_d.ptr; w.sh_c = d.sh_c.ptr;
   w.counters = d.counters.ptr; w.stats = d.stats.ptr; w.capacity = d.wave_capacity;
   return PBRGPU_OK;
@@ -250,19 +243,20 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
       tm->launches += 1;
     }
     mark(1);
-    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill);
-    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill);
+    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes);
+    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes);
     mark(2);
     pbr::ShadeSurfaceKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
     if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
     mark(3);
-    if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss);
-    else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss);
+    if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
+    else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
+    pbr::SssExitKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next);
     mark(4);
-    if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, refill);
-    else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, refill);
+    if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, refill, ctx->tune_prim_lanes);
+    else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, refill, ctx->tune_prim_lanes);
     mark(5);
-    tm->launches += s.num_curves ? 5 : 4;
+    tm->launches += s.num_curves ? 6 : 5;
     tm->closest_launches += 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(d.h_counters, w.counters, sizeof(uint32_t) * pbr::kCounterCount,
                                   cudaMemcpyDeviceToHost, st));
@@ -340,7 +334,6 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   frame.first_sample = sample_offset;
   frame.sample_stride = sample_stride;
   frame.rgba = d.rgba.ptr;
-  frame.count = d.count.ptr;
 
   CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
   pbr::ResetPoolKernel<<<(std::max<uint32_t>(n_slots, 64) + 255) / 256, 256, 0, d.stream>>>(d.wave, n_slots);
@@ -349,6 +342,8 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   flags.skip_emission_and_roulette = 0;
   rc = RunPool(ctx, d, &frame, 0xffffffffu, flags, tm, cancel, finish_pass, sample_offset, sample_stride, spp);
   if (rc != PBRGPU_OK) return rc;
+  pbr::FinishFrameKernel<<<(npix + 255) / 256, 256, 0, d.stream>>>(d.rgba.ptr, d.count.ptr, npix);
+  tm->launches++;
   CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
   float ms = 0.f;
@@ -377,9 +372,7 @@ __global__ void KatKernel(int op, const float* params, const float* in, uint32_t
 __global__ void SurfaceFaceKernel(pbr::SceneView s, pbr::WaveState w, uint32_t n, float* face_t) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  const float4 h4 = w.hit[p];
-  pbr::HitT hit;
-  hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
+  const pbr::HitT hit = pbr::LoadHit(w, p);
   face_t[2 * p] = -1.f;
   face_t[2 * p + 1] = 0.f;
   if (hit.prim == pbr::kInvalid) return;
@@ -441,6 +434,8 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   auto env_int = [](const char* name, int def) { const char* v = getenv(name); return v && *v ? atoi(v) : def; };
   ctx->tune_refill = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_REFILL", int(ctx->tune_refill)))));
   ctx->tune_refill_sss = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_REFILL_SSS", int(ctx->tune_refill_sss)))));
+  ctx->tune_prim_lanes = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_PRIM_LANES", int(ctx->tune_prim_lanes)))));
+  ctx->tune_prim_lanes_sss = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_PRIM_LANES_SSS", int(ctx->tune_prim_lanes_sss)))));
   ctx->tune_trace_blocks = std::max(1, env_int("PBRGPU_TRACE_BLOCKS", ctx->tune_trace_blocks));
   ctx->tune_shade_blocks = std::max(1, env_int("PBRGPU_SHADE_BLOCKS", ctx->tune_shade_blocks));
   ctx->tune_walk_blocks = std::max(1, env_int("PBRGPU_WALK_BLOCKS", ctx->tune_walk_blocks));
@@ -700,7 +695,7 @@ int pbrgpu_trace_device(pbrgpu_ctx* ctx, const pbrgpu_ray* d_rays, uint64_t n, p
     const bool curves = d.view.num_curves != 0u;
 #define PBR_LAUNCH_BATCH(C, S)                                                                                    \
     pbr::TraceBatchKernel<C, S><<<grid, kBlock, 0, d.stream>>>(d.view, r4, n, tuv.ptr, ids.ptr, ng.ptr, fetch,   \
-                                                                d.stats.ptr, ctx->tune_refill)
+                                                                d.stats.ptr, ctx->tune_refill, ctx->tune_prim_lanes)
     if (curves && collect_stats) PBR_LAUNCH_BATCH(true, true);
     else if (curves) PBR_LAUNCH_BATCH(true, false);
     else if (collect_stats) PBR_LAUNCH_BATCH(false, true);
@@ -745,11 +740,11 @@ int pbrgpu_occluded_device(pbrgpu_ctx* ctx, const pbrgpu_ray* d_rays, uint64_t n
   if (d.view.num_curves)
     pbr::OccludedBatchKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(
         d.view, reinterpret_cast<const float4*>(d_rays), n, d_occluded, d.counters.ptr + pbr::kFetchShadow,
-        ctx->tune_refill);
+        ctx->tune_refill, ctx->tune_prim_lanes);
   else
     pbr::OccludedBatchKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(
         d.view, reinterpret_cast<const float4*>(d_rays), n, d_occluded, d.counters.ptr + pbr::kFetchShadow,
-        ctx->tune_refill);
+        ctx->tune_refill, ctx->tune_prim_lanes);
   CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
   CUDA_TRY(ctx, cudaGetLastError());
@@ -832,9 +827,9 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
     CUDA_TRY(ctx, dface.Alloc(2 * n));
     pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters, 0u);
     if (d.view.num_curves)
-      pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill);
+      pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes);
     else
-      pbr::TraceClosestKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill);
+      pbr::TraceClosestKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes);
     SurfaceFaceKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.view, d.wave, n32, dface.ptr);
     // restore the entry state for the real iteration below
     pbr::InitPathsFromRaysKernel<<<(std::max(n32, 64u) + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);
@@ -846,12 +841,17 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
   rc = RunPool(ctx, d, nullptr, mode == 1 ? 1u : 0xffffffffu, flags, &tm, nullptr, nullptr, 0, 1, 0);
   if (rc != PBRGPU_OK) { dr.Free(); ds.Free(); return rc; }
   std::vector<float4> rad(n), thr, ro, rdv;
-  CUDA_TRY(ctx, cudaMemcpyAsync(rad.data(), d.rad.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+  // one 16-byte record out of every 128-byte slot line
+  auto fetch_field = [&](std::vector<float4>& dst, int field) {
+    return cudaMemcpy2DAsync(dst.data(), sizeof(float4), d.slot.ptr + field, sizeof(float4) * pbr::kSlotStride,
+                             sizeof(float4), n, cudaMemcpyDeviceToHost, d.stream);
+  };
+  CUDA_TRY(ctx, fetch_field(rad, pbr::kRad));
   if (mode == 1) {
     thr.resize(n); ro.resize(n); rdv.resize(n);
-    CUDA_TRY(ctx, cudaMemcpyAsync(thr.data(), d.thr.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ro.data(), d.ray_o.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(rdv.data(), d.ray_d.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, fetch_field(thr, pbr::kThr));
+    CUDA_TRY(ctx, fetch_field(ro, pbr::kRayO));
+    CUDA_TRY(ctx, fetch_field(rdv, pbr::kRayD));
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
   if (mode == 0) {

@@ -1,31 +1,42 @@
 // Wavefront path tracer kernels (sm_100a).
 //
-// Render() keeps a POOL of N path slots resident in HBM for the whole frame.  A slot's state is structure-of-arrays,
-// every field a 16-byte record so each lane issues one 128-bit load per field and a warp reading a dense queue
-// touches contiguous 512-byte spans:
+// Render() keeps a POOL of N path slots resident in HBM for the whole frame.  Slots are visited through index
+// queues, i.e. in random order, so a slot's state is ONE 128-byte line (eight 16-byte records) instead of eight
+// separate arrays: a random 16-byte access costs a full 32-byte sector (64 bytes at the DRAM), and measured on B200 the
+// one-array-per-field layout moved 1.3 kB of DRAM traffic per shaded vertex for 176 bytes of state
+// (profiles/r1a_summary.md).  The line is grouped into 32-byte sectors by WRITER, so that every store replaces whole
+// sectors and never forces a read-modify-write:
 //
-//   ray_o[N]  (org.xyz, tmin)      ray_d[N]  (dir.xyz, tmax)      hit[N]  (t, u, v, leaf-order primitive | curve flag)
-//   thr[N]    (throughput.rgb, pdf of the last BSDF sample)       rad[N]  (radiance.rgb, depth)
-//   rng[N]    (PCG32 state, inc)   pixel[N]  (u32)                walk_a..d[N], walk_n[N]  parked random walk
+//   sector 0   ray_o (org.xyz, tmin)            ray_d (dir.xyz, tmax)              written by shade / regenerate
+//   sector 1   thr   (throughput.rgb, pdf)      rad   (radiance.rgb, depth)        written by shade / regenerate
+//   sector 2   hit   (t, u, v, leaf-order prim) pad                                written by trace_closest
+//   sector 3   rng   (PCG32 state, inc)         pix   (pixel, -, -, -)             written by shade / regenerate
+//
+// A second line per slot (`walk`) holds a parked random walk or the exit record of a finished one; only slots
+// that are inside a subsurface walk ever touch it.  Slot state is read and written with streaming (evict-first)
+// cache hints so that the ~1-2 GB that stream through per iteration do not push the BVH (19 MB on the Cornell scene)
+// out of the 126 MB L2.
 //
 // Index queues (u32 slot ids) are compacted with warp ballots + one atomicAdd per warp:
 //
 //   q_active[2]  slots that need a closest-hit query (ping-pong between iterations)
 //   q_surface    hit a triangle-type material (or none): emission + roulette + Principled vertex
 //   q_hair       hit a hair material
-//   q_sss        the Principled vertex selected the random-walk closure this iteration
+//   q_sss        the Principled vertex selected the random-walk closure this iteration (walk state already parked)
 //   q_walk[2]    random walks that used up their bounce budget and continue next iteration (ping-pong)
+//   q_exit       walks that left the medium this iteration: exit vertex still to be shaded
 //   q_done[2]    paths that ended this iteration; consumed at the start of the next one (ping-pong)
-//   shadow queue (ray, contribution, slot): NEE any-hit queries
+//   shadow queue (ray, contribution, slot) as three dense arrays: NEE any-hit queries, written and read coalesced
 //
 // One iteration:
-//   begin -> regenerate -> trace_closest -> shade_surface, shade_hair -> sss_walk -> trace_any
-// `regenerate` retires every slot of q_done (adds its radiance to its pixel: rgba += (L,1), count += 1, the sums
-// RenderLayer holds) and immediately starts the next camera sample in the same slot, so the pool stays full until the
-// frame runs out of samples: long random walks and deep paths never leave the GPU idle, and the number of iterations
-// is (total rays) / N instead of (longest path).  Every kernel is persistent — a grid that is a fixed multiple of
-// the SM count, warps pulling 32-entry batches with an atomic counter — and reads its queue length from device
-// memory, so nothing but one small counter block crosses PCIe per iteration.
+//   begin -> regenerate -> trace_closest -> shade_surface, shade_hair -> sss_walk -> sss_exit -> trace_any
+// `regenerate` retires every slot of q_done (adds its radiance to its pixel: rgba += (L,1), the sums RenderLayer
+// holds) and immediately starts the next camera sample in the same slot, so the pool stays full until the frame runs
+// out of samples: long random walks and deep paths never leave the GPU idle, and the number of iterations is
+// (total rays) / N instead of (longest path).  Every kernel is persistent — a grid that is a fixed multiple of the SM
+// count, warps pulling work with an atomic counter — and reads its queue length from device memory, so nothing but
+// one small counter block crosses PCIe per iteration.  The three ray kernels run in the warp traversal engine
+// (device/trav_engine.cuh), which refills finished lanes while the rest of the warp keeps traversing.
 //
 // Replaces the per-pixel loops of the reference (src/render.cc:24-90,125-190); the per-vertex functions and their
 // citations are in device/shade.cuh.
@@ -41,8 +52,8 @@ enum Counter {
   kNumActive0 = 0, kNumActive1,   // length of q_active[parity]
   kNumWalk0, kNumWalk1,           // length of q_walk[parity]
   kNumDone0, kNumDone1,           // length of q_done[parity]
-  kNumSurface, kNumHair, kNumSss, kNumShadow,
-  kFetchRegen, kFetchTrace, kFetchSurface, kFetchHair, kFetchSss, kFetchShadow,
+  kNumSurface, kNumHair, kNumSss, kNumExit, kNumShadow,
+  kFetchRegen, kFetchTrace, kFetchSurface, kFetchHair, kFetchSss, kFetchExit, kFetchShadow,
   kCounterCount
 };
 // 64-bit counters that live for a whole frame
@@ -53,25 +64,20 @@ enum Stat {
   kStatCount
 };
 
+// records of a slot line / walk line (units of float4)
+enum SlotField { kRayO = 0, kRayD = 1, kThr = 2, kRad = 3, kHit = 4, kHitPad = 5, kRng = 6, kPix = 7, kSlotStride = 8 };
+enum WalkField { kWalkA = 0, kWalkB = 1, kWalkC = 2, kWalkD = 3, kWalkN = 4, kWalkStride = 8 };
+
 struct WaveState {
-  float4* ray_o;
-  float4* ray_d;
-  float4* hit;
-  float4* thr;
-  float4* rad;
-  ulonglong2* rng;
-  uint32_t* pixel;
+  float4* slot;                  // kSlotStride x float4 per path slot
+  float4* walk;                  // kWalkStride x float4 per path slot
   uint32_t* q_active[2];
   uint32_t* q_walk[2];
   uint32_t* q_done[2];
   uint32_t* q_surface;
   uint32_t* q_hair;
   uint32_t* q_sss;
-  float4* walk_a;                // parked walk: (sigma_t.xyz, throughput.x)
-  float4* walk_b;                //              (sigma_s.xyz, throughput.y)
-  float4* walk_c;                //              (ray.org.xyz, throughput.z)
-  float4* walk_d;                //              (ray.dir.xyz, tmin)
-  uint32_t* walk_n;              //              bounce count
+  uint32_t* q_exit;
   float4* sh_o;
   float4* sh_d;
   float4* sh_c;
@@ -81,6 +87,20 @@ struct WaveState {
 };
 
 constexpr uint32_t kNoPixel = 0xFFFFFFFFu;
+
+// ---- streaming access to slot state (ld/st.global.cs: evict-first in L2)
+__device__ __forceinline__ float4 LdSlot(const WaveState& w, uint32_t p, int field) {
+  return __ldcs(&w.slot[size_t(p) * kSlotStride + field]);
+}
+__device__ __forceinline__ void StSlot(const WaveState& w, uint32_t p, int field, const float4& v) {
+  __stcs(&w.slot[size_t(p) * kSlotStride + field], v);
+}
+__device__ __forceinline__ float4 LdWalk(const WaveState& w, uint32_t p, int field) {
+  return __ldcs(&w.walk[size_t(p) * kWalkStride + field]);
+}
+__device__ __forceinline__ void StWalk(const WaveState& w, uint32_t p, int field, const float4& v) {
+  __stcs(&w.walk[size_t(p) * kWalkStride + field], v);
+}
 
 // ---- warp-aggregated queue append: one atomicAdd per warp.  Must be reached by all 32 lanes.
 __device__ __forceinline__ uint32_t WarpAppend(uint32_t* counter, bool pred) {
@@ -104,17 +124,28 @@ __device__ __forceinline__ uint32_t WarpFetch(uint32_t* fetch_counter) {
 }
 
 __device__ __forceinline__ RayT LoadRay(const WaveState& w, uint32_t p) {
-  const float4 o = w.ray_o[p], d = w.ray_d[p];
+  const float4 o = LdSlot(w, p, kRayO), d = LdSlot(w, p, kRayD);
   RayT r;
   r.o = vec3(o.x, o.y, o.z); r.tmin = o.w;
   r.d = vec3(d.x, d.y, d.z); r.tmax = d.w;
   return r;
 }
 __device__ __forceinline__ HitT LoadHit(const WaveState& w, uint32_t p) {
-  const float4 h4 = w.hit[p];
+  const float4 h4 = LdSlot(w, p, kHit);
   HitT hit;
   hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
   return hit;
+}
+__device__ __forceinline__ Pcg32 LoadRng(const WaveState& w, uint32_t p) {
+  const float4 r = LdSlot(w, p, kRng);
+  Pcg32 rng;
+  rng.state = (uint64_t(__float_as_uint(r.y)) << 32) | __float_as_uint(r.x);
+  rng.inc = (uint64_t(__float_as_uint(r.w)) << 32) | __float_as_uint(r.z);
+  return rng;
+}
+__device__ __forceinline__ float4 PackRng(const Pcg32& rng) {
+  return make_float4(__uint_as_float(uint32_t(rng.state)), __uint_as_float(uint32_t(rng.state >> 32)),
+                     __uint_as_float(uint32_t(rng.inc)), __uint_as_float(uint32_t(rng.inc >> 32)));
 }
 
 __device__ __forceinline__ void PushShadow(const WaveState& w, const ShadowRequest& req, const vec3& throughput,
@@ -122,9 +153,9 @@ __device__ __forceinline__ void PushShadow(const WaveState& w, const ShadowReque
   const uint32_t slot = WarpAppend(&w.counters[kNumShadow], req.active);
   if (req.active) {
     const vec3 c = throughput * req.contribute;
-    w.sh_o[slot] = make_float4(req.ray.o.x, req.ray.o.y, req.ray.o.z, req.ray.tmin);
-    w.sh_d[slot] = make_float4(req.ray.d.x, req.ray.d.y, req.ray.d.z, req.ray.tmax);
-    w.sh_c[slot] = make_float4(c.x, c.y, c.z, __uint_as_float(path));
+    __stcs(&w.sh_o[slot], make_float4(req.ray.o.x, req.ray.o.y, req.ray.o.z, req.ray.tmin));
+    __stcs(&w.sh_d[slot], make_float4(req.ray.d.x, req.ray.d.y, req.ray.d.z, req.ray.tmax));
+    __stcs(&w.sh_c[slot], make_float4(c.x, c.y, c.z, __uint_as_float(path)));
   }
 }
 
@@ -161,8 +192,7 @@ struct FrameParams {
   uint64_t seed;
   uint32_t first_sample;      // global index of local sample 0
   uint32_t sample_stride;     // global sample index = first_sample + local * stride
-  float4* rgba;               // frame accumulators (sums)
-  uint32_t* count;
+  float4* rgba;               // frame accumulator (sums); alpha counts the samples (render.cc:175-183)
 };
 
 __device__ __forceinline__ void StartCameraPath(const WaveState& w, const FrameParams& f, uint32_t p,
@@ -177,16 +207,17 @@ __device__ __forceinline__ void StartCameraPath(const WaveState& w, const FrameP
   float dx = tx - f.cam.eye[0], dy = ty - f.cam.eye[1], dz = f.cam.z_corner - f.cam.eye[2];
   const float inv_norm = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);   // Normalize (render.cc:243-249)
   dx *= inv_norm; dy *= inv_norm; dz *= inv_norm;
-  w.ray_o[p] = make_float4(f.cam.eye[0], f.cam.eye[1], f.cam.eye[2], 0.0f);
-  w.ray_d[p] = make_float4(dx, dy, dz, kInf);
-  w.thr[p] = make_float4(1.f, 1.f, 1.f, 0.f);
-  w.rad[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
-  w.rng[p] = make_ulonglong2(rng.state, rng.inc);
-  w.pixel[p] = pixel;
+  StSlot(w, p, kRayO, make_float4(f.cam.eye[0], f.cam.eye[1], f.cam.eye[2], 0.0f));
+  StSlot(w, p, kRayD, make_float4(dx, dy, dz, kInf));
+  StSlot(w, p, kThr, make_float4(1.f, 1.f, 1.f, 0.f));
+  StSlot(w, p, kRad, make_float4(0.f, 0.f, 0.f, __uint_as_float(0u)));
+  StSlot(w, p, kRng, PackRng(rng));
+  StSlot(w, p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
 }
 
-// Retire the slots of q_done[cur] (render.cc:175-183: rgba += (L, 1), count += 1) and restart them on the next
-// camera samples.  Several samples of one pixel can retire in the same iteration, hence atomics.
+// Retire the slots of q_done[cur] (render.cc:175-183: rgba += (L, 1); count is the alpha sum, written out by
+// FinishFrameKernel) and restart them on the next camera samples.  Several samples of one pixel can retire in the
+// same iteration, hence the atomic: ONE 128-bit vector reduction per path (red.global.add.v4.f32, sm_90+).
 __global__ void __launch_bounds__(256) RegenerateKernel(WaveState w, FrameParams f, uint32_t cur_parity) {
   const uint32_t n = w.counters[kNumDone0 + cur_parity];
   unsigned long long retired = 0;
@@ -197,16 +228,10 @@ __global__ void __launch_bounds__(256) RegenerateKernel(WaveState w, FrameParams
     uint32_t p = 0;
     if (valid) {
       p = w.q_done[cur_parity][i];
-      const uint32_t pixel = w.pixel[p];
+      const uint32_t pixel = __float_as_uint(LdSlot(w, p, kPix).x);
       if (pixel != kNoPixel) {
-        const float4 r = w.rad[p];
-        float* dst = reinterpret_cast<float*>(&f.rgba[pixel]);
-        atomicAdd(dst + 0, r.x);
-        atomicAdd(dst + 1, r.y);
-        atomicAdd(dst + 2, r.z);
-        atomicAdd(dst + 3, 1.0f);
-        atomicAdd(&f.count[pixel], 1u);
-        w.pixel[p] = kNoPixel;
+        const float4 r = LdSlot(w, p, kRad);
+        atomicAdd(&f.rgba[pixel], make_float4(r.x, r.y, r.z, 1.0f));
         ++retired;
       }
     }
@@ -222,17 +247,24 @@ __global__ void __launch_bounds__(256) RegenerateKernel(WaveState w, FrameParams
     const unsigned long long id = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
     const bool start = valid && id < f.total_samples;
     if (start) StartCameraPath(w, f, p, id);
+    else if (valid) StSlot(w, p, kPix, make_float4(__uint_as_float(kNoPixel), 0.f, 0.f, 0.f));
     const uint32_t a = WarpAppend(&w.counters[kNumActive0 + cur_parity], start);
     if (start) w.q_active[cur_parity][a] = p;
   }
   if (retired) atomicAdd(&w.stats[kStatRetired], retired);
 }
 
+// RenderLayer::count (render-layer.h:11-26) from the alpha sums: both are incremented together per sample
+__global__ void FinishFrameKernel(const float4* rgba, uint32_t* count, uint32_t npix) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npix) count[i] = uint32_t(rgba[i].w);
+}
+
 // all slots idle and queued for (re)generation: the state a frame starts from
 __global__ void ResetPoolKernel(WaveState w, uint32_t n_slots) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < n_slots) {
-    w.pixel[p] = kNoPixel;
+    StSlot(w, p, kPix, make_float4(__uint_as_float(kNoPixel), 0.f, 0.f, 0.f));
     w.q_done[0][p] = p;
   }
   if (p < kCounterCount) w.counters[p] = (p == kNumDone0) ? n_slots : 0u;
@@ -243,14 +275,14 @@ __global__ void InitPathsFromRaysKernel(WaveState w, const float4* rays, const u
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < kCounterCount) w.counters[p] = (p == kNumActive0) ? n : 0u;
   if (p >= n) return;
-  w.ray_o[p] = rays[2 * p];
-  w.ray_d[p] = rays[2 * p + 1];
+  StSlot(w, p, kRayO, rays[2 * p]);
+  StSlot(w, p, kRayD, rays[2 * p + 1]);
   Pcg32 rng;
   pcg32_srandom(&rng, seeds[2 * p], seeds[2 * p + 1]);
-  w.thr[p] = make_float4(1.f, 1.f, 1.f, 0.f);
-  w.rad[p] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
-  w.rng[p] = make_ulonglong2(rng.state, rng.inc);
-  w.pixel[p] = p;
+  StSlot(w, p, kThr, make_float4(1.f, 1.f, 1.f, 0.f));
+  StSlot(w, p, kRad, make_float4(0.f, 0.f, 0.f, __uint_as_float(0u)));
+  StSlot(w, p, kRng, PackRng(rng));
+  StSlot(w, p, kPix, make_float4(__uint_as_float(p), 0.f, 0.f, 0.f));
   w.q_active[0][p] = p;
 }
 
@@ -275,7 +307,8 @@ struct ClosestClient {
     if (!t.active && has_result) {
       has_result = false;
       const HitT hit = t.hit;
-      w.hit[p] = make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
+      StSlot(w, p, kHit, make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim)));
+      StSlot(w, p, kHitPad, make_float4(0.f, 0.f, 0.f, 0.f));   // completes the sector: no read-modify-write
       kind = 0;
       if (hit.prim != kInvalid) {
         uint32_t mat;
@@ -315,9 +348,9 @@ struct ClosestClient {
 
 template <bool HAS_CURVES>
 __global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState w, uint32_t cur_parity,
-                                                          uint32_t refill_min_idle) {
+                                                          uint32_t refill_min_idle, uint32_t prim_min_lanes) {
   ClosestClient client(s, w, cur_parity);
-  TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle);
+  TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle, prim_min_lanes);
 }
 
 // ------------------------------------------------------------------------------------------------ shading
@@ -325,17 +358,70 @@ struct ShadeFlags {
   uint32_t skip_emission_and_roulette;   // pbrgpu_shade hook: call Shader() only
 };
 
-__device__ __forceinline__ void CommitVertex(const WaveState& w, uint32_t p, const VertexResult& vr,
-                                             const vec3& throughput, const vec3& L, uint32_t depth, const Pcg32& rng) {
-  const vec3 new_thr = vr.throughput * throughput;                     // render.cc:80
-  w.thr[p] = make_float4(new_thr.x, new_thr.y, new_thr.z, vr.pdf);
-  w.rad[p] = make_float4(L.x, L.y, L.z, __uint_as_float(depth + 1u));
-  w.rng[p] = make_ulonglong2(rng.state, rng.inc);
-  w.ray_o[p] = make_float4(vr.P.x, vr.P.y, vr.P.z, 1e-3f);             // render.cc:83-86
-  w.ray_d[p] = make_float4(vr.wi.x, vr.wi.y, vr.wi.z, kInf);
+// what a shading kernel holds of its path between load and commit
+struct PathRegs {
+  RayT ray;
+  HitT hit;
+  vec3 throughput, L;
+  float pdf_prev;
+  uint32_t depth, pixel;
+  Pcg32 rng;
+};
+
+__device__ __forceinline__ PathRegs LoadPath(const WaveState& w, uint32_t p) {
+  PathRegs r;
+  r.ray = LoadRay(w, p);
+  r.hit = LoadHit(w, p);
+  const float4 t4 = LdSlot(w, p, kThr), r4 = LdSlot(w, p, kRad);
+  r.throughput = vec3(t4.x, t4.y, t4.z);
+  r.pdf_prev = t4.w;
+  r.L = vec3(r4.x, r4.y, r4.z);
+  r.depth = __float_as_uint(r4.w);
+  r.rng = LoadRng(w, p);
+  r.pixel = __float_as_uint(LdSlot(w, p, kPix).x);
+  return r;
 }
 
-// emission + MIS, roulette, material dispatch, Principled vertex (everything but the random walk)
+// after a vertex: sectors 0, 1 and 3 of the line are rewritten whole (render.cc:79-86)
+__device__ __forceinline__ void CommitVertex(const WaveState& w, uint32_t p, const VertexResult& vr,
+                                             const vec3& throughput, const vec3& L, uint32_t depth, const Pcg32& rng,
+                                             uint32_t pixel) {
+  const vec3 new_thr = vr.throughput * throughput;                     // render.cc:80
+  StSlot(w, p, kRayO, make_float4(vr.P.x, vr.P.y, vr.P.z, 1e-3f));     // render.cc:83-86
+  StSlot(w, p, kRayD, make_float4(vr.wi.x, vr.wi.y, vr.wi.z, kInf));
+  StSlot(w, p, kThr, make_float4(new_thr.x, new_thr.y, new_thr.z, vr.pdf));
+  StSlot(w, p, kRad, make_float4(L.x, L.y, L.z, __uint_as_float(depth + 1u)));
+  StSlot(w, p, kRng, PackRng(rng));
+  StSlot(w, p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
+}
+
+// the path ends here: only its radiance (and pixel) are read again
+__device__ __forceinline__ void CommitEnd(const WaveState& w, uint32_t p, const vec3& L, uint32_t depth) {
+  StSlot(w, p, kThr, make_float4(0.f, 0.f, 0.f, 0.f));
+  StSlot(w, p, kRad, make_float4(L.x, L.y, L.z, __uint_as_float(depth)));
+}
+
+__device__ __forceinline__ void ParkWalk(const WaveState& w, uint32_t p, const SssWalkState& k) {
+  StWalk(w, p, kWalkA, make_float4(k.sigma_t.x, k.sigma_t.y, k.sigma_t.z, k.throughput.x));
+  StWalk(w, p, kWalkB, make_float4(k.sigma_s.x, k.sigma_s.y, k.sigma_s.z, k.throughput.y));
+  StWalk(w, p, kWalkC, make_float4(k.ray.o.x, k.ray.o.y, k.ray.o.z, k.throughput.z));
+  StWalk(w, p, kWalkD, make_float4(k.ray.d.x, k.ray.d.y, k.ray.d.z, k.ray.tmin));
+  StWalk(w, p, kWalkN, make_float4(__uint_as_float(k.bounce), 0.f, 0.f, 0.f));
+}
+__device__ __forceinline__ void ResumeWalk(const WaveState& w, uint32_t p, SssWalkState* k) {
+  const float4 a = LdWalk(w, p, kWalkA), b = LdWalk(w, p, kWalkB), c = LdWalk(w, p, kWalkC), d = LdWalk(w, p, kWalkD);
+  k->sigma_t = vec3(a.x, a.y, a.z);
+  k->sigma_s = vec3(b.x, b.y, b.z);
+  k->throughput = vec3(a.w, b.w, c.w);
+  k->ray.o = vec3(c.x, c.y, c.z);
+  k->ray.d = vec3(d.x, d.y, d.z);
+  k->ray.tmin = d.w;
+  k->ray.tmax = kInf;
+  k->bounce = __float_as_uint(LdWalk(w, p, kWalkN).x);
+}
+
+// emission + MIS, roulette, material dispatch, Principled vertex.  When the vertex selects the random-walk closure
+// the walk is set up here (entry direction + coefficients, random-walk-sss.h:227-279) and parked for sss_walk.
 __global__ void __launch_bounds__(128) ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t next_parity,
                                                           ShadeFlags flags) {
   const uint32_t n = w.counters[kNumSurface];
@@ -350,38 +436,42 @@ __global__ void __launch_bounds__(128) ShadeSurfaceKernel(SceneView s, WaveState
     vec3 throughput(0.f);
     if (valid) {
       p = w.q_surface[slot];
-      const RayT ray = LoadRay(w, p);
-      const HitT hit = LoadHit(w, p);
-      const float4 t4 = w.thr[p];
-      const float4 r4 = w.rad[p];
-      throughput = vec3(t4.x, t4.y, t4.z);
-      vec3 L(r4.x, r4.y, r4.z);
-      const uint32_t depth = __float_as_uint(r4.w);
-      const ulonglong2 rs = w.rng[p];
-      Pcg32 rng;
-      rng.state = rs.x; rng.inc = rs.y;
-      const Surface si = MakeSurface(s, ray, hit);
+      PathRegs r = LoadPath(w, p);
+      throughput = r.throughput;
+      vec3 L = r.L;
+      const Surface si = MakeSurface(s, r.ray, r.hit);
       bool alive = true;
       if (!flags.skip_emission_and_roulette)
-        alive = EmissionAndRoulette(s, ray, hit, si, depth, t4.w, &rng, &L, &throughput);
+        alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &L, &throughput);
       if (!alive) {
-        w.rad[p] = make_float4(L.x, L.y, L.z, __uint_as_float(depth));
+        CommitEnd(w, p, L, r.depth);
         to_done = true;
       } else {
         const int kind = MaterialKind(s, si);
         VertexResult vr;
-        const vec3 wo = -ray.d;
-        if (kind == 1) to_sss = PrincipledVertex(s, si, wo, &rng, &vr);
+        const vec3 wo = -r.ray.d;
+        Frame fr;
+        PrincipledBsdf bsdf;
+        bool sss = false;
+        if (kind == 1) sss = PrincipledVertex(s, si, wo, &r.rng, &vr, &fr, &bsdf);
         else AbsorbVertex(wo, si.P, &vr);   // no material (shader.cc:11-17)
         req = vr.shadow[0];
-        if (to_sss) {
-          // the walk runs in its own kernel: park the path with the post-roulette throughput and the rng positioned
-          // right after the closure selector
-          w.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, t4.w);
-          w.rad[p] = make_float4(L.x, L.y, L.z, __uint_as_float(depth));
-          w.rng[p] = make_ulonglong2(rng.state, rng.inc);
+        if (sss) {
+          SssWalkState walk;
+          if (SssBegin(si, fr, bsdf, &r.rng, &walk)) {
+            // the walk runs in its own kernel: park it, and the path with the post-roulette throughput
+            ParkWalk(w, p, walk);
+            StSlot(w, p, kThr, make_float4(throughput.x, throughput.y, throughput.z, r.pdf_prev));
+            StSlot(w, p, kRad, make_float4(L.x, L.y, L.z, __uint_as_float(r.depth)));
+            StSlot(w, p, kRng, PackRng(r.rng));
+            StSlot(w, p, kPix, make_float4(__uint_as_float(r.pixel), 0.f, 0.f, 0.f));
+            to_sss = true;
+          } else {   // walk rejected: throughput 0, the path ends (cycles-principled-shader.cc:217-220)
+            CommitEnd(w, p, L, r.depth + 1u);
+            to_done = true;
+          }
         } else {
-          CommitVertex(w, p, vr, throughput, L, depth, rng);
+          CommitVertex(w, p, vr, throughput, L, r.depth, r.rng, r.pixel);
           to_next = !IsBlack(vr.throughput * throughput);               // render.cc:31
           to_done = !to_next;
         }
@@ -408,28 +498,21 @@ __global__ void __launch_bounds__(128) ShadeHairKernel(SceneView s, WaveState w,
     vec3 throughput(0.f);
     if (valid) {
       p = w.q_hair[slot];
-      const RayT ray = LoadRay(w, p);
-      const HitT hit = LoadHit(w, p);
-      const float4 t4 = w.thr[p];
-      const float4 r4 = w.rad[p];
-      throughput = vec3(t4.x, t4.y, t4.z);
-      vec3 L(r4.x, r4.y, r4.z);
-      const uint32_t depth = __float_as_uint(r4.w);
-      const ulonglong2 rs = w.rng[p];
-      Pcg32 rng;
-      rng.state = rs.x; rng.inc = rs.y;
-      const Surface si = MakeSurface(s, ray, hit);
+      PathRegs r = LoadPath(w, p);
+      throughput = r.throughput;
+      vec3 L = r.L;
+      const Surface si = MakeSurface(s, r.ray, r.hit);
       bool alive = true;
       if (!flags.skip_emission_and_roulette)
-        alive = EmissionAndRoulette(s, ray, hit, si, depth, t4.w, &rng, &L, &throughput);
+        alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &L, &throughput);
       if (!alive) {
-        w.rad[p] = make_float4(L.x, L.y, L.z, __uint_as_float(depth));
+        CommitEnd(w, p, L, r.depth);
         to_done = true;
       } else {
         VertexResult vr;
-        HairVertex(s, si, -ray.d, &rng, &vr);
+        HairVertex(s, si, -r.ray.d, &r.rng, &vr);
         req = vr.shadow[0];
-        CommitVertex(w, p, vr, throughput, L, depth, rng);
+        CommitVertex(w, p, vr, throughput, L, r.depth, r.rng, r.pixel);
         to_next = !IsBlack(vr.throughput * throughput);
         to_done = !to_next;
       }
@@ -440,39 +523,24 @@ __global__ void __launch_bounds__(128) ShadeHairKernel(SceneView s, WaveState w,
 }
 
 // ------------------------------------------------------------------------------------------------ random-walk SSS
-// RandomWalkSubsurface (random-walk-sss.h:227-405).  Walk lengths are wildly uneven (1 .. 8192 bounces; Lucy's red
-// channel has albedo ~1, so neither absorption nor roulette ends a walk early) and every bounce is a dependent
-// short closest-hit query (~10 us of latency), hence:
-//   * lanes are refilled from the queue the moment their walk ends — every loop trip runs at most one bounce per
-//     lane, no lane waits for the longest walk of its warp;
-//   * a walk gets at most `max_bounces` bounces per launch; if it is still inside the medium its 68-byte state is
-//     parked in HBM (walk_a..d, walk_n) and the slot goes to q_walk[next]: the next iteration resumes it first.
-//     A launch therefore never outlives its queue by more than max_bounces bounces, and because the pool is kept
-//     full by regeneration, long walks cost slots, not idle SMs.
-__device__ __forceinline__ void ParkWalk(const WaveState& w, uint32_t p, const SssWalkState& k) {
-  w.walk_a[p] = make_float4(k.sigma_t.x, k.sigma_t.y, k.sigma_t.z, k.throughput.x);
-  w.walk_b[p] = make_float4(k.sigma_s.x, k.sigma_s.y, k.sigma_s.z, k.throughput.y);
-  w.walk_c[p] = make_float4(k.ray.o.x, k.ray.o.y, k.ray.o.z, k.throughput.z);
-  w.walk_d[p] = make_float4(k.ray.d.x, k.ray.d.y, k.ray.d.z, k.ray.tmin);
-  w.walk_n[p] = k.bounce;
-}
-__device__ __forceinline__ void ResumeWalk(const WaveState& w, uint32_t p, SssWalkState* k) {
-  const float4 a = w.walk_a[p], b = w.walk_b[p], c = w.walk_c[p], d = w.walk_d[p];
-  k->sigma_t = vec3(a.x, a.y, a.z);
-  k->sigma_s = vec3(b.x, b.y, b.z);
-  k->throughput = vec3(a.w, b.w, c.w);
-  k->ray.o = vec3(c.x, c.y, c.z);
-  k->ray.d = vec3(d.x, d.y, d.z);
-  k->ray.tmin = d.w;
-  k->ray.tmax = kInf;
-  k->bounce = w.walk_n[p];
-}
-
+// RandomWalkSubsurface (random-walk-sss.h:281-383), the bounce loop only.  Walk lengths are wildly uneven (1 .. 8192
+// bounces; Lucy's red channel has albedo ~1, so neither absorption nor roulette ends a walk early) and every bounce
+// is a dependent short closest-hit query, hence:
+//   * the queries run in the warp traversal engine; a lane whose segment ends waits until `refill_min_idle` lanes are
+//     in that state, then they all do the scatter step (transmittance, roulette, new direction and distance)
+//     converged and go back to traversing — no lane waits for the longest walk of its warp;
+//   * a walk gets at most `max_bounces` bounces per launch; if it is still inside the medium its state is parked in
+//     its walk line and the slot goes to q_walk[next]: the next iteration resumes it first.  A launch therefore
+//     never outlives its queue by more than max_bounces bounces, and because the pool is kept full by
+//     regeneration, long walks cost slots, not idle SMs;
+//   * entering the medium is part of shade_surface, leaving it (exit vertex: NEE + diffuse bounce,
+//     cycles-principled-shader.cc:187-216) is sss_exit: both are rare per bounce and ran at 2-3 lanes per warp when
+//     they were inlined here (profiles/r1b_summary.md).
 struct SssClient {
   const SceneView& s;
   const WaveState& w;
   uint32_t cur_parity, next_parity, n_resume, n, max_bounces;
-  uint32_t p = 0, budget = 0;
+  uint32_t p = 0, budget = 0, pixel = 0;
   bool has_walk = false;
   Pcg32 rng;
   SssWalkState walk;    // walk.ray is rebuilt from the traversal state after every segment
@@ -486,57 +554,49 @@ struct SssClient {
   __device__ __forceinline__ void StartSegment(Trav& t) {
     SssPrepareSegment(&rng, &walk);
     TravBegin(s, walk.ray, t);
-    if (!t.active) {   // empty scene: the segment ends without a hit
-      t.hit.prim = kInvalid;
-    }
   }
 
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     // ---- (1) walks whose segment query finished: scatter / exit / absorb
-    bool to_next = false, to_done = false, to_park = false;
-    ShadowRequest req;
-    req.active = false;
-    vec3 throughput(0.f);
-    uint32_t routed_p = p;
+    bool to_exit = false, to_done = false, to_park = false;
+    const uint32_t routed_p = p;
     if (!t.active && has_walk) {
       walk.ray.o = t.O; walk.ray.d = t.D; walk.ray.tmin = t.tmin;   // tmax untouched: the scatter distance
       const bool is_hit = t.hit.prim != kInvalid;
       const SssStep st = SssFinishSegment(is_hit, t.hit.t, &rng, &walk);
       ++rays;
       --budget;
-      if (st != kSssContinue) {
-        // the entry vertex is only needed now: rebuild it from the parked path's ray + hit
-        const RayT ray = LoadRay(w, p);
-        const Surface entry_si = MakeSurface(s, ray, LoadHit(w, p));
-        const Frame entry_frame = PrincipledFrame(entry_si);
-        const float4 t4 = w.thr[p], r4 = w.rad[p];
-        throughput = vec3(t4.x, t4.y, t4.z);
-        VertexResult vr;
-        vr.P = entry_si.P;
-        vr.shadow[1].active = false;
-        if (st == kSssHit) SssFinish(s, entry_si, entry_frame, walk, t.hit, &rng, &vr);
-        else FinishPrincipled(entry_frame, vec3(0.f), vec3(0.f), 0.f, &vr);
-        req = vr.shadow[1];
-        CommitVertex(w, p, vr, throughput, vec3(r4.x, r4.y, r4.z), __float_as_uint(r4.w), rng);
-        to_next = !IsBlack(vr.throughput * throughput);
-        to_done = !to_next;
+      if (st == kSssHit) {
+        // exit record for sss_exit: the segment ray, its hit and the walk throughput
+        StWalk(w, p, kWalkA, make_float4(t.hit.t, t.hit.u, t.hit.v, __uint_as_float(t.hit.prim)));
+        StWalk(w, p, kWalkB, make_float4(walk.throughput.x, walk.throughput.y, walk.throughput.z, 0.f));
+        StWalk(w, p, kWalkC, make_float4(walk.ray.o.x, walk.ray.o.y, walk.ray.o.z, walk.ray.tmin));
+        StWalk(w, p, kWalkD, make_float4(walk.ray.d.x, walk.ray.d.y, walk.ray.d.z, walk.ray.tmax));
+        StSlot(w, p, kRng, PackRng(rng));
+        StSlot(w, p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
+        to_exit = true;
+        has_walk = false;
+      } else if (st == kSssAbsorbed) {
+        to_done = true;   // throughput 0: the path ends with the radiance it already holds
         has_walk = false;
       } else if (budget == 0u) {
         ParkWalk(w, p, walk);
-        w.rng[p] = make_ulonglong2(rng.state, rng.inc);
+        StSlot(w, p, kRng, PackRng(rng));
+        StSlot(w, p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
         to_park = true;
         has_walk = false;
       } else {
         StartSegment(t);
       }
     }
-    PushShadow(w, req, throughput, routed_p);
-    RouteSlot(w, next_parity, routed_p, to_next, to_done);
+    const uint32_t e = WarpAppend(&w.counters[kNumExit], to_exit);
+    if (to_exit) w.q_exit[e] = routed_p;
+    RouteSlot(w, next_parity, routed_p, false, to_done);
     const uint32_t c = WarpAppend(&w.counters[kNumWalk0 + next_parity], to_park);
     if (to_park) w.q_walk[next_parity][c] = routed_p;
 
     // ---- (2) lanes without a walk take the next one: parked walks first, then this iteration's new ones
-    bool dry = false, rejected = false;
+    bool dry = false;
     if (!exhausted) {
       const bool need = !t.active && !has_walk;
       const uint32_t slot = WarpAppend(&w.counters[kFetchSss], need);
@@ -544,33 +604,15 @@ struct SssClient {
         if (slot >= n) {
           dry = true;
         } else {
-          const bool resume = slot < n_resume;
-          p = resume ? w.q_walk[cur_parity][slot] : w.q_sss[slot - n_resume];
-          const ulonglong2 rs = w.rng[p];
-          rng.state = rs.x; rng.inc = rs.y;
+          p = (slot < n_resume) ? w.q_walk[cur_parity][slot] : w.q_sss[slot - n_resume];
+          rng = LoadRng(w, p);
+          pixel = __float_as_uint(LdSlot(w, p, kPix).x);
           budget = max_bounces;
-          if (resume) {
-            ResumeWalk(w, p, &walk);
-            has_walk = true;
-          } else {
-            const RayT ray = LoadRay(w, p);
-            const Surface entry_si = MakeSurface(s, ray, LoadHit(w, p));
-            const Frame entry_frame = PrincipledFrame(entry_si);
-            const PrincipledBsdf bsdf = SurfaceBsdf(s, entry_si);
-            has_walk = SssBegin(entry_si, entry_frame, bsdf, &rng, &walk);
-            if (!has_walk) {   // walk rejected: the path's throughput becomes 0 and it ends
-              const float4 t4 = w.thr[p], r4 = w.rad[p];
-              VertexResult vr;
-              vr.P = entry_si.P;
-              FinishPrincipled(entry_frame, vec3(0.f), vec3(0.f), 0.f, &vr);
-              CommitVertex(w, p, vr, vec3(t4.x, t4.y, t4.z), vec3(r4.x, r4.y, r4.z), __float_as_uint(r4.w), rng);
-              rejected = true;
-            }
-          }
-          if (has_walk) StartSegment(t);
+          ResumeWalk(w, p, &walk);
+          has_walk = true;
+          StartSegment(t);
         }
       }
-      RouteSlot(w, next_parity, p, false, rejected);
     }
     return dry;
   }
@@ -581,9 +623,51 @@ struct SssClient {
 
 template <bool HAS_CURVES>
 __global__ void __launch_bounds__(128) SssWalkKernel(SceneView s, WaveState w, uint32_t cur_parity,
-                                                     uint32_t max_bounces, uint32_t refill_min_idle) {
+                                                     uint32_t max_bounces, uint32_t refill_min_idle,
+                                                     uint32_t prim_min_lanes) {
   SssClient client(s, w, cur_parity, max_bounces);
-  TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle);
+  TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle, prim_min_lanes);
+}
+
+// The exit vertex of every walk that left the medium this iteration (random-walk-sss.h:385-404 +
+// cycles-principled-shader.cc:187-216): same-instance / back-face acceptance, NEE at the exit point, diffuse bounce.
+__global__ void __launch_bounds__(128) SssExitKernel(SceneView s, WaveState w, uint32_t next_parity) {
+  const uint32_t n = w.counters[kNumExit];
+  for (;;) {
+    const uint32_t slot = WarpFetch(&w.counters[kFetchExit]);
+    if (__all_sync(0xffffffffu, slot >= n)) break;
+    const bool valid = slot < n;
+    uint32_t p = 0;
+    bool to_next = false, to_done = false;
+    ShadowRequest req;
+    req.active = false;
+    vec3 throughput(0.f);
+    if (valid) {
+      p = w.q_exit[slot];
+      PathRegs r = LoadPath(w, p);   // ray + hit are still those of the ENTRY vertex
+      throughput = r.throughput;
+      const Surface entry_si = MakeSurface(s, r.ray, r.hit);
+      const Frame entry_frame = PrincipledFrame(entry_si);
+      const float4 a = LdWalk(w, p, kWalkA), b = LdWalk(w, p, kWalkB), c = LdWalk(w, p, kWalkC),
+                   d = LdWalk(w, p, kWalkD);
+      HitT hit;
+      hit.t = a.x; hit.u = a.y; hit.v = a.z; hit.prim = __float_as_uint(a.w);
+      SssWalkState walk;
+      walk.throughput = vec3(b.x, b.y, b.z);
+      walk.ray.o = vec3(c.x, c.y, c.z); walk.ray.tmin = c.w;
+      walk.ray.d = vec3(d.x, d.y, d.z); walk.ray.tmax = d.w;
+      VertexResult vr;
+      vr.P = entry_si.P;
+      vr.shadow[1].active = false;
+      SssFinish(s, entry_si, entry_frame, walk, hit, &r.rng, &vr);
+      req = vr.shadow[1];
+      CommitVertex(w, p, vr, throughput, r.L, r.depth, r.rng, r.pixel);
+      to_next = !IsBlack(vr.throughput * throughput);
+      to_done = !to_next;
+    }
+    PushShadow(w, req, throughput, p);
+    RouteSlot(w, next_parity, p, to_next, to_done);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ shadow rays
@@ -604,7 +688,7 @@ struct ShadowClient {
     if (!t.active && has_result) {
       has_result = false;
       if (t.hit.prim == kInvalid) {
-        float* dst = reinterpret_cast<float*>(&w.rad[__float_as_uint(c.w)]);
+        float* dst = reinterpret_cast<float*>(&w.slot[size_t(__float_as_uint(c.w)) * kSlotStride + kRad]);
         atomicAdd(dst + 0, c.x);
         atomicAdd(dst + 1, c.y);
         atomicAdd(dst + 2, c.z);
@@ -616,8 +700,8 @@ struct ShadowClient {
       const uint32_t slot = WarpAppend(&w.counters[kFetchShadow], need);
       if (need) {
         if (slot < n) {
-          const float4 o = w.sh_o[slot], d = w.sh_d[slot];
-          c = w.sh_c[slot];
+          const float4 o = __ldcs(&w.sh_o[slot]), d = __ldcs(&w.sh_d[slot]);
+          c = __ldcs(&w.sh_c[slot]);
           RayT ray;
           ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
           ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
@@ -637,9 +721,10 @@ struct ShadowClient {
 };
 
 template <bool HAS_CURVES>
-__global__ void __launch_bounds__(128) TraceAnyKernel(SceneView s, WaveState w, uint32_t refill_min_idle) {
+__global__ void __launch_bounds__(128) TraceAnyKernel(SceneView s, WaveState w, uint32_t refill_min_idle,
+                                                      uint32_t prim_min_lanes) {
   ShadowClient client(s, w);
-  TravEngine<true, HAS_CURVES, false>(s, client, refill_min_idle);
+  TravEngine<true, HAS_CURVES, false>(s, client, refill_min_idle, prim_min_lanes);
 }
 
 // ------------------------------------------------------------------------------------------------ test hooks
@@ -714,16 +799,17 @@ template <bool HAS_CURVES, bool STATS>
 __global__ void __launch_bounds__(128) TraceBatchKernel(SceneView s, const float4* __restrict__ rays, uint64_t n,
                                                         float4* hits_tuv, uint4* hits_ids, float4* hits_ng,
                                                         uint32_t* fetch, unsigned long long* stats,
-                                                        uint32_t refill_min_idle) {
+                                                        uint32_t refill_min_idle, uint32_t prim_min_lanes) {
   BatchClient client(s, rays, n, hits_tuv, hits_ids, hits_ng, nullptr, fetch, STATS ? stats : nullptr);
-  TravEngine<false, HAS_CURVES, STATS>(s, client, refill_min_idle);
+  TravEngine<false, HAS_CURVES, STATS>(s, client, refill_min_idle, prim_min_lanes);
 }
 
 template <bool HAS_CURVES>
 __global__ void __launch_bounds__(128) OccludedBatchKernel(SceneView s, const float4* __restrict__ rays, uint64_t n,
-                                                           uint8_t* out, uint32_t* fetch, uint32_t refill_min_idle) {
+                                                           uint8_t* out, uint32_t* fetch, uint32_t refill_min_idle,
+                                                           uint32_t prim_min_lanes) {
   BatchClient client(s, rays, n, nullptr, nullptr, nullptr, out, fetch, nullptr);
-  TravEngine<true, HAS_CURVES, false>(s, client, refill_min_idle);
+  TravEngine<true, HAS_CURVES, false>(s, client, refill_min_idle, prim_min_lanes);
 }
 
 }  // namespace pbr
