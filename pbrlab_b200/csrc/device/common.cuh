@@ -17,9 +17,13 @@
 #if defined(__CUDACC__)
 #define PBR_HD __host__ __device__ __forceinline__
 #define PBR_D __device__ __forceinline__
+// large routines with several call sites per kernel: one out-of-line copy keeps the shading kernels inside the
+// instruction cache (the fully inlined ShadeSurfaceKernel was 120 KB of SASS and stalled on instruction fetch)
+#define PBR_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define PBR_HD inline
 #define PBR_D inline
+#define PBR_HD_NOINLINE inline
 #include <algorithm>
 #include <cmath>
 #endif

@@ -65,7 +65,8 @@ struct Device {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t kev[12] = {};   // per-kernel-family timing of one iteration (profiling mode)
   // scene
-  DevBuf<float4> tri_nodes, tri_data, curve_nodes, curve_data, verts, normals, emissive, lprim_info;
+  DevBuf<float4> geom;   // [tri_nodes | tri_data | curve_nodes | curve_data]: one range for the L2 persistence window
+  DevBuf<float4> verts, normals, emissive, lprim_info;
   DevBuf<float2> texcoords;
   DevBuf<uint32_t> curve_prim, lprim_tri;
   DevBuf<uint4> tri_ids, tri_nidx, tri_vidx, tri_tidx, curve_ids;
@@ -87,7 +88,7 @@ struct Device {
   unsigned long long* h_stats = nullptr;
 
   void Release() {
-    tri_nodes.Free(); tri_data.Free(); curve_nodes.Free(); curve_data.Free(); verts.Free(); normals.Free();
+    geom.Free(); verts.Free(); normals.Free();
     emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); lprim_tri.Free(); tri_ids.Free();
     tri_nidx.Free(); tri_vidx.Free(); tri_tidx.Free(); curve_ids.Free(); materials.Free(); light_cdf.Free();
     lprim_cdf.Free(); lights.Free();
@@ -119,7 +120,10 @@ struct pbrgpu_ctx {
   uint32_t tune_refill = 16;       // idle lanes that trigger a refill in the traversal engine
   uint32_t tune_refill_sss = 24;   // same for the random-walk kernel (its converged section is the bounce itself)
   uint32_t tune_prim_lanes = 1, tune_prim_lanes_sss = 1;   // lanes with pending primitives that trigger a primitive phase
-  int tune_trace_blocks = 8, tune_shade_blocks = 4, tune_walk_blocks = 6;   // resident 128-thread blocks per SM
+  int tune_l2_persist = 0;         // persisting-L2 window over the traversal data
+  int tune_regen_blocks = 1;
+  int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
+  int tune_trace_blocks = 8, tune_shade_blocks = 1, tune_walk_blocks = 6;   // resident 128-thread blocks per SM
 };
 
 namespace {
@@ -141,10 +145,39 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   const pbrhost::HostScene& h = ctx->host;
   CUDA_TRY(ctx, cudaSetDevice(d.id));
   cudaStream_t st = d.stream;
-  CUDA_TRY(ctx, d.tri_nodes.Upload(h.tri_bvh.nodes.data(), h.tri_bvh.nodes.size() / 4, st));
-  CUDA_TRY(ctx, d.tri_data.Upload(h.tri_data.data(), h.tri_data.size(), st));
-  CUDA_TRY(ctx, d.curve_nodes.Upload(h.curve_bvh.nodes.data(), h.curve_bvh.nodes.size() / 4, st));
-  CUDA_TRY(ctx, d.curve_data.Upload(h.curve_data.data(), h.curve_data.size(), st));
+  // traversal data in one allocation: nodes first (hottest), then the leaf-ordered primitives
+  const size_t n_tn = h.tri_bvh.nodes.size() / 4, n_td = h.tri_data.size(), n_cn = h.curve_bvh.nodes.size() / 4,
+               n_cd = h.curve_data.size();
+  CUDA_TRY(ctx, d.geom.Alloc(std::max<size_t>(n_tn + n_td + n_cn + n_cd, 1)));
+  float4* g_tn = d.geom.ptr;
+  float4* g_cn = g_tn + n_tn;
+  float4* g_td = g_cn + n_cn;
+  float4* g_cd = g_td + n_td;
+  if (n_tn) CUDA_TRY(ctx, cudaMemcpyAsync(g_tn, h.tri_bvh.nodes.data(), n_tn * sizeof(float4), cudaMemcpyHostToDevice, st));
+  if (n_cn) CUDA_TRY(ctx, cudaMemcpyAsync(g_cn, h.curve_bvh.nodes.data(), n_cn * sizeof(float4), cudaMemcpyHostToDevice, st));
+  if (n_td) CUDA_TRY(ctx, cudaMemcpyAsync(g_td, h.tri_data.data(), n_td * sizeof(float4), cudaMemcpyHostToDevice, st));
+  if (n_cd) CUDA_TRY(ctx, cudaMemcpyAsync(g_cd, h.curve_data.data(), n_cd * sizeof(float4), cudaMemcpyHostToDevice, st));
+  {
+    // Keep the BVH in L2 while path state streams through: persisting window over as much of the traversal data as
+    // the device allows (nodes first), everything else in this stream is treated as streaming.
+    cudaDeviceProp prop;
+    CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, d.id));
+    const size_t bytes = (n_tn + n_td + n_cn + n_cd) * sizeof(float4);
+    if (ctx->tune_l2_persist && prop.persistingL2CacheMaxSize > 0 && bytes > 0) {
+      const size_t carve = std::min<size_t>(size_t(prop.persistingL2CacheMaxSize), bytes);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof(attr));
+      const size_t window = std::min<size_t>(bytes, size_t(prop.accessPolicyMaxWindowSize));
+      attr.accessPolicyWindow.base_ptr = d.geom.ptr;
+      attr.accessPolicyWindow.num_bytes = window;
+      attr.accessPolicyWindow.hitRatio = float(std::min(1.0, double(carve) / double(window)));
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();   // best effort
+    }
+  }
   CUDA_TRY(ctx, d.curve_prim.Upload(h.curve_prim.data(), h.curve_prim.size(), st));
   CUDA_TRY(ctx, d.tri_ids.Upload(h.tri_ids.data(), h.tri_ids.size(), st));
   CUDA_TRY(ctx, d.tri_nidx.Upload(h.tri_nidx.data(), h.tri_nidx.size(), st));
@@ -164,8 +197,8 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   SceneView& v = d.view;
   memset(&v, 0, sizeof(v));
-  v.tri_nodes = d.tri_nodes.ptr; v.tri_data = d.tri_data.ptr;
-  v.curve_nodes = d.curve_nodes.ptr; v.curve_data = d.curve_data.ptr; v.curve_prim = d.curve_prim.ptr;
+  v.tri_nodes = g_tn; v.tri_data = g_td;
+  v.curve_nodes = g_cn; v.curve_data = g_cd; v.curve_prim = d.curve_prim.ptr;
   v.num_tris = h.num_tris(); v.num_curves = h.num_curves();
   v.tri_ids = d.tri_ids.ptr; v.tri_nidx = d.tri_nidx.ptr; v.tri_vidx = d.tri_vidx.ptr; v.tri_tidx = d.tri_tidx.ptr;
   v.verts = d.verts.ptr; v.normals = d.normals.ptr; v.texcoords = d.texcoords.ptr; v.curve_ids = d.curve_ids.ptr;
@@ -239,19 +272,19 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     tm->launches += 1;
     mark(0);
     if (frame && have_done) {
-      pbr::RegenerateKernel<<<grid_shade, 256, 0, st>>>(w, *frame, parity);
+      pbr::RegenerateKernel<<<PersistentGrid(d, ctx->tune_regen_blocks), 256, 0, st>>>(w, *frame, parity);
       tm->launches += 1;
     }
     mark(1);
     if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes);
     else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes);
     mark(2);
-    pbr::ShadeSurfaceKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
-    if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next, flags);
+    pbr::ShadeSurfaceKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
+    if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
     mark(3);
     if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
     else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
-    pbr::SssExitKernel<<<grid_shade, kBlock, 0, st>>>(s, w, next);
+    pbr::SssExitKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next);
     mark(4);
     if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, refill, ctx->tune_prim_lanes);
     else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, refill, ctx->tune_prim_lanes);
@@ -439,6 +472,9 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_trace_blocks = std::max(1, env_int("PBRGPU_TRACE_BLOCKS", ctx->tune_trace_blocks));
   ctx->tune_shade_blocks = std::max(1, env_int("PBRGPU_SHADE_BLOCKS", ctx->tune_shade_blocks));
   ctx->tune_walk_blocks = std::max(1, env_int("PBRGPU_WALK_BLOCKS", ctx->tune_walk_blocks));
+  ctx->tune_regen_blocks = std::max(1, env_int("PBRGPU_REGEN_BLOCKS", ctx->tune_regen_blocks));
+  ctx->tune_l2_persist = env_int("PBRGPU_L2_PERSIST", ctx->tune_l2_persist);
+  ctx->tune_shade_threads = std::min(pbr::kShadeBlock, std::max(32, env_int("PBRGPU_SHADE_THREADS", ctx->tune_shade_threads) & ~31));
   for (int id : ids) {
     if (id < 0 || id >= ndev) {
       g_create_error = "pbrgpu_create: device id out of range";

@@ -87,6 +87,7 @@ struct WaveState {
 };
 
 constexpr uint32_t kNoPixel = 0xFFFFFFFFu;
+constexpr int kShadeBlock = 512;   // most threads per block of the shading kernels (block-synchronous batches)
 
 // ---- streaming access to slot state (ld/st.global.cs: evict-first in L2)
 __device__ __forceinline__ float4 LdSlot(const WaveState& w, uint32_t p, int field) {
@@ -121,6 +122,18 @@ __device__ __forceinline__ uint32_t WarpFetch(uint32_t* fetch_counter) {
   if (lane == 0) base = atomicAdd(fetch_counter, 32u);
   base = __shfl_sync(0xffffffffu, base, 0);
   return base + uint32_t(lane);
+}
+
+// A whole block pulls the next blockDim.x queue slots and re-converges: the shading kernels are long straight-line
+// code (70-120 KB of SASS, every instruction executed once per path), so warps that drift apart each stream the
+// code from L2 on their own — measured 67 % of warp time waiting on instruction fetch.  Warps that start every batch
+// together share the fetched lines.
+__device__ __forceinline__ uint32_t BlockFetch(uint32_t* fetch_counter) {
+  __shared__ uint32_t s_base;
+  __syncthreads();
+  if (threadIdx.x == 0) s_base = atomicAdd(fetch_counter, blockDim.x);
+  __syncthreads();
+  return s_base + threadIdx.x;
 }
 
 __device__ __forceinline__ RayT LoadRay(const WaveState& w, uint32_t p) {
@@ -422,12 +435,12 @@ __device__ __forceinline__ void ResumeWalk(const WaveState& w, uint32_t p, SssWa
 
 // emission + MIS, roulette, material dispatch, Principled vertex.  When the vertex selects the random-walk closure
 // the walk is set up here (entry direction + coefficients, random-walk-sss.h:227-279) and parked for sss_walk.
-__global__ void __launch_bounds__(128) ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t next_parity,
+__global__ void __launch_bounds__(kShadeBlock) ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t next_parity,
                                                           ShadeFlags flags) {
   const uint32_t n = w.counters[kNumSurface];
   for (;;) {
-    const uint32_t slot = WarpFetch(&w.counters[kFetchSurface]);
-    if (__all_sync(0xffffffffu, slot >= n)) break;
+    const uint32_t slot = BlockFetch(&w.counters[kFetchSurface]);
+    if (slot - threadIdx.x >= n) break;   // block-uniform
     const bool valid = slot < n;
     uint32_t p = 0;
     bool to_sss = false, to_next = false, to_done = false;
@@ -484,12 +497,12 @@ __global__ void __launch_bounds__(128) ShadeSurfaceKernel(SceneView s, WaveState
   }
 }
 
-__global__ void __launch_bounds__(128) ShadeHairKernel(SceneView s, WaveState w, uint32_t next_parity,
+__global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, WaveState w, uint32_t next_parity,
                                                        ShadeFlags flags) {
   const uint32_t n = w.counters[kNumHair];
   for (;;) {
-    const uint32_t slot = WarpFetch(&w.counters[kFetchHair]);
-    if (__all_sync(0xffffffffu, slot >= n)) break;
+    const uint32_t slot = BlockFetch(&w.counters[kFetchHair]);
+    if (slot - threadIdx.x >= n) break;   // block-uniform
     const bool valid = slot < n;
     uint32_t p = 0;
     bool to_next = false, to_done = false;
@@ -631,11 +644,11 @@ __global__ void __launch_bounds__(128) SssWalkKernel(SceneView s, WaveState w, u
 
 // The exit vertex of every walk that left the medium this iteration (random-walk-sss.h:385-404 +
 // cycles-principled-shader.cc:187-216): same-instance / back-face acceptance, NEE at the exit point, diffuse bounce.
-__global__ void __launch_bounds__(128) SssExitKernel(SceneView s, WaveState w, uint32_t next_parity) {
+__global__ void __launch_bounds__(kShadeBlock) SssExitKernel(SceneView s, WaveState w, uint32_t next_parity) {
   const uint32_t n = w.counters[kNumExit];
   for (;;) {
-    const uint32_t slot = WarpFetch(&w.counters[kFetchExit]);
-    if (__all_sync(0xffffffffu, slot >= n)) break;
+    const uint32_t slot = BlockFetch(&w.counters[kFetchExit]);
+    if (slot - threadIdx.x >= n) break;   // block-uniform
     const bool valid = slot < n;
     uint32_t p = 0;
     bool to_next = false, to_done = false;
