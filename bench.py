@@ -95,25 +95,46 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def reference_arm(args, rank):
-    """times pbrlab::Render() of the compiled reference on the host cores (all hardware threads, as it always does)"""
+def cpu_render(files, w, h, spp, warm_spp=1):
+    """pbrlab::Render() on the host cores: the compiled unmodified reference (oracle/_ref) when it travelled with the
+    snapshot, else the restated oracle (oracle/libpbr_oracle.so).  Returns (seconds, cores, kind)."""
     import refbind
+    if refbind.available():
+        R = refbind.RefLib()
+        S = R.scene(files)
+        if warm_spp:
+            S.render(w, h, warm_spp)
+        _, _, sec = S.render(w, h, spp)
+        return sec, R.num_threads(), "reference"
+    import oraclebind
+    import pbrlab_b200 as pb
+    if not oraclebind.available():
+        return None, 0, "unavailable"
+    host = pb.Scene(files, commit_to_device=False)
+    O = oraclebind.Oracle(host.flat())
+    if warm_spp:
+        O.render(w, h, warm_spp)
+    _, _, sec, _ = O.render(w, h, spp)
+    return sec, os.cpu_count() or 1, "port"
+
+
+def reference_arm(args, rank):
+    """times the reference's own CPU implementation of the path on the host cores (all hardware threads, as
+    pbrlab::Render() always does) on a bounded sample of the workload"""
     desc, w, h, spp = WORKLOADS[args.workload]
     if rank != 0:
         return
-    if not refbind.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpbrlab_ref.so not present on this box"}))
-        return
     files, _, _ = scene_files(args.workload)
-    R = refbind.RefLib()
-    S = R.scene(files)
     sample_spp = args.ref_spp
-    for _ in range(args.warmup):
-        S.render(w, h, 1)
     secs = []
-    for _ in range(args.steps):
-        _, _, sec = S.render(w, h, sample_spp)
-        secs.append(sec)
+    cores, kind = 0, "unavailable"
+    for i in range(args.warmup + args.steps):
+        sec, cores, kind = cpu_render(files, w, h, 1 if i < args.warmup else sample_spp, warm_spp=0)
+        if sec is None:
+            print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref nor oracle/libpbr_oracle.so is present"}))
+            return
+        if i >= args.warmup:
+            secs.append(sec)
     t = sum(secs) / len(secs)
     v = w * h * sample_spp / t * 1e-6
     sample = "%dx%d, %d of %d spp per step (throughput is spp-independent)" % (w, h, sample_spp, spp)
@@ -121,8 +142,7 @@ def reference_arm(args, rank):
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": desc, "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": R.num_threads(), "kind": "reference",
-                             "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -250,7 +270,7 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("TraceClosestKernel")
+        traffic = json.load(open(tpath)).get("TraceClosestKernel_bytes_per_launch")
 
     if rank == 0:
         samples_step = npix * spp_total
@@ -263,7 +283,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": w, "height": h, "spp_per_gpu": spp_per_gpu, "spp_total": spp_total,
                        "split": "interleaved samples, scene replicated, one NCCL reduce per frame" if world > 1 else "single GPU",
-                       "l2": "path pool state (~2.4 GB SoA) is larger than L2; scene (19 MB) is L2-resident by nature",
+                       "l2": "inputs larger than L2: the path pool (~2 GB of slot lines) streams through every iteration; the scene (19 MB) is L2-resident by nature",
                        "scene_commit_s": commit_s, "seed": seed},
             "Mrays_per_s": mrays, "rays_per_sample": float(rays_t.item()) / samples_step,
             "e2e": {"value": e2e_value, "unit": "Msamples/s",
@@ -276,18 +296,11 @@ def main():
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
-            import refbind
-            if refbind.available():
-                R = refbind.RefLib()
-                S = R.scene(files)
-                S.render(w, h, 1)
-                _, _, sec = S.render(w, h, args.ref_spp)
-                line["cpu_baseline"] = {"value": w * h * args.ref_spp / sec * 1e-6, "unit": "Msamples/s",
-                                        "cores": R.num_threads(), "kind": "reference",
-                                        "sample": "%dx%d at %d spp (of %d), pbrlab::Render() of oracle/_ref" % (w, h, args.ref_spp, spp_total)}
-            else:
-                line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference",
-                                        "sample": "oracle/_ref not present on this box"}
+            sec, cores, kind = cpu_render(files, w, h, args.ref_spp)
+            sample = "%dx%d at %d spp (of %d), pbrlab::Render() of %s" % (
+                w, h, args.ref_spp, spp_total, "oracle/_ref" if kind == "reference" else "oracle/pbr_oracle.cc")
+            line["cpu_baseline"] = {"value": (w * h * args.ref_spp / sec * 1e-6) if sec else None, "unit": "Msamples/s",
+                                    "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
