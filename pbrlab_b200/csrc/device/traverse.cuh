@@ -206,8 +206,22 @@ PBR_HD uint32_t popc(uint32_t x) {
 #endif
 }
 
+// byte j of x as the float 32768 + byte: the byte goes to mantissa bits 8..15 of 2^15 (one PRMT on the device instead
+// of an int->float conversion on the quarter-rate XU pipe, which ncu showed as the busiest pipe of the traversal)
+PBR_HD float byte_as_biased_float(uint32_t x, uint32_t j) {
+#if defined(__CUDA_ARCH__)
+  // result bytes: b0 = 0x00 (magic.b0), b1 = x.bj, b2 = 0x00 (magic.b2), b3 = 0x47 (magic.b3)
+  return __uint_as_float(__byte_perm(x, 0x47000000u, 0x7604u | (j << 4)));
+#else
+  return u2f(0x47000000u | (((x >> (8u * j)) & 0xffu) << 8));
+#endif
+}
+
 // Slab-test the 8 quantised child boxes of one node; returns the hit mask: bits 24..31 = internal children in
 // octant-adjusted traversal order, bits 0..23 = primitives of hit leaf children (relative to the node's prim base).
+// t = (p + q*2^e - o) / d is evaluated as fma(32768 + q, s, c) with s = 2^e/d and c = (p - o)/d - 32768 s.  c carries a
+// rounding error of up to |s|/512 (1/512 of a grid step), so the near side is pushed out by |s|/256 and the far side
+// by the same plus 4 ulps: the test stays conservative, which is all a box test has to be.
 PBR_HD uint32_t NodeIntersect(const vec3& o_over_d, const vec3& inv_d, uint32_t oct_inv4, bool neg_x, bool neg_y,
                               bool neg_z, float tmin, float tmax, const float4& n0, const float4& n1,
                               const float4& n2, const float4& n3, const float4& n4) {
@@ -215,9 +229,13 @@ PBR_HD uint32_t NodeIntersect(const vec3& o_over_d, const vec3& inv_d, uint32_t 
   const float sx = u2f(extract_byte(ew, 0) << 23) * inv_d.x;
   const float sy = u2f(extract_byte(ew, 1) << 23) * inv_d.y;
   const float sz = u2f(extract_byte(ew, 2) << 23) * inv_d.z;
-  const float ox = n0.x * inv_d.x - o_over_d.x;   // (p - o) / d
-  const float oy = n0.y * inv_d.y - o_over_d.y;
-  const float oz = n0.z * inv_d.z - o_over_d.z;
+  const float ox = pbr_fma(-32768.0f, sx, pbr_fma(n0.x, inv_d.x, -o_over_d.x));   // (p - o)/d - 32768 s
+  const float oy = pbr_fma(-32768.0f, sy, pbr_fma(n0.y, inv_d.y, -o_over_d.y));
+  const float oz = pbr_fma(-32768.0f, sz, pbr_fma(n0.z, inv_d.z, -o_over_d.z));
+  const float mx = fabsf(sx) * (1.0f / 256.0f), my = fabsf(sy) * (1.0f / 256.0f), mz = fabsf(sz) * (1.0f / 256.0f);
+  const float olx = ox - mx, oly = oy - my, olz = oz - mz;   // near side
+  const float ohx = ox + mx, ohy = oy + my, ohz = oz + mz;   // far side
+  const float tmax_s = tmax * 1.0000004f + 1e-30f;
   uint32_t hit_mask = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -238,16 +256,15 @@ PBR_HD uint32_t NodeIntersect(const vec3& o_over_d, const vec3& inv_d, uint32_t 
 #pragma unroll
 #endif
     for (uint32_t j = 0; j < 4; ++j) {
-      const float tlx = pbr_fma(float(extract_byte(x_min, j)), sx, ox);
-      const float tly = pbr_fma(float(extract_byte(y_min, j)), sy, oy);
-      const float tlz = pbr_fma(float(extract_byte(z_min, j)), sz, oz);
-      const float thx = pbr_fma(float(extract_byte(x_max, j)), sx, ox);
-      const float thy = pbr_fma(float(extract_byte(y_max, j)), sy, oy);
-      const float thz = pbr_fma(float(extract_byte(z_max, j)), sz, oz);
+      const float tlx = pbr_fma(byte_as_biased_float(x_min, j), sx, olx);
+      const float tly = pbr_fma(byte_as_biased_float(y_min, j), sy, oly);
+      const float tlz = pbr_fma(byte_as_biased_float(z_min, j), sz, olz);
+      const float thx = pbr_fma(byte_as_biased_float(x_max, j), sx, ohx);
+      const float thy = pbr_fma(byte_as_biased_float(y_max, j), sy, ohy);
+      const float thz = pbr_fma(byte_as_biased_float(z_max, j), sz, ohz);
       const float tn = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
-      const float tf = fminf(fminf(thx, thy), fminf(thz, tmax));
-      // a few ulps of slack keep the quantised-box test conservative under rounding
-      if (tn <= tf * 1.0000004f + 1e-30f) {
+      const float tf = fminf(fminf(thx, thy), fminf(thz, tmax_s));
+      if (tn <= tf) {
         hit_mask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
       }
     }
