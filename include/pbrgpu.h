@@ -92,6 +92,7 @@ typedef struct pbrgpu_stats {
   double   device_ms;      /* CUDA-event time from the first to the last kernel of the call on the launching stream
                               (max over the context's devices) */
   uint64_t trace_closest_launches;
+  uint64_t sss_skipped;    /* random-walk segments answered by the clearance grid instead of a ray query */
 } pbrgpu_stats;
 
 /* ---- life cycle.  device_ids == NULL / n_devices == 0: the current device only. */

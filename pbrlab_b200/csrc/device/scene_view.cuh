@@ -47,6 +47,14 @@ struct SceneView {
   const float* lprim_cdf;      // per light primitive: AreaLight::cumulative_probability_
   const float4* lprim_info;    // per light primitive: emission rgb, pdf = P(light) P(prim) / area
   const uint32_t* lprim_tri;   // per light primitive: triangle primitive id
+  // ---- clearance grid for random-walk segments (scene_host.cc: BuildClearance): bit = 1 <=> some primitive's box
+  // touches the 3x3x3 cells around this cell.  kClearLevels resolutions, level L has (clear_dim >> L)^3 cells.
+  const uint32_t* clear_bits;  // null: no subsurface material in the scene
+  float clear_org[3], clear_inv_cell[3];   // level-0 grid: origin, 1 / cell size per axis
+  float clear_cell_min;        // shortest level-0 cell edge
+  uint32_t clear_dim;          // level-0 cells per axis
+  uint32_t clear_off[6];       // first 32-bit word of every level
 };
+constexpr uint32_t kClearLevels = 5;
 
 }  // namespace pbr

@@ -348,6 +348,30 @@ PBR_HD bool SssBegin(const Surface& si, const Frame& entry, const PrincipledBsdf
 
 enum SssStep { kSssContinue = 0, kSssHit = 1, kSssAbsorbed = 2 };
 
+// Can a walk segment of length `len` starting at `o` (any direction) be declared free of intersections without
+// tracing it?  Most segments of a random walk are much shorter than the distance to the nearest surface, yet each one
+// costs a root-to-leaf traversal.  The clearance grid answers conservatively: at the coarsest level whose cells are
+// longer than the segment, a clear bit means no primitive box touches the 27 cells around the start point, and the
+// segment cannot leave those cells.  A segment that is skipped is one the query would have reported "no hit" for, so
+// the walk takes exactly the same decisions (same random numbers, same result).
+PBR_HD bool SegmentIsClear(const SceneView& s, const vec3& o, float len) {
+  if (!s.clear_bits) return false;
+  const float gx = (o.x - s.clear_org[0]) * s.clear_inv_cell[0];
+  const float gy = (o.y - s.clear_org[1]) * s.clear_inv_cell[1];
+  const float gz = (o.z - s.clear_org[2]) * s.clear_inv_cell[2];
+  const float dim = float(s.clear_dim);
+  if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < dim && gy < dim && gz < dim)) return false;
+  float reach = s.clear_cell_min * 0.98f;   // 2 % margin: rounding of the cell index and of the hit point
+  uint32_t level = 0;
+  while (len > reach && level < kClearLevels) { reach *= 2.0f; ++level; }
+  if (level >= kClearLevels) return false;
+  const uint32_t d = s.clear_dim >> level;
+  const uint32_t ix = uint32_t(gx) >> level, iy = uint32_t(gy) >> level, iz = uint32_t(gz) >> level;
+  const uint32_t idx = (iz * d + iy) * d + ix;
+  const uint32_t word = s.clear_bits[s.clear_off[level] + (idx >> 5)];
+  return ((word >> (idx & 31u)) & 1u) == 0u;
+}
+
 // One iteration of the walk loop (:281-383), split at the ray query so that the wavefront's walk kernel can run the
 // query in its warp traversal engine:
 //   SssPrepareSegment: new direction (bounces > 0) + scatter distance -> w->ray (tmax = scatter distance)

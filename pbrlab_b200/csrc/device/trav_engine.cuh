@@ -164,7 +164,9 @@ __device__ __forceinline__ void TravEngine(const SceneView& s, Client& client, u
       const bool dry = client.Refill(t, exhausted);
       exhausted = __any_sync(0xffffffffu, dry) || exhausted;
       if (__ballot_sync(0xffffffffu, t.active) == 0u) {
-        if (exhausted) break;
+        // nobody traverses: done once the source is dry and no idle lane still holds work for another Refill
+        // (a walk whose segment was answered without a query is idle but not finished)
+        if (exhausted && __ballot_sync(0xffffffffu, client.Wants(t, exhausted)) == 0u) break;
         continue;
       }
     }

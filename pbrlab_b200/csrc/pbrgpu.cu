@@ -68,7 +68,7 @@ struct Device {
   DevBuf<float4> geom;   // [tri_nodes | tri_data | curve_nodes | curve_data]: one range for the L2 persistence window
   DevBuf<float4> verts, normals, emissive, lprim_info;
   DevBuf<float2> texcoords;
-  DevBuf<uint32_t> curve_prim, lprim_tri;
+  DevBuf<uint32_t> curve_prim, lprim_tri, clear_bits;
   DevBuf<uint4> tri_ids, tri_nidx, tri_vidx, tri_tidx, curve_ids;
   DevBuf<pbr::DeviceMaterial> materials;
   DevBuf<float> light_cdf, lprim_cdf;
@@ -88,7 +88,7 @@ struct Device {
   unsigned long long* h_stats = nullptr;
 
   void Release() {
-    geom.Free(); verts.Free(); normals.Free();
+    geom.Free(); clear_bits.Free(); verts.Free(); normals.Free();
     emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); lprim_tri.Free(); tri_ids.Free();
     tri_nidx.Free(); tri_vidx.Free(); tri_tidx.Free(); curve_ids.Free(); materials.Free(); light_cdf.Free();
     lprim_cdf.Free(); lights.Free();
@@ -122,6 +122,8 @@ struct pbrgpu_ctx {
   uint32_t tune_prim_lanes = 1, tune_prim_lanes_sss = 1;   // lanes with pending primitives that trigger a primitive phase
   int tune_l2_persist = 0;         // persisting-L2 window over the traversal data
   int tune_regen_blocks = 1;
+  int tune_sss_skip = 1;           // clearance grid: random-walk segments that provably hit nothing are not traced
+  int tune_fuse_regen = 1;         // retire + regenerate inside the closest-hit kernel instead of a separate launch
   int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
   int tune_trace_blocks = 8, tune_shade_blocks = 1, tune_walk_blocks = 6;   // resident 128-thread blocks per SM
 };
@@ -194,6 +196,7 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   CUDA_TRY(ctx, d.lprim_cdf.Upload(h.lprim_cdf.data(), h.lprim_cdf.size(), st));
   CUDA_TRY(ctx, d.lprim_info.Upload(h.lprim_info.data(), h.lprim_info.size(), st));
   CUDA_TRY(ctx, d.lprim_tri.Upload(h.lprim_tri.data(), h.lprim_tri.size(), st));
+  CUDA_TRY(ctx, d.clear_bits.Upload(h.clear_bits.data(), h.clear_bits.size(), st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   SceneView& v = d.view;
   memset(&v, 0, sizeof(v));
@@ -206,6 +209,11 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   v.emissive = d.emissive.ptr; v.light_cdf = d.light_cdf.ptr; v.lights = d.lights.ptr;
   v.num_lights = uint32_t(h.lights.size());
   v.lprim_cdf = d.lprim_cdf.ptr; v.lprim_info = d.lprim_info.ptr; v.lprim_tri = d.lprim_tri.ptr;
+  v.clear_bits = (ctx->tune_sss_skip && !h.clear_bits.empty()) ? d.clear_bits.ptr : nullptr;
+  for (int k = 0; k < 3; ++k) { v.clear_org[k] = h.clear_org[k]; v.clear_inv_cell[k] = h.clear_inv_cell[k]; }
+  v.clear_cell_min = h.clear_cell_min;
+  v.clear_dim = h.clear_dim;
+  for (int k = 0; k < 6; ++k) v.clear_off[k] = h.clear_off[k];
   return PBRGPU_OK;
 }
 
@@ -257,6 +265,8 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
   const int grid_walk = PersistentGrid(d, ctx->tune_walk_blocks);
   const bool curves = s.num_curves != 0u;
   const uint32_t refill = ctx->tune_refill;
+  pbr::FrameParams no_frame;
+  memset(&no_frame, 0, sizeof(no_frame));
   // state after the set-up kernel (host knows it): hooks start with n active slots, frames with N retired slots
   bool have_active = (frame == nullptr), have_walk = false, have_done = (frame != nullptr);
   uint64_t in_flight = ~0ull;   // slots that will trace or walk in the coming iteration (unknown before the first)
@@ -271,13 +281,14 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, parity);
     tm->launches += 1;
     mark(0);
-    if (frame && have_done) {
+    const bool fuse = frame && ctx->tune_fuse_regen;
+    if (frame && have_done && !fuse) {
       pbr::RegenerateKernel<<<PersistentGrid(d, ctx->tune_regen_blocks), 256, 0, st>>>(w, *frame, parity);
       tm->launches += 1;
     }
     mark(1);
-    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes);
-    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes);
+    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, fuse ? 1u : 0u);
+    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, fuse ? 1u : 0u);
     mark(2);
     pbr::ShadeSurfaceKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
     if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
@@ -474,6 +485,8 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_walk_blocks = std::max(1, env_int("PBRGPU_WALK_BLOCKS", ctx->tune_walk_blocks));
   ctx->tune_regen_blocks = std::max(1, env_int("PBRGPU_REGEN_BLOCKS", ctx->tune_regen_blocks));
   ctx->tune_l2_persist = env_int("PBRGPU_L2_PERSIST", ctx->tune_l2_persist);
+  ctx->tune_fuse_regen = env_int("PBRGPU_FUSE_REGEN", ctx->tune_fuse_regen);
+  ctx->tune_sss_skip = env_int("PBRGPU_SSS_SKIP", ctx->tune_sss_skip);
   ctx->tune_shade_threads = std::min(pbr::kShadeBlock, std::max(32, env_int("PBRGPU_SHADE_THREADS", ctx->tune_shade_threads) & ~31));
   for (int id : ids) {
     if (id < 0 || id >= ndev) {
@@ -680,6 +693,7 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
       s.closest_rays += d.h_stats[pbr::kStatClosest];
       s.shadow_rays += d.h_stats[pbr::kStatShadow];
       s.sss_rays += d.h_stats[pbr::kStatSss];
+      s.sss_skipped += d.h_stats[pbr::kStatSssSkipped];
     }
     s.kernel_launches += tms[k].launches;
     s.trace_closest_launches += tms[k].closest_launches;
@@ -863,9 +877,9 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
     CUDA_TRY(ctx, dface.Alloc(2 * n));
     pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters, 0u);
     if (d.view.num_curves)
-      pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes);
+      pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), 0u);
     else
-      pbr::TraceClosestKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes);
+      pbr::TraceClosestKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), 0u);
     SurfaceFaceKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.view, d.wave, n32, dface.ptr);
     // restore the entry state for the real iteration below
     pbr::InitPathsFromRaysKernel<<<(std::max(n32, 64u) + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);
@@ -913,6 +927,7 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
   ctx->stats.closest_rays = d.h_stats[pbr::kStatClosest];
   ctx->stats.shadow_rays = d.h_stats[pbr::kStatShadow];
   ctx->stats.sss_rays = d.h_stats[pbr::kStatSss];
+  ctx->stats.sss_skipped = d.h_stats[pbr::kStatSssSkipped];
   ctx->stats.kernel_launches = tm.launches;
   dr.Free(); ds.Free();
   return rc;

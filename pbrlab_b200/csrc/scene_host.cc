@@ -252,9 +252,139 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
     bmin[k] = bmin_in ? bmin_in[k] : lo[k];
     bmax[k] = bmax_in ? bmax_in[k] : hi[k];
   }
+  BuildClearance();
   committed = true;
   build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return true;
+}
+
+// Multi-resolution occupancy of the region where random walks happen (the bounds of every triangle whose material has
+// subsurface enabled).  ALL primitives are rasterised — a walk segment is intersected with the whole scene
+// (random-walk-sss.h:310) — by their boxes, refined for large triangles by the triangle's plane; each level is then
+// dilated by one cell so that a clear bit vouches for the 27 cells around a point.
+void HostScene::BuildClearance() {
+  clear_bits.clear();
+  clear_dim = 0;
+  const uint32_t nt = num_tris();
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  bool any = false;
+  for (uint32_t i = 0; i < nt; ++i) {
+    const uint32_t m = tri_ids[i].w;
+    if (m == PBRGPU_INVALID_ID || m >= materials.size()) continue;
+    if (materials[m].type != 0 || !(materials[m].p[3] > 1e-3f)) continue;   // subsurface > kClosureWeightCutOff
+    any = true;
+    const F4* v[3] = {&verts[tri_vidx[i].x], &verts[tri_vidx[i].y], &verts[tri_vidx[i].z]};
+    for (int c = 0; c < 3; ++c) {
+      lo[0] = std::min(lo[0], v[c]->x); hi[0] = std::max(hi[0], v[c]->x);
+      lo[1] = std::min(lo[1], v[c]->y); hi[1] = std::max(hi[1], v[c]->y);
+      lo[2] = std::min(lo[2], v[c]->z); hi[2] = std::max(hi[2], v[c]->z);
+    }
+  }
+  if (!any) return;
+  const uint32_t R = 256;
+  float cell[3];
+  for (int k = 0; k < 3; ++k) {
+    const float ext = std::max(hi[k] - lo[k], 1e-6f);
+    lo[k] -= 0.01f * ext;
+    cell[k] = (1.02f * ext) / float(R);
+    clear_org[k] = lo[k];
+    clear_inv_cell[k] = 1.0f / cell[k];
+  }
+  clear_cell_min = std::min(cell[0], std::min(cell[1], cell[2]));
+  clear_dim = R;
+  std::vector<uint8_t> occ(size_t(R) * R * R, 0);
+  auto mark_box = [&](const float* blo, const float* bhi, const float* plane /* n.xyz, d or null */) {
+    int a[3], b[3];
+    for (int k = 0; k < 3; ++k) {
+      const float fa = (blo[k] - clear_org[k]) * clear_inv_cell[k] - 0.01f, fb = (bhi[k] - clear_org[k]) * clear_inv_cell[k] + 0.01f;
+      if (fb < 0.f || fa >= float(R)) return;
+      a[k] = std::max(0, int(std::floor(fa)));
+      b[k] = std::min(int(R) - 1, int(std::floor(fb)));
+    }
+    const bool refine = plane && (size_t(b[0] - a[0] + 1) * (b[1] - a[1] + 1) * (b[2] - a[2] + 1) > 64);
+    const float rad = refine ? 0.51f * (std::fabs(plane[0]) * cell[0] + std::fabs(plane[1]) * cell[1] + std::fabs(plane[2]) * cell[2]) : 0.f;
+    for (int z = a[2]; z <= b[2]; ++z)
+      for (int y = a[1]; y <= b[1]; ++y) {
+        uint8_t* row = &occ[(size_t(z) * R + y) * R];
+        if (!refine) {
+          for (int x = a[0]; x <= b[0]; ++x) row[x] = 1;
+        } else {
+          const float cy = clear_org[1] + (y + 0.5f) * cell[1], cz = clear_org[2] + (z + 0.5f) * cell[2];
+          for (int x = a[0]; x <= b[0]; ++x) {
+            const float cx = clear_org[0] + (x + 0.5f) * cell[0];
+            if (std::fabs(plane[0] * cx + plane[1] * cy + plane[2] * cz + plane[3]) <= rad) row[x] = 1;
+          }
+        }
+      }
+  };
+  for (uint32_t i = 0; i < nt; ++i) {
+    const F4 &a = verts[tri_vidx[i].x], &b = verts[tri_vidx[i].y], &c = verts[tri_vidx[i].z];
+    const float blo[3] = {std::min(a.x, std::min(b.x, c.x)), std::min(a.y, std::min(b.y, c.y)), std::min(a.z, std::min(b.z, c.z))};
+    const float bhi[3] = {std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z))};
+    const float e1[3] = {b.x - a.x, b.y - a.y, b.z - a.z}, e2[3] = {c.x - a.x, c.y - a.y, c.z - a.z};
+    float n[4] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0], 0.f};
+    const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (len > 0.f) {
+      n[0] /= len; n[1] /= len; n[2] /= len;
+      n[3] = -(n[0] * a.x + n[1] * a.y + n[2] * a.z);
+      mark_box(blo, bhi, n);
+    } else {
+      mark_box(blo, bhi, nullptr);
+    }
+  }
+  for (uint32_t i = 0; i < num_curves(); ++i) {
+    const F4* cp = &curve_cps[4 * size_t(i)];
+    float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, r = 0.f;
+    for (int c = 0; c < 4; ++c) {
+      r = std::max(r, std::fabs(cp[c].w));
+      blo[0] = std::min(blo[0], cp[c].x); bhi[0] = std::max(bhi[0], cp[c].x);
+      blo[1] = std::min(blo[1], cp[c].y); bhi[1] = std::max(bhi[1], cp[c].y);
+      blo[2] = std::min(blo[2], cp[c].z); bhi[2] = std::max(bhi[2], cp[c].z);
+    }
+    for (int k = 0; k < 3; ++k) { blo[k] -= r; bhi[k] += r; }   // convex hull of the control points grown by the radius
+    mark_box(blo, bhi, nullptr);
+  }
+  // levels: dilate a copy, pack, then halve the undilated occupancy
+  size_t words = 0;
+  for (uint32_t l = 0; l < pbr::kClearLevels; ++l) {
+    clear_off[l] = uint32_t(words);
+    const size_t d = R >> l;
+    words += (d * d * d + 31) / 32;
+  }
+  clear_off[pbr::kClearLevels] = uint32_t(words);
+  clear_bits.assign(words, 0u);
+  std::vector<uint8_t> cur = std::move(occ), tmp, nxt;
+  for (uint32_t l = 0; l < pbr::kClearLevels; ++l) {
+    const int d = int(R >> l);
+    tmp = cur;
+    // separable 3-wide maximum along x, y, z
+    for (int axis = 0; axis < 3; ++axis) {
+      std::vector<uint8_t> out(tmp.size());
+      const size_t stride = axis == 0 ? 1 : (axis == 1 ? size_t(d) : size_t(d) * d);
+      for (int z = 0; z < d; ++z)
+        for (int y = 0; y < d; ++y)
+          for (int x = 0; x < d; ++x) {
+            const size_t i = (size_t(z) * d + y) * d + x;
+            const int c = axis == 0 ? x : (axis == 1 ? y : z);
+            uint8_t v = tmp[i];
+            if (c > 0) v |= tmp[i - stride];
+            if (c + 1 < d) v |= tmp[i + stride];
+            out[i] = v;
+          }
+      tmp.swap(out);
+    }
+    uint32_t* bits = &clear_bits[clear_off[l]];
+    for (size_t i = 0; i < tmp.size(); ++i) if (tmp[i]) bits[i >> 5] |= 1u << (i & 31);
+    if (l + 1 < pbr::kClearLevels) {
+      const int h = d / 2;
+      nxt.assign(size_t(h) * h * h, 0);
+      for (int z = 0; z < d; ++z)
+        for (int y = 0; y < d; ++y)
+          for (int x = 0; x < d; ++x)
+            if (cur[(size_t(z) * d + y) * d + x]) nxt[(size_t(z / 2) * h + y / 2) * h + x / 2] = 1;
+      cur.swap(nxt);
+    }
+  }
 }
 
 pbr::SceneView HostScene::HostView() const {
@@ -284,6 +414,11 @@ pbr::SceneView HostScene::HostView() const {
   v.lprim_cdf = lprim_cdf.data();
   v.lprim_info = reinterpret_cast<const float4*>(lprim_info.data());
   v.lprim_tri = lprim_tri.data();
+  v.clear_bits = clear_bits.empty() ? nullptr : clear_bits.data();
+  for (int k = 0; k < 3; ++k) { v.clear_org[k] = clear_org[k]; v.clear_inv_cell[k] = clear_inv_cell[k]; }
+  v.clear_cell_min = clear_cell_min;
+  v.clear_dim = clear_dim;
+  for (int k = 0; k < 6; ++k) v.clear_off[k] = clear_off[k];
   return v;
 }
 

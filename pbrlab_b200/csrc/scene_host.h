@@ -39,6 +39,10 @@ struct HostScene {
   std::vector<F4> curve_data;    // 4 per segment, leaf order
   std::vector<uint32_t> curve_prim;
   float bmin[3], bmax[3];
+  // clearance grid for random-walk segments (see device/scene_view.cuh); empty when no material scatters
+  std::vector<uint32_t> clear_bits;
+  float clear_org[3] = {0, 0, 0}, clear_inv_cell[3] = {0, 0, 0}, clear_cell_min = 0.f;
+  uint32_t clear_dim = 0, clear_off[6] = {0, 0, 0, 0, 0, 0};
   bool committed = false;
   double build_seconds = 0.0;
 
@@ -53,6 +57,7 @@ struct HostScene {
   bool SetMaterials(const pbrgpu_material* m, uint32_t n);
   bool SetLights(const pbrgpu_light_tables* t);
   bool Commit(const float* bmin_in, const float* bmax_in);
+  void BuildClearance();
 
   uint32_t num_tris() const { return uint32_t(tri_vidx.size()); }
   uint32_t num_curves() const { return uint32_t(curve_ids.size()); }

@@ -61,6 +61,7 @@ enum Stat {
   kStatClosest = 0, kStatShadow, kStatSss, kStatNodes, kStatPrims,
   kStatNextSample,      // next camera sample id to hand out
   kStatRetired,         // camera samples accumulated into the frame so far
+  kStatSssSkipped,      // walk segments answered by the clearance grid
   kStatCount
 };
 
@@ -208,7 +209,7 @@ struct FrameParams {
   float4* rgba;               // frame accumulator (sums); alpha counts the samples (render.cc:175-183)
 };
 
-__device__ __forceinline__ void StartCameraPath(const WaveState& w, const FrameParams& f, uint32_t p,
+__device__ __forceinline__ RayT StartCameraPath(const WaveState& w, const FrameParams& f, uint32_t p,
                                                 unsigned long long id) {
   const uint32_t s_local = uint32_t(id / f.npix), pixel = uint32_t(id - (unsigned long long)s_local * f.npix);
   const uint32_t x = pixel % f.cam.width, y = pixel / f.cam.width;
@@ -226,11 +227,25 @@ __device__ __forceinline__ void StartCameraPath(const WaveState& w, const FrameP
   StSlot(w, p, kRad, make_float4(0.f, 0.f, 0.f, __uint_as_float(0u)));
   StSlot(w, p, kRng, PackRng(rng));
   StSlot(w, p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
+  RayT ray;
+  ray.o = vec3(f.cam.eye[0], f.cam.eye[1], f.cam.eye[2]); ray.tmin = 0.0f;
+  ray.d = vec3(dx, dy, dz); ray.tmax = kInf;
+  return ray;
+}
+
+// render.cc:175-183 for one finished path: rgba += (L, 1) as ONE 128-bit vector reduction (red.global.add.v4.f32,
+// sm_90+); count is the alpha sum, written out by FinishFrameKernel.  Returns whether the slot held a path.
+__device__ __forceinline__ bool RetirePath(const WaveState& w, const FrameParams& f, uint32_t p) {
+  const uint32_t pixel = __float_as_uint(LdSlot(w, p, kPix).x);
+  if (pixel == kNoPixel) return false;
+  const float4 r = LdSlot(w, p, kRad);
+  atomicAdd(&f.rgba[pixel], make_float4(r.x, r.y, r.z, 1.0f));
+  return true;
 }
 
 // Retire the slots of q_done[cur] (render.cc:175-183: rgba += (L, 1); count is the alpha sum, written out by
 // FinishFrameKernel) and restart them on the next camera samples.  Several samples of one pixel can retire in the
-// same iteration, hence the atomic: ONE 128-bit vector reduction per path (red.global.add.v4.f32, sm_90+).
+// same iteration, hence the atomic.  Only used when regeneration is not fused into the closest-hit kernel.
 __global__ void __launch_bounds__(256) RegenerateKernel(WaveState w, FrameParams f, uint32_t cur_parity) {
   const uint32_t n = w.counters[kNumDone0 + cur_parity];
   unsigned long long retired = 0;
@@ -241,12 +256,7 @@ __global__ void __launch_bounds__(256) RegenerateKernel(WaveState w, FrameParams
     uint32_t p = 0;
     if (valid) {
       p = w.q_done[cur_parity][i];
-      const uint32_t pixel = __float_as_uint(LdSlot(w, p, kPix).x);
-      if (pixel != kNoPixel) {
-        const float4 r = LdSlot(w, p, kRad);
-        atomicAdd(&f.rgba[pixel], make_float4(r.x, r.y, r.z, 1.0f));
-        ++retired;
-      }
+      if (RetirePath(w, f, p)) ++retired;
     }
     // hand out new sample ids, one atomic per warp
     const unsigned mask = __ballot_sync(0xffffffffu, valid);
@@ -305,14 +315,20 @@ __global__ void InitPathsFromRaysKernel(WaveState w, const float4* rays, const u
 struct ClosestClient {
   const SceneView& s;
   const WaveState& w;
+  const FrameParams& frame;      // used when `fused`: retire + regenerate the slots of q_done[cur] in here
+  const bool fused;
   const uint32_t* __restrict__ queue;
-  uint32_t n, next_parity;
+  const uint32_t* __restrict__ done;
+  uint32_t n_active, n, next_parity;
   uint32_t p = 0;
   bool has_result = false;
-  unsigned long long rays = 0;
+  unsigned long long rays = 0, retired = 0;
 
-  __device__ __forceinline__ ClosestClient(const SceneView& s_, const WaveState& w_, uint32_t cur_parity)
-      : s(s_), w(w_), queue(w_.q_active[cur_parity]), n(w_.counters[kNumActive0 + cur_parity]),
+  __device__ __forceinline__ ClosestClient(const SceneView& s_, const WaveState& w_, uint32_t cur_parity,
+                                           const FrameParams& frame_, bool fused_)
+      : s(s_), w(w_), frame(frame_), fused(fused_), queue(w_.q_active[cur_parity]), done(w_.q_done[cur_parity]),
+        n_active(w_.counters[kNumActive0 + cur_parity]),
+        n(w_.counters[kNumActive0 + cur_parity] + (fused_ ? w_.counters[kNumDone0 + cur_parity] : 0u)),
         next_parity(cur_parity ^ 1u) {}
   __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
@@ -341,28 +357,63 @@ struct ClosestClient {
     if (!exhausted) {
       const bool need = !t.active;
       const uint32_t slot = WarpAppend(&w.counters[kFetchTrace], need);
-      if (need) {
-        if (slot < n) {
-          p = queue[slot];
-          TravBegin(s, LoadRay(w, p), t);
-          has_result = true;
-          ++rays;
-        } else {
-          dry = true;
+      // work items: first the slots that shading sent on, then (frame mode) last iteration's finished slots, which
+      // are retired and restarted on the next camera samples right here — the camera ray never makes a round trip
+      // through memory before its first traversal, and no separate retire/regenerate launch is needed
+      const bool regen = need && slot >= n_active && slot < n;
+      RayT ray;
+      bool have_ray = false;
+      if (need && slot < n_active) {
+        p = queue[slot];
+        ray = LoadRay(w, p);
+        have_ray = true;
+      }
+      if (fused) {   // warp-uniform
+        uint32_t rp = 0;
+        if (regen) {
+          rp = done[slot - n_active];
+          if (RetirePath(w, frame, rp)) ++retired;
         }
+        const unsigned mask = __ballot_sync(0xffffffffu, regen);
+        if (mask) {
+          const int lane = threadIdx.x & 31;
+          const int leader = __ffs(mask) - 1;
+          unsigned long long base = 0;
+          if (lane == leader) base = atomicAdd(&w.stats[kStatNextSample], (unsigned long long)__popc(mask));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          const unsigned long long id = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+          if (regen) {
+            if (id < frame.total_samples) {
+              p = rp;
+              ray = StartCameraPath(w, frame, p, id);
+              have_ray = true;
+            } else {
+              StSlot(w, rp, kPix, make_float4(__uint_as_float(kNoPixel), 0.f, 0.f, 0.f));
+            }
+          }
+        }
+      }
+      if (have_ray) {
+        TravBegin(s, ray, t);
+        has_result = true;
+        ++rays;
+      } else if (need && slot >= n) {
+        dry = true;
       }
     }
     return dry;
   }
   __device__ __forceinline__ void End(const Trav&) {
     if (rays) atomicAdd(&w.stats[kStatClosest], rays);
+    if (retired) atomicAdd(&w.stats[kStatRetired], retired);
   }
 };
 
 template <bool HAS_CURVES>
 __global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState w, uint32_t cur_parity,
-                                                          uint32_t refill_min_idle, uint32_t prim_min_lanes) {
-  ClosestClient client(s, w, cur_parity);
+                                                          uint32_t refill_min_idle, uint32_t prim_min_lanes,
+                                                          FrameParams frame, uint32_t fuse_regenerate) {
+  ClosestClient client(s, w, cur_parity, frame, fuse_regenerate != 0u);
   TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle, prim_min_lanes);
 }
 
@@ -555,9 +606,10 @@ struct SssClient {
   uint32_t cur_parity, next_parity, n_resume, n, max_bounces;
   uint32_t p = 0, budget = 0, pixel = 0;
   bool has_walk = false;
+  bool skipped_seg = false;   // the current segment was answered by the clearance grid, not traced
   Pcg32 rng;
   SssWalkState walk;    // walk.ray is rebuilt from the traversal state after every segment
-  unsigned long long rays = 0;
+  unsigned long long rays = 0, skipped = 0;
 
   __device__ __forceinline__ SssClient(const SceneView& s_, const WaveState& w_, uint32_t cur, uint32_t max_b)
       : s(s_), w(w_), cur_parity(cur), next_parity(cur ^ 1u), n_resume(w_.counters[kNumWalk0 + cur]),
@@ -567,6 +619,11 @@ struct SssClient {
   __device__ __forceinline__ void StartSegment(Trav& t) {
     SssPrepareSegment(&rng, &walk);
     TravBegin(s, walk.ray, t);
+    // Segments that end far from any surface: the clearance grid answers those ("no hit") without a traversal; the
+    // lane then waits for the next converged section like any lane whose query has finished.  (Finishing chains of
+    // such segments inline was measured and is slower: the converged section serialises on the longest chain.)
+    skipped_seg = SegmentIsClear(s, walk.ray.o, walk.ray.tmax * 1.001f);
+    if (skipped_seg) t.active = false;
   }
 
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
@@ -577,7 +634,7 @@ struct SssClient {
       walk.ray.o = t.O; walk.ray.d = t.D; walk.ray.tmin = t.tmin;   // tmax untouched: the scatter distance
       const bool is_hit = t.hit.prim != kInvalid;
       const SssStep st = SssFinishSegment(is_hit, t.hit.t, &rng, &walk);
-      ++rays;
+      if (skipped_seg) ++skipped; else ++rays;
       --budget;
       if (st == kSssHit) {
         // exit record for sss_exit: the segment ray, its hit and the walk throughput
@@ -631,6 +688,7 @@ struct SssClient {
   }
   __device__ __forceinline__ void End(const Trav&) {
     if (rays) atomicAdd(&w.stats[kStatSss], rays);
+    if (skipped) atomicAdd(&w.stats[kStatSssSkipped], skipped);
   }
 };
 

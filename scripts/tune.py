@@ -12,6 +12,8 @@ for a in sys.argv[4:]:
     k, v = a.split("=")
     if k == "FILES":
         files = v.split(","); continue
+    if k == "SCENE" and v == "c3":
+        files = [scenes.light_stage(), scenes.cyhair(50000, 21, center=(-2.5, 3.5, 0.0), radius=1.2, length=2.5, thickness=0.008)]; continue
     keys.append(k); vals.append(v.split(","))
 for combo in itertools.product(*vals):
     for k, v in zip(keys, combo):
@@ -24,6 +26,6 @@ for combo in itertools.product(*vals):
         t = time.time(); ctx.render(w, h, spp); best = min(best, time.time() - t)
     ctx.set_profiling(True); ctx.render(w, h, spp); st = ctx.stats(); ctx.set_profiling(False)
     rays = st["closest_rays"] + st["shadow_rays"] + st["sss_rays"]
-    print(" ".join("%s=%s" % kv for kv in zip(keys, combo)), "| %.4f s %.1f Msamples/s %.1f Mrays/s | closest %.1f any %.1f shade %.1f sss %.1f regen %.1f ms | launches %d | rays c %.1fM s %.1fM w %.1fM" % (
-        best, w * h * spp / best * 1e-6, rays / best * 1e-6, st["trace_closest_ms"], st["trace_any_ms"], st["shade_ms"], st["sss_ms"], st["regen_ms"], st["kernel_launches"], st["closest_rays"] * 1e-6, st["shadow_rays"] * 1e-6, st["sss_rays"] * 1e-6), flush=True)
+    print(" ".join("%s=%s" % kv for kv in zip(keys, combo)), "| %.4f s %.1f Msamples/s %.1f Mrays/s | closest %.1f any %.1f shade %.1f sss %.1f regen %.1f ms | launches %d | rays c %.1fM s %.1fM w %.1fM skipped %.1fM" % (
+        best, w * h * spp / best * 1e-6, rays / best * 1e-6, st["trace_closest_ms"], st["trace_any_ms"], st["shade_ms"], st["sss_ms"], st["regen_ms"], st["kernel_launches"], st["closest_rays"] * 1e-6, st["shadow_rays"] * 1e-6, st["sss_rays"] * 1e-6, st["sss_skipped"] * 1e-6), flush=True)
     S.close()
