@@ -28,6 +28,7 @@ struct SceneView {
   const float4* curve_data;    // leaf-ordered, 4 x float4 (xyz, radius) per cubic Bezier segment
   const uint32_t* curve_prim;  // leaf order -> curve primitive id
   uint32_t num_tris, num_curves;
+  uint32_t bias_magic;         // kBiasMagic (traverse.cuh), as a run-time value on purpose
   // ---- per-primitive shading tables (indexed by primitive id = order given to pbrgpu_set_*)
   const uint4* tri_ids;        // instance_id, geom_id, prim_id inside the shape, material_id
   const uint4* tri_nidx;       // 3 normal indices (0xFFFFFFFF = none), index into emissive[] or 0xFFFFFFFF
@@ -39,6 +40,7 @@ struct SceneView {
   const uint4* curve_ids;      // instance_id, geom_id, segment id inside the shape, material_id
   const DeviceMaterial* materials;
   uint32_t num_materials;
+  uint32_t num_hair_materials; // materials of type 1: scenes without any route every hit to the Principled queue unseen
   // ---- lights (light-manager.h:172-193 flattened)
   const float4* emissive;      // per emissive triangle: emission rgb, pdf = P(light) P(prim) / area   (ImplicitAreaLight)
   const float* light_cdf;      // cumulative_probability_ over lights

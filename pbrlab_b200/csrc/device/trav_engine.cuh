@@ -73,7 +73,7 @@ __device__ __forceinline__ void TravNodeStep(const SceneView& s, Trav& t, uint2*
   if (STATS) t.n_nodes++;
   const bool neg_x = !(t.oct_inv4 & 0x04u), neg_y = !(t.oct_inv4 & 0x02u), neg_z = !(t.oct_inv4 & 0x01u);
   const uint32_t hitmask = NodeIntersect(t.ood, t.inv_d, t.oct_inv4, neg_x, neg_y, neg_z, t.tmin, t.tfar, n0, n1,
-                                         n2, n3, n4);
+                                         n2, n3, n4, s.bias_magic);
   t.group.x = f2u(n1.x);
   t.group.y = (hitmask & 0xff000000u) | extract_byte(f2u(n0.w), 3);
   t.pgroup.x = f2u(n1.y);

@@ -208,10 +208,15 @@ PBR_HD uint32_t popc(uint32_t x) {
 
 // byte j of x as the float 32768 + byte: the byte goes to mantissa bits 8..15 of 2^15 (one PRMT on the device instead
 // of an int->float conversion on the quarter-rate XU pipe, which ncu showed as the busiest pipe of the traversal)
-PBR_HD float byte_as_biased_float(uint32_t x, uint32_t j) {
+// `magic` is 0x47000000 and MUST reach the kernel as a run-time value (SceneView::bias_magic): PRMT takes one
+// immediate, and when both the constant and the selector are known at compile time ptxas keeps the constant as the
+// immediate and re-materialises the selector in front of every one of the 48 PRMTs of a node test (UMOV + IMAD.U32,
+// seen in the SASS: 17 % of the node step).  With the constant in a register the selector is the immediate.
+constexpr uint32_t kBiasMagic = 0x47000000u;
+PBR_HD float byte_as_biased_float(uint32_t x, uint32_t j, uint32_t magic) {
 #if defined(__CUDA_ARCH__)
   // result bytes: b0 = 0x00 (magic.b0), b1 = x.bj, b2 = 0x00 (magic.b2), b3 = 0x47 (magic.b3)
-  return __uint_as_float(__byte_perm(x, 0x47000000u, 0x7604u | (j << 4)));
+  return __uint_as_float(__byte_perm(x, magic, 0x7604u | (j << 4)));
 #else
   return u2f(0x47000000u | (((x >> (8u * j)) & 0xffu) << 8));
 #endif
@@ -224,7 +229,8 @@ PBR_HD float byte_as_biased_float(uint32_t x, uint32_t j) {
 // by the same plus 4 ulps: the test stays conservative, which is all a box test has to be.
 PBR_HD uint32_t NodeIntersect(const vec3& o_over_d, const vec3& inv_d, uint32_t oct_inv4, bool neg_x, bool neg_y,
                               bool neg_z, float tmin, float tmax, const float4& n0, const float4& n1,
-                              const float4& n2, const float4& n3, const float4& n4) {
+                              const float4& n2, const float4& n3, const float4& n4,
+                              uint32_t magic = kBiasMagic) {
   const uint32_t ew = f2u(n0.w);
   const float sx = u2f(extract_byte(ew, 0) << 23) * inv_d.x;
   const float sy = u2f(extract_byte(ew, 1) << 23) * inv_d.y;
@@ -256,12 +262,12 @@ PBR_HD uint32_t NodeIntersect(const vec3& o_over_d, const vec3& inv_d, uint32_t 
 #pragma unroll
 #endif
     for (uint32_t j = 0; j < 4; ++j) {
-      const float tlx = pbr_fma(byte_as_biased_float(x_min, j), sx, olx);
-      const float tly = pbr_fma(byte_as_biased_float(y_min, j), sy, oly);
-      const float tlz = pbr_fma(byte_as_biased_float(z_min, j), sz, olz);
-      const float thx = pbr_fma(byte_as_biased_float(x_max, j), sx, ohx);
-      const float thy = pbr_fma(byte_as_biased_float(y_max, j), sy, ohy);
-      const float thz = pbr_fma(byte_as_biased_float(z_max, j), sz, ohz);
+      const float tlx = pbr_fma(byte_as_biased_float(x_min, j, magic), sx, olx);
+      const float tly = pbr_fma(byte_as_biased_float(y_min, j, magic), sy, oly);
+      const float tlz = pbr_fma(byte_as_biased_float(z_min, j, magic), sz, olz);
+      const float thx = pbr_fma(byte_as_biased_float(x_max, j, magic), sx, ohx);
+      const float thy = pbr_fma(byte_as_biased_float(y_max, j, magic), sy, ohy);
+      const float thz = pbr_fma(byte_as_biased_float(z_max, j, magic), sz, ohz);
       const float tn = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
       const float tf = fminf(fminf(thx, thy), fminf(thz, tmax_s));
       if (tn <= tf) {

@@ -121,10 +121,9 @@ struct pbrgpu_ctx {
   uint32_t tune_refill_sss = 24;   // same for the random-walk kernel (its converged section is the bounce itself)
   uint32_t tune_prim_lanes = 1, tune_prim_lanes_sss = 1;   // lanes with pending primitives that trigger a primitive phase
   int tune_l2_persist = 0;         // persisting-L2 window over the traversal data
-  int tune_regen_blocks = 1;
   int tune_sss_skip = 1;           // clearance grid: random-walk segments that provably hit nothing are not traced
-  int tune_fuse_regen = 1;         // retire + regenerate inside the closest-hit kernel instead of a separate launch
   int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
+  int tune_pool_mi = 8;            // path slots kept in flight, in Mi (x 256 B of slot + walk lines)
   int tune_trace_blocks = 8, tune_shade_blocks = 1, tune_walk_blocks = 6;   // resident 128-thread blocks per SM
 };
 
@@ -142,6 +141,12 @@ constexpr uint32_t kSssBouncesBusy = 16;
 constexpr uint32_t kSssBouncesDrain = 1024;
 constexpr uint32_t kDrainThreshold = 1u << 16;   // slots in flight below which the pool counts as draining
 int PersistentGrid(const Device& d, int blocks_per_sm) { return d.sm_count * blocks_per_sm; }
+
+uint32_t CountHairMaterials(const pbrhost::HostScene& h) {
+  uint32_t n = 0;
+  for (const auto& m : h.materials) n += (m.type == 1u) ? 1u : 0u;
+  return n;
+}
 
 int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   const pbrhost::HostScene& h = ctx->host;
@@ -203,9 +208,11 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   v.tri_nodes = g_tn; v.tri_data = g_td;
   v.curve_nodes = g_cn; v.curve_data = g_cd; v.curve_prim = d.curve_prim.ptr;
   v.num_tris = h.num_tris(); v.num_curves = h.num_curves();
+  v.bias_magic = pbr::kBiasMagic;
   v.tri_ids = d.tri_ids.ptr; v.tri_nidx = d.tri_nidx.ptr; v.tri_vidx = d.tri_vidx.ptr; v.tri_tidx = d.tri_tidx.ptr;
   v.verts = d.verts.ptr; v.normals = d.normals.ptr; v.texcoords = d.texcoords.ptr; v.curve_ids = d.curve_ids.ptr;
   v.materials = d.materials.ptr; v.num_materials = uint32_t(h.materials.size());
+  v.num_hair_materials = CountHairMaterials(h);
   v.emissive = d.emissive.ptr; v.light_cdf = d.light_cdf.ptr; v.lights = d.lights.ptr;
   v.num_lights = uint32_t(h.lights.size());
   v.lprim_cdf = d.lprim_cdf.ptr; v.lprim_info = d.lprim_info.ptr; v.lprim_tri = d.lprim_tri.ptr;
@@ -278,17 +285,13 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
         (max_iterations == 1u) ? 0x7fffffffu : (in_flight < kDrainThreshold ? kSssBouncesDrain : kSssBouncesBusy);
     const bool prof = ctx->profile;
     auto mark = [&](int k) { if (prof) cudaEventRecord(d.kev[k], st); };
-    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, parity);
+    const uint32_t regen = frame ? 1u : 0u;
+    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, regen);
     tm->launches += 1;
     mark(0);
-    const bool fuse = frame && ctx->tune_fuse_regen;
-    if (frame && have_done && !fuse) {
-      pbr::RegenerateKernel<<<PersistentGrid(d, ctx->tune_regen_blocks), 256, 0, st>>>(w, *frame, parity);
-      tm->launches += 1;
-    }
     mark(1);
-    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, fuse ? 1u : 0u);
-    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, fuse ? 1u : 0u);
+    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, regen);
+    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, regen);
     mark(2);
     pbr::ShadeSurfaceKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
     if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
@@ -339,7 +342,7 @@ int FetchStats(pbrgpu_ctx* ctx, Device& d) {
 // number of path slots kept in flight: enough to fill the GPU many times over (each iteration costs one host
 // round-trip), small enough that the SoA state (~300 B/slot) streams through HBM quickly
 uint32_t ChoosePoolSize(const pbrgpu_ctx* ctx, uint64_t npix, uint64_t total_samples) {
-  uint64_t n = ctx->wave_spp ? uint64_t(ctx->wave_spp) * npix : (8ull << 20);
+  uint64_t n = ctx->wave_spp ? uint64_t(ctx->wave_spp) * npix : (uint64_t(ctx->tune_pool_mi) << 20);
   n = std::min<uint64_t>(n, total_samples);
   n = std::min<uint64_t>(n, 64ull << 20);
   return uint32_t(std::max<uint64_t>(n, 1));
@@ -483,9 +486,8 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_trace_blocks = std::max(1, env_int("PBRGPU_TRACE_BLOCKS", ctx->tune_trace_blocks));
   ctx->tune_shade_blocks = std::max(1, env_int("PBRGPU_SHADE_BLOCKS", ctx->tune_shade_blocks));
   ctx->tune_walk_blocks = std::max(1, env_int("PBRGPU_WALK_BLOCKS", ctx->tune_walk_blocks));
-  ctx->tune_regen_blocks = std::max(1, env_int("PBRGPU_REGEN_BLOCKS", ctx->tune_regen_blocks));
+  ctx->tune_pool_mi = std::min(64, std::max(1, env_int("PBRGPU_POOL_MI", ctx->tune_pool_mi)));
   ctx->tune_l2_persist = env_int("PBRGPU_L2_PERSIST", ctx->tune_l2_persist);
-  ctx->tune_fuse_regen = env_int("PBRGPU_FUSE_REGEN", ctx->tune_fuse_regen);
   ctx->tune_sss_skip = env_int("PBRGPU_SSS_SKIP", ctx->tune_sss_skip);
   ctx->tune_shade_threads = std::min(pbr::kShadeBlock, std::max(32, env_int("PBRGPU_SHADE_THREADS", ctx->tune_shade_threads) & ~31));
   for (int id : ids) {
@@ -576,6 +578,7 @@ int pbrgpu_set_materials(pbrgpu_ctx* ctx, const pbrgpu_material* materials, uint
       CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
       d.view.materials = d.materials.ptr;
       d.view.num_materials = n;
+      d.view.num_hair_materials = CountHairMaterials(ctx->host);
     }
   }
   return PBRGPU_OK;
@@ -875,7 +878,7 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
     // the hook reports face direction and t of the first hit: run the closest-hit stage alone first
     DevBuf<float> dface;
     CUDA_TRY(ctx, dface.Alloc(2 * n));
-    pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters, 0u);
+    pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters, d.wave.stats, 0u, 0u);
     if (d.view.num_curves)
       pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), 0u);
     else

@@ -60,6 +60,7 @@ enum Counter {
 enum Stat {
   kStatClosest = 0, kStatShadow, kStatSss, kStatNodes, kStatPrims,
   kStatNextSample,      // next camera sample id to hand out
+  kStatSampleBase,      // first camera sample id of the current iteration (set by BeginIterationKernel)
   kStatRetired,         // camera samples accumulated into the frame so far
   kStatSssSkipped,      // walk segments answered by the clearance grid
   kStatCount
@@ -125,6 +126,43 @@ __device__ __forceinline__ uint32_t WarpFetch(uint32_t* fetch_counter) {
   return base + uint32_t(lane);
 }
 
+// Four queue reservations with ONE atomic instruction: lanes 0..3 each reserve the range of one queue (different
+// addresses, so the L2 handles them in parallel) instead of four dependent atomic round trips — waiting for atomic
+// results was 18 % of the closest-hit kernel's stall samples (profiles/r1e_ncu.md).  Issue early, resolve late:
+// whatever is issued in between overlaps the round trip.
+struct Append4 {
+  unsigned m0, m1, m2, m3;
+  uint32_t base;   // lane k < 4: first index reserved in queue k
+};
+__device__ __forceinline__ Append4 Append4Issue(uint32_t* c0, uint32_t* c1, uint32_t* c2, uint32_t* c3, bool p0,
+                                                bool p1, bool p2, bool p3) {
+  Append4 a;
+  a.m0 = __ballot_sync(0xffffffffu, p0);
+  a.m1 = __ballot_sync(0xffffffffu, p1);
+  a.m2 = __ballot_sync(0xffffffffu, p2);
+  a.m3 = __ballot_sync(0xffffffffu, p3);
+  a.base = 0;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cnt = uint32_t(__popc(lane == 0 ? a.m0 : (lane == 1 ? a.m1 : (lane == 2 ? a.m2 : a.m3))));
+  uint32_t* ctr = lane == 0 ? c0 : (lane == 1 ? c1 : (lane == 2 ? c2 : c3));
+  if (lane < 4 && cnt) a.base = atomicAdd(ctr, cnt);
+  return a;
+}
+__device__ __forceinline__ void Append4Resolve(const Append4& a, uint32_t* i0, uint32_t* i1, uint32_t* i2,
+                                               uint32_t* i3) {
+  const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+  *i0 = __shfl_sync(0xffffffffu, a.base, 0) + uint32_t(__popc(a.m0 & lt));
+  *i1 = __shfl_sync(0xffffffffu, a.base, 1) + uint32_t(__popc(a.m1 & lt));
+  *i2 = __shfl_sync(0xffffffffu, a.base, 2) + uint32_t(__popc(a.m2 & lt));
+  *i3 = __shfl_sync(0xffffffffu, a.base, 3) + uint32_t(__popc(a.m3 & lt));
+}
+
+// one 64-bit atomic per warp for a per-lane tally (kernel epilogues: 32 same-address atomics per warp otherwise)
+__device__ __forceinline__ void WarpTally(unsigned long long* counter, uint32_t v) {
+  const uint32_t sum = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && sum) atomicAdd(counter, (unsigned long long)sum);
+}
+
 // A whole block pulls the next blockDim.x queue slots and re-converges: the shading kernels are long straight-line
 // code (70-120 KB of SASS, every instruction executed once per path), so warps that drift apart each stream the
 // code from L2 on their own — measured 67 % of warp time waiting on instruction fetch.  Warps that start every batch
@@ -184,8 +222,16 @@ __device__ __forceinline__ void RouteSlot(const WaveState& w, uint32_t next_pari
 
 // ------------------------------------------------------------------------------------------------ iteration set-up
 // zeroes every per-iteration counter; the three ping-pong lists keep the half that this iteration consumes
-__global__ void BeginIterationKernel(uint32_t* counters, uint32_t cur_parity) {
+// In frame mode it also hands this iteration's camera sample ids to the slots of q_done[cur]: the closest-hit kernel
+// gives work item (n_active + k) the sample id (base + k), so regeneration needs no atomic of its own.
+__global__ void BeginIterationKernel(uint32_t* counters, unsigned long long* stats, uint32_t cur_parity,
+                                     uint32_t frame_mode) {
   const uint32_t i = threadIdx.x;
+  if (i == 0 && frame_mode) {
+    const unsigned long long base = stats[kStatNextSample];
+    stats[kStatSampleBase] = base;
+    stats[kStatNextSample] = base + counters[kNumDone0 + cur_parity];
+  }
   if (i >= kCounterCount) return;
   const uint32_t keep0 = kNumActive0 + cur_parity, keep1 = kNumWalk0 + cur_parity, keep2 = kNumDone0 + cur_parity;
   if (i == keep0 || i == keep1 || i == keep2) return;
@@ -233,50 +279,6 @@ __device__ __forceinline__ RayT StartCameraPath(const WaveState& w, const FrameP
   return ray;
 }
 
-// render.cc:175-183 for one finished path: rgba += (L, 1) as ONE 128-bit vector reduction (red.global.add.v4.f32,
-// sm_90+); count is the alpha sum, written out by FinishFrameKernel.  Returns whether the slot held a path.
-__device__ __forceinline__ bool RetirePath(const WaveState& w, const FrameParams& f, uint32_t p) {
-  const uint32_t pixel = __float_as_uint(LdSlot(w, p, kPix).x);
-  if (pixel == kNoPixel) return false;
-  const float4 r = LdSlot(w, p, kRad);
-  atomicAdd(&f.rgba[pixel], make_float4(r.x, r.y, r.z, 1.0f));
-  return true;
-}
-
-// Retire the slots of q_done[cur] (render.cc:175-183: rgba += (L, 1); count is the alpha sum, written out by
-// FinishFrameKernel) and restart them on the next camera samples.  Several samples of one pixel can retire in the
-// same iteration, hence the atomic.  Only used when regeneration is not fused into the closest-hit kernel.
-__global__ void __launch_bounds__(256) RegenerateKernel(WaveState w, FrameParams f, uint32_t cur_parity) {
-  const uint32_t n = w.counters[kNumDone0 + cur_parity];
-  unsigned long long retired = 0;
-  for (;;) {
-    const uint32_t i = WarpFetch(&w.counters[kFetchRegen]);
-    if (__all_sync(0xffffffffu, i >= n)) break;
-    const bool valid = i < n;
-    uint32_t p = 0;
-    if (valid) {
-      p = w.q_done[cur_parity][i];
-      if (RetirePath(w, f, p)) ++retired;
-    }
-    // hand out new sample ids, one atomic per warp
-    const unsigned mask = __ballot_sync(0xffffffffu, valid);
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (mask) {
-      const int leader = __ffs(mask) - 1;
-      if (lane == leader) base = atomicAdd(&w.stats[kStatNextSample], (unsigned long long)__popc(mask));
-      base = __shfl_sync(0xffffffffu, base, leader);
-    }
-    const unsigned long long id = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
-    const bool start = valid && id < f.total_samples;
-    if (start) StartCameraPath(w, f, p, id);
-    else if (valid) StSlot(w, p, kPix, make_float4(__uint_as_float(kNoPixel), 0.f, 0.f, 0.f));
-    const uint32_t a = WarpAppend(&w.counters[kNumActive0 + cur_parity], start);
-    if (start) w.q_active[cur_parity][a] = p;
-  }
-  if (retired) atomicAdd(&w.stats[kStatRetired], retired);
-}
-
 // RenderLayer::count (render-layer.h:11-26) from the alpha sums: both are incremented together per sample
 __global__ void FinishFrameKernel(const float4* rgba, uint32_t* count, uint32_t npix) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,105 +317,117 @@ __global__ void InitPathsFromRaysKernel(WaveState w, const float4* rays, const u
 struct ClosestClient {
   const SceneView& s;
   const WaveState& w;
-  const FrameParams& frame;      // used when `fused`: retire + regenerate the slots of q_done[cur] in here
-  const bool fused;
+  const FrameParams& frame;      // frame mode: retire + regenerate the slots of q_done[cur] in here
+  const bool regen;
   const uint32_t* __restrict__ queue;
   const uint32_t* __restrict__ done;
   uint32_t n_active, n, next_parity;
+  unsigned long long sample_base;
   uint32_t p = 0;
   bool has_result = false;
-  unsigned long long rays = 0, retired = 0;
+  uint32_t rays = 0, retired = 0;
 
   __device__ __forceinline__ ClosestClient(const SceneView& s_, const WaveState& w_, uint32_t cur_parity,
-                                           const FrameParams& frame_, bool fused_)
-      : s(s_), w(w_), frame(frame_), fused(fused_), queue(w_.q_active[cur_parity]), done(w_.q_done[cur_parity]),
+                                           const FrameParams& frame_, bool regen_)
+      : s(s_), w(w_), frame(frame_), regen(regen_), queue(w_.q_active[cur_parity]), done(w_.q_done[cur_parity]),
         n_active(w_.counters[kNumActive0 + cur_parity]),
-        n(w_.counters[kNumActive0 + cur_parity] + (fused_ ? w_.counters[kNumDone0 + cur_parity] : 0u)),
-        next_parity(cur_parity ^ 1u) {}
+        n(w_.counters[kNumActive0 + cur_parity] + (regen_ ? w_.counters[kNumDone0 + cur_parity] : 0u)),
+        next_parity(cur_parity ^ 1u),
+        sample_base(regen_ ? w_.stats[kStatSampleBase] : 0ull) {}
   __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
+
+  // work item -> slot: first the slots that shading sent on, then (frame mode) last iteration's finished slots
+  __device__ __forceinline__ uint32_t SlotOf(uint32_t item) const {
+    return item < n_active ? queue[item] : done[item - n_active];
+  }
+
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
+    const bool finished = !t.active && has_result;
+    const bool need = !exhausted && !t.active;
+    // ---- (1) finished rays: miss -> retire, else the shading queue of the material kind
     int kind = -1;   // -1 nothing, 0 miss, 1 surface queue, 2 hair queue
-    if (!t.active && has_result) {
+    const HitT hit = t.hit;
+    const uint32_t done_p = p;
+    if (finished) {
       has_result = false;
-      const HitT hit = t.hit;
-      StSlot(w, p, kHit, make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim)));
-      StSlot(w, p, kHitPad, make_float4(0.f, 0.f, 0.f, 0.f));   // completes the sector: no read-modify-write
       kind = 0;
       if (hit.prim != kInvalid) {
-        uint32_t mat;
-        if (hit.prim & kCurveFlag) mat = s.curve_ids[s.curve_prim[hit.prim & ~kCurveFlag]].w;
-        else mat = s.tri_ids[__float_as_uint(s.tri_data[hit.prim * 3].w)].w;
-        kind = (mat < s.num_materials && s.materials[mat].type == 1u) ? 2 : 1;
+        kind = 1;
+        if (s.num_hair_materials) {   // scene-uniform: only scenes with a hair material pay for the look-ups
+          uint32_t mat;
+          if (hit.prim & kCurveFlag) mat = s.curve_ids[s.curve_prim[hit.prim & ~kCurveFlag]].w;
+          else mat = s.tri_ids[__float_as_uint(s.tri_data[hit.prim * 3].w)].w;
+          if (mat < s.num_materials && s.materials[mat].type == 1u) kind = 2;
+        }
       }
     }
-    const uint32_t done_p = p;
-    const uint32_t a = WarpAppend(&w.counters[kNumSurface], kind == 1);
-    if (kind == 1) w.q_surface[a] = done_p;
-    const uint32_t b = WarpAppend(&w.counters[kNumHair], kind == 2);
-    if (kind == 2) w.q_hair[b] = done_p;
-    const uint32_t c = WarpAppend(&w.counters[kNumDone0 + next_parity], kind == 0);
-    if (kind == 0) w.q_done[next_parity][c] = done_p;
-    bool dry = false;
-    if (!exhausted) {
-      const bool need = !t.active;
-      const uint32_t slot = WarpAppend(&w.counters[kFetchTrace], need);
-      // work items: first the slots that shading sent on, then (frame mode) last iteration's finished slots, which
-      // are retired and restarted on the next camera samples right here — the camera ray never makes a round trip
-      // through memory before its first traversal, and no separate retire/regenerate launch is needed
-      const bool regen = need && slot >= n_active && slot < n;
+    // ---- (2) the three output queues and the work fetch: one atomic instruction
+    const Append4 app = Append4Issue(&w.counters[kNumSurface], &w.counters[kNumHair],
+                                     &w.counters[kNumDone0 + next_parity], &w.counters[kFetchTrace], kind == 1,
+                                     kind == 2, kind == 0, need);
+    uint32_t i_surf, i_hair, i_done, item;
+    Append4Resolve(app, &i_surf, &i_hair, &i_done, &item);
+    // ---- (3) new work: the loads are issued here and consumed after the finished rays have been written out
+    const bool take = need && item < n_active;          // a path that continues
+    const bool renew = need && item >= n_active && item < n;   // a finished slot: retire it, start the next sample
+    float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = ro, rrad = ro;
+    uint32_t np = 0, rpix = kNoPixel;
+    if (take || renew) np = SlotOf(item);
+    if (take) {
+      ro = LdSlot(w, np, kRayO);
+      rd = LdSlot(w, np, kRayD);
+    } else if (renew) {
+      rpix = __float_as_uint(LdSlot(w, np, kPix).x);
+      rrad = LdSlot(w, np, kRad);
+    }
+    // ---- (4) write out the finished rays
+    if (kind >= 0) {
+      StSlot(w, done_p, kHit, make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim)));
+      StSlot(w, done_p, kHitPad, make_float4(0.f, 0.f, 0.f, 0.f));   // completes the sector: no read-modify-write
+      if (kind == 1) w.q_surface[i_surf] = done_p;
+      else if (kind == 2) w.q_hair[i_hair] = done_p;
+      else w.q_done[next_parity][i_done] = done_p;
+    }
+    // ---- (5) start the new rays
+    if (take) {
+      p = np;
       RayT ray;
-      bool have_ray = false;
-      if (need && slot < n_active) {
-        p = queue[slot];
-        ray = LoadRay(w, p);
-        have_ray = true;
+      ray.o = vec3(ro.x, ro.y, ro.z); ray.tmin = ro.w;
+      ray.d = vec3(rd.x, rd.y, rd.z); ray.tmax = rd.w;
+      TravBegin(s, ray, t);
+      has_result = true;
+      ++rays;
+    } else if (renew) {
+      // render.cc:175-183 for the path that ended in this slot, then the next camera sample in the same slot: the
+      // camera ray never makes a round trip through memory before its first traversal
+      if (rpix != kNoPixel) {
+        atomicAdd(&frame.rgba[rpix], make_float4(rrad.x, rrad.y, rrad.z, 1.0f));
+        ++retired;
       }
-      if (fused) {   // warp-uniform
-        uint32_t rp = 0;
-        if (regen) {
-          rp = done[slot - n_active];
-          if (RetirePath(w, frame, rp)) ++retired;
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, regen);
-        if (mask) {
-          const int lane = threadIdx.x & 31;
-          const int leader = __ffs(mask) - 1;
-          unsigned long long base = 0;
-          if (lane == leader) base = atomicAdd(&w.stats[kStatNextSample], (unsigned long long)__popc(mask));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          const unsigned long long id = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
-          if (regen) {
-            if (id < frame.total_samples) {
-              p = rp;
-              ray = StartCameraPath(w, frame, p, id);
-              have_ray = true;
-            } else {
-              StSlot(w, rp, kPix, make_float4(__uint_as_float(kNoPixel), 0.f, 0.f, 0.f));
-            }
-          }
-        }
-      }
-      if (have_ray) {
+      const unsigned long long id = sample_base + (item - n_active);
+      if (id < frame.total_samples) {
+        p = np;
+        const RayT ray = StartCameraPath(w, frame, p, id);
         TravBegin(s, ray, t);
         has_result = true;
         ++rays;
-      } else if (need && slot >= n) {
-        dry = true;
+      } else {
+        StSlot(w, np, kPix, make_float4(__uint_as_float(kNoPixel), 0.f, 0.f, 0.f));
       }
     }
-    return dry;
+    return need && item >= n;
   }
   __device__ __forceinline__ void End(const Trav&) {
-    if (rays) atomicAdd(&w.stats[kStatClosest], rays);
-    if (retired) atomicAdd(&w.stats[kStatRetired], retired);
+    WarpTally(&w.stats[kStatClosest], rays);
+    if (regen) WarpTally(&w.stats[kStatRetired], retired);
   }
 };
 
 template <bool HAS_CURVES>
 __global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState w, uint32_t cur_parity,
                                                           uint32_t refill_min_idle, uint32_t prim_min_lanes,
-                                                          FrameParams frame, uint32_t fuse_regenerate) {
-  ClosestClient client(s, w, cur_parity, frame, fuse_regenerate != 0u);
+                                                          FrameParams frame, uint32_t regenerate) {
+  ClosestClient client(s, w, cur_parity, frame, regenerate != 0u);
   TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle, prim_min_lanes);
 }
 
@@ -609,7 +623,7 @@ struct SssClient {
   bool skipped_seg = false;   // the current segment was answered by the clearance grid, not traced
   Pcg32 rng;
   SssWalkState walk;    // walk.ray is rebuilt from the traversal state after every segment
-  unsigned long long rays = 0, skipped = 0;
+  uint32_t rays = 0, skipped = 0;
 
   __device__ __forceinline__ SssClient(const SceneView& s_, const WaveState& w_, uint32_t cur, uint32_t max_b)
       : s(s_), w(w_), cur_parity(cur), next_parity(cur ^ 1u), n_resume(w_.counters[kNumWalk0 + cur]),
@@ -626,74 +640,75 @@ struct SssClient {
     if (skipped_seg) t.active = false;
   }
 
+  __device__ __forceinline__ uint32_t SlotOf(uint32_t item) const {
+    return item < n_resume ? w.q_walk[cur_parity][item] : w.q_sss[item - n_resume];
+  }
+
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     // ---- (1) walks whose segment query finished: scatter / exit / absorb
-    bool to_exit = false, to_done = false, to_park = false;
+    bool to_exit = false, to_done = false, to_park = false, go_on = false;
     const uint32_t routed_p = p;
+    const HitT hit = t.hit;
     if (!t.active && has_walk) {
       walk.ray.o = t.O; walk.ray.d = t.D; walk.ray.tmin = t.tmin;   // tmax untouched: the scatter distance
-      const bool is_hit = t.hit.prim != kInvalid;
-      const SssStep st = SssFinishSegment(is_hit, t.hit.t, &rng, &walk);
+      const bool is_hit = hit.prim != kInvalid;
+      const SssStep st = SssFinishSegment(is_hit, hit.t, &rng, &walk);
       if (skipped_seg) ++skipped; else ++rays;
       --budget;
-      if (st == kSssHit) {
-        // exit record for sss_exit: the segment ray, its hit and the walk throughput
-        StWalk(w, p, kWalkA, make_float4(t.hit.t, t.hit.u, t.hit.v, __uint_as_float(t.hit.prim)));
-        StWalk(w, p, kWalkB, make_float4(walk.throughput.x, walk.throughput.y, walk.throughput.z, 0.f));
-        StWalk(w, p, kWalkC, make_float4(walk.ray.o.x, walk.ray.o.y, walk.ray.o.z, walk.ray.tmin));
-        StWalk(w, p, kWalkD, make_float4(walk.ray.d.x, walk.ray.d.y, walk.ray.d.z, walk.ray.tmax));
-        StSlot(w, p, kRng, PackRng(rng));
-        StSlot(w, p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
-        to_exit = true;
-        has_walk = false;
-      } else if (st == kSssAbsorbed) {
-        to_done = true;   // throughput 0: the path ends with the radiance it already holds
-        has_walk = false;
-      } else if (budget == 0u) {
-        ParkWalk(w, p, walk);
-        StSlot(w, p, kRng, PackRng(rng));
-        StSlot(w, p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
-        to_park = true;
-        has_walk = false;
-      } else {
-        StartSegment(t);
-      }
+      if (st == kSssHit) to_exit = true;
+      else if (st == kSssAbsorbed) to_done = true;   // throughput 0: the path ends with the radiance it already holds
+      else if (budget == 0u) to_park = true;
+      else go_on = true;
+      has_walk = go_on;
     }
-    const uint32_t e = WarpAppend(&w.counters[kNumExit], to_exit);
-    if (to_exit) w.q_exit[e] = routed_p;
-    RouteSlot(w, next_parity, routed_p, false, to_done);
-    const uint32_t c = WarpAppend(&w.counters[kNumWalk0 + next_parity], to_park);
-    if (to_park) w.q_walk[next_parity][c] = routed_p;
-
-    // ---- (2) lanes without a walk take the next one: parked walks first, then this iteration's new ones
-    bool dry = false;
-    if (!exhausted) {
-      const bool need = !t.active && !has_walk;
-      const uint32_t slot = WarpAppend(&w.counters[kFetchSss], need);
-      if (need) {
-        if (slot >= n) {
-          dry = true;
-        } else {
-          p = (slot < n_resume) ? w.q_walk[cur_parity][slot] : w.q_sss[slot - n_resume];
-          rng = LoadRng(w, p);
-          pixel = __float_as_uint(LdSlot(w, p, kPix).x);
-          budget = max_bounces;
-          ResumeWalk(w, p, &walk);
-          has_walk = true;
-          StartSegment(t);
-        }
-      }
+    // ---- (2) the three output queues and the work fetch (lanes without a walk): one atomic instruction
+    const bool need = !exhausted && !t.active && !has_walk;
+    const Append4 app = Append4Issue(&w.counters[kNumExit], &w.counters[kNumDone0 + next_parity],
+                                     &w.counters[kNumWalk0 + next_parity], &w.counters[kFetchSss], to_exit, to_done,
+                                     to_park, need);
+    uint32_t i_exit, i_done, i_park, item;
+    Append4Resolve(app, &i_exit, &i_done, &i_park, &item);
+    // ---- (3) write out the walks that stopped
+    if (to_exit) {
+      // exit record for sss_exit: the segment ray, its hit and the walk throughput
+      StWalk(w, routed_p, kWalkA, make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim)));
+      StWalk(w, routed_p, kWalkB, make_float4(walk.throughput.x, walk.throughput.y, walk.throughput.z, 0.f));
+      StWalk(w, routed_p, kWalkC, make_float4(walk.ray.o.x, walk.ray.o.y, walk.ray.o.z, walk.ray.tmin));
+      StWalk(w, routed_p, kWalkD, make_float4(walk.ray.d.x, walk.ray.d.y, walk.ray.d.z, walk.ray.tmax));
+      w.q_exit[i_exit] = routed_p;
+    } else if (to_park) {
+      ParkWalk(w, routed_p, walk);
+      w.q_walk[next_parity][i_park] = routed_p;
+    } else if (to_done) {
+      w.q_done[next_parity][i_done] = routed_p;
     }
-    return dry;
+    if (to_exit || to_park) {
+      StSlot(w, routed_p, kRng, PackRng(rng));
+      StSlot(w, routed_p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
+    }
+    // ---- (4) new walks: parked ones first, then this iteration's new ones (loaded straight into the walk registers
+    // that (3) has just finished with)
+    const bool take = need && item < n;
+    if (take) {
+      p = SlotOf(item);
+      rng = LoadRng(w, p);
+      pixel = __float_as_uint(LdSlot(w, p, kPix).x);
+      budget = max_bounces;
+      ResumeWalk(w, p, &walk);
+      has_walk = true;
+    }
+    // ---- (5) next segment: of the walk that goes on, or of the one just taken
+    if (take || go_on) StartSegment(t);
+    return need && item >= n;
   }
   __device__ __forceinline__ void End(const Trav&) {
-    if (rays) atomicAdd(&w.stats[kStatSss], rays);
-    if (skipped) atomicAdd(&w.stats[kStatSssSkipped], skipped);
+    WarpTally(&w.stats[kStatSss], rays);
+    WarpTally(&w.stats[kStatSssSkipped], skipped);
   }
 };
 
 template <bool HAS_CURVES>
-__global__ void __launch_bounds__(128) SssWalkKernel(SceneView s, WaveState w, uint32_t cur_parity,
+__global__ void __launch_bounds__(128, 5) SssWalkKernel(SceneView s, WaveState w, uint32_t cur_parity,
                                                      uint32_t max_bounces, uint32_t refill_min_idle,
                                                      uint32_t prim_min_lanes) {
   SssClient client(s, w, cur_parity, max_bounces);
@@ -750,13 +765,18 @@ struct ShadowClient {
   uint32_t n;
   float4 c;
   bool has_result = false;
-  unsigned long long rays = 0;
+  uint32_t rays = 0;
 
   __device__ __forceinline__ ShadowClient(const SceneView& s_, const WaveState& w_)
       : s(s_), w(w_), n(w_.counters[kNumShadow]) {}
   __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
-    if (!t.active && has_result) {
+    const unsigned lane = threadIdx.x & 31u;
+    const bool need = !exhausted && !t.active;
+    const unsigned m_need = __ballot_sync(0xffffffffu, need);
+    uint32_t fetch_base = 0;
+    if (lane == 0u && m_need) fetch_base = atomicAdd(&w.counters[kFetchShadow], uint32_t(__popc(m_need)));
+    if (!t.active && has_result) {   // overlaps the fetch round trip
       has_result = false;
       if (t.hit.prim == kInvalid) {
         float* dst = reinterpret_cast<float*>(&w.slot[size_t(__float_as_uint(c.w)) * kSlotStride + kRad]);
@@ -765,30 +785,21 @@ struct ShadowClient {
         atomicAdd(dst + 2, c.z);
       }
     }
-    bool dry = false;
-    if (!exhausted) {
-      const bool need = !t.active;
-      const uint32_t slot = WarpAppend(&w.counters[kFetchShadow], need);
-      if (need) {
-        if (slot < n) {
-          const float4 o = __ldcs(&w.sh_o[slot]), d = __ldcs(&w.sh_d[slot]);
-          c = __ldcs(&w.sh_c[slot]);
-          RayT ray;
-          ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
-          ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
-          TravBegin(s, ray, t);
-          has_result = true;
-          ++rays;
-        } else {
-          dry = true;
-        }
-      }
+    fetch_base = __shfl_sync(0xffffffffu, fetch_base, 0);
+    const uint32_t slot = fetch_base + uint32_t(__popc(m_need & ((1u << lane) - 1u)));
+    if (need && slot < n) {
+      const float4 o = __ldcs(&w.sh_o[slot]), d = __ldcs(&w.sh_d[slot]);
+      c = __ldcs(&w.sh_c[slot]);
+      RayT ray;
+      ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
+      ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
+      TravBegin(s, ray, t);
+      has_result = true;
+      ++rays;
     }
-    return dry;
+    return need && slot >= n;
   }
-  __device__ __forceinline__ void End(const Trav&) {
-    if (rays) atomicAdd(&w.stats[kStatShadow], rays);
-  }
+  __device__ __forceinline__ void End(const Trav&) { WarpTally(&w.stats[kStatShadow], rays); }
 };
 
 template <bool HAS_CURVES>
