@@ -17,7 +17,7 @@ HOST     := pbrlab_b200/host
 DEVHDRS  := $(wildcard $(CSRC)/device/*.cuh) $(CSRC)/kat.cuh $(CSRC)/wavefront.cuh $(CSRC)/scene_host.h \
             $(CSRC)/bvh_builder.h include/pbrgpu.h
 HOSTSRCS := $(HOST)/scene.cc $(HOST)/render.cc $(HOST)/light-manager.cc $(HOST)/mesh/triangle-mesh.cc \
-            $(HOST)/curve-util.cc $(HOST)/io/triangle-mesh-io.cc $(HOST)/io/cyhair.cc $(HOST)/io/curve-mesh-io.cc \
+            $(HOST)/curve-util.cc $(HOST)/io/triangle-mesh-io.cc $(HOST)/io/image-io.cc $(HOST)/io/cyhair.cc $(HOST)/io/curve-mesh-io.cc \
             $(HOST)/pc-common.cc $(HOST)/c_api.cc
 HOSTHDRS := $(wildcard $(HOST)/*.h $(HOST)/*/*.h)
 
@@ -43,9 +43,9 @@ $(LIB)/libpbrgpu.so: $(LIB)/pbrgpu.o $(LIB)/scene_host.o $(LIB)/bvh_builder.o
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $^ -lpthread
 
 $(LIB)/libpbrlab_host.so: $(HOSTSRCS) $(HOSTHDRS) $(LIB)/libpbrgpu.so
-	$(HOSTCXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRCS) -L$(LIB) -lpbrgpu -Wl,-rpath,'$$ORIGIN' -lpthread
+	$(HOSTCXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRCS) -L$(LIB) -lpbrgpu -Wl,-rpath,'$$ORIGIN' -lpthread -lz
 $(LIB)/pbrlab-cli: $(HOST)/pbrlab-cli.cc $(LIB)/libpbrlab_host.so
-	$(HOSTCXX) $(CXXFLAGS) -o $@ $(HOST)/pbrlab-cli.cc -L$(LIB) -lpbrlab_host -lpbrgpu -Wl,-rpath,'$$ORIGIN' -lpthread
+	$(HOSTCXX) $(CXXFLAGS) -o $@ $(HOST)/pbrlab-cli.cc -L$(LIB) -lpbrlab_host -lpbrgpu -Wl,-rpath,'$$ORIGIN' -lpthread -lz
 
 tests/host_emul/libpbr_emul.so: tests/host_emul/emul.cc $(CSRC)/scene_host.cc $(CSRC)/bvh_builder.cc $(DEVHDRS)
 	$(HOSTCXX) $(CXXFLAGS) -Wno-unused-function -shared -o $@ tests/host_emul/emul.cc $(CSRC)/scene_host.cc \

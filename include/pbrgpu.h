@@ -62,6 +62,16 @@ typedef struct pbrgpu_hit {
   uint32_t instance_id, geom_id, prim_id;
 } pbrgpu_hit;
 
+/* One texture of Scene::AddTexture (reference src/scene.h:45-51, src/texture.h:10-44): row-major float pixels with
+ * `channels` (1..4) interleaved values per texel, already in linear colour (the loader de-gammas sRGB files,
+ * reference src/io/triangle-mesh-io.cc:80-104).  Sampled as Texture::FetchFloat3 does: bilinear, clamp addressing
+ * (src/texture.cc:43-72, src/image-utils.cc:99-167). */
+typedef struct pbrgpu_texture {
+  const float* pixels;
+  uint32_t width, height, channels;
+  uint32_t reserved;
+} pbrgpu_texture;
+
 /* Flattened area-light tables, exactly the numbers LightManager holds after Commit()
  * (reference src/light-manager.cc:29-184): one entry per light in global light order, and per light one entry per
  * primitive of its mesh. */
@@ -121,6 +131,9 @@ int pbrgpu_set_curves(pbrgpu_ctx* ctx, const float* xyzr, uint32_t nverts, const
 /* May be called again between renders (live material edits, reference pc/pbrlab-gui.cc:207-238). */
 int pbrgpu_set_materials(pbrgpu_ctx* ctx, const pbrgpu_material* materials, uint32_t n);
 int pbrgpu_set_lights(pbrgpu_ctx* ctx, const pbrgpu_light_tables* tables);
+/* Texture table the materials' tex_id index (pixels are copied).  Call before pbrgpu_commit; a material whose
+ * tex_id is neither PBRGPU_INVALID_ID nor inside this table fails the commit. */
+int pbrgpu_set_textures(pbrgpu_ctx* ctx, const pbrgpu_texture* textures, uint32_t n);
 /* Builds the acceleration structure and uploads everything to every device of the context.  bmin/bmax: the scene
  * AABB the camera is derived from (reference src/render.cc:132-158); pass NULL to use the bounds of the uploaded
  * geometry (triangle vertices in use; curve bounds as Embree's accurateFlatBounds). */
@@ -142,6 +155,14 @@ int pbrgpu_render(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp
 int pbrgpu_render_device(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed,
                          uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, float* d_rgba,
                          uint32_t* d_count, size_t* finish_pass);
+/* Output stage of the reference CLI on the device (pc/pbrlab-cli.cc:47-57, src/image-utils.cc:26-38,72-90,
+ * src/io/image-io.cc:172-210): colour = rgba / count -> LinerToSrgb on r,g,b (alpha untouched) -> 8 bit as
+ * WritePNG quantises, (unsigned char)clamp(v * 256, 0, 255).  Reads the accumulators the last pbrgpu_render* call
+ * left on the context's first device (for pbrgpu_render_device: the caller's d_rgba / d_count).  rgba8_out is a HOST
+ * buffer of width*height*4 bytes; pbrgpu_resolve_srgb8_device writes a DEVICE buffer instead. */
+int pbrgpu_resolve_srgb8(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint8_t* rgba8_out);
+int pbrgpu_resolve_srgb8_device(pbrgpu_ctx* ctx, const float* d_rgba, const uint32_t* d_count, uint32_t width,
+                                uint32_t height, uint8_t* d_rgba8_out);
 int pbrgpu_get_stats(const pbrgpu_ctx* ctx, pbrgpu_stats* out);
 /* profiling mode: every kernel family of every iteration is bracketed by CUDA events on the launching stream and the
  * sums are reported in pbrgpu_stats (adds ~10 event records per iteration) */

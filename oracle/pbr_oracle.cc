@@ -421,10 +421,28 @@ void BssrdfSetup(F3* weight, F3* albedo, F3* radius, F3* diffuse_weight) {   // 
   }
 }
 
-Principled ParamToBsdf(const float* p) {   // :244-412 (no textures: SURVEY §8(f)-4)
-  const F3 base(p[0], p[1], p[2]);
+// Texture::FetchFloat3 -> BilinearFilter, clamp addressing (src/texture.cc:43-72, src/image-utils.cc:99-167)
+struct TextureRef { const float* px; uint32_t w, h, c; };
+F3 TextureFetch3(const TextureRef& t, float u, float v) {
+  const float uu = std::min(std::max(u, 0.0f), 1.0f), vv = std::min(std::max(v, 0.0f), 1.0f);
+  const float px = float(t.w) * uu, py = float(t.h) * vv;
+  const int W = int(t.w), H = int(t.h);
+  const int x0 = std::max(0, std::min(W - 1, int(px))), y0 = std::max(0, std::min(H - 1, int(py)));
+  const int x1 = (x0 + 1 >= W) ? W - 1 : x0 + 1, y1 = (y0 + 1 >= H) ? H - 1 : y0 + 1;
+  const float dx = px - float(x0), dy = py - float(y0);
+  const float w0 = (1.0f - dx) * (1.0f - dy), w1 = (1.0f - dx) * dy, w2 = dx * (1.0f - dy), w3 = dx * dy;
+  const int st = int(t.c);
+  const int i00 = st * (y0 * W + x0), i01 = st * (y0 * W + x1), i10 = st * (y1 * W + x0), i11 = st * (y1 * W + x1);
+  float o[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < 3 && k < st; ++k)
+    o[k] = t.px[i00 + k] * w0 + t.px[i10 + k] * w1 + t.px[i01 + k] * w2 + t.px[i11 + k] * w3;
+  return F3(o[0], o[1], o[2]);
+}
+
+// :244-412; base / ss_color arrive texture-resolved (:281-301)
+Principled ParamToBsdf(const float* p, const F3& base, const F3& ss_color) {
   const float subsurface = p[3];
-  const F3 ss_radius(p[4], p[5], p[6]), ss_color(p[7], p[8], p[9]);
+  const F3 ss_radius(p[4], p[5], p[6]);
   const float metallic = p[10], specular = p[11], specular_tint = p[12], roughness = p[13], anisotropic = p[14];
   const float clearcoat = p[18], clearcoat_roughness = p[19], transmission = p[21];
   const float cut = kEps;
@@ -854,6 +872,8 @@ struct pbo_scene {
   std::vector<uint32_t> vidx, nidx, tidx, tri_mat, tri_inst, tri_geom, tri_prim;
   std::vector<uint32_t> seg_first, seg_mat, seg_inst, seg_geom, seg_prim;
   std::vector<Material> materials;
+  std::vector<float> tex_pixels;
+  std::vector<TextureRef> textures;
   // LightManager tables (src/light-manager.h:172-193)
   std::vector<float> light_prob, light_cdf, prim_prob, prim_cdf, prim_area_pdf, prim_emission;
   std::vector<uint32_t> light_off, prim_emissive, prim_tri;
@@ -939,6 +959,7 @@ enum Face { kFront = 0, kBack = 1, kAmbiguous = 2 };
 struct Surface {   // SurfaceInfo (src/shader/shader-utils.h:18-41)
   F3 P, Ns, Ng;
   float u, v;
+  float tex_u = 0.f, tex_v = 0.f;   // Scene::FetchMeshTexcoord (scene.cc:226-249)
   uint32_t inst, mat;
   int light_entry;
   int face;
@@ -965,6 +986,15 @@ Surface MakeSurface(const pbo_scene& s, const Ray& r, const Hit& h) {
       si.Ns = Normalized(Cross(p1 - p0, p2 - p1));   // CalcGeometryNormal (triangle-mesh.cc:181-184)
     } else {
       si.Ns = Normalized(Lerp3(s.Norm(n0), s.Norm(n1), s.Norm(n2), h.u, h.v));
+    }
+    // TriangleMesh::FetchTexcoord (triangle-mesh.cc:126-155): barycentrics when a corner has no texcoord
+    const uint32_t t0 = s.tidx[3 * f], t1 = s.tidx[3 * f + 1], t2 = s.tidx[3 * f + 2];
+    if (t0 == 0xFFFFFFFFu || t1 == 0xFFFFFFFFu || t2 == 0xFFFFFFFFu) {
+      si.tex_u = h.u; si.tex_v = h.v;
+    } else {
+      const float w = 1.0f - h.u - h.v;   // Lerp3 (pbrlab_math.h:35-38)
+      si.tex_u = w * s.uvs[2 * t0] + h.u * s.uvs[2 * t1] + h.v * s.uvs[2 * t2];
+      si.tex_v = w * s.uvs[2 * t0 + 1] + h.u * s.uvs[2 * t1 + 1] + h.v * s.uvs[2 * t2 + 1];
     }
   }
   const float dg = Dot(r.d, si.Ng), ds = Dot(r.d, si.Ns);
@@ -1156,7 +1186,11 @@ void PrincipledShader(const pbo_scene& s, F3 wo_world, Rng& rng, Surface* si, Ve
   BranchlessONB(entry.ez, &entry.ex, &entry.ey);
   Frame Rgl = entry;
   const F3 wo = Rgl.ToLocal(wo_world);
-  const Principled b = ParamToBsdf(s.materials[si->mat].p);
+  const Material& mp = s.materials[si->mat];
+  F3 base(mp.p[0], mp.p[1], mp.p[2]), ss_color(mp.p[7], mp.p[8], mp.p[9]);
+  if (mp.tex[0] < s.textures.size()) base = TextureFetch3(s.textures[mp.tex[0]], si->tex_u, si->tex_v);
+  if (mp.tex[1] < s.textures.size()) ss_color = TextureFetch3(s.textures[mp.tex[1]], si->tex_u, si->tex_v);
+  const Principled b = ParamToBsdf(mp.p, base, ss_color);
   F3 contribute = DirectIllumination(s, *si, Rgl, entry.ez, rng, true,
                                      [&](F3 wl, F3* ff, float* pp) { EvalBsdf(wl, wo, b, ff, pp); }, cnt);
   F3 wi(0.f), f(0.f), c2(0.f);
@@ -1350,6 +1384,22 @@ int pbo_set_materials(pbo_scene* s, const void* materials, uint32_t n) {
   if (!s) return 1;
   s->materials.resize(n);
   if (n) memcpy(s->materials.data(), materials, sizeof(Material) * n);
+  return 0;
+}
+
+int pbo_set_textures(pbo_scene* s, const pbo_texture* t, uint32_t n) {
+  if (!s || (n && !t)) return 1;
+  size_t total = 0;
+  for (uint32_t i = 0; i < n; ++i) total += size_t(t[i].width) * t[i].height * t[i].channels;
+  s->tex_pixels.resize(total);
+  s->textures.resize(n);
+  size_t off = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const size_t cnt = size_t(t[i].width) * t[i].height * t[i].channels;
+    memcpy(s->tex_pixels.data() + off, t[i].pixels, cnt * sizeof(float));
+    s->textures[i] = {s->tex_pixels.data() + off, t[i].width, t[i].height, t[i].channels};
+    off += cnt;
+  }
   return 0;
 }
 

@@ -57,7 +57,14 @@ class Flat(C.Structure):
                 ("curve_first", C.c_void_p), ("curve_material", C.c_void_p), ("curve_instance", C.c_void_p),
                 ("curve_geom", C.c_void_p), ("curve_prim", C.c_void_p), ("nsegs", C.c_uint64),
                 ("materials", C.c_void_p), ("nmaterials", C.c_uint32),
-                ("lights", LightTables), ("bmin", C.c_float * 3), ("bmax", C.c_float * 3)]
+                ("lights", LightTables), ("bmin", C.c_float * 3), ("bmax", C.c_float * 3),
+                ("tex_pixels", C.c_void_p), ("ntex_floats", C.c_uint64), ("tex_desc", C.c_void_p),
+                ("ntextures", C.c_uint32)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("channels", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 RAY_DTYPE = np.dtype([("org", np.float32, 3), ("tmin", np.float32), ("dir", np.float32, 3), ("tmax", np.float32)])
@@ -131,6 +138,16 @@ class FlatScene:
         self.prim_triangle = _np_view(L.prim_triangle, npr, np.uint32)
         self.bmin = np.array(list(f.bmin), np.float32)
         self.bmax = np.array(list(f.bmax), np.float32)
+        self.tex_pixels = _np_view(f.tex_pixels, int(f.ntex_floats), np.float32)
+        self.tex_desc = _np_view(f.tex_desc, int(f.ntextures), np.uint32, 4)   # offset, width, height, channels
+
+    def textures(self):
+        """ctypes array of pbrgpu_texture over self.tex_pixels (keep `self` alive while it is in use)."""
+        arr = (Texture * max(1, len(self.tex_desc)))()
+        for i, (off, w, h, c) in enumerate(self.tex_desc):
+            arr[i].pixels = self.tex_pixels.ctypes.data + 4 * int(off)
+            arr[i].width, arr[i].height, arr[i].channels = int(w), int(h), int(c)
+        return arr
 
     def light_tables(self):
         t = LightTables()
@@ -146,6 +163,8 @@ class FlatScene:
     def upload(self, lib, h, prefix):
         """Feed the flat scene to an object exposing <prefix>set_* / commit (libpbrgpu or the test emulation)."""
         g = lambda name: getattr(lib, prefix + name)
+        rc = g("set_textures")(h, self.textures(), C.c_uint32(len(self.tex_desc)))
+        if rc: return rc
         rc = g("set_materials")(h, _p(self.materials), C.c_uint32(len(self.materials)))
         if rc: return rc
         rc = g("set_triangles")(h, _p(self.verts), C.c_uint32(len(self.verts)), _p(self.vidx), _p(self.normals),
@@ -180,7 +199,8 @@ def gpu_lib():
         L.pbrgpu_last_error.restype = C.c_char_p
         L.pbrgpu_last_error.argtypes = [C.c_void_p]
         L.pbrgpu_destroy.argtypes = [C.c_void_p]
-        for name in ("pbrgpu_set_triangles", "pbrgpu_set_curves", "pbrgpu_set_materials", "pbrgpu_set_lights",
+        for name in ("pbrgpu_set_triangles", "pbrgpu_set_curves", "pbrgpu_set_materials", "pbrgpu_set_lights", "pbrgpu_set_textures",
+                     "pbrgpu_resolve_srgb8", "pbrgpu_resolve_srgb8_device",
                      "pbrgpu_commit", "pbrgpu_scene_bounds", "pbrgpu_render", "pbrgpu_render_device",
                      "pbrgpu_get_stats", "pbrgpu_set_wave_spp", "pbrgpu_set_profiling", "pbrgpu_trace", "pbrgpu_occluded",
                      "pbrgpu_trace_device", "pbrgpu_occluded_device", "pbrgpu_radiance", "pbrgpu_radiance_mega",
@@ -280,6 +300,12 @@ class Context:
                                                   C.c_uint64(seed), C.c_uint32(sample_offset),
                                                   C.c_uint32(sample_stride), None, C.c_void_p(d_rgba_ptr),
                                                   C.c_void_p(d_count_ptr), None))
+
+    def resolve_srgb8(self, width, height):
+        """pbrgpu_resolve_srgb8: the CLI's output stage (mean -> sRGB -> 8 bit) of the last rendered frame."""
+        out = np.empty((height, width, 4), np.uint8)
+        self._check(self.lib.pbrgpu_resolve_srgb8(self.h, C.c_uint32(width), C.c_uint32(height), _p(out)))
+        return out
 
     def trace(self, rays):
         rays = np.ascontiguousarray(rays)

@@ -20,6 +20,18 @@ struct LightRec {        // one entry of LightManager::lights_ (light-manager.h:
   uint32_t pad;
 };
 
+// Shading queue of a material (scene_host.cc: ClassifyMaterial): the closest-hit kernel routes every hit by this
+enum MaterialClass : uint32_t {
+  kClassGeneral = 0,   // Principled with any closure set (incl. none, textured, subsurface): ShadeSurfaceKernel<false>
+  kClassDiffuse = 1,   // Principled that can only ever enable the Lambert closure: ShadeSurfaceKernel<true>
+  kClassHair = 2       // HairBsdfParameter: ShadeHairKernel
+};
+
+struct TexDesc {         // one Texture (texture.h:10-44): row-major float pixels, `channels` interleaved
+  uint32_t offset;       // first float in SceneView::tex_pixels
+  uint32_t width, height, channels;
+};
+
 struct SceneView {
   // ---- traversal (see bvh_builder.h for the node format)
   const float4* tri_nodes;     // 5 x float4 per 8-wide compressed node; root = node 0
@@ -40,7 +52,12 @@ struct SceneView {
   const uint4* curve_ids;      // instance_id, geom_id, segment id inside the shape, material_id
   const DeviceMaterial* materials;
   uint32_t num_materials;
-  uint32_t num_hair_materials; // materials of type 1: scenes without any route every hit to the Principled queue unseen
+  uint32_t num_hair_materials; // materials of type 1
+  const uint32_t* material_class;   // MaterialClass per material
+  // ---- textures (Scene::AddTexture; sampled by ParamToBsdf for base_color / subsurface_color)
+  const float* tex_pixels;     // all textures back to back
+  const TexDesc* tex_desc;
+  uint32_t num_textures;
   // ---- lights (light-manager.h:172-193 flattened)
   const float4* emissive;      // per emissive triangle: emission rgb, pdf = P(light) P(prim) / area   (ImplicitAreaLight)
   const float* light_cdf;      // cumulative_probability_ over lights

@@ -233,15 +233,42 @@ PBR_HD void FinishPrincipled(const Frame& entry, const vec3& omega_in, const vec
   }
 }
 
+// Texture::FetchFloat3 (texture.cc:43-72) -> BilinearFilter with clamp addressing (image-utils.cc:99-167): the
+// texel grid is addressed by px = width * clamp(u, 0, 1) (no half-texel offset), neighbours clamp at the border,
+// channels beyond the texture's own read as 0.
+PBR_HD vec3 TextureFetch3(const SceneView& s, uint32_t tex_id, float u, float v) {
+  const TexDesc td = s.tex_desc[tex_id];
+  const float uu = fminf_(fmaxf_(u, 0.0f), 1.0f), vv = fminf_(fmaxf_(v, 0.0f), 1.0f);
+  const float px = float(td.width) * uu, py = float(td.height) * vv;
+  const int w = int(td.width), h = int(td.height);
+  int x0 = int(px), y0 = int(py);
+  x0 = x0 < 0 ? 0 : (x0 > w - 1 ? w - 1 : x0);
+  y0 = y0 < 0 ? 0 : (y0 > h - 1 ? h - 1 : y0);
+  const int x1 = (x0 + 1 >= w) ? w - 1 : x0 + 1, y1 = (y0 + 1 >= h) ? h - 1 : y0 + 1;
+  const float dx = px - float(x0), dy = py - float(y0);
+  const float w0 = (1.0f - dx) * (1.0f - dy), w1 = (1.0f - dx) * dy, w2 = dx * (1.0f - dy), w3 = dx * dy;
+  const int st = int(td.channels);
+  const float* img = s.tex_pixels + td.offset;
+  const int i00 = st * (y0 * w + x0), i01 = st * (y0 * w + x1), i10 = st * (y1 * w + x0), i11 = st * (y1 * w + x1);
+  float out[3] = {0.f, 0.f, 0.f};
+  for (int c = 0; c < 3 && c < st; ++c)
+    out[c] = ((img[i00 + c] * w0 + img[i10 + c] * w1) + img[i01 + c] * w2) + img[i11 + c] * w3;
+  return vec3(out[0], out[1], out[2]);
+}
+
 PBR_HD PrincipledBsdf SurfaceBsdf(const SceneView& s, const Surface& si) {
   const DeviceMaterial& m = s.materials[si.material_id];
   PrincipledParams pp;
   memcpy(&pp, m.p, 23 * sizeof(float));
   pp.base_color_tex_id = m.tex_id[0];
   pp.subsurface_color_tex_id = m.tex_id[1];
-  // textures: SURVEY §8(f)-4 (next row); ids other than "none" are rejected at pbrgpu_set_materials
-  return ParamToBsdf(pp, vec3(pp.base_color[0], pp.base_color[1], pp.base_color[2]),
-                     vec3(pp.subsurface_color[0], pp.subsurface_color[1], pp.subsurface_color[2]));
+  // cycles-principled-shader.cc:281-301: a texture id other than -1 replaces the constant colour (ids are validated
+  // against the texture table at pbrgpu_commit / pbrgpu_set_materials)
+  vec3 base(pp.base_color[0], pp.base_color[1], pp.base_color[2]);
+  vec3 sub(pp.subsurface_color[0], pp.subsurface_color[1], pp.subsurface_color[2]);
+  if (pp.base_color_tex_id < s.num_textures) base = TextureFetch3(s, pp.base_color_tex_id, si.tex_u, si.tex_v);
+  if (pp.subsurface_color_tex_id < s.num_textures) sub = TextureFetch3(s, pp.subsurface_color_tex_id, si.tex_u, si.tex_v);
+  return ParamToBsdf(pp, base, sub);
 }
 
 PBR_HD Frame PrincipledFrame(const Surface& si) {
@@ -255,15 +282,23 @@ PBR_HD Frame PrincipledFrame(const Surface& si) {
 // random walk: the caller then runs the walk (SubsurfaceVertex, or SssBegin + the wavefront's walk kernels); rng is
 // left right after the selector draw in that case.  fr_out / bsdf_out: the shading frame and closure set of the
 // vertex, for the caller that continues with the walk.
-PBR_HD bool PrincipledVertex(const SceneView& s, const Surface& si, const vec3& wo_world, Pcg32* rng,
-                             VertexResult* out, Frame* fr_out, PrincipledBsdf* bsdf_out) {
+// DIFFUSE_ONLY: the material is of class kClassDiffuse (scene_host.cc: ClassifyMaterial) — ParamToBsdf enables the
+// Lambert closure and nothing else, and its selection weight is exactly 1, so `select < w.diffuse` always holds.  The
+// same statements run in the same order; the other closures are compiled out.
+template <bool DIFFUSE_ONLY>
+PBR_HD bool PrincipledVertexT(const SceneView& s, const Surface& si, const vec3& wo_world, Pcg32* rng,
+                              VertexResult* out, Frame* fr_out, PrincipledBsdf* bsdf_out) {
   if (si.face == kAmbiguous) {
     AbsorbVertex(wo_world, si.P, out);
     return false;
   }
   const Frame fr = PrincipledFrame(si);
   const vec3 wo = fr.ToLocal(wo_world);
-  const PrincipledBsdf bsdf = SurfaceBsdf(s, si);
+  PrincipledBsdf bsdf = SurfaceBsdf(s, si);
+  if (DIFFUSE_ONLY) {
+    bsdf.enable_diffuse = true;
+    bsdf.enable_subsurface = bsdf.enable_specular = bsdf.enable_clearcoat = false;
+  }
   out->P = si.P;
   out->shadow[1].active = false;
   PrincipledEval ev = {&bsdf, wo};
@@ -271,16 +306,26 @@ PBR_HD bool PrincipledVertex(const SceneView& s, const Surface& si, const vec3& 
 
   const SampleWeight w = FetchClosureSampleWeight(wo, bsdf);
   const float select = Draw(rng);
-  if (!(select < w.diffuse) && select < w.diffuse + w.subsurface) {
-    *fr_out = fr;
-    *bsdf_out = bsdf;
-    return true;
-  }
   vec3 wi(0.f), f(0.f);
   float pdf = 0.f;
-  SampleBsdfLobes(bsdf, w, select, wo, rng, &wi, &f, &pdf);
+  if (DIFFUSE_ONLY) {
+    const float u0 = Draw(rng), u1 = Draw(rng);
+    wi = CosineSampleHemisphere(u0, u1);
+    EvalBsdf(wi, wo, bsdf, &f, &pdf);
+  } else {
+    if (!(select < w.diffuse) && select < w.diffuse + w.subsurface) {
+      *fr_out = fr;
+      *bsdf_out = bsdf;
+      return true;
+    }
+    SampleBsdfLobes(bsdf, w, select, wo, rng, &wi, &f, &pdf);
+  }
   FinishPrincipled(fr, wi, f, pdf, out);
   return false;
+}
+PBR_HD bool PrincipledVertex(const SceneView& s, const Surface& si, const vec3& wo_world, Pcg32* rng,
+                             VertexResult* out, Frame* fr_out, PrincipledBsdf* bsdf_out) {
+  return PrincipledVertexT<false>(s, si, wo_world, rng, out, fr_out, bsdf_out);
 }
 PBR_HD bool PrincipledVertex(const SceneView& s, const Surface& si, const vec3& wo_world, Pcg32* rng,
                              VertexResult* out) {

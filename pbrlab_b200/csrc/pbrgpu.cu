@@ -68,7 +68,9 @@ struct Device {
   DevBuf<float4> geom;   // [tri_nodes | tri_data | curve_nodes | curve_data]: one range for the L2 persistence window
   DevBuf<float4> verts, normals, emissive, lprim_info;
   DevBuf<float2> texcoords;
-  DevBuf<uint32_t> curve_prim, lprim_tri, clear_bits;
+  DevBuf<uint32_t> curve_prim, lprim_tri, clear_bits, material_class;
+  DevBuf<float> tex_pixels;
+  DevBuf<pbr::TexDesc> tex_desc;
   DevBuf<uint4> tri_ids, tri_nidx, tri_vidx, tri_tidx, curve_ids;
   DevBuf<pbr::DeviceMaterial> materials;
   DevBuf<float> light_cdf, lprim_cdf;
@@ -76,19 +78,22 @@ struct Device {
   pbr::SceneView view;
   // wave
   DevBuf<float4> slot, walk, sh_o, sh_d, sh_c;
-  DevBuf<uint32_t> q0, q1, q_surface, q_hair, q_sss, q_exit, q_walk0, q_walk1, q_done0, q_done1, counters;
+  DevBuf<uint32_t> q0, q1, q_surface, q_diffuse, q_hair, q_sss, q_exit, q_walk0, q_walk1, q_done0, q_done1, counters;
   DevBuf<unsigned long long> stats;
   pbr::WaveState wave;
   uint32_t wave_capacity = 0;
   // frame accumulators (device side of RenderLayer)
   DevBuf<float4> rgba;
   DevBuf<uint32_t> count;
+  DevBuf<uint8_t> srgb8;      // output stage (pbrgpu_resolve_srgb8)
+  uint32_t frame_width = 0, frame_height = 0;   // size of the last rendered frame
   // pinned host mirror of the counters
   uint32_t* h_counters = nullptr;
   unsigned long long* h_stats = nullptr;
 
   void Release() {
-    geom.Free(); clear_bits.Free(); verts.Free(); normals.Free();
+    geom.Free(); clear_bits.Free(); verts.Free(); normals.Free(); material_class.Free(); tex_pixels.Free();
+    tex_desc.Free(); q_diffuse.Free(); srgb8.Free();
     emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); lprim_tri.Free(); tri_ids.Free();
     tri_nidx.Free(); tri_vidx.Free(); tri_tidx.Free(); curve_ids.Free(); materials.Free(); light_cdf.Free();
     lprim_cdf.Free(); lights.Free();
@@ -125,6 +130,8 @@ struct pbrgpu_ctx {
   int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
   int tune_pool_mi = 8;            // path slots kept in flight, in Mi (x 256 B of slot + walk lines)
   int tune_trace_blocks = 8, tune_shade_blocks = 1, tune_walk_blocks = 6;   // resident 128-thread blocks per SM
+  int tune_diffuse_threads = pbr::kDiffuseBlock, tune_diffuse_blocks = pbr::kDiffuseBlocksPerSm;   // launch shape of the diffuse-only shading kernel
+  int tune_sort_materials = 1;     // diffuse-only Principled materials get their own shading queue and kernel
 };
 
 namespace {
@@ -202,6 +209,9 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   CUDA_TRY(ctx, d.lprim_info.Upload(h.lprim_info.data(), h.lprim_info.size(), st));
   CUDA_TRY(ctx, d.lprim_tri.Upload(h.lprim_tri.data(), h.lprim_tri.size(), st));
   CUDA_TRY(ctx, d.clear_bits.Upload(h.clear_bits.data(), h.clear_bits.size(), st));
+  CUDA_TRY(ctx, d.material_class.Upload(h.material_class.data(), h.material_class.size(), st));
+  CUDA_TRY(ctx, d.tex_pixels.Upload(h.tex_pixels.data(), h.tex_pixels.size(), st));
+  CUDA_TRY(ctx, d.tex_desc.Upload(h.tex_desc.data(), h.tex_desc.size(), st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   SceneView& v = d.view;
   memset(&v, 0, sizeof(v));
@@ -213,6 +223,8 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   v.verts = d.verts.ptr; v.normals = d.normals.ptr; v.texcoords = d.texcoords.ptr; v.curve_ids = d.curve_ids.ptr;
   v.materials = d.materials.ptr; v.num_materials = uint32_t(h.materials.size());
   v.num_hair_materials = CountHairMaterials(h);
+  v.material_class = d.material_class.ptr;
+  v.tex_pixels = d.tex_pixels.ptr; v.tex_desc = d.tex_desc.ptr; v.num_textures = uint32_t(h.tex_desc.size());
   v.emissive = d.emissive.ptr; v.light_cdf = d.light_cdf.ptr; v.lights = d.lights.ptr;
   v.num_lights = uint32_t(h.lights.size());
   v.lprim_cdf = d.lprim_cdf.ptr; v.lprim_info = d.lprim_info.ptr; v.lprim_tri = d.lprim_tri.ptr;
@@ -231,6 +243,7 @@ int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
     CUDA_TRY(ctx, d.walk.Alloc(size_t(capacity) * pbr::kWalkStride));
     CUDA_TRY(ctx, d.q0.Alloc(capacity)); CUDA_TRY(ctx, d.q1.Alloc(capacity));
     CUDA_TRY(ctx, d.q_surface.Alloc(capacity)); CUDA_TRY(ctx, d.q_hair.Alloc(capacity));
+    CUDA_TRY(ctx, d.q_diffuse.Alloc(capacity));
     CUDA_TRY(ctx, d.q_sss.Alloc(capacity)); CUDA_TRY(ctx, d.q_exit.Alloc(capacity));
     CUDA_TRY(ctx, d.q_walk0.Alloc(capacity)); CUDA_TRY(ctx, d.q_walk1.Alloc(capacity));
     CUDA_TRY(ctx, d.q_done0.Alloc(capacity)); CUDA_TRY(ctx, d.q_done1.Alloc(capacity));
@@ -245,7 +258,7 @@ int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
   WaveState& w = d.wave;
   w.slot = d.slot.ptr; w.walk = d.walk.ptr;
   w.q_active[0] = d.q0.ptr; w.q_active[1] = d.q1.ptr; w.q_surface = d.q_surface.ptr;
-  w.q_hair = d.q_hair.ptr; w.q_sss = d.q_sss.ptr; w.q_exit = d.q_exit.ptr;
+  w.q_diffuse = d.q_diffuse.ptr; w.q_hair = d.q_hair.ptr; w.q_sss = d.q_sss.ptr; w.q_exit = d.q_exit.ptr;
   w.q_walk[0] = d.q_walk0.ptr; w.q_walk[1] = d.q_walk1.ptr;
   w.q_done[0] = d.q_done0.ptr; w.q_done[1] = d.q_done1.ptr;
   w.sh_o = d.sh_o.ptr; w.sh_d = d.sh_d.ptr; w.sh_c = d.sh_c.ptr;
@@ -270,6 +283,7 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
   uint32_t parity = 0;
   const int grid_trace = PersistentGrid(d, ctx->tune_trace_blocks), grid_shade = PersistentGrid(d, ctx->tune_shade_blocks);
   const int grid_walk = PersistentGrid(d, ctx->tune_walk_blocks);
+  const int grid_diffuse = PersistentGrid(d, ctx->tune_diffuse_blocks);
   const bool curves = s.num_curves != 0u;
   const uint32_t refill = ctx->tune_refill;
   pbr::FrameParams no_frame;
@@ -286,14 +300,16 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     const bool prof = ctx->profile;
     auto mark = [&](int k) { if (prof) cudaEventRecord(d.kev[k], st); };
     const uint32_t regen = frame ? 1u : 0u;
+    const uint32_t sort = ctx->tune_sort_materials ? 1u : 0u;
     pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, regen);
     tm->launches += 1;
     mark(0);
     mark(1);
-    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, regen);
-    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, regen);
+    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, regen, sort);
+    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, regen, sort);
     mark(2);
-    pbr::ShadeSurfaceKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
+    pbr::ShadeSurfaceKernel<false><<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
+    if (sort) pbr::ShadeSurfaceKernel<true><<<grid_diffuse, ctx->tune_diffuse_threads, 0, st>>>(s, w, next, flags);
     if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
     mark(3);
     if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
@@ -303,7 +319,7 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, refill, ctx->tune_prim_lanes);
     else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, refill, ctx->tune_prim_lanes);
     mark(5);
-    tm->launches += s.num_curves ? 6 : 5;
+    tm->launches += (s.num_curves ? 6 : 5) + (sort ? 1 : 0);
     tm->closest_launches += 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(d.h_counters, w.counters, sizeof(uint32_t) * pbr::kCounterCount,
                                   cudaMemcpyDeviceToHost, st));
@@ -359,6 +375,7 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   const uint32_t local_spp = (spp > sample_offset) ? (spp - sample_offset + sample_stride - 1) / sample_stride : 0;
   CUDA_TRY(ctx, d.rgba.Alloc(npix));
   CUDA_TRY(ctx, d.count.Alloc(npix));
+  d.frame_width = width; d.frame_height = height;
   CUDA_TRY(ctx, cudaMemsetAsync(d.rgba.ptr, 0, sizeof(float4) * npix, d.stream));
   CUDA_TRY(ctx, cudaMemsetAsync(d.count.ptr, 0, sizeof(uint32_t) * npix, d.stream));
   if (local_spp == 0) { CUDA_TRY(ctx, cudaStreamSynchronize(d.stream)); return PBRGPU_OK; }
@@ -407,6 +424,31 @@ __global__ void AddBuffersKernel(float4* dst, const float4* src, uint32_t* cdst,
   a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
   dst[i] = a;
   cdst[i] += csrc[i];
+}
+
+// Output stage (pc/pbrlab-cli.cc:47-57): mean = sum / count, LinerTosRGB on r,g,b (image-utils.cc:26-38: 12.92 c
+// below 0.0031308, else pow(1.055 c, 1/2.4) - 0.055), alpha untouched, then WritePNG's quantisation
+// (unsigned char)clamp(v * 256, 0, 255) (io/image-io.cc:200-206).  One thread per pixel, 16 B in, 4 B out.
+__device__ __forceinline__ float LinearToSrgbDev(float c) {
+  if (c <= 0.0031308f) return 12.92f * c;
+  return powf((1.0f + 0.055f) * c, float(1.0 / 2.4)) - 0.055f;
+}
+__device__ __forceinline__ unsigned char Quantise8(float v) {
+  const float x = fmaxf(0.0f, fminf(255.0f, v * 256.0f));   // Clamp(x, 0, 255): NaN -> 0 like std::max(a, std::min(b, x))
+  return static_cast<unsigned char>(x);
+}
+__global__ void ResolveSrgb8Kernel(const float4* __restrict__ rgba, const uint32_t* __restrict__ count, uint32_t npix,
+                                   uchar4* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float4 a = rgba[i];
+  const float n = float(count[i]);
+  uchar4 o;
+  o.x = Quantise8(LinearToSrgbDev(a.x / n));
+  o.y = Quantise8(LinearToSrgbDev(a.y / n));
+  o.z = Quantise8(LinearToSrgbDev(a.z / n));
+  o.w = Quantise8(a.w / n);
+  out[i] = o;
 }
 
 __global__ void KatKernel(int op, const float* params, const float* in, uint32_t in_stride, uint64_t n, float* out,
@@ -489,6 +531,9 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_pool_mi = std::min(64, std::max(1, env_int("PBRGPU_POOL_MI", ctx->tune_pool_mi)));
   ctx->tune_l2_persist = env_int("PBRGPU_L2_PERSIST", ctx->tune_l2_persist);
   ctx->tune_sss_skip = env_int("PBRGPU_SSS_SKIP", ctx->tune_sss_skip);
+  ctx->tune_sort_materials = env_int("PBRGPU_SORT_MATERIALS", ctx->tune_sort_materials);
+  ctx->tune_diffuse_blocks = std::max(1, env_int("PBRGPU_DIFFUSE_BLOCKS", ctx->tune_diffuse_blocks));
+  ctx->tune_diffuse_threads = std::min(pbr::kDiffuseBlock, std::max(32, env_int("PBRGPU_DIFFUSE_THREADS", ctx->tune_diffuse_threads) & ~31));
   ctx->tune_shade_threads = std::min(pbr::kShadeBlock, std::max(32, env_int("PBRGPU_SHADE_THREADS", ctx->tune_shade_threads) & ~31));
   for (int id : ids) {
     if (id < 0 || id >= ndev) {
@@ -575,11 +620,23 @@ int pbrgpu_set_materials(pbrgpu_ctx* ctx, const pbrgpu_material* materials, uint
     for (Device& d : ctx->devices) {
       CUDA_TRY(ctx, cudaSetDevice(d.id));
       CUDA_TRY(ctx, d.materials.Upload(ctx->host.materials.data(), ctx->host.materials.size(), d.stream));
+      CUDA_TRY(ctx, d.material_class.Upload(ctx->host.material_class.data(), ctx->host.material_class.size(), d.stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
       d.view.materials = d.materials.ptr;
+      d.view.material_class = d.material_class.ptr;
       d.view.num_materials = n;
       d.view.num_hair_materials = CountHairMaterials(ctx->host);
     }
+  }
+  return PBRGPU_OK;
+}
+
+int pbrgpu_set_textures(pbrgpu_ctx* ctx, const pbrgpu_texture* textures, uint32_t n) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  ctx->committed = false;
+  if (!ctx->host.SetTextures(textures, n)) {
+    ctx->error = ctx->host.error;
+    return PBRGPU_ERR_INVALID;
   }
   return PBRGPU_OK;
 }
@@ -708,6 +765,37 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
   for (uint32_t sidx = sample_offset; sidx < spp; sidx += sample_stride) ++samples;
   s.paths = samples * npix;
   s.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return PBRGPU_OK;
+}
+
+int pbrgpu_resolve_srgb8_device(pbrgpu_ctx* ctx, const float* d_rgba, const uint32_t* d_count, uint32_t width,
+                                uint32_t height, uint8_t* d_rgba8_out) {
+  if (!ctx || ctx->devices.empty() || !d_rgba || !d_count || !d_rgba8_out) return PBRGPU_ERR_INVALID;
+  const uint64_t npix = uint64_t(width) * height;
+  if (npix == 0 || npix > 0x7fffffffull) { ctx->error = "pbrgpu_resolve_srgb8: bad image size"; return PBRGPU_ERR_INVALID; }
+  Device& d = ctx->devices[0];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  ResolveSrgb8Kernel<<<unsigned((npix + 255) / 256), 256, 0, d.stream>>>(
+      reinterpret_cast<const float4*>(d_rgba), d_count, uint32_t(npix), reinterpret_cast<uchar4*>(d_rgba8_out));
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  return PBRGPU_OK;
+}
+
+int pbrgpu_resolve_srgb8(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint8_t* rgba8_out) {
+  if (!ctx || ctx->devices.empty() || !rgba8_out) return PBRGPU_ERR_INVALID;
+  Device& d = ctx->devices[0];
+  if (!d.rgba.ptr || d.frame_width != width || d.frame_height != height) {
+    ctx->error = "pbrgpu_resolve_srgb8: no rendered frame of this size on the device";
+    return PBRGPU_ERR_INVALID;
+  }
+  const size_t npix = size_t(width) * height;
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  CUDA_TRY(ctx, d.srgb8.Alloc(npix * 4));
+  const int rc = pbrgpu_resolve_srgb8_device(ctx, reinterpret_cast<const float*>(d.rgba.ptr), d.count.ptr, width,
+                                             height, d.srgb8.ptr);
+  if (rc != PBRGPU_OK) return rc;
+  CUDA_TRY(ctx, cudaMemcpy(rgba8_out, d.srgb8.ptr, npix * 4, cudaMemcpyDeviceToHost));
   return PBRGPU_OK;
 }
 
@@ -880,9 +968,9 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
     CUDA_TRY(ctx, dface.Alloc(2 * n));
     pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters, d.wave.stats, 0u, 0u);
     if (d.view.num_curves)
-      pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), 0u);
+      pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), 0u, 0u);
     else
-      pbr::TraceClosestKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), 0u);
+      pbr::TraceClosestKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), 0u, 0u);
     SurfaceFaceKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.view, d.wave, n32, dface.ptr);
     // restore the entry state for the real iteration below
     pbr::InitPathsFromRaysKernel<<<(std::max(n32, 64u) + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);

@@ -1,6 +1,8 @@
 // See scene_host.h.
 #include "scene_host.h"
 
+#include "device/principled.cuh"
+
 #include <algorithm>
 #include <chrono>
 #include <cfloat>
@@ -75,16 +77,76 @@ bool HostScene::SetCurves(const float* xyzr, uint32_t nverts, const uint32_t* fi
   return true;
 }
 
+// Which shading queue a material's vertices go to (device/scene_view.cuh: MaterialClass).  A Principled material is
+// "diffuse only" when ParamToBsdf (cycles-principled-shader.cc:244-412) enables the Lambert closure and nothing
+// else for EVERY hit, i.e. no texture can change the closure set, and its selection weight is exactly 1
+// (luma > 0 and finite, so w = x / x).  The specialised kernel runs the same code with the other closures compiled out.
+static uint32_t ClassifyMaterial(const pbrgpu_material& m) {
+  if (m.type == 1) return pbr::kClassHair;
+  if (m.tex_id[0] != PBRGPU_INVALID_ID || m.tex_id[1] != PBRGPU_INVALID_ID) return pbr::kClassGeneral;
+  pbr::PrincipledParams pp;
+  memcpy(&pp, m.p, 23 * sizeof(float));
+  pp.base_color_tex_id = pp.subsurface_color_tex_id = PBRGPU_INVALID_ID;
+  const pbr::PrincipledBsdf b =
+      pbr::ParamToBsdf(pp, pbr::vec3(pp.base_color[0], pp.base_color[1], pp.base_color[2]),
+                       pbr::vec3(pp.subsurface_color[0], pp.subsurface_color[1], pp.subsurface_color[2]));
+  if (!b.enable_diffuse || b.enable_subsurface || b.enable_specular || b.enable_clearcoat) return pbr::kClassGeneral;
+  const float y = pbr::RgbToY(b.diffuse_weight);
+  if (!(y > 0.0f) || !std::isfinite(y) || !std::isfinite(y / y)) return pbr::kClassGeneral;
+  return pbr::kClassDiffuse;
+}
+
 bool HostScene::SetMaterials(const pbrgpu_material* m, uint32_t n) {
   if (n && !m) { error = "pbrgpu_set_materials: null array"; return false; }
   for (uint32_t i = 0; i < n; ++i) {
     if (m[i].type > 1) { error = "pbrgpu_set_materials: unknown material type"; return false; }
-    if (m[i].type == 0 && (m[i].tex_id[0] != PBRGPU_INVALID_ID || m[i].tex_id[1] != PBRGPU_INVALID_ID)) {
-      error = "pbrgpu_set_materials: textured materials are not supported by this backend yet";
-      return false;
-    }
+  }
+  if (committed) {   // live edit: texture ids must stay inside the committed texture table
+    for (uint32_t i = 0; i < n; ++i)
+      for (int k = 0; k < 2; ++k)
+        if (m[i].type == 0 && m[i].tex_id[k] != PBRGPU_INVALID_ID && m[i].tex_id[k] >= tex_desc.size()) {
+          error = "pbrgpu_set_materials: texture id out of range";
+          return false;
+        }
   }
   materials.assign(m, m + n);
+  material_class.resize(n);
+  for (uint32_t i = 0; i < n; ++i) material_class[i] = ClassifyMaterial(m[i]);
+  return true;
+}
+
+// Scene::AddTexture (scene.h:45-51): pixels are copied; channel count 1..4 as Texture stores them (texture.cc:10-41)
+bool HostScene::SetTextures(const pbrgpu_texture* t, uint32_t n) {
+  committed = false;
+  if (n && !t) { error = "pbrgpu_set_textures: null array"; return false; }
+  size_t total = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!t[i].pixels || t[i].width == 0 || t[i].height == 0 || t[i].channels == 0 || t[i].channels > 4) {
+      error = "pbrgpu_set_textures: empty texture or bad channel count";
+      return false;
+    }
+    total += size_t(t[i].width) * t[i].height * t[i].channels;
+  }
+  if (total > 0xffffffffull) { error = "pbrgpu_set_textures: more than 2^32 texels in total"; return false; }
+  tex_pixels.resize(total);
+  tex_desc.resize(n);
+  size_t off = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const size_t cnt = size_t(t[i].width) * t[i].height * t[i].channels;
+    memcpy(tex_pixels.data() + off, t[i].pixels, cnt * sizeof(float));
+    tex_desc[i] = {uint32_t(off), t[i].width, t[i].height, t[i].channels};
+    off += cnt;
+  }
+  return true;
+}
+
+bool HostScene::CheckTextureIds() {
+  for (const auto& m : materials)
+    for (int k = 0; k < 2; ++k)
+      if (m.type == 0 && m.tex_id[k] != PBRGPU_INVALID_ID && m.tex_id[k] >= tex_desc.size()) {
+        error = "pbrgpu_commit: texture id out of range (call pbrgpu_set_textures first)";
+        return false;
+      }
   return true;
 }
 
@@ -150,6 +212,7 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
   const auto t0 = std::chrono::steady_clock::now();
   const uint32_t nt = num_tris(), nc = num_curves();
   if (nt == 0 && nc == 0) { error = "pbrgpu_commit: empty scene"; return false; }
+  if (!CheckTextureIds()) return false;
   for (auto& id : tri_ids) {
     if (id.w != PBRGPU_INVALID_ID && id.w >= materials.size()) { error = "pbrgpu_commit: material id out of range"; return false; }
   }
@@ -180,7 +243,9 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
       float idbits;
       memcpy(&idbits, &i, 4);
       tri_data[3 * k + 0] = {a.x, a.y, a.z, idbits};
-      tri_data[3 * k + 1] = {a.x - b.x, a.y - b.y, a.z - b.z, 0.f};
+      float matbits;   // material id rides in the spare lane of e1: the closest-hit kernel routes by material class
+      memcpy(&matbits, &tri_ids[i].w, 4);
+      tri_data[3 * k + 1] = {a.x - b.x, a.y - b.y, a.z - b.z, matbits};
       tri_data[3 * k + 2] = {c.x - a.x, c.y - a.y, c.z - a.z, 0.f};
     }
   } else {
@@ -407,6 +472,11 @@ pbr::SceneView HostScene::HostView() const {
   v.curve_ids = reinterpret_cast<const uint4*>(curve_ids.data());
   v.materials = reinterpret_cast<const pbr::DeviceMaterial*>(materials.data());
   v.num_materials = uint32_t(materials.size());
+  v.material_class = material_class.data();
+  for (const auto& m : materials) v.num_hair_materials += (m.type == 1u) ? 1u : 0u;
+  v.tex_pixels = tex_pixels.data();
+  v.tex_desc = tex_desc.data();
+  v.num_textures = uint32_t(tex_desc.size());
   v.emissive = reinterpret_cast<const float4*>(emissive.data());
   v.light_cdf = light_cdf.data();
   v.lights = lights.data();

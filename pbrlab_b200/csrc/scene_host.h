@@ -24,6 +24,9 @@ struct HostScene {
   std::vector<F4> curve_cps;                               // 4 per segment, gathered
   std::vector<U4> curve_ids;
   std::vector<pbrgpu_material> materials;
+  std::vector<uint32_t> material_class;                    // per material: pbr::MaterialClass (shading queue it is routed to)
+  std::vector<float> tex_pixels;                           // all textures back to back
+  std::vector<pbr::TexDesc> tex_desc;
   // lights
   std::vector<float> light_cdf;
   std::vector<pbr::LightRec> lights;
@@ -55,6 +58,8 @@ struct HostScene {
   bool SetCurves(const float* xyzr, uint32_t nverts, const uint32_t* first_cp, const uint32_t* material_id,
                  const uint32_t* instance_id, const uint32_t* geom_id, const uint32_t* prim_id, uint64_t nsegs);
   bool SetMaterials(const pbrgpu_material* m, uint32_t n);
+  bool SetTextures(const pbrgpu_texture* t, uint32_t n);
+  bool CheckTextureIds();
   bool SetLights(const pbrgpu_light_tables* t);
   bool Commit(const float* bmin_in, const float* bmax_in);
   void BuildClearance();

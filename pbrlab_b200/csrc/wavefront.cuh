@@ -20,7 +20,9 @@
 // Index queues (u32 slot ids) are compacted with warp ballots + one atomicAdd per warp:
 //
 //   q_active[2]  slots that need a closest-hit query (ping-pong between iterations)
-//   q_surface    hit a triangle-type material (or none): emission + roulette + Principled vertex
+//   q_surface    hit a Principled material of the general class (or none): emission + roulette + Principled vertex
+//   q_diffuse    hit a Principled material that can only enable the Lambert closure (scene_host.cc: ClassifyMaterial):
+//                same vertex function with the other closures compiled out (material-sorted shading)
 //   q_hair       hit a hair material
 //   q_sss        the Principled vertex selected the random-walk closure this iteration (walk state already parked)
 //   q_walk[2]    random walks that used up their bounce budget and continue next iteration (ping-pong)
@@ -52,8 +54,8 @@ enum Counter {
   kNumActive0 = 0, kNumActive1,   // length of q_active[parity]
   kNumWalk0, kNumWalk1,           // length of q_walk[parity]
   kNumDone0, kNumDone1,           // length of q_done[parity]
-  kNumSurface, kNumHair, kNumSss, kNumExit, kNumShadow,
-  kFetchRegen, kFetchTrace, kFetchSurface, kFetchHair, kFetchSss, kFetchExit, kFetchShadow,
+  kNumSurface, kNumDiffuse, kNumHair, kNumSss, kNumExit, kNumShadow,
+  kFetchRegen, kFetchTrace, kFetchSurface, kFetchDiffuse, kFetchHair, kFetchSss, kFetchExit, kFetchShadow,
   kCounterCount
 };
 // 64-bit counters that live for a whole frame
@@ -77,6 +79,7 @@ struct WaveState {
   uint32_t* q_walk[2];
   uint32_t* q_done[2];
   uint32_t* q_surface;
+  uint32_t* q_diffuse;
   uint32_t* q_hair;
   uint32_t* q_sss;
   uint32_t* q_exit;
@@ -126,35 +129,33 @@ __device__ __forceinline__ uint32_t WarpFetch(uint32_t* fetch_counter) {
   return base + uint32_t(lane);
 }
 
-// Four queue reservations with ONE atomic instruction: lanes 0..3 each reserve the range of one queue (different
-// addresses, so the L2 handles them in parallel) instead of four dependent atomic round trips — waiting for atomic
+// Five queue reservations with ONE atomic instruction: lanes 0..4 each reserve the range of one queue (different
+// addresses, so the L2 handles them in parallel) instead of five dependent atomic round trips — waiting for atomic
 // results was 18 % of the closest-hit kernel's stall samples (profiles/r1e_ncu.md).  Issue early, resolve late:
 // whatever is issued in between overlaps the round trip.
-struct Append4 {
-  unsigned m0, m1, m2, m3;
-  uint32_t base;   // lane k < 4: first index reserved in queue k
+struct Append5 {
+  unsigned m[5];
+  uint32_t base;   // lane k < 5: first index reserved in queue k
 };
-__device__ __forceinline__ Append4 Append4Issue(uint32_t* c0, uint32_t* c1, uint32_t* c2, uint32_t* c3, bool p0,
-                                                bool p1, bool p2, bool p3) {
-  Append4 a;
-  a.m0 = __ballot_sync(0xffffffffu, p0);
-  a.m1 = __ballot_sync(0xffffffffu, p1);
-  a.m2 = __ballot_sync(0xffffffffu, p2);
-  a.m3 = __ballot_sync(0xffffffffu, p3);
+__device__ __forceinline__ Append5 Append5Issue(uint32_t* c0, uint32_t* c1, uint32_t* c2, uint32_t* c3, uint32_t* c4,
+                                                bool p0, bool p1, bool p2, bool p3, bool p4) {
+  Append5 a;
+  a.m[0] = __ballot_sync(0xffffffffu, p0);
+  a.m[1] = __ballot_sync(0xffffffffu, p1);
+  a.m[2] = __ballot_sync(0xffffffffu, p2);
+  a.m[3] = __ballot_sync(0xffffffffu, p3);
+  a.m[4] = c4 ? __ballot_sync(0xffffffffu, p4) : 0u;
   a.base = 0;
   const int lane = threadIdx.x & 31;
-  const uint32_t cnt = uint32_t(__popc(lane == 0 ? a.m0 : (lane == 1 ? a.m1 : (lane == 2 ? a.m2 : a.m3))));
-  uint32_t* ctr = lane == 0 ? c0 : (lane == 1 ? c1 : (lane == 2 ? c2 : c3));
-  if (lane < 4 && cnt) a.base = atomicAdd(ctr, cnt);
+  const unsigned mine = lane == 0 ? a.m[0] : (lane == 1 ? a.m[1] : (lane == 2 ? a.m[2] : (lane == 3 ? a.m[3] : a.m[4])));
+  const uint32_t cnt = uint32_t(__popc(mine));
+  uint32_t* ctr = lane == 0 ? c0 : (lane == 1 ? c1 : (lane == 2 ? c2 : (lane == 3 ? c3 : c4)));
+  if (lane < 5 && cnt) a.base = atomicAdd(ctr, cnt);
   return a;
 }
-__device__ __forceinline__ void Append4Resolve(const Append4& a, uint32_t* i0, uint32_t* i1, uint32_t* i2,
-                                               uint32_t* i3) {
+__device__ __forceinline__ uint32_t Append5Index(const Append5& a, int k) {
   const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
-  *i0 = __shfl_sync(0xffffffffu, a.base, 0) + uint32_t(__popc(a.m0 & lt));
-  *i1 = __shfl_sync(0xffffffffu, a.base, 1) + uint32_t(__popc(a.m1 & lt));
-  *i2 = __shfl_sync(0xffffffffu, a.base, 2) + uint32_t(__popc(a.m2 & lt));
-  *i3 = __shfl_sync(0xffffffffu, a.base, 3) + uint32_t(__popc(a.m3 & lt));
+  return __shfl_sync(0xffffffffu, a.base, k) + uint32_t(__popc(a.m[k] & lt));
 }
 
 // one 64-bit atomic per warp for a per-lane tally (kernel epilogues: 32 same-address atomics per warp otherwise)
@@ -319,6 +320,7 @@ struct ClosestClient {
   const WaveState& w;
   const FrameParams& frame;      // frame mode: retire + regenerate the slots of q_done[cur] in here
   const bool regen;
+  const bool sort_materials;     // route diffuse-only materials to their own shading queue
   const uint32_t* __restrict__ queue;
   const uint32_t* __restrict__ done;
   uint32_t n_active, n, next_parity;
@@ -328,8 +330,8 @@ struct ClosestClient {
   uint32_t rays = 0, retired = 0;
 
   __device__ __forceinline__ ClosestClient(const SceneView& s_, const WaveState& w_, uint32_t cur_parity,
-                                           const FrameParams& frame_, bool regen_)
-      : s(s_), w(w_), frame(frame_), regen(regen_), queue(w_.q_active[cur_parity]), done(w_.q_done[cur_parity]),
+                                           const FrameParams& frame_, bool regen_, bool sort_)
+      : s(s_), w(w_), frame(frame_), regen(regen_), sort_materials(sort_), queue(w_.q_active[cur_parity]), done(w_.q_done[cur_parity]),
         n_active(w_.counters[kNumActive0 + cur_parity]),
         n(w_.counters[kNumActive0 + cur_parity] + (regen_ ? w_.counters[kNumDone0 + cur_parity] : 0u)),
         next_parity(cur_parity ^ 1u),
@@ -344,8 +346,8 @@ struct ClosestClient {
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     const bool finished = !t.active && has_result;
     const bool need = !exhausted && !t.active;
-    // ---- (1) finished rays: miss -> retire, else the shading queue of the material kind
-    int kind = -1;   // -1 nothing, 0 miss, 1 surface queue, 2 hair queue
+    // ---- (1) finished rays: miss -> retire, else the shading queue of the material's class
+    int kind = -1;   // -1 nothing, 0 miss, 1 general surface queue, 2 hair queue, 3 diffuse-only queue
     const HitT hit = t.hit;
     const uint32_t done_p = p;
     if (finished) {
@@ -353,20 +355,23 @@ struct ClosestClient {
       kind = 0;
       if (hit.prim != kInvalid) {
         kind = 1;
-        if (s.num_hair_materials) {   // scene-uniform: only scenes with a hair material pay for the look-ups
-          uint32_t mat;
+        uint32_t mat = kInvalid;   // triangles carry their material id in the spare lane of e1 (scene_host.cc: Commit)
+        if (sort_materials || s.num_hair_materials) {   // scene-uniform
           if (hit.prim & kCurveFlag) mat = s.curve_ids[s.curve_prim[hit.prim & ~kCurveFlag]].w;
-          else mat = s.tri_ids[__float_as_uint(s.tri_data[hit.prim * 3].w)].w;
-          if (mat < s.num_materials && s.materials[mat].type == 1u) kind = 2;
+          else mat = __float_as_uint(s.tri_data[hit.prim * 3 + 1].w);
+        }
+        if (mat < s.num_materials) {
+          const uint32_t cls = s.material_class[mat];
+          kind = (cls == kClassHair) ? 2 : ((cls == kClassDiffuse && sort_materials) ? 3 : 1);
         }
       }
     }
-    // ---- (2) the three output queues and the work fetch: one atomic instruction
-    const Append4 app = Append4Issue(&w.counters[kNumSurface], &w.counters[kNumHair],
-                                     &w.counters[kNumDone0 + next_parity], &w.counters[kFetchTrace], kind == 1,
-                                     kind == 2, kind == 0, need);
-    uint32_t i_surf, i_hair, i_done, item;
-    Append4Resolve(app, &i_surf, &i_hair, &i_done, &item);
+    // ---- (2) the four output queues and the work fetch: one atomic instruction
+    const Append5 app = Append5Issue(&w.counters[kNumSurface], &w.counters[kNumHair],
+                                     &w.counters[kNumDone0 + next_parity], &w.counters[kFetchTrace],
+                                     &w.counters[kNumDiffuse], kind == 1, kind == 2, kind == 0, need, kind == 3);
+    const uint32_t i_surf = Append5Index(app, 0), i_hair = Append5Index(app, 1), i_done = Append5Index(app, 2),
+                   item = Append5Index(app, 3), i_diff = Append5Index(app, 4);
     // ---- (3) new work: the loads are issued here and consumed after the finished rays have been written out
     const bool take = need && item < n_active;          // a path that continues
     const bool renew = need && item >= n_active && item < n;   // a finished slot: retire it, start the next sample
@@ -386,6 +391,7 @@ struct ClosestClient {
       StSlot(w, done_p, kHitPad, make_float4(0.f, 0.f, 0.f, 0.f));   // completes the sector: no read-modify-write
       if (kind == 1) w.q_surface[i_surf] = done_p;
       else if (kind == 2) w.q_hair[i_hair] = done_p;
+      else if (kind == 3) w.q_diffuse[i_diff] = done_p;
       else w.q_done[next_parity][i_done] = done_p;
     }
     // ---- (5) start the new rays
@@ -426,8 +432,9 @@ struct ClosestClient {
 template <bool HAS_CURVES>
 __global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState w, uint32_t cur_parity,
                                                           uint32_t refill_min_idle, uint32_t prim_min_lanes,
-                                                          FrameParams frame, uint32_t regenerate) {
-  ClosestClient client(s, w, cur_parity, frame, regenerate != 0u);
+                                                          FrameParams frame, uint32_t regenerate,
+                                                          uint32_t sort_materials) {
+  ClosestClient client(s, w, cur_parity, frame, regenerate != 0u, sort_materials != 0u);
   TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle, prim_min_lanes);
 }
 
@@ -500,11 +507,17 @@ __device__ __forceinline__ void ResumeWalk(const WaveState& w, uint32_t p, SssWa
 
 // emission + MIS, roulette, material dispatch, Principled vertex.  When the vertex selects the random-walk closure
 // the walk is set up here (entry direction + coefficients, random-walk-sss.h:227-279) and parked for sss_walk.
-__global__ void __launch_bounds__(kShadeBlock) ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t next_parity,
+// Launch shapes: the general kernel needs ~110-128 registers, so one 512-thread block per SM; the diffuse-only kernel is
+// 7x smaller (2.1k vs 15.7k SASS instructions) and fits three 256-thread blocks per SM.
+constexpr int kDiffuseBlock = 256, kDiffuseBlocksPerSm = 3;
+template <bool DIFFUSE_ONLY>
+__global__ void __launch_bounds__(DIFFUSE_ONLY ? kDiffuseBlock : kShadeBlock, DIFFUSE_ONLY ? kDiffuseBlocksPerSm : 1)
+ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t next_parity,
                                                           ShadeFlags flags) {
-  const uint32_t n = w.counters[kNumSurface];
+  const uint32_t n = w.counters[DIFFUSE_ONLY ? kNumDiffuse : kNumSurface];
+  const uint32_t* __restrict__ queue = DIFFUSE_ONLY ? w.q_diffuse : w.q_surface;
   for (;;) {
-    const uint32_t slot = BlockFetch(&w.counters[kFetchSurface]);
+    const uint32_t slot = BlockFetch(&w.counters[DIFFUSE_ONLY ? kFetchDiffuse : kFetchSurface]);
     if (slot - threadIdx.x >= n) break;   // block-uniform
     const bool valid = slot < n;
     uint32_t p = 0;
@@ -513,7 +526,7 @@ __global__ void __launch_bounds__(kShadeBlock) ShadeSurfaceKernel(SceneView s, W
     req.active = false;
     vec3 throughput(0.f);
     if (valid) {
-      p = w.q_surface[slot];
+      p = queue[slot];
       PathRegs r = LoadPath(w, p);
       throughput = r.throughput;
       vec3 L = r.L;
@@ -525,16 +538,16 @@ __global__ void __launch_bounds__(kShadeBlock) ShadeSurfaceKernel(SceneView s, W
         CommitEnd(w, p, L, r.depth);
         to_done = true;
       } else {
-        const int kind = MaterialKind(s, si);
+        const int kind = DIFFUSE_ONLY ? 1 : MaterialKind(s, si);
         VertexResult vr;
         const vec3 wo = -r.ray.d;
         Frame fr;
         PrincipledBsdf bsdf;
         bool sss = false;
-        if (kind == 1) sss = PrincipledVertex(s, si, wo, &r.rng, &vr, &fr, &bsdf);
+        if (kind == 1) sss = PrincipledVertexT<DIFFUSE_ONLY>(s, si, wo, &r.rng, &vr, &fr, &bsdf);
         else AbsorbVertex(wo, si.P, &vr);   // no material (shader.cc:11-17)
         req = vr.shadow[0];
-        if (sss) {
+        if (!DIFFUSE_ONLY && sss) {
           SssWalkState walk;
           if (SssBegin(si, fr, bsdf, &r.rng, &walk)) {
             // the walk runs in its own kernel: park it, and the path with the post-roulette throughput
@@ -556,8 +569,10 @@ __global__ void __launch_bounds__(kShadeBlock) ShadeSurfaceKernel(SceneView s, W
       }
     }
     PushShadow(w, req, throughput, p);
-    const uint32_t a = WarpAppend(&w.counters[kNumSss], to_sss);
-    if (to_sss) w.q_sss[a] = p;
+    if (!DIFFUSE_ONLY) {
+      const uint32_t a = WarpAppend(&w.counters[kNumSss], to_sss);
+      if (to_sss) w.q_sss[a] = p;
+    }
     RouteSlot(w, next_parity, p, to_next, to_done);
   }
 }
@@ -663,11 +678,11 @@ struct SssClient {
     }
     // ---- (2) the three output queues and the work fetch (lanes without a walk): one atomic instruction
     const bool need = !exhausted && !t.active && !has_walk;
-    const Append4 app = Append4Issue(&w.counters[kNumExit], &w.counters[kNumDone0 + next_parity],
-                                     &w.counters[kNumWalk0 + next_parity], &w.counters[kFetchSss], to_exit, to_done,
-                                     to_park, need);
-    uint32_t i_exit, i_done, i_park, item;
-    Append4Resolve(app, &i_exit, &i_done, &i_park, &item);
+    const Append5 app = Append5Issue(&w.counters[kNumExit], &w.counters[kNumDone0 + next_parity],
+                                     &w.counters[kNumWalk0 + next_parity], &w.counters[kFetchSss], nullptr, to_exit,
+                                     to_done, to_park, need, false);
+    const uint32_t i_exit = Append5Index(app, 0), i_done = Append5Index(app, 1), i_park = Append5Index(app, 2),
+                   item = Append5Index(app, 3);
     // ---- (3) write out the walks that stopped
     if (to_exit) {
       // exit record for sss_exit: the segment ray, its hit and the walk throughput

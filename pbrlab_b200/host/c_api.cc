@@ -32,6 +32,8 @@ struct pbrhost_flat {   // views into Scene::Flat(); valid until the scene is de
   const float* materials; uint32_t nmaterials;
   pbrgpu_light_tables lights;
   float bmin[3], bmax[3];
+  const float* tex_pixels; uint64_t ntex_floats;
+  const uint32_t* tex_desc; uint32_t ntextures;   // 4 words per texture: offset (floats), width, height, channels
 };
 
 const char* pbrhost_last_error(void) { return g_error.c_str(); }
@@ -95,6 +97,8 @@ void pbrhost_scene_flat(void* s, pbrhost_flat* o) {
   o->lights.prim_is_emissive = f.lights.prim_is_emissive.data();
   o->lights.prim_triangle = f.light_prim_triangle.data();
   for (int k = 0; k < 3; ++k) { o->bmin[k] = f.bmin[k]; o->bmax[k] = f.bmax[k]; }
+  o->tex_pixels = f.tex_pixels.data(); o->ntex_floats = f.tex_pixels.size();
+  o->tex_desc = f.tex_desc.data(); o->ntextures = uint32_t(f.tex_desc.size() / 4);
 }
 
 void* pbrhost_scene_ctx(void* s) { return static_cast<pbrlab::Scene*>(s)->DeviceContext(); }
@@ -117,6 +121,15 @@ double pbrhost_render(void* s, uint32_t w, uint32_t h, uint32_t spp, uint64_t se
     g_error = e.what();
     return -1.0;
   }
+}
+
+// the CLI's output stage on the device: rgba8 [w*h*4] of the frame the last pbrhost_render left on the GPU
+int pbrhost_resolve_srgb8(void* s, uint32_t w, uint32_t h, uint8_t* rgba8) {
+  pbrgpu_ctx* ctx = static_cast<pbrlab::Scene*>(s)->DeviceContext();
+  if (!ctx) { g_error = "scene is not committed to a device"; return 1; }
+  const int rc = pbrgpu_resolve_srgb8(ctx, w, h, rgba8);
+  if (rc != PBRGPU_OK) g_error = pbrgpu_last_error(ctx);
+  return rc;
 }
 
 // Scene::TraceFirstHit1 / AnyHit1 through the C++ API (single-ray entry points of the reference)

@@ -1,11 +1,16 @@
 #include "triangle-mesh-io.h"
 
+#include <algorithm>
+#include <cctype>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <map>
 #include <memory>
+
+#include "image-io.h"
 
 namespace pbrlab {
 namespace io {
@@ -130,12 +135,83 @@ bool GetFloat3(const RawMaterial& m, const char* key, float3* out) {
   return true;
 }
 
-MaterialParameter ToPrincipled(const RawMaterial& m) {
+// tinyobj::ParseTextureNameAndOption (reference src/io/tiny_obj_loader.h:1243-1318): options first, the file name
+// is everything from the first non-option token to the end of the line (it may contain spaces).  Only -colorspace
+// matters to the caller; the other options are skipped with their arguments.
+void ParseTextureNameAndOption(const std::string& value, std::string* texname, std::string* colorspace) {
+  texname->clear();
+  colorspace->clear();
+  const char* t = value.c_str();
+  auto skip_space = [&]() { while (*t == ' ' || *t == '\t') ++t; };
+  auto skip_token = [&]() { skip_space(); while (*t && *t != ' ' && *t != '\t' && *t != '\r') ++t; };
+  auto opt = [&](const char* name) {
+    const size_t n = strlen(name);
+    if (strncmp(t, name, n) == 0 && (t[n] == ' ' || t[n] == '\t')) { t += n; return true; }
+    return false;
+  };
+  auto skip_reals = [&](int max_count) {   // parseReal / parseReal2 / parseReal3: numbers until something else
+    for (int k = 0; k < max_count; ++k) {
+      skip_space();
+      char* end = nullptr;
+      strtod(t, &end);
+      if (end == t) break;
+      t = end;
+    }
+  };
+  while (*t && *t != '\r' && *t != '\n') {
+    skip_space();
+    if (opt("-blendu") || opt("-blendv") || opt("-clamp") || opt("-type") || opt("-texres") || opt("-imfchan")) skip_token();
+    else if (opt("-boost") || opt("-bm")) skip_reals(1);
+    else if (opt("-mm")) skip_reals(2);
+    else if (opt("-o") || opt("-s") || opt("-t")) skip_reals(3);
+    else if (opt("-colorspace")) {
+      skip_space();
+      const char* b = t;
+      skip_token();
+      colorspace->assign(b, t);
+    } else {
+      *texname = std::string(t);
+      while (!texname->empty() && (texname->back() == '\r' || texname->back() == '\n')) texname->pop_back();
+      break;
+    }
+  }
+}
+
+bool IsHdr(const std::string& path) {   // reference triangle-mesh-io.cc:106-114
+  const size_t dot = path.find_last_of('.');
+  if (dot == std::string::npos) return false;
+  std::string e = path.substr(dot);
+  std::transform(e.begin(), e.end(), e.begin(), [](unsigned char c) { return char(tolower(c)); });
+  return e == ".exr" || e == ".hdr";
+}
+
+// LoadTextureFromTinyObjMaterial + LoadTexture (reference triangle-mesh-io.cc:80-141): sRGB files are converted to
+// linear at load time unless the file is HDR or `-colorspace` names something other than sRGB; a file that cannot
+// be read leaves the id at -1.
+void LoadMaterialTexture(const RawMaterial& m, const char* key, const std::string& base_dir, uint32_t* tex_id,
+                         std::vector<Texture>* textures) {
+  auto it = m.keys.find(key);
+  if (it == m.keys.end() || !textures) return;
+  std::string texname, colorspace;
+  ParseTextureNameAndOption(it->second, &texname, &colorspace);
+  const bool degamma = (colorspace.empty() || colorspace == "sRGB") && !IsHdr(texname);
+  std::vector<float> pixels;
+  size_t w = 0, h = 0, c = 0;
+  if (!LoadImageFromFile(texname, base_dir, &pixels, &w, &h, &c)) { *tex_id = uint32_t(-1); return; }
+  if (degamma) SrgbToLiner(pixels, w, h, c, &pixels);
+  *tex_id = uint32_t(textures->size());
+  textures->emplace_back(pixels, uint32_t(w), uint32_t(h), uint32_t(c), texname);
+  std::cout << "Loaded texture for " << key << " : " << texname << std::endl;
+}
+
+MaterialParameter ToPrincipled(const RawMaterial& m, const std::string& base_dir, std::vector<Texture>* textures) {
   CyclesPrincipledBsdfParameter p;
   GetFloat3(m, "base_color", &p.base_color);
+  LoadMaterialTexture(m, "map_base_color", base_dir, &p.base_color_tex_id, textures);
   GetFloat(m, "subsurface", &p.subsurface);
   GetFloat3(m, "subsurface_radius", &p.subsurface_radius);
   GetFloat3(m, "subsurface_color", &p.subsurface_color);
+  LoadMaterialTexture(m, "map_subsurface_color", base_dir, &p.subsurface_color_tex_id, textures);
   GetFloat(m, "metallic", &p.metallic);
   GetFloat(m, "specular", &p.specular);
   GetFloat(m, "specular_tint", &p.specular_tint);
@@ -149,11 +225,6 @@ MaterialParameter ToPrincipled(const RawMaterial& m) {
   GetFloat(m, "ior", &p.ior);
   GetFloat(m, "transmission", &p.transmission);
   GetFloat(m, "transmission_roughness", &p.transmission_roughness);
-  for (const char* k : {"map_base_color", "map_subsurface_color"}) {
-    if (m.keys.count(k))
-      std::cerr << "warning : material [" << m.name << "] " << k
-                << " ignored (texture sampling is not implemented in the B200 backend)" << std::endl;
-  }
   p.name = m.name;
   return MaterialParameter(p);
 }
@@ -167,7 +238,6 @@ struct ShapeBuild {
 
 bool LoadTriangleMeshFromObj(const std::string& filename, std::vector<TriangleMesh>* meshes,
                              std::vector<MaterialParameter>* material_params, std::vector<Texture>* textures) {
-  (void)textures;
   std::string text;
   if (!ReadFile(filename, &text)) {
     std::cerr << "error : cannot open [" << filename << "]" << std::endl;
@@ -295,7 +365,7 @@ bool LoadTriangleMeshFromObj(const std::string& filename, std::vector<TriangleMe
 
   meshes->clear();
   for (const ShapeBuild& s : shapes) meshes->emplace_back(s.name, attr, s.v, s.vn, s.vt, s.mat);
-  for (const RawMaterial& m : raw_materials) material_params->push_back(ToPrincipled(m));
+  for (const RawMaterial& m : raw_materials) material_params->push_back(ToPrincipled(m, base_dir, textures));
   return true;
 }
 

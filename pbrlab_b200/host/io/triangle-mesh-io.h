@@ -7,8 +7,9 @@
 //   * MTL: the Principled keys are free-form `key value...` lines; when a key repeats inside one material the FIRST
 //     occurrence wins (tinyobj keeps unknown keys in a std::map and uses insert; reference
 //     src/io/tiny_obj_loader.h:2413-2428);
-//   * map_base_color / map_subsurface_color are recognised; texture sampling is not in this backend yet, so they
-//     are reported on stderr and ignored.
+//   * map_base_color / map_subsurface_color name texture files (options as tinyobj parses them, `-colorspace`
+//     honoured); they are loaded by io/image-io.cc, de-gammaed unless HDR / non-sRGB, appended to `textures`, and the
+//     material's tex id is the index in that vector (reference src/io/triangle-mesh-io.cc:80-141).
 #ifndef PBRLAB_B200_TRIANGLE_MESH_IO_H_
 #define PBRLAB_B200_TRIANGLE_MESH_IO_H_
 #include <string>

@@ -1,7 +1,8 @@
 // Command-line front-end: the reference's pbrlab-cli (reference pc/pbrlab-cli.cc:16-60) with the three values it
 // hard-codes (512 x 512, 32 spp) exposed as flags, plus a raw dump for the parity tests.
-//   pbrlab-cli [--width W] [--height H] [--spp N] [--seed S] [--gpus N] [--raw out.bin] [--ppm out.ppm] files...
-// Writes ./rgba.ppm (8-bit sRGB, same tone mapping as the reference's rgba.png: clamp(srgb(v) * 256, 0, 255)).
+//   pbrlab-cli [--width W] [--height H] [--spp N] [--seed S] [--gpus N] [--raw out.bin] [--png out.png] [--ppm out.ppm] files...
+// Writes ./rgba.png like the reference: colour = rgba / count -> LinerToSrgb -> 8 bit (pc/pbrlab-cli.cc:47-57), the
+// output stage running on the device (pbrgpu_resolve_srgb8) so only 4 bytes per pixel come back for the file.
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -16,16 +17,13 @@
 #include "pc-common.h"
 #include "render.h"
 
-static float LinearToSrgb(float v) {   // reference src/image-utils.cc:26-38
-  if (v <= 0.0031308f) return 12.92f * v;
-  return 1.055f * std::pow(v, 1.0f / 2.4f) - 0.055f;
-}
+#include "io/image-io.h"
 
 int main(int argc, char** argv) {
   uint32_t width = 512, height = 512, spp = 32;
   uint64_t seed = 1234567890ull;
   int gpus = 1;
-  std::string raw_path, ppm_path = "rgba.ppm";
+  std::string raw_path, ppm_path, png_path = "rgba.png";
   std::vector<char*> files;
   files.push_back(argv[0]);
   for (int i = 1; i < argc; ++i) {
@@ -41,6 +39,7 @@ int main(int argc, char** argv) {
     else if (a == "--gpus") gpus = atoi(next("--gpus"));
     else if (a == "--raw") raw_path = next("--raw");
     else if (a == "--ppm") ppm_path = next("--ppm");
+    else if (a == "--png") png_path = next("--png");
     else files.push_back(argv[i]);
   }
   if (files.size() < 2) {
@@ -93,21 +92,27 @@ int main(int argc, char** argv) {
       fclose(fp);
     }
   }
-  // color = rgba / count -> sRGB -> 8 bit (reference pc/pbrlab-cli.cc:47-57, src/io/image-io.cc WritePNG)
-  FILE* fp = fopen(ppm_path.c_str(), "wb");
-  if (!fp) return EXIT_FAILURE;
-  fprintf(fp, "P6\n%u %u\n255\n", width, height);
-  std::vector<unsigned char> row(size_t(width) * 3);
-  for (uint32_t y = 0; y < height; ++y) {
-    for (uint32_t x = 0; x < width; ++x) {
-      const size_t i = size_t(y) * width + x;
-      for (int c = 0; c < 3; ++c) {
-        const float v = LinearToSrgb(layer.rgba[i * 4 + c] / float(layer.count[i]));
-        row[x * 3 + c] = static_cast<unsigned char>(std::max(0.0f, std::min(255.0f, v * 256.0f)));
-      }
-    }
-    fwrite(row.data(), 1, row.size(), fp);
+  // color = rgba / count -> sRGB -> 8 bit (reference pc/pbrlab-cli.cc:47-57, src/io/image-io.cc WritePNG), on the device
+  std::vector<unsigned char> rgba8(size_t(width) * height * 4);
+  if (pbrgpu_resolve_srgb8(scene.DeviceContext(), width, height, rgba8.data()) != PBRGPU_OK) {
+    std::cerr << pbrgpu_last_error(scene.DeviceContext()) << std::endl;
+    return EXIT_FAILURE;
   }
-  fclose(fp);
+  if (!png_path.empty() && !pbrlab::io::WritePNG8(png_path, rgba8.data(), width, height, 4)) {
+    std::cerr << "faild save image" << std::endl;
+    return EXIT_FAILURE;
+  }
+  if (!ppm_path.empty()) {
+    FILE* fp = fopen(ppm_path.c_str(), "wb");
+    if (!fp) return EXIT_FAILURE;
+    fprintf(fp, "P6\n%u %u\n255\n", width, height);
+    std::vector<unsigned char> row(size_t(width) * 3);
+    for (uint32_t y = 0; y < height; ++y) {
+      for (uint32_t x = 0; x < width; ++x)
+        for (int c = 0; c < 3; ++c) row[x * 3 + c] = rgba8[(size_t(y) * width + x) * 4 + c];
+      fwrite(row.data(), 1, row.size(), fp);
+    }
+    fclose(fp);
+  }
   return EXIT_SUCCESS;
 }

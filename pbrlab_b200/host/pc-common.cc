@@ -21,6 +21,15 @@ bool AddObj(const std::string& path, pbrlab::Scene* scene) {
     return false;
   }
   std::cerr << "Load obj file [" << path << "]" << std::endl;
+  // file-local texture index -> scene texture id (reference pc/pc-common.cc:93-98,122-140)
+  std::vector<uint32_t> texture_ids;
+  for (const auto& t : textures) texture_ids.push_back(scene->AddTexture(t));
+  for (auto& m : materials) {
+    if (m.index() != pbrlab::kCyclesPrincipledBsdfParameter) continue;
+    auto& p = std::get<pbrlab::kCyclesPrincipledBsdfParameter>(m);
+    if (p.base_color_tex_id != uint32_t(-1)) p.base_color_tex_id = texture_ids.at(p.base_color_tex_id);
+    if (p.subsurface_color_tex_id != uint32_t(-1)) p.subsurface_color_tex_id = texture_ids.at(p.subsurface_color_tex_id);
+  }
   std::vector<uint32_t> material_ids;
   for (const auto& m : materials) material_ids.push_back(scene->AddMaterialParam(m));
   std::cerr << "The Number of shapes is " << meshes.size() << " in [" << path << "]" << std::endl;

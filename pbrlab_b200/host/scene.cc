@@ -236,6 +236,13 @@ void Scene::CommitHostOnly(void) {
     for (uint32_t p = 0; p < n; ++p) f.light_prim_triangle.push_back(base + p);
   }
   PackMaterials(&f.materials);
+  for (const auto& tex : textures_) {
+    f.tex_desc.push_back(uint32_t(f.tex_pixels.size()));
+    f.tex_desc.push_back(tex->GetWidth());
+    f.tex_desc.push_back(tex->GetHeight());
+    f.tex_desc.push_back(tex->GetChannels());
+    f.tex_pixels.insert(f.tex_pixels.end(), tex->GetPixels().begin(), tex->GetPixels().end());
+  }
   for (int c = 0; c < 3; ++c) { f.bmin[c] = bmin_[c] = lo[c]; f.bmax[c] = bmax_[c] = hi[c]; }
 }
 
@@ -249,6 +256,13 @@ void Scene::CommitScene(void) {
   auto check = [this](int rc) {
     if (rc != PBRGPU_OK) throw std::runtime_error(std::string("pbrlab: device upload failed: ") + pbrgpu_last_error(ctx_));
   };
+  std::vector<pbrgpu_texture> tex(f.tex_desc.size() / 4);
+  for (size_t i = 0; i < tex.size(); ++i) {
+    tex[i].pixels = f.tex_pixels.data() + f.tex_desc[4 * i];
+    tex[i].width = f.tex_desc[4 * i + 1]; tex[i].height = f.tex_desc[4 * i + 2]; tex[i].channels = f.tex_desc[4 * i + 3];
+    tex[i].reserved = 0;
+  }
+  check(pbrgpu_set_textures(ctx_, tex.data(), uint32_t(tex.size())));
   check(pbrgpu_set_materials(ctx_, reinterpret_cast<const pbrgpu_material*>(f.materials.data()),
                              uint32_t(f.materials.size() / 28)));
   check(pbrgpu_set_triangles(ctx_, f.verts.data(), uint32_t(f.verts.size() / 4), f.vidx.data(), f.normals.data(),

@@ -37,6 +37,8 @@ struct FlatScene {
   std::vector<float> curve_verts;                                 // xyzr
   std::vector<uint32_t> curve_first, curve_material, curve_instance, curve_geom, curve_prim;
   std::vector<float> materials;                                   // 28 words per material (pbrgpu_material)
+  std::vector<float> tex_pixels;                                  // all textures back to back
+  std::vector<uint32_t> tex_desc;                                 // per texture: offset (floats), width, height, channels
   LightManager::Tables lights;
   std::vector<uint32_t> light_prim_triangle;                      // per light primitive: flattened triangle index
   float bmin[3], bmax[3];

@@ -65,6 +65,9 @@ int emul_set_curves(void* h, const float* xyzr, uint32_t nverts, const uint32_t*
 int emul_set_materials(void* h, const pbrgpu_material* m, uint32_t n) {
   return static_cast<Emul*>(h)->scene.SetMaterials(m, n) ? 0 : 1;
 }
+int emul_set_textures(void* h, const pbrgpu_texture* t, uint32_t n) {
+  return static_cast<Emul*>(h)->scene.SetTextures(t, n) ? 0 : 1;
+}
 int emul_set_lights(void* h, const pbrgpu_light_tables* t) { return static_cast<Emul*>(h)->scene.SetLights(t) ? 0 : 1; }
 int emul_commit(void* h, const float* bmin, const float* bmax) {
   Emul* e = static_cast<Emul*>(h);
