@@ -14,6 +14,7 @@
 // closure-level known-answer vectors.
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -331,6 +332,29 @@ REF_API int ref_obj_material(void* h, int i, float* p23, uint32_t* tex2, char* n
   tex2[0] = m.base_color_tex_id; tex2[1] = m.subsurface_color_tex_id;
   if (name) { strncpy(name, m.name.c_str(), size_t(name_cap - 1)); name[name_cap - 1] = 0; }
   return 0;
+}
+// textures the OBJ loader produced (src/io/triangle-mesh-io.cc:80-141): call with pixels == nullptr for the sizes
+REF_API int ref_obj_num_textures(void* h) { return int(static_cast<ObjData*>(h)->textures.size()); }
+REF_API void ref_obj_texture(void* h, int i, uint32_t* whc, float* pixels) {
+  const Texture& t = static_cast<ObjData*>(h)->textures[size_t(i)];
+  whc[0] = t.GetWidth(); whc[1] = t.GetHeight(); whc[2] = t.GetChannels();
+  if (!pixels) return;
+  // Texture keeps its pixels private; read them back through FetchFloatN at the texel origins, where the bilinear
+  // weights are exactly (1, 0, 0, 0): px = width * u must land on the integer x, so u = x / width is checked
+  for (uint32_t y = 0; y < whc[1]; ++y)
+    for (uint32_t x = 0; x < whc[0]; ++x) {
+      float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+      float u = float(x) / float(whc[0]), v = float(y) / float(whc[1]);
+      if (float(whc[0]) * u != float(x)) u = std::nextafter(u, float(whc[0]) * u < float(x) ? 2.0f : -1.0f);
+      if (float(whc[1]) * v != float(y)) v = std::nextafter(v, float(whc[1]) * v < float(y) ? 2.0f : -1.0f);
+      t.FetchFloatN(u, v, whc[2], tmp);
+      for (uint32_t c = 0; c < whc[2]; ++c) pixels[(size_t(y) * whc[0] + x) * whc[2] + c] = tmp[c];
+    }
+}
+// Texture::FetchFloat3 at arbitrary coordinates (src/texture.cc:43-72)
+REF_API void ref_obj_texture_fetch3(void* h, int i, const float* uv, uint64_t n, float* out) {
+  const Texture& t = static_cast<ObjData*>(h)->textures[size_t(i)];
+  for (uint64_t k = 0; k < n; ++k) t.FetchFloat3(uv[2 * k], uv[2 * k + 1], out + 3 * k);
 }
 // CyHair -> cubic Bezier (src/io/curve-mesh-io.cc:32-121), memory_saving_mode=false as the CLI uses.
 // call with vt==nullptr to query sizes.

@@ -185,3 +185,146 @@ def displaced(n_tris=20_000_000, seed=7):
         write_displaced_obj(path, n_tris, seed)
         open(done, "w").close()
     return path
+
+
+# ---------------------------------------------------------------- textured scene
+def _png_chunk(tag, data):
+    import zlib
+    return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+
+def write_png(path, img, palette=None, trns=None):
+    """Minimal PNG encoder for the test textures: img (h, w[, c]) uint8 or uint16; rows cycle through the five PNG
+    filter types so that a decoder's un-filtering is exercised.  palette (n,3) uint8 -> colour type 3."""
+    import zlib
+    img = np.asarray(img)
+    if img.ndim == 2:
+        img = img[..., None]
+    h, w, c = img.shape
+    depth = 16 if img.dtype == np.uint16 else 8
+    ctype = 3 if palette is not None else {1: 0, 2: 4, 3: 2, 4: 6}[c]
+    raw = img.astype(">u2").tobytes() if depth == 16 else img.astype(np.uint8).tobytes()
+    bpp = c * depth // 8
+    stride = w * bpp
+    rows = [np.frombuffer(raw[y * stride:(y + 1) * stride], np.uint8).astype(np.int32) for y in range(h)]
+    out = bytearray()
+    prev = np.zeros(stride, np.int32)
+    for y, cur in enumerate(rows):
+        ft = y % 5
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        cc = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        if ft == 0: f = cur
+        elif ft == 1: f = cur - a
+        elif ft == 2: f = cur - prev
+        elif ft == 3: f = cur - ((a + prev) >> 1)
+        else:
+            p = a + prev - cc
+            pa, pb, pc = np.abs(p - a), np.abs(p - prev), np.abs(p - cc)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, cc))
+            f = cur - pred
+        out.append(ft)
+        out += (f & 0xFF).astype(np.uint8).tobytes()
+        prev = cur
+    data = b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    if palette is not None:
+        data += _png_chunk(b"PLTE", np.asarray(palette, np.uint8).tobytes())
+    if trns is not None:
+        data += _png_chunk(b"tRNS", bytes(trns))
+    data += _png_chunk(b"IDAT", zlib.compress(bytes(out), 6)) + _png_chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(data)
+    return path
+
+
+def write_textured_obj(path, seed=5):
+    """A small lit box whose materials use map_base_color / map_subsurface_color (the two texture slots the
+    reference's Principled path samples, cycles-principled-shader.cc:281-301): floor with an sRGB RGB8 checker and
+    texcoords running outside [0,1] (clamp addressing), back wall with an RGBA8 gradient declared `-colorspace linear`,
+    a pedestal with a palette PNG on a glossy material, a box with a binary PPM, and a subsurface sphere whose
+    subsurface colour comes from a 1-channel PNG (channels a texture lacks read as 0)."""
+    rng = np.random.default_rng(seed)
+    d = os.path.dirname(path)
+    checker = np.zeros((48, 64, 3), np.uint8)
+    cols = rng.integers(40, 255, size=(6, 8, 3))
+    for j in range(6):
+        for i in range(8):
+            checker[j * 8:(j + 1) * 8, i * 8:(i + 1) * 8] = cols[j, i]
+    checker = (checker * (0.6 + 0.4 * np.linspace(0, 1, 64)[None, :, None])).astype(np.uint8)
+    write_png(os.path.join(d, "tex_checker.png"), checker)
+    gy, gx = np.mgrid[0:32, 0:32]
+    grad = np.stack([gx * 8, gy * 8, 255 - gx * 4 - gy * 4, 128 + gx * 0], -1).clip(0, 255).astype(np.uint8)
+    write_png(os.path.join(d, "tex grad rgba.png"), grad)          # file name with spaces (tinyobj reads to line end)
+    pal = rng.integers(0, 255, size=(16, 3)).astype(np.uint8)
+    write_png(os.path.join(d, "tex_palette.png"), rng.integers(0, 16, size=(16, 16)).astype(np.uint8), palette=pal)
+    skin = (128 + 100 * np.sin(gx / 5.0) * np.cos(gy / 7.0)).astype(np.uint8)
+    write_png(os.path.join(d, "tex_skin_gray.png"), skin)
+    wood = (rng.integers(60, 200, size=(20, 24, 1)) * np.array([1.0, 0.7, 0.4])).astype(np.uint8)
+    with open(os.path.join(d, "tex_wood.ppm"), "wb") as f:
+        f.write(b"P6\n# test texture\n24 20\n255\n" + wood.tobytes())
+    deep = (rng.integers(0, 65535, size=(8, 8, 3))).astype(np.uint16)
+    write_png(os.path.join(d, "tex_deep16.png"), deep)
+    mtl = os.path.splitext(path)[0] + ".mtl"
+    with open(mtl, "w") as f:
+        f.write("newmtl Floor\nbase_color 0.5 0.5 0.5\nmap_base_color tex_checker.png\nspecular 0.0\n\n"
+                "newmtl Back\nbase_color 0.5 0.5 0.5\nmap_base_color -colorspace linear -clamp on tex grad rgba.png\nspecular 0.0\n\n"
+                "newmtl Glossy\nbase_color 0.8 0.8 0.8\nmap_base_color -bm 1.0 tex_palette.png\nspecular 1.0\nroughness 0.25\n\n"
+                "newmtl Wood\nbase_color 0.2 0.2 0.2\nmap_base_color tex_wood.ppm\nspecular 0.3\nroughness 0.5\n\n"
+                "newmtl Skin\nbase_color 0.8 0.6 0.5\nsubsurface 1.0\nsubsurface_radius 0.3 0.2 0.1\n"
+                "subsurface_color 0.9 0.6 0.5\nmap_subsurface_color tex_skin_gray.png\nspecular 0.5\nroughness 0.3\n\n"
+                "newmtl Deep\nbase_color 0.3 0.3 0.3\nmap_base_color tex_deep16.png\nspecular 0.0\n\n"
+                "newmtl Missing\nbase_color 0.6 0.2 0.2\nmap_base_color no_such_file.png\nspecular 0.0\n\n"
+                "newmtl Light\nbase_color 0.0 0.0 0.0\nspecular 0.0\n")
+    with open(path, "w") as f:
+        f.write("mtllib %s\n" % os.path.basename(mtl))
+        nv = [0]; nt = [0]; nn = [0]
+
+        def quad(name, mat, P, T=None):
+            f.write("o %s\n" % name)
+            for p in P:
+                f.write("v %f %f %f\n" % tuple(p))
+            if T is not None:
+                for t in T:
+                    f.write("vt %f %f\n" % tuple(t))
+            f.write("usemtl %s\n" % mat)
+            b, tb = nv[0] + 1, nt[0] + 1
+            if T is not None:
+                f.write("f %d/%d %d/%d %d/%d\nf %d/%d %d/%d %d/%d\n" % (b, tb, b + 1, tb + 1, b + 2, tb + 2, b, tb, b + 2, tb + 2, b + 3, tb + 3))
+                nt[0] += 4
+            else:
+                f.write("f %d %d %d\nf %d %d %d\n" % (b, b + 1, b + 2, b, b + 2, b + 3))
+            nv[0] += 4
+
+        S = 4.0
+        quad("floor", "Floor", [(-S, 0, S), (S, 0, S), (S, 0, -S), (-S, 0, -S)], [(-0.2, -0.1), (1.3, -0.1), (1.3, 1.2), (-0.2, 1.2)])
+        quad("back", "Back", [(-S, 0, -S), (S, 0, -S), (S, 2 * S, -S), (-S, 2 * S, -S)], [(0, 0), (1, 0), (1, 1), (0, 1)])
+        quad("left", "Deep", [(-S, 0, S), (-S, 0, -S), (-S, 2 * S, -S), (-S, 2 * S, S)], [(0, 0), (1, 0), (1, 1), (0, 1)])
+        quad("right", "Missing", [(S, 0, -S), (S, 0, S), (S, 2 * S, S), (S, 2 * S, -S)], [(0, 0), (1, 0), (1, 1), (0, 1)])
+        quad("pedestal", "Glossy", [(-3, 1.0, 1), (-1, 1.0, 1), (-1, 1.0, -1), (-3, 1.0, -1)], [(0, 0), (1, 0), (1, 1), (0, 1)])
+        quad("plank", "Wood", [(1, 0.6, 2), (3, 0.9, 2), (3, 0.9, 0.5), (1, 0.6, 0.5)])      # no texcoords: barycentrics
+        quad("light_top", "Light", [(-1.5, 2 * S - 0.01, -1.5), (1.5, 2 * S - 0.01, -1.5), (1.5, 2 * S - 0.01, 1.5), (-1.5, 2 * S - 0.01, 1.5)])
+        # uv sphere with normals and texcoords
+        nu, nvv = 48, 24
+        th = np.linspace(0, np.pi, nvv + 1)[:, None]; ph = np.linspace(0, 2 * np.pi, nu + 1)[None, :]
+        dirs = np.stack([np.sin(th) * np.cos(ph), np.cos(th) * np.ones_like(ph), np.sin(th) * np.sin(ph)], -1)
+        P = np.array([0.8, 3.0, -0.5]) + 1.3 * dirs
+        f.write("o ball\n")
+        np.savetxt(f, P.reshape(-1, 3), fmt="v %.6f %.6f %.6f")
+        np.savetxt(f, dirs.reshape(-1, 3), fmt="vn %.6f %.6f %.6f")
+        uv = np.stack([np.broadcast_to(ph / (2 * np.pi), dirs.shape[:2]), np.broadcast_to(1 - th / np.pi, dirs.shape[:2])], -1)
+        np.savetxt(f, uv.reshape(-1, 2), fmt="vt %.6f %.6f")
+        f.write("usemtl Skin\n")
+        b, tb = nv[0] + 1, nt[0] + 1
+        for j in range(nvv):
+            for i in range(nu):
+                a0 = j * (nu + 1) + i; a1 = a0 + 1; a2 = a0 + nu + 1; a3 = a2 + 1
+                if j > 0:
+                    f.write("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % (b + a0, tb + a0, a0 + 1, b + a1, tb + a1, a1 + 1, b + a3, tb + a3, a3 + 1))
+                if j < nvv - 1:
+                    f.write("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % (b + a0, tb + a0, a0 + 1, b + a3, tb + a3, a3 + 1, b + a2, tb + a2, a2 + 1))
+    return path
+
+
+def textured():
+    path = _cache("textured_box.obj")
+    write_textured_obj(path)
+    return path

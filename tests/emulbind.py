@@ -38,6 +38,18 @@ class Emul:
         self.lib.emul_scene_bounds(self.h, _p(a), _p(b))
         return a, b
 
+    def texture_fetch3(self, tex, uv):
+        uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros((len(uv), 3), np.float32)
+        rc = self.lib.emul_texture_fetch3(self.h, C.c_uint32(tex), _p(uv), C.c_uint64(len(uv)), _p(out))
+        assert rc == 0
+        return out
+
+    def material_classes(self):
+        out = np.zeros(4096, np.uint32)
+        n = self.lib.emul_material_classes(self.h, _p(out))
+        return out[:n]
+
     def bvh_info(self):
         o = np.zeros(6, np.float64)
         self.lib.emul_bvh_info(self.h, _p(o))

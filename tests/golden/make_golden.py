@@ -174,9 +174,40 @@ def hair():
     save("hair_bounds.npz", bmin=b0, bmax=b1)
 
 
+# ---------------------------------------------------------------- textured scene: loader textures, fetches, vertices, paths
+def textured():
+    obj = scenes.textured()
+    L = R.obj_load(obj)
+    out = {"num_textures": np.array([L.num_textures()], np.uint32)}
+    uv = np.concatenate([rng.uniform(-0.3, 1.3, (2048, 2)), [[0, 0], [1, 1], [0.5, 1.0], [1.0, 0.25], [-1, 2]]]).astype(np.float32)
+    out["fetch_uv"] = uv
+    for i in range(L.num_textures()):
+        out["tex_%d" % i] = L.texture(i)
+        out["fetch_%d" % i] = L.texture_fetch3(i, uv)
+    mats = []
+    for i in range(L.num_materials()):
+        kind, p, tex, name = L.material(i)
+        mats.append(np.concatenate([p, tex.astype(np.float64)]))
+    out["materials"] = np.array(mats, np.float64)
+    S = R.scene([obj])
+    n = 20000
+    rays = common.camera_rays(S.camera(512, 512), n, rng)
+    f, ids = S.trace(pb.rays_to_f8(rays))
+    surf = S.surface(pb.rays_to_f8(rays))
+    seeds = np.stack([rng.integers(0, 2**62, n, dtype=np.uint64), rng.integers(0, 2**62, n, dtype=np.uint64)], 1)
+    shade = S.shade(pb.rays_to_f8(rays), seeds)
+    rad = S.radiance(pb.rays_to_f8(rays), seeds)
+    save("textured_scene.npz", rays=pb.rays_to_f8(rays), hit_f=f, hit_ids=ids, occluded=S.occluded(pb.rays_to_f8(rays)),
+         surface=surf, seeds=seeds, shade=shade, radiance=rad, **out)
+
+
 if __name__ == "__main__":
+    if "--textured-only" in sys.argv:
+        textured()
+        sys.exit(0)
     kat()
     S = cornell()
     hair()
+    textured()
     if "--image" in sys.argv:
         image(S)

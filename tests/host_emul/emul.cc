@@ -68,6 +68,21 @@ int emul_set_materials(void* h, const pbrgpu_material* m, uint32_t n) {
 int emul_set_textures(void* h, const pbrgpu_texture* t, uint32_t n) {
   return static_cast<Emul*>(h)->scene.SetTextures(t, n) ? 0 : 1;
 }
+// Texture::FetchFloat3 through the device function
+int emul_texture_fetch3(void* h, uint32_t tex, const float* uv, uint64_t n, float* out) {
+  Emul* e = static_cast<Emul*>(h);
+  if (tex >= e->view.num_textures) return 1;
+  for (uint64_t k = 0; k < n; ++k) {
+    const pbr::vec3 c = pbr::TextureFetch3(e->view, tex, uv[2 * k], uv[2 * k + 1]);
+    out[3 * k] = c.x; out[3 * k + 1] = c.y; out[3 * k + 2] = c.z;
+  }
+  return 0;
+}
+int emul_material_classes(void* h, uint32_t* out) {
+  Emul* e = static_cast<Emul*>(h);
+  for (size_t i = 0; i < e->scene.material_class.size(); ++i) out[i] = e->scene.material_class[i];
+  return int(e->scene.material_class.size());
+}
 int emul_set_lights(void* h, const pbrgpu_light_tables* t) { return static_cast<Emul*>(h)->scene.SetLights(t) ? 0 : 1; }
 int emul_commit(void* h, const float* bmin, const float* bmax) {
   Emul* e = static_cast<Emul*>(h);

@@ -204,6 +204,24 @@ class RefObj:
         return kind, p, tex, name.value.decode()
 
 
+    def num_textures(self):
+        return int(self.ref.lib.ref_obj_num_textures(self.h))
+
+    def texture(self, i):
+        """(h, w, c) float pixels of texture i as the reference's loader left them (de-gammaed where it does)"""
+        whc = np.zeros(3, np.uint32)
+        self.ref.lib.ref_obj_texture(self.h, C.c_int(i), _fp(whc), None)
+        px = np.zeros((int(whc[1]), int(whc[0]), int(whc[2])), np.float32)
+        self.ref.lib.ref_obj_texture(self.h, C.c_int(i), _fp(whc), _fp(px))
+        return px
+
+    def texture_fetch3(self, i, uv):
+        uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros((len(uv), 3), np.float32)
+        self.ref.lib.ref_obj_texture_fetch3(self.h, C.c_int(i), _fp(uv), C.c_uint64(len(uv)), _fp(out))
+        return out
+
+
 class RefScene:
     def __init__(self, ref, h):
         self.ref, self.h = ref, C.c_void_p(h)

@@ -1,0 +1,121 @@
+"""Textures: the two texture slots the reference's Principled path samples — map_base_color and
+map_subsurface_color (reference src/shader/cycles-principled-shader.cc:281-301) — from image file to shaded vertex.
+Fixtures: tests/golden/textured_scene.npz, generated from the compiled reference on the scene
+pbrlab_b200.scenes.textured() writes (RGB8 / RGBA8 / palette / grey / 16-bit PNGs, a binary PPM, a missing file,
+`-colorspace linear`, a file name with spaces, texcoords outside [0,1], a shape without texcoords).
+CPU tests: loader, Texture::FetchFloat3, the g++ emulation of the device shading code, the restated oracle.
+GPU tests (marked): the CUDA path through the C ABI against the same fixture."""
+import numpy as np
+import pytest
+
+import checks
+import common
+import pbrlab_b200 as pb
+from pbrlab_b200 import scenes
+from conftest import golden
+
+
+@pytest.fixture(scope="module")
+def textured_host(built):
+    return pb.Scene([scenes.textured()], commit_to_device=False)
+
+
+def test_loader_textures_match_reference(textured_host):
+    """decoded + de-gammaed pixels, channel counts and material texture ids equal the reference loader's"""
+    g = golden("textured_scene.npz")
+    f = textured_host.flat()
+    n = int(g["num_textures"][0])
+    assert len(f.tex_desc) == n == 6
+    for i, (off, w, h, c) in enumerate(f.tex_desc):
+        ref = g["tex_%d" % i]
+        assert ref.shape == (h, w, c), (i, ref.shape, (h, w, c))
+        ours = f.tex_pixels[off:off + w * h * c].reshape(h, w, c)
+        assert np.abs(ours - ref).max() <= 2e-7, (i, np.abs(ours - ref).max())   # pow() of the two libms: last ulp
+    mats = g["materials"]
+    words = f.materials
+    assert len(words) == len(mats)
+    for k in range(len(mats)):
+        assert np.array_equal(words[k, 4:27].view(np.float32), mats[k, :23].astype(np.float32))
+        assert int(words[k, 1]) == int(mats[k, 23]) and int(words[k, 2]) == int(mats[k, 24])
+    # the unreadable file leaves the slot empty (reference triangle-mesh-io.cc:80-92)
+    assert int(words[6, 1]) == pb.INVALID and int(words[6, 2]) == pb.INVALID
+
+
+def test_texture_fetch_is_bilinear_clamp(textured_host):
+    """Texture::FetchFloat3 known answers (incl. coordinates outside [0,1] and exactly 1.0) through the g++ build of
+    the device function"""
+    import emulbind
+    g = golden("textured_scene.npz")
+    e = emulbind.Emul(textured_host.flat())
+    for i in range(6):
+        got = e.texture_fetch3(i, g["fetch_uv"])
+        assert np.abs(got - g["fetch_%d" % i]).max() <= 1e-6, i
+
+
+def test_emulated_device_shading_on_textured_scene(textured_host):
+    import emulbind
+    g = golden("textured_scene.npz")
+    e = emulbind.Emul(textured_host.flat())
+    assert checks.check_rays(e, g) >= 0.9999
+    rays = common.rays_from_f8(g["rays"])
+    a = e.surface(rays); b = g["surface"]
+    hit = b[:, 11] >= 0
+    assert np.abs(a[hit, 9:11] - b[hit, 9:11]).max() < 1e-5       # interpolated texcoords
+    assert checks.check_shade(e, g, min_agree=0.995) >= 0.995
+    assert checks.check_radiance(e, g, min_agree=0.99) >= 0.99
+
+
+def test_oracle_port_on_textured_scene(textured_host):
+    import oraclebind
+    if not oraclebind.available():
+        pytest.skip("oracle/libpbr_oracle.so not built")
+    g = golden("textured_scene.npz")
+    o = oraclebind.Oracle(textured_host.flat())
+    assert checks.check_radiance(o, g, min_agree=0.99) >= 0.99
+
+
+def test_material_classes(textured_host, cornell_host):
+    """routing table of the material-sorted shading queues: only Principled materials that can enable nothing but
+    the Lambert closure, whatever the hit, are 'diffuse only' — never a textured one, never one with specular > 0"""
+    import emulbind
+    e = emulbind.Emul(textured_host.flat())
+    assert list(e.material_classes()) == [0, 0, 0, 0, 0, 0, 1, 0]   # only "Missing" (constant colour, specular 0); Light has no closure
+    c = emulbind.Emul(cornell_host.flat()).material_classes()
+    names = {m["name"]: i for i, m in enumerate(__import__("json").load(open(__import__("os").path.join(
+        __import__("conftest").GOLDEN, "cornell_loader.json")))["materials"])}
+    assert c[names["Lucy"]] == 0 and c[names["Monkey"]] == 0 and c[names["Light"]] == 0
+    assert sum(int(x) for x in c) == len(c) - 3                     # every other Cornell material is diffuse only
+
+
+@pytest.mark.gpu
+def test_gpu_textured_scene(built):
+    g = golden("textured_scene.npz")
+    S = pb.Scene([scenes.textured()])
+    ctx = S.context()
+    assert checks.check_rays(ctx, g) >= 0.9999
+    assert checks.check_shade(ctx, g, min_agree=0.995) >= 0.995
+    assert checks.check_radiance(ctx, g, min_agree=0.99) >= 0.99
+    # wavefront (material-sorted queues) and the one-thread-per-path megakernel run the same vertices
+    rays = common.rays_from_f8(g["rays"])
+    a = ctx.radiance(rays, g["seeds"]); b = ctx.radiance(rays, g["seeds"], mega=True)
+    assert common.path_agreement(a, b) >= 0.995
+    rgba, count, _ = S.render(96, 96, 16)
+    assert np.all(count == 16) and not np.isnan(rgba).any() and rgba[..., :3].sum() > 0
+
+
+@pytest.mark.gpu
+def test_gpu_output_stage_matches_reference_formula(cornell_gpu):
+    """pbrgpu_resolve_srgb8 = rgba / count -> LinerToSrgb -> (unsigned char)clamp(v * 256, 0, 255)
+    (reference pc/pbrlab-cli.cc:47-57, src/image-utils.cc:24-36, src/io/image-io.cc:200-206)"""
+    S, ctx = cornell_gpu
+    rgba, count, _ = S.render(160, 120, 8)
+    got = ctx.resolve_srgb8(160, 120)
+    mean = rgba / count[..., None].astype(np.float32)
+    c = mean[..., :3]
+    srgb = np.where(c <= np.float32(0.0031308), np.float32(12.92) * c,
+                    np.power(np.float32(1.055) * c, np.float32(1.0 / 2.4), dtype=np.float32) - np.float32(0.055))
+    want = np.concatenate([srgb, mean[..., 3:]], -1)
+    want8 = np.clip(want * np.float32(256.0), 0, 255).astype(np.uint8)
+    diff = np.abs(got.astype(np.int32) - want8.astype(np.int32))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3              # powf of two libms: a quantisation edge at most
+    assert np.all(got[..., 3] == 255)
