@@ -84,7 +84,7 @@ def check_rays(impl, g, min_agree=0.9999):
     return float(same.mean())
 
 
-def check_shade(impl, g, min_agree):
+def check_shade(impl, g, min_agree, subset=None):
     """one shading vertex = Shader(): wi, throughput, NEE contribution, pdf, next origin"""
     rays = common.rays_from_f8(g["rays"])
     a = impl.shade(rays, g["seeds"]); b = g["shade"]
@@ -94,6 +94,8 @@ def check_shade(impl, g, min_agree):
     for sl in (slice(1, 4), slice(4, 7), slice(7, 10), slice(10, 11), slice(11, 14)):
         scale = np.maximum(1.0, np.abs(b[:, sl]).max(axis=1))
         ok &= np.abs(a[:, sl] - b[:, sl]).max(axis=1) <= 1e-4 * scale
+    if subset is not None:
+        hit = hit & subset
     frac = ok[hit].mean()
     assert frac >= min_agree, "shading vertices agreeing: %.5f" % frac
     return float(frac)

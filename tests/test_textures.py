@@ -93,7 +93,17 @@ def test_gpu_textured_scene(built):
     S = pb.Scene([scenes.textured()])
     ctx = S.context()
     assert checks.check_rays(ctx, g) >= 0.9999
-    assert checks.check_shade(ctx, g, min_agree=0.995) >= 0.995
+    # vertices on the subsurface material run a random walk whose bounces amplify ulp differences between the device
+    # and host libm (same bar as the Cornell GPU test); every other vertex has to agree
+    assert checks.check_shade(ctx, g, min_agree=0.99) >= 0.99
+    fl = S.flat()
+    inst_mat = np.full(int(fl.tri_instance.max()) + 1, -1, np.int64)
+    inst_mat[fl.tri_instance] = fl.tri_material                       # one material per shape in this scene
+    inst = g["hit_ids"][:, 0].astype(np.int64)
+    hit = inst < len(inst_mat)
+    no_sss = hit & (g["materials"][inst_mat[np.where(hit, inst, 0)], 3] == 0)
+    assert no_sss.sum() > 5000
+    assert checks.check_shade(ctx, g, min_agree=0.9995, subset=no_sss) >= 0.9995
     assert checks.check_radiance(ctx, g, min_agree=0.99) >= 0.99
     # wavefront (material-sorted queues) and the one-thread-per-path megakernel run the same vertices
     rays = common.rays_from_f8(g["rays"])
