@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the path-tracing hot path (BASELINE.json: "Msamples/s and Mrays/s at 1/2/4/8 B200 vs Embree CPU").
 
-    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c1|c2|c3|c4|c5] [--spp S] [--impl reference]
     (N > 1: launched by torchrun, one rank per GPU)
 
 A step is one Render() of the workload: every camera sample of the frame traced to termination.
@@ -38,6 +38,8 @@ WORKLOADS = {
     "c1": ("cornellbox_suzanne_lucy 512x512 64spp PrincipledBSDF + area light", 512, 512, 64),
     "c2": ("cornellbox_suzanne_lucy 1920x1080 1024spp, Lucy random-walk SSS", 1920, 1080, 1024),
     "c3": ("synthetic CyHair 50k strands (1M segments) + light stage, 1920x1080 256spp, Principled Hair", 1920, 1080, 256),
+    "c4": ("cornellbox_suzanne_lucy + synthetic CyHair 50k strands, 3840x2160 512spp", 3840, 2160, 512),
+    "c5": ("synthetic displaced 20M-triangle OBJ, GGX + SSS materials, 3840x2160 1024spp", 3840, 2160, 1024),
 }
 
 
@@ -48,6 +50,11 @@ def scene_files(workload):
     if workload == "c3":
         return [scenes.light_stage(), scenes.cyhair(50000, 21, center=(-2.5, 3.5, 0.0), radius=1.2, length=2.5,
                                                     thickness=0.008)], 6, 1000000
+    if workload == "c4":
+        return [scenes.cornell(), scenes.cyhair(50000, 21, center=(-2.5, 6.0, 0.0), radius=1.2, length=2.5,
+                                                thickness=0.008)], 362620, 1000000
+    if workload == "c5":
+        return [scenes.displaced(20_000_000)], 19_920_012, 0
     raise SystemExit("unknown workload " + workload)
 
 
@@ -191,7 +198,9 @@ def main():
     d_count = torch.zeros(npix, dtype=torch.int32, device="cuda")
     h_rgba = torch.empty(npix * 4, dtype=torch.float32).pin_memory()
     h_count = torch.empty(npix, dtype=torch.int32).pin_memory()
-    mat_words = scene.flat().materials
+    flat = scene.flat()
+    mat_words = flat.materials
+    ntris, nsegs = int(len(flat.vidx)), int(len(flat.curve_first))      # what was actually loaded
     seed = 1234567890
 
     def step_device():
@@ -283,7 +292,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": w, "height": h, "spp_per_gpu": spp_per_gpu, "spp_total": spp_total,
                        "split": "interleaved samples, scene replicated, one NCCL reduce per frame" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: the path pool (~2 GB of slot lines) streams through every iteration; the scene (19 MB) is L2-resident by nature",
+                       "l2": "inputs larger than L2: the path pool (~2 GB of slot lines) streams through every iteration between two visits of a slot",
+                       "triangles": ntris, "curve_segments": nsegs,
                        "scene_commit_s": commit_s, "seed": seed},
             "Mrays_per_s": mrays, "rays_per_sample": float(rays_t.item()) / samples_step,
             "e2e": {"value": e2e_value, "unit": "Msamples/s",

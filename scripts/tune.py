@@ -14,6 +14,10 @@ for a in sys.argv[4:]:
         files = v.split(","); continue
     if k == "SCENE" and v == "c3":
         files = [scenes.light_stage(), scenes.cyhair(50000, 21, center=(-2.5, 3.5, 0.0), radius=1.2, length=2.5, thickness=0.008)]; continue
+    if k == "SCENE" and v == "c4":
+        files = [scenes.cornell(), scenes.cyhair(50000, 21, center=(-2.5, 6.0, 0.0), radius=1.2, length=2.5, thickness=0.008)]; continue
+    if k == "SCENE" and v.startswith("c5"):
+        files = [scenes.displaced(int(v.split(":")[1]) if ":" in v else 20_000_000)]; continue
     keys.append(k); vals.append(v.split(","))
 for combo in itertools.product(*vals):
     for k, v in zip(keys, combo):
