@@ -39,6 +39,8 @@ struct SceneView {
   const float4* curve_nodes;
   const float4* curve_data;    // leaf-ordered, 4 x float4 (xyz, radius) per cubic Bezier segment
   const uint32_t* curve_prim;  // leaf order -> curve primitive id
+  uint32_t ribbon_min_lanes;   // traversal engine: lanes holding a curve candidate that trigger a ribbon phase
+  const float2* curve_cull;    // leaf order: (capsule radius around the line c0c3, |c3 - c0|), see CurveMayHit; may be null
   uint32_t num_tris, num_curves;
   uint32_t bias_magic;         // kBiasMagic (traverse.cuh), as a run-time value on purpose
   // ---- per-primitive shading tables (indexed by primitive id = order given to pbrgpu_set_*)
@@ -66,14 +68,13 @@ struct SceneView {
   const float* lprim_cdf;      // per light primitive: AreaLight::cumulative_probability_
   const float4* lprim_info;    // per light primitive: emission rgb, pdf = P(light) P(prim) / area
   const uint32_t* lprim_tri;   // per light primitive: triangle primitive id
-  // ---- clearance grid for random-walk segments (scene_host.cc: BuildClearance): bit = 1 <=> some primitive's box
-  // touches the 3x3x3 cells around this cell.  kClearLevels resolutions, level L has (clear_dim >> L)^3 cells.
-  const uint32_t* clear_bits;  // null: no subsurface material in the scene
-  float clear_org[3], clear_inv_cell[3];   // level-0 grid: origin, 1 / cell size per axis
-  float clear_cell_min;        // shortest level-0 cell edge
-  uint32_t clear_dim;          // level-0 cells per axis
-  uint32_t clear_off[6];       // first 32-bit word of every level
+  // ---- clearance field for random-walk segments (scene_host.cc: BuildClearance): one byte per cell of an isotropic
+  // grid = a lower bound, in units of clear_quantum, of the distance from any point of the cell to any primitive
+  const uint8_t* clear_dist;   // null: no subsurface material in the scene
+  float clear_org[3];          // grid origin
+  float clear_inv_cell;        // 1 / cell edge
+  float clear_quantum;         // cell edge / 4
+  uint32_t clear_dims[3];      // cells per axis
 };
-constexpr uint32_t kClearLevels = 5;
 
 }  // namespace pbr

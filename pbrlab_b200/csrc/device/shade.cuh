@@ -395,26 +395,22 @@ enum SssStep { kSssContinue = 0, kSssHit = 1, kSssAbsorbed = 2 };
 
 // Can a walk segment of length `len` starting at `o` (any direction) be declared free of intersections without
 // tracing it?  Most segments of a random walk are much shorter than the distance to the nearest surface, yet each one
-// costs a root-to-leaf traversal.  The clearance grid answers conservatively: at the coarsest level whose cells are
-// longer than the segment, a clear bit means no primitive box touches the 27 cells around the start point, and the
-// segment cannot leave those cells.  A segment that is skipped is one the query would have reported "no hit" for, so
-// the walk takes exactly the same decisions (same random numbers, same result).
+// costs a root-to-leaf traversal.  The clearance field answers conservatively: the byte of the cell holding `o` is a
+// lower bound of the distance from any point of that cell to any primitive of the scene; a shorter segment cannot
+// reach one.  A segment that is skipped is one the query would have reported "no hit" for, so the walk takes exactly
+// the same decisions (same random numbers, same result).
 PBR_HD bool SegmentIsClear(const SceneView& s, const vec3& o, float len) {
-  if (!s.clear_bits) return false;
-  const float gx = (o.x - s.clear_org[0]) * s.clear_inv_cell[0];
-  const float gy = (o.y - s.clear_org[1]) * s.clear_inv_cell[1];
-  const float gz = (o.z - s.clear_org[2]) * s.clear_inv_cell[2];
-  const float dim = float(s.clear_dim);
-  if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < dim && gy < dim && gz < dim)) return false;
-  float reach = s.clear_cell_min * 0.98f;   // 2 % margin: rounding of the cell index and of the hit point
-  uint32_t level = 0;
-  while (len > reach && level < kClearLevels) { reach *= 2.0f; ++level; }
-  if (level >= kClearLevels) return false;
-  const uint32_t d = s.clear_dim >> level;
-  const uint32_t ix = uint32_t(gx) >> level, iy = uint32_t(gy) >> level, iz = uint32_t(gz) >> level;
-  const uint32_t idx = (iz * d + iy) * d + ix;
-  const uint32_t word = s.clear_bits[s.clear_off[level] + (idx >> 5)];
-  return ((word >> (idx & 31u)) & 1u) == 0u;
+  if (!s.clear_dist) return false;
+  const float gx = (o.x - s.clear_org[0]) * s.clear_inv_cell;
+  const float gy = (o.y - s.clear_org[1]) * s.clear_inv_cell;
+  const float gz = (o.z - s.clear_org[2]) * s.clear_inv_cell;
+  if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < float(s.clear_dims[0]) && gy < float(s.clear_dims[1]) &&
+        gz < float(s.clear_dims[2])))
+    return false;
+  const uint32_t idx = (uint32_t(gz) * s.clear_dims[1] + uint32_t(gy)) * s.clear_dims[0] + uint32_t(gx);
+  const float bound = float(s.clear_dist[idx]) * s.clear_quantum;
+  // 2 % + 1/64 cell of margin: rounding of the cell index (a point a few ulps across a cell face) and of the hit point
+  return len * 1.02f + 0.0625f * s.clear_quantum < bound;
 }
 
 // One iteration of the walk loop (:281-383), split at the ray query so that the wavefront's walk kernel can run the
@@ -461,6 +457,9 @@ PBR_HD SssStep SssFinishSegment(bool is_hit, float hit_t, Pcg32* rng, SssWalkSta
 PBR_HD SssStep SssBounce(const SceneView& s, Pcg32* rng, SssWalkState* w, HitT* hit, uint64_t* rays) {
   SssPrepareSegment(rng, w);
   const bool is_hit = TraceClosest<false>(s, w->ray, hit, nullptr);
+#ifdef PBR_CLEARANCE_PROBE   // tests/host_emul only: every segment the field would skip must be a miss
+  PBR_CLEARANCE_PROBE(SegmentIsClear(s, w->ray.o, w->ray.tmax * 1.001f), is_hit);
+#endif
   if (rays) ++*rays;
   return SssFinishSegment(is_hit, hit->t, rng, w);
 }

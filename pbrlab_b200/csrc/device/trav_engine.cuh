@@ -26,6 +26,7 @@ struct Trav {
   int sp;                  // stack entries in use
   bool active;             // still traversing
   bool curves;             // walking the curve BVH (after the triangle BVH)
+  uint32_t held;           // curve segment (leaf order) that passed CurveMayHit and waits for the ribbon test; kInvalid: none
   HitT hit;                // closest hit so far (prim == kInvalid: none)
   uint32_t n_nodes, n_prims;   // STATS only
 };
@@ -46,6 +47,7 @@ __device__ __forceinline__ void TravBegin(const SceneView& s, const RayT& ray, T
   t.curves = (s.num_tris == 0u);
   t.group = make_uint2(0u, 0x80000000u);   // the root as the only child of a virtual parent (see TraverseBvh)
   t.pgroup = make_uint2(0u, 0u);
+  t.held = kInvalid;
   t.active = (s.num_tris | s.num_curves) != 0u;
 }
 
@@ -108,27 +110,53 @@ __device__ __forceinline__ void TravAdvance(const SceneView& s, Trav& t) {
   }
 }
 
-template <bool ANY, bool HAS_CURVES, bool STATS>
-__device__ __forceinline__ void TravPrimStep(const SceneView& s, Trav& t) {
+// One pending TRIANGLE of the lane.
+template <bool ANY, bool STATS>
+__device__ __forceinline__ void TravTriStep(const SceneView& s, Trav& t) {
   const uint32_t bit = msb(t.pgroup.y);
   t.pgroup.y &= ~(1u << bit);
   const uint32_t idx = t.pgroup.x + bit;
   if (STATS) t.n_prims++;
+  const float4* __restrict__ prims = s.tri_data;
+  const float4 a = prims[idx * 3 + 0], b = prims[idx * 3 + 1], c = prims[idx * 3 + 2];
   float ht, hu, hv;
-  bool h;
-  if (HAS_CURVES && t.curves) {
-    const CurveRaySpace rs = MakeCurveRaySpace(t.D);
-    const float4* __restrict__ prims = s.curve_data;
-    const float4 c0 = prims[idx * 4 + 0], c1 = prims[idx * 4 + 1], c2 = prims[idx * 4 + 2], c3 = prims[idx * 4 + 3];
-    h = IntersectCurve(t.O, rs, t.tmin, t.tfar, c0, c1, c2, c3, &ht, &hu, &hv);
-  } else {
-    const float4* __restrict__ prims = s.tri_data;
-    const float4 a = prims[idx * 3 + 0], b = prims[idx * 3 + 1], c = prims[idx * 3 + 2];
-    h = IntersectTriangle(t.O, t.D, t.tmin, t.tfar, from4(a), from4(b), from4(c), &ht, &hu, &hv);
-  }
-  if (h) {
+  if (IntersectTriangle(t.O, t.D, t.tmin, t.tfar, from4(a), from4(b), from4(c), &ht, &hu, &hv)) {
     t.hit.t = ht; t.hit.u = hu; t.hit.v = hv;
-    t.hit.prim = (HAS_CURVES && t.curves) ? (idx | kCurveFlag) : idx;
+    t.hit.prim = idx;
+    t.tfar = ht;
+    if (ANY) t.active = false;
+  }
+}
+
+// Pending CURVE segments of the lane.  Leaf boxes of thin diagonal segments are much fatter than the ribbon: 5 of 6
+// candidates fail the cheap line-distance test (CurveMayHit).  The lane drops those on its own; the first one that
+// passes is HELD for the ribbon test, which costs ~700 instructions and which the warp therefore runs for many lanes
+// at once (TravRibbonStep) — measured on B200 (profiles/r1i): run the moment a lane had a candidate, 70 % of the
+// kernel's instructions executed with ONE active lane.
+template <bool STATS>
+__device__ __forceinline__ void TravCurveCullStep(const SceneView& s, Trav& t) {
+  const float4* __restrict__ prims = s.curve_data;
+  do {
+    const uint32_t bit = msb(t.pgroup.y);
+    t.pgroup.y &= ~(1u << bit);
+    const uint32_t idx = t.pgroup.x + bit;
+    if (STATS) t.n_prims++;
+    const float4 c0 = prims[idx * 4 + 0], c3 = prims[idx * 4 + 3];
+    if (!s.curve_cull || CurveMayHit(t.O, t.D, c0, c3, s.curve_cull[idx])) t.held = idx;
+  } while (t.held == kInvalid && t.pgroup.y != 0u);
+}
+
+template <bool ANY>
+__device__ __forceinline__ void TravRibbonStep(const SceneView& s, Trav& t) {
+  const uint32_t idx = t.held;
+  t.held = kInvalid;
+  const float4* __restrict__ prims = s.curve_data;
+  const float4 c0 = prims[idx * 4 + 0], c1 = prims[idx * 4 + 1], c2 = prims[idx * 4 + 2], c3 = prims[idx * 4 + 3];
+  const CurveRaySpace rs = MakeCurveRaySpace(t.D);
+  float ht, hu, hv;
+  if (IntersectCurve(t.O, rs, t.tmin, t.tfar, c0, c1, c2, c3, &ht, &hu, &hv)) {
+    t.hit.t = ht; t.hit.u = hu; t.hit.v = hv;
+    t.hit.prim = idx | kCurveFlag;
     t.tfar = ht;
     if (ANY) t.active = false;
   }
@@ -155,6 +183,7 @@ __device__ __forceinline__ void TravEngine(const SceneView& s, Client& client, u
   Trav t;
   t.active = false;
   t.pgroup = make_uint2(0u, 0u);
+  t.held = kInvalid;
   t.n_nodes = 0; t.n_prims = 0;
   bool exhausted = false;   // warp-uniform: the work source ran dry
   for (;;) {
@@ -170,17 +199,37 @@ __device__ __forceinline__ void TravEngine(const SceneView& s, Client& client, u
         continue;
       }
     }
-    const bool node_work = t.active && t.pgroup.y == 0u;
+    const bool node_work = t.active && t.pgroup.y == 0u && (!HAS_CURVES || t.held == kInvalid);
     if (node_work) {
       TravNodeStep<HAS_CURVES, STATS, false>(s, t, stack);   // prefetching the next node was measured: 1.6x slower
       TravAdvance<HAS_CURVES>(s, t);
     }
-    const unsigned prim = __ballot_sync(0xffffffffu, t.active && t.pgroup.y != 0u);
-    const unsigned node = __ballot_sync(0xffffffffu, t.active && t.pgroup.y == 0u);
+    if (HAS_CURVES) {
+      // curve candidates: cheap rejection now, per lane; the survivor (if any) is held for the ribbon phase
+      if (t.active && t.curves && t.held == kInvalid && t.pgroup.y != 0u) {
+        TravCurveCullStep<STATS>(s, t);
+        if (t.held == kInvalid) TravAdvance<HAS_CURVES>(s, t);
+      }
+    }
+    const bool tri_work = t.active && t.pgroup.y != 0u && !(HAS_CURVES && t.curves);
+    const unsigned prim = __ballot_sync(0xffffffffu, tri_work);
+    const unsigned node = __ballot_sync(0xffffffffu, t.active && t.pgroup.y == 0u && (!HAS_CURVES || t.held == kInvalid));
     if (prim != 0u && (uint32_t(__popc(prim)) >= prim_min_lanes || node == 0u)) {
-      if (t.active && t.pgroup.y != 0u) {
-        TravPrimStep<ANY, HAS_CURVES, STATS>(s, t);
+      if (tri_work) {
+        TravTriStep<ANY, STATS>(s, t);
         if (t.active) TravAdvance<HAS_CURVES>(s, t);
+      }
+    }
+    if (HAS_CURVES) {
+      // ribbon phase: when enough lanes hold a candidate, or when nobody can make progress without it
+      const bool holding = t.active && t.held != kInvalid;
+      const unsigned hold = __ballot_sync(0xffffffffu, holding);
+      const unsigned free_lanes = __ballot_sync(0xffffffffu, t.active && t.held == kInvalid);
+      if (hold != 0u && (uint32_t(__popc(hold)) >= s.ribbon_min_lanes || free_lanes == 0u)) {
+        if (holding) {
+          TravRibbonStep<ANY>(s, t);
+          if (t.active) TravAdvance<HAS_CURVES>(s, t);
+        }
       }
     }
   }

@@ -103,7 +103,31 @@ PBR_HD vec3 CurveTangent(const float4& c0, const float4& c1, const float4& c2, c
   return vec3(bz(b, c0.x, c1.x, c2.x, c3.x), bz(b, c0.y, c1.y, c2.y, c3.y), bz(b, c0.z, c1.z, c2.z, c3.z));
 }
 
-// One cubic segment against the ray.  any_hit: return on the first accepted sub-segment.
+// Cheap conservative rejection ahead of IntersectCurve.  The ribbon of a segment is four ray-facing quads between
+// consecutive points B(i/4) of the curve, each quad inside the capsule of radius max(r_i, r_i+1) around its chord
+// (the corners are at distance r from the chord's ends and a capsule is convex); every point of the curve, hence of
+// those chords, lies within `dev` = max distance of the inner control points from the line c0c3 (convex hull).  So a
+// ray that hits the ribbon passes within R = r_max + dev of the LINE through c0 and c3: if the distance between the
+// two lines is larger, the full test cannot succeed.  cull = (R with its safety factor, |c3 - c0|), built at commit
+// (scene_host.cc); the second term bounds the rounding error of the triple product (2^-22 |w| |D| |e|).
+PBR_HD bool CurveMayHit(const vec3& O, const vec3& D, const float4& c0, const float4& c3, const float2& cull) {
+  const vec3 e(c3.x - c0.x, c3.y - c0.y, c3.z - c0.z);
+  const vec3 w(c0.x - O.x, c0.y - O.y, c0.z - O.z);
+  const vec3 n = ecross(D, e);
+  const float q = edot(w, n);
+  const float nn = edot(n, n), ww = edot(w, w), dd = edot(D, D);
+  return !(fabsf(q) > cull.x * sqrtf(nn) + 3e-7f * (sqrtf(ww * dd) * cull.y));
+}
+
+// One cubic segment against the ray: Embree's ribbon intersector (curve_intersector_ribbon.h:72-177) — the curve is
+// cut at u = 0, 1/4, .. 1 into four ray-facing quads; the nearest accepted quad hit wins (lowest sub-segment on ties).
+// Two stages so that the lanes of a warp stay together: (1) the five points in ray space and, per sub-segment, the
+// two 2-D rejections (a bit mask); (2) the quad test, once per surviving sub-segment.
+//   * cylinder_culling_test: distance from the ray (the 2-D origin) to the LINE p0p1 <= max(r0, r1) — Embree's own;
+//   * ours: the foot of that perpendicular must lie within max(r0, r1) of the SEGMENT p0p1.  The quad's corners are
+//     p0 +- r0 n0, p1 +- r1 n1 with unit n in the xy plane, all inside the (convex) 2-D capsule of radius max(r0, r1)
+//     around p0p1, and so is the quad; a ray outside the capsule cannot hit it.  Near-collinear sub-segments all pass
+//     the line test, this one keeps the one or two the ray actually crosses.
 PBR_HD bool IntersectCurve(const vec3& O, const CurveRaySpace& rs, float tnear, float tfar, const float4& c0,
                            const float4& c1, const float4& c2, const float4& c3, float* t_out, float* u_out,
                            float* v_out) {
@@ -119,9 +143,47 @@ PBR_HD bool IntersectCurve(const vec3& O, const CurveRaySpace& rs, float tnear, 
   m = fmaxf(m, fmaxf(fmaxf(fabsf(q3.x), fabsf(q3.y)), fabsf(q3.z)));
   const float eps = 4.0f * kFltEps * m;
 
+  // ---- stage 1: which sub-segments can be hit (xy and radius of the five points only)
+  uint32_t mask = 0u;
+  {
+    float px0, py0, pr0;
+    {
+      float b[4];
+      BezierBasis(0.0f, b);
+      px0 = bz(b, q0.x, q1.x, q2.x, q3.x); py0 = bz(b, q0.y, q1.y, q2.y, q3.y); pr0 = bz(b, c0.w, c1.w, c2.w, c3.w);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) {
+      float b[4];
+      BezierBasis(float(i + 1) / 4.0f, b);
+      const float px1 = bz(b, q0.x, q1.x, q2.x, q3.x), py1 = bz(b, q0.y, q1.y, q2.y, q3.y),
+                  pr1 = bz(b, c0.w, c1.w, c2.w, c3.w);
+      // cylinder_culling_test(0, p0.xy, p1.xy, max(r0, r1))
+      const float ax = px1 - px0, ay = py1 - py0;
+      const float bx = px0 - 0.f, by = py0 - 0.f;
+      const float num = ax * by - ay * bx;
+      const float den2 = ax * ax + ay * ay;
+      const float r = fmaxf(pr0, pr1);
+      bool keep = num * num <= r * r * den2;
+      // capsule ends: s = -(b.a) is the foot's parameter times |a|^2; outside [0, |a|^2] by more than r |a| -> no hit
+      const float sfoot = -(bx * ax + by * ay);
+      const float lim = r * r * den2 * 1.001f + 1e-12f * (m * m) * den2;
+      const float over = sfoot - den2;
+      if ((sfoot < 0.f && sfoot * sfoot > lim) || (over > 0.f && over * over > lim)) keep = false;
+      if (keep) mask |= 1u << i;
+      px0 = px1; py0 = py1; pr0 = pr1;
+    }
+  }
+
+  // ---- stage 2: the quad of every surviving sub-segment, in ascending order
   bool found = false;
   float best_t = 0.f, best_u = 0.f, best_v = 0.f;
-  for (int i = 0; i < 4; ++i) {
+  while (mask != 0u) {
+    int i = 0;
+    while (!((mask >> i) & 1u)) ++i;
+    mask &= mask - 1u;
     float b0[4], b1[4], d0[4], d1[4];
     BezierBasis(float(i) / 4.0f, b0);
     BezierBasis(float(i + 1) / 4.0f, b1);
@@ -129,14 +191,6 @@ PBR_HD bool IntersectCurve(const vec3& O, const CurveRaySpace& rs, float tnear, 
                      bz(b0, c0.w, c1.w, c2.w, c3.w)};
     const vec4 p1 = {bz(b1, q0.x, q1.x, q2.x, q3.x), bz(b1, q0.y, q1.y, q2.y, q3.y), bz(b1, q0.z, q1.z, q2.z, q3.z),
                      bz(b1, c0.w, c1.w, c2.w, c3.w)};
-    {  // cylinder_culling_test(0, p0.xy, p1.xy, max(r0, r1))
-      const float ax = p1.x - p0.x, ay = p1.y - p0.y;
-      const float bx = p0.x - 0.f, by = p0.y - 0.f;
-      const float num = ax * by - ay * bx;
-      const float den2 = ax * ax + ay * ay;
-      const float r = fmaxf(p0.w, p1.w);
-      if (!(num * num <= r * r * den2)) continue;
-    }
     BezierDerivative(float(i) / 4.0f, d0);
     BezierDerivative(float(i + 1) / 4.0f, d1);
     vec3 dp0(bz(d0, q0.x, q1.x, q2.x, q3.x), bz(d0, q0.y, q1.y, q2.y, q3.y), bz(d0, q0.z, q1.z, q2.z, q3.z));
@@ -280,8 +334,9 @@ PBR_HD uint32_t NodeIntersect(const vec3& o_over_d, const vec3& inv_d, uint32_t 
 
 // Generic traversal of one BVH.  CURVES selects the leaf test, ANY the early-out.
 template <bool CURVES, bool ANY, bool STATS>
-PBR_HD bool TraverseBvh(const float4* __restrict__ nodes, const float4* __restrict__ prims, const RayT& ray,
-                        float* tfar_io, HitT* hit, TraverseStats* st) {
+PBR_HD bool TraverseBvh(const float4* __restrict__ nodes, const float4* __restrict__ prims,
+                        const float2* __restrict__ cull, const RayT& ray, float* tfar_io, HitT* hit,
+                        TraverseStats* st) {
   const vec3 O = ray.o, D = ray.d;
   // slab-test direction: zero components are nudged so 1/d stays finite (sign kept)
   const float tiny = 1e-30f;
@@ -334,9 +389,16 @@ PBR_HD bool TraverseBvh(const float4* __restrict__ nodes, const float4* __restri
       float t, u, v;
       bool h;
       if (CURVES) {
-        const float4 c0 = prims[idx * 4 + 0], c1 = prims[idx * 4 + 1], c2 = prims[idx * 4 + 2],
-                     c3 = prims[idx * 4 + 3];
-        h = IntersectCurve(O, rs, ray.tmin, tfar, c0, c1, c2, c3, &t, &u, &v);
+        const float4 c0 = prims[idx * 4 + 0], c3 = prims[idx * 4 + 3];
+        h = false;
+        const bool may = !cull || CurveMayHit(O, D, c0, c3, cull[idx]);
+#ifdef PBR_CURVE_PROBE   // tests/host_emul only
+        PBR_CURVE_PROBE(may);
+#endif
+        if (may) {
+          const float4 c1 = prims[idx * 4 + 1], c2 = prims[idx * 4 + 2];
+          h = IntersectCurve(O, rs, ray.tmin, tfar, c0, c1, c2, c3, &t, &u, &v);
+        }
       } else {
         const float4 a = prims[idx * 3 + 0], b = prims[idx * 3 + 1], c = prims[idx * 3 + 2];
         h = IntersectTriangle(O, D, ray.tmin, tfar, from4(a), from4(b), from4(c), &t, &u, &v);
@@ -364,8 +426,8 @@ PBR_HD bool TraceClosest(const SceneView& s, const RayT& ray, HitT* hit, Travers
   float tfar = ray.tmax;
   hit->prim = kInvalid;
   bool found = false;
-  if (s.num_tris) found |= TraverseBvh<false, false, STATS>(s.tri_nodes, s.tri_data, ray, &tfar, hit, st);
-  if (s.num_curves) found |= TraverseBvh<true, false, STATS>(s.curve_nodes, s.curve_data, ray, &tfar, hit, st);
+  if (s.num_tris) found |= TraverseBvh<false, false, STATS>(s.tri_nodes, s.tri_data, nullptr, ray, &tfar, hit, st);
+  if (s.num_curves) found |= TraverseBvh<true, false, STATS>(s.curve_nodes, s.curve_data, s.curve_cull, ray, &tfar, hit, st);
   return found;
 }
 
@@ -374,8 +436,8 @@ template <bool STATS>
 PBR_HD bool TraceAny(const SceneView& s, const RayT& ray, TraverseStats* st) {
   float tfar = ray.tmax;
   HitT hit;
-  if (s.num_tris && TraverseBvh<false, true, STATS>(s.tri_nodes, s.tri_data, ray, &tfar, &hit, st)) return true;
-  if (s.num_curves && TraverseBvh<true, true, STATS>(s.curve_nodes, s.curve_data, ray, &tfar, &hit, st)) return true;
+  if (s.num_tris && TraverseBvh<false, true, STATS>(s.tri_nodes, s.tri_data, nullptr, ray, &tfar, &hit, st)) return true;
+  if (s.num_curves && TraverseBvh<true, true, STATS>(s.curve_nodes, s.curve_data, s.curve_cull, ray, &tfar, &hit, st)) return true;
   return false;
 }
 

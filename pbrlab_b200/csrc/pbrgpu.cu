@@ -68,7 +68,8 @@ struct Device {
   DevBuf<float4> geom;   // [tri_nodes | tri_data | curve_nodes | curve_data]: one range for the L2 persistence window
   DevBuf<float4> verts, normals, emissive, lprim_info;
   DevBuf<float2> texcoords;
-  DevBuf<uint32_t> curve_prim, lprim_tri, clear_bits, material_class;
+  DevBuf<uint32_t> curve_prim, lprim_tri, clear_dist, material_class;
+  DevBuf<float> curve_cull;
   DevBuf<float> tex_pixels;
   DevBuf<pbr::TexDesc> tex_desc;
   DevBuf<uint4> tri_ids, tri_nidx, tri_vidx, tri_tidx, curve_ids;
@@ -92,9 +93,9 @@ struct Device {
   unsigned long long* h_stats = nullptr;
 
   void Release() {
-    geom.Free(); clear_bits.Free(); verts.Free(); normals.Free(); material_class.Free(); tex_pixels.Free();
+    geom.Free(); clear_dist.Free(); verts.Free(); normals.Free(); material_class.Free(); tex_pixels.Free();
     tex_desc.Free(); q_diffuse.Free(); srgb8.Free();
-    emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); lprim_tri.Free(); tri_ids.Free();
+    emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); curve_cull.Free(); lprim_tri.Free(); tri_ids.Free();
     tri_nidx.Free(); tri_vidx.Free(); tri_tidx.Free(); curve_ids.Free(); materials.Free(); light_cdf.Free();
     lprim_cdf.Free(); lights.Free();
     slot.Free(); walk.Free(); sh_o.Free(); sh_d.Free(); sh_c.Free();
@@ -125,6 +126,7 @@ struct pbrgpu_ctx {
   uint32_t tune_refill = 16;       // idle lanes that trigger a refill in the traversal engine
   uint32_t tune_refill_sss = 24;   // same for the random-walk kernel (its converged section is the bounce itself)
   uint32_t tune_prim_lanes = 1, tune_prim_lanes_sss = 1;   // lanes with pending primitives that trigger a primitive phase
+  uint32_t tune_ribbon_lanes = 8;  // lanes holding a curve candidate that trigger the (batched) ribbon test
   int tune_l2_persist = 0;         // persisting-L2 window over the traversal data
   int tune_sss_skip = 1;           // clearance grid: random-walk segments that provably hit nothing are not traced
   int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
@@ -193,6 +195,7 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
     }
   }
   CUDA_TRY(ctx, d.curve_prim.Upload(h.curve_prim.data(), h.curve_prim.size(), st));
+  CUDA_TRY(ctx, d.curve_cull.Upload(h.curve_cull.data(), h.curve_cull.size(), st));
   CUDA_TRY(ctx, d.tri_ids.Upload(h.tri_ids.data(), h.tri_ids.size(), st));
   CUDA_TRY(ctx, d.tri_nidx.Upload(h.tri_nidx.data(), h.tri_nidx.size(), st));
   CUDA_TRY(ctx, d.tri_vidx.Upload(h.tri_vidx.data(), h.tri_vidx.size(), st));
@@ -208,7 +211,7 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   CUDA_TRY(ctx, d.lprim_cdf.Upload(h.lprim_cdf.data(), h.lprim_cdf.size(), st));
   CUDA_TRY(ctx, d.lprim_info.Upload(h.lprim_info.data(), h.lprim_info.size(), st));
   CUDA_TRY(ctx, d.lprim_tri.Upload(h.lprim_tri.data(), h.lprim_tri.size(), st));
-  CUDA_TRY(ctx, d.clear_bits.Upload(h.clear_bits.data(), h.clear_bits.size(), st));
+  CUDA_TRY(ctx, d.clear_dist.Upload(h.clear_dist.data(), h.clear_dist.size(), st));
   CUDA_TRY(ctx, d.material_class.Upload(h.material_class.data(), h.material_class.size(), st));
   CUDA_TRY(ctx, d.tex_pixels.Upload(h.tex_pixels.data(), h.tex_pixels.size(), st));
   CUDA_TRY(ctx, d.tex_desc.Upload(h.tex_desc.data(), h.tex_desc.size(), st));
@@ -217,6 +220,8 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   memset(&v, 0, sizeof(v));
   v.tri_nodes = g_tn; v.tri_data = g_td;
   v.curve_nodes = g_cn; v.curve_data = g_cd; v.curve_prim = d.curve_prim.ptr;
+  v.ribbon_min_lanes = ctx->tune_ribbon_lanes;
+  v.curve_cull = h.curve_cull.empty() ? nullptr : reinterpret_cast<const float2*>(d.curve_cull.ptr);
   v.num_tris = h.num_tris(); v.num_curves = h.num_curves();
   v.bias_magic = pbr::kBiasMagic;
   v.tri_ids = d.tri_ids.ptr; v.tri_nidx = d.tri_nidx.ptr; v.tri_vidx = d.tri_vidx.ptr; v.tri_tidx = d.tri_tidx.ptr;
@@ -228,11 +233,10 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   v.emissive = d.emissive.ptr; v.light_cdf = d.light_cdf.ptr; v.lights = d.lights.ptr;
   v.num_lights = uint32_t(h.lights.size());
   v.lprim_cdf = d.lprim_cdf.ptr; v.lprim_info = d.lprim_info.ptr; v.lprim_tri = d.lprim_tri.ptr;
-  v.clear_bits = (ctx->tune_sss_skip && !h.clear_bits.empty()) ? d.clear_bits.ptr : nullptr;
-  for (int k = 0; k < 3; ++k) { v.clear_org[k] = h.clear_org[k]; v.clear_inv_cell[k] = h.clear_inv_cell[k]; }
-  v.clear_cell_min = h.clear_cell_min;
-  v.clear_dim = h.clear_dim;
-  for (int k = 0; k < 6; ++k) v.clear_off[k] = h.clear_off[k];
+  v.clear_dist = (ctx->tune_sss_skip && !h.clear_dist.empty()) ? reinterpret_cast<const uint8_t*>(d.clear_dist.ptr) : nullptr;
+  for (int k = 0; k < 3; ++k) { v.clear_org[k] = h.clear_org[k]; v.clear_dims[k] = h.clear_dims[k]; }
+  v.clear_inv_cell = h.clear_inv_cell;
+  v.clear_quantum = h.clear_quantum;
   return PBRGPU_OK;
 }
 
@@ -525,6 +529,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_refill_sss = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_REFILL_SSS", int(ctx->tune_refill_sss)))));
   ctx->tune_prim_lanes = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_PRIM_LANES", int(ctx->tune_prim_lanes)))));
   ctx->tune_prim_lanes_sss = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_PRIM_LANES_SSS", int(ctx->tune_prim_lanes_sss)))));
+  ctx->tune_ribbon_lanes = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_RIBBON_LANES", int(ctx->tune_ribbon_lanes)))));
   ctx->tune_trace_blocks = std::max(1, env_int("PBRGPU_TRACE_BLOCKS", ctx->tune_trace_blocks));
   ctx->tune_shade_blocks = std::max(1, env_int("PBRGPU_SHADE_BLOCKS", ctx->tune_shade_blocks));
   ctx->tune_walk_blocks = std::max(1, env_int("PBRGPU_WALK_BLOCKS", ctx->tune_walk_blocks));

@@ -4,10 +4,13 @@
 #include "device/principled.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <limits>
 
 namespace pbrhost {
 
@@ -298,8 +301,37 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
       memcpy(&curve_data[4 * size_t(k)], &curve_cps[4 * size_t(i)], sizeof(F4) * 4);
       curve_prim[k] = i;
     }
+    // CurveMayHit: capsule radius around the line c0c3 = largest |r| + largest distance of c1, c2 from that line
+    // (double arithmetic, then 0.1 % + 1e-6 |coordinates| of slack for the float evaluation on the device)
+    curve_cull.assign(size_t(2) * nc, 0.f);
+    if (!getenv("PBRGPU_NO_CURVE_CULL")) {
+      for (uint32_t k = 0; k < nc; ++k) {
+        const F4* cp = &curve_data[4 * size_t(k)];
+        const double e[3] = {double(cp[3].x) - cp[0].x, double(cp[3].y) - cp[0].y, double(cp[3].z) - cp[0].z};
+        const double ee = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+        double rmax = 0.0, dev = 0.0, mag = 0.0;
+        for (int j = 0; j < 4; ++j) {
+          rmax = std::max(rmax, std::fabs(double(cp[j].w)));
+          mag = std::max(mag, std::max(std::fabs(double(cp[j].x)), std::max(std::fabs(double(cp[j].y)), std::fabs(double(cp[j].z)))));
+        }
+        float R = std::numeric_limits<float>::infinity();   // degenerate chord: never reject
+        if (ee > 1e-24 && ee > 1e-10 * mag * mag) {
+          for (int j = 1; j <= 2; ++j) {
+            const double a[3] = {double(cp[j].x) - cp[0].x, double(cp[j].y) - cp[0].y, double(cp[j].z) - cp[0].z};
+            const double c[3] = {a[1] * e[2] - a[2] * e[1], a[2] * e[0] - a[0] * e[2], a[0] * e[1] - a[1] * e[0]};
+            dev = std::max(dev, std::sqrt((c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) / ee));
+          }
+          R = float((rmax + dev) * 1.001 + 1e-6 * mag);
+        }
+        curve_cull[2 * size_t(k)] = R;
+        curve_cull[2 * size_t(k) + 1] = float(std::sqrt(ee) * 1.0001);
+      }
+    } else {
+      curve_cull.clear();
+    }
   } else {
     curve_bvh = pbrbvh::Bvh8();
+    curve_cull.clear();
   }
 
   // ---- emissive triangle entries (LightManager::ImplicitAreaLight)
@@ -323,13 +355,51 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
   return true;
 }
 
-// Multi-resolution occupancy of the region where random walks happen (the bounds of every triangle whose material has
-// subsurface enabled).  ALL primitives are rasterised — a walk segment is intersected with the whole scene
-// (random-walk-sss.h:310) — by their boxes, refined for large triangles by the triangle's plane; each level is then
-// dilated by one cell so that a clear bit vouches for the 27 cells around a point.
+// Clearance field of the region where random walks happen (the bounds of every triangle whose material has
+// subsurface enabled): one byte per cell of an isotropic grid = a lower bound, in quarter cells, of the distance from
+// any point of the cell to any primitive.  ALL primitives are rasterised — a walk segment is intersected with the
+// whole scene (random-walk-sss.h:310) — by their boxes, refined for large triangles by the triangle's plane.  The
+// occupancy is dilated by one cell, so the exact Euclidean distance transform between cell centres of the dilated
+// set equals the box-to-box distance between a cell and the nearest occupied cell; the outermost layer of the grid
+// counts as occupied (primitives outside the grid are not rasterised).
+namespace {
+// 1-D squared distance transform (lower envelope of parabolas, Felzenszwalb & Huttenlocher 2012) of f[0..n), in place
+inline void Edt1D(float* f, int n, float* z, int* v, float* out) {
+  const float kBig = 1e20f;
+  int k = 0;
+  v[0] = 0; z[0] = -kBig; z[1] = kBig;
+  for (int q = 1; q < n; ++q) {
+    float sx;
+    for (;;) {   // z[0] = -kBig is below every finite intersection, so k never drops under 0
+      const int p = v[k];
+      sx = ((f[q] + float(q) * float(q)) - (f[p] + float(p) * float(p))) / (2.0f * float(q - p));
+      if (sx <= z[k]) --k; else break;
+    }
+    ++k; v[k] = q; z[k] = sx; z[k + 1] = kBig;
+  }
+  k = 0;
+  for (int q = 0; q < n; ++q) {
+    while (z[k + 1] < float(q)) ++k;
+    const float dq = float(q - v[k]);
+    out[q] = dq * dq + f[v[k]];
+  }
+  for (int q = 0; q < n; ++q) f[q] = out[q];
+}
+
+template <class F>
+void ParallelFor(int n, F fn) {
+  const int nt = std::max(1, std::min(int(std::thread::hardware_concurrency()), n));
+  std::vector<std::thread> th;
+  std::atomic<int> next{0};
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&]() { for (int i; (i = next.fetch_add(1)) < n;) fn(i); });
+  for (auto& t : th) t.join();
+}
+}  // namespace
+
 void HostScene::BuildClearance() {
-  clear_bits.clear();
-  clear_dim = 0;
+  clear_dist.clear();
+  clear_dims[0] = clear_dims[1] = clear_dims[2] = 0;
   const uint32_t nt = num_tris();
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   bool any = false;
@@ -346,37 +416,50 @@ void HostScene::BuildClearance() {
     }
   }
   if (!any) return;
-  const uint32_t R = 256;
-  float cell[3];
-  for (int k = 0; k < 3; ++k) {
-    const float ext = std::max(hi[k] - lo[k], 1e-6f);
-    lo[k] -= 0.01f * ext;
-    cell[k] = (1.02f * ext) / float(R);
-    clear_org[k] = lo[k];
-    clear_inv_cell[k] = 1.0f / cell[k];
+  // isotropic cells: as fine as the cell budget allows (PBRGPU_CLEAR_CELLS, default 24 Mi cells = 24 MiB in L2)
+  double budget = 24.0 * 1048576.0;
+  if (const char* e = getenv("PBRGPU_CLEAR_CELLS")) budget = std::max(4096.0, atof(e));
+  double ext[3];
+  for (int k = 0; k < 3; ++k) ext[k] = std::max(double(hi[k]) - double(lo[k]), 1e-6);
+  const double longest = std::max(ext[0], std::max(ext[1], ext[2]));
+  for (int k = 0; k < 3; ++k) ext[k] = std::max(ext[k], longest * 0.01);   // a flat region still gets a few layers
+  double h = std::cbrt(ext[0] * ext[1] * ext[2] / budget);
+  for (;;) {
+    double cells = 1.0;
+    for (int k = 0; k < 3; ++k) cells *= std::ceil(ext[k] / h) + 4.0;
+    if (cells <= budget) break;
+    h *= 1.02;
   }
-  clear_cell_min = std::min(cell[0], std::min(cell[1], cell[2]));
-  clear_dim = R;
-  std::vector<uint8_t> occ(size_t(R) * R * R, 0);
+  int D[3];
+  for (int k = 0; k < 3; ++k) {
+    D[k] = int(std::ceil(ext[k] / h)) + 4;                       // two spare layers on each side
+    clear_org[k] = float(0.5 * (double(lo[k]) + double(hi[k])) - 0.5 * double(D[k]) * h);
+    clear_dims[k] = uint32_t(D[k]);
+  }
+  const float cell = float(h);
+  clear_inv_cell = 1.0f / cell;
+  clear_quantum = 0.25f * cell;
+  const size_t ncell = size_t(D[0]) * D[1] * D[2];
+  std::vector<uint8_t> occ(ncell, 0);
   auto mark_box = [&](const float* blo, const float* bhi, const float* plane /* n.xyz, d or null */) {
     int a[3], b[3];
     for (int k = 0; k < 3; ++k) {
-      const float fa = (blo[k] - clear_org[k]) * clear_inv_cell[k] - 0.01f, fb = (bhi[k] - clear_org[k]) * clear_inv_cell[k] + 0.01f;
-      if (fb < 0.f || fa >= float(R)) return;
+      const float fa = (blo[k] - clear_org[k]) * clear_inv_cell - 0.01f, fb = (bhi[k] - clear_org[k]) * clear_inv_cell + 0.01f;
+      if (fb < 0.f || fa >= float(D[k])) return;
       a[k] = std::max(0, int(std::floor(fa)));
-      b[k] = std::min(int(R) - 1, int(std::floor(fb)));
+      b[k] = std::min(D[k] - 1, int(std::floor(fb)));
     }
     const bool refine = plane && (size_t(b[0] - a[0] + 1) * (b[1] - a[1] + 1) * (b[2] - a[2] + 1) > 64);
-    const float rad = refine ? 0.51f * (std::fabs(plane[0]) * cell[0] + std::fabs(plane[1]) * cell[1] + std::fabs(plane[2]) * cell[2]) : 0.f;
+    const float rad = refine ? 0.51f * cell * (std::fabs(plane[0]) + std::fabs(plane[1]) + std::fabs(plane[2])) : 0.f;
     for (int z = a[2]; z <= b[2]; ++z)
       for (int y = a[1]; y <= b[1]; ++y) {
-        uint8_t* row = &occ[(size_t(z) * R + y) * R];
+        uint8_t* row = &occ[(size_t(z) * D[1] + y) * D[0]];
         if (!refine) {
           for (int x = a[0]; x <= b[0]; ++x) row[x] = 1;
         } else {
-          const float cy = clear_org[1] + (y + 0.5f) * cell[1], cz = clear_org[2] + (z + 0.5f) * cell[2];
+          const float cy = clear_org[1] + (y + 0.5f) * cell, cz = clear_org[2] + (z + 0.5f) * cell;
           for (int x = a[0]; x <= b[0]; ++x) {
-            const float cx = clear_org[0] + (x + 0.5f) * cell[0];
+            const float cx = clear_org[0] + (x + 0.5f) * cell;
             if (std::fabs(plane[0] * cx + plane[1] * cy + plane[2] * cz + plane[3]) <= rad) row[x] = 1;
           }
         }
@@ -409,47 +492,86 @@ void HostScene::BuildClearance() {
     for (int k = 0; k < 3; ++k) { blo[k] -= r; bhi[k] += r; }   // convex hull of the control points grown by the radius
     mark_box(blo, bhi, nullptr);
   }
-  // levels: dilate a copy, pack, then halve the undilated occupancy
-  size_t words = 0;
-  for (uint32_t l = 0; l < pbr::kClearLevels; ++l) {
-    clear_off[l] = uint32_t(words);
-    const size_t d = R >> l;
-    words += (d * d * d + 31) / 32;
-  }
-  clear_off[pbr::kClearLevels] = uint32_t(words);
-  clear_bits.assign(words, 0u);
-  std::vector<uint8_t> cur = std::move(occ), tmp, nxt;
-  for (uint32_t l = 0; l < pbr::kClearLevels; ++l) {
-    const int d = int(R >> l);
-    tmp = cur;
-    // separable 3-wide maximum along x, y, z
-    for (int axis = 0; axis < 3; ++axis) {
-      std::vector<uint8_t> out(tmp.size());
-      const size_t stride = axis == 0 ? 1 : (axis == 1 ? size_t(d) : size_t(d) * d);
-      for (int z = 0; z < d; ++z)
-        for (int y = 0; y < d; ++y)
-          for (int x = 0; x < d; ++x) {
-            const size_t i = (size_t(z) * d + y) * d + x;
-            const int c = axis == 0 ? x : (axis == 1 ? y : z);
-            uint8_t v = tmp[i];
-            if (c > 0) v |= tmp[i - stride];
-            if (c + 1 < d) v |= tmp[i + stride];
-            out[i] = v;
-          }
-      tmp.swap(out);
+  // the outermost layer vouches for nothing: whatever lies outside the grid was not rasterised
+  for (int z = 0; z < D[2]; ++z)
+    for (int y = 0; y < D[1]; ++y) {
+      uint8_t* row = &occ[(size_t(z) * D[1] + y) * D[0]];
+      if (z == 0 || z == D[2] - 1 || y == 0 || y == D[1] - 1) memset(row, 1, size_t(D[0]));
+      else row[0] = row[D[0] - 1] = 1;
     }
-    uint32_t* bits = &clear_bits[clear_off[l]];
-    for (size_t i = 0; i < tmp.size(); ++i) if (tmp[i]) bits[i >> 5] |= 1u << (i & 31);
-    if (l + 1 < pbr::kClearLevels) {
-      const int h = d / 2;
-      nxt.assign(size_t(h) * h * h, 0);
-      for (int z = 0; z < d; ++z)
-        for (int y = 0; y < d; ++y)
-          for (int x = 0; x < d; ++x)
-            if (cur[(size_t(z) * d + y) * d + x]) nxt[(size_t(z / 2) * h + y / 2) * h + x / 2] = 1;
-      cur.swap(nxt);
-    }
+  // dilate by one cell (separable 3-wide maximum), then the squared distance transform along x, y, z
+  const float kFar = 1e12f;
+  std::vector<float> d2(ncell);
+  const int maxd = std::max(D[0], std::max(D[1], D[2]));
+  // pass x: dilation along x folded into the seed (a cell is a seed if it or an x-neighbour is occupied after the
+  // y/z dilation below) -> do the y/z dilation first
+  {
+    std::vector<uint8_t> tmp(ncell);
+    ParallelFor(D[2], [&](int z) {
+      for (int y = 0; y < D[1]; ++y)
+        for (int x = 0; x < D[0]; ++x) {
+          const size_t i = (size_t(z) * D[1] + y) * D[0] + x;
+          uint8_t v = occ[i];
+          if (y > 0) v |= occ[i - D[0]];
+          if (y + 1 < D[1]) v |= occ[i + D[0]];
+          tmp[i] = v;
+        }
+    });
+    const size_t sz = size_t(D[0]) * D[1];
+    ParallelFor(D[2], [&](int z) {
+      for (size_t j = 0; j < sz; ++j) {
+        const size_t i = size_t(z) * sz + j;
+        uint8_t v = tmp[i];
+        if (z > 0) v |= tmp[i - sz];
+        if (z + 1 < D[2]) v |= tmp[i + sz];
+        occ[i] = v;
+      }
+    });
+    ParallelFor(D[2], [&](int z) {
+      for (int y = 0; y < D[1]; ++y) {
+        const size_t r = (size_t(z) * D[1] + y) * D[0];
+        for (int x = 0; x < D[0]; ++x) {
+          uint8_t v = occ[r + x];
+          if (x > 0) v |= occ[r + x - 1];
+          if (x + 1 < D[0]) v |= occ[r + x + 1];
+          d2[r + x] = v ? 0.f : kFar;
+        }
+      }
+    });
   }
+  ParallelFor(D[2], [&](int z) {   // along x
+    std::vector<float> zb(maxd + 1), ob(maxd); std::vector<int> vb(maxd);
+    for (int y = 0; y < D[1]; ++y) Edt1D(&d2[(size_t(z) * D[1] + y) * D[0]], D[0], zb.data(), vb.data(), ob.data());
+  });
+  ParallelFor(D[2], [&](int z) {   // along y
+    std::vector<float> zb(maxd + 1), ob(maxd), col(maxd); std::vector<int> vb(maxd);
+    for (int x = 0; x < D[0]; ++x) {
+      float* base = &d2[size_t(z) * D[1] * D[0] + x];
+      for (int y = 0; y < D[1]; ++y) col[y] = base[size_t(y) * D[0]];
+      Edt1D(col.data(), D[1], zb.data(), vb.data(), ob.data());
+      for (int y = 0; y < D[1]; ++y) base[size_t(y) * D[0]] = col[y];
+    }
+  });
+  ParallelFor(D[1], [&](int y) {   // along z
+    std::vector<float> zb(maxd + 1), ob(maxd), col(maxd); std::vector<int> vb(maxd);
+    const size_t sz = size_t(D[0]) * D[1];
+    for (int x = 0; x < D[0]; ++x) {
+      float* base = &d2[size_t(y) * D[0] + x];
+      for (int z = 0; z < D[2]; ++z) col[z] = base[size_t(z) * sz];
+      Edt1D(col.data(), D[2], zb.data(), vb.data(), ob.data());
+      for (int z = 0; z < D[2]; ++z) base[size_t(z) * sz] = col[z];
+    }
+  });
+  clear_dist.assign((ncell + 3) / 4, 0u);
+  uint8_t* q = reinterpret_cast<uint8_t*>(clear_dist.data());
+  ParallelFor(D[2], [&](int z) {
+    const size_t sz = size_t(D[0]) * D[1];
+    for (size_t i = size_t(z) * sz; i < size_t(z + 1) * sz; ++i) {
+      // floor(4 d) with a hair of slack for the float arithmetic of the transform
+      const float d = std::sqrt(std::min(d2[i], 1e8f)) * 4.0f * 0.9999f;
+      q[i] = uint8_t(std::min(255.0f, std::floor(d)));
+    }
+  });
 }
 
 pbr::SceneView HostScene::HostView() const {
@@ -460,6 +582,7 @@ pbr::SceneView HostScene::HostView() const {
   v.curve_nodes = reinterpret_cast<const float4*>(curve_bvh.nodes.data());
   v.curve_data = reinterpret_cast<const float4*>(curve_data.data());
   v.curve_prim = curve_prim.data();
+  v.curve_cull = curve_cull.empty() ? nullptr : reinterpret_cast<const float2*>(curve_cull.data());
   v.num_tris = num_tris();
   v.num_curves = num_curves();
   v.tri_ids = reinterpret_cast<const uint4*>(tri_ids.data());
@@ -484,11 +607,10 @@ pbr::SceneView HostScene::HostView() const {
   v.lprim_cdf = lprim_cdf.data();
   v.lprim_info = reinterpret_cast<const float4*>(lprim_info.data());
   v.lprim_tri = lprim_tri.data();
-  v.clear_bits = clear_bits.empty() ? nullptr : clear_bits.data();
-  for (int k = 0; k < 3; ++k) { v.clear_org[k] = clear_org[k]; v.clear_inv_cell[k] = clear_inv_cell[k]; }
-  v.clear_cell_min = clear_cell_min;
-  v.clear_dim = clear_dim;
-  for (int k = 0; k < 6; ++k) v.clear_off[k] = clear_off[k];
+  v.clear_dist = clear_dist.empty() ? nullptr : reinterpret_cast<const uint8_t*>(clear_dist.data());
+  for (int k = 0; k < 3; ++k) { v.clear_org[k] = clear_org[k]; v.clear_dims[k] = clear_dims[k]; }
+  v.clear_inv_cell = clear_inv_cell;
+  v.clear_quantum = clear_quantum;
   return v;
 }
 

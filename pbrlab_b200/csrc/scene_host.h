@@ -41,11 +41,12 @@ struct HostScene {
   std::vector<F4> tri_data;      // 3 per triangle, leaf order
   std::vector<F4> curve_data;    // 4 per segment, leaf order
   std::vector<uint32_t> curve_prim;
+  std::vector<float> curve_cull;   // 2 per segment, leaf order (device/traverse.cuh: CurveMayHit)
   float bmin[3], bmax[3];
   // clearance grid for random-walk segments (see device/scene_view.cuh); empty when no material scatters
-  std::vector<uint32_t> clear_bits;
-  float clear_org[3] = {0, 0, 0}, clear_inv_cell[3] = {0, 0, 0}, clear_cell_min = 0.f;
-  uint32_t clear_dim = 0, clear_off[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<uint32_t> clear_dist;   // one byte per cell, packed
+  float clear_org[3] = {0, 0, 0}, clear_inv_cell = 0.f, clear_quantum = 0.f;
+  uint32_t clear_dims[3] = {0, 0, 0};
   bool committed = false;
   double build_seconds = 0.0;
 

@@ -1,4 +1,4 @@
-"""One small render for profiling: python scripts/render_once.py W H SPP [warmup]"""
+"""One small render for profiling: python scripts/render_once.py W H SPP [warmup] [c3|c4|c5|files...]"""
 import os
 import sys
 import time
@@ -11,6 +11,13 @@ from pbrlab_b200 import scenes  # noqa: E402
 w, h, spp = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 warm = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 files = sys.argv[5:] if len(sys.argv) > 5 else [scenes.cornell()]
+hair = dict(n_strands=50000, n_points=21, radius=1.2, length=2.5, thickness=0.008)
+if files == ["c3"]:
+    files = [scenes.light_stage(), scenes.cyhair(center=(-2.5, 3.5, 0.0), **hair)]
+elif files == ["c4"]:
+    files = [scenes.cornell(), scenes.cyhair(center=(-2.5, 6.0, 0.0), **hair)]
+elif files == ["c5"]:
+    files = [scenes.displaced(20_000_000)]
 S = pb.Scene(files)
 ctx = S.context()
 for _ in range(warm):

@@ -75,6 +75,18 @@ class Emul:
         self.lib.emul_radiance(self.h, _p(rays), _p(seeds), C.c_uint64(len(rays)), _p(out), _p(c))
         return (out, c) if counts else out
 
+    def curve_probe(self):
+        """(curve leaf tests, tests that passed CurveMayHit) since the last call"""
+        o = np.zeros(2, np.uint64)
+        self.lib.emul_curve_probe(_p(o))
+        return [int(x) for x in o]
+
+    def clearance_probe(self):
+        """(walk segments, segments the clearance field skips, skipped segments that hit) since the last call"""
+        o = np.zeros(3, np.uint64)
+        self.lib.emul_clearance_probe(_p(o))
+        return [int(x) for x in o]
+
     def shade(self, rays, seeds):
         rays = np.ascontiguousarray(rays); seeds = np.ascontiguousarray(seeds, np.uint64)
         out = np.zeros((len(rays), 16), np.float32)

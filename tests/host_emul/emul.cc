@@ -8,6 +8,15 @@
 #include <thread>
 #include <vector>
 
+// walk segments seen by PathRadiance: [0] all, [1] the clearance field says "cannot hit", [2] of those, segments that hit
+static std::atomic<uint64_t> g_clear_probe[3];
+#define PBR_CLEARANCE_PROBE(clear, hit) \
+  do { const bool c_ = (clear); ++g_clear_probe[0]; if (c_) { ++g_clear_probe[1]; if (hit) ++g_clear_probe[2]; } } while (0)
+
+// curve leaf tests: [0] all, [1] those that pass CurveMayHit and run the full ribbon test
+static std::atomic<uint64_t> g_curve_probe[2];
+#define PBR_CURVE_PROBE(may) do { ++g_curve_probe[0]; if (may) ++g_curve_probe[1]; } while (0)
+
 #include "../../pbrlab_b200/csrc/kat.cuh"
 #include "../../pbrlab_b200/csrc/scene_host.h"
 
@@ -149,6 +158,15 @@ int emul_radiance(void* h, const pbrgpu_ray* rays, const uint64_t* seeds, uint64
   });
   if (counts3) { counts3[0] = c0; counts3[1] = c1; counts3[2] = c2; }
   return 0;
+}
+
+void emul_curve_probe(uint64_t* out2) {
+  for (int k = 0; k < 2; ++k) out2[k] = g_curve_probe[k].exchange(0);
+}
+
+// counters of PBR_CLEARANCE_PROBE since the last call (and reset)
+void emul_clearance_probe(uint64_t* out3) {
+  for (int k = 0; k < 3; ++k) out3[k] = g_clear_probe[k].exchange(0);
 }
 
 // one shading vertex, layout of pbrgpu_shade

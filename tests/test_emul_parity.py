@@ -122,3 +122,44 @@ def test_render_sample_split_is_additive(cornell_emul):
     assert np.array_equal(ca + cb, cfull) and np.all(cfull == 6)
     assert np.allclose(a + b, full, rtol=1e-5, atol=1e-6)
     assert np.all(full[..., 3] == 6.0)
+
+
+def test_curve_cull_never_changes_a_hit(hair_host, monkeypatch):
+    """CurveMayHit (the line-distance rejection ahead of the ribbon test) is conservative: with and without it every
+    ray reports bit-identical hits, while most leaf candidates are rejected by it"""
+    import emulbind
+    with_cull = emulbind.Emul(hair_host.flat())
+    monkeypatch.setenv("PBRGPU_NO_CURVE_CULL", "1")
+    without = emulbind.Emul(hair_host.flat())
+    monkeypatch.delenv("PBRGPU_NO_CURVE_CULL")
+    rng = np.random.default_rng(3)
+    n = 200000
+    # origins in a box around the hair ball, directions uniform; a third of the rays are short (walk / shadow like)
+    org = (np.array([-2.5, 5.0, 0.0]) + rng.uniform(-2.0, 2.0, (n, 3))).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    tmax = np.where(rng.random(n) < 0.33, rng.exponential(0.3, n), 1.844e18).astype(np.float32)
+    rays = pb.make_rays(org, d, tmin=1e-3)
+    rays["tmax"] = tmax
+    with_cull.curve_probe()
+    a = with_cull.trace(rays)
+    tested, passed = with_cull.curve_probe()
+    b = without.trace(rays)
+    for k in ("t", "u", "v", "instance_id", "geom_id", "prim_id"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(with_cull.occluded(rays), without.occluded(rays))
+    assert (a["instance_id"] == 9).sum() > 10000            # plenty of curve hits in the batch
+    assert tested > 0 and passed < 0.5 * tested, (tested, passed)
+    with_cull.close(); without.close()
+
+
+def test_clearance_field_only_skips_segments_that_miss(cornell_emul):
+    """every random-walk segment the clearance field (SegmentIsClear) would answer without a query is a segment the
+    query reports "no hit" for — so skipping changes nothing — and it answers a good share of them"""
+    g = golden("cornell_paths.npz")
+    cornell_emul.clearance_probe()
+    cornell_emul.radiance(common.rays_from_f8(g["rays"]), g["seeds"])
+    segments, skipped, wrong = cornell_emul.clearance_probe()
+    assert segments > 20000
+    assert wrong == 0
+    assert skipped > 0.3 * segments, (skipped, segments)
