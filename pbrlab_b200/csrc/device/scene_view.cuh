@@ -37,10 +37,12 @@ struct SceneView {
   const float4* tri_nodes;     // 5 x float4 per 8-wide compressed node; root = node 0
   const float4* tri_data;      // leaf-ordered, 3 x float4 per triangle: (v0, prim id) (e1=v0-v1, 0) (e2=v2-v0, 0)
   const float4* curve_nodes;
-  const float4* curve_data;    // leaf-ordered, 4 x float4 (xyz, radius) per cubic Bezier segment
-  const uint32_t* curve_prim;  // leaf order -> curve primitive id
+  const float4* curve_data;    // 4 x float4 (xyz, radius) per cubic Bezier segment, in "slot" order (spatially sorted)
+  const uint32_t* curve_prim;  // slot -> curve primitive id
+  const uint32_t* curve_sub;   // curve BVH leaf order: (slot << 2) | first quad; the BVH primitive is a PART of a segment
+  uint32_t curve_part_quads;   // quads (quarter sub-segments) per part: 4 (whole segments), 2 or 1
   uint32_t ribbon_min_lanes;   // traversal engine: lanes holding a curve candidate that trigger a ribbon phase
-  const float2* curve_cull;    // leaf order: (capsule radius around the line c0c3, |c3 - c0|), see CurveMayHit; may be null
+  const float4* curve_cull;    // slot order, 2 per segment: (c0, capsule radius around the line c0c3), (c3 - c0, |c3 - c0|), see CurveMayHit; may be null
   uint32_t num_tris, num_curves;
   uint32_t bias_magic;         // kBiasMagic (traverse.cuh), as a run-time value on purpose
   // ---- per-primitive shading tables (indexed by primitive id = order given to pbrgpu_set_*)

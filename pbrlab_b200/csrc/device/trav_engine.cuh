@@ -26,7 +26,7 @@ struct Trav {
   int sp;                  // stack entries in use
   bool active;             // still traversing
   bool curves;             // walking the curve BVH (after the triangle BVH)
-  uint32_t held;           // curve segment (leaf order) that passed CurveMayHit and waits for the ribbon test; kInvalid: none
+  uint32_t held;           // curve part ((slot << 2) | first quad) that passed CurveMayHit and waits for the ribbon test; kInvalid: none
   HitT hit;                // closest hit so far (prim == kInvalid: none)
   uint32_t n_nodes, n_prims;   // STATS only
 };
@@ -135,26 +135,26 @@ __device__ __forceinline__ void TravTriStep(const SceneView& s, Trav& t) {
 // kernel's instructions executed with ONE active lane.
 template <bool STATS>
 __device__ __forceinline__ void TravCurveCullStep(const SceneView& s, Trav& t) {
-  const float4* __restrict__ prims = s.curve_data;
+  const float4* __restrict__ cull = s.curve_cull;
   do {
     const uint32_t bit = msb(t.pgroup.y);
     t.pgroup.y &= ~(1u << bit);
-    const uint32_t idx = t.pgroup.x + bit;
+    const uint32_t code = s.curve_sub[t.pgroup.x + bit];   // (slot << 2) | first quad of the part
+    const uint32_t idx = code >> 2;
     if (STATS) t.n_prims++;
-    const float4 c0 = prims[idx * 4 + 0], c3 = prims[idx * 4 + 3];
-    if (!s.curve_cull || CurveMayHit(t.O, t.D, c0, c3, s.curve_cull[idx])) t.held = idx;
+    if (!cull || CurveMayHit(t.O, t.D, cull[idx * 2], cull[idx * 2 + 1])) t.held = code;
   } while (t.held == kInvalid && t.pgroup.y != 0u);
 }
 
 template <bool ANY>
 __device__ __forceinline__ void TravRibbonStep(const SceneView& s, Trav& t) {
-  const uint32_t idx = t.held;
+  const uint32_t code = t.held, idx = code >> 2;
   t.held = kInvalid;
   const float4* __restrict__ prims = s.curve_data;
   const float4 c0 = prims[idx * 4 + 0], c1 = prims[idx * 4 + 1], c2 = prims[idx * 4 + 2], c3 = prims[idx * 4 + 3];
   const CurveRaySpace rs = MakeCurveRaySpace(t.D);
   float ht, hu, hv;
-  if (IntersectCurve(t.O, rs, t.tmin, t.tfar, c0, c1, c2, c3, &ht, &hu, &hv)) {
+  if (IntersectCurve(t.O, rs, t.tmin, t.tfar, c0, c1, c2, c3, code & 3u, s.curve_part_quads, &ht, &hu, &hv)) {
     t.hit.t = ht; t.hit.u = hu; t.hit.v = hv;
     t.hit.prim = idx | kCurveFlag;
     t.tfar = ht;

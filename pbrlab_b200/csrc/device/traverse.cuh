@@ -21,7 +21,7 @@ struct RayT {
 };
 struct HitT {
   float t, u, v;
-  uint32_t prim;   // leaf-order index; bit 31 set = curve segment; kInvalid = miss
+  uint32_t prim;   // triangle: leaf-order index; curve: bit 31 | segment slot; kInvalid = miss
 };
 constexpr uint32_t kCurveFlag = 0x80000000u;
 constexpr int kStackSize = 32;
@@ -59,6 +59,13 @@ struct CurveRaySpace {
   vec3 dx, dy, dz;   // rows of the transposed frame: p_ray = (dot(dx,p), dot(dy,p), dot(dz,p))
   float depth_scale;
 };
+PBR_HD uint32_t lowest_bit(uint32_t x) {   // x != 0
+#if defined(__CUDA_ARCH__)
+  return uint32_t(__ffs(int(x)) - 1);
+#else
+  return uint32_t(__builtin_ctz(x));
+#endif
+}
 PBR_HD vec3 enormalize(const vec3& v) { return v * (1.0f / sqrtf(edot(v, v))); }
 PBR_HD CurveRaySpace MakeCurveRaySpace(const vec3& D) {
   CurveRaySpace s;
@@ -108,15 +115,18 @@ PBR_HD vec3 CurveTangent(const float4& c0, const float4& c1, const float4& c2, c
 // (the corners are at distance r from the chord's ends and a capsule is convex); every point of the curve, hence of
 // those chords, lies within `dev` = max distance of the inner control points from the line c0c3 (convex hull).  So a
 // ray that hits the ribbon passes within R = r_max + dev of the LINE through c0 and c3: if the distance between the
-// two lines is larger, the full test cannot succeed.  cull = (R with its safety factor, |c3 - c0|), built at commit
-// (scene_host.cc); the second term bounds the rounding error of the triple product (2^-22 |w| |D| |e|).
-PBR_HD bool CurveMayHit(const vec3& O, const vec3& D, const float4& c0, const float4& c3, const float2& cull) {
-  const vec3 e(c3.x - c0.x, c3.y - c0.y, c3.z - c0.z);
-  const vec3 w(c0.x - O.x, c0.y - O.y, c0.z - O.z);
+// two lines is larger, the full test cannot succeed.  The test reads its own 32-byte record per segment
+// (c0, R with its safety factor | c3 - c0, its length), built at commit (scene_host.cc), so the 64 bytes of control
+// points are only fetched for the one candidate in six that passes; the second term bounds the rounding error of
+// the triple product (2^-22 |w| |D| |e|).
+PBR_HD bool CurveMayHit(const vec3& O, const vec3& D, const float4& a, const float4& b) {
+  // a = (c0.xyz, R), b = (c3 - c0, |c3 - c0|)
+  const vec3 e(b.x, b.y, b.z);
+  const vec3 w(a.x - O.x, a.y - O.y, a.z - O.z);
   const vec3 n = ecross(D, e);
   const float q = edot(w, n);
   const float nn = edot(n, n), ww = edot(w, w), dd = edot(D, D);
-  return !(fabsf(q) > cull.x * sqrtf(nn) + 3e-7f * (sqrtf(ww * dd) * cull.y));
+  return !(fabsf(q) > a.w * sqrtf(nn) + 3e-7f * (sqrtf(ww * dd) * b.w));
 }
 
 // One cubic segment against the ray: Embree's ribbon intersector (curve_intersector_ribbon.h:72-177) — the curve is
@@ -128,9 +138,10 @@ PBR_HD bool CurveMayHit(const vec3& O, const vec3& D, const float4& c0, const fl
 //     p0 +- r0 n0, p1 +- r1 n1 with unit n in the xy plane, all inside the (convex) 2-D capsule of radius max(r0, r1)
 //     around p0p1, and so is the quad; a ray outside the capsule cannot hit it.  Near-collinear sub-segments all pass
 //     the line test, this one keeps the one or two the ray actually crosses.
+// [first_quad, first_quad + num_quads): the quads this BVH primitive stands for (0, 4 = the whole segment).
 PBR_HD bool IntersectCurve(const vec3& O, const CurveRaySpace& rs, float tnear, float tfar, const float4& c0,
-                           const float4& c1, const float4& c2, const float4& c3, float* t_out, float* u_out,
-                           float* v_out) {
+                           const float4& c1, const float4& c2, const float4& c3, uint32_t first_quad,
+                           uint32_t num_quads, float* t_out, float* u_out, float* v_out) {
   // control points in ray space (xfm_pr): position relative to the origin, radius carried in w
   const vec3 q0 = ToRaySpace(rs, vec3(c0.x, c0.y, c0.z) - O);
   const vec3 q1 = ToRaySpace(rs, vec3(c1.x, c1.y, c1.z) - O);
@@ -149,13 +160,10 @@ PBR_HD bool IntersectCurve(const vec3& O, const CurveRaySpace& rs, float tnear, 
     float px0, py0, pr0;
     {
       float b[4];
-      BezierBasis(0.0f, b);
+      BezierBasis(float(first_quad) / 4.0f, b);
       px0 = bz(b, q0.x, q1.x, q2.x, q3.x); py0 = bz(b, q0.y, q1.y, q2.y, q3.y); pr0 = bz(b, c0.w, c1.w, c2.w, c3.w);
     }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < 4; ++i) {
+    for (uint32_t i = first_quad; i < first_quad + num_quads; ++i) {
       float b[4];
       BezierBasis(float(i + 1) / 4.0f, b);
       const float px1 = bz(b, q0.x, q1.x, q2.x, q3.x), py1 = bz(b, q0.y, q1.y, q2.y, q3.y),
@@ -180,9 +188,9 @@ PBR_HD bool IntersectCurve(const vec3& O, const CurveRaySpace& rs, float tnear, 
   // ---- stage 2: the quad of every surviving sub-segment, in ascending order
   bool found = false;
   float best_t = 0.f, best_u = 0.f, best_v = 0.f;
+  // (straight-line body, no early exits: the lanes of a warp that are in this loop stay converged)
   while (mask != 0u) {
-    int i = 0;
-    while (!((mask >> i) & 1u)) ++i;
+    const int i = int(lowest_bit(mask));
     mask &= mask - 1u;
     float b0[4], b1[4], d0[4], d1[4];
     BezierBasis(float(i) / 4.0f, b0);
@@ -216,20 +224,19 @@ PBR_HD bool IntersectCurve(const vec3& O, const CurveRaySpace& rs, float tnear, 
     const vec3 e1 = v0 - v1;
     const float U = ecross(v0, e0).z;
     const float V = ecross(v1, e1).z;
-    if (!(fmaxf(U, V) <= 0.0f)) continue;
+    bool ok = fmaxf(U, V) <= 0.0f;
     const vec3 Ng = ecross(e1, e0);
     const float den = Ng.z;
     const float rcpDen = 1.0f / den;
     const float t = rcpDen * edot(v0, Ng);
-    if (!((tnear <= t) & (t <= tfar))) continue;
-    if (!(den != 0.0f)) continue;
+    ok = ok & (tnear <= t) & (t <= tfar) & (den != 0.0f);
     float u = U * rcpDen, v = V * rcpDen;
     u = first ? u : 1.0f - u;
     v = first ? v : 1.0f - v;
     // self-intersection avoidance (EMBREE_CURVE_SELF_INTERSECTION_AVOIDANCE_FACTOR 2.0)
     const float r = u * (p1.w - p0.w) + p0.w;                        // lerp = madd(t, b-a, a)
-    if (!(t > 2.0f * r * rs.depth_scale)) continue;
-    if (!found || t < best_t) {   // select_min over the 4 lanes: lowest t, lowest lane on ties
+    ok = ok & (t > 2.0f * r * rs.depth_scale);
+    if (ok && (!found || t < best_t)) {   // select_min over the 4 lanes: lowest t, lowest lane on ties
       found = true;
       best_t = t;
       best_u = (float(i) + u + 0.0f) * (1.0f / 4.0f);
@@ -335,8 +342,8 @@ PBR_HD uint32_t NodeIntersect(const vec3& o_over_d, const vec3& inv_d, uint32_t 
 // Generic traversal of one BVH.  CURVES selects the leaf test, ANY the early-out.
 template <bool CURVES, bool ANY, bool STATS>
 PBR_HD bool TraverseBvh(const float4* __restrict__ nodes, const float4* __restrict__ prims,
-                        const float2* __restrict__ cull, const RayT& ray, float* tfar_io, HitT* hit,
-                        TraverseStats* st) {
+                        const float4* __restrict__ cull, const uint32_t* __restrict__ sub, uint32_t part_quads,
+                        const RayT& ray, float* tfar_io, HitT* hit, TraverseStats* st) {
   const vec3 O = ray.o, D = ray.d;
   // slab-test direction: zero components are nudged so 1/d stays finite (sign kept)
   const float tiny = 1e-30f;
@@ -384,20 +391,22 @@ PBR_HD bool TraverseBvh(const float4* __restrict__ nodes, const float4* __restri
     while (pgroup.y != 0u) {
       const uint32_t bit = msb(pgroup.y);
       pgroup.y &= ~(1u << bit);
-      const uint32_t idx = pgroup.x + bit;
+      uint32_t idx = pgroup.x + bit;
       if (STATS) st->prims++;
       float t, u, v;
       bool h;
       if (CURVES) {
-        const float4 c0 = prims[idx * 4 + 0], c3 = prims[idx * 4 + 3];
         h = false;
-        const bool may = !cull || CurveMayHit(O, D, c0, c3, cull[idx]);
+        const uint32_t code = sub[idx];   // the BVH primitive is a part of a segment: (slot << 2) | first quad
+        idx = code >> 2;
+        const bool may = !cull || CurveMayHit(O, D, cull[idx * 2], cull[idx * 2 + 1]);
 #ifdef PBR_CURVE_PROBE   // tests/host_emul only
         PBR_CURVE_PROBE(may);
 #endif
         if (may) {
-          const float4 c1 = prims[idx * 4 + 1], c2 = prims[idx * 4 + 2];
-          h = IntersectCurve(O, rs, ray.tmin, tfar, c0, c1, c2, c3, &t, &u, &v);
+          const float4 c0 = prims[idx * 4 + 0], c1 = prims[idx * 4 + 1], c2 = prims[idx * 4 + 2],
+                       c3 = prims[idx * 4 + 3];
+          h = IntersectCurve(O, rs, ray.tmin, tfar, c0, c1, c2, c3, code & 3u, part_quads, &t, &u, &v);
         }
       } else {
         const float4 a = prims[idx * 3 + 0], b = prims[idx * 3 + 1], c = prims[idx * 3 + 2];
@@ -426,8 +435,8 @@ PBR_HD bool TraceClosest(const SceneView& s, const RayT& ray, HitT* hit, Travers
   float tfar = ray.tmax;
   hit->prim = kInvalid;
   bool found = false;
-  if (s.num_tris) found |= TraverseBvh<false, false, STATS>(s.tri_nodes, s.tri_data, nullptr, ray, &tfar, hit, st);
-  if (s.num_curves) found |= TraverseBvh<true, false, STATS>(s.curve_nodes, s.curve_data, s.curve_cull, ray, &tfar, hit, st);
+  if (s.num_tris) found |= TraverseBvh<false, false, STATS>(s.tri_nodes, s.tri_data, nullptr, nullptr, 0u, ray, &tfar, hit, st);
+  if (s.num_curves) found |= TraverseBvh<true, false, STATS>(s.curve_nodes, s.curve_data, s.curve_cull, s.curve_sub, s.curve_part_quads, ray, &tfar, hit, st);
   return found;
 }
 
@@ -436,8 +445,8 @@ template <bool STATS>
 PBR_HD bool TraceAny(const SceneView& s, const RayT& ray, TraverseStats* st) {
   float tfar = ray.tmax;
   HitT hit;
-  if (s.num_tris && TraverseBvh<false, true, STATS>(s.tri_nodes, s.tri_data, nullptr, ray, &tfar, &hit, st)) return true;
-  if (s.num_curves && TraverseBvh<true, true, STATS>(s.curve_nodes, s.curve_data, s.curve_cull, ray, &tfar, &hit, st)) return true;
+  if (s.num_tris && TraverseBvh<false, true, STATS>(s.tri_nodes, s.tri_data, nullptr, nullptr, 0u, ray, &tfar, &hit, st)) return true;
+  if (s.num_curves && TraverseBvh<true, true, STATS>(s.curve_nodes, s.curve_data, s.curve_cull, s.curve_sub, s.curve_part_quads, ray, &tfar, &hit, st)) return true;
   return false;
 }
 

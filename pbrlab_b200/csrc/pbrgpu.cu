@@ -68,7 +68,7 @@ struct Device {
   DevBuf<float4> geom;   // [tri_nodes | tri_data | curve_nodes | curve_data]: one range for the L2 persistence window
   DevBuf<float4> verts, normals, emissive, lprim_info;
   DevBuf<float2> texcoords;
-  DevBuf<uint32_t> curve_prim, lprim_tri, clear_dist, material_class;
+  DevBuf<uint32_t> curve_prim, curve_sub, lprim_tri, clear_dist, material_class;
   DevBuf<float> curve_cull;
   DevBuf<float> tex_pixels;
   DevBuf<pbr::TexDesc> tex_desc;
@@ -95,7 +95,7 @@ struct Device {
   void Release() {
     geom.Free(); clear_dist.Free(); verts.Free(); normals.Free(); material_class.Free(); tex_pixels.Free();
     tex_desc.Free(); q_diffuse.Free(); srgb8.Free();
-    emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); curve_cull.Free(); lprim_tri.Free(); tri_ids.Free();
+    emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); curve_sub.Free(); curve_cull.Free(); lprim_tri.Free(); tri_ids.Free();
     tri_nidx.Free(); tri_vidx.Free(); tri_tidx.Free(); curve_ids.Free(); materials.Free(); light_cdf.Free();
     lprim_cdf.Free(); lights.Free();
     slot.Free(); walk.Free(); sh_o.Free(); sh_d.Free(); sh_c.Free();
@@ -195,6 +195,7 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
     }
   }
   CUDA_TRY(ctx, d.curve_prim.Upload(h.curve_prim.data(), h.curve_prim.size(), st));
+  CUDA_TRY(ctx, d.curve_sub.Upload(h.curve_sub.data(), h.curve_sub.size(), st));
   CUDA_TRY(ctx, d.curve_cull.Upload(h.curve_cull.data(), h.curve_cull.size(), st));
   CUDA_TRY(ctx, d.tri_ids.Upload(h.tri_ids.data(), h.tri_ids.size(), st));
   CUDA_TRY(ctx, d.tri_nidx.Upload(h.tri_nidx.data(), h.tri_nidx.size(), st));
@@ -220,8 +221,9 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   memset(&v, 0, sizeof(v));
   v.tri_nodes = g_tn; v.tri_data = g_td;
   v.curve_nodes = g_cn; v.curve_data = g_cd; v.curve_prim = d.curve_prim.ptr;
+  v.curve_sub = d.curve_sub.ptr; v.curve_part_quads = h.curve_part_quads;
   v.ribbon_min_lanes = ctx->tune_ribbon_lanes;
-  v.curve_cull = h.curve_cull.empty() ? nullptr : reinterpret_cast<const float2*>(d.curve_cull.ptr);
+  v.curve_cull = h.curve_cull.empty() ? nullptr : reinterpret_cast<const float4*>(d.curve_cull.ptr);
   v.num_tris = h.num_tris(); v.num_curves = h.num_curves();
   v.bias_magic = pbr::kBiasMagic;
   v.tri_ids = d.tri_ids.ptr; v.tri_nidx = d.tri_nidx.ptr; v.tri_vidx = d.tri_vidx.ptr; v.tri_tidx = d.tri_tidx.ptr;

@@ -255,19 +255,30 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
     tri_bvh = pbrbvh::Bvh8();
   }
 
-  // ---- curves: a segment's ribbon lies inside the union of balls (B(i/4), r(i/4)), i = 0..4
-  curve_data.clear(); curve_prim.clear();
+  // ---- curves.  Embree's ribbon intersector cuts a segment at u = 0, 1/4, .. 1 into four ray-facing quads; each
+  // quad lies inside the capsule of radius max(r_a, r_b) around the chord between consecutive cut points.  The BVH is
+  // built over PARTS of segments (curve_split = 1, 2 or 4 parts of 4, 2 or 1 quads): boxes of thin diagonal segments
+  // are mostly empty and hair is nothing but such segments; four parts have a quarter of the surface area.  A part
+  // is tested like the whole segment, restricted to its quads, so the hits are those of the unsplit segment.
+  curve_data.clear(); curve_prim.clear(); curve_sub.clear();
   if (nc) {
-    std::vector<pbrbvh::Aabb> boxes(nc);
+    int split = 4;
+    if (const char* e = getenv("PBRGPU_CURVE_SPLIT")) split = atoi(e);
+    if (split != 1 && split != 2 && split != 4) split = 4;
+    if (uint64_t(nc) * uint64_t(split) > 0x3fffffffull) split = 1;
+    if (nc > 0x1fffffffu) { error = "pbrgpu_commit: too many curve segments"; return false; }
+    const uint32_t quads_per_part = uint32_t(4 / split);
+    curve_part_quads = quads_per_part;
+    std::vector<pbrbvh::Aabb> boxes(size_t(nc) * split);
     for (uint32_t i = 0; i < nc; ++i) {
       const F4* cp = &curve_cps[4 * size_t(i)];
-      pbrbvh::Aabb& bx = boxes[i];
-      for (int k = 0; k < 3; ++k) { bx.lo[k] = FLT_MAX; bx.hi[k] = -FLT_MAX; }
       // Embree accurateFlatBounds(4): bbox of B(0), B(1/4), B(1/2), B(3/4) and v3, enlarged by the largest |r| of
       // those points (kernels/subdiv/bezier_curve.h:631-640) — this is what feeds rtcGetSceneBounds, hence the camera
       float ebl[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ebh[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, er = 0.f;
+      float pts[5][4];
+      float mag = 0.f;
       for (int j = 0; j <= 4; ++j) {
-        float p[4];
+        float* p = pts[j];
         if (j < 4) {
           float b[4];
           BezierBasisQuarter(j, b);
@@ -276,13 +287,23 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
         } else {
           p[0] = cp[3].x; p[1] = cp[3].y; p[2] = cp[3].z; p[3] = cp[3].w;
         }
-        const float r = std::fabs(p[3]);
-        er = std::max(er, r);
+        er = std::max(er, std::fabs(p[3]));
         for (int k = 0; k < 3; ++k) {
           ebl[k] = std::min(ebl[k], p[k]); ebh[k] = std::max(ebh[k], p[k]);
-          // BVH box: small safety margin on top of the exact ball bound
-          bx.lo[k] = std::min(bx.lo[k], p[k] - r * 1.0001f);
-          bx.hi[k] = std::max(bx.hi[k], p[k] + r * 1.0001f);
+          mag = std::max(mag, std::fabs(p[k]));
+        }
+      }
+      // BVH boxes: capsule bound per quad + a margin for the float evaluation of the cut points in ray space
+      const float slack = 16.0f * FLT_EPSILON * mag;
+      for (int part = 0; part < split; ++part) {
+        pbrbvh::Aabb& bx = boxes[size_t(i) * split + part];
+        for (int k = 0; k < 3; ++k) { bx.lo[k] = FLT_MAX; bx.hi[k] = -FLT_MAX; }
+        for (uint32_t q = part * quads_per_part; q < (part + 1) * quads_per_part; ++q) {
+          const float r = std::max(std::fabs(pts[q][3]), std::fabs(pts[q + 1][3])) * 1.0001f + slack;
+          for (int k = 0; k < 3; ++k) {
+            bx.lo[k] = std::min(bx.lo[k], std::min(pts[q][k], pts[q + 1][k]) - r);
+            bx.hi[k] = std::max(bx.hi[k], std::max(pts[q][k], pts[q + 1][k]) + r);
+          }
         }
       }
       float size = 0.f;   // enlarge_bounds: + 4 ulp of the largest coordinate (kernels/common/scene_curves.cpp:377-381)
@@ -293,17 +314,24 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
       const float pad = 4.0f * FLT_EPSILON * size;
       for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], ebl[k] - pad); hi[k] = std::max(hi[k], ebh[k] + pad); }
     }
-    if (!pbrbvh::BuildBvh8(boxes.data(), nc, prm, &curve_bvh, &err)) { error = err; return false; }
-    curve_data.resize(size_t(4) * nc);
-    curve_prim.resize(nc);
-    for (uint32_t k = 0; k < nc; ++k) {
-      const uint32_t i = curve_bvh.prim_order[k];
-      memcpy(&curve_data[4 * size_t(k)], &curve_cps[4 * size_t(i)], sizeof(F4) * 4);
-      curve_prim[k] = i;
+    const uint32_t nparts = nc * uint32_t(split);
+    if (!pbrbvh::BuildBvh8(boxes.data(), nparts, prm, &curve_bvh, &err)) { error = err; return false; }
+    // segment storage ("slots") in order of first appearance in the leaves: neighbours in space are neighbours in memory
+    std::vector<uint32_t> slot_of(nc, 0xffffffffu);
+    curve_prim.reserve(nc);
+    curve_sub.resize(nparts);
+    for (uint32_t k = 0; k < nparts; ++k) {
+      const uint32_t part = curve_bvh.prim_order[k];
+      const uint32_t i = part / uint32_t(split), j = part % uint32_t(split);
+      if (slot_of[i] == 0xffffffffu) { slot_of[i] = uint32_t(curve_prim.size()); curve_prim.push_back(i); }
+      curve_sub[k] = (slot_of[i] << 2) | (j * quads_per_part);
     }
+    curve_data.resize(size_t(4) * nc);
+    for (uint32_t k = 0; k < nc; ++k)
+      memcpy(&curve_data[4 * size_t(k)], &curve_cps[4 * size_t(curve_prim[k])], sizeof(F4) * 4);
     // CurveMayHit: capsule radius around the line c0c3 = largest |r| + largest distance of c1, c2 from that line
     // (double arithmetic, then 0.1 % + 1e-6 |coordinates| of slack for the float evaluation on the device)
-    curve_cull.assign(size_t(2) * nc, 0.f);
+    curve_cull.assign(size_t(8) * nc, 0.f);
     if (!getenv("PBRGPU_NO_CURVE_CULL")) {
       for (uint32_t k = 0; k < nc; ++k) {
         const F4* cp = &curve_data[4 * size_t(k)];
@@ -323,8 +351,11 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
           }
           R = float((rmax + dev) * 1.001 + 1e-6 * mag);
         }
-        curve_cull[2 * size_t(k)] = R;
-        curve_cull[2 * size_t(k) + 1] = float(std::sqrt(ee) * 1.0001);
+        // the device subtracts in float from these rounded values: (c0, e) only has to describe SOME line within the
+        // slack of R, which the 0.1 % + 1e-6 |coordinates| above covers
+        float* rec = &curve_cull[8 * size_t(k)];
+        rec[0] = cp[0].x; rec[1] = cp[0].y; rec[2] = cp[0].z; rec[3] = R;
+        rec[4] = float(e[0]); rec[5] = float(e[1]); rec[6] = float(e[2]); rec[7] = float(std::sqrt(ee) * 1.0001);
       }
     } else {
       curve_cull.clear();
@@ -332,6 +363,7 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
   } else {
     curve_bvh = pbrbvh::Bvh8();
     curve_cull.clear();
+    curve_part_quads = 4;
   }
 
   // ---- emissive triangle entries (LightManager::ImplicitAreaLight)
@@ -582,7 +614,9 @@ pbr::SceneView HostScene::HostView() const {
   v.curve_nodes = reinterpret_cast<const float4*>(curve_bvh.nodes.data());
   v.curve_data = reinterpret_cast<const float4*>(curve_data.data());
   v.curve_prim = curve_prim.data();
-  v.curve_cull = curve_cull.empty() ? nullptr : reinterpret_cast<const float2*>(curve_cull.data());
+  v.curve_sub = curve_sub.data();
+  v.curve_part_quads = curve_part_quads;
+  v.curve_cull = curve_cull.empty() ? nullptr : reinterpret_cast<const float4*>(curve_cull.data());
   v.num_tris = num_tris();
   v.num_curves = num_curves();
   v.tri_ids = reinterpret_cast<const uint4*>(tri_ids.data());

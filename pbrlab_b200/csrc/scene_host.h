@@ -39,9 +39,11 @@ struct HostScene {
   // ---- built by Commit()
   pbrbvh::Bvh8 tri_bvh, curve_bvh;
   std::vector<F4> tri_data;      // 3 per triangle, leaf order
-  std::vector<F4> curve_data;    // 4 per segment, leaf order
-  std::vector<uint32_t> curve_prim;
-  std::vector<float> curve_cull;   // 2 per segment, leaf order (device/traverse.cuh: CurveMayHit)
+  std::vector<F4> curve_data;    // 4 per segment, slot order
+  std::vector<uint32_t> curve_prim;   // slot -> curve primitive (segment) index of pbrgpu_set_curves
+  std::vector<uint32_t> curve_sub;    // leaf order: (slot << 2) | first quad of the part
+  uint32_t curve_part_quads = 4;      // quads (quarter sub-segments) per BVH primitive: 4, 2 or 1
+  std::vector<float> curve_cull;   // 8 per segment, slot order (device/traverse.cuh: CurveMayHit)
   float bmin[3], bmax[3];
   // clearance grid for random-walk segments (see device/scene_view.cuh); empty when no material scatters
   std::vector<uint32_t> clear_dist;   // one byte per cell, packed
