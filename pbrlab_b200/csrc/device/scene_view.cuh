@@ -77,6 +77,7 @@ struct SceneView {
   float clear_inv_cell;        // 1 / cell edge
   float clear_quantum;         // cell edge / 4
   uint32_t clear_dims[3];      // cells per axis
+  uint32_t clear_march_steps;  // SegmentIsClear: sphere-tracing steps along a segment before giving up (>= 1)
 };
 
 }  // namespace pbr

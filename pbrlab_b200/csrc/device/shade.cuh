@@ -393,24 +393,34 @@ PBR_HD bool SssBegin(const Surface& si, const Frame& entry, const PrincipledBsdf
 
 enum SssStep { kSssContinue = 0, kSssHit = 1, kSssAbsorbed = 2 };
 
-// Can a walk segment of length `len` starting at `o` (any direction) be declared free of intersections without
-// tracing it?  Most segments of a random walk are much shorter than the distance to the nearest surface, yet each one
-// costs a root-to-leaf traversal.  The clearance field answers conservatively: the byte of the cell holding `o` is a
-// lower bound of the distance from any point of that cell to any primitive of the scene; a shorter segment cannot
-// reach one.  A segment that is skipped is one the query would have reported "no hit" for, so the walk takes exactly
-// the same decisions (same random numbers, same result).
-PBR_HD bool SegmentIsClear(const SceneView& s, const vec3& o, float len) {
+// Can a walk segment (origin o, unit direction d, length len) be declared free of intersections without tracing it?
+// Most segments of a random walk stay away from the surface, yet each one costs a traversal, and a deep one: a point
+// inside a closed mesh lies inside the boxes of many BVH nodes (measured: 3x the node steps of a camera ray).  The
+// clearance field answers conservatively: the byte of the cell holding a point p is a lower bound of the distance
+// from any point of that cell to any primitive of the scene, so the stretch of the segment from p up to that
+// distance is free; the march continues from its end (sphere tracing along the segment) until the segment is
+// exhausted (clear), or a cell next to the surface is reached, or the step budget runs out (trace it).  A segment
+// that is skipped is one the query would have reported "no hit" for, so the walk takes exactly the same decisions
+// (same random numbers, same result).
+PBR_HD bool SegmentIsClear(const SceneView& s, const vec3& o, const vec3& d, float len) {
   if (!s.clear_dist) return false;
-  const float gx = (o.x - s.clear_org[0]) * s.clear_inv_cell;
-  const float gy = (o.y - s.clear_org[1]) * s.clear_inv_cell;
-  const float gz = (o.z - s.clear_org[2]) * s.clear_inv_cell;
-  if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < float(s.clear_dims[0]) && gy < float(s.clear_dims[1]) &&
-        gz < float(s.clear_dims[2])))
-    return false;
-  const uint32_t idx = (uint32_t(gz) * s.clear_dims[1] + uint32_t(gy)) * s.clear_dims[0] + uint32_t(gx);
-  const float bound = float(s.clear_dist[idx]) * s.clear_quantum;
-  // 2 % + 1/64 cell of margin: rounding of the cell index (a point a few ulps across a cell face) and of the hit point
-  return len * 1.02f + 0.0625f * s.clear_quantum < bound;
+  const float need = len * 1.02f;   // 2 % of margin: |d| = 1 up to rounding, rounding of the hit point
+  const float slack = 0.0625f * s.clear_quantum;   // a point a few ulps across a cell face
+  float t = 0.f;
+  for (uint32_t i = 0; i < s.clear_march_steps; ++i) {
+    const float gx = ((o.x + t * d.x) - s.clear_org[0]) * s.clear_inv_cell;
+    const float gy = ((o.y + t * d.y) - s.clear_org[1]) * s.clear_inv_cell;
+    const float gz = ((o.z + t * d.z) - s.clear_org[2]) * s.clear_inv_cell;
+    if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < float(s.clear_dims[0]) && gy < float(s.clear_dims[1]) &&
+          gz < float(s.clear_dims[2])))
+      return false;
+    const uint32_t idx = (uint32_t(gz) * s.clear_dims[1] + uint32_t(gy)) * s.clear_dims[0] + uint32_t(gx);
+    const float bound = float(s.clear_dist[idx]) * s.clear_quantum - slack;
+    if (!(bound > 0.f)) return false;        // next to the surface
+    t += bound * 0.98f;                       // the stretch [t, t + bound) is free; restart a little before its end
+    if (t >= need) return true;
+  }
+  return false;
 }
 
 // One iteration of the walk loop (:281-383), split at the ray query so that the wavefront's walk kernel can run the
@@ -458,7 +468,7 @@ PBR_HD SssStep SssBounce(const SceneView& s, Pcg32* rng, SssWalkState* w, HitT* 
   SssPrepareSegment(rng, w);
   const bool is_hit = TraceClosest<false>(s, w->ray, hit, nullptr);
 #ifdef PBR_CLEARANCE_PROBE   // tests/host_emul only: every segment the field would skip must be a miss
-  PBR_CLEARANCE_PROBE(SegmentIsClear(s, w->ray.o, w->ray.tmax * 1.001f), is_hit);
+  PBR_CLEARANCE_PROBE(SegmentIsClear(s, w->ray.o, w->ray.d, w->ray.tmax * 1.001f), is_hit);
 #endif
   if (rays) ++*rays;
   return SssFinishSegment(is_hit, hit->t, rng, w);

@@ -128,6 +128,7 @@ struct pbrgpu_ctx {
   uint32_t tune_prim_lanes = 1, tune_prim_lanes_sss = 1;   // lanes with pending primitives that trigger a primitive phase
   uint32_t tune_ribbon_lanes = 8;  // lanes holding a curve candidate that trigger the (batched) ribbon test
   int tune_l2_persist = 0;         // persisting-L2 window over the traversal data
+  int tune_clear_march = 4;        // sphere-tracing steps of the clearance test along a walk segment
   int tune_sss_skip = 1;           // clearance grid: random-walk segments that provably hit nothing are not traced
   int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
   int tune_pool_mi = 8;            // path slots kept in flight, in Mi (x 256 B of slot + walk lines)
@@ -239,6 +240,7 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   for (int k = 0; k < 3; ++k) { v.clear_org[k] = h.clear_org[k]; v.clear_dims[k] = h.clear_dims[k]; }
   v.clear_inv_cell = h.clear_inv_cell;
   v.clear_quantum = h.clear_quantum;
+  v.clear_march_steps = uint32_t(ctx->tune_clear_march);
   return PBRGPU_OK;
 }
 
@@ -538,6 +540,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_pool_mi = std::min(64, std::max(1, env_int("PBRGPU_POOL_MI", ctx->tune_pool_mi)));
   ctx->tune_l2_persist = env_int("PBRGPU_L2_PERSIST", ctx->tune_l2_persist);
   ctx->tune_sss_skip = env_int("PBRGPU_SSS_SKIP", ctx->tune_sss_skip);
+  ctx->tune_clear_march = std::min(64, std::max(1, env_int("PBRGPU_CLEAR_MARCH", ctx->tune_clear_march)));
   ctx->tune_sort_materials = env_int("PBRGPU_SORT_MATERIALS", ctx->tune_sort_materials);
   ctx->tune_diffuse_blocks = std::max(1, env_int("PBRGPU_DIFFUSE_BLOCKS", ctx->tune_diffuse_blocks));
   ctx->tune_diffuse_threads = std::min(pbr::kDiffuseBlock, std::max(32, env_int("PBRGPU_DIFFUSE_THREADS", ctx->tune_diffuse_threads) & ~31));

@@ -645,6 +645,7 @@ pbr::SceneView HostScene::HostView() const {
   for (int k = 0; k < 3; ++k) { v.clear_org[k] = clear_org[k]; v.clear_dims[k] = clear_dims[k]; }
   v.clear_inv_cell = clear_inv_cell;
   v.clear_quantum = clear_quantum;
+  v.clear_march_steps = 4;
   return v;
 }
 

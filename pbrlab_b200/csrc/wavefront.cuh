@@ -651,7 +651,7 @@ struct SssClient {
     // Segments that end far from any surface: the clearance grid answers those ("no hit") without a traversal; the
     // lane then waits for the next converged section like any lane whose query has finished.  (Finishing chains of
     // such segments inline was measured and is slower: the converged section serialises on the longest chain.)
-    skipped_seg = SegmentIsClear(s, walk.ray.o, walk.ray.tmax * 1.001f);
+    skipped_seg = SegmentIsClear(s, walk.ray.o, walk.ray.d, walk.ray.tmax * 1.001f);
     if (skipped_seg) t.active = false;
   }
 
