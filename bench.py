@@ -276,6 +276,10 @@ def main():
         peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "measured (MEASURED_PEAKS.json)"
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+    # the L2-resident scenes are bounded by L2 gather bandwidth, which MEASURED_PEAKS.json does not hold:
+    # node-sized (80 B) dependent random gathers over a 32 MB (L2) and a 4 GB (HBM) working set, 8 chains per thread
+    gather_l2 = ctx.measure_gather(32 << 20, 4096, 8) if rank == 0 else None
+    gather_hbm = ctx.measure_gather(4 << 30, 2048, 8) if rank == 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -302,7 +306,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "TraceClosestKernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_ray": a_ray, "rays_per_launch": rays_per_launch,
-                         "launch_ms": dur_ms, "kernel_family_ms_per_step": fam},
+                         "launch_ms": dur_ms, "kernel_family_ms_per_step": fam,
+                         "gather_80B_l2_gbs": gather_l2, "gather_80B_hbm_gbs": gather_hbm,
+                         "frac_of_l2_gather": (achieved / gather_l2) if gather_l2 else None},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:

@@ -170,6 +170,15 @@ int pbrgpu_set_profiling(pbrgpu_ctx* ctx, int enabled);
 /* samples of one pixel traced concurrently per wave (0 = choose from free memory) */
 int pbrgpu_set_wave_spp(pbrgpu_ctx* ctx, uint32_t spp_per_wave);
 
+/* Measurement hook for the roofline of the L2-resident scenes ("L2 bandwidth is not in
+ * MEASURED_PEAKS.json — measure it with a resident-working-set gather microbenchmark"): every thread of a persistent
+ * grid fetches node-sized records (80 bytes = five 128-bit loads, the traversal's access unit) at pseudo-random
+ * positions of a working set of `working_set_bytes` (resident in L2 when it is a few tens of MB, in HBM when it is
+ * GBs), `records_per_thread` times, with `chains` independent dependent-load chains per thread (1 = latency bound like
+ * a single traversal, 8 = bandwidth bound).  Reports the achieved GB/s of the best of 5 launches (CUDA events). */
+int pbrgpu_measure_gather(pbrgpu_ctx* ctx, uint64_t working_set_bytes, uint32_t records_per_thread, uint32_t chains,
+                          double* gbytes_per_s);
+
 /* ---- test hooks for the parity gates (host pointers) */
 /* closest hit / occlusion for a batch of rays: Scene::TraceFirstHit1 / AnyHit1 semantics */
 int pbrgpu_trace(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, uint64_t n, pbrgpu_hit* hits);

@@ -204,7 +204,7 @@ def gpu_lib():
                      "pbrgpu_commit", "pbrgpu_scene_bounds", "pbrgpu_render", "pbrgpu_render_device",
                      "pbrgpu_get_stats", "pbrgpu_set_wave_spp", "pbrgpu_set_profiling", "pbrgpu_trace", "pbrgpu_occluded",
                      "pbrgpu_trace_device", "pbrgpu_occluded_device", "pbrgpu_radiance", "pbrgpu_radiance_mega",
-                     "pbrgpu_shade", "pbrgpu_eval_closure"):
+                     "pbrgpu_shade", "pbrgpu_eval_closure", "pbrgpu_measure_gather"):
             getattr(L, name).restype = C.c_int
         _gpu = L
     return _gpu
@@ -273,6 +273,13 @@ class Context:
 
     def set_profiling(self, on):
         self._check(self.lib.pbrgpu_set_profiling(self.h, C.c_int(1 if on else 0)))
+
+    def measure_gather(self, working_set_bytes, records_per_thread=4096, chains=8):
+        """GB/s of node-sized (80 B) random gathers over a working set: the L2 / HBM gather roofline of the traversal"""
+        out = C.c_double(0.0)
+        self._check(self.lib.pbrgpu_measure_gather(self.h, C.c_uint64(int(working_set_bytes)),
+                                                   C.c_uint32(records_per_thread), C.c_uint32(chains), C.byref(out)))
+        return out.value
 
     def bounds(self):
         a = np.zeros(3, np.float32); b = np.zeros(3, np.float32)

@@ -26,6 +26,7 @@ struct Trav {
   int sp;                  // stack entries in use
   bool active;             // still traversing
   bool curves;             // walking the curve BVH (after the triangle BVH)
+  bool checked;            // curves: the pending primitives in pgroup have been through CurveMayHit (survivors only)
   uint32_t held;           // curve part ((slot << 2) | first quad) that passed CurveMayHit and waits for the ribbon test; kInvalid: none
   HitT hit;                // closest hit so far (prim == kInvalid: none)
   uint32_t n_nodes, n_prims;   // STATS only
@@ -48,6 +49,7 @@ __device__ __forceinline__ void TravBegin(const SceneView& s, const RayT& ray, T
   t.group = make_uint2(0u, 0x80000000u);   // the root as the only child of a virtual parent (see TraverseBvh)
   t.pgroup = make_uint2(0u, 0u);
   t.held = kInvalid;
+  t.checked = false;
   t.active = (s.num_tris | s.num_curves) != 0u;
 }
 
@@ -80,6 +82,7 @@ __device__ __forceinline__ void TravNodeStep(const SceneView& s, Trav& t, uint2*
   t.group.y = (hitmask & 0xff000000u) | extract_byte(f2u(n0.w), 3);
   t.pgroup.x = f2u(n1.y);
   t.pgroup.y = hitmask & 0x00ffffffu;
+  t.checked = false;
   if ((t.group.y & 0xff000000u) == 0u) {
     if (t.sp > 0) t.group = stack[--t.sp];
     else t.group.y = 0u;
@@ -128,22 +131,66 @@ __device__ __forceinline__ void TravTriStep(const SceneView& s, Trav& t) {
   }
 }
 
-// Pending CURVE segments of the lane.  Leaf boxes of thin diagonal segments are much fatter than the ribbon: 5 of 6
-// candidates fail the cheap line-distance test (CurveMayHit).  The lane drops those on its own; the first one that
-// passes is HELD for the ribbon test, which costs ~700 instructions and which the warp therefore runs for many lanes
-// at once (TravRibbonStep) — measured on B200 (profiles/r1i): run the moment a lane had a candidate, 70 % of the
-// kernel's instructions executed with ONE active lane.
+// Pending CURVE candidates, warp-cooperatively.  Leaf boxes of thin diagonal segments are much fatter than the
+// ribbon: two of three candidates fail the cheap line-distance test (CurveMayHit).  Candidates are spread unevenly
+// (0 .. 10 per lane and node step), so a per-lane loop ran with 3-4 of 32 lanes and as many rounds as the busiest
+// lane had candidates (profiles/r1o: a quarter of the kernel's instructions, a third of its stall samples).  Here the
+// candidates of ALL lanes are numbered by a prefix sum and tested 32 at a time, one per lane: the tester fetches the
+// owner's ray by shuffle and reports a pass by setting the candidate's bit in the owner's word of `pass_row` (shared
+// memory, one word per lane).  Afterwards a lane's pgroup holds the survivors only (t.checked).
+// Called by all 32 lanes, converged.  `fresh`: this lane has unchecked candidates.
 template <bool STATS>
-__device__ __forceinline__ void TravCurveCullStep(const SceneView& s, Trav& t) {
+__device__ __forceinline__ void TravCurveCullWarp(const SceneView& s, Trav& t, bool fresh, uint32_t* pass_row) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t cnt = fresh ? popc(t.pgroup.y) : 0u;
+  uint32_t incl = cnt;
+#pragma unroll
+  for (uint32_t d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t excl = incl - cnt;
+  pass_row[lane] = 0u;
+  __syncwarp();
   const float4* __restrict__ cull = s.curve_cull;
-  do {
-    const uint32_t bit = msb(t.pgroup.y);
-    t.pgroup.y &= ~(1u << bit);
-    const uint32_t code = s.curve_sub[t.pgroup.x + bit];   // (slot << 2) | first quad of the part
-    const uint32_t idx = code >> 2;
-    if (STATS) t.n_prims++;
-    if (!cull || CurveMayHit(t.O, t.D, cull[idx * 2], cull[idx * 2 + 1])) t.held = code;
-  } while (t.held == kInvalid && t.pgroup.y != 0u);
+  for (uint32_t base = 0; base < total; base += 32u) {
+    const uint32_t j = base + lane;
+    // owner of candidate j: the first lane whose inclusive count exceeds j
+    uint32_t lo = 0;
+#pragma unroll
+    for (uint32_t step = 16; step >= 1; step >>= 1) {
+      const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + step - 1u);
+      if (v <= j) lo += step;
+    }
+    const uint32_t owner = lo & 31u;
+    const uint32_t k = j - __shfl_sync(0xffffffffu, excl, owner);
+    const uint32_t oy = __shfl_sync(0xffffffffu, t.pgroup.y, owner);
+    const uint32_t ox = __shfl_sync(0xffffffffu, t.pgroup.x, owner);
+    const vec3 O(__shfl_sync(0xffffffffu, t.O.x, owner), __shfl_sync(0xffffffffu, t.O.y, owner),
+                 __shfl_sync(0xffffffffu, t.O.z, owner));
+    const vec3 D(__shfl_sync(0xffffffffu, t.D.x, owner), __shfl_sync(0xffffffffu, t.D.y, owner),
+                 __shfl_sync(0xffffffffu, t.D.z, owner));
+    if (j < total) {
+      const uint32_t bit = __fns(oy, 0u, int(k) + 1);            // the (k+1)-th pending primitive of the owner
+      const uint32_t slot = s.curve_sub[ox + bit] >> 2;
+      if (!cull || CurveMayHit(O, D, cull[slot * 2], cull[slot * 2 + 1])) atomicOr(&pass_row[owner], 1u << bit);
+    }
+  }
+  __syncwarp();
+  if (fresh) {
+    if (STATS) t.n_prims += cnt;
+    t.pgroup.y &= pass_row[lane];
+    t.checked = true;
+  }
+  __syncwarp();
+}
+
+// next survivor of the lane's (checked) pending candidates -> held for the ribbon test
+__device__ __forceinline__ void TravCurveTake(const SceneView& s, Trav& t) {
+  const uint32_t bit = msb(t.pgroup.y);
+  t.pgroup.y &= ~(1u << bit);
+  t.held = s.curve_sub[t.pgroup.x + bit];   // (slot << 2) | first quad of the part
 }
 
 template <bool ANY>
@@ -180,8 +227,11 @@ template <bool ANY, bool HAS_CURVES, bool STATS, class Client>
 __device__ __forceinline__ void TravEngine(const SceneView& s, Client& client, uint32_t refill_min_idle,
                                            uint32_t prim_min_lanes) {
   uint2 stack[kStackSize];
+  __shared__ uint32_t pass_words[HAS_CURVES ? 128 : 1];   // TravCurveCullWarp: one word per thread of the (128-thread) block
+  uint32_t* pass_row = pass_words + (HAS_CURVES ? (threadIdx.x & ~31u) : 0u);
   Trav t;
   t.active = false;
+  t.checked = false;
   t.pgroup = make_uint2(0u, 0u);
   t.held = kInvalid;
   t.n_nodes = 0; t.n_prims = 0;
@@ -205,10 +255,12 @@ __device__ __forceinline__ void TravEngine(const SceneView& s, Client& client, u
       TravAdvance<HAS_CURVES>(s, t);
     }
     if (HAS_CURVES) {
-      // curve candidates: cheap rejection now, per lane; the survivor (if any) is held for the ribbon phase
-      if (t.active && t.curves && t.held == kInvalid && t.pgroup.y != 0u) {
-        TravCurveCullStep<STATS>(s, t);
-        if (t.held == kInvalid) TravAdvance<HAS_CURVES>(s, t);
+      // curve candidates: cheap rejection now, across the warp; a survivor (if any) is held for the ribbon phase
+      const bool fresh = t.active && t.curves && !t.checked && t.held == kInvalid && t.pgroup.y != 0u;
+      if (__ballot_sync(0xffffffffu, fresh) != 0u) TravCurveCullWarp<STATS>(s, t, fresh, pass_row);
+      if (t.active && t.curves && t.checked && t.held == kInvalid) {
+        if (t.pgroup.y != 0u) TravCurveTake(s, t);
+        else TravAdvance<HAS_CURVES>(s, t);
       }
     }
     const bool tri_work = t.active && t.pgroup.y != 0u && !(HAS_CURVES && t.curves);

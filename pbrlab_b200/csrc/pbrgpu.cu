@@ -503,6 +503,30 @@ bool CheckCommitted(pbrgpu_ctx* ctx, const char* who) {
 
 }  // namespace
 
+// ---- gather microbenchmark (measurement hook, see pbrgpu.h)
+namespace {
+template <int CHAINS>
+__global__ void __launch_bounds__(128) GatherKernel(const float4* __restrict__ recs, uint32_t num_recs, uint32_t iters,
+                                                     float* sink) {
+  uint32_t idx[CHAINS];
+  float acc = 0.f;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < CHAINS; ++c) idx[c] = (tid * 2654435761u + uint32_t(c) * 40503u) % num_recs;
+  for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) {
+      const float4* r = recs + size_t(idx[c]) * 5;
+      const float4 a = r[0], b = r[1], d = r[2], e = r[3], f = r[4];
+      acc += a.x + b.y + d.z + e.w + f.x;
+      // the next position depends on the loaded data (like a child index read from a node)
+      idx[c] = (idx[c] * 1664525u + 1013904223u + (__float_as_uint(a.w) & 1u)) % num_recs;
+    }
+  }
+  if (acc == 1.2345e30f) *sink = acc;
+}
+}  // namespace
+
 extern "C" {
 
 int pbrgpu_device_count(void) {
@@ -905,6 +929,41 @@ int pbrgpu_occluded_device(pbrgpu_ctx* ctx, const pbrgpu_ray* d_rays, uint64_t n
   ctx->stats.shadow_rays = n;
   ctx->stats.trace_any_ms = ms;
   ctx->stats.kernel_launches = 1;
+  return PBRGPU_OK;
+}
+
+// ---- gather microbenchmark (measurement hook, see pbrgpu.h; kernel: GatherKernel above)
+
+int pbrgpu_measure_gather(pbrgpu_ctx* ctx, uint64_t working_set_bytes, uint32_t records_per_thread, uint32_t chains,
+                          double* gbytes_per_s) {
+  if (!ctx || !gbytes_per_s || ctx->devices.empty()) return PBRGPU_ERR_INVALID;
+  Device& d = ctx->devices[0];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  const uint32_t num_recs = uint32_t(std::min<uint64_t>(std::max<uint64_t>(working_set_bytes / 80, 1024), 0x7fffffffull / 5));
+  DevBuf<float4> recs;
+  DevBuf<float> sink;
+  CUDA_TRY(ctx, recs.Alloc(size_t(num_recs) * 5));
+  CUDA_TRY(ctx, sink.Alloc(1));
+  CUDA_TRY(ctx, cudaMemsetAsync(recs.ptr, 0, size_t(num_recs) * 80, d.stream));
+  const int grid = PersistentGrid(d, ctx->tune_trace_blocks);
+  const uint32_t per_chain = std::max(1u, records_per_thread / std::max(1u, chains));
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
+    if (chains >= 8) GatherKernel<8><<<grid, kBlock, 0, d.stream>>>(recs.ptr, num_recs, per_chain, sink.ptr);
+    else if (chains >= 4) GatherKernel<4><<<grid, kBlock, 0, d.stream>>>(recs.ptr, num_recs, per_chain, sink.ptr);
+    else if (chains >= 2) GatherKernel<2><<<grid, kBlock, 0, d.stream>>>(recs.ptr, num_recs, per_chain, sink.ptr);
+    else GatherKernel<1><<<grid, kBlock, 0, d.stream>>>(recs.ptr, num_recs, per_chain, sink.ptr);
+    CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+    if (rep > 0) best_ms = std::min(best_ms, ms);   // the first launch warms the working set into L2
+  }
+  const uint32_t c = chains >= 8 ? 8 : chains >= 4 ? 4 : chains >= 2 ? 2 : 1;
+  const double bytes = double(grid) * kBlock * double(per_chain) * c * 80.0;
+  *gbytes_per_s = bytes / (double(best_ms) * 1e-3) / 1e9;
+  recs.Free(); sink.Free();
   return PBRGPU_OK;
 }
 
