@@ -283,7 +283,7 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("TraceClosestKernel_bytes_per_launch")
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("TraceClosestKernel_bytes_per_launch")
 
     if rank == 0:
         samples_step = npix * spp_total

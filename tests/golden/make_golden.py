@@ -145,6 +145,20 @@ def image(S):
          mean_8192=(b[..., :3] / cb[..., None]).astype(np.float32))
 
 
+def image_more():
+    """image gates for the hair and the many-triangle configurations at fixture size: the C4 geometry at a tenth of
+    the strand count, and the C5 generator at 200 k triangles (GGX + SSS blobs)"""
+    w = h = 96
+    for name, files in (("hair_image_96.npz", [scenes.cornell(), scenes.cyhair(5000, 21, center=(-2.5, 6.0, 0.0), radius=1.2,
+                                                                               length=2.5, thickness=0.008)]),
+                        ("displaced_image_96.npz", [scenes.displaced(200_000)])):
+        S = R.scene(files)
+        a, ca, _ = S.render(w, h, 2048)
+        b, cb, _ = S.render(w, h, 4096)
+        save(name, mean_2048=(a[..., :3] / ca[..., None]).astype(np.float32),
+             mean_4096=(b[..., :3] / cb[..., None]).astype(np.float32))
+
+
 # ---------------------------------------------------------------- hair: CyHair ingest, curve hits, hair vertices
 def hair():
     hp = os.path.join(scenes.CACHE, "golden_hair.hair")
@@ -202,6 +216,9 @@ def textured():
 
 
 if __name__ == "__main__":
+    if "--image-more-only" in sys.argv:
+        image_more()
+        sys.exit(0)
     if "--textured-only" in sys.argv:
         textured()
         sys.exit(0)

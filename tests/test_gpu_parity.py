@@ -242,3 +242,28 @@ def test_multi_device_context_matches_one_device(built):
     assert np.all(b[..., 3] == 16.0)
     assert np.allclose(a, b, rtol=1e-4, atol=1e-4), float(np.abs(a - b).max())
     one.close(); two.close()
+
+
+@pytest.mark.parametrize("fixture,files", [
+    ("hair_image_96.npz", lambda: [scenes.cornell(), scenes.cyhair(5000, 21, center=(-2.5, 6.0, 0.0), radius=1.2,
+                                                                   length=2.5, thickness=0.008)]),
+    ("displaced_image_96.npz", lambda: [scenes.displaced(200_000)]),
+])
+def test_image_statistics_hair_and_displaced(built, fixture, files):
+    """north_star image gate on the other two scene families (fixtures rendered by oracle/_ref at 2048 and 4096 spp,
+    tests/golden/make_golden.py --image-more-only): the C4 geometry at a tenth of the strand count (Principled Hair +
+    Lucy SSS) and the C5 generator at 200 k triangles (GGX + SSS blobs): mean luminance within 0.5 %, per-pixel RMSE
+    no larger than the reference's own 2048-vs-4096-spp noise floor"""
+    g = golden(fixture)
+    sc = pb.Scene(files())
+    rgba, count, _ = sc.render(96, 96, 4096, seed=20261018)
+    assert np.all(count == 4096)
+    img = rgba[..., :3] / count[..., None]
+    assert not np.isnan(img).any()
+    lum = lambda x: (0.212671 * x[..., 0] + 0.715160 * x[..., 1] + 0.072169 * x[..., 2])
+    ref4, ref2 = g["mean_4096"], g["mean_2048"]
+    assert abs(lum(img).mean() - lum(ref4).mean()) <= 0.005 * lum(ref4).mean(), (lum(img).mean(), lum(ref4).mean())
+    floor = np.sqrt(np.mean((ref2 - ref4) ** 2))
+    rmse = np.sqrt(np.mean((img - ref4) ** 2))
+    assert rmse <= floor * 1.05, (rmse, floor)
+    sc.close()
