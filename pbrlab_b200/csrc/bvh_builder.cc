@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -46,21 +47,57 @@ struct Builder {
   std::atomic<uint32_t> next_node{0};
   std::atomic<int> spare_threads{0};
 
+  std::vector<uint32_t> tmp;       // scratch of the parallel partition (same size as idx)
+  bool serial_top = false;         // PBRGPU_BVH_SERIAL_TOP: A/B switch for the chunked passes
+
   uint32_t Alloc() { return next_node.fetch_add(1); }
+
+  // Near the root there are fewer ranges than host threads: the passes over a large range are cut into chunks and
+  // run on the threads nobody uses yet.  Every reduction below is a min / max / integer sum, so the result does
+  // not depend on the chunking.
+  static constexpr uint32_t kParallelMin = 1u << 18;
+  int GrabThreads(int want) {
+    int got = 0;
+    while (got < want) {
+      if (spare_threads.fetch_sub(1) > 0) ++got;
+      else { spare_threads.fetch_add(1); break; }
+    }
+    return got;
+  }
+  template <class F>
+  void RunChunks(uint32_t begin, uint32_t end, int nchunks, F fn) {   // fn(chunk, chunk_begin, chunk_end)
+    const uint64_t cnt = end - begin;
+    std::vector<std::thread> th;
+    for (int c = 1; c < nchunks; ++c)
+      th.emplace_back([=]() { fn(c, begin + uint32_t(cnt * c / nchunks), begin + uint32_t(cnt * (c + 1) / nchunks)); });
+    fn(0, begin, begin + uint32_t(cnt / nchunks));
+    for (auto& t : th) t.join();
+  }
   const float* C(int axis) const { return axis == 0 ? cx.data() : (axis == 1 ? cy.data() : cz.data()); }
 
   void BuildRange(uint32_t node_id, uint32_t begin, uint32_t end) {
     Node2& node = nodes[node_id];
     const uint32_t cnt = end - begin;
     Aabb box = Empty(), cbox = Empty();
-    for (uint32_t i = begin; i < end; ++i) {
-      const uint32_t p = idx[i];
-      Grow(&box, pb[p]);
-      const float c[3] = {cx[p], cy[p], cz[p]};
-      for (int k = 0; k < 3; ++k) {
-        cbox.lo[k] = std::min(cbox.lo[k], c[k]);
-        cbox.hi[k] = std::max(cbox.hi[k], c[k]);
+    const int helpers = (cnt >= kParallelMin && !serial_top) ? GrabThreads(15) : 0;
+    const int nchunks = helpers + 1;
+    auto bounds_of = [&](uint32_t b0, uint32_t e0, Aabb* bx, Aabb* cbx) {
+      for (uint32_t i = b0; i < e0; ++i) {
+        const uint32_t p = idx[i];
+        Grow(bx, pb[p]);
+        const float c[3] = {cx[p], cy[p], cz[p]};
+        for (int k = 0; k < 3; ++k) {
+          cbx->lo[k] = std::min(cbx->lo[k], c[k]);
+          cbx->hi[k] = std::max(cbx->hi[k], c[k]);
+        }
       }
+    };
+    if (helpers == 0) {
+      bounds_of(begin, end, &box, &cbox);
+    } else {
+      std::vector<Aabb> pbx(nchunks, Empty()), pcb(nchunks, Empty());
+      RunChunks(begin, end, nchunks, [&](int c, uint32_t b0, uint32_t e0) { bounds_of(b0, e0, &pbx[c], &pcb[c]); });
+      for (int c = 0; c < nchunks; ++c) { Grow(&box, pbx[c]); Grow(&cbox, pcb[c]); }
     }
     node.box = box;
     if (cnt == 1) {
@@ -72,6 +109,28 @@ struct Builder {
     // binned SAH over the three axes
     float best_cost = FLT_MAX;
     int best_axis = -1, best_bin = -1;
+    struct Bins { Aabb bb[3][kBins]; uint32_t bc[3][kBins]; };
+    std::vector<Bins> pbins;
+    if (helpers > 0) {   // all three axes in one pass over each chunk
+      pbins.resize(nchunks);
+      RunChunks(begin, end, nchunks, [&](int ch, uint32_t b0, uint32_t e0) {
+        Bins& B = pbins[ch];
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < kBins; ++b) { B.bb[a][b] = Empty(); B.bc[a][b] = 0; }
+        for (int a = 0; a < 3; ++a) {
+          const float lo = cbox.lo[a], ext = cbox.hi[a] - cbox.lo[a];
+          if (!(ext > 0.f)) continue;
+          const float scale = float(kBins) / ext;
+          const float* c = C(a);
+          for (uint32_t i = b0; i < e0; ++i) {
+            const uint32_t p = idx[i];
+            int b = int((c[p] - lo) * scale);
+            b = std::min(std::max(b, 0), kBins - 1);
+            Grow(&B.bb[a][b], pb[p]);
+            B.bc[a][b]++;
+          }
+        }
+      });
+    }
     for (int axis = 0; axis < 3; ++axis) {
       const float lo = cbox.lo[axis], ext = cbox.hi[axis] - cbox.lo[axis];
       if (!(ext > 0.f)) continue;
@@ -80,12 +139,17 @@ struct Builder {
       uint32_t bc[kBins];
       for (int b = 0; b < kBins; ++b) { bb[b] = Empty(); bc[b] = 0; }
       const float* c = C(axis);
-      for (uint32_t i = begin; i < end; ++i) {
-        const uint32_t p = idx[i];
-        int b = int((c[p] - lo) * scale);
-        b = std::min(std::max(b, 0), kBins - 1);
-        Grow(&bb[b], pb[p]);
-        bc[b]++;
+      if (helpers > 0) {
+        for (int ch = 0; ch < nchunks; ++ch)
+          for (int b = 0; b < kBins; ++b) { Grow(&bb[b], pbins[ch].bb[axis][b]); bc[b] += pbins[ch].bc[axis][b]; }
+      } else {
+        for (uint32_t i = begin; i < end; ++i) {
+          const uint32_t p = idx[i];
+          int b = int((c[p] - lo) * scale);
+          b = std::min(std::max(b, 0), kBins - 1);
+          Grow(&bb[b], pb[p]);
+          bc[b]++;
+        }
       }
       float right_area[kBins];
       uint32_t right_cnt[kBins];
@@ -113,6 +177,7 @@ struct Builder {
     }
 
     const float area = HalfArea(box);
+    auto release_helpers = [&]() { if (helpers > 0) spare_threads.fetch_add(helpers); };
     if (int(cnt) <= prm.max_leaf_prims) {
       const float leaf_cost = prm.prim_cost * float(cnt) * area;
       const float split_cost =
@@ -120,6 +185,7 @@ struct Builder {
       if (leaf_cost <= split_cost) {
         node.first = begin;
         node.count = cnt;
+        release_helpers();
         return;
       }
     }
@@ -130,16 +196,43 @@ struct Builder {
       const float scale = float(kBins) / ext;
       const float* c = C(best_axis);
       const int bin = best_bin;
-      uint32_t* m = std::partition(idx.data() + begin, idx.data() + end, [&](uint32_t p) {
+      auto goes_left = [&](uint32_t p) {
         int b = int((c[p] - lo) * scale);
         b = std::min(std::max(b, 0), kBins - 1);
         return b <= bin;
-      });
-      mid = uint32_t(m - idx.data());
+      };
+      if (helpers > 0) {   // stable partition through the scratch array: count per chunk, then scatter
+        std::vector<uint32_t> nleft(nchunks, 0u), cb(nchunks + 1, 0u);
+        RunChunks(begin, end, nchunks, [&](int ch, uint32_t b0, uint32_t e0) {
+          uint32_t k = 0;
+          for (uint32_t i = b0; i < e0; ++i) k += goes_left(idx[i]) ? 1u : 0u;
+          nleft[ch] = k; cb[ch] = b0; if (ch == nchunks - 1) cb[nchunks] = e0;
+        });
+        uint32_t total_left = 0;
+        for (int ch = 0; ch < nchunks; ++ch) total_left += nleft[ch];
+        std::vector<uint32_t> lo_off(nchunks), hi_off(nchunks);
+        uint32_t lacc = begin, racc = begin + total_left;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          lo_off[ch] = lacc; hi_off[ch] = racc;
+          lacc += nleft[ch]; racc += (cb[ch + 1] - cb[ch]) - nleft[ch];
+        }
+        RunChunks(begin, end, nchunks, [&](int ch, uint32_t b0, uint32_t e0) {
+          uint32_t l = lo_off[ch], r = hi_off[ch];
+          for (uint32_t i = b0; i < e0; ++i) { const uint32_t p = idx[i]; if (goes_left(p)) tmp[l++] = p; else tmp[r++] = p; }
+        });
+        RunChunks(begin, end, nchunks, [&](int, uint32_t b0, uint32_t e0) {
+          memcpy(idx.data() + b0, tmp.data() + b0, sizeof(uint32_t) * size_t(e0 - b0));
+        });
+        mid = begin + total_left;
+      } else {
+        uint32_t* m = std::partition(idx.data() + begin, idx.data() + end, goes_left);
+        mid = uint32_t(m - idx.data());
+      }
     } else {
       mid = begin;   // all centroids coincide
     }
     if (mid == begin || mid == end) mid = begin + cnt / 2;   // degenerate: split the index range in half
+    release_helpers();
 
     const uint32_t l = Alloc(), r = Alloc();
     node.left = l;
@@ -186,6 +279,8 @@ bool BuildBvh8(const Aabb* prim_bounds, uint32_t n, const BuildParams& params, B
   b.n = n;
   b.prm = params;
   b.idx.resize(n);
+  b.serial_top = getenv("PBRGPU_BVH_SERIAL_TOP") != nullptr;
+  if (n >= Builder::kParallelMin) b.tmp.resize(n);
   b.cx.resize(n); b.cy.resize(n); b.cz.resize(n);
   for (uint32_t i = 0; i < n; ++i) {
     b.idx[i] = i;

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 
@@ -238,7 +239,10 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
       bx.lo[2] = std::min(a.z, std::min(b.z, c.z)); bx.hi[2] = std::max(a.z, std::max(b.z, c.z));
       for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], bx.lo[k]); hi[k] = std::max(hi[k], bx.hi[k]); }
     }
+    const auto tb0 = std::chrono::steady_clock::now();
     if (!pbrbvh::BuildBvh8(boxes.data(), nt, prm, &tri_bvh, &err)) { error = err; return false; }
+    if (getenv("PBRGPU_VERBOSE_COMMIT"))
+      fprintf(stderr, "commit: triangle BVH (%u prims) %.3f s\n", nt, std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count());
     tri_data.resize(size_t(3) * nt);
     for (uint32_t k = 0; k < nt; ++k) {
       const uint32_t i = tri_bvh.prim_order[k];
@@ -381,7 +385,11 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
     bmin[k] = bmin_in ? bmin_in[k] : lo[k];
     bmax[k] = bmax_in ? bmax_in[k] : hi[k];
   }
+  const auto tc0 = std::chrono::steady_clock::now();
   BuildClearance();
+  if (getenv("PBRGPU_VERBOSE_COMMIT"))
+    fprintf(stderr, "commit: clearance field %.3f s, total %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count(),
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   committed = true;
   build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return true;

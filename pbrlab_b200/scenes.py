@@ -165,7 +165,7 @@ def write_displaced_obj(path, n_tris=20_000_000, seed=7, blobs=8):
             j = np.arange(nu)[None, :]
             j1 = (j + 1) % nu
             a = (i + j).ravel(); bq = (i + j1).ravel(); cq = (i + nu + j1).ravel(); dq = (i + nu + j).ravel()
-            tri = np.concatenate([np.stack([a, cq, bq], 1), np.stack([a, dq, cq], 1)], 0)
+            tri = np.concatenate([np.stack([a, bq, cq], 1), np.stack([a, cq, dq], 1)], 0)   # (v1-v0)x(v2-v0) points outwards, like vn
             # drop the zero-area triangles at the two poles
             row = tri[:, 0] // nu
             keep = ~(((row == 0) & (np.arange(len(tri)) < len(a))) | ((row == nv - 1) & (np.arange(len(tri)) >= len(a))))
@@ -179,7 +179,7 @@ def write_displaced_obj(path, n_tris=20_000_000, seed=7, blobs=8):
 
 
 def displaced(n_tris=20_000_000, seed=7):
-    path = _cache("displaced_%d_%d.obj" % (n_tris, seed))
+    path = _cache("displaced_v2_%d_%d.obj" % (n_tris, seed))
     done = path + ".done"
     if not os.path.exists(done):
         write_displaced_obj(path, n_tris, seed)
