@@ -5,6 +5,8 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -296,7 +298,10 @@ bool BuildBvh8(const Aabb* prim_bounds, uint32_t n, const BuildParams& params, B
   int threads = params.threads > 0 ? params.threads : int(std::max(1u, std::thread::hardware_concurrency()));
   b.spare_threads = threads - 1;
   const uint32_t root2 = b.Alloc();
+  const auto tb = std::chrono::steady_clock::now();
   b.BuildRange(root2, 0, n);
+  if (getenv("PBRGPU_VERBOSE_COMMIT"))
+    fprintf(stderr, "  BuildBvh8: binary SAH build %.3f s (%d threads)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count(), threads);
   const std::vector<Node2>& n2 = b.nodes;
 
   // ---- collapse to 8-wide and emit breadth-first
