@@ -389,7 +389,15 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   CUDA_TRY(ctx, cudaMemsetAsync(d.count.ptr, 0, sizeof(uint32_t) * npix, d.stream));
   if (local_spp == 0) { CUDA_TRY(ctx, cudaStreamSynchronize(d.stream)); return PBRGPU_OK; }
   const uint64_t total = npix64 * local_spp;
-  const uint32_t n_slots = ChoosePoolSize(ctx, npix, total);
+  uint32_t n_slots = ChoosePoolSize(ctx, npix, total);
+  if (n_slots > d.wave_capacity) {
+    // a pool of 32 Mi slots is 13 GB (slot + walk lines, queues, shadow queue: ~400 B per slot): never more than half
+    // of what the device has free, whatever else lives on it
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t fit = std::max<uint64_t>(free_b / 2 / 400, 1u << 16);
+    n_slots = uint32_t(std::min<uint64_t>(n_slots, std::max<uint64_t>(fit, d.wave_capacity)));
+  }
   int rc = EnsureWave(ctx, d, n_slots);
   if (rc != PBRGPU_OK) return rc;
   CUDA_TRY(ctx, cudaMemsetAsync(d.stats.ptr, 0, sizeof(unsigned long long) * pbr::kStatCount, d.stream));

@@ -164,6 +164,25 @@ def test_clearance_field_only_skips_segments_that_miss(cornell_emul):
     assert segments > 20000
     assert wrong == 0
     assert skipped > 0.3 * segments, (skipped, segments)
+    # the many-triangle generator (several scattering blobs, walls close by)
+    import emulbind
+    host = pb.Scene([scenes.displaced(200_000)], commit_to_device=False)
+    E = emulbind.Emul(host.flat())
+    rng = np.random.default_rng(5)
+    lo, hi = E.bounds()
+    cam = np.zeros(8, np.float32)
+    org = np.tile(np.array([0.0, 10.0, 45.0], np.float32), (20000, 1))
+    tgt = np.stack([rng.uniform(-9, 9, 20000), rng.uniform(1, 19, 20000), np.full(20000, 0.0)], 1).astype(np.float32)
+    d = tgt - org
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = pb.make_rays(org, d.astype(np.float32))
+    seeds = np.stack([rng.integers(0, 2**62, len(rays), dtype=np.uint64)] * 2, 1)
+    E.clearance_probe()
+    E.radiance(rays, seeds)
+    segments, skipped, wrong = E.clearance_probe()
+    assert segments > 20000, segments
+    assert wrong == 0
+    E.close(); host.close()
 
 
 def test_image_mean_hair_and_displaced_fixtures(built):
