@@ -2,7 +2,7 @@
 # One gpurun call: GPU parity tests, then bench lines (reduced spp; throughput is spp-independent) for the C3, C4 and
 # C5 workloads with the CPU reference timed beside each.  Usage: scripts/gpu_workloads.sh TAG [steps...]
 TAG=${1:-wl}; shift
-STEPS=${@:-tests c3 c4 c5}
+STEPS=${@:-tests c1 c3 c4 c5}
 mkdir -p gpurun_out
 has() { [[ " $STEPS " == *" $1 "* ]]; }
 if has tests; then
@@ -15,6 +15,7 @@ run() {  # workload spp ref_spp
     > gpurun_out/${TAG}_bench_$1.json 2> gpurun_out/${TAG}_bench_$1.err
   echo "bench $1 exit $?"; grep '^{' gpurun_out/${TAG}_bench_$1.json | cut -c1-1800
 }
+if has c1; then run c1 64 16; fi
 if has c3; then run c3 64 8; fi
 if has c4; then run c4 16 4; fi
 if has c5; then run c5 16 4; fi
