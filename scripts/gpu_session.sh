@@ -35,9 +35,9 @@ if has launches; then
 fi
 if has ncu; then
   # one launch of every kernel family out of the middle of a frame (skip the first iterations: the pool is filling)
-  timeout 1200 ncu --set full --clock-control none --import-source on --launch-skip 60 --launch-count 8 \
+  timeout 1200 ncu --set full --clock-control none --import-source on --launch-skip 44 --launch-count 8 \
     -k regex:'TraceClosest|ShadeSurface|SssWalk|SssExit|TraceAny|Regenerate' -f -o gpurun_out/${TAG}_full \
-    python scripts/render_once.py 1920 1080 32 0 > gpurun_out/${TAG}_ncu.log 2>&1
+    python scripts/render_once.py 1920 1080 128 0 > gpurun_out/${TAG}_ncu.log 2>&1
   tail -2 gpurun_out/${TAG}_ncu.log
 fi
 ls -la gpurun_out | tail -20
