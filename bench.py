@@ -280,6 +280,31 @@ def main():
     # node-sized (80 B) dependent random gathers over a 32 MB (L2) and a 4 GB (HBM) working set, 8 chains per thread
     gather_l2 = ctx.measure_gather(32 << 20, 4096, 8) if rank == 0 else None
     gather_hbm = ctx.measure_gather(4 << 30, 2048, 8) if rank == 0 else None
+    # nodes visited / primitives tested per ray, counted by the traversal kernel itself on a batch of
+    # 1 Mi camera rays + 1 Mi secondary rays leaving from what they hit, and the bytes those steps touch
+    trav = None
+    if rank == 0:
+        import pbrlab_b200 as _pb
+        rng = np.random.default_rng(7)
+        bmin, bmax = ctx.bounds()
+        hs = bmax[0] - bmin[0]; vs = bmax[1] - bmin[1]
+        if hs > vs: vs = hs * h / w
+        else: hs = vs * w / h
+        eye = np.array([(bmax[0] + bmin[0]) * 0.5, (bmax[1] + bmin[1]) * 0.5, bmax[2] + hs * 0.5 * np.sqrt(3.0)], np.float32)
+        nr = 1 << 20
+        px = rng.random((nr, 2)).astype(np.float32)
+        tgt = np.stack([eye[0] - hs * 0.5 + hs * px[:, 0], eye[1] + vs * 0.5 - vs * px[:, 1], np.full(nr, bmax[2], np.float32)], 1)
+        d = tgt - eye; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        cam_rays = _pb.make_rays(np.tile(eye, (nr, 1)), d.astype(np.float32))
+        hits = ctx.trace(cam_rays); st1 = ctx.stats()
+        hit = hits["instance_id"] != 0xFFFFFFFF
+        P = cam_rays["org"][hit] + hits["t"][hit, None] * cam_rays["dir"][hit]
+        d2 = rng.normal(size=P.shape).astype(np.float32); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+        ctx.trace(_pb.make_rays(P, d2, tmin=1e-3)); st2 = ctx.stats()
+        prim_bytes = 64 if (nsegs and not ntris > 1000) else 48
+        per = lambda st, n: {"nodes_per_ray": st["nodes_visited"] / max(n, 1), "prims_per_ray": st["prims_tested"] / max(n, 1),
+                             "touched_bytes_per_ray": 64 + 80 * st["nodes_visited"] / max(n, 1) + prim_bytes * st["prims_tested"] / max(n, 1)}
+        trav = {"camera_rays": per(st1, nr), "secondary_rays": per(st2, int(hit.sum()))}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -308,7 +333,8 @@ def main():
                          "algorithmic_bytes_per_ray": a_ray, "rays_per_launch": rays_per_launch,
                          "launch_ms": dur_ms, "kernel_family_ms_per_step": fam,
                          "gather_80B_l2_gbs": gather_l2, "gather_80B_hbm_gbs": gather_hbm,
-                         "frac_of_l2_gather": (achieved / gather_l2) if gather_l2 else None},
+                         "frac_of_l2_gather": (achieved / gather_l2) if gather_l2 else None,
+                         "traversal_counters": trav},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
