@@ -138,7 +138,7 @@ def reference_arm(args, rank):
     for i in range(args.warmup + args.steps):
         sec, cores, kind = cpu_render(files, w, h, 1 if i < args.warmup else sample_spp, warm_spp=0)
         if sec is None:
-            print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref nor oracle/libpbr_oracle.so is present"}))
+            emit({"impl": "reference", "unavailable": "neither oracle/_ref nor oracle/libpbr_oracle.so is present"})
             return
         if i >= args.warmup:
             secs.append(sec)
@@ -151,10 +151,31 @@ def reference_arm(args, rank):
             "config": {"workload": desc, "sample": sample},
             "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The host C++ code mirrors the reference's progress prints on stdout ("Load obj file ...", "finish pass N").
+    The contract is ONE JSON line on stdout: everything else written to fd 1, by Python or by native code, goes to
+    stderr from here on; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -343,7 +364,7 @@ def main():
                 w, h, args.ref_spp, spp_total, "oracle/_ref" if kind == "reference" else "oracle/pbr_oracle.cc")
             line["cpu_baseline"] = {"value": (w * h * args.ref_spp / sec * 1e-6) if sec else None, "unit": "Msamples/s",
                                     "cores": cores, "kind": kind, "sample": sample}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

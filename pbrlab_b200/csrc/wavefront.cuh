@@ -509,7 +509,7 @@ __device__ __forceinline__ void ResumeWalk(const WaveState& w, uint32_t p, SssWa
 // the walk is set up here (entry direction + coefficients, random-walk-sss.h:227-279) and parked for sss_walk.
 // Launch shapes: the general kernel needs ~110-128 registers, so one 512-thread block per SM; the diffuse-only kernel is
 // 7x smaller (2.1k vs 15.7k SASS instructions) and fits three 256-thread blocks per SM.
-constexpr int kDiffuseBlock = 256, kDiffuseBlocksPerSm = 4;
+constexpr int kDiffuseBlock = 256, kDiffuseBlocksPerSm = 3;
 template <bool DIFFUSE_ONLY>
 __global__ void __launch_bounds__(DIFFUSE_ONLY ? kDiffuseBlock : kShadeBlock, DIFFUSE_ONLY ? kDiffuseBlocksPerSm : 1)
 ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t next_parity,
