@@ -10,6 +10,8 @@
 #include <map>
 #include <memory>
 
+#include <sys/stat.h>
+
 #include "image-io.h"
 
 namespace pbrlab {
@@ -234,10 +236,111 @@ struct ShapeBuild {
   std::vector<uint32_t> v, vn, vt, mat;
 };
 
+// ---- binary cache of the parsed geometry (at 20 M triangles the 1.5 GB of OBJ text takes 13 s to
+// parse).  Opt-in (PBRLAB_SCENE_CACHE=1): `<file>.pbrcache` next to the OBJ holds the attribute pools, the per-shape
+// index arrays and the names of the material libraries; it is used only while the OBJ and every MTL it names still
+// have the size and modification time recorded in it.  Materials and textures are always read from their files.
+struct FileStamp { uint64_t size = 0; int64_t mtime = 0; bool ok = false; };
+FileStamp StampOf(const std::string& path) {
+  FileStamp st;
+  struct stat sb;
+  if (stat(path.c_str(), &sb) == 0) { st.size = uint64_t(sb.st_size); st.mtime = int64_t(sb.st_mtime); st.ok = true; }
+  return st;
+}
+const char kCacheMagic[8] = {'P', 'B', 'R', 'C', 'A', 'C', 'H', '2'};
+template <class T> bool PutVec(FILE* fp, const std::vector<T>& v) {
+  const uint64_t n = v.size();
+  return fwrite(&n, 8, 1, fp) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, fp) == n);
+}
+template <class T> bool GetVec(FILE* fp, std::vector<T>* v) {
+  uint64_t n = 0;
+  if (fread(&n, 8, 1, fp) != 1 || n > (uint64_t(1) << 36) / sizeof(T)) return false;
+  v->resize(size_t(n));
+  return n == 0 || fread(v->data(), sizeof(T), n, fp) == n;
+}
+bool PutStr(FILE* fp, const std::string& s) { return PutVec(fp, std::vector<char>(s.begin(), s.end())); }
+bool GetStr(FILE* fp, std::string* s) {
+  std::vector<char> v;
+  if (!GetVec(fp, &v)) return false;
+  s->assign(v.begin(), v.end());
+  return true;
+}
+bool PutStamp(FILE* fp, const FileStamp& st) { return fwrite(&st.size, 8, 1, fp) == 1 && fwrite(&st.mtime, 8, 1, fp) == 1; }
+bool SameStamp(FILE* fp, const FileStamp& now) {
+  uint64_t size = 0; int64_t mtime = 0;
+  return fread(&size, 8, 1, fp) == 1 && fread(&mtime, 8, 1, fp) == 1 && now.ok && size == now.size && mtime == now.mtime;
+}
+
+bool WriteObjCache(const std::string& obj, const std::string& base_dir, const std::vector<std::string>& mtllibs,
+                   const Attribute& attr, const std::vector<ShapeBuild>& shapes) {
+  const std::string tmp = obj + ".pbrcache.tmp";
+  FILE* fp = fopen(tmp.c_str(), "wb");
+  if (!fp) return false;
+  bool ok = fwrite(kCacheMagic, 8, 1, fp) == 1 && PutStamp(fp, StampOf(obj));
+  const uint64_t nlib = mtllibs.size();
+  ok = ok && fwrite(&nlib, 8, 1, fp) == 1;
+  for (const std::string& m : mtllibs)
+    ok = ok && PutStr(fp, m) && PutStamp(fp, StampOf(base_dir.empty() ? m : base_dir + "/" + m));
+  ok = ok && PutVec(fp, attr.vertices) && PutVec(fp, attr.normals) && PutVec(fp, attr.texcoords);
+  const uint64_t ns = shapes.size();
+  ok = ok && fwrite(&ns, 8, 1, fp) == 1;
+  for (const ShapeBuild& sh : shapes)
+    ok = ok && PutStr(fp, sh.name) && PutVec(fp, sh.v) && PutVec(fp, sh.vn) && PutVec(fp, sh.vt) && PutVec(fp, sh.mat);
+  ok = (fclose(fp) == 0) && ok;
+  if (ok) ok = rename(tmp.c_str(), (obj + ".pbrcache").c_str()) == 0;
+  if (!ok) remove(tmp.c_str());
+  return ok;
+}
+
+bool ReadObjCache(const std::string& obj, const std::string& base_dir, std::vector<std::string>* mtllibs, Attribute* attr,
+                  std::vector<ShapeBuild>* shapes) {
+  FILE* fp = fopen((obj + ".pbrcache").c_str(), "rb");
+  if (!fp) return false;
+  char magic[8];
+  bool ok = fread(magic, 8, 1, fp) == 1 && memcmp(magic, kCacheMagic, 8) == 0 && SameStamp(fp, StampOf(obj));
+  uint64_t nlib = 0;
+  ok = ok && fread(&nlib, 8, 1, fp) == 1 && nlib < 4096;
+  for (uint64_t i = 0; ok && i < nlib; ++i) {
+    std::string m;
+    ok = GetStr(fp, &m) && SameStamp(fp, StampOf(base_dir.empty() ? m : base_dir + "/" + m));
+    if (ok) mtllibs->push_back(m);
+  }
+  ok = ok && GetVec(fp, &attr->vertices) && GetVec(fp, &attr->normals) && GetVec(fp, &attr->texcoords);
+  uint64_t ns = 0;
+  ok = ok && fread(&ns, 8, 1, fp) == 1 && ns < (uint64_t(1) << 24);
+  for (uint64_t i = 0; ok && i < ns; ++i) {
+    ShapeBuild sh;
+    ok = GetStr(fp, &sh.name) && GetVec(fp, &sh.v) && GetVec(fp, &sh.vn) && GetVec(fp, &sh.vt) && GetVec(fp, &sh.mat);
+    if (ok) shapes->push_back(std::move(sh));
+  }
+  fclose(fp);
+  if (!ok) { mtllibs->clear(); shapes->clear(); *attr = Attribute(); }
+  return ok;
+}
+
 }  // namespace
 
 bool LoadTriangleMeshFromObj(const std::string& filename, std::vector<TriangleMesh>* meshes,
                              std::vector<MaterialParameter>* material_params, std::vector<Texture>* textures) {
+  std::shared_ptr<Attribute> attr(new Attribute());
+  std::vector<RawMaterial> raw_materials;
+  std::map<std::string, int> material_index;
+  std::vector<ShapeBuild> shapes;
+  std::vector<std::string> mtllibs;
+  const char* cache_env = getenv("PBRLAB_SCENE_CACHE");
+  const bool use_cache = cache_env && cache_env[0] == '1';
+  {
+    const size_t sl = filename.find_last_of('/');
+    const std::string dir = (sl == std::string::npos) ? std::string("") : filename.substr(0, sl);
+    if (use_cache && ReadObjCache(filename, dir, &mtllibs, attr.get(), &shapes)) {
+      std::cerr << "Load obj file [" << filename << "] from its binary cache" << std::endl;
+      for (const std::string& m : mtllibs) LoadMtl(dir.empty() ? m : dir + "/" + m, &raw_materials, &material_index);
+      meshes->clear();
+      for (const ShapeBuild& sb : shapes) meshes->emplace_back(sb.name, attr, sb.v, sb.vn, sb.vt, sb.mat);
+      for (const RawMaterial& m : raw_materials) material_params->push_back(ToPrincipled(m, dir, textures));
+      return true;
+    }
+  }
   std::string text;
   if (!ReadFile(filename, &text)) {
     std::cerr << "error : cannot open [" << filename << "]" << std::endl;
@@ -247,10 +350,6 @@ bool LoadTriangleMeshFromObj(const std::string& filename, std::vector<TriangleMe
   const std::string base_dir = (slash == std::string::npos) ? std::string("") : filename.substr(0, slash);
   std::cerr << "base dir : " << base_dir << std::endl;
 
-  std::shared_ptr<Attribute> attr(new Attribute());
-  std::vector<RawMaterial> raw_materials;
-  std::map<std::string, int> material_index;
-  std::vector<ShapeBuild> shapes;
   ShapeBuild cur;
   int cur_material = -1;
   std::vector<Corner> face;
@@ -355,6 +454,7 @@ bool LoadTriangleMeshFromObj(const std::string& filename, std::vector<TriangleMe
       const char* q = line + 7;
       SkipSpace(&q);
       const std::string name = RestOfLine(q);
+      mtllibs.push_back(name);
       LoadMtl(base_dir.empty() ? name : base_dir + "/" + name, &raw_materials, &material_index);
     }
     while (!IsEol(*p)) ++p;
@@ -362,6 +462,7 @@ bool LoadTriangleMeshFromObj(const std::string& filename, std::vector<TriangleMe
     if (*p == '\n') ++p;
   }
   flush();
+  if (use_cache) WriteObjCache(filename, base_dir, mtllibs, *attr, shapes);
 
   meshes->clear();
   for (const ShapeBuild& s : shapes) meshes->emplace_back(s.name, attr, s.v, s.vn, s.vt, s.mat);

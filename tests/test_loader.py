@@ -113,3 +113,30 @@ def test_quad_and_polygon_triangulation(built, tmp_path):
     assert fl.vidx[:2].tolist() == [[0, 1, 3], [1, 2, 3]]
     assert np.all(fl.tri_material == 0xFFFFFFFF)          # no usemtl -> no material -> paths are absorbed
     assert len(fl.light_probability) == 1                 # name starts with "light"
+
+
+def test_binary_scene_cache_round_trip(built, tmp_path, monkeypatch):
+    """PBRLAB_SCENE_CACHE=1: the second load of an OBJ comes from `<file>.pbrcache` and yields the same
+    flat scene, array for array; touching the OBJ invalidates the cache"""
+    import shutil, os, time
+    src = scenes.cornell()
+    obj = str(tmp_path / "cornell.obj")
+    shutil.copy(src, obj)
+    shutil.copy(os.path.splitext(src)[0] + ".mtl", str(tmp_path / os.path.basename(os.path.splitext(src)[0] + ".mtl")))
+    plain = pb.Scene([obj], commit_to_device=False).flat()
+    assert not os.path.exists(obj + ".pbrcache")
+    monkeypatch.setenv("PBRLAB_SCENE_CACHE", "1")
+    first = pb.Scene([obj], commit_to_device=False).flat()
+    assert os.path.exists(obj + ".pbrcache")
+    t = time.time()
+    cached = pb.Scene([obj], commit_to_device=False).flat()
+    for name in ("verts", "normals", "texcoords", "vidx", "nidx", "tidx", "tri_material", "tri_instance", "tri_prim",
+                 "materials", "prim_cdf", "light_cdf", "bmin", "bmax"):
+        a, b, c = getattr(plain, name), getattr(first, name), getattr(cached, name)
+        assert np.array_equal(a, b) and np.array_equal(a, c), name
+    # a newer OBJ is parsed again (and the cache rewritten)
+    stamp = os.path.getmtime(obj + ".pbrcache")
+    os.utime(obj, (time.time() + 5, time.time() + 5))
+    again = pb.Scene([obj], commit_to_device=False).flat()
+    assert np.array_equal(again.vidx, plain.vidx)
+    assert os.path.getmtime(obj + ".pbrcache") >= stamp
