@@ -129,6 +129,7 @@ struct pbrgpu_ctx {
   uint32_t tune_prim_lanes = 1, tune_prim_lanes_sss = 1;   // lanes with pending primitives that trigger a primitive phase
   uint32_t tune_ribbon_lanes = 8;  // lanes holding a curve candidate that trigger the (batched) ribbon test
   int tune_l2_persist = 0;         // persisting-L2 window over the traversal data
+  int tune_walk_bounces = 16;   // bounces a walk gets per launch before it is parked (pool busy)
   int tune_clear_march = 4;        // sphere-tracing steps of the clearance test along a walk segment
   int tune_sss_skip = 1;           // clearance grid: random-walk segments that provably hit nothing are not traced
   int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
@@ -305,7 +306,7 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     const uint32_t next = parity ^ 1u;
     // single-vertex mode lets the walk run to its end inside the one iteration
     const uint32_t walk_budget =
-        (max_iterations == 1u) ? 0x7fffffffu : (in_flight < kDrainThreshold ? kSssBouncesDrain : kSssBouncesBusy);
+        (max_iterations == 1u) ? 0x7fffffffu : (in_flight < kDrainThreshold ? kSssBouncesDrain : uint32_t(ctx->tune_walk_bounces));
     const bool prof = ctx->profile;
     auto mark = [&](int k) { if (prof) cudaEventRecord(d.kev[k], st); };
     const uint32_t regen = frame ? 1u : 0u;
@@ -574,6 +575,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_pool_mi = std::min(64, std::max(1, env_int("PBRGPU_POOL_MI", ctx->tune_pool_mi)));
   ctx->tune_l2_persist = env_int("PBRGPU_L2_PERSIST", ctx->tune_l2_persist);
   ctx->tune_sss_skip = env_int("PBRGPU_SSS_SKIP", ctx->tune_sss_skip);
+  ctx->tune_walk_bounces = std::min(8192, std::max(1, env_int("PBRGPU_WALK_BOUNCES", ctx->tune_walk_bounces)));
   ctx->tune_clear_march = std::min(64, std::max(1, env_int("PBRGPU_CLEAR_MARCH", ctx->tune_clear_march)));
   ctx->tune_sort_materials = env_int("PBRGPU_SORT_MATERIALS", ctx->tune_sort_materials);
   ctx->tune_diffuse_blocks = std::max(1, env_int("PBRGPU_DIFFUSE_BLOCKS", ctx->tune_diffuse_blocks));
