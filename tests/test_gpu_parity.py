@@ -267,3 +267,31 @@ def test_image_statistics_hair_and_displaced(built, fixture, files):
     rmse = np.sqrt(np.mean((img - ref4) ** 2))
     assert rmse <= floor * 1.05, (rmse, floor)
     sc.close()
+
+
+def test_curve_part_splits_report_the_same_hits(built, hair_file, monkeypatch):
+    """the curve BVH over whole segments, halves and quarters (PBRGPU_CURVE_SPLIT = 1, 2, 4) and the engine with and
+    without the line-distance rejection report bit-identical hits and occlusion flags on the GPU"""
+    g = golden("hair_scene.npz")
+    rays = common.rays_from_f8(g["rays"])
+    rng = np.random.default_rng(31)
+    inside = (np.array([-2.5, 5.5, 0.0]) + rng.uniform(-1.2, 1.2, (60000, 3))).astype(np.float32)
+    more = pb.make_rays(inside, common.sphere_dirs(rng, len(inside)), tmin=1e-3)
+    rays = np.concatenate([rays, more])
+    results = []
+    for split, nocull in (("4", False), ("2", False), ("1", False), ("4", True)):
+        monkeypatch.setenv("PBRGPU_CURVE_SPLIT", split)
+        if nocull:
+            monkeypatch.setenv("PBRGPU_NO_CURVE_CULL", "1")
+        sc = pb.Scene([scenes.cornell(), hair_file])
+        ctx = sc.context()
+        results.append((ctx.trace(rays), ctx.occluded(rays)))
+        sc.close()
+    monkeypatch.delenv("PBRGPU_CURVE_SPLIT")
+    monkeypatch.delenv("PBRGPU_NO_CURVE_CULL")
+    h0, o0 = results[0]
+    assert (h0["instance_id"] == 9).sum() > 5000
+    for h, o in results[1:]:
+        for k in ("t", "u", "v", "instance_id", "geom_id", "prim_id"):
+            assert np.array_equal(h0[k], h[k]), k
+        assert np.array_equal(o0, o)
