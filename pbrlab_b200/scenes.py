@@ -2,6 +2,8 @@
 ones (downloaded hair models / large meshes are unavailable offline).  Everything is written in the
 file formats the reference's CLI reads (.obj + .mtl, CyHair .hair), so the same files feed the compiled reference
 (oracle/_ref) and this backend.  Plain numpy; nothing here is on the hot path."""
+import contextlib
+import fcntl
 import gzip
 import os
 import shutil
@@ -20,17 +22,33 @@ def _cache(name):
     return os.path.join(CACHE, name)
 
 
+@contextlib.contextmanager
+def _generating(name):
+    """One process at a time checks for / writes the files of one generated scene: bench.py under torchrun starts
+    N ranks that all ask for the same files at the same moment."""
+    os.makedirs(CACHE, exist_ok=True)
+    with open(os.path.join(CACHE, "." + name + ".lock"), "w") as f:
+        fcntl.flock(f, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(f, fcntl.LOCK_UN)
+
+
 def cornell():
     """data/cornellbox_suzanne_lucy.obj of the reference (kept gzip-compressed in the repo), unpacked once."""
     obj = _cache("cornellbox_suzanne_lucy.obj")
     mtl = _cache("cornellbox_suzanne_lucy.mtl")
-    if not os.path.exists(obj) or os.path.getsize(obj) == 0:
-        tmp = obj + ".tmp%d" % os.getpid()
-        with gzip.open(os.path.join(DATA, "cornellbox_suzanne_lucy.obj.gz"), "rb") as src, open(tmp, "wb") as dst:
-            shutil.copyfileobj(src, dst, 1 << 22)
-        os.replace(tmp, obj)
-    if not os.path.exists(mtl):
-        shutil.copyfile(os.path.join(DATA, "cornellbox_suzanne_lucy.mtl"), mtl)
+    with _generating("cornell"):
+        if not os.path.exists(mtl):
+            tmp = mtl + ".tmp%d" % os.getpid()
+            shutil.copyfile(os.path.join(DATA, "cornellbox_suzanne_lucy.mtl"), tmp)
+            os.replace(tmp, mtl)
+        if not os.path.exists(obj) or os.path.getsize(obj) == 0:
+            tmp = obj + ".tmp%d" % os.getpid()
+            with gzip.open(os.path.join(DATA, "cornellbox_suzanne_lucy.obj.gz"), "rb") as src, open(tmp, "wb") as dst:
+                shutil.copyfileobj(src, dst, 1 << 22)
+            os.replace(tmp, obj)
     return obj
 
 
@@ -68,9 +86,10 @@ def write_cyhair(path, n_strands=50000, n_points=21, center=(-2.5, 6.0, 0.0), ra
 
 def cyhair(n_strands=50000, n_points=21, **kw):
     path = _cache("hair_%d_%d_%s.hair" % (n_strands, n_points, "_".join("%s%s" % (k, v) for k, v in sorted(kw.items()))))
-    if not os.path.exists(path):
-        write_cyhair(path + ".tmp", n_strands, n_points, **kw)
-        os.replace(path + ".tmp", path)
+    with _generating(os.path.basename(path)):
+        if not os.path.exists(path):
+            write_cyhair(path + ".tmp", n_strands, n_points, **kw)
+            os.replace(path + ".tmp", path)
     return path
 
 
@@ -100,8 +119,10 @@ def write_light_stage_obj(path, size=6.0, light_y=9.0):
 
 def light_stage():
     path = _cache("light_stage.obj")
-    if not os.path.exists(path):
-        write_light_stage_obj(path)
+    with _generating("light_stage"):
+        if not os.path.exists(path + ".done"):
+            write_light_stage_obj(path)
+            open(path + ".done", "w").close()
     return path
 
 
@@ -181,9 +202,10 @@ def write_displaced_obj(path, n_tris=20_000_000, seed=7, blobs=8):
 def displaced(n_tris=20_000_000, seed=7):
     path = _cache("displaced_v2_%d_%d.obj" % (n_tris, seed))
     done = path + ".done"
-    if not os.path.exists(done):
-        write_displaced_obj(path, n_tris, seed)
-        open(done, "w").close()
+    with _generating(os.path.basename(path)):
+        if not os.path.exists(done):
+            write_displaced_obj(path, n_tris, seed)
+            open(done, "w").close()
     return path
 
 
@@ -326,5 +348,6 @@ def write_textured_obj(path, seed=5):
 
 def textured():
     path = _cache("textured_box.obj")
-    write_textured_obj(path)
+    with _generating("textured_box"):
+        write_textured_obj(path)
     return path
