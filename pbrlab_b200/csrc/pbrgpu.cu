@@ -124,6 +124,7 @@ struct pbrgpu_ctx {
   bool profile = false;   // time every kernel family with CUDA events (pbrgpu_set_profiling)
   // launch tuning (defaults measured on B200; PBRGPU_* environment variables override for sweeps)
   uint32_t tune_refill = 16;       // idle lanes that trigger a refill in the traversal engine
+  uint32_t tune_refill_any = 24;      // any-hit kernel in triangle scenes (shadow rays end early: fewer, fuller refills win; sweep profiles/r1z_refill_any_sweep.log)
   uint32_t tune_refill_curves = 12;   // same in scenes with curves (lanes wait longer there: held ribbon candidates)
   uint32_t tune_refill_sss = 24;   // same for the random-walk kernel (its converged section is the bounce itself)
   uint32_t tune_prim_lanes = 1, tune_prim_lanes_sss = 1;   // lanes with pending primitives that trigger a primitive phase
@@ -326,8 +327,9 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
     pbr::SssExitKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next);
     mark(4);
-    if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, refill, ctx->tune_prim_lanes);
-    else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, refill, ctx->tune_prim_lanes);
+    const uint32_t refill_any = curves ? refill : ctx->tune_refill_any;
+    if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, refill_any, ctx->tune_prim_lanes);
+    else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, refill_any, ctx->tune_prim_lanes);
     mark(5);
     tm->launches += (s.num_curves ? 6 : 5) + (sort ? 1 : 0);
     tm->closest_launches += 1;
@@ -564,6 +566,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   auto env_int = [](const char* name, int def) { const char* v = getenv(name); return v && *v ? atoi(v) : def; };
   ctx->tune_refill = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_REFILL", int(ctx->tune_refill)))));
+  ctx->tune_refill_any = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_REFILL_ANY", int(ctx->tune_refill_any)))));
   ctx->tune_refill_curves = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_REFILL", int(ctx->tune_refill_curves)))));
   ctx->tune_refill_sss = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_REFILL_SSS", int(ctx->tune_refill_sss)))));
   ctx->tune_prim_lanes = uint32_t(std::min(32, std::max(1, env_int("PBRGPU_PRIM_LANES", int(ctx->tune_prim_lanes)))));
