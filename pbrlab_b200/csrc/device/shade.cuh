@@ -428,7 +428,9 @@ PBR_HD bool SegmentIsClear(const SceneView& s, const vec3& o, const vec3& d, flo
 //   SssPrepareSegment: new direction (bounces > 0) + scatter distance -> w->ray (tmax = scatter distance)
 //   SssFinishSegment:  transmittance / throughput update, roulette, advance.  On kSssHit the caller holds the exit
 //                      intersection along w->ray.
-PBR_HD void SssPrepareSegment(Pcg32* rng, SssWalkState* w) {
+// `channel_pdf`: the channel probabilities the distance was drawn with; the caller hands them back to
+// SssFinishSegment (throughput is unchanged in between), which saves recomputing six IEEE divisions per segment.
+PBR_HD void SssPrepareSegment(Pcg32* rng, SssWalkState* w, vec3* channel_pdf_out) {
   if (w->bounce > 0) {
 #if PBR_SSS_SPHERE_DRAW_RIGHT_TO_LEFT
     const float u2 = Draw(rng), u1 = Draw(rng);
@@ -438,13 +440,11 @@ PBR_HD void SssPrepareSegment(Pcg32* rng, SssWalkState* w) {
     w->ray.d = vnormalized(UniformSampleSphere(u1, u2));
     w->ray.tmin = 0.f;
   }
-  vec3 channel_pdf;
   const float ua = Draw(rng), ub = Draw(rng);
-  w->ray.tmax = SampleScatterDistance(w->throughput, w->sigma_s, w->sigma_t, ua, ub, &channel_pdf);
+  w->ray.tmax = SampleScatterDistance(w->throughput, w->sigma_s, w->sigma_t, ua, ub, channel_pdf_out);
 }
 
-PBR_HD SssStep SssFinishSegment(bool is_hit, float hit_t, Pcg32* rng, SssWalkState* w) {
-  const vec3 channel_pdf = SssChannelPdf(w->throughput, w->sigma_s, w->sigma_t);   // same value as in Prepare
+PBR_HD SssStep SssFinishSegment(bool is_hit, float hit_t, Pcg32* rng, SssWalkState* w, const vec3& channel_pdf) {
   const float t = is_hit ? hit_t : w->ray.tmax;
   const vec3 tr(expf(-w->sigma_t.x * t), expf(-w->sigma_t.y * t), expf(-w->sigma_t.z * t));
   if (is_hit) {
@@ -465,13 +465,14 @@ PBR_HD SssStep SssFinishSegment(bool is_hit, float hit_t, Pcg32* rng, SssWalkSta
 }
 
 PBR_HD SssStep SssBounce(const SceneView& s, Pcg32* rng, SssWalkState* w, HitT* hit, uint64_t* rays) {
-  SssPrepareSegment(rng, w);
+  vec3 channel_pdf;
+  SssPrepareSegment(rng, w, &channel_pdf);
   const bool is_hit = TraceClosest<false>(s, w->ray, hit, nullptr);
 #ifdef PBR_CLEARANCE_PROBE   // tests/host_emul only: every segment the field would skip must be a miss
   PBR_CLEARANCE_PROBE(SegmentIsClear(s, w->ray.o, w->ray.d, w->ray.tmax * 1.001f), is_hit);
 #endif
   if (rays) ++*rays;
-  return SssFinishSegment(is_hit, hit->t, rng, w);
+  return SssFinishSegment(is_hit, hit->t, rng, w, channel_pdf);
 }
 
 // After a surface hit (:385-404) + the success branch of SampleBsdf (cycles-principled-shader.cc:187-216).

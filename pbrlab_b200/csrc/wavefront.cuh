@@ -638,6 +638,7 @@ struct SssClient {
   bool skipped_seg = false;   // the current segment was answered by the clearance grid, not traced
   Pcg32 rng;
   SssWalkState walk;    // walk.ray is rebuilt from the traversal state after every segment
+  vec3 cpdf;            // channel probabilities of the segment in flight (SssPrepareSegment -> SssFinishSegment)
   uint32_t rays = 0, skipped = 0;
 
   __device__ __forceinline__ SssClient(const SceneView& s_, const WaveState& w_, uint32_t cur, uint32_t max_b)
@@ -646,7 +647,7 @@ struct SssClient {
   __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_walk || !exhausted; }
 
   __device__ __forceinline__ void StartSegment(Trav& t) {
-    SssPrepareSegment(&rng, &walk);
+    SssPrepareSegment(&rng, &walk, &cpdf);
     TravBegin(s, walk.ray, t);
     // Segments that end far from any surface: the clearance grid answers those ("no hit") without a traversal; the
     // lane then waits for the next converged section like any lane whose query has finished.  (Finishing chains of
@@ -667,7 +668,7 @@ struct SssClient {
     if (!t.active && has_walk) {
       walk.ray.o = t.O; walk.ray.d = t.D; walk.ray.tmin = t.tmin;   // tmax untouched: the scatter distance
       const bool is_hit = hit.prim != kInvalid;
-      const SssStep st = SssFinishSegment(is_hit, hit.t, &rng, &walk);
+      const SssStep st = SssFinishSegment(is_hit, hit.t, &rng, &walk, cpdf);
       if (skipped_seg) ++skipped; else ++rays;
       --budget;
       if (st == kSssHit) to_exit = true;
