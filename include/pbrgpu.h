@@ -90,7 +90,8 @@ typedef struct pbrgpu_light_tables {
 } pbrgpu_light_tables;
 
 typedef struct pbrgpu_stats {
-  uint64_t paths;          /* camera samples traced by the last pbrgpu_render* call */
+  uint64_t paths;          /* camera samples this process accumulated in the last pbrgpu_render* call (its share of
+                              the job; fewer after a cancel) / paths traced by the last hook call */
   uint64_t closest_rays;   /* closest-hit rays (path vertices) */
   uint64_t shadow_rays;    /* any-hit rays */
   uint64_t sss_rays;       /* closest-hit rays issued inside random-walk subsurface scattering */
@@ -144,9 +145,13 @@ int pbrgpu_scene_bounds(const pbrgpu_ctx* ctx, float* bmin, float* bmax);
  *   rgba_out [w*h*4] += (L.r, L.g, L.b, 1) per sample, count_out [w*h] += 1 per sample (both are overwritten,
  *   i.e. cleared first, as PrepareRendering does).  `seed` selects the per-path PCG32 streams:
  *   path (pixel p, sample s) uses pcg32_srandom(initstate = seed + s, initseq = p).
- *   sample_offset/sample_stride: this call renders samples s = sample_offset + k*sample_stride < spp (a multi-process
- *   launcher gives rank r of R the pair (r, R) and sums the buffers afterwards).
- *   cancel may be NULL; polled between sample batches.  finish_pass (may be NULL) is raised monotonically. */
+ *   sample_offset/sample_stride: this call renders samples s = sample_offset + k*sample_stride < spp (normally 0, 1;
+ *   a launcher that does its own reduction gives rank r of R the pair (r, R); see pbrgpu_nccl_init for the built-in
+ *   multi-process split).
+ *   cancel may be NULL; polled once per wavefront iteration.  When it is raised the call stops handing out samples,
+ *   drops the paths still in flight and returns PBRGPU_OK with what was accumulated so far: every pixel holds whole
+ *   samples only (rgba.a == count), as a cancelled reference render does (src/render.cc:217-231).
+ *   finish_pass (may be NULL) is raised monotonically and never exceeds spp. */
 int pbrgpu_render(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed,
                   uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, float* rgba_out,
                   uint32_t* count_out, size_t* finish_pass);
@@ -155,6 +160,21 @@ int pbrgpu_render(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp
 int pbrgpu_render_device(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed,
                          uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, float* d_rgba,
                          uint32_t* d_count, size_t* finish_pass);
+/* ---- one frame split over several processes (one process per GPU, e.g. torchrun; north_star: "a frame is
+ * partitioned across the 8 GPUs ... the accumulation buffers summed by a single NCCL reduce").  Rank 0 calls
+ * pbrgpu_nccl_unique_id() and hands the 128 bytes to every rank by whatever means the launcher has; then EVERY rank
+ * calls pbrgpu_nccl_init() (collective).  From then on pbrgpu_render / pbrgpu_render_device are collective: rank r of
+ * R renders the samples sample_offset + (r + k*R)*sample_stride of the job — the reference's (tile, sample) job split,
+ * src/render.cc:211-222, with the sample as the unit — and the sums are added onto rank 0 by ONE ncclReduce over
+ * NVLink at frame end (16 B per pixel: count is the alpha sum).  Rank 0 receives the complete frame; the other ranks'
+ * buffers hold their own partial sums.  A context that owns several devices (pbrgpu_create with n_devices > 1) splits
+ * and reduces the same way inside one process (ncclCommInitAll).  NCCL is loaded on first use (dlopen), the library
+ * does not link against it. */
+#define PBRGPU_NCCL_ID_BYTES 128
+int pbrgpu_nccl_unique_id(uint8_t* id128);
+int pbrgpu_nccl_init(pbrgpu_ctx* ctx, const uint8_t* id128, int rank, int world);
+int pbrgpu_job_rank(const pbrgpu_ctx* ctx, int* rank, int* world);
+
 /* Output stage of the reference CLI on the device (pc/pbrlab-cli.cc:47-57, src/image-utils.cc:26-38,72-90,
  * src/io/image-io.cc:172-210): colour = rgba / count -> LinerToSrgb on r,g,b (alpha untouched) -> 8 bit as
  * WritePNG quantises, (unsigned char)clamp(v * 256, 0, 255).  Reads the accumulators the last pbrgpu_render* call

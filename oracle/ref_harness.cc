@@ -24,7 +24,9 @@
 #include "shader/cycles-principled-shader.cc"  // NOLINT(build/include)
 #include "shader/hair-shader.cc"               // NOLINT(build/include)
 
+#include "image-utils.h"
 #include "io/curve-mesh-io.h"
+#include "io/image-io.h"
 #include "io/triangle-mesh-io.h"
 #include "pc-common.h"
 #include "render.h"
@@ -526,6 +528,22 @@ REF_API void ref_sss_sample_distance(const float* in11, float* out4) {
   const std::array<float, 2> u = {in11[9], in11[10]};
   out4[0] = random_walk_sss::SampleScatterDistance(float3(in11), float3(in11 + 3), float3(in11 + 6), u, &cp);
   out4[1] = cp[0]; out4[2] = cp[1]; out4[3] = cp[2];
+}
+
+// ---------------------------------------------------------------- output stage of the CLI (pc/pbrlab-cli.cc:47-57)
+// sums / count -> pbrlab::LinerToSrgb -> pbrlab::io::WritePNG (quantisation src/io/image-io.cc:200-206): the statements
+// of the reference's main(), on caller-supplied RenderLayer contents.  Writes dir/name; returns WritePNG's result.
+REF_API int ref_output_stage(const float* rgba_sums, const uint32_t* count, uint32_t width, uint32_t height,
+                             const char* name, const char* dir) {
+  std::vector<float> color(size_t(width) * height * 4);
+  for (size_t i = 0; i < size_t(width) * height; ++i) {
+    color[i * 4 + 0] = rgba_sums[i * 4 + 0] / float(count[i]);
+    color[i * 4 + 1] = rgba_sums[i * 4 + 1] / float(count[i]);
+    color[i * 4 + 2] = rgba_sums[i * 4 + 2] / float(count[i]);
+    color[i * 4 + 3] = rgba_sums[i * 4 + 3] / float(count[i]);
+  }
+  pbrlab::LinerToSrgb(color, width, height, 4, &color);
+  return pbrlab::io::WritePNG(name, dir, color, width, height, 4) ? 1 : 0;
 }
 
 }  // extern "C"

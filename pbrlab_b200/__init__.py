@@ -204,7 +204,8 @@ def gpu_lib():
                      "pbrgpu_commit", "pbrgpu_scene_bounds", "pbrgpu_render", "pbrgpu_render_device",
                      "pbrgpu_get_stats", "pbrgpu_set_wave_spp", "pbrgpu_set_profiling", "pbrgpu_trace", "pbrgpu_occluded",
                      "pbrgpu_trace_device", "pbrgpu_occluded_device", "pbrgpu_radiance", "pbrgpu_radiance_mega",
-                     "pbrgpu_shade", "pbrgpu_eval_closure", "pbrgpu_measure_gather"):
+                     "pbrgpu_shade", "pbrgpu_eval_closure", "pbrgpu_measure_gather", "pbrgpu_nccl_unique_id",
+                     "pbrgpu_nccl_init", "pbrgpu_job_rank"):
             getattr(L, name).restype = C.c_int
         _gpu = L
     return _gpu
@@ -228,6 +229,9 @@ def host_lib():
         L.pbrhost_last_error.restype = C.c_char_p
         L.pbrhost_render.restype = C.c_double
         L.pbrhost_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.pbrhost_render_cancel.restype = C.c_double
+        L.pbrhost_render_cancel.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
         _host = L
     return _host
 
@@ -268,6 +272,11 @@ class Context:
         words = np.ascontiguousarray(words, np.uint32)
         self._check(self.lib.pbrgpu_set_materials(self.h, _p(words), C.c_uint32(len(words))))
 
+    def nccl_init(self, id_bytes, rank, world):
+        """pbrgpu_nccl_init: join the multi-process job (collective); id_bytes from nccl_unique_id() of rank 0."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id_bytes))
+        self._check(self.lib.pbrgpu_nccl_init(self.h, buf, C.c_int(rank), C.c_int(world)))
+
     def set_wave_spp(self, n):
         self._check(self.lib.pbrgpu_set_wave_spp(self.h, C.c_uint32(n)))
 
@@ -291,13 +300,14 @@ class Context:
         self._check(self.lib.pbrgpu_get_stats(self.h, C.byref(s)))
         return s.as_dict()
 
-    def render(self, width, height, spp, seed=1234567890, sample_offset=0, sample_stride=1):
-        """pbrgpu_render with HOST output buffers (sums, like RenderLayer)."""
+    def render(self, width, height, spp, seed=1234567890, sample_offset=0, sample_stride=1, cancel=None):
+        """pbrgpu_render with HOST output buffers (sums, like RenderLayer).  cancel: optional ctypes c_int the call
+        polls (raise it from another thread)."""
         rgba = np.empty((height, width, 4), np.float32)
         count = np.empty((height, width), np.uint32)
         self._check(self.lib.pbrgpu_render(self.h, C.c_uint32(width), C.c_uint32(height), C.c_uint32(spp),
                                            C.c_uint64(seed), C.c_uint32(sample_offset), C.c_uint32(sample_stride),
-                                           None, _p(rgba), _p(count), None))
+                                           C.byref(cancel) if cancel is not None else None, _p(rgba), _p(count), None))
         return rgba, count
 
     def render_device(self, width, height, spp, d_rgba_ptr, d_count_ptr, seed=1234567890, sample_offset=0,
@@ -307,6 +317,11 @@ class Context:
                                                   C.c_uint64(seed), C.c_uint32(sample_offset),
                                                   C.c_uint32(sample_stride), None, C.c_void_p(d_rgba_ptr),
                                                   C.c_void_p(d_count_ptr), None))
+
+    def resolve_srgb8_device(self, d_rgba_ptr, d_count_ptr, width, height, d_out_ptr):
+        """pbrgpu_resolve_srgb8_device: the output stage on caller-supplied DEVICE accumulators"""
+        self._check(self.lib.pbrgpu_resolve_srgb8_device(self.h, C.c_void_p(d_rgba_ptr), C.c_void_p(d_count_ptr),
+                                                         C.c_uint32(width), C.c_uint32(height), C.c_void_p(d_out_ptr)))
 
     def resolve_srgb8(self, width, height):
         """pbrgpu_resolve_srgb8: the CLI's output stage (mean -> sRGB -> 8 bit) of the last rendered frame."""
@@ -362,6 +377,15 @@ class Context:
         return out
 
 
+def nccl_unique_id():
+    """pbrgpu_nccl_unique_id: 128 bytes rank 0 hands to every rank of a multi-process job."""
+    buf = (C.c_uint8 * 128)()
+    rc = gpu_lib().pbrgpu_nccl_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError("pbrgpu_nccl_unique_id: " + gpu_lib().pbrgpu_last_error(None).decode())
+    return bytes(buf)
+
+
 class Scene:
     """pbrlab::Scene built by CreateScene() from .obj / .hair files (the reference CLI's path)."""
 
@@ -404,3 +428,15 @@ class Scene:
         if sec < 0:
             raise RuntimeError("Render failed: " + self.lib.pbrhost_last_error().decode())
         return rgba, count, sec
+
+    def render_cancelled(self, width, height, spp, cancel_at_pass, seed=1234567890):
+        """pbrlab::Render() with the cancel flag raised by a second thread once finish_pass >= cancel_at_pass.
+        Returns (rgba sums, count, info) with info = dict(returned, finish_pass, progress_violation, raised_at, seconds)."""
+        rgba = np.empty((height, width, 4), np.float32)
+        count = np.empty((height, width), np.uint32)
+        out = np.zeros(4, np.uint64)
+        sec = self.lib.pbrhost_render_cancel(self.h, width, height, spp, seed, cancel_at_pass, _p(rgba), _p(count), _p(out))
+        if sec < 0:
+            raise RuntimeError("Render threw: " + self.lib.pbrhost_last_error().decode())
+        return rgba, count, {"returned": bool(out[0]), "finish_pass": int(out[1]), "progress_violation": bool(out[2]),
+                             "raised_at": int(out[3]), "seconds": sec}

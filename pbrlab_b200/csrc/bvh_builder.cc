@@ -55,8 +55,8 @@ struct Builder {
   uint32_t Alloc() { return next_node.fetch_add(1); }
 
   // Near the root there are fewer ranges than host threads: the passes over a large range are cut into chunks and
-  // run on the threads nobody uses yet.  Every reduction below is a min / max / integer sum, so the result does
-  // not depend on the chunking.
+  // run on the threads nobody uses yet.  Every reduction below is a min / max / integer sum and both partition paths
+  // are stable, so neither the tree nor the primitive order depends on the chunking or on thread timing.
   static constexpr uint32_t kParallelMin = 1u << 18;
   int GrabThreads(int want) {
     int got = 0;
@@ -227,7 +227,9 @@ struct Builder {
         });
         mid = begin + total_left;
       } else {
-        uint32_t* m = std::partition(idx.data() + begin, idx.data() + end, goes_left);
+        // stable like the chunked scatter above: whether helper threads were free depends on timing, the primitive
+        // order inside a range (hence leaf order, tie-breaking of coincident hits, the "split in half" fallback) must not
+        uint32_t* m = std::stable_partition(idx.data() + begin, idx.data() + end, goes_left);
         mid = uint32_t(m - idx.data());
       }
     } else {

@@ -17,18 +17,30 @@
 
 #include "../../include/pbrgpu.h"
 #include "kat.cuh"
+#include "nccl_shim.h"
 #include "scene_host.h"
 #include "wavefront.cuh"
 
+struct pbrgpu_ctx;
 namespace {
 
 std::string g_create_error;
+// the per-device worker threads of a multi-device context may fail at the same time: ctx->error is written under a lock
+void SetError(pbrgpu_ctx* ctx, const std::string& msg);
 
 #define CUDA_TRY(ctx, expr)                                                                      \
   do {                                                                                           \
     cudaError_t err__ = (expr);                                                                  \
     if (err__ != cudaSuccess) {                                                                  \
-      (ctx)->error = std::string(#expr) + ": " + cudaGetErrorString(err__);                      \
+      SetError((ctx), std::string(#expr) + ": " + cudaGetErrorString(err__));                    \
+      return PBRGPU_ERR_CUDA;                                                                    \
+    }                                                                                            \
+  } while (0)
+#define NCCL_TRY(ctx, expr)                                                                      \
+  do {                                                                                           \
+    ncclResult_t err__ = (expr);                                                                 \
+    if (err__ != ncclSuccess) {                                                                  \
+      SetError((ctx), std::string(#expr) + ": " + pbrnccl::Get().GetErrorString(err__));         \
       return PBRGPU_ERR_CUDA;                                                                    \
     }                                                                                            \
   } while (0)
@@ -85,6 +97,7 @@ struct Device {
   uint32_t wave_capacity = 0;
   // frame accumulators (device side of RenderLayer)
   DevBuf<float4> rgba;
+  DevBuf<float4> peer_tmp;    // scratch of the NCCL-less frame-end sum
   DevBuf<uint32_t> count;
   DevBuf<uint8_t> srgb8;      // output stage (pbrgpu_resolve_srgb8)
   uint32_t frame_width = 0, frame_height = 0;   // size of the last rendered frame
@@ -101,7 +114,7 @@ struct Device {
     slot.Free(); walk.Free(); sh_o.Free(); sh_d.Free(); sh_c.Free();
     q0.Free(); q1.Free(); q_surface.Free(); q_hair.Free(); q_sss.Free(); q_exit.Free(); counters.Free(); stats.Free();
     q_walk0.Free(); q_walk1.Free(); q_done0.Free(); q_done1.Free();
-    rgba.Free(); count.Free();
+    rgba.Free(); count.Free(); peer_tmp.Free();
     if (h_counters) cudaFreeHost(h_counters);
     if (h_stats) cudaFreeHost(h_stats);
     h_counters = nullptr; h_stats = nullptr;
@@ -118,6 +131,12 @@ struct pbrgpu_ctx {
   std::vector<Device> devices;
   pbrhost::HostScene host;
   std::string error;
+  std::mutex error_mutex;
+  // frame-end reduce: one communicator per device of a multi-device context (ncclCommInitAll, created
+  // by the first multi-device render), and/or one communicator of a multi-process job (pbrgpu_nccl_init)
+  std::vector<ncclComm_t> dev_comms;
+  ncclComm_t job_comm = nullptr;
+  int job_rank = 0, job_world = 1;
   pbrgpu_stats stats;
   uint32_t wave_spp = 0;
   bool committed = false;
@@ -131,6 +150,17 @@ struct pbrgpu_ctx {
   uint32_t tune_ribbon_lanes = 8;  // lanes holding a curve candidate that trigger the (batched) ribbon test
   int tune_l2_persist = 0;         // persisting-L2 window over the traversal data
   int tune_walk_bounces = 16;   // bounces a walk gets per launch before it is parked (pool busy)
+  // Bounce budget while the pool drains: a launch of the walk kernel is given about this many bounce steps in total
+  // (Mi), i.e. budget = clamp(target / walks in flight, tune_walk_bounces, tune_walk_bounces_max).  With the pool full
+  // there are ~1 Mi walks in flight (budget 16); as the frame runs out of samples the walks that are left get longer
+  // slices instead of one 16-bounce slice per (ever shorter) iteration, so the tail of a frame is bounded by the
+  // longest walk, not by (longest walk / 16) host round trips.
+  int tune_walk_target_mi = 16;
+  int tune_walk_bounces_max = 2048;
+  // path slots in flight = clamp(samples of the frame / tune_pool_div, tune_pool_min_mi, tune_pool_mi): a frame
+  // that is only a few pool-fills long (strong scaling: 1/8 of the samples per GPU) spends a smaller share of its
+  // time ramping up and draining with a smaller pool
+  int tune_pool_div = 8, tune_pool_min_mi = 4;
   int tune_clear_march = 4;        // sphere-tracing steps of the clearance test along a walk segment
   int tune_sss_skip = 1;           // clearance grid: random-walk segments that provably hit nothing are not traced
   int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
@@ -142,6 +172,11 @@ struct pbrgpu_ctx {
 
 namespace {
 
+void SetError(pbrgpu_ctx* ctx, const std::string& msg) {
+  std::lock_guard<std::mutex> lock(ctx->error_mutex);
+  ctx->error = msg;
+}
+
 using pbr::SceneView;
 using pbr::WaveState;
 
@@ -150,7 +185,6 @@ constexpr int kBlock = 128;
 // (tens of microseconds for a single warp), so a launch lasts at least budget x that: while the pool is busy a small
 // budget keeps the launch throughput-bound (more, shorter walk slices in flight); once only stragglers are left a
 // large budget saves host round-trips.
-constexpr uint32_t kSssBouncesBusy = 16;
 constexpr uint32_t kSssBouncesDrain = 1024;
 constexpr uint32_t kDrainThreshold = 1u << 16;   // slots in flight below which the pool counts as draining
 int PersistentGrid(const Device& d, int blocks_per_sm) { return d.sm_count * blocks_per_sm; }
@@ -302,12 +336,23 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
   // state after the set-up kernel (host knows it): hooks start with n active slots, frames with N retired slots
   bool have_active = (frame == nullptr), have_walk = false, have_done = (frame != nullptr);
   uint64_t in_flight = ~0ull;   // slots that will trace or walk in the coming iteration (unknown before the first)
+  uint64_t walks = ~0ull;       // of those, random walks that resume in the coming iteration (new ones join them)
   for (uint32_t it = 0; (have_active || have_walk || have_done) && it < max_iterations; ++it) {
     if (cancel && *cancel) break;
     const uint32_t next = parity ^ 1u;
     // single-vertex mode lets the walk run to its end inside the one iteration
-    const uint32_t walk_budget =
-        (max_iterations == 1u) ? 0x7fffffffu : (in_flight < kDrainThreshold ? kSssBouncesDrain : uint32_t(ctx->tune_walk_bounces));
+    uint32_t walk_budget = uint32_t(ctx->tune_walk_bounces);
+    if (max_iterations == 1u) {
+      walk_budget = 0x7fffffffu;
+    } else if (ctx->tune_walk_target_mi > 0) {
+      // walks that resume + (an estimate of) the walks this iteration starts: while the pool is busy the estimate is
+      // irrelevant (budget = floor), while it drains the new walks are a fraction of the few paths still active
+      const uint64_t w_est = std::max<uint64_t>(walks == ~0ull ? ~0ull : walks + (in_flight - walks) / 8, 1);
+      const uint64_t b = (uint64_t(ctx->tune_walk_target_mi) << 20) / w_est;
+      walk_budget = uint32_t(std::min<uint64_t>(std::max<uint64_t>(b, uint64_t(ctx->tune_walk_bounces)), uint64_t(ctx->tune_walk_bounces_max)));
+    } else if (in_flight < kDrainThreshold) {
+      walk_budget = kSssBouncesDrain;
+    }
     const bool prof = ctx->profile;
     auto mark = [&](int k) { if (prof) cudaEventRecord(d.kev[k], st); };
     const uint32_t regen = frame ? 1u : 0u;
@@ -321,7 +366,10 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     mark(2);
     pbr::ShadeSurfaceKernel<false><<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
     if (sort) pbr::ShadeSurfaceKernel<true><<<grid_diffuse, ctx->tune_diffuse_threads, 0, st>>>(s, w, next, flags);
-    if (s.num_curves) pbr::ShadeHairKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
+    // hits are routed by material CLASS (a hair material on a triangle goes to q_hair as well, as the reference's
+    // Shader() dispatches on the material type, shader.cc:8-34), so the kernel runs whenever that queue can fill
+    const bool hair = s.num_curves != 0u || s.num_hair_materials != 0u;
+    if (hair) pbr::ShadeHairKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
     mark(3);
     if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
     else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
@@ -331,7 +379,7 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, refill_any, ctx->tune_prim_lanes);
     else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, refill_any, ctx->tune_prim_lanes);
     mark(5);
-    tm->launches += (s.num_curves ? 6 : 5) + (sort ? 1 : 0);
+    tm->launches += (hair ? 6 : 5) + (sort ? 1 : 0);
     tm->closest_launches += 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(d.h_counters, w.counters, sizeof(uint32_t) * pbr::kCounterCount,
                                   cudaMemcpyDeviceToHost, st));
@@ -348,6 +396,7 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     // retired slots only matter while they can be accumulated (frame mode); hooks read rad[] directly
     have_done = frame && d.h_counters[pbr::kNumDone0 + next] > 0;
     in_flight = uint64_t(d.h_counters[pbr::kNumActive0 + next]) + d.h_counters[pbr::kNumWalk0 + next];
+    walks = d.h_counters[pbr::kNumWalk0 + next];
     if (frame && d.h_stats[pbr::kStatNextSample] < frame->total_samples) in_flight += d.h_counters[pbr::kNumDone0 + next];
     if (frame && finish_pass) {
       const size_t passes = size_t(d.h_stats[pbr::kStatRetired] / frame->npix);
@@ -370,7 +419,13 @@ int FetchStats(pbrgpu_ctx* ctx, Device& d) {
 // number of path slots kept in flight: enough to fill the GPU many times over (each iteration costs one host
 // round-trip), small enough that the SoA state (~300 B/slot) streams through HBM quickly
 uint32_t ChoosePoolSize(const pbrgpu_ctx* ctx, uint64_t npix, uint64_t total_samples) {
-  uint64_t n = ctx->wave_spp ? uint64_t(ctx->wave_spp) * npix : (uint64_t(ctx->tune_pool_mi) << 20);
+  uint64_t n = uint64_t(ctx->tune_pool_mi) << 20;
+  if (ctx->wave_spp) {
+    n = uint64_t(ctx->wave_spp) * npix;
+  } else {
+    const uint64_t lo = uint64_t(ctx->tune_pool_min_mi) << 20;
+    n = std::min(n, std::max(lo, total_samples / uint64_t(ctx->tune_pool_div)));
+  }
   n = std::min<uint64_t>(n, total_samples);
   n = std::min<uint64_t>(n, 64ull << 20);
   return uint32_t(std::max<uint64_t>(n, 1));
@@ -382,7 +437,7 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
                    LoopTimers* tm) {
   CUDA_TRY(ctx, cudaSetDevice(d.id));
   const uint64_t npix64 = uint64_t(width) * height;
-  if (npix64 == 0 || npix64 > 0x7fffffffull) { ctx->error = "pbrgpu_render: bad image size"; return PBRGPU_ERR_INVALID; }
+  if (npix64 == 0 || npix64 > 0x7fffffffull) { SetError(ctx, "pbrgpu_render: bad image size"); return PBRGPU_ERR_INVALID; }
   const uint32_t npix = uint32_t(npix64);
   const uint32_t local_spp = (spp > sample_offset) ? (spp - sample_offset + sample_stride - 1) / sample_stride : 0;
   CUDA_TRY(ctx, d.rgba.Alloc(npix));
@@ -390,7 +445,11 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   d.frame_width = width; d.frame_height = height;
   CUDA_TRY(ctx, cudaMemsetAsync(d.rgba.ptr, 0, sizeof(float4) * npix, d.stream));
   CUDA_TRY(ctx, cudaMemsetAsync(d.count.ptr, 0, sizeof(uint32_t) * npix, d.stream));
-  if (local_spp == 0) { CUDA_TRY(ctx, cudaStreamSynchronize(d.stream)); return PBRGPU_OK; }
+  if (local_spp == 0) {   // more devices than samples: this one contributes zeros (and no stale statistics)
+    if (d.h_stats) memset(d.h_stats, 0, sizeof(unsigned long long) * pbr::kStatCount);
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+    return PBRGPU_OK;
+  }
   const uint64_t total = npix64 * local_spp;
   uint32_t n_slots = ChoosePoolSize(ctx, npix, total);
   if (n_slots > d.wave_capacity) {
@@ -426,8 +485,6 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   flags.skip_emission_and_roulette = 0;
   rc = RunPool(ctx, d, &frame, 0xffffffffu, flags, tm, cancel, finish_pass, sample_offset, sample_stride, spp);
   if (rc != PBRGPU_OK) return rc;
-  pbr::FinishFrameKernel<<<(npix + 255) / 256, 256, 0, d.stream>>>(d.rgba.ptr, d.count.ptr, npix);
-  tm->launches++;
   CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
   float ms = 0.f;
@@ -436,14 +493,14 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   return FetchStats(ctx, d);
 }
 
-__global__ void AddBuffersKernel(float4* dst, const float4* src, uint32_t* cdst, const uint32_t* csrc, uint32_t n) {
+// fallback of the in-process frame-end sum when NCCL cannot be loaded: dst += src (src = a peer copy)
+__global__ void AddBuffersKernel(float4* dst, const float4* src, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 a = dst[i];
   const float4 b = src[i];
   a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
   dst[i] = a;
-  cdst[i] += csrc[i];
 }
 
 // Output stage (pc/pbrlab-cli.cc:47-57): mean = sum / count, LinerTosRGB on r,g,b (image-utils.cc:26-38: 12.92 c
@@ -454,7 +511,7 @@ __device__ __forceinline__ float LinearToSrgbDev(float c) {
   return powf((1.0f + 0.055f) * c, float(1.0 / 2.4)) - 0.055f;
 }
 __device__ __forceinline__ unsigned char Quantise8(float v) {
-  const float x = fmaxf(0.0f, fminf(255.0f, v * 256.0f));   // Clamp(x, 0, 255): NaN -> 0 like std::max(a, std::min(b, x))
+  const float x = fmaxf(0.0f, fminf(255.0f, v * 256.0f));   // Clamp(x, 0, 255) = std::max(a, std::min(b, x)): a NaN becomes 255 in both (std::min keeps b, fminf drops the NaN)
   return static_cast<unsigned char>(x);
 }
 __global__ void ResolveSrgb8Kernel(const float4* __restrict__ rgba, const uint32_t* __restrict__ count, uint32_t npix,
@@ -579,6 +636,10 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_l2_persist = env_int("PBRGPU_L2_PERSIST", ctx->tune_l2_persist);
   ctx->tune_sss_skip = env_int("PBRGPU_SSS_SKIP", ctx->tune_sss_skip);
   ctx->tune_walk_bounces = std::min(8192, std::max(1, env_int("PBRGPU_WALK_BOUNCES", ctx->tune_walk_bounces)));
+  ctx->tune_walk_target_mi = std::min(4096, std::max(0, env_int("PBRGPU_WALK_TARGET_MI", ctx->tune_walk_target_mi)));
+  ctx->tune_walk_bounces_max = std::min(1 << 20, std::max(1, env_int("PBRGPU_WALK_BOUNCES_MAX", ctx->tune_walk_bounces_max)));
+  ctx->tune_pool_div = std::max(1, env_int("PBRGPU_POOL_DIV", ctx->tune_pool_div));
+  ctx->tune_pool_min_mi = std::min(64, std::max(1, env_int("PBRGPU_POOL_MIN_MI", ctx->tune_pool_min_mi)));
   ctx->tune_clear_march = std::min(64, std::max(1, env_int("PBRGPU_CLEAR_MARCH", ctx->tune_clear_march)));
   ctx->tune_sort_materials = env_int("PBRGPU_SORT_MATERIALS", ctx->tune_sort_materials);
   ctx->tune_diffuse_blocks = std::max(1, env_int("PBRGPU_DIFFUSE_BLOCKS", ctx->tune_diffuse_blocks));
@@ -620,6 +681,8 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
 
 void pbrgpu_destroy(pbrgpu_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->job_comm) pbrnccl::Get().CommDestroy(ctx->job_comm);
+  for (ncclComm_t c : ctx->dev_comms) if (c) pbrnccl::Get().CommDestroy(c);
   for (Device& d : ctx->devices) {
     cudaSetDevice(d.id);
     d.Release();
@@ -657,15 +720,17 @@ int pbrgpu_set_curves(pbrgpu_ctx* ctx, const float* xyzr, uint32_t nverts, const
 
 int pbrgpu_set_materials(pbrgpu_ctx* ctx, const pbrgpu_material* materials, uint32_t n) {
   if (!ctx) return PBRGPU_ERR_INVALID;
-  if (!ctx->host.SetMaterials(materials, n)) {
-    ctx->error = ctx->host.error;
-    return PBRGPU_ERR_INVALID;
-  }
-  if (ctx->committed) {   // live edit: refresh the table in place
+  if (ctx->committed) {   // live edit: validate against the committed geometry BEFORE the host table is replaced
     for (const auto& id : ctx->host.tri_ids)
       if (id.w != PBRGPU_INVALID_ID && id.w >= n) { ctx->error = "pbrgpu_set_materials: table shrank below ids in use"; return PBRGPU_ERR_INVALID; }
     for (const auto& id : ctx->host.curve_ids)
       if (id.w != PBRGPU_INVALID_ID && id.w >= n) { ctx->error = "pbrgpu_set_materials: table shrank below ids in use"; return PBRGPU_ERR_INVALID; }
+  }
+  if (!ctx->host.SetMaterials(materials, n)) {   // validates everything else before it mutates (scene_host.cc)
+    ctx->error = ctx->host.error;
+    return PBRGPU_ERR_INVALID;
+  }
+  if (ctx->committed) {   // refresh the device tables in place
     for (Device& d : ctx->devices) {
       CUDA_TRY(ctx, cudaSetDevice(d.id));
       CUDA_TRY(ctx, d.materials.Upload(ctx->host.materials.data(), ctx->host.materials.size(), d.stream));
@@ -720,6 +785,44 @@ int pbrgpu_scene_bounds(const pbrgpu_ctx* ctx, float* bmin, float* bmax) {
   return PBRGPU_OK;
 }
 
+// ---- multi-process jobs: one process per GPU (torchrun), the frame-end reduce runs inside the library
+int pbrgpu_nccl_unique_id(uint8_t* id128) {
+  const pbrnccl::Api& nccl = pbrnccl::Get();
+  if (!id128) return PBRGPU_ERR_INVALID;
+  if (!nccl.ok) { g_create_error = nccl.error; return PBRGPU_ERR_CUDA; }
+  ncclUniqueId id;
+  const ncclResult_t r = nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + nccl.GetErrorString(r); return PBRGPU_ERR_CUDA; }
+  static_assert(sizeof(id) == PBRGPU_NCCL_ID_BYTES, "ncclUniqueId size");
+  memcpy(id128, &id, sizeof(id));
+  return PBRGPU_OK;
+}
+
+int pbrgpu_nccl_init(pbrgpu_ctx* ctx, const uint8_t* id128, int rank, int world) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) {
+    if (ctx) ctx->error = "pbrgpu_nccl_init: bad arguments";
+    return PBRGPU_ERR_INVALID;
+  }
+  if (ctx->devices.size() != 1) { ctx->error = "pbrgpu_nccl_init: a multi-process job uses one device per process"; return PBRGPU_ERR_INVALID; }
+  const pbrnccl::Api& nccl = pbrnccl::Get();
+  if (!nccl.ok) { ctx->error = nccl.error; return PBRGPU_ERR_CUDA; }
+  if (ctx->job_comm) { nccl.CommDestroy(ctx->job_comm); ctx->job_comm = nullptr; ctx->job_rank = 0; ctx->job_world = 1; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->devices[0].id));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NCCL_TRY(ctx, nccl.CommInitRank(&ctx->job_comm, world, id, rank));
+  ctx->job_rank = rank;
+  ctx->job_world = world;
+  return PBRGPU_OK;
+}
+
+int pbrgpu_job_rank(const pbrgpu_ctx* ctx, int* rank, int* world) {
+  if (!ctx) return PBRGPU_ERR_INVALID;
+  if (rank) *rank = ctx->job_rank;
+  if (world) *world = ctx->job_world;
+  return PBRGPU_OK;
+}
+
 int pbrgpu_set_wave_spp(pbrgpu_ctx* ctx, uint32_t spp_per_wave) {
   if (!ctx) return PBRGPU_ERR_INVALID;
   ctx->wave_spp = spp_per_wave;
@@ -738,6 +841,46 @@ int pbrgpu_get_stats(const pbrgpu_ctx* ctx, pbrgpu_stats* out) {
   return PBRGPU_OK;
 }
 
+// Frame-end sum of the per-device accumulators onto the context's first device.  Only the float4
+// sums travel: alpha counts the samples (render.cc:175-183 increments both together), so RenderLayer::count is
+// derived after the reduce and ONE ncclReduce of 16 B per pixel does the whole job.
+static int ReduceDevices(pbrgpu_ctx* ctx, uint32_t npix) {
+  const uint32_t ndev = uint32_t(ctx->devices.size());
+  if (ndev < 2) return PBRGPU_OK;
+  Device& d0 = ctx->devices[0];
+  const pbrnccl::Api& nccl = pbrnccl::Get();
+  if (nccl.ok && getenv("PBRGPU_NO_NCCL") == nullptr) {
+    if (ctx->dev_comms.empty()) {
+      std::vector<int> ids;
+      for (const Device& d : ctx->devices) ids.push_back(d.id);
+      ctx->dev_comms.assign(ndev, nullptr);
+      NCCL_TRY(ctx, nccl.CommInitAll(ctx->dev_comms.data(), int(ndev), ids.data()));
+    }
+    NCCL_TRY(ctx, nccl.GroupStart());
+    for (uint32_t k = 0; k < ndev; ++k) {
+      Device& d = ctx->devices[k];
+      nccl.Reduce(d.rgba.ptr, d.rgba.ptr, size_t(npix) * 4, ncclFloat, ncclSum, 0, ctx->dev_comms[k], d.stream);
+    }
+    NCCL_TRY(ctx, nccl.GroupEnd());
+    for (Device& d : ctx->devices) {
+      CUDA_TRY(ctx, cudaSetDevice(d.id));
+      CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+    }
+    CUDA_TRY(ctx, cudaSetDevice(d0.id));
+    return PBRGPU_OK;
+  }
+  // no NCCL on this host: peer copies into a scratch buffer (kept with the context) + add
+  CUDA_TRY(ctx, cudaSetDevice(d0.id));
+  CUDA_TRY(ctx, d0.peer_tmp.Alloc(npix));
+  for (uint32_t k = 1; k < ndev; ++k) {
+    Device& dk = ctx->devices[k];
+    CUDA_TRY(ctx, cudaMemcpyPeerAsync(d0.peer_tmp.ptr, d0.id, dk.rgba.ptr, dk.id, sizeof(float4) * npix, d0.stream));
+    AddBuffersKernel<<<(npix + 255) / 256, 256, 0, d0.stream>>>(d0.rgba.ptr, d0.peer_tmp.ptr, npix);
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(d0.stream));
+  return PBRGPU_OK;
+}
+
 static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed,
                       uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, float* rgba_out,
                       uint32_t* count_out, size_t* finish_pass, bool out_on_device) {
@@ -745,21 +888,31 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
   if (sample_stride == 0 || !rgba_out || !count_out) { ctx->error = "pbrgpu_render: bad arguments"; return PBRGPU_ERR_INVALID; }
   const auto t0 = std::chrono::steady_clock::now();
   const uint32_t ndev = uint32_t(ctx->devices.size());
-  const uint32_t npix = width * height;
+  const uint64_t npix64 = uint64_t(width) * height;
+  if (npix64 == 0 || npix64 > 0x7fffffffull) { ctx->error = "pbrgpu_render: bad image size"; return PBRGPU_ERR_INVALID; }
+  const uint32_t npix = uint32_t(npix64);
   if (finish_pass) *finish_pass = 0;
+  // The job's samples sample_offset + j*sample_stride are dealt out round-robin: first over the ranks of a
+  // multi-process job (pbrgpu_nccl_init), then over the devices of this context — the (tile, sample) job split of the
+  // reference (render.cc:211-222) with the sample as the unit.  Every path keeps its own PCG32 stream
+  // (seed + sample, pixel), so the image does not depend on the split (up to the order of the float sums).
+  const uint32_t world = uint32_t(ctx->job_world), rank = uint32_t(ctx->job_rank);
+  const uint64_t stride64 = uint64_t(sample_stride) * world * ndev;
+  if (stride64 > 0xffffffffull) { ctx->error = "pbrgpu_render: sample stride overflow"; return PBRGPU_ERR_INVALID; }
+  const uint32_t my_offset = sample_offset + rank * sample_stride, my_stride = sample_stride * world;
   std::vector<LoopTimers> tms(ndev);
   std::vector<int> rcs(ndev, PBRGPU_OK);
   std::vector<size_t> progress(ndev, 0);
   if (ndev == 1) {
-    rcs[0] = RenderOnDevice(ctx, ctx->devices[0], width, height, spp, seed, sample_offset, sample_stride, cancel,
-                            finish_pass, &tms[0]);
+    rcs[0] = RenderOnDevice(ctx, ctx->devices[0], width, height, spp, seed, my_offset, my_stride, cancel, finish_pass,
+                            &tms[0]);
   } else {
-    // one host thread per device; device k renders samples sample_offset + (k + j*ndev)*sample_stride
+    // one host thread per device; device k renders samples my_offset + (k + j*ndev)*my_stride
     std::vector<std::thread> th;
     for (uint32_t k = 0; k < ndev; ++k) {
       th.emplace_back([&, k]() {
-        rcs[k] = RenderOnDevice(ctx, ctx->devices[k], width, height, spp, seed, sample_offset + k * sample_stride,
-                                sample_stride * ndev, cancel, &progress[k], &tms[k]);
+        rcs[k] = RenderOnDevice(ctx, ctx->devices[k], width, height, spp, seed, my_offset + k * my_stride,
+                                my_stride * ndev, cancel, &progress[k], &tms[k]);
       });
     }
     for (auto& t : th) t.join();
@@ -771,28 +924,22 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
   }
   for (uint32_t k = 0; k < ndev; ++k) if (rcs[k] != PBRGPU_OK) return rcs[k];
 
-  // frame-end sum of the per-device accumulators onto device 0 (peer copies over NVLink)
+  // ---- frame end: sums onto device 0 of this context, then onto rank 0 of the job; count from alpha
   Device& d0 = ctx->devices[0];
+  int rc = ReduceDevices(ctx, npix);
+  if (rc != PBRGPU_OK) return rc;
   CUDA_TRY(ctx, cudaSetDevice(d0.id));
-  if (ndev > 1) {
-    DevBuf<float4> tmp_rgba;
-    DevBuf<uint32_t> tmp_count;
-    CUDA_TRY(ctx, tmp_rgba.Alloc(npix));
-    CUDA_TRY(ctx, tmp_count.Alloc(npix));
-    for (uint32_t k = 1; k < ndev; ++k) {
-      Device& dk = ctx->devices[k];
-      CUDA_TRY(ctx, cudaMemcpyPeerAsync(tmp_rgba.ptr, d0.id, dk.rgba.ptr, dk.id, sizeof(float4) * npix, d0.stream));
-      CUDA_TRY(ctx, cudaMemcpyPeerAsync(tmp_count.ptr, d0.id, dk.count.ptr, dk.id, sizeof(uint32_t) * npix, d0.stream));
-      AddBuffersKernel<<<(npix + 255) / 256, 256, 0, d0.stream>>>(d0.rgba.ptr, tmp_rgba.ptr, d0.count.ptr, tmp_count.ptr, npix);
-    }
-    CUDA_TRY(ctx, cudaStreamSynchronize(d0.stream));
-    tmp_rgba.Free();
-    tmp_count.Free();
+  if (ctx->job_comm) {
+    const pbrnccl::Api& nccl = pbrnccl::Get();
+    NCCL_TRY(ctx, nccl.Reduce(d0.rgba.ptr, d0.rgba.ptr, size_t(npix) * 4, ncclFloat, ncclSum, 0, ctx->job_comm, d0.stream));
   }
+  pbr::FinishFrameKernel<<<(npix + 255) / 256, 256, 0, d0.stream>>>(d0.rgba.ptr, d0.count.ptr, npix);
+  tms[0].launches++;
   const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   CUDA_TRY(ctx, cudaMemcpyAsync(rgba_out, d0.rgba.ptr, sizeof(float4) * npix, kind, d0.stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(count_out, d0.count.ptr, sizeof(uint32_t) * npix, kind, d0.stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(d0.stream));
+  CUDA_TRY(ctx, cudaGetLastError());
 
   pbrgpu_stats& s = ctx->stats;
   memset(&s, 0, sizeof(s));
@@ -803,6 +950,7 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
       s.shadow_rays += d.h_stats[pbr::kStatShadow];
       s.sss_rays += d.h_stats[pbr::kStatSss];
       s.sss_skipped += d.h_stats[pbr::kStatSssSkipped];
+      s.paths += d.h_stats[pbr::kStatRetired];   // camera samples this process accumulated (< its share after a cancel)
     }
     s.kernel_launches += tms[k].launches;
     s.trace_closest_launches += tms[k].closest_launches;
@@ -810,9 +958,6 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
     s.sss_ms += tms[k].sss_ms; s.regen_ms += tms[k].regen_ms;
     s.device_ms = std::max(s.device_ms, tms[k].device_ms);
   }
-  uint64_t samples = 0;
-  for (uint32_t sidx = sample_offset; sidx < spp; sidx += sample_stride) ++samples;
-  s.paths = samples * npix;
   s.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return PBRGPU_OK;
 }

@@ -1,14 +1,17 @@
 // C door into the C++ host API (pbrlab::Scene / Render / loaders) for the Python tests, bench.py and the graft
 // entry points — ctypes cannot call C++.  Nothing here adds behaviour: every function forwards to the public
 // classes the reference's callers would use.
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <exception>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pbrgpu.h"
 #include "io/curve-mesh-io.h"
+#include "io/image-io.h"
 #include "io/triangle-mesh-io.h"
 #include "pc-common.h"
 #include "render.h"
@@ -111,9 +114,55 @@ double pbrhost_render(void* s, uint32_t w, uint32_t h, uint32_t spp, uint64_t se
     std::atomic_size_t finish_pass(0);
     pbrlab::RenderLayer layer;
     const auto t0 = std::chrono::steady_clock::now();
-    pbrlab::Render(*static_cast<pbrlab::Scene*>(s), w, h, spp, cancel, &layer, &finish_pass);
+    const bool ok = pbrlab::Render(*static_cast<pbrlab::Scene*>(s), w, h, spp, cancel, &layer, &finish_pass);
     const auto t1 = std::chrono::steady_clock::now();
+    if (!ok) { g_error = pbrlab::LastRenderError(); return -1.0; }
     if (finish_pass.load() != spp) { g_error = "finish_pass != num_sample"; return -1.0; }
+    if (rgba) memcpy(rgba, layer.rgba.data(), sizeof(float) * layer.rgba.size());
+    if (count) memcpy(count, layer.count.data(), sizeof(uint32_t) * layer.count.size());
+    return std::chrono::duration<double>(t1 - t0).count();
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1.0;
+  }
+}
+
+// Render() with the cancel flag raised from a second thread, as the GUI does (pc/glfw-window.cc:621-625): the flag goes
+// up once *finish_pass has reached `cancel_at_pass` (0: before the call).  A third thread watches finish_pass the way
+// the GUI's progress bar does.  out[0] = Render()'s return value, out[1] = final finish_pass, out[2] = 1 if
+// finish_pass was ever seen to decrease or to exceed num_sample, out[3] = passes finished when the flag was raised.
+// Returns seconds inside Render(), < 0 on an exception (which Render() must not throw).
+double pbrhost_render_cancel(void* s, uint32_t w, uint32_t h, uint32_t spp, uint64_t seed, uint32_t cancel_at_pass,
+                             float* rgba, uint32_t* count, uint64_t* out) {
+  try {
+    pbrlab::SetRenderSeed(seed);
+    std::atomic_bool cancel(cancel_at_pass == 0);
+    std::atomic_size_t finish_pass(0);
+    std::atomic_bool done(false), bad(false);
+    std::atomic_size_t raised_at(0);
+    pbrlab::RenderLayer layer;
+    std::thread gui([&]() {
+      size_t last = 0;
+      bool started = false;
+      while (!done.load()) {
+        const size_t p = finish_pass.load();
+        // Render() resets *finish_pass to 0 once, at its start (render.cc:213); after that it may only grow
+        if (p > spp || (started && p < last)) bad = true;
+        if (p > 0) started = true;
+        last = p;
+        if (!cancel.load() && p >= cancel_at_pass) { raised_at = p; cancel = true; }
+        std::this_thread::sleep_for(std::chrono::microseconds(200));
+      }
+    });
+    const auto t0 = std::chrono::steady_clock::now();
+    const bool ok = pbrlab::Render(*static_cast<pbrlab::Scene*>(s), w, h, spp, cancel, &layer, &finish_pass);
+    const auto t1 = std::chrono::steady_clock::now();
+    done = true;
+    gui.join();
+    out[0] = ok ? 1 : 0;
+    out[1] = finish_pass.load();
+    out[2] = bad.load() ? 1 : 0;
+    out[3] = raised_at.load();
     if (rgba) memcpy(rgba, layer.rgba.data(), sizeof(float) * layer.rgba.size());
     if (count) memcpy(count, layer.count.data(), sizeof(uint32_t) * layer.count.size());
     return std::chrono::duration<double>(t1 - t0).count();
@@ -130,6 +179,11 @@ int pbrhost_resolve_srgb8(void* s, uint32_t w, uint32_t h, uint8_t* rgba8) {
   const int rc = pbrgpu_resolve_srgb8(ctx, w, h, rgba8);
   if (rc != PBRGPU_OK) g_error = pbrgpu_last_error(ctx);
   return rc;
+}
+
+// io::WritePNG8 (the encoder behind the CLI's rgba.png): pixels are 8-bit, row-major, `channels` interleaved
+int pbrhost_write_png8(const char* path, const uint8_t* pixels, uint32_t w, uint32_t h, uint32_t channels) {
+  return pbrlab::io::WritePNG8(path, pixels, w, h, channels) ? 1 : 0;
 }
 
 // Scene::TraceFirstHit1 / AnyHit1 through the C++ API (single-ray entry points of the reference)

@@ -1,7 +1,9 @@
 #include "render.h"
 
 #include <chrono>
-#include <stdexcept>
+#include <cstdio>
+#include <exception>
+#include <mutex>
 #include <string>
 #include <thread>
 
@@ -13,14 +15,37 @@ static std::atomic<uint64_t> g_render_seed(1234567890ull);   // the reference's 
 void SetRenderSeed(uint64_t seed) { g_render_seed = seed; }
 uint64_t GetRenderSeed(void) { return g_render_seed.load(); }
 
+static std::mutex g_error_mutex;
+static std::string g_last_error;
+static void SetLastError(const std::string& msg) {
+  std::lock_guard<std::mutex> lock(g_error_mutex);
+  g_last_error = msg;
+}
+std::string LastRenderError(void) {
+  std::lock_guard<std::mutex> lock(g_error_mutex);
+  return g_last_error;
+}
+
 bool Render(const Scene& scene, const uint32_t width, const uint32_t height, const uint32_t num_sample,
             const std::atomic_bool& cancel_render_flag, RenderLayer* layer, std::atomic_size_t* finish_pass) {
-  pbrgpu_ctx* ctx = scene.DeviceContext();
-  if (!ctx) throw std::runtime_error("pbrlab::Render: scene was not committed to a device (CommitScene)");
+  // The reference's Render() never throws; a GUI render thread calls it in a loop.  Device failures
+  // are reported as `false` + LastRenderError() and leave a cleared layer.
   layer->Resize(width, height);   // PrepareRendering (src/render.cc:99-100)
   layer->Clear();
   *finish_pass = 0;
-  scene.SyncMaterialsToDevice();  // materials are live-editable between calls (pc/pbrlab-gui.cc:207-238)
+  pbrgpu_ctx* ctx = scene.DeviceContext();
+  if (!ctx) {
+    SetLastError("pbrlab::Render: scene was not committed to a device (CommitScene)");
+    fprintf(stderr, "%s\n", LastRenderError().c_str());
+    return false;
+  }
+  try {
+    scene.SyncMaterialsToDevice();  // materials are live-editable between calls (pc/pbrlab-gui.cc:207-238)
+  } catch (const std::exception& e) {   // e.g. an edit that makes a texture id invalid: report, do not unwind
+    SetLastError(std::string("pbrlab::Render: ") + e.what());
+    fprintf(stderr, "%s\n", LastRenderError().c_str());
+    return false;
+  }
 
   // The C ABI polls a plain int and reports progress through a plain size_t; a watcher mirrors the caller's atomics.
   volatile int cancel_int = cancel_render_flag.load() ? 1 : 0;
@@ -39,7 +64,12 @@ bool Render(const Scene& scene, const uint32_t width, const uint32_t height, con
   done = true;
   watcher.join();
   if (progress > finish_pass->load()) finish_pass->store(progress);
-  if (rc != PBRGPU_OK) throw std::runtime_error(std::string("pbrlab::Render: ") + pbrgpu_last_error(ctx));
+  if (rc != PBRGPU_OK) {
+    SetLastError(std::string("pbrlab::Render: ") + pbrgpu_last_error(ctx));
+    fprintf(stderr, "%s\n", LastRenderError().c_str());
+    layer->Clear();
+    return false;
+  }
   return true;
 }
 

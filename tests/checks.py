@@ -7,6 +7,12 @@ import common
 import pbrlab_b200 as pb
 
 REL = 1e-5   # north_star: BSDF eval/sample/pdf within 1e-5 relative given the same random numbers
+# Explicit outlier budgets (vectors of 4096) for the samplers of peaked lobes; everything else allows none.  The CPU
+# emulation (same libm as the reference) has 0 everywhere; on the GPU the counts come from CUDA's sqrtf / division /
+# sincosf differing from glibc in the last ulp of a direction that the lobe then amplifies.
+MAX_WEIGHT_OUTLIERS = 4        # f/pdf of a GGX / GTR1 sample outside 1e-5
+MAX_PEAKED_RAW_OUTLIERS = 4    # raw f or pdf of a lobe with alpha < 1e-2 outside 2e-2
+MAX_HAIR_OUTLIERS = 4          # hair sample: direction, f/pdf, raw f and pdf outside 1e-5
 
 
 def close(a, b, rel=REL, abs_=1e-7):
@@ -21,9 +27,30 @@ def frac_close(a, b, rel=REL, abs_=1e-7):
     return float(close(a, b, rel, abs_).mean())
 
 
+KAT_REPORT = {}   # outlier counts of the last check_kat run (the GPU test writes them to gpurun_out/)
+
+
+def outliers(a, b, rel=REL, abs_=1e-7):
+    """number of ROWS with a component outside the tolerance"""
+    ok = close(a, b, rel, abs_)
+    return int((~ok.reshape(len(ok), -1).all(axis=1)).sum())
+
+
+def weight(fp):
+    """f / pdf per row (the factor `throughput` is multiplied by, render.cc:80): f and pdf of a peaked lobe both carry
+    the lobe's 1/alpha^2, which amplifies the last ulp of the sampled direction; their quotient does not"""
+    fp = np.asarray(fp, np.float64)
+    with np.errstate(all="ignore"):
+        return np.where(fp[:, -1:] > 0, fp[:, :-1] / fp[:, -1:], 0.0)
+
+
 def check_kat(impl, g):
-    """closure-level known-answer vectors (tests/golden/kat_closures.npz)"""
+    """closure-level known-answer vectors (tests/golden/kat_closures.npz).  north_star: eval / sample / pdf within 1e-5
+    relative given the same random numbers.  Everything is held to 1e-5 with ZERO outliers except the two samplers of
+    peaked lobes, where the tolerance applies to the well-conditioned quantities (sampled direction, f/pdf) and the
+    raw f and pdf are additionally counted: the number of vectors outside 1e-5 is recorded in KAT_REPORT and bounded."""
     ev = impl.eval_closure
+    KAT_REPORT.clear()
     # PCG32: bit exact
     for (st, sq), want in zip(g["rng_seeds"], g["rng_draws"]):
         words = np.array([[int(st) & 0xffffffff, int(st) >> 32, int(sq) & 0xffffffff, int(sq) >> 32]], np.uint32)
@@ -47,11 +74,19 @@ def check_kat(impl, g):
         assert frac_close(e, g["ggx"][k][:, 0:2]) == 1.0, ("ggx eval", ax, ay, d)
         s = ev(7, [ax, ay, d], np.concatenate([wo, u], 1), 5)
         want = g["ggx"][k][:, 2:7]
-        # the sampled direction is compared tightly; f and pdf of a near-delta lobe amplify the last ulp of wi by
-        # 1/alpha^2, so they are compared on the cases where the reference's own value is well conditioned
-        assert frac_close(s[:, 0:3], want[:, 0:3], REL, 1e-6) == 1.0, ("ggx sample dir", ax, ay, d)
-        tol = REL if min(ax, ay) >= 1e-2 else 2e-2
-        assert frac_close(s[:, 3:5], want[:, 3:5], tol, 1e-7) >= 0.999, ("ggx sample f/pdf", ax, ay, d)
+        n_dir = outliers(s[:, 0:3], want[:, 0:3], REL, 1e-6)
+        n_w = outliers(weight(s[:, 3:5]), weight(want[:, 3:5]), REL, 1e-7)
+        n_raw = outliers(s[:, 3:5], want[:, 3:5], REL, 1e-7)
+        n_raw_loose = outliers(s[:, 3:5], want[:, 3:5], 2e-2, 1e-7)
+        KAT_REPORT["ggx_sample alpha=(%g,%g) distrib=%d" % (ax, ay, d)] = {
+            "vectors": len(s), "dir_outside_1e-5": n_dir, "f_over_pdf_outside_1e-5": n_w,
+            "raw_f_or_pdf_outside_1e-5": n_raw, "raw_f_or_pdf_outside_2e-2": n_raw_loose}
+        assert n_dir == 0, ("ggx sample dir", ax, ay, d, n_dir)
+        assert n_w <= MAX_WEIGHT_OUTLIERS, ("ggx sample f/pdf", ax, ay, d, n_w)
+        if min(ax, ay) >= 1e-2:
+            assert n_raw == 0, ("ggx sample f, pdf", ax, ay, d, n_raw)
+        else:   # lobes with 1/alpha^2 >= 1e4: raw values bounded at the amplified tolerance, outliers counted
+            assert n_raw_loose <= MAX_PEAKED_RAW_OUTLIERS, ("ggx sample raw f, pdf", ax, ay, d, n_raw_loose)
     for k, p in enumerate(common.PRINCIPLED_CASES):
         assert frac_close(ev(10, p, np.zeros((1, 1), np.float32), 36)[0][:34], g["principled_bsdf"][k][:34], 1e-6, 1e-9) == 1.0
         assert frac_close(ev(9, p, wo, 4), g["principled_w"][k]) == 1.0, ("principled weights", k)
@@ -62,7 +97,15 @@ def check_kat(impl, g):
         e = ev(11, p, np.concatenate([h[:, None], hwi, hwo], 1), 4)
         assert frac_close(e, g["hair_eval"][k], REL, 1e-9) >= 0.9999, ("hair eval", k)
         s = ev(12, p, np.concatenate([h[:, None], hwo, us], 1), 7)
-        assert frac_close(s, g["hair_sample"][k], REL, 1e-7) >= 0.999, ("hair sample", k)
+        want = g["hair_sample"][k]
+        n_dir = outliers(s[:, 0:3], want[:, 0:3], REL, 1e-6)
+        n_w = outliers(weight(s[:, 3:7]), weight(want[:, 3:7]), REL, 1e-7)
+        n_raw = outliers(s[:, 3:7], want[:, 3:7], REL, 1e-7)
+        KAT_REPORT["hair_sample case %d" % k] = {"vectors": len(s), "dir_outside_1e-5": n_dir,
+                                                 "f_over_pdf_outside_1e-5": n_w, "raw_f_or_pdf_outside_1e-5": n_raw}
+        assert n_dir <= MAX_HAIR_OUTLIERS, ("hair sample dir", k, n_dir)
+        assert n_w <= MAX_HAIR_OUTLIERS, ("hair sample f/pdf", k, n_w)
+        assert n_raw <= MAX_HAIR_OUTLIERS, ("hair sample f, pdf", k, n_raw)
     assert frac_close(ev(14, None, g["sss_in"], 9), g["sss_coeff"], REL, 1e-9) == 1.0
     assert frac_close(ev(15, None, g["sss_dist_in"], 4), g["sss_dist"], REL, 1e-9) == 1.0
 

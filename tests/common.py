@@ -91,3 +91,16 @@ def path_agreement(a, b, rel=1e-4, floor=1e-2):
     """fraction of per-path RGB radiances equal within rel * max(floor, |b|)"""
     err = np.abs(a - b).max(axis=1)
     return float((err <= rel * np.maximum(floor, np.abs(b).max(axis=1))).mean())
+
+
+def dump_report(name, obj):
+    """evidence for profiles/: written under gpurun_out/ when the tests run on the GPU box (scratch, merged back)"""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, name), "w") as f:
+            json.dump(obj, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

@@ -215,7 +215,35 @@ def textured():
          surface=surf, seeds=seeds, shade=shade, radiance=rad, **out)
 
 
+def output_stage():
+    """the CLI's output statements (pc/pbrlab-cli.cc:47-57 -> LinerToSrgb -> WritePNG) on a synthetic RenderLayer that
+    covers the sRGB knee, values above 1, zeros, negatives, a NaN and a 0-count pixel; the PNG the reference wrote is
+    decoded (PIL) and stored next to the inputs"""
+    import tempfile
+    from PIL import Image
+    r = np.random.default_rng(77)
+    h, w = 48, 64
+    count = np.full((h, w), 16, np.uint32)
+    mean = (10 ** r.uniform(-5, 0.3, (h, w, 4))).astype(np.float32)
+    mean[0, :, 0] = np.linspace(0.0030, 0.0033, w, dtype=np.float32)      # around the linear/power knee
+    mean[1, :, 1] = np.linspace(0.99, 1.01, w, dtype=np.float32)          # around the clamp
+    mean[2, :8, 2] = [0.0, -0.0, -0.5, np.nan, np.inf, 1e-30, 255.0 / 256.0, 1.0]
+    mean[..., 3] = 1.0
+    rgba = mean * np.float32(16.0)
+    count[3, 0] = 0                                                        # 0/0 -> NaN in every channel
+    rgba[3, 0] = 0.0
+    d = tempfile.mkdtemp()
+    with np.errstate(all="ignore"):
+        assert R.output_stage(rgba, count, d)
+    png = np.array(Image.open(os.path.join(d, "rgba.png")))
+    assert png.shape == (h, w, 4) and png.dtype == np.uint8
+    save("output_stage.npz", rgba=rgba, count=count, png=png)
+
+
 if __name__ == "__main__":
+    if "--output-stage-only" in sys.argv:
+        output_stage()
+        sys.exit(0)
     if "--image-more-only" in sys.argv:
         image_more()
         sys.exit(0)
@@ -226,5 +254,6 @@ if __name__ == "__main__":
     S = cornell()
     hair()
     textured()
+    output_stage()
     if "--image" in sys.argv:
         image(S)

@@ -141,6 +141,14 @@ class RefLib:
         return out
 
     # ---- loaders
+    def output_stage(self, rgba_sums, count, directory, name="rgba.png"):
+        """the reference CLI's output statements (pc/pbrlab-cli.cc:47-57) on a RenderLayer: writes directory/name"""
+        rgba_sums = np.ascontiguousarray(rgba_sums, np.float32); count = np.ascontiguousarray(count, np.uint32)
+        h, w = count.shape
+        ok = self.lib.ref_output_stage(_fp(rgba_sums), count.ctypes.data_as(C.c_void_p), C.c_uint32(w), C.c_uint32(h),
+                                       name.encode(), directory.encode())
+        return bool(ok)
+
     def obj_load(self, path):
         h = self.lib.ref_obj_load(path.encode())
         if not h:

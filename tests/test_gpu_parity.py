@@ -26,7 +26,10 @@ def test_native_library_is_the_one_running(cornell_gpu):
 
 def test_closure_known_answers(cornell_gpu):
     _, ctx = cornell_gpu
-    checks.check_kat(ctx, golden("kat_closures.npz"))
+    try:
+        checks.check_kat(ctx, golden("kat_closures.npz"))
+    finally:
+        common.dump_report("kat_outliers_gpu.json", checks.KAT_REPORT)
 
 
 def test_rays_vs_embree_golden(cornell_gpu):
@@ -57,15 +60,30 @@ def test_hair_scene(hair_gpu):
     rays = common.rays_from_f8(g["rays"])
     hits = ctx.trace(rays)
     ids = g["hit_ids"]; f = g["hit_f"]
-    same = (hits["instance_id"] == ids[:, 0]) & (hits["prim_id"] == ids[:, 2])
-    assert same.mean() >= 0.999
+    same = (hits["instance_id"] == ids[:, 0]) & (hits["geom_id"] == ids[:, 1]) & (hits["prim_id"] == ids[:, 2])
+    # the thresholds of the dense-hair gate below (north_star: >= 99.99 %, t within 1e-5 relative); this fixture is
+    # small (tests/golden/hair_scene.npz), so the 99.99 % is spelt as a count of rays
+    n_diff = int((~same).sum())
+    assert n_diff <= max(1, len(rays) // 10000), (n_diff, len(rays))
     curve = same & (ids[:, 0] == 9)
     assert curve.sum() > 3000
-    assert np.all(np.abs(hits["t"][curve] - f[curve, 0]) <= 2e-5 * np.abs(f[curve, 0]))
-    assert np.abs(hits["v"][curve] - f[curve, 2]).max() < 2e-3
-    assert (ctx.occluded(rays) == g["occluded"]).mean() >= 0.999
-    frac = common.path_agreement(ctx.radiance(rays, g["seeds"]), g["radiance"], rel=1e-3)
+    assert np.all(np.abs(hits["t"][curve] - f[curve, 0]) <= 1e-5 * np.abs(f[curve, 0]))
+    assert np.abs(hits["u"][curve] - f[curve, 1]).max() < 1e-3
+    # v = the hair BSDF's h: 2 * (distance from the ribbon's axis) / width - 1, a quotient of two differences of
+    # ray-space coordinates ~1e3 times larger than the ribbon is wide, so 1e-5 relative on t is ~1e-3 absolute on v
+    dv = np.abs(hits["v"][curve] - f[curve, 2])
+    assert dv.max() < 2e-3 and np.mean(dv > 2e-4) < 1e-3, (float(dv.max()), float(np.mean(dv > 2e-4)))
+    n_occ = int((ctx.occluded(rays) != g["occluded"]).sum())
+    assert n_occ <= max(1, len(rays) // 10000), n_occ
+    rad = ctx.radiance(rays, g["seeds"])
+    frac = common.path_agreement(rad, g["radiance"], rel=1e-4)
+    common.dump_report("hair_scene_gpu.json", {"rays": len(rays), "hit_mismatch": n_diff, "occlusion_mismatch": n_occ,
+                                               "max_dv": float(dv.max()), "paths_within_1e-4": frac})
+    # whole paths through hair: every bounce re-derives h from v, and the near-specular lobes (roughness 0.2) turn a
+    # 1e-4 change of h into a different sampled direction; paths that do not diverge agree to 1e-4, means agree
     assert frac >= 0.97, frac
+    ma, mb = rad.mean(axis=0), g["radiance"].mean(axis=0)
+    assert np.all(np.abs(ma - mb) <= 0.02 * np.maximum(mb, 1e-3)), (ma, mb)
 
 
 def test_dense_hair_rays_vs_live_embree(built, ref):
@@ -295,3 +313,149 @@ def test_curve_part_splits_report_the_same_hits(built, hair_file, monkeypatch):
         for k in ("t", "u", "v", "instance_id", "geom_id", "prim_id"):
             assert np.array_equal(h0[k], h[k]), k
         assert np.array_equal(o0, o)
+
+
+def test_cancel_mid_frame(cornell_gpu):
+    """Render() with the flag raised from a second thread mid-frame (reference src/render.cc:217-231,
+    pc/glfw-window.cc:621-625): returns true, every pixel holds whole samples only (rgba.a == count), finish_pass
+    rose monotonically and stayed <= num_sample, and the next Render() on the same scene is clean."""
+    scene, ctx = cornell_gpu
+    w = h = 512
+    spp = 4096
+    rgba, count, info = scene.render_cancelled(w, h, spp, cancel_at_pass=8, seed=5)
+    st = ctx.stats()
+    assert info["returned"] is True
+    assert not info["progress_violation"]
+    assert info["raised_at"] >= 8 and info["finish_pass"] >= info["raised_at"] and info["finish_pass"] <= spp
+    assert np.array_equal(rgba[..., 3], count.astype(np.float32))          # alpha and count incremented together
+    assert int(count.max()) <= spp and not np.isnan(rgba).any()
+    total = int(count.sum(dtype=np.uint64))
+    assert 0 < total < w * h * spp // 2, total                              # it really stopped early
+    assert total == st["paths"]                                            # everything accumulated is reported
+    assert info["finish_pass"] <= total // (w * h) + 1
+    # cancelled before the first batch: a cleared layer, finish_pass 0, still `true`
+    r0, c0, i0 = scene.render_cancelled(w, h, 64, cancel_at_pass=0, seed=5)
+    assert i0["returned"] is True and i0["finish_pass"] == 0 and not c0.any() and not r0.any()
+    # and the scene renders normally afterwards
+    r2, c2, _ = scene.render(w, h, 16, seed=5)
+    assert np.all(c2 == 16) and np.all(r2[..., 3] == 16.0) and not np.isnan(r2).any()
+    r1, c1 = ctx.render(w, h, 16, seed=5)
+    assert np.allclose(r1, r2, rtol=1e-4, atol=1e-4)                       # nothing of the cancelled frame leaked in
+    # the C ABI's own flag, raised before the call
+    import ctypes as C
+    flag = C.c_int(1)
+    r3, c3 = ctx.render(64, 64, 8, cancel=flag)
+    assert not c3.any() and not r3.any()
+
+
+def test_clearance_field_never_changes_a_walk(built, monkeypatch):
+    """PBRGPU_SSS_SKIP=0 traces every random-walk segment, =1 answers the segments the clearance field can vouch for
+    without a traversal.  On the GPU, one Shader() call per path through the single-vertex hook (the walk runs to its
+    end): exit position, direction, throughput, pdf are bit-identical; the NEE column only up to the order of its two
+    atomic additions."""
+    g = golden("cornell_paths.npz")
+    rays = common.rays_from_f8(g["rays"])
+    out = []
+    skipped = []
+    for skip in ("1", "0"):
+        monkeypatch.setenv("PBRGPU_SSS_SKIP", skip)
+        sc = pb.Scene([scenes.cornell()])
+        ctx = sc.context()
+        out.append(ctx.shade(rays, g["seeds"]))
+        st = ctx.stats()
+        skipped.append(st["sss_skipped"])
+        assert st["sss_rays"] + st["sss_skipped"] > 100_000
+        sc.close()
+    monkeypatch.delenv("PBRGPU_SSS_SKIP")
+    a, b = out
+    assert skipped[0] > 10_000 and skipped[1] == 0, skipped
+    exact = [0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14, 15]
+    assert np.array_equal(a[:, exact], b[:, exact])
+    assert np.allclose(a[:, 7:10], b[:, 7:10], rtol=1e-6, atol=1e-9)
+
+
+def test_hair_material_on_triangles_is_shaded(built):
+    """the C ABI allows a type-1 (hair) material on triangles and the reference's Shader() dispatches on the material
+    type, not the geometry (src/shader/shader.cc:8-34): in a scene WITHOUT curves those hits must still be shaded and
+    retired (they were parked in the hair queue for ever: count < spp)"""
+    import ctypes as C
+    ctx = pb.Context()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    v = np.array([[-1, 0, -1, 1], [1, 0, -1, 1], [1, 0, 1, 1], [-1, 0, 1, 1],
+                  [-1, 0, -1, 1], [1, 0, -1, 1], [1, 2, -1, 1], [-1, 2, -1, 1]], np.float32)
+    idx = np.array([0, 2, 1, 0, 3, 2, 4, 5, 6, 4, 6, 7], np.uint32)
+    mats = np.zeros((2, 28), np.uint32)
+    mats[0, 0] = 1; mats[0, 1:3] = 0xFFFFFFFF
+    mats[0, 4:24] = common.hair_params().view(np.uint32)
+    mats[1, 0] = 0; mats[1, 1:3] = 0xFFFFFFFF
+    mats[1, 4:27] = common.principled().view(np.uint32)
+    mid = np.array([0, 0, 1, 1], np.uint32); z = np.zeros(4, np.uint32); prim = np.arange(4, dtype=np.uint32)
+    assert ctx.lib.pbrgpu_set_materials(ctx.h, P(mats), 2) == 0
+    assert ctx.lib.pbrgpu_set_triangles(ctx.h, P(v), 8, P(idx), None, 0, None, None, 0, None, P(mid), P(z), P(z), P(prim), C.c_uint64(4)) == 0
+    assert ctx.lib.pbrgpu_commit(ctx.h, None, None) == 0
+    rgba, count = ctx.render(64, 64, 32)
+    assert np.all(count == 32) and np.all(rgba[..., 3] == 32.0)
+    st = ctx.stats()
+    assert st["paths"] == 64 * 64 * 32 and st["closest_rays"] > st["paths"]     # the hair vertices bounced on
+    ctx.close()
+
+
+def _big_gate(ctx, S, rng, n_cam, box_lo, box_hi, curve_instance=None):
+    """camera rays + secondary / short rays from what they hit + rays born inside the geometry's box, against the live
+    reference; returns (rays, agreement, t_ok, occlusion agreement, curve hits)"""
+    rays = common.camera_rays(S.camera(512, 512), n_cam, rng)
+    f, ids = S.trace(pb.rays_to_f8(rays))
+    hit = ids[:, 0] != 0xFFFFFFFF
+    P = rays["org"][hit] + f[hit, 0:1] * rays["dir"][hit]
+    inside = rng.uniform(box_lo, box_hi, (n_cam, 3)).astype(np.float32)
+    org = np.concatenate([P, inside]).astype(np.float32)
+    k = len(org)
+    tmax = np.where(rng.random(k) < 0.3, 10 ** rng.uniform(-3, 0.5, k), 1.844e18).astype(np.float32)
+    tmin = np.where(rng.random(k) < 0.5, 1e-3, 0.0).astype(np.float32)
+    rays2 = pb.make_rays(org, common.sphere_dirs(rng, k), tmin=tmin, tmax=tmax)
+    f2, ids2 = S.trace(pb.rays_to_f8(rays2))
+    R = np.concatenate([rays, rays2]); F = np.concatenate([f, f2]); I = np.concatenate([ids, ids2])
+    H = ctx.trace(R)
+    same = (H["instance_id"] == I[:, 0]) & (H["geom_id"] == I[:, 1]) & (H["prim_id"] == I[:, 2])
+    both = same & (I[:, 0] != 0xFFFFFFFF)
+    t_ok = bool(np.all(np.abs(H["t"][both] - F[both, 0]) <= 1e-5 * np.abs(F[both, 0])))
+    occ = float((ctx.occluded(rays2) == S.occluded(pb.rays_to_f8(rays2))).mean())
+    curves = int((both & (I[:, 0] == curve_instance)).sum()) if curve_instance is not None else 0
+    return len(R), float(same.mean()), int(both.sum()), t_ok, occ, curves
+
+
+@pytest.mark.parametrize("which", ["displaced_2m", "hair_1m_segments", "displaced_20m"])
+def test_ray_gate_at_scale(built, ref, which):
+    """north_star ray gate (>= 99.99 % hit / primID agreement, t within 1e-5 relative, occlusion flags) at the scale of
+    the large configurations, against the live compiled reference (Embree, src/scene.h:89-91):
+      displaced_2m      the C5 generator at 2 M triangles — the builder's chunked parallel passes and its stable
+                        partitions run on every range >= 2^18 primitives (bvh_builder.cc), 4 Mi rays
+      hair_1m_segments  the C3 CyHair file itself (50 000 strands x 20 segments) over the light stage, 4 Mi rays
+      displaced_20m     the C5 OBJ itself (19.9 M triangles); minutes of OBJ parsing on both sides, so it runs only with
+                        PBR_RUN_SLOW=1 (the log of the builder's run is under profiles/)"""
+    import os
+    if ref is None:
+        pytest.skip("oracle/_ref did not travel")
+    if which == "displaced_20m" and os.environ.get("PBR_RUN_SLOW", "0") != "1":
+        pytest.skip("set PBR_RUN_SLOW=1 (parses a 1.5 GB OBJ twice)")
+    rng = np.random.default_rng(2026)
+    if which == "hair_1m_segments":
+        files = [scenes.light_stage(), scenes.cyhair(50000, 21, center=(-2.5, 3.5, 0.0), radius=1.2, length=2.5, thickness=0.008)]
+        lo, hi, curve_inst = (-5.0, 0.5, -2.5), (0.0, 6.0, 2.5), 3
+    else:
+        files = [scenes.displaced(2_000_000 if which == "displaced_2m" else 20_000_000)]
+        lo, hi, curve_inst = (-9.0, 0.5, -9.0), (9.0, 17.0, 7.0), None
+    sc = pb.Scene(files)
+    ctx = sc.context()
+    S = ref.scene(files)
+    n, agree, hits, t_ok, occ, curves = _big_gate(ctx, S, rng, 1 << 21, lo, hi, curve_inst)
+    common.dump_report("ray_gate_%s.json" % which, {"rays": n, "agreement": agree, "hits_compared": hits,
+                                                    "t_within_1e-5": t_ok, "occlusion_agreement": occ,
+                                                    "curve_hits": curves})
+    assert n >= 4_000_000
+    assert agree >= 0.9999, agree
+    assert hits > 1_000_000 and t_ok
+    assert occ >= 0.9999, occ
+    if curve_inst is not None:
+        assert curves > 200_000, curves
+    sc.close()
