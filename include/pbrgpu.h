@@ -104,6 +104,8 @@ typedef struct pbrgpu_stats {
                               (max over the context's devices) */
   uint64_t trace_closest_launches;
   uint64_t sss_skipped;    /* random-walk segments answered by the clearance grid instead of a ray query */
+  uint64_t shade_vertices; /* path vertices shaded (Shader() calls incl. the exit vertex of a random walk) */
+  uint64_t iterations;     /* wavefront iterations (= launches of each kernel family) of the last render */
 } pbrgpu_stats;
 
 /* ---- life cycle.  device_ids == NULL / n_devices == 0: the current device only. */

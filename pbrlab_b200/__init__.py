@@ -42,7 +42,8 @@ class Stats(C.Structure):
                 ("sss_rays", C.c_uint64), ("kernel_launches", C.c_uint64), ("seconds", C.c_double),
                 ("trace_closest_ms", C.c_double), ("trace_any_ms", C.c_double), ("shade_ms", C.c_double),
                 ("sss_ms", C.c_double), ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
-                ("regen_ms", C.c_double), ("device_ms", C.c_double), ("trace_closest_launches", C.c_uint64), ("sss_skipped", C.c_uint64)]
+                ("regen_ms", C.c_double), ("device_ms", C.c_double), ("trace_closest_launches", C.c_uint64), ("sss_skipped", C.c_uint64),
+                ("shade_vertices", C.c_uint64), ("iterations", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

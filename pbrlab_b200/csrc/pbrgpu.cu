@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/pbrgpu.h"
+#include "job_split.h"
 #include "kat.cuh"
 #include "nccl_shim.h"
 #include "scene_host.h"
@@ -168,6 +169,7 @@ struct pbrgpu_ctx {
   int tune_trace_blocks = 8, tune_shade_blocks = 1, tune_walk_blocks = 6;   // resident 128-thread blocks per SM
   int tune_diffuse_threads = 128, tune_diffuse_blocks = 6;   // launch shape of the diffuse-only shading kernel (sweep: 128 x 6 beats 256 x 3 by 2 %)
   int tune_sort_materials = 1;     // diffuse-only Principled materials get their own shading queue and kernel
+  int tune_diffuse_pipe = 1;       // diffuse-only kernel with the cp.async slot-line pipeline (wavefront.cuh)
 };
 
 namespace {
@@ -365,7 +367,10 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, regen, sort);
     mark(2);
     pbr::ShadeSurfaceKernel<false><<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
-    if (sort) pbr::ShadeSurfaceKernel<true><<<grid_diffuse, ctx->tune_diffuse_threads, 0, st>>>(s, w, next, flags);
+    if (sort && ctx->tune_diffuse_pipe)
+      pbr::ShadeDiffusePipelinedKernel<<<grid_diffuse, ctx->tune_diffuse_threads,
+                                         size_t(2) * ctx->tune_diffuse_threads * pbr::kSlotStride * sizeof(float4), st>>>(s, w, next, flags);
+    else if (sort) pbr::ShadeSurfaceKernel<true><<<grid_diffuse, ctx->tune_diffuse_threads, 0, st>>>(s, w, next, flags);
     // hits are routed by material CLASS (a hair material on a triangle goes to q_hair as well, as the reference's
     // Shader() dispatches on the material type, shader.cc:8-34), so the kernel runs whenever that queue can fill
     const bool hair = s.num_curves != 0u || s.num_hair_materials != 0u;
@@ -439,7 +444,7 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   const uint64_t npix64 = uint64_t(width) * height;
   if (npix64 == 0 || npix64 > 0x7fffffffull) { SetError(ctx, "pbrgpu_render: bad image size"); return PBRGPU_ERR_INVALID; }
   const uint32_t npix = uint32_t(npix64);
-  const uint32_t local_spp = (spp > sample_offset) ? (spp - sample_offset + sample_stride - 1) / sample_stride : 0;
+  const uint32_t local_spp = pbrjob::CountOf(pbrjob::Share{sample_offset, sample_stride, true}, spp);
   CUDA_TRY(ctx, d.rgba.Alloc(npix));
   CUDA_TRY(ctx, d.count.Alloc(npix));
   d.frame_width = width; d.frame_height = height;
@@ -642,6 +647,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_pool_min_mi = std::min(64, std::max(1, env_int("PBRGPU_POOL_MIN_MI", ctx->tune_pool_min_mi)));
   ctx->tune_clear_march = std::min(64, std::max(1, env_int("PBRGPU_CLEAR_MARCH", ctx->tune_clear_march)));
   ctx->tune_sort_materials = env_int("PBRGPU_SORT_MATERIALS", ctx->tune_sort_materials);
+  ctx->tune_diffuse_pipe = env_int("PBRGPU_DIFFUSE_PIPE", ctx->tune_diffuse_pipe);
   ctx->tune_diffuse_blocks = std::max(1, env_int("PBRGPU_DIFFUSE_BLOCKS", ctx->tune_diffuse_blocks));
   ctx->tune_diffuse_threads = std::min(pbr::kDiffuseBlock, std::max(32, env_int("PBRGPU_DIFFUSE_THREADS", ctx->tune_diffuse_threads) & ~31));
   ctx->tune_shade_threads = std::min(pbr::kShadeBlock, std::max(32, env_int("PBRGPU_SHADE_THREADS", ctx->tune_shade_threads) & ~31));
@@ -672,6 +678,19 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
     if (can) {
       cudaSetDevice(ctx->devices[0].id);
       cudaDeviceEnablePeerAccess(ctx->devices[a].id, 0);
+      cudaGetLastError();
+    }
+  }
+  if (ctx->tune_diffuse_pipe) {
+    // the pipelined diffuse kernel stages two slot lines per thread in shared memory: ask for the carve-out that lets
+    // the intended number of blocks be resident (the default heuristic may keep a larger L1 and fewer blocks)
+    const size_t per_block = size_t(2) * ctx->tune_diffuse_threads * pbr::kSlotStride * sizeof(float4) + 1024;
+    const int pct = int(std::min<size_t>(100, (per_block * ctx->tune_diffuse_blocks * 100 + 228 * 1024 - 1) / (228 * 1024)));
+    for (const Device& d : ctx->devices) {
+      cudaSetDevice(d.id);
+      cudaFuncSetAttribute(pbr::ShadeDiffusePipelinedKernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(pbr::ShadeDiffusePipelinedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           int(per_block - 1024));
       cudaGetLastError();
     }
   }
@@ -897,22 +916,23 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
   // reference (render.cc:211-222) with the sample as the unit.  Every path keeps its own PCG32 stream
   // (seed + sample, pixel), so the image does not depend on the split (up to the order of the float sums).
   const uint32_t world = uint32_t(ctx->job_world), rank = uint32_t(ctx->job_rank);
-  const uint64_t stride64 = uint64_t(sample_stride) * world * ndev;
-  if (stride64 > 0xffffffffull) { ctx->error = "pbrgpu_render: sample stride overflow"; return PBRGPU_ERR_INVALID; }
-  const uint32_t my_offset = sample_offset + rank * sample_stride, my_stride = sample_stride * world;
+  std::vector<pbrjob::Share> shares(ndev);
+  for (uint32_t k = 0; k < ndev; ++k) {
+    shares[k] = pbrjob::ShareOf(sample_offset, sample_stride, rank, world, k, ndev);
+    if (!shares[k].ok) { ctx->error = "pbrgpu_render: sample stride overflow"; return PBRGPU_ERR_INVALID; }
+  }
   std::vector<LoopTimers> tms(ndev);
   std::vector<int> rcs(ndev, PBRGPU_OK);
   std::vector<size_t> progress(ndev, 0);
   if (ndev == 1) {
-    rcs[0] = RenderOnDevice(ctx, ctx->devices[0], width, height, spp, seed, my_offset, my_stride, cancel, finish_pass,
-                            &tms[0]);
+    rcs[0] = RenderOnDevice(ctx, ctx->devices[0], width, height, spp, seed, shares[0].offset, shares[0].stride, cancel,
+                            finish_pass, &tms[0]);
   } else {
-    // one host thread per device; device k renders samples my_offset + (k + j*ndev)*my_stride
-    std::vector<std::thread> th;
+    std::vector<std::thread> th;   // one host thread per device
     for (uint32_t k = 0; k < ndev; ++k) {
       th.emplace_back([&, k]() {
-        rcs[k] = RenderOnDevice(ctx, ctx->devices[k], width, height, spp, seed, my_offset + k * my_stride,
-                                my_stride * ndev, cancel, &progress[k], &tms[k]);
+        rcs[k] = RenderOnDevice(ctx, ctx->devices[k], width, height, spp, seed, shares[k].offset, shares[k].stride,
+                                cancel, &progress[k], &tms[k]);
       });
     }
     for (auto& t : th) t.join();
@@ -950,10 +970,12 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
       s.shadow_rays += d.h_stats[pbr::kStatShadow];
       s.sss_rays += d.h_stats[pbr::kStatSss];
       s.sss_skipped += d.h_stats[pbr::kStatSssSkipped];
+      s.shade_vertices += d.h_stats[pbr::kStatVertices];
       s.paths += d.h_stats[pbr::kStatRetired];   // camera samples this process accumulated (< its share after a cancel)
     }
     s.kernel_launches += tms[k].launches;
     s.trace_closest_launches += tms[k].closest_launches;
+    s.iterations = std::max<uint64_t>(s.iterations, tms[k].closest_launches);
     s.trace_closest_ms += tms[k].closest_ms; s.trace_any_ms += tms[k].any_ms; s.shade_ms += tms[k].shade_ms;
     s.sss_ms += tms[k].sss_ms; s.regen_ms += tms[k].regen_ms;
     s.device_ms = std::max(s.device_ms, tms[k].device_ms);

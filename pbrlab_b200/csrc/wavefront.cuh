@@ -65,6 +65,7 @@ enum Stat {
   kStatSampleBase,      // first camera sample id of the current iteration (set by BeginIterationKernel)
   kStatRetired,         // camera samples accumulated into the frame so far
   kStatSssSkipped,      // walk segments answered by the clearance grid
+  kStatVertices,        // path vertices shaded (surface + diffuse + hair + SSS exit kernels)
   kStatCount
 };
 
@@ -453,18 +454,25 @@ struct PathRegs {
   Pcg32 rng;
 };
 
-__device__ __forceinline__ PathRegs LoadPath(const WaveState& w, uint32_t p) {
+// the seven records of a slot line that a shading kernel reads (kHitPad is never read)
+__device__ __forceinline__ PathRegs PathFromRecords(const float4& o, const float4& d, const float4& t4, const float4& r4,
+                                                    const float4& h4, const float4& g4, const float4& x4) {
   PathRegs r;
-  r.ray = LoadRay(w, p);
-  r.hit = LoadHit(w, p);
-  const float4 t4 = LdSlot(w, p, kThr), r4 = LdSlot(w, p, kRad);
+  r.ray.o = vec3(o.x, o.y, o.z); r.ray.tmin = o.w;
+  r.ray.d = vec3(d.x, d.y, d.z); r.ray.tmax = d.w;
+  r.hit.t = h4.x; r.hit.u = h4.y; r.hit.v = h4.z; r.hit.prim = __float_as_uint(h4.w);
   r.throughput = vec3(t4.x, t4.y, t4.z);
   r.pdf_prev = t4.w;
   r.L = vec3(r4.x, r4.y, r4.z);
   r.depth = __float_as_uint(r4.w);
-  r.rng = LoadRng(w, p);
-  r.pixel = __float_as_uint(LdSlot(w, p, kPix).x);
+  r.rng.state = (uint64_t(__float_as_uint(g4.y)) << 32) | __float_as_uint(g4.x);
+  r.rng.inc = (uint64_t(__float_as_uint(g4.w)) << 32) | __float_as_uint(g4.z);
+  r.pixel = __float_as_uint(x4.x);
   return r;
+}
+__device__ __forceinline__ PathRegs LoadPath(const WaveState& w, uint32_t p) {
+  return PathFromRecords(LdSlot(w, p, kRayO), LdSlot(w, p, kRayD), LdSlot(w, p, kThr), LdSlot(w, p, kRad),
+                         LdSlot(w, p, kHit), LdSlot(w, p, kRng), LdSlot(w, p, kPix));
 }
 
 // after a vertex: sectors 0, 1 and 3 of the line are rewritten whole (render.cc:79-86)
@@ -510,80 +518,171 @@ __device__ __forceinline__ void ResumeWalk(const WaveState& w, uint32_t p, SssWa
 // Launch shapes: the general kernel needs ~110-128 registers, so one 512-thread block per SM; the diffuse-only kernel is
 // 7x smaller (2.1k vs 15.7k SASS instructions) and fits three 256-thread blocks per SM.
 constexpr int kDiffuseBlock = 256, kDiffuseBlocksPerSm = 3;
+// One Principled vertex (render.cc:33-86 + shader.cc:8-34) of path slot p whose state is in r; called by every lane of
+// a warp (lanes without an item pass valid = false): the queue appends are warp collectives.
+template <bool DIFFUSE_ONLY>
+__device__ __forceinline__ void ShadeSurfaceItem(const SceneView& s, const WaveState& w, uint32_t next_parity,
+                                                 const ShadeFlags& flags, bool valid, uint32_t p, PathRegs& r) {
+  bool to_sss = false, to_next = false, to_done = false;
+  ShadowRequest req;
+  req.active = false;
+  vec3 throughput(0.f);
+  if (valid) {
+    throughput = r.throughput;
+    vec3 L = r.L;
+    const Surface si = MakeSurface(s, r.ray, r.hit);
+    bool alive = true;
+    if (!flags.skip_emission_and_roulette)
+      alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &L, &throughput);
+    if (!alive) {
+      CommitEnd(w, p, L, r.depth);
+      to_done = true;
+    } else {
+      const int kind = DIFFUSE_ONLY ? 1 : MaterialKind(s, si);
+      VertexResult vr;
+      const vec3 wo = -r.ray.d;
+      Frame fr;
+      PrincipledBsdf bsdf;
+      bool sss = false;
+      if (kind == 1) sss = PrincipledVertexT<DIFFUSE_ONLY>(s, si, wo, &r.rng, &vr, &fr, &bsdf);
+      else AbsorbVertex(wo, si.P, &vr);   // no material (shader.cc:11-17)
+      req = vr.shadow[0];
+      if (!DIFFUSE_ONLY && sss) {
+        SssWalkState walk;
+        if (SssBegin(si, fr, bsdf, &r.rng, &walk)) {
+          // the walk runs in its own kernel: park it, and the path with the post-roulette throughput
+          ParkWalk(w, p, walk);
+          StSlot(w, p, kThr, make_float4(throughput.x, throughput.y, throughput.z, r.pdf_prev));
+          StSlot(w, p, kRad, make_float4(L.x, L.y, L.z, __uint_as_float(r.depth)));
+          StSlot(w, p, kRng, PackRng(r.rng));
+          StSlot(w, p, kPix, make_float4(__uint_as_float(r.pixel), 0.f, 0.f, 0.f));
+          to_sss = true;
+        } else {   // walk rejected: throughput 0, the path ends (cycles-principled-shader.cc:217-220)
+          CommitEnd(w, p, L, r.depth + 1u);
+          to_done = true;
+        }
+      } else {
+        CommitVertex(w, p, vr, throughput, L, r.depth, r.rng, r.pixel);
+        to_next = !IsBlack(vr.throughput * throughput);               // render.cc:31
+        to_done = !to_next;
+      }
+    }
+  }
+  PushShadow(w, req, throughput, p);
+  if (!DIFFUSE_ONLY) {
+    const uint32_t a = WarpAppend(&w.counters[kNumSss], to_sss);
+    if (to_sss) w.q_sss[a] = p;
+  }
+  RouteSlot(w, next_parity, p, to_next, to_done);
+}
+
 template <bool DIFFUSE_ONLY>
 __global__ void __launch_bounds__(DIFFUSE_ONLY ? kDiffuseBlock : kShadeBlock, DIFFUSE_ONLY ? kDiffuseBlocksPerSm : 1)
 ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t next_parity,
                                                           ShadeFlags flags) {
   const uint32_t n = w.counters[DIFFUSE_ONLY ? kNumDiffuse : kNumSurface];
   const uint32_t* __restrict__ queue = DIFFUSE_ONLY ? w.q_diffuse : w.q_surface;
+  uint32_t shaded = 0;
   for (;;) {
     const uint32_t slot = BlockFetch(&w.counters[DIFFUSE_ONLY ? kFetchDiffuse : kFetchSurface]);
     if (slot - threadIdx.x >= n) break;   // block-uniform
     const bool valid = slot < n;
+    shaded += valid ? 1u : 0u;
     uint32_t p = 0;
-    bool to_sss = false, to_next = false, to_done = false;
-    ShadowRequest req;
-    req.active = false;
-    vec3 throughput(0.f);
+    PathRegs r;
     if (valid) {
       p = queue[slot];
-      PathRegs r = LoadPath(w, p);
-      throughput = r.throughput;
-      vec3 L = r.L;
-      const Surface si = MakeSurface(s, r.ray, r.hit);
-      bool alive = true;
-      if (!flags.skip_emission_and_roulette)
-        alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &L, &throughput);
-      if (!alive) {
-        CommitEnd(w, p, L, r.depth);
-        to_done = true;
-      } else {
-        const int kind = DIFFUSE_ONLY ? 1 : MaterialKind(s, si);
-        VertexResult vr;
-        const vec3 wo = -r.ray.d;
-        Frame fr;
-        PrincipledBsdf bsdf;
-        bool sss = false;
-        if (kind == 1) sss = PrincipledVertexT<DIFFUSE_ONLY>(s, si, wo, &r.rng, &vr, &fr, &bsdf);
-        else AbsorbVertex(wo, si.P, &vr);   // no material (shader.cc:11-17)
-        req = vr.shadow[0];
-        if (!DIFFUSE_ONLY && sss) {
-          SssWalkState walk;
-          if (SssBegin(si, fr, bsdf, &r.rng, &walk)) {
-            // the walk runs in its own kernel: park it, and the path with the post-roulette throughput
-            ParkWalk(w, p, walk);
-            StSlot(w, p, kThr, make_float4(throughput.x, throughput.y, throughput.z, r.pdf_prev));
-            StSlot(w, p, kRad, make_float4(L.x, L.y, L.z, __uint_as_float(r.depth)));
-            StSlot(w, p, kRng, PackRng(r.rng));
-            StSlot(w, p, kPix, make_float4(__uint_as_float(r.pixel), 0.f, 0.f, 0.f));
-            to_sss = true;
-          } else {   // walk rejected: throughput 0, the path ends (cycles-principled-shader.cc:217-220)
-            CommitEnd(w, p, L, r.depth + 1u);
-            to_done = true;
-          }
-        } else {
-          CommitVertex(w, p, vr, throughput, L, r.depth, r.rng, r.pixel);
-          to_next = !IsBlack(vr.throughput * throughput);               // render.cc:31
-          to_done = !to_next;
-        }
-      }
+      r = LoadPath(w, p);
     }
-    PushShadow(w, req, throughput, p);
-    if (!DIFFUSE_ONLY) {
-      const uint32_t a = WarpAppend(&w.counters[kNumSss], to_sss);
-      if (to_sss) w.q_sss[a] = p;
-    }
-    RouteSlot(w, next_parity, p, to_next, to_done);
+    ShadeSurfaceItem<DIFFUSE_ONLY>(s, w, next_parity, flags, valid, p, r);
   }
+  WarpTally(&w.stats[kStatVertices], shaded);
+}
+
+// The diffuse-only vertex is short (2.1 k SASS instructions) and its kernel was bound by the latency of one dependent
+// chain per thread — work fetch (atomic) -> queue entry -> slot line (a random 128-byte line in HBM) -> primitive ->
+// normals -> material -> light tables — with 15 % of the issue slots busy and DRAM at 16 % (profiles/r1_final_ncu.md).
+// This version takes the first three links off the chain: a block reserves kPipeBatches batches with ONE atomic, reads
+// the queue entries (dense, coalesced) one batch ahead, and copies the slot line of batch b+1 into shared memory with
+// cp.async (L2 evict-first, no registers held) while batch b is shaded.  A thread reads back only the row it copied
+// itself, so the pipeline needs no block barrier.  Rows are swizzled by (record ^ row) so that the 128-bit shared
+// loads of a quarter warp fall into different banks.
+constexpr int kPipeBatches = 8;
+__device__ __forceinline__ void CpAsync16(void* smem_dst, const void* gmem_src, uint64_t policy) {
+  const uint32_t dst = uint32_t(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void CpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kDiffuseBlock, kDiffuseBlocksPerSm)
+ShadeDiffusePipelinedKernel(SceneView s, WaveState w, uint32_t next_parity, ShadeFlags flags) {
+  extern __shared__ float4 stage[];   // [2][blockDim.x][8 records]
+  __shared__ uint32_t s_base;
+  const uint32_t n = w.counters[kNumDiffuse];
+  const uint32_t* __restrict__ queue = w.q_diffuse;
+  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  float4* row0 = stage + size_t(tid) * 8;
+  float4* row1 = stage + size_t(nthr + tid) * 8;
+  const uint32_t sw = tid & 7u;
+  auto issue = [&](float4* row, uint32_t p) {
+    const float4* src = w.slot + size_t(p) * kSlotStride;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k)
+      if (k != uint32_t(kHitPad)) CpAsync16(row + (k ^ sw), src + k, policy);
+  };
+  uint32_t shaded = 0;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_base = atomicAdd(&w.counters[kFetchDiffuse], nthr * uint32_t(kPipeBatches));
+    __syncthreads();
+    const uint32_t base = s_base;
+    if (base >= n) break;   // block-uniform
+    uint32_t item = base + tid;
+    uint32_t p_cur = item < n ? queue[item] : kInvalid;
+    if (p_cur != kInvalid) issue(row0, p_cur);
+    CpAsyncCommit();
+    uint32_t p_next = (item + nthr < n) ? queue[item + nthr] : kInvalid;
+#pragma unroll 1
+    for (int b = 0; b < kPipeBatches; ++b) {
+      if (base + uint32_t(b) * nthr >= n) break;   // block-uniform: nothing left in this chunk
+      float4* cur = (b & 1) ? row1 : row0;
+      float4* nxt = (b & 1) ? row0 : row1;
+      uint32_t p_next2 = kInvalid;
+      if (b + 1 < kPipeBatches) {
+        if (p_next != kInvalid) issue(nxt, p_next);
+        const uint32_t item2 = base + uint32_t(b + 2) * nthr + tid;
+        if (b + 2 < kPipeBatches && item2 < n) p_next2 = queue[item2];
+      }
+      CpAsyncCommit();
+      CpAsyncWait<1>();   // everything but the group just committed has landed: batch b is in `cur`
+      const bool valid = p_cur != kInvalid;
+      shaded += valid ? 1u : 0u;
+      PathRegs r;
+      if (valid)
+        r = PathFromRecords(cur[kRayO ^ sw], cur[kRayD ^ sw], cur[kThr ^ sw], cur[kRad ^ sw], cur[kHit ^ sw],
+                            cur[kRng ^ sw], cur[kPix ^ sw]);
+      ShadeSurfaceItem<true>(s, w, next_parity, flags, valid, valid ? p_cur : 0u, r);
+      p_cur = p_next;
+      p_next = p_next2;
+    }
+    CpAsyncWait<0>();
+  }
+  WarpTally(&w.stats[kStatVertices], shaded);
 }
 
 __global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, WaveState w, uint32_t next_parity,
                                                        ShadeFlags flags) {
   const uint32_t n = w.counters[kNumHair];
+  uint32_t shaded = 0;
   for (;;) {
     const uint32_t slot = BlockFetch(&w.counters[kFetchHair]);
     if (slot - threadIdx.x >= n) break;   // block-uniform
     const bool valid = slot < n;
+    shaded += valid ? 1u : 0u;
     uint32_t p = 0;
     bool to_next = false, to_done = false;
     ShadowRequest req;
@@ -613,6 +712,7 @@ __global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, Wave
     PushShadow(w, req, throughput, p);
     RouteSlot(w, next_parity, p, to_next, to_done);
   }
+  WarpTally(&w.stats[kStatVertices], shaded);
 }
 
 // ------------------------------------------------------------------------------------------------ random-walk SSS
@@ -735,10 +835,12 @@ __global__ void __launch_bounds__(128, 5) SssWalkKernel(SceneView s, WaveState w
 // cycles-principled-shader.cc:187-216): same-instance / back-face acceptance, NEE at the exit point, diffuse bounce.
 __global__ void __launch_bounds__(kShadeBlock) SssExitKernel(SceneView s, WaveState w, uint32_t next_parity) {
   const uint32_t n = w.counters[kNumExit];
+  uint32_t shaded = 0;
   for (;;) {
     const uint32_t slot = BlockFetch(&w.counters[kFetchExit]);
     if (slot - threadIdx.x >= n) break;   // block-uniform
     const bool valid = slot < n;
+    shaded += valid ? 1u : 0u;
     uint32_t p = 0;
     bool to_next = false, to_done = false;
     ShadowRequest req;
@@ -770,6 +872,7 @@ __global__ void __launch_bounds__(kShadeBlock) SssExitKernel(SceneView s, WaveSt
     PushShadow(w, req, throughput, p);
     RouteSlot(w, next_parity, p, to_next, to_done);
   }
+  WarpTally(&w.stats[kStatVertices], shaded);
 }
 
 // ------------------------------------------------------------------------------------------------ shadow rays

@@ -126,6 +126,35 @@ def light_stage():
     return path
 
 
+def _append_rows(f, path, kind, data):
+    """rows of `v` / `vn` / `f` lines: formatted by the host library's threads when it is built (same text as
+    numpy.savetxt, 10x faster), else by savetxt"""
+    fmt = ["v %.6f %.6f %.6f", "vn %.5f %.5f %.5f", "f %d//%d %d//%d %d//%d"][kind]
+    lib = None
+    try:
+        import ctypes as C
+        so = os.path.join(_ROOT, "lib", "libpbrlab_host.so")
+        if os.path.exists(so):
+            C.CDLL(os.path.join(_ROOT, "lib", "libpbrgpu.so"), mode=C.RTLD_GLOBAL)
+            lib = C.CDLL(so)
+            lib.pbrhost_append_rows.restype = C.c_int
+    except OSError:
+        lib = None
+    if lib is None:
+        np.savetxt(f, data, fmt=fmt)
+        return
+    f.flush()
+    if kind == 2:
+        a = np.ascontiguousarray(data, np.int64)
+        ok = lib.pbrhost_append_rows(path.encode(), 2, None, a.ctypes.data_as(C.c_void_p), C.c_uint64(len(a)))
+    else:
+        a = np.ascontiguousarray(data, np.float64)
+        ok = lib.pbrhost_append_rows(path.encode(), kind, a.ctypes.data_as(C.c_void_p), None, C.c_uint64(len(a)))
+    if not ok:
+        raise RuntimeError("pbrhost_append_rows failed for " + path)
+    f.seek(0, os.SEEK_END)
+
+
 def write_displaced_obj(path, n_tris=20_000_000, seed=7, blobs=8):
     """C5: closed, displaced, tessellated surfaces (uv-spheres with smooth noise displacement and per-vertex normals)
     inside an open-front box with a `light...` quad; two materials: GGX (specular 1 / roughness 0.2) and SSS
@@ -179,8 +208,8 @@ def write_displaced_obj(path, n_tris=20_000_000, seed=7, blobs=8):
             N = np.where(nl > 1e-12, N / np.maximum(nl, 1e-12), d)
             N[0] = d[0]; N[-1] = d[-1]
             f.write("o blob%d\n" % b)
-            np.savetxt(f, P.reshape(-1, 3), fmt="v %.6f %.6f %.6f")
-            np.savetxt(f, N.reshape(-1, 3), fmt="vn %.5f %.5f %.5f")
+            _append_rows(f, path, 0, P.reshape(-1, 3))
+            _append_rows(f, path, 1, N.reshape(-1, 3))
             f.write("usemtl %s\n" % ("Sss" if b % 2 else "Ggx"))
             i = np.arange(nv)[:, None] * nu
             j = np.arange(nu)[None, :]
@@ -193,7 +222,7 @@ def write_displaced_obj(path, n_tris=20_000_000, seed=7, blobs=8):
             tri = tri[keep]
             v = tri + base
             n = tri + nbase
-            np.savetxt(f, np.stack([v[:, 0], n[:, 0], v[:, 1], n[:, 1], v[:, 2], n[:, 2]], 1), fmt="f %d//%d %d//%d %d//%d")
+            _append_rows(f, path, 2, np.stack([v[:, 0], n[:, 0], v[:, 1], n[:, 1], v[:, 2], n[:, 2]], 1))
             base += (nv + 1) * nu
             nbase += (nv + 1) * nu
     return path

@@ -119,6 +119,14 @@ class Emul:
                                    C.c_uint32(out_stride))
         return out
 
+    def job_share(self, rank, world, spp, job_offset=0, job_stride=1, device=0, num_devices=1):
+        """(offset, stride, count): the samples pbrgpu_render gives this worker (csrc/job_split.h)"""
+        out = np.zeros(3, np.uint32)
+        ok = self.lib.emul_job_share(C.c_uint32(job_offset), C.c_uint32(job_stride), C.c_uint32(rank), C.c_uint32(world),
+                                     C.c_uint32(device), C.c_uint32(num_devices), C.c_uint32(spp), _p(out))
+        assert ok
+        return int(out[0]), int(out[1]), int(out[2])
+
     def render(self, width, height, spp, seed=1234567890, sample_offset=0, sample_stride=1):
         rgba = np.zeros((height, width, 4), np.float32); count = np.zeros((height, width), np.uint32)
         c = np.zeros(3, np.uint64)

@@ -19,6 +19,7 @@ static std::atomic<uint64_t> g_curve_probe[2];
 
 #include "../../pbrlab_b200/csrc/kat.cuh"
 #include "../../pbrlab_b200/csrc/scene_host.h"
+#include "../../pbrlab_b200/csrc/job_split.h"
 
 using namespace pbr;  // NOLINT
 
@@ -247,6 +248,14 @@ int emul_eval_closure(int op, const float* params, const float* in, uint32_t in_
                       uint32_t out_stride) {
   for (uint64_t i = 0; i < n; ++i) KatEval(op, params, in + size_t(i) * in_stride, out + size_t(i) * out_stride, out_stride);
   return 0;
+}
+
+// the library's own job-split arithmetic (csrc/job_split.h, used by pbrgpu.cu: RenderImpl): out = {offset, stride, count}
+int emul_job_share(uint32_t job_offset, uint32_t job_stride, uint32_t rank, uint32_t world, uint32_t device,
+                   uint32_t num_devices, uint32_t spp, uint32_t* out3) {
+  const pbrjob::Share s = pbrjob::ShareOf(job_offset, job_stride, rank, world, device, num_devices);
+  out3[0] = s.offset; out3[1] = s.stride; out3[2] = pbrjob::CountOf(s, spp);
+  return s.ok ? 1 : 0;
 }
 
 // Render() on the host cores with the GPU's path numbering: path (pixel p, sample s) = pcg32_srandom(seed + s, p)

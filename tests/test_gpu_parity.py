@@ -246,9 +246,10 @@ def test_edge_cases(built):
 
 
 def test_multi_device_context_matches_one_device(built):
-    """SURVEY §8(e) inside the library: a context over two devices renders interleaved sample shares with the scene
-    replicated and sums the accumulators; per-path streams are keyed by (global sample, pixel), so the frame equals
-    the single-device frame up to the order of the float additions"""
+    """SURVEY §8(e) inside the library, one process: a context over two devices renders interleaved sample shares with
+    the scene replicated and sums the accumulators with one grouped ncclReduce (ncclCommInitAll); per-path streams are
+    keyed by (global sample, pixel), so the frame equals the single-device frame up to the order of the float
+    additions.  PBRGPU_NO_NCCL=1 takes the peer-copy fallback."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -259,6 +260,9 @@ def test_multi_device_context_matches_one_device(built):
     assert np.array_equal(ca, cb) and np.all(cb == 16)
     assert np.all(b[..., 3] == 16.0)
     assert np.allclose(a, b, rtol=1e-4, atol=1e-4), float(np.abs(a - b).max())
+    b3, cb3, _ = two.render(192, 160, 3, seed=99)                         # uneven shares: 2 + 1 samples
+    a3, ca3, _ = one.render(192, 160, 3, seed=99)
+    assert np.array_equal(ca3, cb3) and np.allclose(a3, b3, rtol=1e-4, atol=1e-4)
     one.close(); two.close()
 
 
@@ -459,3 +463,63 @@ def test_ray_gate_at_scale(built, ref, which):
     if curve_inst is not None:
         assert curves > 200_000, curves
     sc.close()
+
+
+JOB_WORKER = r"""
+import os, sys, time
+sys.path.insert(0, {root!r}); sys.path.insert(0, {here!r})
+import numpy as np
+import pbrlab_b200 as pb
+from pbrlab_b200 import scenes
+rank, world, idfile, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
+if rank == 0:
+    ident = pb.nccl_unique_id()
+    with open(idfile + ".tmp", "wb") as f: f.write(ident)
+    os.replace(idfile + ".tmp", idfile)
+else:
+    while not os.path.exists(idfile): time.sleep(0.05)
+    ident = open(idfile, "rb").read()
+sc = pb.Scene([scenes.cornell()], device_ids=[rank])
+ctx = sc.context()
+ctx.nccl_init(ident, rank, world)
+rgba, count = ctx.render(192, 160, 18, seed=99)          # collective: the library splits and reduces
+np.savez(out, rgba=rgba, count=count, paths=ctx.stats()["paths"])
+rgba2, count2 = ctx.render(192, 160, 5, seed=3)           # fewer samples than 2 * ranks leave uneven shares
+np.savez(out.replace(".npz", "_b.npz"), rgba=rgba2, count=count2)
+sc.close()
+"""
+
+
+def test_multi_process_job_matches_one_device(built, tmp_path):
+    """north_star / SURVEY §8(e): a frame partitioned over the GPUs of one box, one process per GPU, the accumulators
+    summed by ONE ncclReduce inside the library (pbrgpu_nccl_init + pbrgpu_render).  Rank 0's frame equals the
+    single-device frame up to the order of the float additions; the other ranks keep their partial sums."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    world = 2 if n < 4 else 4
+    here = os.path.dirname(os.path.abspath(__file__))
+    script = tmp_path / "job_worker.py"
+    script.write_text(JOB_WORKER.format(root=os.path.dirname(here), here=here))
+    idfile = str(tmp_path / "nccl_id")
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), idfile, str(tmp_path / ("r%d.npz" % r))],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
+    one = pb.Scene([scenes.cornell()], device_ids=[0])
+    a, ca, _ = one.render(192, 160, 18, seed=99)
+    r0 = np.load(tmp_path / "r0.npz")
+    assert np.array_equal(r0["count"], ca) and np.all(ca == 18)
+    assert np.allclose(r0["rgba"], a, rtol=1e-4, atol=1e-4), float(np.abs(r0["rgba"] - a).max())
+    shares = [int(np.load(tmp_path / ("r%d.npz" % r))["paths"]) for r in range(world)]
+    assert sum(shares) == 192 * 160 * 18 and max(shares) - min(shares) <= 192 * 160
+    r1 = np.load(tmp_path / "r1.npz")
+    assert np.all(r1["count"] == len(range(1, 18, world)))                 # a non-root rank keeps its own share
+    b, cb, _ = one.render(192, 160, 5, seed=3)
+    rb = np.load(tmp_path / "r0_b.npz")
+    assert np.array_equal(rb["count"], cb) and np.allclose(rb["rgba"], b, rtol=1e-4, atol=1e-4)
+    one.close()

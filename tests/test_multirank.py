@@ -1,7 +1,9 @@
-"""N > 1 host logic on CPU: two gloo ranks render interleaved sample shares (rank r of R: samples r, r+R, ...) with the
-g++ emulation of the device code and sum the accumulators with one reduce, exactly as bench.py does over NCCL.
-The sum must equal the single-process frame: per-path streams are keyed by (global sample, pixel), so the split
-does not change any path."""
+"""N > 1 host logic on CPU: two gloo ranks take the sample shares the library's own split arithmetic gives them
+(csrc/job_split.h, what pbrgpu_render does on a context joined to a job by pbrgpu_nccl_init), render them with the g++
+emulation of the device code and add the float4 sums with ONE reduce; count is derived from the alpha sum afterwards,
+exactly as the library does over NCCL.  The result must equal the single-process frame: per-path streams are keyed by
+(global sample, pixel), so the split does not change any path.  Also checked: the shares of every (ranks x devices)
+layout partition the samples, and the NCCL entry points of the library fail cleanly without a device."""
 import os
 import subprocess
 import sys
@@ -21,18 +23,19 @@ dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(s
 rank = dist.get_rank(); world = dist.get_world_size()
 S = pb.Scene([scenes.cornell()], commit_to_device=False)
 E = emulbind.Emul(S.flat())
-w, h, spp = 24, 24, 6
-rgba, count, _ = E.render(w, h, spp, seed=77, sample_offset=rank, sample_stride=world)
-t_rgba = torch.from_numpy(rgba.copy()); t_count = torch.from_numpy(count.astype(np.int64))
-dist.reduce(t_rgba, 0, op=dist.ReduceOp.SUM); dist.reduce(t_count, 0, op=dist.ReduceOp.SUM)
+w, h, spp = 24, 24, 7
+off, stride, mine = E.job_share(rank, world, spp)
+rgba, count, _ = E.render(w, h, spp, seed=77, sample_offset=off, sample_stride=stride)
+assert np.all(count == mine) and mine == (4 if rank == 0 else 3)
+t_rgba = torch.from_numpy(rgba.copy())
+dist.reduce(t_rgba, 0, op=dist.ReduceOp.SUM)            # the one reduce: 16 B per pixel
 if rank == 0:
     full, fcount, _ = E.render(w, h, spp, seed=77)
-    assert np.array_equal(t_count.numpy(), fcount.astype(np.int64)), "sample counts differ"
-    assert np.all(fcount == spp)
     a, b = t_rgba.numpy(), full
+    derived = a[..., 3].astype(np.uint32)                # FinishFrameKernel: count = alpha sum
+    assert np.array_equal(derived, fcount), "sample counts differ"
+    assert np.all(fcount == spp)
     assert np.allclose(a, b, rtol=1e-5, atol=1e-6), float(np.abs(a - b).max())
-    # each rank alone holds only its share
-    assert count.sum() == w * h * (spp // 2)
     print("MULTIRANK_OK")
 dist.barrier()
 dist.destroy_process_group()
@@ -48,3 +51,33 @@ def test_two_rank_sample_split_sums_to_the_full_frame(built, tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "MULTIRANK_OK" in outs[0]
+
+
+def test_shares_partition_the_samples(cornell_emul):
+    """every (ranks x devices-per-rank) layout deals each sample of the job to exactly one worker"""
+    E = cornell_emul
+    for spp, job_off, job_stride in [(1024, 0, 1), (7, 0, 1), (64, 3, 5), (5, 0, 1)]:
+        want = sorted(range(job_off, spp, job_stride))
+        for world, ndev in [(1, 1), (2, 1), (8, 1), (1, 2), (2, 4), (3, 3)]:
+            got = []
+            for r in range(world):
+                for d in range(ndev):
+                    off, stride, cnt = E.job_share(r, world, spp, job_off, job_stride, d, ndev)
+                    mine = list(range(off, spp, stride))
+                    assert len(mine) == cnt
+                    got += mine
+            assert sorted(got) == want, (spp, job_off, job_stride, world, ndev)
+
+
+def test_nccl_entry_points_without_a_device(built):
+    """the library loads without libnccl linked in; the job entry points validate their arguments and a unique id can
+    be made on a host without a GPU (ncclGetUniqueId needs none)"""
+    import ctypes as C
+    import pbrlab_b200 as pb
+    lib = pb.gpu_lib()
+    assert lib.pbrgpu_nccl_unique_id(None) != 0
+    ident = pb.nccl_unique_id()
+    assert len(ident) == 128 and any(ident)
+    assert lib.pbrgpu_nccl_init(None, (C.c_uint8 * 128)(), 0, 1) != 0        # no context
+    deps = subprocess.run(["ldd", pb.GPU_LIB], capture_output=True, text=True).stdout
+    assert "libnccl" not in deps                                             # reached through dlopen only
