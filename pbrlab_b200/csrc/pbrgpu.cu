@@ -91,8 +91,8 @@ struct Device {
   DevBuf<pbr::LightRec> lights;
   pbr::SceneView view;
   // wave
-  DevBuf<float4> slot, walk, sh_o, sh_d, sh_c;
-  DevBuf<uint32_t> q0, q1, q_surface, q_diffuse, q_hair, q_sss, q_exit, q_walk0, q_walk1, q_done0, q_done1, counters;
+  DevBuf<float4> state0, state1, walk0, walk1, exit_rec, done0, done1, sh_o, sh_d, sh_c;
+  DevBuf<uint32_t> q_surface, q_diffuse, q_hair, counters;
   DevBuf<unsigned long long> stats;
   pbr::WaveState wave;
   uint32_t wave_capacity = 0;
@@ -112,9 +112,9 @@ struct Device {
     emissive.Free(); lprim_info.Free(); texcoords.Free(); curve_prim.Free(); curve_sub.Free(); curve_cull.Free(); lprim_tri.Free(); tri_ids.Free();
     tri_nidx.Free(); tri_vidx.Free(); tri_tidx.Free(); curve_ids.Free(); materials.Free(); light_cdf.Free();
     lprim_cdf.Free(); lights.Free();
-    slot.Free(); walk.Free(); sh_o.Free(); sh_d.Free(); sh_c.Free();
-    q0.Free(); q1.Free(); q_surface.Free(); q_hair.Free(); q_sss.Free(); q_exit.Free(); counters.Free(); stats.Free();
-    q_walk0.Free(); q_walk1.Free(); q_done0.Free(); q_done1.Free();
+    state0.Free(); state1.Free(); walk0.Free(); walk1.Free(); exit_rec.Free(); done0.Free(); done1.Free();
+    sh_o.Free(); sh_d.Free(); sh_c.Free();
+    q_surface.Free(); q_hair.Free(); counters.Free(); stats.Free();
     rgba.Free(); count.Free(); peer_tmp.Free();
     if (h_counters) cudaFreeHost(h_counters);
     if (h_stats) cudaFreeHost(h_stats);
@@ -151,13 +151,6 @@ struct pbrgpu_ctx {
   uint32_t tune_ribbon_lanes = 8;  // lanes holding a curve candidate that trigger the (batched) ribbon test
   int tune_l2_persist = 0;         // persisting-L2 window over the traversal data
   int tune_walk_bounces = 16;   // bounces a walk gets per launch before it is parked (pool busy)
-  // Bounce budget while the pool drains: a launch of the walk kernel is given about this many bounce steps in total
-  // (Mi), i.e. budget = clamp(target / walks in flight, tune_walk_bounces, tune_walk_bounces_max).  With the pool full
-  // there are ~1 Mi walks in flight (budget 16); as the frame runs out of samples the walks that are left get longer
-  // slices instead of one 16-bounce slice per (ever shorter) iteration, so the tail of a frame is bounded by the
-  // longest walk, not by (longest walk / 16) host round trips.
-  int tune_walk_target_mi = 16;
-  int tune_walk_bounces_max = 2048;
   // path slots in flight = clamp(samples of the frame / tune_pool_div, tune_pool_min_mi, tune_pool_mi): a frame
   // that is only a few pool-fills long (strong scaling: 1/8 of the samples per GPU) spends a smaller share of its
   // time ramping up and draining with a smaller pool
@@ -165,11 +158,10 @@ struct pbrgpu_ctx {
   int tune_clear_march = 4;        // sphere-tracing steps of the clearance test along a walk segment
   int tune_sss_skip = 1;           // clearance grid: random-walk segments that provably hit nothing are not traced
   int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
-  int tune_pool_mi = 32;           // path slots kept in flight, in Mi (x 256 B of slot + walk lines): 8 -> 32 Mi is +5 % on C2 (fewer, longer launches)
+  int tune_pool_mi = 32;           // paths kept in flight, in Mi (x ~800 B of queue storage each): 8 -> 32 Mi is +5 % on C2 (fewer, longer launches)
   int tune_trace_blocks = 8, tune_shade_blocks = 1, tune_walk_blocks = 6;   // resident 128-thread blocks per SM
   int tune_diffuse_threads = 128, tune_diffuse_blocks = 6;   // launch shape of the diffuse-only shading kernel (sweep: 128 x 6 beats 256 x 3 by 2 %)
   int tune_sort_materials = 1;     // diffuse-only Principled materials get their own shading queue and kernel
-  int tune_diffuse_pipe = 1;       // diffuse-only kernel with the cp.async slot-line pipeline (wavefront.cuh)
 };
 
 namespace {
@@ -283,19 +275,24 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   return PBRGPU_OK;
 }
 
+// bytes of wave storage per path in flight: S[2] + W[2] + E + D[2] + three index queues + the shadow queue
+constexpr size_t kWaveBytesPerPath =
+    sizeof(float4) * (2 * pbr::kStateFields + 2 * pbr::kWalkFields + pbr::kExitFields + 2 + 3 * 2) + 3 * sizeof(uint32_t);
+
 int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
   CUDA_TRY(ctx, cudaSetDevice(d.id));
   if (capacity > d.wave_capacity) {
-    CUDA_TRY(ctx, d.slot.Alloc(size_t(capacity) * pbr::kSlotStride));
-    CUDA_TRY(ctx, d.walk.Alloc(size_t(capacity) * pbr::kWalkStride));
-    CUDA_TRY(ctx, d.q0.Alloc(capacity)); CUDA_TRY(ctx, d.q1.Alloc(capacity));
-    CUDA_TRY(ctx, d.q_surface.Alloc(capacity)); CUDA_TRY(ctx, d.q_hair.Alloc(capacity));
-    CUDA_TRY(ctx, d.q_diffuse.Alloc(capacity));
-    CUDA_TRY(ctx, d.q_sss.Alloc(capacity)); CUDA_TRY(ctx, d.q_exit.Alloc(capacity));
-    CUDA_TRY(ctx, d.q_walk0.Alloc(capacity)); CUDA_TRY(ctx, d.q_walk1.Alloc(capacity));
-    CUDA_TRY(ctx, d.q_done0.Alloc(capacity)); CUDA_TRY(ctx, d.q_done1.Alloc(capacity));
-    CUDA_TRY(ctx, d.sh_o.Alloc(size_t(2) * capacity)); CUDA_TRY(ctx, d.sh_d.Alloc(size_t(2) * capacity));
-    CUDA_TRY(ctx, d.sh_c.Alloc(size_t(2) * capacity));
+    // grow: release the old arrays first (the largest pool is tens of GB)
+    d.state0.Free(); d.state1.Free(); d.walk0.Free(); d.walk1.Free(); d.exit_rec.Free(); d.done0.Free(); d.done1.Free();
+    d.q_surface.Free(); d.q_hair.Free(); d.q_diffuse.Free(); d.sh_o.Free(); d.sh_d.Free(); d.sh_c.Free();
+    d.wave_capacity = 0;
+    const size_t cap = capacity;
+    CUDA_TRY(ctx, d.state0.Alloc(cap * pbr::kStateFields)); CUDA_TRY(ctx, d.state1.Alloc(cap * pbr::kStateFields));
+    CUDA_TRY(ctx, d.walk0.Alloc(cap * pbr::kWalkFields)); CUDA_TRY(ctx, d.walk1.Alloc(cap * pbr::kWalkFields));
+    CUDA_TRY(ctx, d.exit_rec.Alloc(cap * pbr::kExitFields));
+    CUDA_TRY(ctx, d.done0.Alloc(cap)); CUDA_TRY(ctx, d.done1.Alloc(cap));
+    CUDA_TRY(ctx, d.q_surface.Alloc(cap)); CUDA_TRY(ctx, d.q_hair.Alloc(cap)); CUDA_TRY(ctx, d.q_diffuse.Alloc(cap));
+    CUDA_TRY(ctx, d.sh_o.Alloc(2 * cap)); CUDA_TRY(ctx, d.sh_d.Alloc(2 * cap)); CUDA_TRY(ctx, d.sh_c.Alloc(2 * cap));
     d.wave_capacity = capacity;
   }
   CUDA_TRY(ctx, d.counters.Alloc(pbr::kCounterCount));
@@ -303,11 +300,11 @@ int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
   if (!d.h_counters) CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&d.h_counters), sizeof(uint32_t) * pbr::kCounterCount));
   if (!d.h_stats) CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&d.h_stats), sizeof(unsigned long long) * pbr::kStatCount));
   WaveState& w = d.wave;
-  w.slot = d.slot.ptr; w.walk = d.walk.ptr;
-  w.q_active[0] = d.q0.ptr; w.q_active[1] = d.q1.ptr; w.q_surface = d.q_surface.ptr;
-  w.q_diffuse = d.q_diffuse.ptr; w.q_hair = d.q_hair.ptr; w.q_sss = d.q_sss.ptr; w.q_exit = d.q_exit.ptr;
-  w.q_walk[0] = d.q_walk0.ptr; w.q_walk[1] = d.q_walk1.ptr;
-  w.q_done[0] = d.q_done0.ptr; w.q_done[1] = d.q_done1.ptr;
+  w.state[0] = d.state0.ptr; w.state[1] = d.state1.ptr;
+  w.walk[0] = d.walk0.ptr; w.walk[1] = d.walk1.ptr;
+  w.exit_rec = d.exit_rec.ptr;
+  w.done[0] = d.done0.ptr; w.done[1] = d.done1.ptr;
+  w.q_surface = d.q_surface.ptr; w.q_diffuse = d.q_diffuse.ptr; w.q_hair = d.q_hair.ptr;
   w.sh_o = d.sh_o.ptr; w.sh_d = d.sh_d.ptr; w.sh_c = d.sh_c.ptr;
   w.counters = d.counters.ptr; w.stats = d.stats.ptr; w.capacity = d.wave_capacity;
   return PBRGPU_OK;
@@ -318,12 +315,14 @@ struct LoopTimers {
   uint64_t launches = 0, closest_launches = 0;
 };
 
-// Runs iterations on the slot pool until nothing is in flight and (when regenerating) the frame has no samples left.
-// Entry state: counters/queues set up by ResetPoolKernel (frame) or InitPathsFromRaysKernel (hooks).
-// max_iterations == 1 is the single-vertex mode of pbrgpu_shade.
-int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t max_iterations, pbr::ShadeFlags flags,
-            LoopTimers* tm, const volatile int* cancel, size_t* finish_pass, size_t pass_offset, size_t pass_stride,
-            size_t pass_cap) {
+// Runs wavefront iterations until nothing is in flight and (in frame mode) the frame has no samples left.
+// Entry state: counters set up by ResetPoolKernel (frame) or InitPathsFromRaysKernel (hooks).  `rgba` receives the
+// retired paths (frame accumulator, or the hook's one-entry-per-path buffer).
+// max_iterations == 1 is the single-vertex mode of pbrgpu_shade: one full iteration, then the walks it started run to
+// their end (walk + exit + shadow kernels only); the results are left in S / D of both parities.
+int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* rgba, uint32_t max_in_flight,
+            uint32_t max_iterations, pbr::ShadeFlags flags, LoopTimers* tm, const volatile int* cancel, size_t* finish_pass, size_t pass_offset,
+            size_t pass_stride, size_t pass_cap) {
   cudaStream_t st = d.stream;
   const SceneView& s = d.view;
   const WaveState& w = d.wave;
@@ -333,58 +332,50 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
   const int grid_diffuse = PersistentGrid(d, ctx->tune_diffuse_blocks);
   const bool curves = s.num_curves != 0u;
   const uint32_t refill = curves ? ctx->tune_refill_curves : ctx->tune_refill;
+  const uint32_t refill_any = curves ? refill : ctx->tune_refill_any;
   pbr::FrameParams no_frame;
   memset(&no_frame, 0, sizeof(no_frame));
-  // state after the set-up kernel (host knows it): hooks start with n active slots, frames with N retired slots
-  bool have_active = (frame == nullptr), have_walk = false, have_done = (frame != nullptr);
-  uint64_t in_flight = ~0ull;   // slots that will trace or walk in the coming iteration (unknown before the first)
-  uint64_t walks = ~0ull;       // of those, random walks that resume in the coming iteration (new ones join them)
-  for (uint32_t it = 0; (have_active || have_walk || have_done) && it < max_iterations; ++it) {
+  const uint32_t regen = frame ? 1u : 0u;
+  const uint32_t sort = ctx->tune_sort_materials ? 1u : 0u;
+  const unsigned long long total = frame ? frame->total_samples : 0ull;
+  // hits are routed by material CLASS (a hair material on a triangle goes to q_hair as well, as the reference's
+  // Shader() dispatches on the material type, shader.cc:8-34), so the kernel runs whenever that queue can fill
+  const bool hair = s.num_curves != 0u || s.num_hair_materials != 0u;
+  const bool single = (max_iterations == 1u);
+  auto launch_walk = [&](uint32_t cur, uint32_t budget) {
+    if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, st>>>(s, w, cur, budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
+    else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, st>>>(s, w, cur, budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
+    pbr::SssExitKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, cur, flags);
+  };
+  auto launch_any = [&](uint32_t next) {
+    if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, next, refill_any, ctx->tune_prim_lanes);
+    else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, next, refill_any, ctx->tune_prim_lanes);
+  };
+  // state after the set-up kernel (host knows it): hooks start with n paths, frames with nothing but samples to start
+  bool have_active = (frame == nullptr), have_walk = false, samples_left = (frame != nullptr) && total > 0;
+  uint64_t in_flight = ~0ull;   // paths + walks that the coming iteration works on (unknown before the first)
+  for (uint32_t it = 0; (have_active || have_walk || samples_left) && it < max_iterations; ++it) {
     if (cancel && *cancel) break;
     const uint32_t next = parity ^ 1u;
-    // single-vertex mode lets the walk run to its end inside the one iteration
-    uint32_t walk_budget = uint32_t(ctx->tune_walk_bounces);
-    if (max_iterations == 1u) {
-      walk_budget = 0x7fffffffu;
-    } else if (ctx->tune_walk_target_mi > 0) {
-      // walks that resume + (an estimate of) the walks this iteration starts: while the pool is busy the estimate is
-      // irrelevant (budget = floor), while it drains the new walks are a fraction of the few paths still active
-      const uint64_t w_est = std::max<uint64_t>(walks == ~0ull ? ~0ull : walks + (in_flight - walks) / 8, 1);
-      const uint64_t b = (uint64_t(ctx->tune_walk_target_mi) << 20) / w_est;
-      walk_budget = uint32_t(std::min<uint64_t>(std::max<uint64_t>(b, uint64_t(ctx->tune_walk_bounces)), uint64_t(ctx->tune_walk_bounces_max)));
-    } else if (in_flight < kDrainThreshold) {
-      walk_budget = kSssBouncesDrain;
-    }
+    const uint32_t walk_budget = in_flight < kDrainThreshold ? kSssBouncesDrain : uint32_t(ctx->tune_walk_bounces);
     const bool prof = ctx->profile;
     auto mark = [&](int k) { if (prof) cudaEventRecord(d.kev[k], st); };
-    const uint32_t regen = frame ? 1u : 0u;
-    const uint32_t sort = ctx->tune_sort_materials ? 1u : 0u;
-    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, regen);
-    tm->launches += 1;
     mark(0);
+    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, regen, std::min(max_in_flight, w.capacity), total);
+    pbr::RetireKernel<<<grid_shade, 256, 0, st>>>(w, parity, rgba);
     mark(1);
-    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, regen, sort);
-    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, regen, sort);
+    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, rgba, sort);
+    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, rgba, sort);
     mark(2);
-    pbr::ShadeSurfaceKernel<false><<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
-    if (sort && ctx->tune_diffuse_pipe)
-      pbr::ShadeDiffusePipelinedKernel<<<grid_diffuse, ctx->tune_diffuse_threads,
-                                         size_t(2) * ctx->tune_diffuse_threads * pbr::kSlotStride * sizeof(float4), st>>>(s, w, next, flags);
-    else if (sort) pbr::ShadeSurfaceKernel<true><<<grid_diffuse, ctx->tune_diffuse_threads, 0, st>>>(s, w, next, flags);
-    // hits are routed by material CLASS (a hair material on a triangle goes to q_hair as well, as the reference's
-    // Shader() dispatches on the material type, shader.cc:8-34), so the kernel runs whenever that queue can fill
-    const bool hair = s.num_curves != 0u || s.num_hair_materials != 0u;
-    if (hair) pbr::ShadeHairKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next, flags);
+    pbr::ShadeSurfaceKernel<false><<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, parity, flags);
+    if (sort) pbr::ShadeSurfaceKernel<true><<<grid_diffuse, ctx->tune_diffuse_threads, 0, st>>>(s, w, parity, flags);
+    if (hair) pbr::ShadeHairKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, parity, flags);
     mark(3);
-    if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
-    else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, st>>>(s, w, parity, walk_budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
-    pbr::SssExitKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, next);
+    launch_walk(parity, walk_budget);
     mark(4);
-    const uint32_t refill_any = curves ? refill : ctx->tune_refill_any;
-    if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, refill_any, ctx->tune_prim_lanes);
-    else pbr::TraceAnyKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, refill_any, ctx->tune_prim_lanes);
+    launch_any(next);
     mark(5);
-    tm->launches += (hair ? 6 : 5) + (sort ? 1 : 0);
+    tm->launches += (hair ? 8 : 7) + (sort ? 1 : 0);
     tm->closest_launches += 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(d.h_counters, w.counters, sizeof(uint32_t) * pbr::kCounterCount,
                                   cudaMemcpyDeviceToHost, st));
@@ -398,17 +389,39 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, uint32_t 
     }
     have_active = d.h_counters[pbr::kNumActive0 + next] > 0;
     have_walk = d.h_counters[pbr::kNumWalk0 + next] > 0;
-    // retired slots only matter while they can be accumulated (frame mode); hooks read rad[] directly
-    have_done = frame && d.h_counters[pbr::kNumDone0 + next] > 0;
+    samples_left = frame && d.h_stats[pbr::kStatNextSample] < total;
     in_flight = uint64_t(d.h_counters[pbr::kNumActive0 + next]) + d.h_counters[pbr::kNumWalk0 + next];
-    walks = d.h_counters[pbr::kNumWalk0 + next];
-    if (frame && d.h_stats[pbr::kStatNextSample] < frame->total_samples) in_flight += d.h_counters[pbr::kNumDone0 + next];
+    if (samples_left) in_flight = ~0ull;
     if (frame && finish_pass) {
       const size_t passes = size_t(d.h_stats[pbr::kStatRetired] / frame->npix);
       const size_t global = std::min(pass_cap, pass_offset + passes * pass_stride);
       if (global > *finish_pass) *finish_pass = global;
     }
     parity = next;
+  }
+  if (single) {
+    // the walks the single vertex started: to their end, then their exit vertices and shadow rays.  The set-up kernel
+    // runs in any case: it clears the counters of the other parity, whose records are the paths BEFORE the vertex.
+    const uint32_t next = parity ^ 1u;
+    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, 0u, w.capacity, 0ull);
+    tm->launches += 1;
+    if (have_walk) {
+      launch_walk(parity, 0x7fffffffu);
+      launch_any(next);
+      tm->launches += 3;
+    }
+  } else if (!(cancel && *cancel)) {
+    // the paths that ended in the last iteration (a cancelled frame drops what is in flight instead)
+    pbr::RetireKernel<<<grid_shade, 256, 0, st>>>(w, parity, rgba);
+    tm->launches += 1;
+    if (frame && finish_pass) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(d.h_stats, w.stats, sizeof(unsigned long long) * pbr::kStatCount,
+                                    cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      const size_t passes = size_t(d.h_stats[pbr::kStatRetired] / frame->npix);
+      const size_t global = std::min(pass_cap, pass_offset + passes * pass_stride);
+      if (global > *finish_pass) *finish_pass = global;
+    }
   }
   CUDA_TRY(ctx, cudaGetLastError());
   return PBRGPU_OK;
@@ -458,11 +471,12 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   const uint64_t total = npix64 * local_spp;
   uint32_t n_slots = ChoosePoolSize(ctx, npix, total);
   if (n_slots > d.wave_capacity) {
-    // a pool of 32 Mi slots is 13 GB (slot + walk lines, queues, shadow queue: ~400 B per slot): never more than half
-    // of what the device has free, whatever else lives on it
+    // 32 Mi paths in flight are 27 GB of queue storage (kWaveBytesPerPath): never more than half of what the device
+    // has free (plus what the current pool would give back), whatever else lives on it
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t fit = std::max<uint64_t>(free_b / 2 / 400, 1u << 16);
+    const uint64_t avail = uint64_t(free_b) + uint64_t(d.wave_capacity) * kWaveBytesPerPath;
+    const uint64_t fit = std::max<uint64_t>(avail / 2 / kWaveBytesPerPath, 1u << 16);
     n_slots = uint32_t(std::min<uint64_t>(n_slots, std::max<uint64_t>(fit, d.wave_capacity)));
   }
   int rc = EnsureWave(ctx, d, n_slots);
@@ -484,11 +498,14 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   frame.rgba = d.rgba.ptr;
 
   CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
-  pbr::ResetPoolKernel<<<(std::max<uint32_t>(n_slots, 64) + 255) / 256, 256, 0, d.stream>>>(d.wave, n_slots);
+  pbr::ResetPoolKernel<<<1, 64, 0, d.stream>>>(d.wave);
   tm->launches++;
   pbr::ShadeFlags flags;
   flags.skip_emission_and_roulette = 0;
-  rc = RunPool(ctx, d, &frame, 0xffffffffu, flags, tm, cancel, finish_pass, sample_offset, sample_stride, spp);
+  // n_slots paths in flight for THIS frame (the allocation, whose size is the stride of the field arrays, may be
+  // larger from an earlier one)
+  rc = RunPool(ctx, d, &frame, d.rgba.ptr, n_slots, 0xffffffffu, flags, tm, cancel, finish_pass, sample_offset,
+               sample_stride, spp);
   if (rc != PBRGPU_OK) return rc;
   CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
@@ -540,14 +557,16 @@ __global__ void KatKernel(int op, const float* params, const float* in, uint32_t
   pbr::KatEval(op, params, in + i * in_stride, out + i * out_stride, out_stride);
 }
 
+// pbrgpu_shade reports the face direction and t of the first hit: path p = item p of S[0] after a closest-hit pass
+// over hit records preset to "miss" (the kernel writes a record only for a hit)
 __global__ void SurfaceFaceKernel(pbr::SceneView s, pbr::WaveState w, uint32_t n, float* face_t) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  const pbr::HitT hit = pbr::LoadHit(w, p);
   face_t[2 * p] = -1.f;
   face_t[2 * p + 1] = 0.f;
+  const pbr::HitT hit = pbr::LoadHit(w, 0u, p);
   if (hit.prim == pbr::kInvalid) return;
-  const pbr::RayT ray = pbr::LoadRay(w, p);
+  const pbr::RayT ray = pbr::LoadRay(w, 0u, p);
   const pbr::Surface si = pbr::MakeSurface(s, ray, hit);
   face_t[2 * p] = float(si.face);
   face_t[2 * p + 1] = hit.t;
@@ -641,13 +660,10 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_l2_persist = env_int("PBRGPU_L2_PERSIST", ctx->tune_l2_persist);
   ctx->tune_sss_skip = env_int("PBRGPU_SSS_SKIP", ctx->tune_sss_skip);
   ctx->tune_walk_bounces = std::min(8192, std::max(1, env_int("PBRGPU_WALK_BOUNCES", ctx->tune_walk_bounces)));
-  ctx->tune_walk_target_mi = std::min(4096, std::max(0, env_int("PBRGPU_WALK_TARGET_MI", ctx->tune_walk_target_mi)));
-  ctx->tune_walk_bounces_max = std::min(1 << 20, std::max(1, env_int("PBRGPU_WALK_BOUNCES_MAX", ctx->tune_walk_bounces_max)));
   ctx->tune_pool_div = std::max(1, env_int("PBRGPU_POOL_DIV", ctx->tune_pool_div));
   ctx->tune_pool_min_mi = std::min(64, std::max(1, env_int("PBRGPU_POOL_MIN_MI", ctx->tune_pool_min_mi)));
   ctx->tune_clear_march = std::min(64, std::max(1, env_int("PBRGPU_CLEAR_MARCH", ctx->tune_clear_march)));
   ctx->tune_sort_materials = env_int("PBRGPU_SORT_MATERIALS", ctx->tune_sort_materials);
-  ctx->tune_diffuse_pipe = env_int("PBRGPU_DIFFUSE_PIPE", ctx->tune_diffuse_pipe);
   ctx->tune_diffuse_blocks = std::max(1, env_int("PBRGPU_DIFFUSE_BLOCKS", ctx->tune_diffuse_blocks));
   ctx->tune_diffuse_threads = std::min(pbr::kDiffuseBlock, std::max(32, env_int("PBRGPU_DIFFUSE_THREADS", ctx->tune_diffuse_threads) & ~31));
   ctx->tune_shade_threads = std::min(pbr::kShadeBlock, std::max(32, env_int("PBRGPU_SHADE_THREADS", ctx->tune_shade_threads) & ~31));
@@ -678,19 +694,6 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
     if (can) {
       cudaSetDevice(ctx->devices[0].id);
       cudaDeviceEnablePeerAccess(ctx->devices[a].id, 0);
-      cudaGetLastError();
-    }
-  }
-  if (ctx->tune_diffuse_pipe) {
-    // the pipelined diffuse kernel stages two slot lines per thread in shared memory: ask for the carve-out that lets
-    // the intended number of blocks be resident (the default heuristic may keep a larger L1 and fewer blocks)
-    const size_t per_block = size_t(2) * ctx->tune_diffuse_threads * pbr::kSlotStride * sizeof(float4) + 1024;
-    const int pct = int(std::min<size_t>(100, (per_block * ctx->tune_diffuse_blocks * 100 + 228 * 1024 - 1) / (228 * 1024)));
-    for (const Device& d : ctx->devices) {
-      cudaSetDevice(d.id);
-      cudaFuncSetAttribute(pbr::ShadeDiffusePipelinedKernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-      cudaFuncSetAttribute(pbr::ShadeDiffusePipelinedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           int(per_block - 1024));
       cudaGetLastError();
     }
   }
@@ -1212,57 +1215,57 @@ static int PathHook(pbrgpu_ctx* ctx, const pbrgpu_ray* rays, const uint64_t* see
   pbr::InitPathsFromRaysKernel<<<(std::max(n32, 64u) + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);
   pbr::ShadeFlags flags;
   flags.skip_emission_and_roulette = (mode == 1) ? 1u : 0u;
+  // retired paths land in a one-entry-per-path accumulator (path i = "pixel" i)
+  DevBuf<float4> acc;
+  CUDA_TRY(ctx, acc.Alloc(n));
+  CUDA_TRY(ctx, cudaMemsetAsync(acc.ptr, 0, sizeof(float4) * n, d.stream));
   std::vector<float> face_t;
   if (mode == 1) {
     // the hook reports face direction and t of the first hit: run the closest-hit stage alone first
     DevBuf<float> dface;
     CUDA_TRY(ctx, dface.Alloc(2 * n));
-    pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters, d.wave.stats, 0u, 0u);
+    CUDA_TRY(ctx, cudaMemsetAsync(d.wave.state[0] + size_t(pbr::kHit) * d.wave.capacity, 0xff, sizeof(float4) * n, d.stream));
+    pbr::BeginIterationKernel<<<1, 32, 0, d.stream>>>(d.wave.counters, d.wave.stats, 0u, 0u, d.wave.capacity, 0ull);
     if (d.view.num_curves)
-      pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), 0u, 0u);
+      pbr::TraceClosestKernel<true><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), acc.ptr, 0u);
     else
-      pbr::TraceClosestKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), 0u, 0u);
+      pbr::TraceClosestKernel<false><<<PersistentGrid(d, ctx->tune_trace_blocks), kBlock, 0, d.stream>>>(d.view, d.wave, 0u, ctx->tune_refill, ctx->tune_prim_lanes, pbr::FrameParams(), acc.ptr, 0u);
     SurfaceFaceKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.view, d.wave, n32, dface.ptr);
     // restore the entry state for the real iteration below
     pbr::InitPathsFromRaysKernel<<<(std::max(n32, 64u) + 255) / 256, 256, 0, d.stream>>>(d.wave, reinterpret_cast<const float4*>(dr.ptr), ds.ptr, n32);
+    CUDA_TRY(ctx, cudaMemsetAsync(acc.ptr, 0, sizeof(float4) * n, d.stream));
     face_t.resize(2 * n);
     CUDA_TRY(ctx, cudaMemcpyAsync(face_t.data(), dface.ptr, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, d.stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
     dface.Free();
   }
-  rc = RunPool(ctx, d, nullptr, mode == 1 ? 1u : 0xffffffffu, flags, &tm, nullptr, nullptr, 0, 1, 0);
-  if (rc != PBRGPU_OK) { dr.Free(); ds.Free(); return rc; }
-  std::vector<float4> rad(n), thr, ro, rdv;
-  // one 16-byte record out of every 128-byte slot line
-  auto fetch_field = [&](std::vector<float4>& dst, int field) {
-    return cudaMemcpy2DAsync(dst.data(), sizeof(float4), d.slot.ptr + field, sizeof(float4) * pbr::kSlotStride,
-                             sizeof(float4), n, cudaMemcpyDeviceToHost, d.stream);
-  };
-  CUDA_TRY(ctx, fetch_field(rad, pbr::kRad));
-  if (mode == 1) {
-    thr.resize(n); ro.resize(n); rdv.resize(n);
-    CUDA_TRY(ctx, fetch_field(thr, pbr::kThr));
-    CUDA_TRY(ctx, fetch_field(ro, pbr::kRayO));
-    CUDA_TRY(ctx, fetch_field(rdv, pbr::kRayD));
-  }
-  CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  rc = RunPool(ctx, d, nullptr, acc.ptr, uint32_t(n), mode == 1 ? 1u : 0xffffffffu, flags, &tm, nullptr, nullptr, 0, 1, 0);
+  if (rc != PBRGPU_OK) { dr.Free(); ds.Free(); acc.Free(); return rc; }
   if (mode == 0) {
+    std::vector<float4> rad(n);
+    CUDA_TRY(ctx, cudaMemcpyAsync(rad.data(), acc.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
     for (uint64_t i = 0; i < n; ++i) { out[3 * i] = rad[i].x; out[3 * i + 1] = rad[i].y; out[3 * i + 2] = rad[i].z; }
   } else {
+    // every path sits in S / D of one of the two parities: scatter the records back to path order
+    DevBuf<float> dout;
+    CUDA_TRY(ctx, dout.Alloc(16 * n));
+    CUDA_TRY(ctx, cudaMemsetAsync(dout.ptr, 0, sizeof(float) * 16 * n, d.stream));
+    pbr::GatherVertexKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.wave, 0u, n32, dout.ptr);
+    pbr::GatherVertexKernel<<<(n32 + 255) / 256, 256, 0, d.stream>>>(d.wave, 1u, n32, dout.ptr);
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, dout.ptr, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+    CUDA_TRY(ctx, cudaGetLastError());
     for (uint64_t i = 0; i < n; ++i) {
       float* o = out + 16 * i;
-      for (int k = 0; k < 16; ++k) o[k] = 0.f;
-      if (face_t[2 * i] < 0.f) continue;
+      if (face_t[2 * i] < 0.f) { for (int k = 0; k < 16; ++k) o[k] = 0.f; continue; }
       o[0] = 1.f;
-      o[1] = rdv[i].x; o[2] = rdv[i].y; o[3] = rdv[i].z;
-      o[4] = thr[i].x; o[5] = thr[i].y; o[6] = thr[i].z;
-      o[7] = rad[i].x; o[8] = rad[i].y; o[9] = rad[i].z;
-      o[10] = thr[i].w;
-      o[11] = ro[i].x; o[12] = ro[i].y; o[13] = ro[i].z;
       o[14] = face_t[2 * i];
       o[15] = face_t[2 * i + 1];
     }
+    dout.Free();
   }
+  acc.Free();
   rc = FetchStats(ctx, d);
   memset(&ctx->stats, 0, sizeof(ctx->stats));
   ctx->stats.paths = n;

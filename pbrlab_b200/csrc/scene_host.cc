@@ -1,5 +1,6 @@
 // See scene_host.h.
 #include "scene_host.h"
+#include "bvh_ploc.h"
 
 #include "device/principled.cuh"
 
@@ -212,6 +213,33 @@ inline void BezierBasisQuarter(int i, float* b) {   // Embree BezierBasis::eval(
 }
 }  // namespace
 
+bool HostScene::BuildBvh(const pbrbvh::Aabb* boxes, uint32_t n, const pbrbvh::BuildParams& prm, pbrbvh::Bvh8* out,
+                         std::string* which) {
+  const char* mode_env = getenv("PBRGPU_BVH");
+  const std::string mode = mode_env ? mode_env : "auto";
+  uint32_t min_prims = 2u << 20;
+  if (const char* e = getenv("PBRGPU_BVH_DEVICE_MIN")) min_prims = uint32_t(std::max(1, atoi(e)));
+  uint32_t radius = 16;
+  if (const char* e = getenv("PBRGPU_PLOC_RADIUS")) radius = uint32_t(std::min(128, std::max(1, atoi(e))));
+  const bool ploc = mode == "ploc" || (mode == "auto" && n >= min_prims && device_builder != nullptr);
+  const char* err = nullptr;
+  bool ok;
+  if (ploc && device_builder) {
+    *which = "ploc-device";
+    ok = device_builder(device_builder_user, boxes, n, prm, radius, out, &err);
+    if (!ok && getenv("PBRGPU_VERBOSE_COMMIT")) fprintf(stderr, "commit: device builder failed (%s), host SAH builder takes over\n", err ? err : "?");
+    if (!ok) { *which = "sah"; ok = pbrbvh::BuildBvh8(boxes, n, prm, out, &err); }   // e.g. a tree too deep to encode
+  } else if (ploc) {
+    *which = "ploc-host";
+    ok = pbrploc::BuildBvh8PlocHost(boxes, n, prm, radius, out, &err);
+  } else {
+    *which = "sah";
+    ok = pbrbvh::BuildBvh8(boxes, n, prm, out, &err);
+  }
+  if (!ok) error = err ? err : "BVH build failed";
+  return ok;
+}
+
 bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
   const auto t0 = std::chrono::steady_clock::now();
   const uint32_t nt = num_tris(), nc = num_curves();
@@ -225,7 +253,7 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
   }
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   pbrbvh::BuildParams prm;
-  const char* err = nullptr;
+
 
   // ---- triangles: Embree's TriangleM stores v0, e1 = v0 - v1, e2 = v2 - v0 (kernels/geometry/triangle.h:40-41)
   tri_data.clear();
@@ -240,7 +268,8 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
       for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], bx.lo[k]); hi[k] = std::max(hi[k], bx.hi[k]); }
     }
     const auto tb0 = std::chrono::steady_clock::now();
-    if (!pbrbvh::BuildBvh8(boxes.data(), nt, prm, &tri_bvh, &err)) { error = err; return false; }
+    if (!BuildBvh(boxes.data(), nt, prm, &tri_bvh, &last_builder)) return false;
+    bvh_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count();
     if (getenv("PBRGPU_VERBOSE_COMMIT"))
       fprintf(stderr, "commit: triangle BVH (%u prims) %.3f s\n", nt, std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count());
     tri_data.resize(size_t(3) * nt);
@@ -319,7 +348,11 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
       for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], ebl[k] - pad); hi[k] = std::max(hi[k], ebh[k] + pad); }
     }
     const uint32_t nparts = nc * uint32_t(split);
-    if (!pbrbvh::BuildBvh8(boxes.data(), nparts, prm, &curve_bvh, &err)) { error = err; return false; }
+    {
+      std::string which;
+      if (!BuildBvh(boxes.data(), nparts, prm, &curve_bvh, &which)) return false;
+      if (!nt) last_builder = which;
+    }
     // segment storage ("slots") in order of first appearance in the leaves: neighbours in space are neighbours in memory
     std::vector<uint32_t> slot_of(nc, 0xffffffffu);
     curve_prim.reserve(nc);

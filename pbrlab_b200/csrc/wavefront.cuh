@@ -1,44 +1,36 @@
-// Wavefront path tracer kernels (sm_100a).
+// Wavefront path tracer kernels (sm_100a): STREAMING path state.
 //
-// Render() keeps a POOL of N path slots resident in HBM for the whole frame.  Slots are visited through index
-// queues, i.e. in random order, so a slot's state is ONE 128-byte line (eight 16-byte records) instead of eight
-// separate arrays: a random 16-byte access costs a full 32-byte sector (64 bytes at the DRAM), and measured on B200 the
-// one-array-per-field layout moved 1.3 kB of DRAM traffic per shaded vertex for 176 bytes of state
-// (profiles/r1a_summary.md).  The line is grouped into 32-byte sectors by WRITER, so that every store replaces whole
-// sectors and never forces a read-modify-write:
+// Render() keeps up to N paths in flight for the whole frame.  A path has no home: its state travels with it
+// through dense structure-of-arrays queues that every kernel reads and writes in (nearly) sequential order, as
+// north_star describes ("SoA ray/hit/path-state queues read with coalesced 128-bit loads and compacted with warp
+// ballot/prefix-sum").  Round 1 kept one 128-byte line per path SLOT and visited the slots through index queues, i.e.
+// in random order; measured on the B200 that design ran every kernel at the RANDOM-access throughput of HBM3e
+// (~1-1.5 TB/s: 7.2 GB per closest-hit launch, 4.4 GB per diffuse-shading launch at 13-15 % issue utilisation —
+// profiles/r1_final_ncu.md; 80-byte random gathers over 4 GB reach 0.94 TB/s, a seventh of the streaming figure),
+// and hiding the LATENCY of those lines with a cp.async pipeline changed nothing (profiles/r2a_*).  Now:
 //
-//   sector 0   ray_o (org.xyz, tmin)            ray_d (dir.xyz, tmax)              written by shade / regenerate
-//   sector 1   thr   (throughput.rgb, pdf)      rad   (radiance.rgb, depth)        written by shade / regenerate
-//   sector 2   hit   (t, u, v, leaf-order prim) pad                                written by trace_closest
-//   sector 3   rng   (PCG32 state, inc)         pix   (pixel, -, -, -)             written by shade / regenerate
+//   S[2]   path state, ping-pong by iteration parity, one array per field (ray_o, ray_d, thr, rad, hit, rng, pix):
+//          iteration `it` traces and shades the paths S[cur][0 .. n_active + n_new); shading APPENDS the paths that go
+//          on to S[next] (warp ballot + one atomic per warp), so S[next] is dense and in shading order
+//   W[2]   random walks (hot: the walk state + rng; cold: the entry vertex and the path state it will resume with),
+//          ping-pong: the walk kernel steps W[cur][0 .. n_walk) and appends the walks that are still inside the
+//          medium to W[next]; shading appends NEW walks to W[next] as well (they start one iteration later)
+//   E      exit records of the walks that left the medium this iteration (the cold part is read from W[cur])
+//   D[2]   (radiance, pixel) of the paths that ended this iteration; retired into the frame at the start of the next
+//   q_surface / q_diffuse / q_hair   positions in S[cur] of the paths whose closest hit has a material of that class:
+//          the only index queues left; closest-hit rays finish roughly in fetch order, so these positions are nearly
+//          ascending and the shading kernels' gathers walk S[cur] front to back
+//   shadow queue (ray, contribution, target) as three dense arrays; the target says where an unoccluded contribution
+//          is added: rad of S[next][j], D[next][j] or W[next][j] — all written by this iteration and stable until
+//          the next one consumes them
 //
-// A second line per slot (`walk`) holds a parked random walk or the exit record of a finished one; only slots
-// that are inside a subsurface walk ever touch it.  Slot state is read and written with streaming (evict-first)
-// cache hints so that the ~1-2 GB that stream through per iteration do not push the BVH (19 MB on the Cornell scene)
-// out of the 126 MB L2.
-//
-// Index queues (u32 slot ids) are compacted with warp ballots + one atomicAdd per warp:
-//
-//   q_active[2]  slots that need a closest-hit query (ping-pong between iterations)
-//   q_surface    hit a Principled material of the general class (or none): emission + roulette + Principled vertex
-//   q_diffuse    hit a Principled material that can only enable the Lambert closure (scene_host.cc: ClassifyMaterial):
-//                same vertex function with the other closures compiled out (material-sorted shading)
-//   q_hair       hit a hair material
-//   q_sss        the Principled vertex selected the random-walk closure this iteration (walk state already parked)
-//   q_walk[2]    random walks that used up their bounce budget and continue next iteration (ping-pong)
-//   q_exit       walks that left the medium this iteration: exit vertex still to be shaded
-//   q_done[2]    paths that ended this iteration; consumed at the start of the next one (ping-pong)
-//   shadow queue (ray, contribution, slot) as three dense arrays: NEE any-hit queries, written and read coalesced
-//
-// One iteration:
-//   begin -> regenerate -> trace_closest -> shade_surface, shade_hair -> sss_walk -> sss_exit -> trace_any
-// `regenerate` retires every slot of q_done (adds its radiance to its pixel: rgba += (L,1), the sums RenderLayer
-// holds) and immediately starts the next camera sample in the same slot, so the pool stays full until the frame runs
-// out of samples: long random walks and deep paths never leave the GPU idle, and the number of iterations is
-// (total rays) / N instead of (longest path).  Every kernel is persistent — a grid that is a fixed multiple of the SM
-// count, warps pulling work with an atomic counter — and reads its queue length from device memory, so nothing but
-// one small counter block crosses PCIe per iteration.  The three ray kernels run in the warp traversal engine
-// (device/trav_engine.cuh), which refills finished lanes while the rest of the warp keeps traversing.
+// One iteration:   begin -> retire D[cur] -> trace_closest (+ camera rays for the free capacity, misses retired in
+//                  place) -> shade_surface, shade_diffuse, shade_hair -> sss_walk -> sss_exit -> trace_any
+// Every kernel is persistent — a grid that is a fixed multiple of the SM count, warps pulling work with an atomic
+// counter — and reads its queue length from device memory, so nothing but one small counter block crosses PCIe per
+// iteration.  The three ray kernels run in the warp traversal engine (device/trav_engine.cuh), which refills finished
+// lanes while the rest of the warp keeps traversing.  The pool stays full until the frame runs out of samples: the
+// number of iterations is (total rays) / N instead of (longest path).
 //
 // Replaces the per-pixel loops of the reference (src/render.cc:24-90,125-190); the per-vertex functions and their
 // citations are in device/shade.cuh.
@@ -51,11 +43,12 @@
 namespace pbr {
 
 enum Counter {
-  kNumActive0 = 0, kNumActive1,   // length of q_active[parity]
-  kNumWalk0, kNumWalk1,           // length of q_walk[parity]
-  kNumDone0, kNumDone1,           // length of q_done[parity]
-  kNumSurface, kNumDiffuse, kNumHair, kNumSss, kNumExit, kNumShadow,
-  kFetchRegen, kFetchTrace, kFetchSurface, kFetchDiffuse, kFetchHair, kFetchSss, kFetchExit, kFetchShadow,
+  kNumActive0 = 0, kNumActive1,   // paths in S[parity]
+  kNumWalk0, kNumWalk1,           // walks in W[parity]
+  kNumDone0, kNumDone1,           // records in D[parity]
+  kNumNew,                        // camera samples started by this iteration's closest-hit kernel
+  kNumSurface, kNumDiffuse, kNumHair, kNumExit, kNumShadow,
+  kFetchRetire, kFetchTrace, kFetchSurface, kFetchDiffuse, kFetchHair, kFetchWalk, kFetchExit, kFetchShadow,
   kCounterCount
 };
 // 64-bit counters that live for a whole frame
@@ -69,21 +62,26 @@ enum Stat {
   kStatCount
 };
 
-// records of a slot line / walk line (units of float4)
-enum SlotField { kRayO = 0, kRayD = 1, kThr = 2, kRad = 3, kHit = 4, kHitPad = 5, kRng = 6, kPix = 7, kSlotStride = 8 };
-enum WalkField { kWalkA = 0, kWalkB = 1, kWalkC = 2, kWalkD = 3, kWalkN = 4, kWalkStride = 8 };
+// fields of the three record streams (one float4 array of `capacity` entries per field)
+enum StateField { kRayO = 0, kRayD, kThr, kRad, kHit, kRng, kPix, kStateFields };
+enum WalkField {
+  kWalkA = 0, kWalkB, kWalkC, kWalkD, kWalkN, kWalkRng,                 // hot: stepped by the walk kernel
+  kWalkRayO, kWalkRayD, kWalkHit, kWalkThr, kWalkRad,                   // cold: entry vertex + the path it resumes
+  kWalkFields
+};
+enum ExitField { kExHit = 0, kExThr, kExO, kExD, kExRng, kExitFields };
+
+// where an unoccluded NEE contribution is added (ShadowRequest target): tag << 30 | position
+constexpr uint32_t kTargetState = 0u, kTargetDone = 1u, kTargetWalk = 2u, kTargetNone = 3u;
 
 struct WaveState {
-  float4* slot;                  // kSlotStride x float4 per path slot
-  float4* walk;                  // kWalkStride x float4 per path slot
-  uint32_t* q_active[2];
-  uint32_t* q_walk[2];
-  uint32_t* q_done[2];
+  float4* state[2];              // kStateFields x capacity
+  float4* walk[2];               // kWalkFields x capacity
+  float4* exit_rec;              // kExitFields x capacity
+  float4* done[2];               // capacity: (radiance rgb, pixel)
   uint32_t* q_surface;
   uint32_t* q_diffuse;
   uint32_t* q_hair;
-  uint32_t* q_sss;
-  uint32_t* q_exit;
   float4* sh_o;
   float4* sh_d;
   float4* sh_c;
@@ -95,18 +93,29 @@ struct WaveState {
 constexpr uint32_t kNoPixel = 0xFFFFFFFFu;
 constexpr int kShadeBlock = 512;   // most threads per block of the shading kernels (block-synchronous batches)
 
-// ---- streaming access to slot state (ld/st.global.cs: evict-first in L2)
-__device__ __forceinline__ float4 LdSlot(const WaveState& w, uint32_t p, int field) {
-  return __ldcs(&w.slot[size_t(p) * kSlotStride + field]);
+// ---- streaming access to path records (ld/st.global.cs: evict-first in L2, the BVH stays resident)
+// (the ping-pong halves are picked with a select, not an index: indexing a kernel-parameter array with a run-time value
+// makes the compiler copy the struct to local memory)
+__device__ __forceinline__ float4* StateBuf(const WaveState& w, uint32_t parity) { return parity ? w.state[1] : w.state[0]; }
+__device__ __forceinline__ float4* WalkBuf(const WaveState& w, uint32_t parity) { return parity ? w.walk[1] : w.walk[0]; }
+__device__ __forceinline__ float4* DoneBuf(const WaveState& w, uint32_t parity) { return parity ? w.done[1] : w.done[0]; }
+__device__ __forceinline__ float4 LdS(const WaveState& w, uint32_t parity, uint32_t i, int field) {
+  return __ldcs(&StateBuf(w, parity)[size_t(field) * w.capacity + i]);
 }
-__device__ __forceinline__ void StSlot(const WaveState& w, uint32_t p, int field, const float4& v) {
-  __stcs(&w.slot[size_t(p) * kSlotStride + field], v);
+__device__ __forceinline__ void StS(const WaveState& w, uint32_t parity, uint32_t i, int field, const float4& v) {
+  __stcs(&StateBuf(w, parity)[size_t(field) * w.capacity + i], v);
 }
-__device__ __forceinline__ float4 LdWalk(const WaveState& w, uint32_t p, int field) {
-  return __ldcs(&w.walk[size_t(p) * kWalkStride + field]);
+__device__ __forceinline__ float4 LdW(const WaveState& w, uint32_t parity, uint32_t i, int field) {
+  return __ldcs(&WalkBuf(w, parity)[size_t(field) * w.capacity + i]);
 }
-__device__ __forceinline__ void StWalk(const WaveState& w, uint32_t p, int field, const float4& v) {
-  __stcs(&w.walk[size_t(p) * kWalkStride + field], v);
+__device__ __forceinline__ void StW(const WaveState& w, uint32_t parity, uint32_t i, int field, const float4& v) {
+  __stcs(&WalkBuf(w, parity)[size_t(field) * w.capacity + i], v);
+}
+__device__ __forceinline__ float4 LdE(const WaveState& w, uint32_t i, int field) {
+  return __ldcs(&w.exit_rec[size_t(field) * w.capacity + i]);
+}
+__device__ __forceinline__ void StE(const WaveState& w, uint32_t i, int field, const float4& v) {
+  __stcs(&w.exit_rec[size_t(field) * w.capacity + i], v);
 }
 
 // ---- warp-aggregated queue append: one atomicAdd per warp.  Must be reached by all 32 lanes.
@@ -121,19 +130,10 @@ __device__ __forceinline__ uint32_t WarpAppend(uint32_t* counter, bool pred) {
   return base + uint32_t(__popc(mask & ((1u << lane) - 1u)));
 }
 
-// a warp pulls the next 32 queue slots; returns this lane's slot (>= n when the queue is exhausted)
-__device__ __forceinline__ uint32_t WarpFetch(uint32_t* fetch_counter) {
-  const int lane = threadIdx.x & 31;
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(fetch_counter, 32u);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  return base + uint32_t(lane);
-}
-
 // Five queue reservations with ONE atomic instruction: lanes 0..4 each reserve the range of one queue (different
 // addresses, so the L2 handles them in parallel) instead of five dependent atomic round trips — waiting for atomic
 // results was 18 % of the closest-hit kernel's stall samples (profiles/r1e_ncu.md).  Issue early, resolve late:
-// whatever is issued in between overlaps the round trip.
+// whatever is issued in between overlaps the round trip.  A null counter is a queue that is not used.
 struct Append5 {
   unsigned m[5];
   uint32_t base;   // lane k < 5: first index reserved in queue k
@@ -141,10 +141,10 @@ struct Append5 {
 __device__ __forceinline__ Append5 Append5Issue(uint32_t* c0, uint32_t* c1, uint32_t* c2, uint32_t* c3, uint32_t* c4,
                                                 bool p0, bool p1, bool p2, bool p3, bool p4) {
   Append5 a;
-  a.m[0] = __ballot_sync(0xffffffffu, p0);
-  a.m[1] = __ballot_sync(0xffffffffu, p1);
-  a.m[2] = __ballot_sync(0xffffffffu, p2);
-  a.m[3] = __ballot_sync(0xffffffffu, p3);
+  a.m[0] = c0 ? __ballot_sync(0xffffffffu, p0) : 0u;
+  a.m[1] = c1 ? __ballot_sync(0xffffffffu, p1) : 0u;
+  a.m[2] = c2 ? __ballot_sync(0xffffffffu, p2) : 0u;
+  a.m[3] = c3 ? __ballot_sync(0xffffffffu, p3) : 0u;
   a.m[4] = c4 ? __ballot_sync(0xffffffffu, p4) : 0u;
   a.base = 0;
   const int lane = threadIdx.x & 31;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void WarpTally(unsigned long long* counter, uint32_t 
   if ((threadIdx.x & 31) == 0 && sum) atomicAdd(counter, (unsigned long long)sum);
 }
 
-// A whole block pulls the next blockDim.x queue slots and re-converges: the shading kernels are long straight-line
+// A whole block pulls the next blockDim.x queue entries and re-converges: the shading kernels are long straight-line
 // code (70-120 KB of SASS, every instruction executed once per path), so warps that drift apart each stream the
 // code from L2 on their own — measured 67 % of warp time waiting on instruction fetch.  Warps that start every batch
 // together share the fetched lines.
@@ -177,21 +177,21 @@ __device__ __forceinline__ uint32_t BlockFetch(uint32_t* fetch_counter) {
   return s_base + threadIdx.x;
 }
 
-__device__ __forceinline__ RayT LoadRay(const WaveState& w, uint32_t p) {
-  const float4 o = LdSlot(w, p, kRayO), d = LdSlot(w, p, kRayD);
+__device__ __forceinline__ RayT RayFrom(const float4& o, const float4& d) {
   RayT r;
   r.o = vec3(o.x, o.y, o.z); r.tmin = o.w;
   r.d = vec3(d.x, d.y, d.z); r.tmax = d.w;
   return r;
 }
-__device__ __forceinline__ HitT LoadHit(const WaveState& w, uint32_t p) {
-  const float4 h4 = LdSlot(w, p, kHit);
+__device__ __forceinline__ HitT HitFrom(const float4& h4) {
   HitT hit;
   hit.t = h4.x; hit.u = h4.y; hit.v = h4.z; hit.prim = __float_as_uint(h4.w);
   return hit;
 }
-__device__ __forceinline__ Pcg32 LoadRng(const WaveState& w, uint32_t p) {
-  const float4 r = LdSlot(w, p, kRng);
+__device__ __forceinline__ float4 PackHit(const HitT& hit) {
+  return make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim));
+}
+__device__ __forceinline__ Pcg32 RngFrom(const float4& r) {
   Pcg32 rng;
   rng.state = (uint64_t(__float_as_uint(r.y)) << 32) | __float_as_uint(r.x);
   rng.inc = (uint64_t(__float_as_uint(r.w)) << 32) | __float_as_uint(r.z);
@@ -201,43 +201,69 @@ __device__ __forceinline__ float4 PackRng(const Pcg32& rng) {
   return make_float4(__uint_as_float(uint32_t(rng.state)), __uint_as_float(uint32_t(rng.state >> 32)),
                      __uint_as_float(uint32_t(rng.inc)), __uint_as_float(uint32_t(rng.inc >> 32)));
 }
+__device__ __forceinline__ RayT LoadRay(const WaveState& w, uint32_t parity, uint32_t i) {
+  return RayFrom(LdS(w, parity, i, kRayO), LdS(w, parity, i, kRayD));
+}
+__device__ __forceinline__ HitT LoadHit(const WaveState& w, uint32_t parity, uint32_t i) {
+  return HitFrom(LdS(w, parity, i, kHit));
+}
 
+__device__ __forceinline__ uint32_t MakeTarget(uint32_t tag, uint32_t index) { return (tag << 30) | index; }
+
+// NEE request of a vertex: the any-hit kernel adds `throughput * contribute` to the target if the ray is unoccluded
 __device__ __forceinline__ void PushShadow(const WaveState& w, const ShadowRequest& req, const vec3& throughput,
-                                           uint32_t path) {
-  const uint32_t slot = WarpAppend(&w.counters[kNumShadow], req.active);
-  if (req.active) {
+                                           uint32_t target) {
+  const bool push = req.active && (target >> 30) != kTargetNone;
+  const uint32_t slot = WarpAppend(&w.counters[kNumShadow], push);
+  if (push) {
     const vec3 c = throughput * req.contribute;
     __stcs(&w.sh_o[slot], make_float4(req.ray.o.x, req.ray.o.y, req.ray.o.z, req.ray.tmin));
     __stcs(&w.sh_d[slot], make_float4(req.ray.d.x, req.ray.d.y, req.ray.d.z, req.ray.tmax));
-    __stcs(&w.sh_c[slot], make_float4(c.x, c.y, c.z, __uint_as_float(path)));
+    __stcs(&w.sh_c[slot], make_float4(c.x, c.y, c.z, __uint_as_float(target)));
   }
 }
 
-// where a slot goes after its vertex: next closest-hit query, or retirement
-__device__ __forceinline__ void RouteSlot(const WaveState& w, uint32_t next_parity, uint32_t p, bool to_next,
-                                          bool to_done) {
+// where a path goes after its vertex: S[next] (it continues) or D[next] (it ended); returns the NEE target
+struct Routed {
+  uint32_t index;    // position in S[next] / D[next]
+  uint32_t target;
+};
+__device__ __forceinline__ Routed RoutePath(const WaveState& w, uint32_t next_parity, bool to_next, bool to_done) {
   const uint32_t a = WarpAppend(&w.counters[kNumActive0 + next_parity], to_next);
-  if (to_next) w.q_active[next_parity][a] = p;
   const uint32_t b = WarpAppend(&w.counters[kNumDone0 + next_parity], to_done);
-  if (to_done) w.q_done[next_parity][b] = p;
+  Routed r;
+  r.index = to_next ? a : b;
+  r.target = to_next ? MakeTarget(kTargetState, a) : (to_done ? MakeTarget(kTargetDone, b) : MakeTarget(kTargetNone, 0u));
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------ iteration set-up
-// zeroes every per-iteration counter; the three ping-pong lists keep the half that this iteration consumes
-// In frame mode it also hands this iteration's camera sample ids to the slots of q_done[cur]: the closest-hit kernel
-// gives work item (n_active + k) the sample id (base + k), so regeneration needs no atomic of its own.
+// zeroes every per-iteration counter; the three ping-pong lists keep the half that this iteration consumes.  In frame
+// mode it also decides how many camera samples this iteration starts: whatever capacity the paths and walks in flight
+// leave free, as long as the frame has samples left.  The closest-hit kernel gives work item (n_active + k) the sample
+// id (base + k), so generation needs no atomic of its own.
 __global__ void BeginIterationKernel(uint32_t* counters, unsigned long long* stats, uint32_t cur_parity,
-                                     uint32_t frame_mode) {
+                                     uint32_t frame_mode, uint32_t capacity, unsigned long long total_samples) {
   const uint32_t i = threadIdx.x;
-  if (i == 0 && frame_mode) {
-    const unsigned long long base = stats[kStatNextSample];
-    stats[kStatSampleBase] = base;
-    stats[kStatNextSample] = base + counters[kNumDone0 + cur_parity];
+  __shared__ uint32_t n_new;
+  if (i == 0) {
+    n_new = 0u;
+    if (frame_mode) {
+      const unsigned long long used = (unsigned long long)counters[kNumActive0 + cur_parity] + counters[kNumWalk0 + cur_parity];
+      const unsigned long long space = capacity > used ? capacity - used : 0ull;
+      const unsigned long long base = stats[kStatNextSample];
+      const unsigned long long left = total_samples > base ? total_samples - base : 0ull;
+      const unsigned long long take = space < left ? space : left;
+      n_new = uint32_t(take);
+      stats[kStatSampleBase] = base;
+      stats[kStatNextSample] = base + take;
+    }
   }
+  __syncthreads();
   if (i >= kCounterCount) return;
   const uint32_t keep0 = kNumActive0 + cur_parity, keep1 = kNumWalk0 + cur_parity, keep2 = kNumDone0 + cur_parity;
   if (i == keep0 || i == keep1 || i == keep2) return;
-  counters[i] = 0u;
+  counters[i] = (i == kNumNew) ? n_new : 0u;
 }
 
 // ------------------------------------------------------------------------------------------------ camera + retire
@@ -257,8 +283,8 @@ struct FrameParams {
   float4* rgba;               // frame accumulator (sums); alpha counts the samples (render.cc:175-183)
 };
 
-__device__ __forceinline__ RayT StartCameraPath(const WaveState& w, const FrameParams& f, uint32_t p,
-                                                unsigned long long id) {
+__device__ __forceinline__ RayT StartCameraPath(const WaveState& w, const FrameParams& f, uint32_t parity, uint32_t i,
+                                                unsigned long long id, uint32_t* pixel_out) {
   const uint32_t s_local = uint32_t(id / f.npix), pixel = uint32_t(id - (unsigned long long)s_local * f.npix);
   const uint32_t x = pixel % f.cam.width, y = pixel / f.cam.width;
   Pcg32 rng;
@@ -269,16 +295,34 @@ __device__ __forceinline__ RayT StartCameraPath(const WaveState& w, const FrameP
   float dx = tx - f.cam.eye[0], dy = ty - f.cam.eye[1], dz = f.cam.z_corner - f.cam.eye[2];
   const float inv_norm = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);   // Normalize (render.cc:243-249)
   dx *= inv_norm; dy *= inv_norm; dz *= inv_norm;
-  StSlot(w, p, kRayO, make_float4(f.cam.eye[0], f.cam.eye[1], f.cam.eye[2], 0.0f));
-  StSlot(w, p, kRayD, make_float4(dx, dy, dz, kInf));
-  StSlot(w, p, kThr, make_float4(1.f, 1.f, 1.f, 0.f));
-  StSlot(w, p, kRad, make_float4(0.f, 0.f, 0.f, __uint_as_float(0u)));
-  StSlot(w, p, kRng, PackRng(rng));
-  StSlot(w, p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
+  StS(w, parity, i, kRayO, make_float4(f.cam.eye[0], f.cam.eye[1], f.cam.eye[2], 0.0f));
+  StS(w, parity, i, kRayD, make_float4(dx, dy, dz, kInf));
+  StS(w, parity, i, kThr, make_float4(1.f, 1.f, 1.f, 0.f));
+  StS(w, parity, i, kRad, make_float4(0.f, 0.f, 0.f, __uint_as_float(0u)));
+  StS(w, parity, i, kRng, PackRng(rng));
+  StS(w, parity, i, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
+  *pixel_out = pixel;
   RayT ray;
   ray.o = vec3(f.cam.eye[0], f.cam.eye[1], f.cam.eye[2]); ray.tmin = 0.0f;
   ray.d = vec3(dx, dy, dz); ray.tmax = kInf;
   return ray;
+}
+
+// render.cc:175-183 for every path that ended in the previous iteration: rgba[pixel] += (L, 1).  D[cur] is read front
+// to back; the frame accumulator (16 B per pixel) is L2-resident.
+__global__ void __launch_bounds__(256) RetireKernel(WaveState w, uint32_t cur_parity, float4* rgba) {
+  const uint32_t n = w.counters[kNumDone0 + cur_parity];
+  const float4* __restrict__ done = DoneBuf(w, cur_parity);
+  uint32_t retired = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 r = __ldcs(&done[i]);
+    const uint32_t pixel = __float_as_uint(r.w);
+    if (pixel != kNoPixel) {
+      atomicAdd(&rgba[pixel], make_float4(r.x, r.y, r.z, 1.0f));
+      ++retired;
+    }
+  }
+  WarpTally(&w.stats[kStatRetired], retired);
 }
 
 // RenderLayer::count (render-layer.h:11-26) from the alpha sums: both are incremented together per sample
@@ -287,62 +331,51 @@ __global__ void FinishFrameKernel(const float4* rgba, uint32_t* count, uint32_t 
   if (i < npix) count[i] = uint32_t(rgba[i].w);
 }
 
-// all slots idle and queued for (re)generation: the state a frame starts from
-__global__ void ResetPoolKernel(WaveState w, uint32_t n_slots) {
+// nothing in flight: the state a frame starts from
+__global__ void ResetPoolKernel(WaveState w) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n_slots) {
-    StSlot(w, p, kPix, make_float4(__uint_as_float(kNoPixel), 0.f, 0.f, 0.f));
-    w.q_done[0][p] = p;
-  }
-  if (p < kCounterCount) w.counters[p] = (p == kNumDone0) ? n_slots : 0u;
+  if (p < kCounterCount) w.counters[p] = 0u;
 }
 
-// caller-supplied rays + seeds (pbrgpu_radiance / pbrgpu_shade hooks): slot i = path i = pixel i, no regeneration
+// caller-supplied rays + seeds (pbrgpu_radiance / pbrgpu_shade hooks): path i = pixel i, no camera samples
 __global__ void InitPathsFromRaysKernel(WaveState w, const float4* rays, const uint64_t* seeds, uint32_t n) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < kCounterCount) w.counters[p] = (p == kNumActive0) ? n : 0u;
   if (p >= n) return;
-  StSlot(w, p, kRayO, rays[2 * p]);
-  StSlot(w, p, kRayD, rays[2 * p + 1]);
+  StS(w, 0u, p, kRayO, rays[2 * p]);
+  StS(w, 0u, p, kRayD, rays[2 * p + 1]);
   Pcg32 rng;
   pcg32_srandom(&rng, seeds[2 * p], seeds[2 * p + 1]);
-  StSlot(w, p, kThr, make_float4(1.f, 1.f, 1.f, 0.f));
-  StSlot(w, p, kRad, make_float4(0.f, 0.f, 0.f, __uint_as_float(0u)));
-  StSlot(w, p, kRng, PackRng(rng));
-  StSlot(w, p, kPix, make_float4(__uint_as_float(p), 0.f, 0.f, 0.f));
-  w.q_active[0][p] = p;
+  StS(w, 0u, p, kThr, make_float4(1.f, 1.f, 1.f, 0.f));
+  StS(w, 0u, p, kRad, make_float4(0.f, 0.f, 0.f, __uint_as_float(0u)));
+  StS(w, 0u, p, kRng, PackRng(rng));
+  StS(w, 0u, p, kPix, make_float4(__uint_as_float(p), 0.f, 0.f, 0.f));
 }
 
 // ------------------------------------------------------------------------------------------------ closest hit
-// Scene::TraceFirstHit1 for every active slot; routes it by the material kind of what it hit, retires it on a miss.
-// Runs in the warp traversal engine (device/trav_engine.cuh): lanes are refilled from q_active while others traverse.
+// Scene::TraceFirstHit1 for every path of S[cur]; a hit is routed by the material class of what it hit, a miss is
+// retired on the spot (render.cc:28-30: the path ends with the radiance it has).  Items past n_active are this
+// iteration's new camera samples: generated here, so a camera ray never makes a round trip through memory before its
+// first traversal.  Runs in the warp traversal engine: lanes are refilled while others traverse.
 struct ClosestClient {
   const SceneView& s;
   const WaveState& w;
-  const FrameParams& frame;      // frame mode: retire + regenerate the slots of q_done[cur] in here
-  const bool regen;
+  const FrameParams& frame;      // frame mode: how camera samples are numbered
+  float4* rgba;                  // accumulator of retired paths (frame.rgba, or the hook's per-path buffer)
   const bool sort_materials;     // route diffuse-only materials to their own shading queue
-  const uint32_t* __restrict__ queue;
-  const uint32_t* __restrict__ done;
-  uint32_t n_active, n, next_parity;
+  uint32_t cur, n_active, n;
   unsigned long long sample_base;
-  uint32_t p = 0;
-  bool has_result = false;
+  uint32_t item = 0, pixel = kNoPixel;
+  bool has_result = false, fresh = false;   // fresh: a camera ray (radiance 0, pixel known)
   uint32_t rays = 0, retired = 0;
 
   __device__ __forceinline__ ClosestClient(const SceneView& s_, const WaveState& w_, uint32_t cur_parity,
-                                           const FrameParams& frame_, bool regen_, bool sort_)
-      : s(s_), w(w_), frame(frame_), regen(regen_), sort_materials(sort_), queue(w_.q_active[cur_parity]), done(w_.q_done[cur_parity]),
+                                           const FrameParams& frame_, float4* rgba_, bool sort_)
+      : s(s_), w(w_), frame(frame_), rgba(rgba_), sort_materials(sort_), cur(cur_parity),
         n_active(w_.counters[kNumActive0 + cur_parity]),
-        n(w_.counters[kNumActive0 + cur_parity] + (regen_ ? w_.counters[kNumDone0 + cur_parity] : 0u)),
-        next_parity(cur_parity ^ 1u),
-        sample_base(regen_ ? w_.stats[kStatSampleBase] : 0ull) {}
+        n(w_.counters[kNumActive0 + cur_parity] + w_.counters[kNumNew]),
+        sample_base(w_.stats[kStatSampleBase]) {}
   __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
-
-  // work item -> slot: first the slots that shading sent on, then (frame mode) last iteration's finished slots
-  __device__ __forceinline__ uint32_t SlotOf(uint32_t item) const {
-    return item < n_active ? queue[item] : done[item - n_active];
-  }
 
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     const bool finished = !t.active && has_result;
@@ -350,7 +383,7 @@ struct ClosestClient {
     // ---- (1) finished rays: miss -> retire, else the shading queue of the material's class
     int kind = -1;   // -1 nothing, 0 miss, 1 general surface queue, 2 hair queue, 3 diffuse-only queue
     const HitT hit = t.hit;
-    const uint32_t done_p = p;
+    const uint32_t done_item = item;
     if (finished) {
       has_result = false;
       kind = 0;
@@ -367,81 +400,72 @@ struct ClosestClient {
         }
       }
     }
-    // ---- (2) the four output queues and the work fetch: one atomic instruction
-    const Append5 app = Append5Issue(&w.counters[kNumSurface], &w.counters[kNumHair],
-                                     &w.counters[kNumDone0 + next_parity], &w.counters[kFetchTrace],
-                                     &w.counters[kNumDiffuse], kind == 1, kind == 2, kind == 0, need, kind == 3);
-    const uint32_t i_surf = Append5Index(app, 0), i_hair = Append5Index(app, 1), i_done = Append5Index(app, 2),
-                   item = Append5Index(app, 3), i_diff = Append5Index(app, 4);
+    // ---- (2) the three output queues and the work fetch: one atomic instruction
+    const Append5 app = Append5Issue(&w.counters[kNumSurface], &w.counters[kNumHair], nullptr, &w.counters[kFetchTrace],
+                                     &w.counters[kNumDiffuse], kind == 1, kind == 2, false, need, kind == 3);
+    const uint32_t i_surf = Append5Index(app, 0), i_hair = Append5Index(app, 1), next_item = Append5Index(app, 3),
+                   i_diff = Append5Index(app, 4);
     // ---- (3) new work: the loads are issued here and consumed after the finished rays have been written out
-    const bool take = need && item < n_active;          // a path that continues
-    const bool renew = need && item >= n_active && item < n;   // a finished slot: retire it, start the next sample
-    float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = ro, rrad = ro;
-    uint32_t np = 0, rpix = kNoPixel;
-    if (take || renew) np = SlotOf(item);
+    const bool take = need && next_item < n_active;                      // a path that continues
+    const bool start = need && next_item >= n_active && next_item < n;   // a new camera sample
+    float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = ro;
     if (take) {
-      ro = LdSlot(w, np, kRayO);
-      rd = LdSlot(w, np, kRayD);
-    } else if (renew) {
-      rpix = __float_as_uint(LdSlot(w, np, kPix).x);
-      rrad = LdSlot(w, np, kRad);
+      ro = LdS(w, cur, next_item, kRayO);
+      rd = LdS(w, cur, next_item, kRayD);
     }
     // ---- (4) write out the finished rays
-    if (kind >= 0) {
-      StSlot(w, done_p, kHit, make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim)));
-      StSlot(w, done_p, kHitPad, make_float4(0.f, 0.f, 0.f, 0.f));   // completes the sector: no read-modify-write
-      if (kind == 1) w.q_surface[i_surf] = done_p;
-      else if (kind == 2) w.q_hair[i_hair] = done_p;
-      else if (kind == 3) w.q_diffuse[i_diff] = done_p;
-      else w.q_done[next_parity][i_done] = done_p;
+    if (kind > 0) {
+      StS(w, cur, done_item, kHit, PackHit(hit));
+      if (kind == 1) w.q_surface[i_surf] = done_item;
+      else if (kind == 2) w.q_hair[i_hair] = done_item;
+      else w.q_diffuse[i_diff] = done_item;
+    } else if (kind == 0) {
+      // render.cc:175-183 for the path that just left the scene
+      float4 rrad = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t rpix = pixel;
+      if (!fresh) {
+        rrad = LdS(w, cur, done_item, kRad);
+        rpix = __float_as_uint(LdS(w, cur, done_item, kPix).x);
+      }
+      if (rpix != kNoPixel) {
+        atomicAdd(&rgba[rpix], make_float4(rrad.x, rrad.y, rrad.z, 1.0f));
+        ++retired;
+      }
     }
     // ---- (5) start the new rays
     if (take) {
-      p = np;
-      RayT ray;
-      ray.o = vec3(ro.x, ro.y, ro.z); ray.tmin = ro.w;
-      ray.d = vec3(rd.x, rd.y, rd.z); ray.tmax = rd.w;
+      item = next_item;
+      fresh = false;
+      TravBegin(s, RayFrom(ro, rd), t);
+      has_result = true;
+      ++rays;
+    } else if (start) {
+      item = next_item;
+      fresh = true;
+      const RayT ray = StartCameraPath(w, frame, cur, item, sample_base + (next_item - n_active), &pixel);
       TravBegin(s, ray, t);
       has_result = true;
       ++rays;
-    } else if (renew) {
-      // render.cc:175-183 for the path that ended in this slot, then the next camera sample in the same slot: the
-      // camera ray never makes a round trip through memory before its first traversal
-      if (rpix != kNoPixel) {
-        atomicAdd(&frame.rgba[rpix], make_float4(rrad.x, rrad.y, rrad.z, 1.0f));
-        ++retired;
-      }
-      const unsigned long long id = sample_base + (item - n_active);
-      if (id < frame.total_samples) {
-        p = np;
-        const RayT ray = StartCameraPath(w, frame, p, id);
-        TravBegin(s, ray, t);
-        has_result = true;
-        ++rays;
-      } else {
-        StSlot(w, np, kPix, make_float4(__uint_as_float(kNoPixel), 0.f, 0.f, 0.f));
-      }
     }
-    return need && item >= n;
+    return need && next_item >= n;
   }
   __device__ __forceinline__ void End(const Trav&) {
     WarpTally(&w.stats[kStatClosest], rays);
-    if (regen) WarpTally(&w.stats[kStatRetired], retired);
+    WarpTally(&w.stats[kStatRetired], retired);
   }
 };
 
 template <bool HAS_CURVES>
 __global__ void __launch_bounds__(128) TraceClosestKernel(SceneView s, WaveState w, uint32_t cur_parity,
                                                           uint32_t refill_min_idle, uint32_t prim_min_lanes,
-                                                          FrameParams frame, uint32_t regenerate,
-                                                          uint32_t sort_materials) {
-  ClosestClient client(s, w, cur_parity, frame, regenerate != 0u, sort_materials != 0u);
+                                                          FrameParams frame, float4* rgba, uint32_t sort_materials) {
+  ClosestClient client(s, w, cur_parity, frame, rgba, sort_materials != 0u);
   TravEngine<false, HAS_CURVES, false>(s, client, refill_min_idle, prim_min_lanes);
 }
 
 // ------------------------------------------------------------------------------------------------ shading
 struct ShadeFlags {
-  uint32_t skip_emission_and_roulette;   // pbrgpu_shade hook: call Shader() only
+  uint32_t skip_emission_and_roulette;   // pbrgpu_shade hook: call Shader() only, and keep every path in S[next]
 };
 
 // what a shading kernel holds of its path between load and commit
@@ -454,92 +478,74 @@ struct PathRegs {
   Pcg32 rng;
 };
 
-// the seven records of a slot line that a shading kernel reads (kHitPad is never read)
-__device__ __forceinline__ PathRegs PathFromRecords(const float4& o, const float4& d, const float4& t4, const float4& r4,
-                                                    const float4& h4, const float4& g4, const float4& x4) {
+__device__ __forceinline__ PathRegs LoadPath(const WaveState& w, uint32_t parity, uint32_t i) {
+  const float4 o = LdS(w, parity, i, kRayO), d = LdS(w, parity, i, kRayD), t4 = LdS(w, parity, i, kThr),
+               r4 = LdS(w, parity, i, kRad), h4 = LdS(w, parity, i, kHit), g4 = LdS(w, parity, i, kRng),
+               x4 = LdS(w, parity, i, kPix);
   PathRegs r;
-  r.ray.o = vec3(o.x, o.y, o.z); r.ray.tmin = o.w;
-  r.ray.d = vec3(d.x, d.y, d.z); r.ray.tmax = d.w;
-  r.hit.t = h4.x; r.hit.u = h4.y; r.hit.v = h4.z; r.hit.prim = __float_as_uint(h4.w);
+  r.ray = RayFrom(o, d);
+  r.hit = HitFrom(h4);
   r.throughput = vec3(t4.x, t4.y, t4.z);
   r.pdf_prev = t4.w;
   r.L = vec3(r4.x, r4.y, r4.z);
   r.depth = __float_as_uint(r4.w);
-  r.rng.state = (uint64_t(__float_as_uint(g4.y)) << 32) | __float_as_uint(g4.x);
-  r.rng.inc = (uint64_t(__float_as_uint(g4.w)) << 32) | __float_as_uint(g4.z);
+  r.rng = RngFrom(g4);
   r.pixel = __float_as_uint(x4.x);
   return r;
 }
-__device__ __forceinline__ PathRegs LoadPath(const WaveState& w, uint32_t p) {
-  return PathFromRecords(LdSlot(w, p, kRayO), LdSlot(w, p, kRayD), LdSlot(w, p, kThr), LdSlot(w, p, kRad),
-                         LdSlot(w, p, kHit), LdSlot(w, p, kRng), LdSlot(w, p, kPix));
-}
 
-// after a vertex: sectors 0, 1 and 3 of the line are rewritten whole (render.cc:79-86)
-__device__ __forceinline__ void CommitVertex(const WaveState& w, uint32_t p, const VertexResult& vr,
+// after a vertex: the path's next state, appended to S[next] (render.cc:79-86)
+__device__ __forceinline__ void CommitVertex(const WaveState& w, uint32_t next_parity, uint32_t j, const VertexResult& vr,
                                              const vec3& throughput, const vec3& L, uint32_t depth, const Pcg32& rng,
                                              uint32_t pixel) {
-  const vec3 new_thr = vr.throughput * throughput;                     // render.cc:80
-  StSlot(w, p, kRayO, make_float4(vr.P.x, vr.P.y, vr.P.z, 1e-3f));     // render.cc:83-86
-  StSlot(w, p, kRayD, make_float4(vr.wi.x, vr.wi.y, vr.wi.z, kInf));
-  StSlot(w, p, kThr, make_float4(new_thr.x, new_thr.y, new_thr.z, vr.pdf));
-  StSlot(w, p, kRad, make_float4(L.x, L.y, L.z, __uint_as_float(depth + 1u)));
-  StSlot(w, p, kRng, PackRng(rng));
-  StSlot(w, p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
+  const vec3 new_thr = vr.throughput * throughput;                                  // render.cc:80
+  StS(w, next_parity, j, kRayO, make_float4(vr.P.x, vr.P.y, vr.P.z, 1e-3f));        // render.cc:83-86
+  StS(w, next_parity, j, kRayD, make_float4(vr.wi.x, vr.wi.y, vr.wi.z, kInf));
+  StS(w, next_parity, j, kThr, make_float4(new_thr.x, new_thr.y, new_thr.z, vr.pdf));
+  StS(w, next_parity, j, kRad, make_float4(L.x, L.y, L.z, __uint_as_float(depth + 1u)));
+  StS(w, next_parity, j, kRng, PackRng(rng));
+  StS(w, next_parity, j, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
 }
 
-// the path ends here: only its radiance (and pixel) are read again
-__device__ __forceinline__ void CommitEnd(const WaveState& w, uint32_t p, const vec3& L, uint32_t depth) {
-  StSlot(w, p, kThr, make_float4(0.f, 0.f, 0.f, 0.f));
-  StSlot(w, p, kRad, make_float4(L.x, L.y, L.z, __uint_as_float(depth)));
+// the path ends here: its radiance waits in D[next] for this iteration's shadow rays, then for the next retire
+__device__ __forceinline__ void CommitDone(const WaveState& w, uint32_t next_parity, uint32_t j, const vec3& L,
+                                           uint32_t pixel) {
+  __stcs(&DoneBuf(w, next_parity)[j], make_float4(L.x, L.y, L.z, __uint_as_float(pixel)));
 }
 
-__device__ __forceinline__ void ParkWalk(const WaveState& w, uint32_t p, const SssWalkState& k) {
-  StWalk(w, p, kWalkA, make_float4(k.sigma_t.x, k.sigma_t.y, k.sigma_t.z, k.throughput.x));
-  StWalk(w, p, kWalkB, make_float4(k.sigma_s.x, k.sigma_s.y, k.sigma_s.z, k.throughput.y));
-  StWalk(w, p, kWalkC, make_float4(k.ray.o.x, k.ray.o.y, k.ray.o.z, k.throughput.z));
-  StWalk(w, p, kWalkD, make_float4(k.ray.d.x, k.ray.d.y, k.ray.d.z, k.ray.tmin));
-  StWalk(w, p, kWalkN, make_float4(__uint_as_float(k.bounce), 0.f, 0.f, 0.f));
-}
-__device__ __forceinline__ void ResumeWalk(const WaveState& w, uint32_t p, SssWalkState* k) {
-  const float4 a = LdWalk(w, p, kWalkA), b = LdWalk(w, p, kWalkB), c = LdWalk(w, p, kWalkC), d = LdWalk(w, p, kWalkD);
-  k->sigma_t = vec3(a.x, a.y, a.z);
-  k->sigma_s = vec3(b.x, b.y, b.z);
-  k->throughput = vec3(a.w, b.w, c.w);
-  k->ray.o = vec3(c.x, c.y, c.z);
-  k->ray.d = vec3(d.x, d.y, d.z);
-  k->ray.tmin = d.w;
-  k->ray.tmax = kInf;
-  k->bounce = __float_as_uint(LdWalk(w, p, kWalkN).x);
+// a walk that starts (or goes on) next iteration: hot part
+__device__ __forceinline__ void StoreWalkHot(const WaveState& w, uint32_t parity, uint32_t k, const SssWalkState& st,
+                                             const Pcg32& rng, uint32_t pixel) {
+  StW(w, parity, k, kWalkA, make_float4(st.sigma_t.x, st.sigma_t.y, st.sigma_t.z, st.throughput.x));
+  StW(w, parity, k, kWalkB, make_float4(st.sigma_s.x, st.sigma_s.y, st.sigma_s.z, st.throughput.y));
+  StW(w, parity, k, kWalkC, make_float4(st.ray.o.x, st.ray.o.y, st.ray.o.z, st.throughput.z));
+  StW(w, parity, k, kWalkD, make_float4(st.ray.d.x, st.ray.d.y, st.ray.d.z, st.ray.tmin));
+  StW(w, parity, k, kWalkN, make_float4(__uint_as_float(st.bounce), __uint_as_float(pixel), 0.f, 0.f));
+  StW(w, parity, k, kWalkRng, PackRng(rng));
 }
 
-// emission + MIS, roulette, material dispatch, Principled vertex.  When the vertex selects the random-walk closure
-// the walk is set up here (entry direction + coefficients, random-walk-sss.h:227-279) and parked for sss_walk.
-// Launch shapes: the general kernel needs ~110-128 registers, so one 512-thread block per SM; the diffuse-only kernel is
-// 7x smaller (2.1k vs 15.7k SASS instructions) and fits three 256-thread blocks per SM.
-constexpr int kDiffuseBlock = 256, kDiffuseBlocksPerSm = 3;
-// One Principled vertex (render.cc:33-86 + shader.cc:8-34) of path slot p whose state is in r; called by every lane of
-// a warp (lanes without an item pass valid = false): the queue appends are warp collectives.
+// One Principled vertex (render.cc:33-86 + shader.cc:8-34) of a path of S[cur] whose state is in r; called by every
+// lane of a warp (lanes without an item pass valid = false): the queue appends are warp collectives.
 template <bool DIFFUSE_ONLY>
 __device__ __forceinline__ void ShadeSurfaceItem(const SceneView& s, const WaveState& w, uint32_t next_parity,
-                                                 const ShadeFlags& flags, bool valid, uint32_t p, PathRegs& r) {
+                                                 const ShadeFlags& flags, bool valid, PathRegs& r) {
   bool to_sss = false, to_next = false, to_done = false;
   ShadowRequest req;
   req.active = false;
-  vec3 throughput(0.f);
+  vec3 throughput(0.f), L(0.f);
+  VertexResult vr;
+  SssWalkState walk;
   if (valid) {
     throughput = r.throughput;
-    vec3 L = r.L;
+    L = r.L;
     const Surface si = MakeSurface(s, r.ray, r.hit);
     bool alive = true;
     if (!flags.skip_emission_and_roulette)
       alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &L, &throughput);
     if (!alive) {
-      CommitEnd(w, p, L, r.depth);
       to_done = true;
     } else {
       const int kind = DIFFUSE_ONLY ? 1 : MaterialKind(s, si);
-      VertexResult vr;
       const vec3 wo = -r.ray.d;
       Frame fr;
       PrincipledBsdf bsdf;
@@ -548,38 +554,42 @@ __device__ __forceinline__ void ShadeSurfaceItem(const SceneView& s, const WaveS
       else AbsorbVertex(wo, si.P, &vr);   // no material (shader.cc:11-17)
       req = vr.shadow[0];
       if (!DIFFUSE_ONLY && sss) {
-        SssWalkState walk;
-        if (SssBegin(si, fr, bsdf, &r.rng, &walk)) {
-          // the walk runs in its own kernel: park it, and the path with the post-roulette throughput
-          ParkWalk(w, p, walk);
-          StSlot(w, p, kThr, make_float4(throughput.x, throughput.y, throughput.z, r.pdf_prev));
-          StSlot(w, p, kRad, make_float4(L.x, L.y, L.z, __uint_as_float(r.depth)));
-          StSlot(w, p, kRng, PackRng(r.rng));
-          StSlot(w, p, kPix, make_float4(__uint_as_float(r.pixel), 0.f, 0.f, 0.f));
-          to_sss = true;
-        } else {   // walk rejected: throughput 0, the path ends (cycles-principled-shader.cc:217-220)
-          CommitEnd(w, p, L, r.depth + 1u);
-          to_done = true;
-        }
+        // the walk runs in its own kernel; rejected: throughput 0, the path ends (cycles-principled-shader.cc:217-220)
+        if (SssBegin(si, fr, bsdf, &r.rng, &walk)) to_sss = true;
+        else to_done = true;
       } else {
-        CommitVertex(w, p, vr, throughput, L, r.depth, r.rng, r.pixel);
-        to_next = !IsBlack(vr.throughput * throughput);               // render.cc:31
+        to_next = flags.skip_emission_and_roulette ? true : !IsBlack(vr.throughput * throughput);   // render.cc:31
         to_done = !to_next;
       }
     }
   }
-  PushShadow(w, req, throughput, p);
+  const Routed route = RoutePath(w, next_parity, to_next, to_done);
+  uint32_t target = route.target;
+  if (to_next) CommitVertex(w, next_parity, route.index, vr, throughput, L, r.depth, r.rng, r.pixel);
+  else if (to_done) CommitDone(w, next_parity, route.index, L, r.pixel);
   if (!DIFFUSE_ONLY) {
-    const uint32_t a = WarpAppend(&w.counters[kNumSss], to_sss);
-    if (to_sss) w.q_sss[a] = p;
+    const uint32_t k = WarpAppend(&w.counters[kNumWalk0 + next_parity], to_sss);
+    if (to_sss) {
+      // the walk, the entry vertex (ray + hit: the exit vertex rebuilds the entry surface from them) and the path it
+      // resumes with (post-roulette throughput)
+      StoreWalkHot(w, next_parity, k, walk, r.rng, r.pixel);
+      StW(w, next_parity, k, kWalkRayO, make_float4(r.ray.o.x, r.ray.o.y, r.ray.o.z, r.ray.tmin));
+      StW(w, next_parity, k, kWalkRayD, make_float4(r.ray.d.x, r.ray.d.y, r.ray.d.z, r.ray.tmax));
+      StW(w, next_parity, k, kWalkHit, PackHit(r.hit));
+      StW(w, next_parity, k, kWalkThr, make_float4(throughput.x, throughput.y, throughput.z, r.pdf_prev));
+      StW(w, next_parity, k, kWalkRad, make_float4(L.x, L.y, L.z, __uint_as_float(r.depth)));
+      target = MakeTarget(kTargetWalk, k);
+    }
   }
-  RouteSlot(w, next_parity, p, to_next, to_done);
+  PushShadow(w, req, throughput, target);
 }
 
+// Launch shapes: the general kernel needs ~110-128 registers, so one 512-thread block per SM; the diffuse-only kernel is
+// 7x smaller (2.1k vs 15.7k SASS instructions): 128-thread blocks, 6 per SM (sweep: profiles/r1z_diffuse_shape_sweep.log)
+constexpr int kDiffuseBlock = 256, kDiffuseBlocksPerSm = 3;
 template <bool DIFFUSE_ONLY>
 __global__ void __launch_bounds__(DIFFUSE_ONLY ? kDiffuseBlock : kShadeBlock, DIFFUSE_ONLY ? kDiffuseBlocksPerSm : 1)
-ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t next_parity,
-                                                          ShadeFlags flags) {
+ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t cur_parity, ShadeFlags flags) {
   const uint32_t n = w.counters[DIFFUSE_ONLY ? kNumDiffuse : kNumSurface];
   const uint32_t* __restrict__ queue = DIFFUSE_ONLY ? w.q_diffuse : w.q_surface;
   uint32_t shaded = 0;
@@ -588,129 +598,50 @@ ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t next_parity,
     if (slot - threadIdx.x >= n) break;   // block-uniform
     const bool valid = slot < n;
     shaded += valid ? 1u : 0u;
-    uint32_t p = 0;
     PathRegs r;
-    if (valid) {
-      p = queue[slot];
-      r = LoadPath(w, p);
-    }
-    ShadeSurfaceItem<DIFFUSE_ONLY>(s, w, next_parity, flags, valid, p, r);
+    if (valid) r = LoadPath(w, cur_parity, queue[slot]);
+    ShadeSurfaceItem<DIFFUSE_ONLY>(s, w, cur_parity ^ 1u, flags, valid, r);
   }
   WarpTally(&w.stats[kStatVertices], shaded);
 }
 
-// The diffuse-only vertex is short (2.1 k SASS instructions) and its kernel was bound by the latency of one dependent
-// chain per thread — work fetch (atomic) -> queue entry -> slot line (a random 128-byte line in HBM) -> primitive ->
-// normals -> material -> light tables — with 15 % of the issue slots busy and DRAM at 16 % (profiles/r1_final_ncu.md).
-// This version takes the first three links off the chain: a block reserves kPipeBatches batches with ONE atomic, reads
-// the queue entries (dense, coalesced) one batch ahead, and copies the slot line of batch b+1 into shared memory with
-// cp.async (L2 evict-first, no registers held) while batch b is shaded.  A thread reads back only the row it copied
-// itself, so the pipeline needs no block barrier.  Rows are swizzled by (record ^ row) so that the 128-bit shared
-// loads of a quarter warp fall into different banks.
-constexpr int kPipeBatches = 8;
-__device__ __forceinline__ void CpAsync16(void* smem_dst, const void* gmem_src, uint64_t policy) {
-  const uint32_t dst = uint32_t(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void CpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__global__ void __launch_bounds__(kDiffuseBlock, kDiffuseBlocksPerSm)
-ShadeDiffusePipelinedKernel(SceneView s, WaveState w, uint32_t next_parity, ShadeFlags flags) {
-  extern __shared__ float4 stage[];   // [2][blockDim.x][8 records]
-  __shared__ uint32_t s_base;
-  const uint32_t n = w.counters[kNumDiffuse];
-  const uint32_t* __restrict__ queue = w.q_diffuse;
-  const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  float4* row0 = stage + size_t(tid) * 8;
-  float4* row1 = stage + size_t(nthr + tid) * 8;
-  const uint32_t sw = tid & 7u;
-  auto issue = [&](float4* row, uint32_t p) {
-    const float4* src = w.slot + size_t(p) * kSlotStride;
-#pragma unroll
-    for (uint32_t k = 0; k < 8; ++k)
-      if (k != uint32_t(kHitPad)) CpAsync16(row + (k ^ sw), src + k, policy);
-  };
-  uint32_t shaded = 0;
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_base = atomicAdd(&w.counters[kFetchDiffuse], nthr * uint32_t(kPipeBatches));
-    __syncthreads();
-    const uint32_t base = s_base;
-    if (base >= n) break;   // block-uniform
-    uint32_t item = base + tid;
-    uint32_t p_cur = item < n ? queue[item] : kInvalid;
-    if (p_cur != kInvalid) issue(row0, p_cur);
-    CpAsyncCommit();
-    uint32_t p_next = (item + nthr < n) ? queue[item + nthr] : kInvalid;
-#pragma unroll 1
-    for (int b = 0; b < kPipeBatches; ++b) {
-      if (base + uint32_t(b) * nthr >= n) break;   // block-uniform: nothing left in this chunk
-      float4* cur = (b & 1) ? row1 : row0;
-      float4* nxt = (b & 1) ? row0 : row1;
-      uint32_t p_next2 = kInvalid;
-      if (b + 1 < kPipeBatches) {
-        if (p_next != kInvalid) issue(nxt, p_next);
-        const uint32_t item2 = base + uint32_t(b + 2) * nthr + tid;
-        if (b + 2 < kPipeBatches && item2 < n) p_next2 = queue[item2];
-      }
-      CpAsyncCommit();
-      CpAsyncWait<1>();   // everything but the group just committed has landed: batch b is in `cur`
-      const bool valid = p_cur != kInvalid;
-      shaded += valid ? 1u : 0u;
-      PathRegs r;
-      if (valid)
-        r = PathFromRecords(cur[kRayO ^ sw], cur[kRayD ^ sw], cur[kThr ^ sw], cur[kRad ^ sw], cur[kHit ^ sw],
-                            cur[kRng ^ sw], cur[kPix ^ sw]);
-      ShadeSurfaceItem<true>(s, w, next_parity, flags, valid, valid ? p_cur : 0u, r);
-      p_cur = p_next;
-      p_next = p_next2;
-    }
-    CpAsyncWait<0>();
-  }
-  WarpTally(&w.stats[kStatVertices], shaded);
-}
-
-__global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, WaveState w, uint32_t next_parity,
-                                                       ShadeFlags flags) {
+__global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, WaveState w, uint32_t cur_parity,
+                                                               ShadeFlags flags) {
   const uint32_t n = w.counters[kNumHair];
+  const uint32_t next_parity = cur_parity ^ 1u;
   uint32_t shaded = 0;
   for (;;) {
     const uint32_t slot = BlockFetch(&w.counters[kFetchHair]);
     if (slot - threadIdx.x >= n) break;   // block-uniform
     const bool valid = slot < n;
     shaded += valid ? 1u : 0u;
-    uint32_t p = 0;
     bool to_next = false, to_done = false;
     ShadowRequest req;
     req.active = false;
-    vec3 throughput(0.f);
+    vec3 throughput(0.f), L(0.f);
+    VertexResult vr;
+    PathRegs r;
     if (valid) {
-      p = w.q_hair[slot];
-      PathRegs r = LoadPath(w, p);
+      r = LoadPath(w, cur_parity, w.q_hair[slot]);
       throughput = r.throughput;
-      vec3 L = r.L;
+      L = r.L;
       const Surface si = MakeSurface(s, r.ray, r.hit);
       bool alive = true;
       if (!flags.skip_emission_and_roulette)
         alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &L, &throughput);
       if (!alive) {
-        CommitEnd(w, p, L, r.depth);
         to_done = true;
       } else {
-        VertexResult vr;
         HairVertex(s, si, -r.ray.d, &r.rng, &vr);
         req = vr.shadow[0];
-        CommitVertex(w, p, vr, throughput, L, r.depth, r.rng, r.pixel);
-        to_next = !IsBlack(vr.throughput * throughput);
+        to_next = flags.skip_emission_and_roulette ? true : !IsBlack(vr.throughput * throughput);
         to_done = !to_next;
       }
     }
-    PushShadow(w, req, throughput, p);
-    RouteSlot(w, next_parity, p, to_next, to_done);
+    const Routed route = RoutePath(w, next_parity, to_next, to_done);
+    if (to_next) CommitVertex(w, next_parity, route.index, vr, throughput, L, r.depth, r.rng, r.pixel);
+    else if (to_done) CommitDone(w, next_parity, route.index, L, r.pixel);
+    PushShadow(w, req, throughput, route.target);
   }
   WarpTally(&w.stats[kStatVertices], shaded);
 }
@@ -722,18 +653,19 @@ __global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, Wave
 //   * the queries run in the warp traversal engine; a lane whose segment ends waits until `refill_min_idle` lanes are
 //     in that state, then they all do the scatter step (transmittance, roulette, new direction and distance)
 //     converged and go back to traversing — no lane waits for the longest walk of its warp;
-//   * a walk gets at most `max_bounces` bounces per launch; if it is still inside the medium its state is parked in
-//     its walk line and the slot goes to q_walk[next]: the next iteration resumes it first.  A launch therefore
-//     never outlives its queue by more than max_bounces bounces, and because the pool is kept full by
-//     regeneration, long walks cost slots, not idle SMs;
+//   * a walk gets at most `max_bounces` bounces per launch; if it is still inside the medium its record is appended
+//     to W[next] and the next iteration goes on with it.  A launch therefore never outlives its queue by more than
+//     max_bounces bounces (and the walks are re-balanced over the warps every time: larger budgets were measured and
+//     are slower, profiles/r2a_tune.log), and because the pool is kept full by new camera samples, long walks cost
+//     capacity, not idle SMs;
 //   * entering the medium is part of shade_surface, leaving it (exit vertex: NEE + diffuse bounce,
 //     cycles-principled-shader.cc:187-216) is sss_exit: both are rare per bounce and ran at 2-3 lanes per warp when
-//     they were inlined here (profiles/r1b_summary.md).
+//     they were inlined here.
 struct SssClient {
   const SceneView& s;
   const WaveState& w;
-  uint32_t cur_parity, next_parity, n_resume, n, max_bounces;
-  uint32_t p = 0, budget = 0, pixel = 0;
+  uint32_t cur, next, n, max_bounces;
+  uint32_t item = 0, budget = 0, pixel = 0;
   bool has_walk = false;
   bool skipped_seg = false;   // the current segment was answered by the clearance grid, not traced
   Pcg32 rng;
@@ -741,9 +673,8 @@ struct SssClient {
   vec3 cpdf;            // channel probabilities of the segment in flight (SssPrepareSegment -> SssFinishSegment)
   uint32_t rays = 0, skipped = 0;
 
-  __device__ __forceinline__ SssClient(const SceneView& s_, const WaveState& w_, uint32_t cur, uint32_t max_b)
-      : s(s_), w(w_), cur_parity(cur), next_parity(cur ^ 1u), n_resume(w_.counters[kNumWalk0 + cur]),
-        n(w_.counters[kNumWalk0 + cur] + w_.counters[kNumSss]), max_bounces(max_b) {}
+  __device__ __forceinline__ SssClient(const SceneView& s_, const WaveState& w_, uint32_t cur_parity, uint32_t max_b)
+      : s(s_), w(w_), cur(cur_parity), next(cur_parity ^ 1u), n(w_.counters[kNumWalk0 + cur_parity]), max_bounces(max_b) {}
   __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_walk || !exhausted; }
 
   __device__ __forceinline__ void StartSegment(Trav& t) {
@@ -756,14 +687,10 @@ struct SssClient {
     if (skipped_seg) t.active = false;
   }
 
-  __device__ __forceinline__ uint32_t SlotOf(uint32_t item) const {
-    return item < n_resume ? w.q_walk[cur_parity][item] : w.q_sss[item - n_resume];
-  }
-
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     // ---- (1) walks whose segment query finished: scatter / exit / absorb
     bool to_exit = false, to_done = false, to_park = false, go_on = false;
-    const uint32_t routed_p = p;
+    const uint32_t src = item;
     const HitT hit = t.hit;
     if (!t.active && has_walk) {
       walk.ray.o = t.O; walk.ray.d = t.D; walk.ray.tmin = t.tmin;   // tmax untouched: the scatter distance
@@ -777,45 +704,51 @@ struct SssClient {
       else go_on = true;
       has_walk = go_on;
     }
-    // ---- (2) the three output queues and the work fetch (lanes without a walk): one atomic instruction
+    // ---- (2) the three output streams and the work fetch (lanes without a walk): one atomic instruction
     const bool need = !exhausted && !t.active && !has_walk;
-    const Append5 app = Append5Issue(&w.counters[kNumExit], &w.counters[kNumDone0 + next_parity],
-                                     &w.counters[kNumWalk0 + next_parity], &w.counters[kFetchSss], nullptr, to_exit,
+    const Append5 app = Append5Issue(&w.counters[kNumExit], &w.counters[kNumDone0 + next],
+                                     &w.counters[kNumWalk0 + next], &w.counters[kFetchWalk], nullptr, to_exit,
                                      to_done, to_park, need, false);
     const uint32_t i_exit = Append5Index(app, 0), i_done = Append5Index(app, 1), i_park = Append5Index(app, 2),
-                   item = Append5Index(app, 3);
+                   next_item = Append5Index(app, 3);
     // ---- (3) write out the walks that stopped
     if (to_exit) {
-      // exit record for sss_exit: the segment ray, its hit and the walk throughput
-      StWalk(w, routed_p, kWalkA, make_float4(hit.t, hit.u, hit.v, __uint_as_float(hit.prim)));
-      StWalk(w, routed_p, kWalkB, make_float4(walk.throughput.x, walk.throughput.y, walk.throughput.z, 0.f));
-      StWalk(w, routed_p, kWalkC, make_float4(walk.ray.o.x, walk.ray.o.y, walk.ray.o.z, walk.ray.tmin));
-      StWalk(w, routed_p, kWalkD, make_float4(walk.ray.d.x, walk.ray.d.y, walk.ray.d.z, walk.ray.tmax));
-      w.q_exit[i_exit] = routed_p;
+      // exit record for sss_exit: the segment ray, its hit, the walk throughput; the cold part stays in W[cur][src]
+      StE(w, i_exit, kExHit, PackHit(hit));
+      StE(w, i_exit, kExThr, make_float4(walk.throughput.x, walk.throughput.y, walk.throughput.z, __uint_as_float(src)));
+      StE(w, i_exit, kExO, make_float4(walk.ray.o.x, walk.ray.o.y, walk.ray.o.z, walk.ray.tmin));
+      StE(w, i_exit, kExD, make_float4(walk.ray.d.x, walk.ray.d.y, walk.ray.d.z, walk.ray.tmax));
+      StE(w, i_exit, kExRng, PackRng(rng));
     } else if (to_park) {
-      ParkWalk(w, routed_p, walk);
-      w.q_walk[next_parity][i_park] = routed_p;
+      StoreWalkHot(w, next, i_park, walk, rng, pixel);
+#pragma unroll
+      for (int f = kWalkRayO; f < kWalkFields; ++f) StW(w, next, i_park, f, LdW(w, cur, src, f));
     } else if (to_done) {
-      w.q_done[next_parity][i_done] = routed_p;
+      const float4 rad = LdW(w, cur, src, kWalkRad);
+      CommitDone(w, next, i_done, vec3(rad.x, rad.y, rad.z), pixel);
     }
-    if (to_exit || to_park) {
-      StSlot(w, routed_p, kRng, PackRng(rng));
-      StSlot(w, routed_p, kPix, make_float4(__uint_as_float(pixel), 0.f, 0.f, 0.f));
-    }
-    // ---- (4) new walks: parked ones first, then this iteration's new ones (loaded straight into the walk registers
-    // that (3) has just finished with)
-    const bool take = need && item < n;
+    // ---- (4) new walks: W[cur] front to back, loaded straight into the walk registers that (3) has finished with
+    const bool take = need && next_item < n;
     if (take) {
-      p = SlotOf(item);
-      rng = LoadRng(w, p);
-      pixel = __float_as_uint(LdSlot(w, p, kPix).x);
+      item = next_item;
+      const float4 a = LdW(w, cur, item, kWalkA), b = LdW(w, cur, item, kWalkB), c = LdW(w, cur, item, kWalkC),
+                   d = LdW(w, cur, item, kWalkD), nn = LdW(w, cur, item, kWalkN);
+      rng = RngFrom(LdW(w, cur, item, kWalkRng));
+      walk.sigma_t = vec3(a.x, a.y, a.z);
+      walk.sigma_s = vec3(b.x, b.y, b.z);
+      walk.throughput = vec3(a.w, b.w, c.w);
+      walk.ray.o = vec3(c.x, c.y, c.z);
+      walk.ray.d = vec3(d.x, d.y, d.z);
+      walk.ray.tmin = d.w;
+      walk.ray.tmax = kInf;
+      walk.bounce = __float_as_uint(nn.x);
+      pixel = __float_as_uint(nn.y);
       budget = max_bounces;
-      ResumeWalk(w, p, &walk);
       has_walk = true;
     }
     // ---- (5) next segment: of the walk that goes on, or of the one just taken
     if (take || go_on) StartSegment(t);
-    return need && item >= n;
+    return need && next_item >= n;
   }
   __device__ __forceinline__ void End(const Trav&) {
     WarpTally(&w.stats[kStatSss], rays);
@@ -833,61 +766,69 @@ __global__ void __launch_bounds__(128, 5) SssWalkKernel(SceneView s, WaveState w
 
 // The exit vertex of every walk that left the medium this iteration (random-walk-sss.h:385-404 +
 // cycles-principled-shader.cc:187-216): same-instance / back-face acceptance, NEE at the exit point, diffuse bounce.
-__global__ void __launch_bounds__(kShadeBlock) SssExitKernel(SceneView s, WaveState w, uint32_t next_parity) {
+__global__ void __launch_bounds__(kShadeBlock) SssExitKernel(SceneView s, WaveState w, uint32_t cur_parity,
+                                                             ShadeFlags flags) {
   const uint32_t n = w.counters[kNumExit];
+  const uint32_t next_parity = cur_parity ^ 1u;
   uint32_t shaded = 0;
   for (;;) {
-    const uint32_t slot = BlockFetch(&w.counters[kFetchExit]);
-    if (slot - threadIdx.x >= n) break;   // block-uniform
-    const bool valid = slot < n;
+    const uint32_t e = BlockFetch(&w.counters[kFetchExit]);
+    if (e - threadIdx.x >= n) break;   // block-uniform
+    const bool valid = e < n;
     shaded += valid ? 1u : 0u;
-    uint32_t p = 0;
     bool to_next = false, to_done = false;
     ShadowRequest req;
     req.active = false;
-    vec3 throughput(0.f);
+    vec3 throughput(0.f), L(0.f);
+    VertexResult vr;
+    Pcg32 rng;
+    rng.state = 0; rng.inc = 1;
+    uint32_t depth = 0, pixel = kNoPixel;
     if (valid) {
-      p = w.q_exit[slot];
-      PathRegs r = LoadPath(w, p);   // ray + hit are still those of the ENTRY vertex
-      throughput = r.throughput;
-      const Surface entry_si = MakeSurface(s, r.ray, r.hit);
+      const float4 xh = LdE(w, e, kExHit), xt = LdE(w, e, kExThr), xo = LdE(w, e, kExO), xd = LdE(w, e, kExD);
+      rng = RngFrom(LdE(w, e, kExRng));
+      const uint32_t src = __float_as_uint(xt.w);
+      // the entry vertex and the path state, left in W[cur] by the iteration that started (or last parked) the walk
+      const RayT entry_ray = RayFrom(LdW(w, cur_parity, src, kWalkRayO), LdW(w, cur_parity, src, kWalkRayD));
+      const HitT entry_hit = HitFrom(LdW(w, cur_parity, src, kWalkHit));
+      const float4 t4 = LdW(w, cur_parity, src, kWalkThr), r4 = LdW(w, cur_parity, src, kWalkRad);
+      pixel = __float_as_uint(LdW(w, cur_parity, src, kWalkN).y);
+      throughput = vec3(t4.x, t4.y, t4.z);
+      L = vec3(r4.x, r4.y, r4.z);
+      depth = __float_as_uint(r4.w);
+      const Surface entry_si = MakeSurface(s, entry_ray, entry_hit);
       const Frame entry_frame = PrincipledFrame(entry_si);
-      const float4 a = LdWalk(w, p, kWalkA), b = LdWalk(w, p, kWalkB), c = LdWalk(w, p, kWalkC),
-                   d = LdWalk(w, p, kWalkD);
-      HitT hit;
-      hit.t = a.x; hit.u = a.y; hit.v = a.z; hit.prim = __float_as_uint(a.w);
       SssWalkState walk;
-      walk.throughput = vec3(b.x, b.y, b.z);
-      walk.ray.o = vec3(c.x, c.y, c.z); walk.ray.tmin = c.w;
-      walk.ray.d = vec3(d.x, d.y, d.z); walk.ray.tmax = d.w;
-      VertexResult vr;
+      walk.throughput = vec3(xt.x, xt.y, xt.z);
+      walk.ray = RayFrom(xo, xd);
       vr.P = entry_si.P;
       vr.shadow[1].active = false;
-      SssFinish(s, entry_si, entry_frame, walk, hit, &r.rng, &vr);
+      SssFinish(s, entry_si, entry_frame, walk, HitFrom(xh), &rng, &vr);
       req = vr.shadow[1];
-      CommitVertex(w, p, vr, throughput, r.L, r.depth, r.rng, r.pixel);
-      to_next = !IsBlack(vr.throughput * throughput);
+      to_next = flags.skip_emission_and_roulette ? true : !IsBlack(vr.throughput * throughput);
       to_done = !to_next;
     }
-    PushShadow(w, req, throughput, p);
-    RouteSlot(w, next_parity, p, to_next, to_done);
+    const Routed route = RoutePath(w, next_parity, to_next, to_done);
+    if (to_next) CommitVertex(w, next_parity, route.index, vr, throughput, L, depth, rng, pixel);
+    else if (to_done) CommitDone(w, next_parity, route.index, L, pixel);
+    PushShadow(w, req, throughput, route.target);
   }
   WarpTally(&w.stats[kStatVertices], shaded);
 }
 
 // ------------------------------------------------------------------------------------------------ shadow rays
-// Scene::AnyHit1 for every NEE request; unoccluded contributions are added to their path's radiance.  A path can
-// have two requests in flight in one iteration (entry + SSS exit), hence the atomics (never contended).
+// Scene::AnyHit1 for every NEE request of this iteration; an unoccluded contribution is added to the radiance of its
+// path wherever that path is now (S[next], D[next] or W[next]; the positions are nearly ascending).
 struct ShadowClient {
   const SceneView& s;
   const WaveState& w;
-  uint32_t n;
+  uint32_t n, next;
   float4 c;
   bool has_result = false;
   uint32_t rays = 0;
 
-  __device__ __forceinline__ ShadowClient(const SceneView& s_, const WaveState& w_)
-      : s(s_), w(w_), n(w_.counters[kNumShadow]) {}
+  __device__ __forceinline__ ShadowClient(const SceneView& s_, const WaveState& w_, uint32_t next_parity)
+      : s(s_), w(w_), n(w_.counters[kNumShadow]), next(next_parity) {}
   __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     const unsigned lane = threadIdx.x & 31u;
@@ -898,7 +839,11 @@ struct ShadowClient {
     if (!t.active && has_result) {   // overlaps the fetch round trip
       has_result = false;
       if (t.hit.prim == kInvalid) {
-        float* dst = reinterpret_cast<float*>(&w.slot[size_t(__float_as_uint(c.w)) * kSlotStride + kRad]);
+        const uint32_t code = __float_as_uint(c.w), tag = code >> 30, idx = code & 0x3fffffffu;
+        float4* rec = tag == kTargetState ? &StateBuf(w, next)[size_t(kRad) * w.capacity + idx]
+                                          : (tag == kTargetDone ? &DoneBuf(w, next)[idx]
+                                                                : &WalkBuf(w, next)[size_t(kWalkRad) * w.capacity + idx]);
+        float* dst = reinterpret_cast<float*>(rec);
         atomicAdd(dst + 0, c.x);
         atomicAdd(dst + 1, c.y);
         atomicAdd(dst + 2, c.z);
@@ -909,10 +854,7 @@ struct ShadowClient {
     if (need && slot < n) {
       const float4 o = __ldcs(&w.sh_o[slot]), d = __ldcs(&w.sh_d[slot]);
       c = __ldcs(&w.sh_c[slot]);
-      RayT ray;
-      ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
-      ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
-      TravBegin(s, ray, t);
+      TravBegin(s, RayFrom(o, d), t);
       has_result = true;
       ++rays;
     }
@@ -922,13 +864,41 @@ struct ShadowClient {
 };
 
 template <bool HAS_CURVES>
-__global__ void __launch_bounds__(128) TraceAnyKernel(SceneView s, WaveState w, uint32_t refill_min_idle,
-                                                      uint32_t prim_min_lanes) {
-  ShadowClient client(s, w);
+__global__ void __launch_bounds__(128) TraceAnyKernel(SceneView s, WaveState w, uint32_t next_parity,
+                                                      uint32_t refill_min_idle, uint32_t prim_min_lanes) {
+  ShadowClient client(s, w, next_parity);
   TravEngine<true, HAS_CURVES, false>(s, client, refill_min_idle, prim_min_lanes);
 }
 
 // ------------------------------------------------------------------------------------------------ test hooks
+// pbrgpu_shade: after the single iteration every path sits somewhere in S[p] / D[p] (p = 0, 1); scatter the records
+// back to path order.  out16 layout: see pbrgpu.h (hit flag and face / t columns are filled by the caller).
+__global__ void GatherVertexKernel(WaveState w, uint32_t parity, uint32_t n_paths, float* out16) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_state = w.counters[kNumActive0 + parity], n_done = w.counters[kNumDone0 + parity];
+  if (i < n_state) {
+    const uint32_t pixel = __float_as_uint(LdS(w, parity, i, kPix).x);
+    if (pixel < n_paths) {
+      const float4 o = LdS(w, parity, i, kRayO), d = LdS(w, parity, i, kRayD), t = LdS(w, parity, i, kThr),
+                   r = LdS(w, parity, i, kRad);
+      float* q = out16 + size_t(16) * pixel;
+      q[1] = d.x; q[2] = d.y; q[3] = d.z;
+      q[4] = t.x; q[5] = t.y; q[6] = t.z;
+      q[7] = r.x; q[8] = r.y; q[9] = r.z;
+      q[10] = t.w;
+      q[11] = o.x; q[12] = o.y; q[13] = o.z;
+    }
+  }
+  if (i < n_done) {
+    const float4 r = __ldcs(&DoneBuf(w, parity)[i]);
+    const uint32_t pixel = __float_as_uint(r.w);
+    if (pixel < n_paths) {
+      float* q = out16 + size_t(16) * pixel;
+      q[7] = r.x; q[8] = r.y; q[9] = r.z;
+    }
+  }
+}
+
 // pbrgpu_trace / pbrgpu_occluded: caller-supplied ray batches through the same engine as the render kernels
 struct BatchClient {
   const SceneView& s;
@@ -975,10 +945,7 @@ struct BatchClient {
       if (need) {
         if (slot < n) {
           const float4 o = rays[2 * slot], d = rays[2 * slot + 1];
-          RayT ray;
-          ray.o = vec3(o.x, o.y, o.z); ray.tmin = o.w;
-          ray.d = vec3(d.x, d.y, d.z); ray.tmax = d.w;
-          TravBegin(s, ray, t);
+          TravBegin(s, RayFrom(o, d), t);
           slot_of_result = slot;
           has_result = true;
         } else {
