@@ -102,6 +102,16 @@ __device__ __forceinline__ float4* DoneBuf(const WaveState& w, uint32_t parity) 
 __device__ __forceinline__ float4 LdS(const WaveState& w, uint32_t parity, uint32_t i, int field) {
   return __ldcs(&StateBuf(w, parity)[size_t(field) * w.capacity + i]);
 }
+// Gathers by queue position (shading kernels) and the scattered 16-byte hit stores: the positions a kernel touches at
+// any time lie in a window of a few hundred thousand neighbours, but neighbours in the same 32-byte sector are
+// touched by different warps at different times — with the evict-first hint the sector went back to HBM in between
+// (L2 hit 21 %, 2x the DRAM bytes).  Default policy: the window (tens of MB over all fields) lives in L2.
+__device__ __forceinline__ float4 LdSGather(const WaveState& w, uint32_t parity, uint32_t i, int field) {
+  return __ldg(&StateBuf(w, parity)[size_t(field) * w.capacity + i]);
+}
+__device__ __forceinline__ void StSScatter(const WaveState& w, uint32_t parity, uint32_t i, int field, const float4& v) {
+  StateBuf(w, parity)[size_t(field) * w.capacity + i] = v;
+}
 __device__ __forceinline__ void StS(const WaveState& w, uint32_t parity, uint32_t i, int field, const float4& v) {
   __stcs(&StateBuf(w, parity)[size_t(field) * w.capacity + i], v);
 }
@@ -177,6 +187,54 @@ __device__ __forceinline__ uint32_t BlockFetch(uint32_t* fetch_counter) {
   return s_base + threadIdx.x;
 }
 
+// The shading kernels append to up to four output streams per batch and then fetch the next batch.  As one atomic per
+// warp and stream these were 4-5 dependent round trips per batch to counters that every warp of the GPU hammers:
+// 67 % of the diffuse kernel's stall samples were waits for atomic results (profiles/r2c_ncu.md).  Here a BLOCK
+// reserves all of it with ONE atomic instruction per batch: the warps leave their ballot counts in shared memory,
+// lanes 0..4 of warp 0 add the column totals to the four counters and the fetch counter (five addresses, served in
+// parallel), and every thread computes its positions from the bases and its warp's offsets.
+struct BlockSlots {
+  uint32_t idx[4];       // position of this thread's record in stream q (valid if its predicate q was set)
+  uint32_t next_fetch;   // first queue entry of the block's next batch
+};
+__device__ __forceinline__ BlockSlots BlockReserve(uint32_t* c0, uint32_t* c1, uint32_t* c2, uint32_t* c3,
+                                                   uint32_t* fetch_counter, bool p0, bool p1, bool p2, bool p3) {
+  __shared__ uint32_t s_cnt[kShadeBlock / 32][4];
+  __shared__ uint32_t s_base[5];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1),
+                 m2 = __ballot_sync(0xffffffffu, p2), m3 = __ballot_sync(0xffffffffu, p3);
+  if (lane == 0u) {
+    s_cnt[warp][0] = uint32_t(__popc(m0)); s_cnt[warp][1] = uint32_t(__popc(m1));
+    s_cnt[warp][2] = uint32_t(__popc(m2)); s_cnt[warp][3] = uint32_t(__popc(m3));
+  }
+  __syncthreads();
+  if (warp == 0u) {
+    if (lane < 4u) {
+      uint32_t acc = 0;
+      for (unsigned k = 0; k < nwarps; ++k) {
+        const uint32_t c = s_cnt[k][lane];
+        s_cnt[k][lane] = acc;   // exclusive offset of warp k in stream `lane`
+        acc += c;
+      }
+      uint32_t* ctr = lane == 0u ? c0 : (lane == 1u ? c1 : (lane == 2u ? c2 : c3));
+      s_base[lane] = (acc && ctr) ? atomicAdd(ctr, acc) : 0u;
+    } else if (lane == 4u) {
+      s_base[4] = atomicAdd(fetch_counter, blockDim.x);
+    }
+  }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  BlockSlots r;
+  r.idx[0] = s_base[0] + s_cnt[warp][0] + uint32_t(__popc(m0 & lt));
+  r.idx[1] = s_base[1] + s_cnt[warp][1] + uint32_t(__popc(m1 & lt));
+  r.idx[2] = s_base[2] + s_cnt[warp][2] + uint32_t(__popc(m2 & lt));
+  r.idx[3] = s_base[3] + s_cnt[warp][3] + uint32_t(__popc(m3 & lt));
+  r.next_fetch = s_base[4];
+  __syncwarp();   // lane 0 overwrites this warp's row in the next batch
+  return r;
+}
+
 __device__ __forceinline__ RayT RayFrom(const float4& o, const float4& d) {
   RayT r;
   r.o = vec3(o.x, o.y, o.z); r.tmin = o.w;
@@ -221,6 +279,15 @@ __device__ __forceinline__ void PushShadow(const WaveState& w, const ShadowReque
     __stcs(&w.sh_d[slot], make_float4(req.ray.d.x, req.ray.d.y, req.ray.d.z, req.ray.tmax));
     __stcs(&w.sh_c[slot], make_float4(c.x, c.y, c.z, __uint_as_float(target)));
   }
+}
+
+// the same with a position reserved by BlockReserve
+__device__ __forceinline__ void StoreShadow(const WaveState& w, uint32_t slot, const ShadowRequest& req,
+                                            const vec3& throughput, uint32_t target) {
+  const vec3 c = throughput * req.contribute;
+  __stcs(&w.sh_o[slot], make_float4(req.ray.o.x, req.ray.o.y, req.ray.o.z, req.ray.tmin));
+  __stcs(&w.sh_d[slot], make_float4(req.ray.d.x, req.ray.d.y, req.ray.d.z, req.ray.tmax));
+  __stcs(&w.sh_c[slot], make_float4(c.x, c.y, c.z, __uint_as_float(target)));
 }
 
 // where a path goes after its vertex: S[next] (it continues) or D[next] (it ended); returns the NEE target
@@ -415,7 +482,7 @@ struct ClosestClient {
     }
     // ---- (4) write out the finished rays
     if (kind > 0) {
-      StS(w, cur, done_item, kHit, PackHit(hit));
+      StSScatter(w, cur, done_item, kHit, PackHit(hit));
       if (kind == 1) w.q_surface[i_surf] = done_item;
       else if (kind == 2) w.q_hair[i_hair] = done_item;
       else w.q_diffuse[i_diff] = done_item;
@@ -479,9 +546,9 @@ struct PathRegs {
 };
 
 __device__ __forceinline__ PathRegs LoadPath(const WaveState& w, uint32_t parity, uint32_t i) {
-  const float4 o = LdS(w, parity, i, kRayO), d = LdS(w, parity, i, kRayD), t4 = LdS(w, parity, i, kThr),
-               r4 = LdS(w, parity, i, kRad), h4 = LdS(w, parity, i, kHit), g4 = LdS(w, parity, i, kRng),
-               x4 = LdS(w, parity, i, kPix);
+  const float4 o = LdSGather(w, parity, i, kRayO), d = LdSGather(w, parity, i, kRayD), t4 = LdSGather(w, parity, i, kThr),
+               r4 = LdSGather(w, parity, i, kRad), h4 = LdSGather(w, parity, i, kHit), g4 = LdSGather(w, parity, i, kRng),
+               x4 = LdSGather(w, parity, i, kPix);
   PathRegs r;
   r.ray = RayFrom(o, d);
   r.hit = HitFrom(h4);
@@ -524,64 +591,70 @@ __device__ __forceinline__ void StoreWalkHot(const WaveState& w, uint32_t parity
   StW(w, parity, k, kWalkRng, PackRng(rng));
 }
 
-// One Principled vertex (render.cc:33-86 + shader.cc:8-34) of a path of S[cur] whose state is in r; called by every
-// lane of a warp (lanes without an item pass valid = false): the queue appends are warp collectives.
-template <bool DIFFUSE_ONLY>
-__device__ __forceinline__ void ShadeSurfaceItem(const SceneView& s, const WaveState& w, uint32_t next_parity,
-                                                 const ShadeFlags& flags, bool valid, PathRegs& r) {
-  bool to_sss = false, to_next = false, to_done = false;
+// What a vertex decided; the kernel then reserves the output positions for the whole block and commits.
+struct VertexOutcome {
+  bool to_next = false, to_done = false, to_sss = false;
   ShadowRequest req;
-  req.active = false;
-  vec3 throughput(0.f), L(0.f);
+  vec3 throughput, L;
   VertexResult vr;
   SssWalkState walk;
-  if (valid) {
-    throughput = r.throughput;
-    L = r.L;
-    const Surface si = MakeSurface(s, r.ray, r.hit);
-    bool alive = true;
-    if (!flags.skip_emission_and_roulette)
-      alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &L, &throughput);
-    if (!alive) {
-      to_done = true;
-    } else {
-      const int kind = DIFFUSE_ONLY ? 1 : MaterialKind(s, si);
-      const vec3 wo = -r.ray.d;
-      Frame fr;
-      PrincipledBsdf bsdf;
-      bool sss = false;
-      if (kind == 1) sss = PrincipledVertexT<DIFFUSE_ONLY>(s, si, wo, &r.rng, &vr, &fr, &bsdf);
-      else AbsorbVertex(wo, si.P, &vr);   // no material (shader.cc:11-17)
-      req = vr.shadow[0];
-      if (!DIFFUSE_ONLY && sss) {
-        // the walk runs in its own kernel; rejected: throughput 0, the path ends (cycles-principled-shader.cc:217-220)
-        if (SssBegin(si, fr, bsdf, &r.rng, &walk)) to_sss = true;
-        else to_done = true;
-      } else {
-        to_next = flags.skip_emission_and_roulette ? true : !IsBlack(vr.throughput * throughput);   // render.cc:31
-        to_done = !to_next;
-      }
-    }
+};
+
+// One Principled vertex (render.cc:33-86 + shader.cc:8-34) of a path of S[cur] whose state is in r.
+template <bool DIFFUSE_ONLY>
+__device__ __forceinline__ void ShadeSurfaceVertex(const SceneView& s, const ShadeFlags& flags, PathRegs& r,
+                                                   VertexOutcome& o) {
+  o.throughput = r.throughput;
+  o.L = r.L;
+  const Surface si = MakeSurface(s, r.ray, r.hit);
+  bool alive = true;
+  if (!flags.skip_emission_and_roulette)
+    alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &o.L, &o.throughput);
+  if (!alive) {
+    o.to_done = true;
+    return;
   }
-  const Routed route = RoutePath(w, next_parity, to_next, to_done);
-  uint32_t target = route.target;
-  if (to_next) CommitVertex(w, next_parity, route.index, vr, throughput, L, r.depth, r.rng, r.pixel);
-  else if (to_done) CommitDone(w, next_parity, route.index, L, r.pixel);
-  if (!DIFFUSE_ONLY) {
-    const uint32_t k = WarpAppend(&w.counters[kNumWalk0 + next_parity], to_sss);
-    if (to_sss) {
-      // the walk, the entry vertex (ray + hit: the exit vertex rebuilds the entry surface from them) and the path it
-      // resumes with (post-roulette throughput)
-      StoreWalkHot(w, next_parity, k, walk, r.rng, r.pixel);
-      StW(w, next_parity, k, kWalkRayO, make_float4(r.ray.o.x, r.ray.o.y, r.ray.o.z, r.ray.tmin));
-      StW(w, next_parity, k, kWalkRayD, make_float4(r.ray.d.x, r.ray.d.y, r.ray.d.z, r.ray.tmax));
-      StW(w, next_parity, k, kWalkHit, PackHit(r.hit));
-      StW(w, next_parity, k, kWalkThr, make_float4(throughput.x, throughput.y, throughput.z, r.pdf_prev));
-      StW(w, next_parity, k, kWalkRad, make_float4(L.x, L.y, L.z, __uint_as_float(r.depth)));
-      target = MakeTarget(kTargetWalk, k);
-    }
+  const int kind = DIFFUSE_ONLY ? 1 : MaterialKind(s, si);
+  const vec3 wo = -r.ray.d;
+  Frame fr;
+  PrincipledBsdf bsdf;
+  bool sss = false;
+  if (kind == 1) sss = PrincipledVertexT<DIFFUSE_ONLY>(s, si, wo, &r.rng, &o.vr, &fr, &bsdf);
+  else AbsorbVertex(wo, si.P, &o.vr);   // no material (shader.cc:11-17)
+  o.req = o.vr.shadow[0];
+  if (!DIFFUSE_ONLY && sss) {
+    // the walk runs in its own kernel; rejected: throughput 0, the path ends (cycles-principled-shader.cc:217-220)
+    if (SssBegin(si, fr, bsdf, &r.rng, &o.walk)) o.to_sss = true;
+    else o.to_done = true;
+  } else {
+    o.to_next = flags.skip_emission_and_roulette ? true : !IsBlack(o.vr.throughput * o.throughput);   // render.cc:31
+    o.to_done = !o.to_next;
   }
-  PushShadow(w, req, throughput, target);
+}
+
+// writes the outcome of a vertex to the positions BlockReserve handed out: S[next] / D[next] / W[next] + shadow queue
+__device__ __forceinline__ void CommitOutcome(const WaveState& w, uint32_t next_parity, const BlockSlots& slots,
+                                              const VertexOutcome& o, const PathRegs& r, bool shadow) {
+  uint32_t target = MakeTarget(kTargetNone, 0u);
+  if (o.to_next) {
+    CommitVertex(w, next_parity, slots.idx[0], o.vr, o.throughput, o.L, r.depth, r.rng, r.pixel);
+    target = MakeTarget(kTargetState, slots.idx[0]);
+  } else if (o.to_done) {
+    CommitDone(w, next_parity, slots.idx[1], o.L, r.pixel);
+    target = MakeTarget(kTargetDone, slots.idx[1]);
+  } else if (o.to_sss) {
+    // the walk, the entry vertex (ray + hit: the exit vertex rebuilds the entry surface from them) and the path it
+    // resumes with (post-roulette throughput)
+    const uint32_t k = slots.idx[2];
+    StoreWalkHot(w, next_parity, k, o.walk, r.rng, r.pixel);
+    StW(w, next_parity, k, kWalkRayO, make_float4(r.ray.o.x, r.ray.o.y, r.ray.o.z, r.ray.tmin));
+    StW(w, next_parity, k, kWalkRayD, make_float4(r.ray.d.x, r.ray.d.y, r.ray.d.z, r.ray.tmax));
+    StW(w, next_parity, k, kWalkHit, PackHit(r.hit));
+    StW(w, next_parity, k, kWalkThr, make_float4(o.throughput.x, o.throughput.y, o.throughput.z, r.pdf_prev));
+    StW(w, next_parity, k, kWalkRad, make_float4(o.L.x, o.L.y, o.L.z, __uint_as_float(r.depth)));
+    target = MakeTarget(kTargetWalk, k);
+  }
+  if (shadow) StoreShadow(w, slots.idx[3], o.req, o.throughput, target);
 }
 
 // Launch shapes: the general kernel needs ~110-128 registers, so one 512-thread block per SM; the diffuse-only kernel is
@@ -592,15 +665,27 @@ __global__ void __launch_bounds__(DIFFUSE_ONLY ? kDiffuseBlock : kShadeBlock, DI
 ShadeSurfaceKernel(SceneView s, WaveState w, uint32_t cur_parity, ShadeFlags flags) {
   const uint32_t n = w.counters[DIFFUSE_ONLY ? kNumDiffuse : kNumSurface];
   const uint32_t* __restrict__ queue = DIFFUSE_ONLY ? w.q_diffuse : w.q_surface;
+  uint32_t* fetch = &w.counters[DIFFUSE_ONLY ? kFetchDiffuse : kFetchSurface];
+  const uint32_t next_parity = cur_parity ^ 1u;
   uint32_t shaded = 0;
-  for (;;) {
-    const uint32_t slot = BlockFetch(&w.counters[DIFFUSE_ONLY ? kFetchDiffuse : kFetchSurface]);
-    if (slot - threadIdx.x >= n) break;   // block-uniform
+  uint32_t base = BlockFetch(fetch) - threadIdx.x;
+  while (base < n) {   // block-uniform
+    const uint32_t slot = base + threadIdx.x;
     const bool valid = slot < n;
     shaded += valid ? 1u : 0u;
     PathRegs r;
-    if (valid) r = LoadPath(w, cur_parity, queue[slot]);
-    ShadeSurfaceItem<DIFFUSE_ONLY>(s, w, cur_parity ^ 1u, flags, valid, r);
+    VertexOutcome o;
+    o.req.active = false;
+    if (valid) {
+      r = LoadPath(w, cur_parity, queue[slot]);
+      ShadeSurfaceVertex<DIFFUSE_ONLY>(s, flags, r, o);
+    }
+    const bool shadow = valid && o.req.active && (o.to_next || o.to_done || o.to_sss);
+    const BlockSlots slots = BlockReserve(&w.counters[kNumActive0 + next_parity], &w.counters[kNumDone0 + next_parity],
+                                          DIFFUSE_ONLY ? nullptr : &w.counters[kNumWalk0 + next_parity],
+                                          &w.counters[kNumShadow], fetch, o.to_next, o.to_done, o.to_sss, shadow);
+    if (valid) CommitOutcome(w, next_parity, slots, o, r, shadow);
+    base = slots.next_fetch;
   }
   WarpTally(&w.stats[kStatVertices], shaded);
 }
@@ -610,38 +695,37 @@ __global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, Wave
   const uint32_t n = w.counters[kNumHair];
   const uint32_t next_parity = cur_parity ^ 1u;
   uint32_t shaded = 0;
-  for (;;) {
-    const uint32_t slot = BlockFetch(&w.counters[kFetchHair]);
-    if (slot - threadIdx.x >= n) break;   // block-uniform
+  uint32_t base = BlockFetch(&w.counters[kFetchHair]) - threadIdx.x;
+  while (base < n) {   // block-uniform
+    const uint32_t slot = base + threadIdx.x;
     const bool valid = slot < n;
     shaded += valid ? 1u : 0u;
-    bool to_next = false, to_done = false;
-    ShadowRequest req;
-    req.active = false;
-    vec3 throughput(0.f), L(0.f);
-    VertexResult vr;
     PathRegs r;
+    VertexOutcome o;
+    o.req.active = false;
     if (valid) {
       r = LoadPath(w, cur_parity, w.q_hair[slot]);
-      throughput = r.throughput;
-      L = r.L;
+      o.throughput = r.throughput;
+      o.L = r.L;
       const Surface si = MakeSurface(s, r.ray, r.hit);
       bool alive = true;
       if (!flags.skip_emission_and_roulette)
-        alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &L, &throughput);
+        alive = EmissionAndRoulette(s, r.ray, r.hit, si, r.depth, r.pdf_prev, &r.rng, &o.L, &o.throughput);
       if (!alive) {
-        to_done = true;
+        o.to_done = true;
       } else {
-        HairVertex(s, si, -r.ray.d, &r.rng, &vr);
-        req = vr.shadow[0];
-        to_next = flags.skip_emission_and_roulette ? true : !IsBlack(vr.throughput * throughput);
-        to_done = !to_next;
+        HairVertex(s, si, -r.ray.d, &r.rng, &o.vr);
+        o.req = o.vr.shadow[0];
+        o.to_next = flags.skip_emission_and_roulette ? true : !IsBlack(o.vr.throughput * o.throughput);
+        o.to_done = !o.to_next;
       }
     }
-    const Routed route = RoutePath(w, next_parity, to_next, to_done);
-    if (to_next) CommitVertex(w, next_parity, route.index, vr, throughput, L, r.depth, r.rng, r.pixel);
-    else if (to_done) CommitDone(w, next_parity, route.index, L, r.pixel);
-    PushShadow(w, req, throughput, route.target);
+    const bool shadow = valid && o.req.active;
+    const BlockSlots slots = BlockReserve(&w.counters[kNumActive0 + next_parity], &w.counters[kNumDone0 + next_parity],
+                                          nullptr, &w.counters[kNumShadow], &w.counters[kFetchHair], o.to_next,
+                                          o.to_done, false, shadow);
+    if (valid) CommitOutcome(w, next_parity, slots, o, r, shadow);
+    base = slots.next_fetch;
   }
   WarpTally(&w.stats[kStatVertices], shaded);
 }
@@ -771,47 +855,44 @@ __global__ void __launch_bounds__(kShadeBlock) SssExitKernel(SceneView s, WaveSt
   const uint32_t n = w.counters[kNumExit];
   const uint32_t next_parity = cur_parity ^ 1u;
   uint32_t shaded = 0;
-  for (;;) {
-    const uint32_t e = BlockFetch(&w.counters[kFetchExit]);
-    if (e - threadIdx.x >= n) break;   // block-uniform
+  uint32_t base = BlockFetch(&w.counters[kFetchExit]) - threadIdx.x;
+  while (base < n) {   // block-uniform
+    const uint32_t e = base + threadIdx.x;
     const bool valid = e < n;
     shaded += valid ? 1u : 0u;
-    bool to_next = false, to_done = false;
-    ShadowRequest req;
-    req.active = false;
-    vec3 throughput(0.f), L(0.f);
-    VertexResult vr;
-    Pcg32 rng;
-    rng.state = 0; rng.inc = 1;
-    uint32_t depth = 0, pixel = kNoPixel;
+    PathRegs r;          // the path as it resumes: depth, pixel, rng (ray / hit unused)
+    VertexOutcome o;
+    o.req.active = false;
     if (valid) {
       const float4 xh = LdE(w, e, kExHit), xt = LdE(w, e, kExThr), xo = LdE(w, e, kExO), xd = LdE(w, e, kExD);
-      rng = RngFrom(LdE(w, e, kExRng));
+      r.rng = RngFrom(LdE(w, e, kExRng));
       const uint32_t src = __float_as_uint(xt.w);
       // the entry vertex and the path state, left in W[cur] by the iteration that started (or last parked) the walk
       const RayT entry_ray = RayFrom(LdW(w, cur_parity, src, kWalkRayO), LdW(w, cur_parity, src, kWalkRayD));
       const HitT entry_hit = HitFrom(LdW(w, cur_parity, src, kWalkHit));
       const float4 t4 = LdW(w, cur_parity, src, kWalkThr), r4 = LdW(w, cur_parity, src, kWalkRad);
-      pixel = __float_as_uint(LdW(w, cur_parity, src, kWalkN).y);
-      throughput = vec3(t4.x, t4.y, t4.z);
-      L = vec3(r4.x, r4.y, r4.z);
-      depth = __float_as_uint(r4.w);
+      r.pixel = __float_as_uint(LdW(w, cur_parity, src, kWalkN).y);
+      r.depth = __float_as_uint(r4.w);
+      o.throughput = vec3(t4.x, t4.y, t4.z);
+      o.L = vec3(r4.x, r4.y, r4.z);
       const Surface entry_si = MakeSurface(s, entry_ray, entry_hit);
       const Frame entry_frame = PrincipledFrame(entry_si);
       SssWalkState walk;
       walk.throughput = vec3(xt.x, xt.y, xt.z);
       walk.ray = RayFrom(xo, xd);
-      vr.P = entry_si.P;
-      vr.shadow[1].active = false;
-      SssFinish(s, entry_si, entry_frame, walk, HitFrom(xh), &rng, &vr);
-      req = vr.shadow[1];
-      to_next = flags.skip_emission_and_roulette ? true : !IsBlack(vr.throughput * throughput);
-      to_done = !to_next;
+      o.vr.P = entry_si.P;
+      o.vr.shadow[1].active = false;
+      SssFinish(s, entry_si, entry_frame, walk, HitFrom(xh), &r.rng, &o.vr);
+      o.req = o.vr.shadow[1];
+      o.to_next = flags.skip_emission_and_roulette ? true : !IsBlack(o.vr.throughput * o.throughput);
+      o.to_done = !o.to_next;
     }
-    const Routed route = RoutePath(w, next_parity, to_next, to_done);
-    if (to_next) CommitVertex(w, next_parity, route.index, vr, throughput, L, depth, rng, pixel);
-    else if (to_done) CommitDone(w, next_parity, route.index, L, pixel);
-    PushShadow(w, req, throughput, route.target);
+    const bool shadow = valid && o.req.active;
+    const BlockSlots slots = BlockReserve(&w.counters[kNumActive0 + next_parity], &w.counters[kNumDone0 + next_parity],
+                                          nullptr, &w.counters[kNumShadow], &w.counters[kFetchExit], o.to_next,
+                                          o.to_done, false, shadow);
+    if (valid) CommitOutcome(w, next_parity, slots, o, r, shadow);
+    base = slots.next_fetch;
   }
   WarpTally(&w.stats[kStatVertices], shaded);
 }
