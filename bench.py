@@ -261,7 +261,8 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, spp_overrid
     t0 = time.time()
     scene = pb.Scene(files, device_ids=[local_rank])
     ctx = scene.context()
-    commit_s = time.time() - t0
+    load_s = time.time() - t0          # parse + flatten + upload + commit
+    commit = ctx.commit_info()
     if world > 1:
         # the library's own multi-process split + NCCL reduce; the 128-byte id travels by the launcher's process group
         ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -390,7 +391,8 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, spp_overrid
                        "split": ("one frame, interleaved samples over %d GPUs, scene replicated, one in-library "
                                  "ncclReduce of the float4 sums per frame" % world) if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: the path pool (GBs of slot lines) streams through every iteration between two visits of a slot",
-                       "triangles": ntris, "curve_segments": nsegs, "scene_commit_s": commit_s, "seed": seed,
+                       "triangles": ntris, "curve_segments": nsegs, "scene_load_s": load_s,
+                       "scene_commit_s": commit["commit_s"], "scene_commit": commit, "seed": seed,
                        "wavefront_iterations_per_step": int(ps["iterations"])},
             "roofline": roof, "roofline_families": fams,
         }

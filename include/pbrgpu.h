@@ -142,6 +142,14 @@ int pbrgpu_set_textures(pbrgpu_ctx* ctx, const pbrgpu_texture* textures, uint32_
  * geometry (triangle vertices in use; curve bounds as Embree's accurateFlatBounds). */
 int pbrgpu_commit(pbrgpu_ctx* ctx, const float* bmin, const float* bmax);
 int pbrgpu_scene_bounds(const pbrgpu_ctx* ctx, float* bmin, float* bmax);
+/* What the last pbrgpu_commit() did: wall seconds in total and of its parts (acceleration-structure build of both BVHs
+ * incl. transfers, clearance field of the subsurface meshes, upload of all tables to the devices), and which builder
+ * made the triangle BVH: 0 = host binned SAH, 1 = PLOC on the host, 2 = PLOC on the device. */
+typedef struct pbrgpu_commit_info {
+  double commit_s, bvh_s, clearance_s, upload_s;
+  uint32_t tri_builder, tri_nodes, curve_nodes, tri_depth;
+} pbrgpu_commit_info;
+int pbrgpu_get_commit_info(const pbrgpu_ctx* ctx, pbrgpu_commit_info* out);
 
 /* ---- rendering: the body of pbrlab::Render().  Blocking.  Accumulates SUMS exactly like RenderLayer:
  *   rgba_out [w*h*4] += (L.r, L.g, L.b, 1) per sample, count_out [w*h] += 1 per sample (both are overwritten,

@@ -49,6 +49,11 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CommitInfo(C.Structure):
+    _fields_ = [("commit_s", C.c_double), ("bvh_s", C.c_double), ("clearance_s", C.c_double), ("upload_s", C.c_double),
+                ("tri_builder", C.c_uint32), ("tri_nodes", C.c_uint32), ("curve_nodes", C.c_uint32), ("tri_depth", C.c_uint32)]
+
+
 class Flat(C.Structure):
     _fields_ = [("verts", C.c_void_p), ("nverts", C.c_uint32), ("normals", C.c_void_p), ("nnormals", C.c_uint32),
                 ("texcoords", C.c_void_p), ("ntexcoords", C.c_uint32),
@@ -206,7 +211,7 @@ def gpu_lib():
                      "pbrgpu_get_stats", "pbrgpu_set_wave_spp", "pbrgpu_set_profiling", "pbrgpu_trace", "pbrgpu_occluded",
                      "pbrgpu_trace_device", "pbrgpu_occluded_device", "pbrgpu_radiance", "pbrgpu_radiance_mega",
                      "pbrgpu_shade", "pbrgpu_eval_closure", "pbrgpu_measure_gather", "pbrgpu_nccl_unique_id",
-                     "pbrgpu_nccl_init", "pbrgpu_job_rank"):
+                     "pbrgpu_nccl_init", "pbrgpu_job_rank", "pbrgpu_get_commit_info"):
             getattr(L, name).restype = C.c_int
         _gpu = L
     return _gpu
@@ -295,6 +300,14 @@ class Context:
         a = np.zeros(3, np.float32); b = np.zeros(3, np.float32)
         self._check(self.lib.pbrgpu_scene_bounds(self.h, _p(a), _p(b)))
         return a, b
+
+    def commit_info(self):
+        """pbrgpu_get_commit_info: seconds of the last commit and of its parts, and which builder made the triangle BVH"""
+        ci = CommitInfo()
+        self._check(self.lib.pbrgpu_get_commit_info(self.h, C.byref(ci)))
+        d = {k: getattr(ci, k) for k, _ in ci._fields_}
+        d["tri_builder"] = ["sah (host)", "ploc (host)", "ploc (device)"][min(2, d["tri_builder"])]
+        return d
 
     def stats(self):
         s = Stats()

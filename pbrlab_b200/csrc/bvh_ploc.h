@@ -120,23 +120,23 @@ PLOC_HD void NearestBody(const F4* clo, const F4* chi, uint32_t m, uint32_t radi
 }
 
 // create[i] = 1: cluster i is the lower member of a mutual pair (allocates the new node); keep[i] = 0: the upper member
-PLOC_HD void PairFlagsBody(const uint32_t* nn, uint32_t i, uint32_t* create, uint32_t* keep) {
+PLOC_HD void PairFlagsBody(const uint32_t* nn, uint32_t i, uint32_t* create_i, uint32_t* keep_i) {
   const uint32_t j = nn[i];
   const bool mutual = (j != i) && (nn[j] == i);
-  create[i] = (mutual && i < j) ? 1u : 0u;
-  keep[i] = (mutual && i > j) ? 0u : 1u;
+  *create_i = (mutual && i < j) ? 1u : 0u;
+  *keep_i = (mutual && i > j) ? 0u : 1u;
 }
 
-// scan_create / scan_keep: exclusive prefix sums of the flags
-PLOC_HD void MergeBody(const uint32_t* nn, const uint32_t* create, const uint32_t* keep, const uint32_t* scan_create,
-                       const uint32_t* scan_keep, uint32_t first_new_node, const uint32_t* cnode, const F4* clo,
+// create_i / keep_i: the flags of element i; scan_create_i / scan_keep_i: their exclusive prefix sums
+PLOC_HD void MergeBody(const uint32_t* nn, uint32_t create_i, uint32_t keep_i, uint32_t scan_create_i,
+                       uint32_t scan_keep_i, uint32_t first_new_node, const uint32_t* cnode, const F4* clo,
                        const F4* chi, uint32_t i, F4* nlo, F4* nhi, uint32_t* ncount, uint32_t* cnode_out, F4* clo_out,
                        F4* chi_out) {
-  if (!keep[i]) return;
-  const uint32_t dst = scan_keep[i];
-  if (create[i]) {
+  if (!keep_i) return;
+  const uint32_t dst = scan_keep_i;
+  if (create_i) {
     const uint32_t j = nn[i];
-    const uint32_t id = first_new_node + scan_create[i];
+    const uint32_t id = first_new_node + scan_create_i;
     const F4 a0 = clo[i], a1 = chi[i], b0 = clo[j], b1 = chi[j];
     F4 lo = {Min2(a0.x, b0.x), Min2(a0.y, b0.y), Min2(a0.z, b0.z), BFloat(cnode[i])};
     F4 hi = {Max2(a1.x, b1.x), Max2(a1.y, b1.y), Max2(a1.z, b1.z), BFloat(cnode[j])};
@@ -203,15 +203,15 @@ PLOC_HD WideChildren GatherChildren(const F4* nlo, const F4* nhi, const uint32_t
 }
 
 PLOC_HD void WideCountBody(const F4* nlo, const F4* nhi, const uint32_t* ncount, const uint32_t* wide_item,
-                           uint32_t level_begin, uint32_t t, uint32_t max_leaf, uint32_t* n_inner, uint32_t* n_prims) {
+                           uint32_t level_begin, uint32_t t, uint32_t max_leaf, uint32_t* n_inner_t, uint32_t* n_prims_t) {
   const WideChildren c = GatherChildren(nlo, nhi, ncount, wide_item[level_begin + t], max_leaf);
   uint32_t ni = 0, np = 0;
   for (int i = 0; i < c.n; ++i) {
     if (IsWideLeaf(ncount, c.node[i], max_leaf)) np += ncount[c.node[i]];
     else ++ni;
   }
-  n_inner[t] = ni;
-  n_prims[t] = np;
+  *n_inner_t = ni;
+  *n_prims_t = np;
 }
 
 // primitives of a leaf subtree (<= 3 of them), left to right
@@ -234,7 +234,7 @@ PLOC_HD uint32_t LeafPrims(const F4* nlo, const F4* nhi, uint32_t node, uint32_t
 // writes wide node (level_begin + t): 20 words, see bvh_builder.h for the layout
 PLOC_HD void WideEmitBody(const F4* nlo, const F4* nhi, const uint32_t* ncount, uint32_t* wide_item,
                           uint32_t level_begin, uint32_t level_end, uint32_t t, uint32_t max_leaf,
-                          const uint32_t* scan_inner, const uint32_t* scan_prims, uint32_t prim_total,
+                          uint32_t scan_inner_t, uint32_t scan_prims_t, uint32_t prim_total,
                           uint32_t* nodes_out, uint32_t* prim_order) {
   const uint32_t self = wide_item[level_begin + t];
   const WideChildren c = GatherChildren(nlo, nhi, ncount, self, max_leaf);
@@ -287,8 +287,8 @@ PLOC_HD void WideEmitBody(const F4* nlo, const F4* nhi, const uint32_t* ncount, 
   uint32_t meta[8], q[6][8];
   for (int s = 0; s < 8; ++s) { meta[s] = 0; for (int k = 0; k < 6; ++k) q[k][s] = 0; }
   uint32_t imask = 0;
-  const uint32_t child_base = level_end + scan_inner[t];
-  const uint32_t prim_base = prim_total + scan_prims[t];
+  const uint32_t child_base = level_end + scan_inner_t;
+  const uint32_t prim_base = prim_total + scan_prims_t;
   uint32_t n_inner = 0, n_prims = 0;
   for (int s = 0; s < 8; ++s) {
     const int k = child_in_slot[s];
@@ -375,11 +375,11 @@ inline bool BuildBvh8PlocHost(const pbrbvh::Aabb* prim, uint32_t n, const pbrbvh
   int cur = 0;
   while (m > 1) {
     for (uint32_t i = 0; i < m; ++i) NearestBody(clo[cur].data(), chi[cur].data(), m, radius, i, nn.data());
-    for (uint32_t i = 0; i < m; ++i) PairFlagsBody(nn.data(), i, create.data(), keep.data());
+    for (uint32_t i = 0; i < m; ++i) PairFlagsBody(nn.data(), i, &create[i], &keep[i]);
     uint32_t a = 0, b = 0;
     for (uint32_t i = 0; i < m; ++i) { sc[i] = a; a += create[i]; sk[i] = b; b += keep[i]; }
     for (uint32_t i = 0; i < m; ++i)
-      MergeBody(nn.data(), create.data(), keep.data(), sc.data(), sk.data(), next_node, cnode[cur].data(), clo[cur].data(),
+      MergeBody(nn.data(), create[i], keep[i], sc[i], sk[i], next_node, cnode[cur].data(), clo[cur].data(),
                 chi[cur].data(), i, nlo.data(), nhi.data(), ncount.data(), cnode[cur ^ 1].data(), clo[cur ^ 1].data(),
                 chi[cur ^ 1].data());
     next_node += a;
@@ -399,11 +399,11 @@ inline bool BuildBvh8PlocHost(const pbrbvh::Aabb* prim, uint32_t n, const pbrbvh
     const uint32_t cnt = le - lb;
     ci.resize(cnt); cp.resize(cnt); si.resize(cnt); sp.resize(cnt);
     for (uint32_t t = 0; t < cnt; ++t)
-      WideCountBody(nlo.data(), nhi.data(), ncount.data(), wide_item.data(), lb, t, max_leaf, ci.data(), cp.data());
+      WideCountBody(nlo.data(), nhi.data(), ncount.data(), wide_item.data(), lb, t, max_leaf, &ci[t], &cp[t]);
     uint32_t a = 0, b = 0;
     for (uint32_t t = 0; t < cnt; ++t) { si[t] = a; a += ci[t]; sp[t] = b; b += cp[t]; }
     for (uint32_t t = 0; t < cnt; ++t)
-      WideEmitBody(nlo.data(), nhi.data(), ncount.data(), wide_item.data(), lb, le, t, max_leaf, si.data(), sp.data(),
+      WideEmitBody(nlo.data(), nhi.data(), ncount.data(), wide_item.data(), lb, le, t, max_leaf, si[t], sp[t],
                    prim_total, out->nodes.data(), out->prim_order.data());
     prim_total += b;
     lb = le;

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/pbrgpu.h"
+#include "bvh_device.cuh"
 #include "job_split.h"
 #include "kat.cuh"
 #include "nccl_shim.h"
@@ -141,6 +142,7 @@ struct pbrgpu_ctx {
   pbrgpu_stats stats;
   uint32_t wave_spp = 0;
   bool committed = false;
+  pbrgpu_commit_info commit_info;
   bool profile = false;   // time every kernel family with CUDA events (pbrgpu_set_profiling)
   // launch tuning (defaults measured on B200; PBRGPU_* environment variables override for sweeps)
   uint32_t tune_refill = 16;       // idle lanes that trigger a refill in the traversal engine
@@ -787,17 +789,55 @@ int pbrgpu_set_lights(pbrgpu_ctx* ctx, const pbrgpu_light_tables* tables) {
   return PBRGPU_OK;
 }
 
+// HostScene::DeviceBuilder: the acceleration-structure build on the context's first device (bvh_device.cuh)
+static bool DeviceBvhBuilder(void* user, const pbrbvh::Aabb* boxes, uint32_t n, const pbrbvh::BuildParams& prm,
+                             uint32_t radius, pbrbvh::Bvh8* out, const char** err) {
+  pbrgpu_ctx* ctx = static_cast<pbrgpu_ctx*>(user);
+  Device& d = ctx->devices[0];
+  if (cudaSetDevice(d.id) != cudaSuccess) { if (err) *err = "cudaSetDevice failed"; return false; }
+  double sec[3] = {0, 0, 0};
+  const bool ok = pbrdev::BuildBvh8OnDevice(d.stream, boxes, n, prm, radius, out, err, sec);
+  if (ok && getenv("PBRGPU_VERBOSE_COMMIT"))
+    fprintf(stderr, "  device BVH build (%u prims): upload %.3f s, build %.3f s, download %.3f s, %u nodes, depth %u\n", n,
+            sec[0], sec[1], sec[2], out->num_nodes, out->max_depth);
+  return ok;
+}
+
 int pbrgpu_commit(pbrgpu_ctx* ctx, const float* bmin, const float* bmax) {
   if (!ctx) return PBRGPU_ERR_INVALID;
+  ctx->host.device_builder = &DeviceBvhBuilder;
+  ctx->host.device_builder_user = ctx;
+  const auto t0 = std::chrono::steady_clock::now();
   if (!ctx->host.Commit(bmin, bmax)) {
     ctx->error = ctx->host.error;
     return PBRGPU_ERR_BUILD;
   }
+  const auto t1 = std::chrono::steady_clock::now();
   for (Device& d : ctx->devices) {
     const int rc = UploadScene(ctx, d);
     if (rc != PBRGPU_OK) return rc;
   }
+  const auto t2 = std::chrono::steady_clock::now();
+  pbrgpu_commit_info& ci = ctx->commit_info;
+  memset(&ci, 0, sizeof(ci));
+  ci.commit_s = std::chrono::duration<double>(t2 - t0).count();
+  ci.upload_s = std::chrono::duration<double>(t2 - t1).count();
+  ci.bvh_s = ctx->host.bvh_seconds;
+  ci.clearance_s = ctx->host.clearance_seconds;
+  ci.tri_builder = ctx->host.last_builder == "ploc-device" ? 2u : (ctx->host.last_builder == "ploc-host" ? 1u : 0u);
+  ci.tri_nodes = ctx->host.tri_bvh.num_nodes;
+  ci.curve_nodes = ctx->host.curve_bvh.num_nodes;
+  ci.tri_depth = ctx->host.tri_bvh.max_depth;
+  if (getenv("PBRGPU_VERBOSE_COMMIT"))
+    fprintf(stderr, "pbrgpu_commit: %.3f s (BVH %.3f, clearance %.3f, upload %.3f), triangle BVH by %s\n", ci.commit_s,
+            ci.bvh_s, ci.clearance_s, ci.upload_s, ctx->host.last_builder.c_str());
   ctx->committed = true;
+  return PBRGPU_OK;
+}
+
+int pbrgpu_get_commit_info(const pbrgpu_ctx* ctx, pbrgpu_commit_info* out) {
+  if (!ctx || !out || !ctx->committed) return PBRGPU_ERR_INVALID;
+  *out = ctx->commit_info;
   return PBRGPU_OK;
 }
 

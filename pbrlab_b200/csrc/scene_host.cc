@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <mutex>
 
 namespace pbrhost {
 
@@ -213,15 +214,39 @@ inline void BezierBasisQuarter(int i, float* b) {   // Embree BezierBasis::eval(
 }
 }  // namespace
 
+namespace {
+template <class F>
+void ParallelFor(int n, F fn) {
+  const int nt = std::max(1, std::min(int(std::thread::hardware_concurrency()), n));
+  std::vector<std::thread> th;
+  std::atomic<int> next{0};
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&]() { for (int i; (i = next.fetch_add(1)) < n;) fn(i); });
+  for (auto& t : th) t.join();
+}
+// fn(begin, end) over [0, n) in chunks on all host threads (the per-primitive passes of Commit at 20 M triangles)
+template <class F>
+void ParallelRanges(uint64_t n, F fn) {
+  const uint64_t chunk = 1u << 16;
+  if (n <= chunk) { fn(uint64_t(0), n); return; }
+  const int nchunks = int((n + chunk - 1) / chunk);
+  ParallelFor(nchunks, [&](int c) { fn(uint64_t(c) * chunk, std::min<uint64_t>(n, uint64_t(c + 1) * chunk)); });
+}
+}  // namespace
+
 bool HostScene::BuildBvh(const pbrbvh::Aabb* boxes, uint32_t n, const pbrbvh::BuildParams& prm, pbrbvh::Bvh8* out,
-                         std::string* which) {
-  const char* mode_env = getenv("PBRGPU_BVH");
+                         std::string* which, bool curves) {
+  // PBRGPU_BVH_TRIS / PBRGPU_BVH_CURVES (or PBRGPU_BVH for both) = sah | ploc | auto.  auto: triangles -> PLOC when a
+  // device builder is installed (better trees AND a 100x faster build, measured: DESIGN.md §6), curves -> the host SAH
+  // builder (PLOC trees over hair are no better and the curve BVHs are small)
+  const char* mode_env = getenv(curves ? "PBRGPU_BVH_CURVES" : "PBRGPU_BVH_TRIS");
+  if (!mode_env) mode_env = getenv("PBRGPU_BVH");
   const std::string mode = mode_env ? mode_env : "auto";
-  uint32_t min_prims = 2u << 20;
-  if (const char* e = getenv("PBRGPU_BVH_DEVICE_MIN")) min_prims = uint32_t(std::max(1, atoi(e)));
-  uint32_t radius = 16;
+  uint32_t min_prims = 0u;
+  if (const char* e = getenv("PBRGPU_BVH_DEVICE_MIN")) min_prims = uint32_t(std::max(0, atoi(e)));
+  uint32_t radius = 8;
   if (const char* e = getenv("PBRGPU_PLOC_RADIUS")) radius = uint32_t(std::min(128, std::max(1, atoi(e))));
-  const bool ploc = mode == "ploc" || (mode == "auto" && n >= min_prims && device_builder != nullptr);
+  const bool ploc = mode == "ploc" || (mode == "auto" && !curves && n >= min_prims && device_builder != nullptr);
   const char* err = nullptr;
   bool ok;
   if (ploc && device_builder) {
@@ -242,6 +267,8 @@ bool HostScene::BuildBvh(const pbrbvh::Aabb* boxes, uint32_t n, const pbrbvh::Bu
 
 bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
   const auto t0 = std::chrono::steady_clock::now();
+  bvh_seconds = 0.0;
+  clearance_seconds = 0.0;
   const uint32_t nt = num_tris(), nc = num_curves();
   if (nt == 0 && nc == 0) { error = "pbrgpu_commit: empty scene"; return false; }
   if (!CheckTextureIds()) return false;
@@ -259,31 +286,39 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
   tri_data.clear();
   if (nt) {
     std::vector<pbrbvh::Aabb> boxes(nt);
-    for (uint32_t i = 0; i < nt; ++i) {
-      const F4 &a = verts[tri_vidx[i].x], &b = verts[tri_vidx[i].y], &c = verts[tri_vidx[i].z];
-      pbrbvh::Aabb& bx = boxes[i];
-      bx.lo[0] = std::min(a.x, std::min(b.x, c.x)); bx.hi[0] = std::max(a.x, std::max(b.x, c.x));
-      bx.lo[1] = std::min(a.y, std::min(b.y, c.y)); bx.hi[1] = std::max(a.y, std::max(b.y, c.y));
-      bx.lo[2] = std::min(a.z, std::min(b.z, c.z)); bx.hi[2] = std::max(a.z, std::max(b.z, c.z));
-      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], bx.lo[k]); hi[k] = std::max(hi[k], bx.hi[k]); }
-    }
+    std::mutex lohi_mutex;
+    ParallelRanges(nt, [&](uint64_t b0, uint64_t e0) {
+      float llo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, lhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+      for (uint64_t i = b0; i < e0; ++i) {
+        const F4 &a = verts[tri_vidx[i].x], &b = verts[tri_vidx[i].y], &c = verts[tri_vidx[i].z];
+        pbrbvh::Aabb& bx = boxes[i];
+        bx.lo[0] = std::min(a.x, std::min(b.x, c.x)); bx.hi[0] = std::max(a.x, std::max(b.x, c.x));
+        bx.lo[1] = std::min(a.y, std::min(b.y, c.y)); bx.hi[1] = std::max(a.y, std::max(b.y, c.y));
+        bx.lo[2] = std::min(a.z, std::min(b.z, c.z)); bx.hi[2] = std::max(a.z, std::max(b.z, c.z));
+        for (int k = 0; k < 3; ++k) { llo[k] = std::min(llo[k], bx.lo[k]); lhi[k] = std::max(lhi[k], bx.hi[k]); }
+      }
+      std::lock_guard<std::mutex> lock(lohi_mutex);
+      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], llo[k]); hi[k] = std::max(hi[k], lhi[k]); }
+    });
     const auto tb0 = std::chrono::steady_clock::now();
-    if (!BuildBvh(boxes.data(), nt, prm, &tri_bvh, &last_builder)) return false;
+    if (!BuildBvh(boxes.data(), nt, prm, &tri_bvh, &last_builder, false)) return false;
     bvh_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count();
     if (getenv("PBRGPU_VERBOSE_COMMIT"))
       fprintf(stderr, "commit: triangle BVH (%u prims) %.3f s\n", nt, std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count());
     tri_data.resize(size_t(3) * nt);
-    for (uint32_t k = 0; k < nt; ++k) {
-      const uint32_t i = tri_bvh.prim_order[k];
-      const F4 &a = verts[tri_vidx[i].x], &b = verts[tri_vidx[i].y], &c = verts[tri_vidx[i].z];
-      float idbits;
-      memcpy(&idbits, &i, 4);
-      tri_data[3 * k + 0] = {a.x, a.y, a.z, idbits};
-      float matbits;   // material id rides in the spare lane of e1: the closest-hit kernel routes by material class
-      memcpy(&matbits, &tri_ids[i].w, 4);
-      tri_data[3 * k + 1] = {a.x - b.x, a.y - b.y, a.z - b.z, matbits};
-      tri_data[3 * k + 2] = {c.x - a.x, c.y - a.y, c.z - a.z, 0.f};
-    }
+    ParallelRanges(nt, [&](uint64_t b0, uint64_t e0) {
+      for (uint64_t k = b0; k < e0; ++k) {
+        const uint32_t i = tri_bvh.prim_order[k];
+        const F4 &a = verts[tri_vidx[i].x], &b = verts[tri_vidx[i].y], &c = verts[tri_vidx[i].z];
+        float idbits;
+        memcpy(&idbits, &i, 4);
+        tri_data[3 * k + 0] = {a.x, a.y, a.z, idbits};
+        float matbits;   // material id rides in the spare lane of e1: the closest-hit kernel routes by material class
+        memcpy(&matbits, &tri_ids[i].w, 4);
+        tri_data[3 * k + 1] = {a.x - b.x, a.y - b.y, a.z - b.z, matbits};
+        tri_data[3 * k + 2] = {c.x - a.x, c.y - a.y, c.z - a.z, 0.f};
+      }
+    });
   } else {
     tri_bvh = pbrbvh::Bvh8();
   }
@@ -350,7 +385,9 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
     const uint32_t nparts = nc * uint32_t(split);
     {
       std::string which;
-      if (!BuildBvh(boxes.data(), nparts, prm, &curve_bvh, &which)) return false;
+      const auto tcb = std::chrono::steady_clock::now();
+      if (!BuildBvh(boxes.data(), nparts, prm, &curve_bvh, &which, true)) return false;
+      bvh_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tcb).count();
       if (!nt) last_builder = which;
     }
     // segment storage ("slots") in order of first appearance in the leaves: neighbours in space are neighbours in memory
@@ -420,6 +457,7 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
   }
   const auto tc0 = std::chrono::steady_clock::now();
   BuildClearance();
+  clearance_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count();
   if (getenv("PBRGPU_VERBOSE_COMMIT"))
     fprintf(stderr, "commit: clearance field %.3f s, total %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count(),
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
@@ -459,15 +497,6 @@ inline void Edt1D(float* f, int n, float* z, int* v, float* out) {
   for (int q = 0; q < n; ++q) f[q] = out[q];
 }
 
-template <class F>
-void ParallelFor(int n, F fn) {
-  const int nt = std::max(1, std::min(int(std::thread::hardware_concurrency()), n));
-  std::vector<std::thread> th;
-  std::atomic<int> next{0};
-  for (int t = 0; t < nt; ++t)
-    th.emplace_back([&]() { for (int i; (i = next.fetch_add(1)) < n;) fn(i); });
-  for (auto& t : th) t.join();
-}
 }  // namespace
 
 void HostScene::BuildClearance() {
@@ -538,7 +567,9 @@ void HostScene::BuildClearance() {
         }
       }
   };
-  for (uint32_t i = 0; i < nt; ++i) {
+  // (all host threads: cells are only ever set to 1, so concurrent writers cannot disagree)
+  ParallelRanges(nt, [&](uint64_t tb, uint64_t te) {
+  for (uint64_t i = tb; i < te; ++i) {
     const F4 &a = verts[tri_vidx[i].x], &b = verts[tri_vidx[i].y], &c = verts[tri_vidx[i].z];
     const float blo[3] = {std::min(a.x, std::min(b.x, c.x)), std::min(a.y, std::min(b.y, c.y)), std::min(a.z, std::min(b.z, c.z))};
     const float bhi[3] = {std::max(a.x, std::max(b.x, c.x)), std::max(a.y, std::max(b.y, c.y)), std::max(a.z, std::max(b.z, c.z))};
@@ -553,6 +584,7 @@ void HostScene::BuildClearance() {
       mark_box(blo, bhi, nullptr);
     }
   }
+  });
   for (uint32_t i = 0; i < num_curves(); ++i) {
     const F4* cp = &curve_cps[4 * size_t(i)];
     float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, r = 0.f;

@@ -51,10 +51,10 @@ struct HostScene {
   uint32_t clear_dims[3] = {0, 0, 0};
   bool committed = false;
   double build_seconds = 0.0;
-  // Which builder Commit() uses for the two BVHs.  PBRGPU_BVH = "sah" (host binned SAH, bvh_builder.cc), "ploc" (the
-  // data-parallel builder of bvh_ploc.h: on the device through `device_builder` when the CUDA library installed one,
-  // else its host loops), "auto" (default): "ploc" from PBRGPU_BVH_DEVICE_MIN primitives up (default 2 Mi), where the
-  // host builder's seconds start to matter; "sah" below.
+  // Which builder Commit() uses for the two BVHs: PBRGPU_BVH_TRIS / PBRGPU_BVH_CURVES (or PBRGPU_BVH for both) =
+  // "sah" (host binned SAH, bvh_builder.cc), "ploc" (the data-parallel builder of bvh_ploc.h: on the device through
+  // `device_builder` when the CUDA library installed one, else its host loops), "auto" (default): triangles "ploc"
+  // when a device builder is installed, curves "sah".
   using DeviceBuilder = bool (*)(void* user, const pbrbvh::Aabb* boxes, uint32_t n, const pbrbvh::BuildParams& prm,
                                  uint32_t radius, pbrbvh::Bvh8* out, const char** err);
   DeviceBuilder device_builder = nullptr;
@@ -62,7 +62,7 @@ struct HostScene {
   std::string last_builder;      // what the last Commit() used for the triangle BVH ("sah", "ploc-host", "ploc-device")
   double bvh_seconds = 0.0, clearance_seconds = 0.0;
   bool BuildBvh(const pbrbvh::Aabb* boxes, uint32_t n, const pbrbvh::BuildParams& prm, pbrbvh::Bvh8* out,
-                std::string* which);
+                std::string* which, bool curves);
 
   std::string error;
 
