@@ -1,14 +1,21 @@
 #include "triangle-mesh-io.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
+#include <chrono>
+#include <functional>
+#include <thread>
 
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <memory>
+#include <thread>
 
 #include <sys/stat.h>
 
@@ -341,132 +348,259 @@ bool LoadTriangleMeshFromObj(const std::string& filename, std::vector<TriangleMe
       return true;
     }
   }
+  const bool verbose = getenv("PBRLAB_VERBOSE_LOAD") != nullptr;
+  const auto tl0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (verbose) std::cerr << "  obj load: " << what << " at " << std::chrono::duration<double>(std::chrono::steady_clock::now() - tl0).count() << " s" << std::endl;
+  };
   std::string text;
   if (!ReadFile(filename, &text)) {
     std::cerr << "error : cannot open [" << filename << "]" << std::endl;
     return false;
   }
+  lap("file read");
   const size_t slash = filename.find_last_of('/');
   const std::string base_dir = (slash == std::string::npos) ? std::string("") : filename.substr(0, slash);
   std::cerr << "base dir : " << base_dir << std::endl;
 
-  ShapeBuild cur;
-  int cur_material = -1;
-  std::vector<Corner> face;
-
-  auto flush = [&]() {
-    if (!cur.v.empty()) shapes.push_back(cur);
-    const std::string keep = cur.name;
-    cur = ShapeBuild();
-    cur.name = keep;
+  // ---- parse on all host threads (the 1.5 GB of text of the 20 M-triangle scene took 13 s on one).
+  // The file is cut into chunks at line ends.  (1) every chunk counts its v / vn / vt lines: prefix sums give each
+  // chunk its place in the attribute pools and the number of elements "read so far" that relative (negative) indices
+  // and the quad split need; (2) the chunks parse their attribute lines into the pools; (3) the chunks parse their
+  // face lines into chunk-local triangle lists and note the lines that change the sequential state (o, g, usemtl,
+  // mtllib) with the triangle count at which they occur; (4) one thread walks the chunks in file order, applies those
+  // events and appends the triangle runs in between to the shapes.  Same arrays as the one-pass loader this replaces
+  // (tests/test_loader.py compares them with the reference's loader element for element).
+  struct Event { int kind; uint64_t tri_index; std::string text; };   // kind: 0 = o / g, 1 = usemtl, 2 = mtllib
+  struct Chunk {
+    const char* begin; const char* end;
+    uint64_t nv = 0, nn = 0, nt = 0, nlines = 0;       // counted in (1)
+    uint64_t v0 = 0, n0 = 0, t0 = 0, line0 = 0;        // elements / lines before this chunk
+    std::vector<uint32_t> v, vn, vt;                   // 3 per triangle
+    std::vector<Event> events;
+    uint64_t bad_line = 0;                             // first `f' line that failed to parse (global number), 0 = none
   };
-
-  const char* p = text.c_str();
-  size_t line_no = 0;
-  while (*p) {
-    ++line_no;
-    SkipSpace(&p);
-    const char* line = p;
+  const char* const text_begin = text.c_str();
+  const char* const text_end = text_begin + text.size();
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t want_chunks = text.size() < (size_t(4) << 20) ? 1 : size_t(hw) * 4;
+  std::vector<Chunk> chunks;
+  {
+    const size_t step = std::max<size_t>(text.size() / want_chunks, 1);
+    const char* b = text_begin;
+    while (b < text_end) {
+      const char* e = (size_t(text_end - b) <= step) ? text_end : b + step;
+      while (e < text_end && e[-1] != '\n') ++e;   // cut after a line end
+      Chunk c;
+      c.begin = b; c.end = e;
+      chunks.push_back(std::move(c));
+      b = e;
+    }
+  }
+  auto parallel_chunks = [&](const std::function<void(Chunk&)>& fn) {
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    const unsigned nth = unsigned(std::min<size_t>(hw, chunks.size()));
+    for (unsigned t = 1; t < nth; ++t)
+      th.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < chunks.size();) fn(chunks[i]); });
+    for (size_t i; (i = next.fetch_add(1)) < chunks.size();) fn(chunks[i]);
+    for (auto& t : th) t.join();
+  };
+  // a line starts after leading blanks; returns the start of the next line
+  auto next_line = [](const char* p, const char* end) {
+    while (p < end && !IsEol(*p)) ++p;
+    while (p < end && *p == '\r') ++p;
+    if (p < end && (*p == '\n' || *p == '\0')) ++p;
+    return p;
+  };
+  auto line_kind = [](const char* line) {   // 1 v, 2 vn, 3 vt, 4 f, 5 o/g, 6 usemtl, 7 mtllib, 0 other
     const char c0 = line[0], c1 = c0 ? line[1] : 0;
-    if (c0 == 'v' && IsSpace(c1)) {
-      p += 2;
-      const float x = ParseFloat(&p), y = ParseFloat(&p), z = ParseFloat(&p);
-      attr->vertices.push_back(x); attr->vertices.push_back(y); attr->vertices.push_back(z);
-      attr->vertices.push_back(1.0f);
-    } else if (c0 == 'v' && c1 == 'n' && IsSpace(line[2])) {
-      p += 3;
-      const float x = ParseFloat(&p), y = ParseFloat(&p), z = ParseFloat(&p);
-      attr->normals.push_back(x); attr->normals.push_back(y); attr->normals.push_back(z);
-      attr->normals.push_back(1.0f);
-    } else if (c0 == 'v' && c1 == 't' && IsSpace(line[2])) {
-      p += 3;
-      const float u = ParseFloat(&p), v = ParseFloat(&p);
-      attr->texcoords.push_back(u);
-      attr->texcoords.push_back(1.f - v);   // reference triangle-mesh-io.cc:286
-    } else if (c0 == 'f' && IsSpace(c1)) {
-      p += 2;
-      face.clear();
-      const int nv = int(attr->vertices.size() / 4), nn = int(attr->normals.size() / 4),
-                nt = int(attr->texcoords.size() / 2);
-      for (;;) {
-        SkipSpace(&p);
-        if (IsEol(*p)) break;
-        Corner c = {-1, -1, -1};
-        int raw;
-        if (!ParseInt(&p, &raw) || !FixIndex(raw, nv, &c.v)) {
-          std::cerr << "error : Failed to parse `f' line " << line_no << std::endl;
-          return false;
-        }
-        if (*p == '/') {
-          ++p;
-          if (*p == '/') {           // v//vn
+    if (c0 == 'v' && IsSpace(c1)) return 1;
+    if (c0 == 'v' && c1 == 'n' && IsSpace(line[2])) return 2;
+    if (c0 == 'v' && c1 == 't' && IsSpace(line[2])) return 3;
+    if (c0 == 'f' && IsSpace(c1)) return 4;
+    if ((c0 == 'o' || c0 == 'g') && IsSpace(c1)) return 5;
+    if (strncmp(line, "usemtl", 6) == 0) return 6;
+    if (strncmp(line, "mtllib", 6) == 0 && IsSpace(line[6])) return 7;
+    return 0;
+  };
+  // (1) count
+  parallel_chunks([&](Chunk& c) {
+    const char* p = c.begin;
+    while (p < c.end) {
+      ++c.nlines;
+      SkipSpace(&p);
+      const int k = line_kind(p);
+      if (k == 1) ++c.nv; else if (k == 2) ++c.nn; else if (k == 3) ++c.nt;
+      p = next_line(p, c.end);
+    }
+  });
+  {
+    uint64_t v = 0, n = 0, t = 0, l = 0;
+    for (Chunk& c : chunks) { c.v0 = v; c.n0 = n; c.t0 = t; c.line0 = l; v += c.nv; n += c.nn; t += c.nt; l += c.nlines; }
+    attr->vertices.resize(size_t(v) * 4);
+    attr->normals.resize(size_t(n) * 4);
+    attr->texcoords.resize(size_t(t) * 2);
+  }
+  lap("counted");
+  // (2) attributes
+  parallel_chunks([&](Chunk& c) {
+    const char* p = c.begin;
+    float* V = attr->vertices.data() + size_t(c.v0) * 4;
+    float* N = attr->normals.data() + size_t(c.n0) * 4;
+    float* T = attr->texcoords.data() + size_t(c.t0) * 2;
+    while (p < c.end) {
+      SkipSpace(&p);
+      const int k = line_kind(p);
+      if (k == 1) {
+        p += 2;
+        V[0] = ParseFloat(&p); V[1] = ParseFloat(&p); V[2] = ParseFloat(&p); V[3] = 1.0f;
+        V += 4;
+      } else if (k == 2) {
+        p += 3;
+        N[0] = ParseFloat(&p); N[1] = ParseFloat(&p); N[2] = ParseFloat(&p); N[3] = 1.0f;
+        N += 4;
+      } else if (k == 3) {
+        p += 3;
+        const float u = ParseFloat(&p), v = ParseFloat(&p);
+        T[0] = u;
+        T[1] = 1.f - v;   // reference triangle-mesh-io.cc:286
+        T += 2;
+      }
+      p = next_line(p, c.end);
+    }
+  });
+  lap("attributes parsed");
+  // (3) faces and state-changing lines
+  parallel_chunks([&](Chunk& c) {
+    const char* p = c.begin;
+    uint64_t nv = c.v0, nn = c.n0, nt = c.t0, line_no = c.line0;
+    std::vector<Corner> face;
+    const float* V = attr->vertices.data();
+    auto emit = [&](const Corner& a, const Corner& b, const Corner& cc) {
+      c.v.push_back(uint32_t(a.v)); c.v.push_back(uint32_t(b.v)); c.v.push_back(uint32_t(cc.v));
+      c.vn.push_back(uint32_t(a.vn)); c.vn.push_back(uint32_t(b.vn)); c.vn.push_back(uint32_t(cc.vn));
+      c.vt.push_back(uint32_t(a.vt)); c.vt.push_back(uint32_t(b.vt)); c.vt.push_back(uint32_t(cc.vt));
+    };
+    while (p < c.end) {
+      ++line_no;
+      SkipSpace(&p);
+      const char* line = p;
+      const int k = line_kind(line);
+      if (k == 1) ++nv;
+      else if (k == 2) ++nn;
+      else if (k == 3) ++nt;
+      else if (k == 4 && c.bad_line == 0) {
+        p += 2;
+        face.clear();
+        bool ok = true;
+        for (;;) {
+          SkipSpace(&p);
+          if (IsEol(*p)) break;
+          Corner cr = {-1, -1, -1};
+          int raw;
+          if (!ParseInt(&p, &raw) || !FixIndex(raw, int(nv), &cr.v)) { ok = false; break; }
+          if (*p == '/') {
             ++p;
-            if (ParseInt(&p, &raw) && !FixIndex(raw, nn, &c.vn)) return false;
-          } else {
-            if (ParseInt(&p, &raw) && !FixIndex(raw, nt, &c.vt)) return false;
-            if (*p == '/') {
+            if (*p == '/') {           // v//vn
               ++p;
-              if (ParseInt(&p, &raw) && !FixIndex(raw, nn, &c.vn)) return false;
+              if (ParseInt(&p, &raw) && !FixIndex(raw, int(nn), &cr.vn)) { ok = false; break; }
+            } else {
+              if (ParseInt(&p, &raw) && !FixIndex(raw, int(nt), &cr.vt)) { ok = false; break; }
+              if (*p == '/') {
+                ++p;
+                if (ParseInt(&p, &raw) && !FixIndex(raw, int(nn), &cr.vn)) { ok = false; break; }
+              }
             }
           }
+          face.push_back(cr);
         }
-        face.push_back(c);
-      }
-      auto emit = [&](const Corner& a, const Corner& b, const Corner& c) {
-        cur.v.push_back(uint32_t(a.v)); cur.v.push_back(uint32_t(b.v)); cur.v.push_back(uint32_t(c.v));
-        cur.vn.push_back(uint32_t(a.vn)); cur.vn.push_back(uint32_t(b.vn)); cur.vn.push_back(uint32_t(c.vn));
-        cur.vt.push_back(uint32_t(a.vt)); cur.vt.push_back(uint32_t(b.vt)); cur.vt.push_back(uint32_t(c.vt));
-        cur.mat.push_back(uint32_t(cur_material));
-      };
-      const size_t n = face.size();
-      if (n == 3) {
-        emit(face[0], face[1], face[2]);
-      } else if (n == 4) {
-        // split along the shorter diagonal (reference src/io/tiny_obj_loader.h:1519-1575)
-        const float* V = attr->vertices.data();
-        auto d2 = [&](int a, int b) {
-          const float dx = V[4 * b] - V[4 * a], dy = V[4 * b + 1] - V[4 * a + 1], dz = V[4 * b + 2] - V[4 * a + 2];
-          return dx * dx + dy * dy + dz * dz;
-        };
-        if (d2(face[0].v, face[2].v) < d2(face[1].v, face[3].v)) {
-          emit(face[0], face[1], face[2]);
-          emit(face[0], face[2], face[3]);
+        if (!ok) {
+          c.bad_line = line_no;
         } else {
-          emit(face[0], face[1], face[3]);
-          emit(face[1], face[2], face[3]);
+          const size_t n = face.size();
+          if (n == 3) {
+            emit(face[0], face[1], face[2]);
+          } else if (n == 4) {
+            // split along the shorter diagonal (reference src/io/tiny_obj_loader.h:1519-1575)
+            auto d2 = [&](int a, int b) {
+              const float dx = V[4 * b] - V[4 * a], dy = V[4 * b + 1] - V[4 * a + 1], dz = V[4 * b + 2] - V[4 * a + 2];
+              return dx * dx + dy * dy + dz * dz;
+            };
+            if (d2(face[0].v, face[2].v) < d2(face[1].v, face[3].v)) {
+              emit(face[0], face[1], face[2]);
+              emit(face[0], face[2], face[3]);
+            } else {
+              emit(face[0], face[1], face[3]);
+              emit(face[1], face[2], face[3]);
+            }
+          } else if (n > 4) {
+            for (size_t q = 1; q + 1 < n; ++q) emit(face[0], face[q], face[q + 1]);
+          }
         }
-      } else if (n > 4) {
-        for (size_t k = 1; k + 1 < n; ++k) emit(face[0], face[k], face[k + 1]);
+      } else if (k == 5) {
+        c.events.push_back({0, uint64_t(c.v.size() / 3), RestOfLine(line + 2)});
+      } else if (k == 6) {
+        const char* q = line + 6;
+        SkipSpace(&q);
+        c.events.push_back({1, uint64_t(c.v.size() / 3), RestOfLine(q)});
+      } else if (k == 7) {
+        const char* q = line + 7;
+        SkipSpace(&q);
+        c.events.push_back({2, uint64_t(c.v.size() / 3), RestOfLine(q)});
       }
-    } else if (c0 == 'o' && IsSpace(c1)) {
-      flush();
-      cur.name = RestOfLine(line + 2);
-    } else if (c0 == 'g' && IsSpace(c1)) {
-      flush();
-      cur.name = RestOfLine(line + 2);
-    } else if (strncmp(line, "usemtl", 6) == 0) {
-      const char* q = line + 6;
-      SkipSpace(&q);
-      const std::string name = RestOfLine(q);
-      auto it = material_index.find(name);
-      cur_material = (it == material_index.end()) ? -1 : it->second;
-    } else if (strncmp(line, "mtllib", 6) == 0 && IsSpace(line[6])) {
-      const char* q = line + 7;
-      SkipSpace(&q);
-      const std::string name = RestOfLine(q);
-      mtllibs.push_back(name);
-      LoadMtl(base_dir.empty() ? name : base_dir + "/" + name, &raw_materials, &material_index);
+      p = next_line(p, c.end);
     }
-    while (!IsEol(*p)) ++p;
-    while (*p == '\r') ++p;
-    if (*p == '\n') ++p;
+  });
+  lap("faces parsed");
+  // (4) the sequential state, in file order
+  ShapeBuild cur;
+  int cur_material = -1;
+  auto flush = [&]() {
+    if (!cur.v.empty()) shapes.push_back(std::move(cur));
+    cur = ShapeBuild();
+  };
+  auto append_run = [&](const Chunk& c, uint64_t t0, uint64_t t1) {
+    if (t1 <= t0) return;
+    cur.v.insert(cur.v.end(), c.v.begin() + 3 * t0, c.v.begin() + 3 * t1);
+    cur.vn.insert(cur.vn.end(), c.vn.begin() + 3 * t0, c.vn.begin() + 3 * t1);
+    cur.vt.insert(cur.vt.end(), c.vt.begin() + 3 * t0, c.vt.begin() + 3 * t1);
+    cur.mat.insert(cur.mat.end(), size_t(t1 - t0), uint32_t(cur_material));
+  };
+  for (Chunk& c : chunks) {
+    uint64_t pos = 0;
+    // a parse error stops the load at that line, like the one-pass loader (everything before it is irrelevant then)
+    if (c.bad_line) {
+      std::cerr << "error : Failed to parse `f' line " << c.bad_line << std::endl;
+      return false;
+    }
+    for (const Event& ev : c.events) {
+      append_run(c, pos, ev.tri_index);
+      pos = ev.tri_index;
+      if (ev.kind == 0) {
+        const std::string name = ev.text;
+        if (!cur.v.empty()) shapes.push_back(std::move(cur));
+        cur = ShapeBuild();
+        cur.name = name;
+      } else if (ev.kind == 1) {
+        auto it = material_index.find(ev.text);
+        cur_material = (it == material_index.end()) ? -1 : it->second;
+      } else {
+        mtllibs.push_back(ev.text);
+        LoadMtl(base_dir.empty() ? ev.text : base_dir + "/" + ev.text, &raw_materials, &material_index);
+      }
+    }
+    append_run(c, pos, c.v.size() / 3);
+    std::vector<uint32_t>().swap(c.v); std::vector<uint32_t>().swap(c.vn); std::vector<uint32_t>().swap(c.vt);
   }
   flush();
+  lap("shapes assembled");
   if (use_cache) WriteObjCache(filename, base_dir, mtllibs, *attr, shapes);
 
   meshes->clear();
   for (const ShapeBuild& s : shapes) meshes->emplace_back(s.name, attr, s.v, s.vn, s.vt, s.mat);
   for (const RawMaterial& m : raw_materials) material_params->push_back(ToPrincipled(m, base_dir, textures));
+  lap("meshes built");
   return true;
 }
 

@@ -1,5 +1,8 @@
 #include "scene.h"
 
+#include <array>
+#include <thread>
+
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -161,23 +164,41 @@ void Scene::CommitHostOnly(void) {
         const auto& nid = mesh.GetNormalIds();
         const auto& tid = mesh.GetTexcoordIds();
         const auto& mat = inst.material_ids[g];
-        for (uint32_t p = 0; p < nf; ++p) {
-          for (int k = 0; k < 3; ++k) {
-            const uint32_t v = vid[p * 3 + k] + vbase;
-            f.vidx.push_back(v);
-            const uint32_t n = nid[p * 3 + k], t = tid[p * 3 + k];
-            f.nidx.push_back(n == uint32_t(-1) ? n : n + nbase);
-            f.tidx.push_back(t == uint32_t(-1) ? t : t + tbase);
-            for (int c = 0; c < 3; ++c) {
-              lo[c] = std::min(lo[c], f.verts[size_t(v) * 4 + c]);
-              hi[c] = std::max(hi[c], f.verts[size_t(v) * 4 + c]);
+        // sized fill on all host threads (20 M triangles: 260 M element appends otherwise)
+        const size_t t0 = f.tri_prim.size();
+        f.vidx.resize((t0 + nf) * 3); f.nidx.resize((t0 + nf) * 3); f.tidx.resize((t0 + nf) * 3);
+        f.tri_material.resize(t0 + nf); f.tri_instance.resize(t0 + nf); f.tri_geom.resize(t0 + nf);
+        f.tri_prim.resize(t0 + nf);
+        const unsigned nth = std::max(1u, std::min(nf / 65536u + 1u, std::thread::hardware_concurrency()));
+        std::vector<std::array<float, 6>> part(nth);
+        std::vector<std::thread> th;
+        auto fill = [&](unsigned t) {
+          float llo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, lhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+          const uint32_t p0 = uint32_t(uint64_t(nf) * t / nth), p1 = uint32_t(uint64_t(nf) * (t + 1) / nth);
+          for (uint32_t p = p0; p < p1; ++p) {
+            for (int k = 0; k < 3; ++k) {
+              const uint32_t v = vid[p * 3 + k] + vbase;
+              f.vidx[(t0 + p) * 3 + k] = v;
+              const uint32_t n = nid[p * 3 + k], tt = tid[p * 3 + k];
+              f.nidx[(t0 + p) * 3 + k] = (n == uint32_t(-1) ? n : n + nbase);
+              f.tidx[(t0 + p) * 3 + k] = (tt == uint32_t(-1) ? tt : tt + tbase);
+              for (int c = 0; c < 3; ++c) {
+                llo[c] = std::min(llo[c], f.verts[size_t(v) * 4 + c]);
+                lhi[c] = std::max(lhi[c], f.verts[size_t(v) * 4 + c]);
+              }
             }
+            f.tri_material[t0 + p] = (p < mat.size() ? mat[p] : uint32_t(-1));
+            f.tri_instance[t0 + p] = i;
+            f.tri_geom[t0 + p] = g;
+            f.tri_prim[t0 + p] = p;
           }
-          f.tri_material.push_back(p < mat.size() ? mat[p] : uint32_t(-1));
-          f.tri_instance.push_back(i);
-          f.tri_geom.push_back(g);
-          f.tri_prim.push_back(p);
-        }
+          for (int c = 0; c < 3; ++c) { part[t][c] = llo[c]; part[t][3 + c] = lhi[c]; }
+        };
+        for (unsigned t = 1; t < nth; ++t) th.emplace_back(fill, t);
+        fill(0);
+        for (auto& x : th) x.join();
+        for (unsigned t = 0; t < nth; ++t)
+          for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], part[t][c]); hi[c] = std::max(hi[c], part[t][3 + c]); }
       } else {
         const CubicBezierCurveMesh& mesh = *std::get<kCubicBezierCurveMesh>(mp);
         const uint32_t base = uint32_t(f.curve_verts.size() / 4);
