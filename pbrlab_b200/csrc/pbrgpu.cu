@@ -144,9 +144,10 @@ struct pbrgpu_ctx {
   bool committed = false;
   pbrgpu_commit_info commit_info;
   bool profile = false;   // time every kernel family with CUDA events (pbrgpu_set_profiling)
+  bool trace_iterations = false;   // PBRGPU_TRACE_ITERATIONS: one line per wavefront iteration on stderr
   // launch tuning (defaults measured on B200; PBRGPU_* environment variables override for sweeps)
   uint32_t tune_refill = 16;       // idle lanes that trigger a refill in the traversal engine
-  uint32_t tune_refill_any = 24;      // any-hit kernel in triangle scenes (shadow rays end early: fewer, fuller refills win; sweep profiles/r1z_refill_any_sweep.log)
+  uint32_t tune_refill_any = 16;      // any-hit kernel in triangle scenes (24 was best on the round-1 trees; with the PLOC trees 16: 43.5 -> 39.9 ms per 128-spp frame, profiles/r2h_tune_engine_knobs.log)
   uint32_t tune_refill_curves = 12;   // same in scenes with curves (lanes wait longer there: held ribbon candidates)
   uint32_t tune_refill_sss = 24;   // same for the random-walk kernel (its converged section is the bounce itself)
   uint32_t tune_prim_lanes = 1, tune_prim_lanes_sss = 1;   // lanes with pending primitives that trigger a primitive phase
@@ -157,6 +158,8 @@ struct pbrgpu_ctx {
   // that is only a few pool-fills long (strong scaling: 1/8 of the samples per GPU) spends a smaller share of its
   // time ramping up and draining with a smaller pool
   int tune_pool_div = 8, tune_pool_min_mi = 4;
+  int tune_drain_paths = 1 << 16, tune_drain_bounces = 256;    // fewer paths in flight than this: long walk slices (sweep: profiles/r2j_tune_drain_stages.log)
+  int tune_drain2_paths = 0, tune_drain2_bounces = 64;          // an intermediate stage (off by default)
   int tune_clear_march = 4;        // sphere-tracing steps of the clearance test along a walk segment
   int tune_sss_skip = 1;           // clearance grid: random-walk segments that provably hit nothing are not traced
   int tune_shade_threads = 512;    // block size of the shading kernels (<= pbr::kShadeBlock)
@@ -181,8 +184,6 @@ constexpr int kBlock = 128;
 // (tens of microseconds for a single warp), so a launch lasts at least budget x that: while the pool is busy a small
 // budget keeps the launch throughput-bound (more, shorter walk slices in flight); once only stragglers are left a
 // large budget saves host round-trips.
-constexpr uint32_t kSssBouncesDrain = 1024;
-constexpr uint32_t kDrainThreshold = 1u << 16;   // slots in flight below which the pool counts as draining
 int PersistentGrid(const Device& d, int blocks_per_sm) { return d.sm_count * blocks_per_sm; }
 
 uint32_t CountHairMaterials(const pbrhost::HostScene& h) {
@@ -356,10 +357,14 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
   // state after the set-up kernel (host knows it): hooks start with n paths, frames with nothing but samples to start
   bool have_active = (frame == nullptr), have_walk = false, samples_left = (frame != nullptr) && total > 0;
   uint64_t in_flight = ~0ull;   // paths + walks that the coming iteration works on (unknown before the first)
+  const double trace_t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   for (uint32_t it = 0; (have_active || have_walk || samples_left) && it < max_iterations; ++it) {
     if (cancel && *cancel) break;
     const uint32_t next = parity ^ 1u;
-    const uint32_t walk_budget = in_flight < kDrainThreshold ? kSssBouncesDrain : uint32_t(ctx->tune_walk_bounces);
+    // few paths left: longer slices (a launch lasts budget x the per-bounce latency of a lone lane, ~3-5 us)
+    uint32_t walk_budget = uint32_t(ctx->tune_walk_bounces);
+    if (in_flight < uint64_t(ctx->tune_drain_paths)) walk_budget = uint32_t(ctx->tune_drain_bounces);
+    else if (in_flight < uint64_t(ctx->tune_drain2_paths)) walk_budget = uint32_t(ctx->tune_drain2_bounces);
     const bool prof = ctx->profile;
     auto mark = [&](int k) { if (prof) cudaEventRecord(d.kev[k], st); };
     mark(0);
@@ -388,6 +393,13 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
       float ms[5] = {0, 0, 0, 0, 0};
       for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&ms[k], d.kev[k], d.kev[k + 1]);
       tm->regen_ms += ms[0]; tm->closest_ms += ms[1]; tm->shade_ms += ms[2]; tm->sss_ms += ms[3]; tm->any_ms += ms[4];
+    }
+    if (ctx->trace_iterations) {
+      const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+      fprintf(stderr, "iter %u t %.3f ms active %u walk %u done %u new %u surface %u diffuse %u exit %u shadow %u budget %u\n", it,
+              (now - trace_t0) * 1e3, d.h_counters[pbr::kNumActive0 + next], d.h_counters[pbr::kNumWalk0 + next],
+              d.h_counters[pbr::kNumDone0 + next], d.h_counters[pbr::kNumNew], d.h_counters[pbr::kNumSurface],
+              d.h_counters[pbr::kNumDiffuse], d.h_counters[pbr::kNumExit], d.h_counters[pbr::kNumShadow], walk_budget);
     }
     have_active = d.h_counters[pbr::kNumActive0 + next] > 0;
     have_walk = d.h_counters[pbr::kNumWalk0 + next] > 0;
@@ -665,7 +677,12 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_pool_div = std::max(1, env_int("PBRGPU_POOL_DIV", ctx->tune_pool_div));
   ctx->tune_pool_min_mi = std::min(64, std::max(1, env_int("PBRGPU_POOL_MIN_MI", ctx->tune_pool_min_mi)));
   ctx->tune_clear_march = std::min(64, std::max(1, env_int("PBRGPU_CLEAR_MARCH", ctx->tune_clear_march)));
+  ctx->tune_drain_paths = std::max(0, env_int("PBRGPU_DRAIN_PATHS", ctx->tune_drain_paths));
+  ctx->tune_drain_bounces = std::min(1 << 20, std::max(1, env_int("PBRGPU_DRAIN_BOUNCES", ctx->tune_drain_bounces)));
+  ctx->tune_drain2_paths = std::max(0, env_int("PBRGPU_DRAIN2_PATHS", ctx->tune_drain2_paths));
+  ctx->tune_drain2_bounces = std::min(1 << 20, std::max(1, env_int("PBRGPU_DRAIN2_BOUNCES", ctx->tune_drain2_bounces)));
   ctx->tune_sort_materials = env_int("PBRGPU_SORT_MATERIALS", ctx->tune_sort_materials);
+  ctx->trace_iterations = env_int("PBRGPU_TRACE_ITERATIONS", 0) != 0;
   ctx->tune_diffuse_blocks = std::max(1, env_int("PBRGPU_DIFFUSE_BLOCKS", ctx->tune_diffuse_blocks));
   ctx->tune_diffuse_threads = std::min(pbr::kDiffuseBlock, std::max(32, env_int("PBRGPU_DIFFUSE_THREADS", ctx->tune_diffuse_threads) & ~31));
   ctx->tune_shade_threads = std::min(pbr::kShadeBlock, std::max(32, env_int("PBRGPU_SHADE_THREADS", ctx->tune_shade_threads) & ~31));
