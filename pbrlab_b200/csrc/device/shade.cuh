@@ -20,7 +20,7 @@
 
 // g++ evaluates the two rng.Draw() arguments of UniformSampleSphere(rng.Draw(), rng.Draw())
 // (random-walk-sss.h:296) right to left: the FIRST draw becomes u2 (cos theta).  Checked against the compiled
-// reference by tests/test_shade_parity.py.
+// reference by tests/test_gpu_parity.py::test_shading_vertices (GPU) and tests/test_emul_parity.py::test_shading_vertices (g++ emulation).
 #ifndef PBR_SSS_SPHERE_DRAW_RIGHT_TO_LEFT
 #define PBR_SSS_SPHERE_DRAW_RIGHT_TO_LEFT 1
 #endif

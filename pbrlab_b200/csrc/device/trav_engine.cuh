@@ -3,7 +3,7 @@
 // written as a RESUMABLE per-lane state machine so that a persistent warp can replace a finished ray by a new one
 // while its neighbours are still traversing.
 //
-// Why: measured on B200 (profiles/r1a_*.txt) the one-ray-per-lane-until-all-32-finish form executed its node step
+// Why: measured on B200 (profiles/r1a_ncu.md) the one-ray-per-lane-until-all-32-finish form executed its node step
 // with 7.0 and its triangle test with 3.0 of 32 lanes active: path-tracing rays have wildly different traversal
 // lengths (2 nodes for a wall, 40 for Lucy) and the warp waits for its slowest lane.  Here a lane that finishes goes
 // idle only until `refill_min_idle` lanes are idle; then the warp runs one converged section that consumes the
@@ -134,7 +134,7 @@ __device__ __forceinline__ void TravTriStep(const SceneView& s, Trav& t) {
 // Pending CURVE candidates, warp-cooperatively.  Leaf boxes of thin diagonal segments are much fatter than the
 // ribbon: two of three candidates fail the cheap line-distance test (CurveMayHit).  Candidates are spread unevenly
 // (0 .. 10 per lane and node step), so a per-lane loop ran with 3-4 of 32 lanes and as many rounds as the busiest
-// lane had candidates (profiles/r1o: a quarter of the kernel's instructions, a third of its stall samples).  Here the
+// lane had candidates (profiles/r1o_hair_c3_ncu.md: a quarter of the kernel's instructions, a third of its stall samples).  Here the
 // candidates of ALL lanes are numbered by a prefix sum and tested 32 at a time, one per lane: the tester fetches the
 // owner's ray by shuffle and reports a pass by setting the candidate's bit in the owner's word of `pass_row` (shared
 // memory, one word per lane).  Afterwards a lane's pgroup holds the survivors only (t.checked).

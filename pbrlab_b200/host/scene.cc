@@ -145,9 +145,11 @@ void Scene::CommitHostOnly(void) {
           if (identity) {
             pools[attr] = {vbase, {nbase, tbase}};
           } else {
-            // Embree transforms instanced geometry (row-vector convention, v' = v * M); shading normals and light
-            // samples are NOT transformed by the reference (// TODO transform at src/scene.cc:219), so only
-            // positions are baked.
+            // Embree transforms instanced geometry (row-vector convention, v' = v * M); the reference transforms
+            // neither shading normals nor light samples (// TODO transform at src/scene.cc:219).  Positions are baked
+            // here, which the device's light sampling (shade.cuh: SampleAllLight) then reads as well: for a transformed
+            // EMISSIVE instance NEE samples the transformed surface, the reference the untransformed one — a known
+            // deviation; neither front-end creates non-identity transforms.
             for (size_t v = size_t(vbase) * 4; v < f.verts.size(); v += 4) {
               const float x = f.verts[v], y = f.verts[v + 1], z = f.verts[v + 2];
               for (int j = 0; j < 3; ++j)

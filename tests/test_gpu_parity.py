@@ -529,3 +529,29 @@ def test_multi_process_job_matches_one_device(built, tmp_path):
     rb = np.load(tmp_path / "r0_b.npz")
     assert np.array_equal(rb["count"], cb) and np.allclose(rb["rgba"], b, rtol=1e-4, atol=1e-4)
     one.close()
+
+
+def test_device_built_bvh_is_the_default_and_reports_the_host_builders_hits(built, monkeypatch):
+    """SURVEY §8(f)-1: pbrgpu_commit builds the triangle BVH on the GPU (csrc/bvh_device.cuh) unless told otherwise;
+    the host binned-SAH builder stays as the parity reference: both trees report the same hits on the golden batch
+    (different trees may break an exact tie between two triangles sharing an edge differently: counted)"""
+    g = golden("cornell_rays.npz")
+    rays = common.rays_from_f8(g["rays"])
+    res = {}
+    for mode in ("auto", "sah"):
+        monkeypatch.setenv("PBRGPU_BVH", mode)
+        sc = pb.Scene([scenes.cornell()])
+        ctx = sc.context()
+        ci = ctx.commit_info()
+        assert ci["tri_builder"] == ("ploc (device)" if mode == "auto" else "sah (host)"), ci
+        assert 0 < ci["tri_nodes"] < 362620 and 0 < ci["tri_depth"] <= 31 and ci["commit_s"] > 0
+        res[mode] = (ctx.trace(rays), ctx.occluded(rays), ci)
+        sc.close()
+    monkeypatch.delenv("PBRGPU_BVH")
+    (ha, oa, ca), (hs, osah, cs) = res["auto"], res["sah"]
+    same = (ha["instance_id"] == hs["instance_id"]) & (ha["geom_id"] == hs["geom_id"]) & (ha["prim_id"] == hs["prim_id"])
+    assert (~same).sum() <= max(1, len(rays) // 10000), int((~same).sum())
+    assert np.array_equal(ha["t"][same], hs["t"][same]) and np.array_equal(ha["u"][same], hs["u"][same])
+    assert np.array_equal(oa, osah)
+    common.dump_report("bvh_builders_cornell.json", {"device_ploc": ca, "host_sah": cs, "rays": len(rays),
+                                                     "different_primitive": int((~same).sum())})
