@@ -95,6 +95,8 @@ struct Device {
   DevBuf<float4> state0, state1, walk0, walk1, exit_rec, done0, done1, sh_o, sh_d, sh_c;
   DevBuf<uint32_t> q_surface, q_diffuse, q_hair, counters;
   DevBuf<unsigned long long> stats;
+  DevBuf<uint32_t> heavy, order, order_keys, order_scratch;   // longest-paths-first sample order (FrameParams::order)
+  DevBuf<uint8_t> order_tmp;
   pbr::WaveState wave;
   uint32_t wave_capacity = 0;
   // frame accumulators (device side of RenderLayer)
@@ -116,6 +118,7 @@ struct Device {
     state0.Free(); state1.Free(); walk0.Free(); walk1.Free(); exit_rec.Free(); done0.Free(); done1.Free();
     sh_o.Free(); sh_d.Free(); sh_c.Free();
     q_surface.Free(); q_hair.Free(); counters.Free(); stats.Free();
+    heavy.Free(); order.Free(); order_keys.Free(); order_scratch.Free(); order_tmp.Free();
     rgba.Free(); count.Free(); peer_tmp.Free();
     if (h_counters) cudaFreeHost(h_counters);
     if (h_stats) cudaFreeHost(h_stats);
@@ -167,6 +170,8 @@ struct pbrgpu_ctx {
   int tune_trace_blocks = 8, tune_shade_blocks = 1, tune_walk_blocks = 6;   // resident 128-thread blocks per SM
   int tune_diffuse_threads = 128, tune_diffuse_blocks = 6;   // launch shape of the diffuse-only shading kernel (sweep: 128 x 6 beats 256 x 3 by 2 %)
   int tune_sort_materials = 1;     // diffuse-only Principled materials get their own shading queue and kernel
+  // longest paths first (FrameParams::order): probing passes per pixel before the order is built, pixels per block
+  int tune_order = 1, tune_order_probe = 4, tune_order_block = 1 << 16;
 };
 
 namespace {
@@ -190,6 +195,14 @@ uint32_t CountHairMaterials(const pbrhost::HostScene& h) {
   uint32_t n = 0;
   for (const auto& m : h.materials) n += (m.type == 1u) ? 1u : 0u;
   return n;
+}
+
+// a Principled material whose subsurface weight passes kClosureWeightCutOff (cycles-principled-shader.cc:217): its
+// paths run random walks (looked up per Render(): live material edits can switch it on)
+bool HasScatteringMaterial(const pbrhost::HostScene& h) {
+  for (const auto& m : h.materials)
+    if (m.type == 0u && m.p[3] > 1e-3f) return true;
+  return false;
 }
 
 int UploadScene(pbrgpu_ctx* ctx, Device& d) {
@@ -310,6 +323,37 @@ int EnsureWave(pbrgpu_ctx* ctx, Device& d, uint32_t capacity) {
   w.q_surface = d.q_surface.ptr; w.q_diffuse = d.q_diffuse.ptr; w.q_hair = d.q_hair.ptr;
   w.sh_o = d.sh_o.ptr; w.sh_d = d.sh_d.ptr; w.sh_c = d.sh_c.ptr;
   w.counters = d.counters.ptr; w.stats = d.stats.ptr; w.capacity = d.wave_capacity;
+  w.heavy = nullptr;
+  return PBRGPU_OK;
+}
+
+// FrameParams::order: pixels sorted by the number of random walks their probing samples started (descending, stable:
+// raster order among equals), as one key kernel + one 8-bit radix sort on the device's stream
+__global__ void PixelOrderKeysKernel(const uint32_t* __restrict__ heavy, uint32_t npix, uint32_t* keys, uint32_t* ids) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  keys[i] = min(heavy[i], 255u);
+  ids[i] = i;
+}
+
+int BuildPixelOrder(pbrgpu_ctx* ctx, Device& d, uint32_t npix) {
+  PixelOrderKeysKernel<<<(npix + 255) / 256, 256, 0, d.stream>>>(d.heavy.ptr, npix, d.order_keys.ptr, d.order_scratch.ptr);
+  size_t tmp_bytes = d.order_tmp.count;
+  CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairsDescending(d.order_tmp.ptr, tmp_bytes, d.order_keys.ptr, d.order_keys.ptr + npix,
+                                                          d.order_scratch.ptr, d.order.ptr, int(npix), 0, 8, d.stream));
+  return PBRGPU_OK;
+}
+
+int EnsurePixelOrder(pbrgpu_ctx* ctx, Device& d, uint32_t npix) {
+  CUDA_TRY(ctx, d.heavy.Alloc(npix));
+  CUDA_TRY(ctx, d.order.Alloc(npix));
+  CUDA_TRY(ctx, d.order_keys.Alloc(size_t(npix) * 2));
+  CUDA_TRY(ctx, d.order_scratch.Alloc(npix));
+  size_t tmp_bytes = 0;
+  CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d.order_keys.ptr, d.order_keys.ptr + npix,
+                                                          d.order_scratch.ptr, d.order.ptr, int(npix), 0, 8, d.stream));
+  CUDA_TRY(ctx, d.order_tmp.Alloc(tmp_bytes));
+  CUDA_TRY(ctx, cudaMemsetAsync(d.heavy.ptr, 0, sizeof(uint32_t) * npix, d.stream));
   return PBRGPU_OK;
 }
 
@@ -328,7 +372,13 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
             size_t pass_stride, size_t pass_cap) {
   cudaStream_t st = d.stream;
   const SceneView& s = d.view;
-  const WaveState& w = d.wave;
+  WaveState w = d.wave;
+  // frames with a pixel order: the probing passes run first (and count walk starts per pixel), the frame is held at
+  // their end until the order is built (one key kernel + one radix sort on this stream, no extra synchronisation)
+  const unsigned long long probe_samples =
+      (frame && frame->order && frame->rest_passes) ? (unsigned long long)frame->probe_passes * frame->npix : 0ull;
+  bool order_ready = probe_samples == 0ull;
+  if (!order_ready) w.heavy = d.heavy.ptr;
   uint32_t parity = 0;
   const int grid_trace = PersistentGrid(d, ctx->tune_trace_blocks), grid_shade = PersistentGrid(d, ctx->tune_shade_blocks);
   const int grid_walk = PersistentGrid(d, ctx->tune_walk_blocks);
@@ -368,7 +418,8 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
     const bool prof = ctx->profile;
     auto mark = [&](int k) { if (prof) cudaEventRecord(d.kev[k], st); };
     mark(0);
-    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, regen, std::min(max_in_flight, w.capacity), total);
+    pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, regen, std::min(max_in_flight, w.capacity),
+                                                order_ready ? total : probe_samples);
     pbr::RetireKernel<<<grid_shade, 256, 0, st>>>(w, parity, rgba);
     mark(1);
     if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, rgba, sort);
@@ -404,6 +455,14 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
     have_active = d.h_counters[pbr::kNumActive0 + next] > 0;
     have_walk = d.h_counters[pbr::kNumWalk0 + next] > 0;
     samples_left = frame && d.h_stats[pbr::kStatNextSample] < total;
+    if (!order_ready && d.h_stats[pbr::kStatNextSample] >= probe_samples) {
+      // every probing sample has been through its first vertex: sort the pixels by the walks they started
+      int rc = BuildPixelOrder(ctx, d, frame->npix);
+      if (rc != PBRGPU_OK) return rc;
+      tm->launches += 2;
+      order_ready = true;
+      w.heavy = nullptr;
+    }
     in_flight = uint64_t(d.h_counters[pbr::kNumActive0 + next]) + d.h_counters[pbr::kNumWalk0 + next];
     if (samples_left) in_flight = ~0ull;
     if (frame && finish_pass) {
@@ -510,6 +569,21 @@ int RenderOnDevice(pbrgpu_ctx* ctx, Device& d, uint32_t width, uint32_t height, 
   frame.first_sample = sample_offset;
   frame.sample_stride = sample_stride;
   frame.rgba = d.rgba.ptr;
+  frame.order = nullptr;
+  frame.probe_passes = frame.rest_passes = 0;
+  frame.order_block = uint32_t(std::min(std::max(ctx->tune_order_block, 1024), 1 << 16));
+  // Longest paths first: only scenes whose paths differ by orders of magnitude (random walks) and frames long enough
+  // to have samples left after the probing passes; the probe is at most one pool fill
+  if (ctx->tune_order && HasScatteringMaterial(ctx->host) && local_spp < 65536u) {
+    const uint32_t probe = std::min<uint32_t>(uint32_t(ctx->tune_order_probe), std::max<uint32_t>(n_slots / npix, 1u));
+    if (local_spp > probe) {
+      rc = EnsurePixelOrder(ctx, d, npix);
+      if (rc != PBRGPU_OK) return rc;
+      frame.order = d.order.ptr;
+      frame.probe_passes = probe;
+      frame.rest_passes = local_spp - probe;
+    }
+  }
 
   CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
   pbr::ResetPoolKernel<<<1, 64, 0, d.stream>>>(d.wave);
@@ -682,6 +756,9 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_drain2_paths = std::max(0, env_int("PBRGPU_DRAIN2_PATHS", ctx->tune_drain2_paths));
   ctx->tune_drain2_bounces = std::min(1 << 20, std::max(1, env_int("PBRGPU_DRAIN2_BOUNCES", ctx->tune_drain2_bounces)));
   ctx->tune_sort_materials = env_int("PBRGPU_SORT_MATERIALS", ctx->tune_sort_materials);
+  ctx->tune_order = env_int("PBRGPU_ORDER", ctx->tune_order);
+  ctx->tune_order_probe = std::max(1, env_int("PBRGPU_ORDER_PROBE", ctx->tune_order_probe));
+  ctx->tune_order_block = std::max(1, env_int("PBRGPU_ORDER_BLOCK", ctx->tune_order_block));
   ctx->trace_iterations = env_int("PBRGPU_TRACE_ITERATIONS", 0) != 0;
   ctx->tune_diffuse_blocks = std::max(1, env_int("PBRGPU_DIFFUSE_BLOCKS", ctx->tune_diffuse_blocks));
   ctx->tune_diffuse_threads = std::min(pbr::kDiffuseBlock, std::max(32, env_int("PBRGPU_DIFFUSE_THREADS", ctx->tune_diffuse_threads) & ~31));

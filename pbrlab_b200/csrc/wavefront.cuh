@@ -88,6 +88,7 @@ struct WaveState {
   uint32_t* counters;            // kCounterCount
   unsigned long long* stats;     // kStatCount
   uint32_t capacity;
+  uint32_t* heavy;               // per pixel: random walks started by its first samples (sample ordering, FrameParams::order); null = off
 };
 
 constexpr uint32_t kNoPixel = 0xFFFFFFFFu;
@@ -311,6 +312,8 @@ __device__ __forceinline__ Routed RoutePath(const WaveState& w, uint32_t next_pa
 // id (base + k), so generation needs no atomic of its own.
 __global__ void BeginIterationKernel(uint32_t* counters, unsigned long long* stats, uint32_t cur_parity,
                                      uint32_t frame_mode, uint32_t capacity, unsigned long long total_samples) {
+  // total_samples: the frame's samples that may have been handed out by the end of this iteration (the host holds the
+  // frame at the end of its probing passes until the pixel order is built, FrameParams::order)
   const uint32_t i = threadIdx.x;
   __shared__ uint32_t n_new;
   if (i == 0) {
@@ -348,11 +351,40 @@ struct FrameParams {
   uint32_t first_sample;      // global index of local sample 0
   uint32_t sample_stride;     // global sample index = first_sample + local * stride
   float4* rgba;               // frame accumulator (sums); alpha counts the samples (render.cc:175-183)
+  // Longest paths first.  The reference hands out (tile, sample) jobs in raster order (render.cc:211-222); which
+  // sample runs when does not change the image (every (pixel, sample) has its own random stream).  Here the first
+  // `probe_passes` samples of every pixel run in that order and count, per pixel, the random walks they start; the
+  // remaining `rest_passes` samples run pixel block by pixel block (`order_block` pixels, sample-major inside a
+  // block) through `order` = the pixels sorted by that count, descending: the paths that live for hundreds of
+  // iterations start early and the frame drains with short ones.  order == null or rest_passes == 0: raster order.
+  const uint32_t* order;
+  uint32_t probe_passes, rest_passes, order_block;
 };
+
+// camera sample id -> (pixel, local sample index)
+__device__ __forceinline__ void SampleOfId(const FrameParams& f, unsigned long long id, uint32_t* pixel, uint32_t* s_local) {
+  const unsigned long long probe = (unsigned long long)f.probe_passes * f.npix;
+  if (f.order == nullptr || f.rest_passes == 0u || id < probe) {
+    const uint32_t s = uint32_t(id / f.npix);
+    *s_local = s;
+    *pixel = uint32_t(id - (unsigned long long)s * f.npix);
+    return;
+  }
+  const unsigned long long r = id - probe;
+  const unsigned long long per_block = (unsigned long long)f.order_block * f.rest_passes;
+  const uint32_t block = uint32_t(r / per_block);
+  const uint32_t within = uint32_t(r - (unsigned long long)block * per_block);
+  const uint32_t first = block * f.order_block;
+  const uint32_t width = min(f.order_block, f.npix - first);
+  const uint32_t s = within / width;
+  *s_local = f.probe_passes + s;
+  *pixel = f.order[first + (within - s * width)];
+}
 
 __device__ __forceinline__ RayT StartCameraPath(const WaveState& w, const FrameParams& f, uint32_t parity, uint32_t i,
                                                 unsigned long long id, uint32_t* pixel_out) {
-  const uint32_t s_local = uint32_t(id / f.npix), pixel = uint32_t(id - (unsigned long long)s_local * f.npix);
+  uint32_t s_local, pixel;
+  SampleOfId(f, id, &pixel, &s_local);
   const uint32_t x = pixel % f.cam.width, y = pixel / f.cam.width;
   Pcg32 rng;
   pcg32_srandom(&rng, f.seed + uint64_t(f.first_sample) + uint64_t(s_local) * f.sample_stride, uint64_t(pixel));
@@ -653,6 +685,7 @@ __device__ __forceinline__ void CommitOutcome(const WaveState& w, uint32_t next_
     StW(w, next_parity, k, kWalkThr, make_float4(o.throughput.x, o.throughput.y, o.throughput.z, r.pdf_prev));
     StW(w, next_parity, k, kWalkRad, make_float4(o.L.x, o.L.y, o.L.z, __uint_as_float(r.depth)));
     target = MakeTarget(kTargetWalk, k);
+    if (w.heavy) atomicAdd(&w.heavy[r.pixel], 1u);   // probing passes of a frame: this pixel's paths are long ones
   }
   if (shadow) StoreShadow(w, slots.idx[3], o.req, o.throughput, target);
 }
