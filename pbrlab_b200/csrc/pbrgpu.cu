@@ -76,6 +76,8 @@ struct Device {
   int id = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t walk_stream = nullptr;              // the random-walk kernels of an iteration run beside closest hit + shading
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t kev[12] = {};   // per-kernel-family timing of one iteration (profiling mode)
   // scene
@@ -125,6 +127,11 @@ struct Device {
     h_counters = nullptr; h_stats = nullptr;
     for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     for (auto& e : kev) { if (e) cudaEventDestroy(e); e = nullptr; }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    ev_fork = ev_join = nullptr;
+    if (walk_stream) cudaStreamDestroy(walk_stream);
+    walk_stream = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -172,6 +179,12 @@ struct pbrgpu_ctx {
   int tune_sort_materials = 1;     // diffuse-only Principled materials get their own shading queue and kernel
   // longest paths first (FrameParams::order): probing passes per pixel before the order is built, pixels per block
   int tune_order = 1, tune_order_probe = 4, tune_order_block = 1 << 16;
+  // Walk kernels on their own stream, beside closest hit + shading of the same iteration (they only share atomically
+  // appended output streams).  Measured (profiles/r2r_tune_overlap.log): with the full launch shapes the two kernels
+  // do not share an SM — the walk blocks fill the register file — but the closest-hit blocks move in as the walk
+  // kernel's last long items drain: +3.5 %.  Shapes that do fit together (3 + 3..6 blocks) are slower than running one
+  // after the other: both kernels need all the warps they can get.  Profiling mode runs the families in sequence.
+  int tune_overlap = 1, tune_trace_blocks_overlap = 8, tune_walk_blocks_overlap = 6;
 };
 
 namespace {
@@ -380,8 +393,12 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
   bool order_ready = probe_samples == 0ull;
   if (!order_ready) w.heavy = d.heavy.ptr;
   uint32_t parity = 0;
+  const bool single = (max_iterations == 1u);
+  const bool overlap = ctx->tune_overlap && !ctx->profile && !single && frame != nullptr;
+  cudaStream_t wst = overlap ? d.walk_stream : st;
   const int grid_trace = PersistentGrid(d, ctx->tune_trace_blocks), grid_shade = PersistentGrid(d, ctx->tune_shade_blocks);
-  const int grid_walk = PersistentGrid(d, ctx->tune_walk_blocks);
+  const int grid_closest = overlap ? PersistentGrid(d, ctx->tune_trace_blocks_overlap) : grid_trace;
+  const int grid_walk = PersistentGrid(d, overlap ? ctx->tune_walk_blocks_overlap : ctx->tune_walk_blocks);
   const int grid_diffuse = PersistentGrid(d, ctx->tune_diffuse_blocks);
   const bool curves = s.num_curves != 0u;
   const uint32_t refill = curves ? ctx->tune_refill_curves : ctx->tune_refill;
@@ -394,11 +411,10 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
   // hits are routed by material CLASS (a hair material on a triangle goes to q_hair as well, as the reference's
   // Shader() dispatches on the material type, shader.cc:8-34), so the kernel runs whenever that queue can fill
   const bool hair = s.num_curves != 0u || s.num_hair_materials != 0u;
-  const bool single = (max_iterations == 1u);
-  auto launch_walk = [&](uint32_t cur, uint32_t budget) {
-    if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, st>>>(s, w, cur, budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
-    else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, st>>>(s, w, cur, budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
-    pbr::SssExitKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, cur, flags);
+  auto launch_walk = [&](uint32_t cur, uint32_t budget, cudaStream_t ws) {
+    if (curves) pbr::SssWalkKernel<true><<<grid_walk, kBlock, 0, ws>>>(s, w, cur, budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
+    else pbr::SssWalkKernel<false><<<grid_walk, kBlock, 0, ws>>>(s, w, cur, budget, ctx->tune_refill_sss, ctx->tune_prim_lanes_sss);
+    pbr::SssExitKernel<<<grid_shade, ctx->tune_shade_threads, 0, ws>>>(s, w, cur, flags);
   };
   auto launch_any = [&](uint32_t next) {
     if (curves) pbr::TraceAnyKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, next, refill_any, ctx->tune_prim_lanes);
@@ -420,20 +436,29 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
     mark(0);
     pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, regen, std::min(max_in_flight, w.capacity),
                                                 order_ready ? total : probe_samples);
+    // the walks in flight (W[cur]) do not depend on anything this iteration's closest-hit and shading kernels do
+    const bool fork = overlap && have_walk;
+    if (fork) {
+      CUDA_TRY(ctx, cudaEventRecord(d.ev_fork, st));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(wst, d.ev_fork, 0));
+      launch_walk(parity, walk_budget, wst);
+      CUDA_TRY(ctx, cudaEventRecord(d.ev_join, wst));
+    }
     pbr::RetireKernel<<<grid_shade, 256, 0, st>>>(w, parity, rgba);
     mark(1);
-    if (curves) pbr::TraceClosestKernel<true><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, rgba, sort);
-    else pbr::TraceClosestKernel<false><<<grid_trace, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, rgba, sort);
+    if (curves) pbr::TraceClosestKernel<true><<<grid_closest, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, rgba, sort);
+    else pbr::TraceClosestKernel<false><<<grid_closest, kBlock, 0, st>>>(s, w, parity, refill, ctx->tune_prim_lanes, frame ? *frame : no_frame, rgba, sort);
     mark(2);
     pbr::ShadeSurfaceKernel<false><<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, parity, flags);
     if (sort) pbr::ShadeSurfaceKernel<true><<<grid_diffuse, ctx->tune_diffuse_threads, 0, st>>>(s, w, parity, flags);
     if (hair) pbr::ShadeHairKernel<<<grid_shade, ctx->tune_shade_threads, 0, st>>>(s, w, parity, flags);
     mark(3);
-    launch_walk(parity, walk_budget);
+    if (fork) CUDA_TRY(ctx, cudaStreamWaitEvent(st, d.ev_join, 0));
+    else if (have_walk) launch_walk(parity, walk_budget, st);   // (W[cur] is empty otherwise: the host has its length)
     mark(4);
     launch_any(next);
     mark(5);
-    tm->launches += (hair ? 8 : 7) + (sort ? 1 : 0);
+    tm->launches += (hair ? 6 : 5) + (sort ? 1 : 0) + (have_walk ? 2 : 0);
     tm->closest_launches += 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(d.h_counters, w.counters, sizeof(uint32_t) * pbr::kCounterCount,
                                   cudaMemcpyDeviceToHost, st));
@@ -479,7 +504,7 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
     pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, 0u, w.capacity, 0ull);
     tm->launches += 1;
     if (have_walk) {
-      launch_walk(parity, 0x7fffffffu);
+      launch_walk(parity, 0x7fffffffu, st);
       launch_any(next);
       tm->launches += 3;
     }
@@ -756,6 +781,9 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_drain2_paths = std::max(0, env_int("PBRGPU_DRAIN2_PATHS", ctx->tune_drain2_paths));
   ctx->tune_drain2_bounces = std::min(1 << 20, std::max(1, env_int("PBRGPU_DRAIN2_BOUNCES", ctx->tune_drain2_bounces)));
   ctx->tune_sort_materials = env_int("PBRGPU_SORT_MATERIALS", ctx->tune_sort_materials);
+  ctx->tune_overlap = env_int("PBRGPU_OVERLAP", ctx->tune_overlap);
+  ctx->tune_trace_blocks_overlap = std::max(1, env_int("PBRGPU_TRACE_BLOCKS_OVERLAP", ctx->tune_trace_blocks_overlap));
+  ctx->tune_walk_blocks_overlap = std::max(1, env_int("PBRGPU_WALK_BLOCKS_OVERLAP", ctx->tune_walk_blocks_overlap));
   ctx->tune_order = env_int("PBRGPU_ORDER", ctx->tune_order);
   ctx->tune_order_probe = std::max(1, env_int("PBRGPU_ORDER_PROBE", ctx->tune_order_probe));
   ctx->tune_order_block = std::max(1, env_int("PBRGPU_ORDER_BLOCK", ctx->tune_order_block));
@@ -774,6 +802,9 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
     cudaDeviceProp prop;
     if (cudaSetDevice(id) != cudaSuccess || cudaGetDeviceProperties(&prop, id) != cudaSuccess ||
         cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&d.walk_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&d.ev[0]) != cudaSuccess || cudaEventCreate(&d.ev[1]) != cudaSuccess) {
       g_create_error = std::string("pbrgpu_create: cannot initialise device: ") + cudaGetErrorString(cudaGetLastError());
       delete ctx;
