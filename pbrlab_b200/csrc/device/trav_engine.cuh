@@ -209,6 +209,48 @@ __device__ __forceinline__ void TravRibbonStep(const SceneView& s, Trav& t) {
   }
 }
 
+// One trip of the engine between two converged sections: a node phase (lanes without pending primitives), the curve
+// candidate rejection, a primitive phase and the ribbon phase (see TravEngine).  Called by all 32 lanes.
+template <bool ANY, bool HAS_CURVES, bool STATS>
+__device__ __forceinline__ void TravTrip(const SceneView& s, Trav& t, uint2* __restrict__ stack, uint32_t* pass_row,
+                                         uint32_t prim_min_lanes) {
+  const bool node_work = t.active && t.pgroup.y == 0u && (!HAS_CURVES || t.held == kInvalid);
+  if (node_work) {
+    TravNodeStep<HAS_CURVES, STATS, false>(s, t, stack);   // prefetching the next node was measured: 1.6x slower
+    TravAdvance<HAS_CURVES>(s, t);
+  }
+  if (HAS_CURVES) {
+    // curve candidates: cheap rejection now, across the warp; a survivor (if any) is held for the ribbon phase
+    const bool fresh = t.active && t.curves && !t.checked && t.held == kInvalid && t.pgroup.y != 0u;
+    if (__ballot_sync(0xffffffffu, fresh) != 0u) TravCurveCullWarp<STATS>(s, t, fresh, pass_row);
+    if (t.active && t.curves && t.checked && t.held == kInvalid) {
+      if (t.pgroup.y != 0u) TravCurveTake(s, t);
+      else TravAdvance<HAS_CURVES>(s, t);
+    }
+  }
+  const bool tri_work = t.active && t.pgroup.y != 0u && !(HAS_CURVES && t.curves);
+  const unsigned prim = __ballot_sync(0xffffffffu, tri_work);
+  const unsigned node = __ballot_sync(0xffffffffu, t.active && t.pgroup.y == 0u && (!HAS_CURVES || t.held == kInvalid));
+  if (prim != 0u && (uint32_t(__popc(prim)) >= prim_min_lanes || node == 0u)) {
+    if (tri_work) {
+      TravTriStep<ANY, STATS>(s, t);
+      if (t.active) TravAdvance<HAS_CURVES>(s, t);
+    }
+  }
+  if (HAS_CURVES) {
+    // ribbon phase: when enough lanes hold a candidate, or when nobody can make progress without it
+    const bool holding = t.active && t.held != kInvalid;
+    const unsigned hold = __ballot_sync(0xffffffffu, holding);
+    const unsigned free_lanes = __ballot_sync(0xffffffffu, t.active && t.held == kInvalid);
+    if (hold != 0u && (uint32_t(__popc(hold)) >= s.ribbon_min_lanes || free_lanes == 0u)) {
+      if (holding) {
+        TravRibbonStep<ANY>(s, t);
+        if (t.active) TravAdvance<HAS_CURVES>(s, t);
+      }
+    }
+  }
+}
+
 // The engine loop.  `Client` supplies the converged section:
 //   bool Wants(const Trav& t, bool exhausted)  — per lane, for idle lanes: could a Refill give this lane work
 //        (a finished walk segment to continue, or a work source that is not dry yet)?
@@ -249,41 +291,7 @@ __device__ __forceinline__ void TravEngine(const SceneView& s, Client& client, u
         continue;
       }
     }
-    const bool node_work = t.active && t.pgroup.y == 0u && (!HAS_CURVES || t.held == kInvalid);
-    if (node_work) {
-      TravNodeStep<HAS_CURVES, STATS, false>(s, t, stack);   // prefetching the next node was measured: 1.6x slower
-      TravAdvance<HAS_CURVES>(s, t);
-    }
-    if (HAS_CURVES) {
-      // curve candidates: cheap rejection now, across the warp; a survivor (if any) is held for the ribbon phase
-      const bool fresh = t.active && t.curves && !t.checked && t.held == kInvalid && t.pgroup.y != 0u;
-      if (__ballot_sync(0xffffffffu, fresh) != 0u) TravCurveCullWarp<STATS>(s, t, fresh, pass_row);
-      if (t.active && t.curves && t.checked && t.held == kInvalid) {
-        if (t.pgroup.y != 0u) TravCurveTake(s, t);
-        else TravAdvance<HAS_CURVES>(s, t);
-      }
-    }
-    const bool tri_work = t.active && t.pgroup.y != 0u && !(HAS_CURVES && t.curves);
-    const unsigned prim = __ballot_sync(0xffffffffu, tri_work);
-    const unsigned node = __ballot_sync(0xffffffffu, t.active && t.pgroup.y == 0u && (!HAS_CURVES || t.held == kInvalid));
-    if (prim != 0u && (uint32_t(__popc(prim)) >= prim_min_lanes || node == 0u)) {
-      if (tri_work) {
-        TravTriStep<ANY, STATS>(s, t);
-        if (t.active) TravAdvance<HAS_CURVES>(s, t);
-      }
-    }
-    if (HAS_CURVES) {
-      // ribbon phase: when enough lanes hold a candidate, or when nobody can make progress without it
-      const bool holding = t.active && t.held != kInvalid;
-      const unsigned hold = __ballot_sync(0xffffffffu, holding);
-      const unsigned free_lanes = __ballot_sync(0xffffffffu, t.active && t.held == kInvalid);
-      if (hold != 0u && (uint32_t(__popc(hold)) >= s.ribbon_min_lanes || free_lanes == 0u)) {
-        if (holding) {
-          TravRibbonStep<ANY>(s, t);
-          if (t.active) TravAdvance<HAS_CURVES>(s, t);
-        }
-      }
-    }
+    TravTrip<ANY, HAS_CURVES, STATS>(s, t, stack, pass_row, prim_min_lanes);
   }
   client.End(t);
 }
