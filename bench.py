@@ -13,7 +13,8 @@ BASELINE.json configs[1] (C2: 1920x1080, 1024 spp, Lucy random-walk SSS) unless 
            every GPU instead.
   value    Msamples/s of the whole job with the scene and the accumulators resident in HBM (pbrgpu_render_device),
            CUDA events around the K blocking steps, max over ranks.
-  e2e      the same through the reference-facing C++ call pbrlab::Render() with HOST RenderLayer buffers: the material
+  e2e      the same through the reference-facing C++ call pbrlab::Render() with HOST RenderLayer buffers (one
+           RenderLayer kept across the steps, as the reference's GUI / CLI hold one): the material
            table goes host->device every step (Render() re-uploads it, the reference reads materials live) and the
            sums come back device->host (rank 0).
   roofline the dominant kernel family; achieved = algorithmic bytes per unit (DESIGN.md §2.2 / SURVEY §8(d)) x units
@@ -283,7 +284,7 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, spp_overrid
 
     def step_e2e():
         """host-to-host step through pbrlab::Render(): materials H2D, RenderLayer D2H (complete on rank 0)"""
-        return scene.render(w, h, spp_total, seed=seed)
+        return scene.render_layer(w, h, spp_total, seed=seed)
 
     def barrier():
         if world > 1:

@@ -235,6 +235,9 @@ def host_lib():
         L.pbrhost_last_error.restype = C.c_char_p
         L.pbrhost_render.restype = C.c_double
         L.pbrhost_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.pbrhost_render_layer.restype = C.c_double
+        L.pbrhost_render_layer.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
+                                           C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_uint32))]
         L.pbrhost_render_cancel.restype = C.c_double
         L.pbrhost_render_cancel.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
@@ -441,6 +444,18 @@ class Scene:
         sec = self.lib.pbrhost_render(self.h, width, height, spp, seed, _p(rgba), _p(count))
         if sec < 0:
             raise RuntimeError("Render failed: " + self.lib.pbrhost_last_error().decode())
+        return rgba, count, sec
+
+    def render_layer(self, width, height, spp, seed=1234567890):
+        """pbrlab::Render() into the RenderLayer the scene keeps across frames (as the reference's GUI / CLI hold one):
+        returns (rgba sums, count, seconds) as VIEWS of the layer's host buffers, valid until the next call."""
+        pr = C.POINTER(C.c_float)()
+        pc = C.POINTER(C.c_uint32)()
+        sec = self.lib.pbrhost_render_layer(self.h, width, height, spp, seed, C.byref(pr), C.byref(pc))
+        if sec < 0:
+            raise RuntimeError("Render failed: " + self.lib.pbrhost_last_error().decode())
+        rgba = np.ctypeslib.as_array(pr, shape=(height, width, 4))
+        count = np.ctypeslib.as_array(pc, shape=(height, width))
         return rgba, count, sec
 
     def render_cancelled(self, width, height, spp, cancel_at_pass, seed=1234567890):

@@ -870,10 +870,11 @@ int pbrgpu_set_curves(pbrgpu_ctx* ctx, const float* xyzr, uint32_t nverts, const
 int pbrgpu_set_materials(pbrgpu_ctx* ctx, const pbrgpu_material* materials, uint32_t n) {
   if (!ctx) return PBRGPU_ERR_INVALID;
   if (ctx->committed) {   // live edit: validate against the committed geometry BEFORE the host table is replaced
-    for (const auto& id : ctx->host.tri_ids)
-      if (id.w != PBRGPU_INVALID_ID && id.w >= n) { ctx->error = "pbrgpu_set_materials: table shrank below ids in use"; return PBRGPU_ERR_INVALID; }
-    for (const auto& id : ctx->host.curve_ids)
-      if (id.w != PBRGPU_INVALID_ID && id.w >= n) { ctx->error = "pbrgpu_set_materials: table shrank below ids in use"; return PBRGPU_ERR_INVALID; }
+    // (Render() re-uploads the table every frame: the highest id in use was recorded by the commit, no scan here)
+    if (ctx->host.any_material_id && ctx->host.max_material_id >= n) {
+      ctx->error = "pbrgpu_set_materials: table shrank below ids in use";
+      return PBRGPU_ERR_INVALID;
+    }
   }
   if (!ctx->host.SetMaterials(materials, n)) {   // validates everything else before it mutates (scene_host.cc)
     ctx->error = ctx->host.error;

@@ -272,11 +272,17 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
   const uint32_t nt = num_tris(), nc = num_curves();
   if (nt == 0 && nc == 0) { error = "pbrgpu_commit: empty scene"; return false; }
   if (!CheckTextureIds()) return false;
+  max_material_id = 0;
+  any_material_id = false;
   for (auto& id : tri_ids) {
-    if (id.w != PBRGPU_INVALID_ID && id.w >= materials.size()) { error = "pbrgpu_commit: material id out of range"; return false; }
+    if (id.w == PBRGPU_INVALID_ID) continue;
+    if (id.w >= materials.size()) { error = "pbrgpu_commit: material id out of range"; return false; }
+    max_material_id = std::max(max_material_id, id.w); any_material_id = true;
   }
   for (auto& id : curve_ids) {
-    if (id.w != PBRGPU_INVALID_ID && id.w >= materials.size()) { error = "pbrgpu_commit: material id out of range"; return false; }
+    if (id.w == PBRGPU_INVALID_ID) continue;
+    if (id.w >= materials.size()) { error = "pbrgpu_commit: material id out of range"; return false; }
+    max_material_id = std::max(max_material_id, id.w); any_material_id = true;
   }
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   pbrbvh::BuildParams prm;

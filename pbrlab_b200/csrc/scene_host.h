@@ -50,6 +50,8 @@ struct HostScene {
   float clear_org[3] = {0, 0, 0}, clear_inv_cell = 0.f, clear_quantum = 0.f;
   uint32_t clear_dims[3] = {0, 0, 0};
   bool committed = false;
+  uint32_t max_material_id = 0;   // highest material id any committed primitive refers to (live edits check against it)
+  bool any_material_id = false;
   double build_seconds = 0.0;
   // Which builder Commit() uses for the two BVHs: PBRGPU_BVH_TRIS / PBRGPU_BVH_CURVES (or PBRGPU_BVH for both) =
   // "sah" (host binned SAH, bvh_builder.cc), "ploc" (the data-parallel builder of bvh_ploc.h: on the device through

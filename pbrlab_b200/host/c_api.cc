@@ -7,6 +7,9 @@
 #include <cstdio>
 #include <cstring>
 #include <exception>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -21,9 +24,18 @@
 
 namespace {
 thread_local std::string g_error;
+// RenderLayers of pbrhost_render_layer, one per scene
+std::mutex g_layers_mutex;
+std::map<void*, std::unique_ptr<pbrlab::RenderLayer>> g_layers;
 }
 
 extern "C" {
+
+void pbrhost_release_layer(void* s) {
+  std::lock_guard<std::mutex> lock(g_layers_mutex);
+  g_layers.erase(s);
+}
+
 
 struct pbrhost_flat {   // views into Scene::Flat(); valid until the scene is destroyed or re-committed
   const float* verts; uint32_t nverts;
@@ -73,7 +85,10 @@ void* pbrhost_scene_create_on(int nfiles, const char** files, int commit_to_devi
   }
   return scene;
 }
-void pbrhost_scene_destroy(void* s) { delete static_cast<pbrlab::Scene*>(s); }
+void pbrhost_scene_destroy(void* s) {
+  pbrhost_release_layer(s);
+  delete static_cast<pbrlab::Scene*>(s);
+}
 
 void pbrhost_scene_flat(void* s, pbrhost_flat* o) {
   const pbrlab::FlatScene& f = static_cast<pbrlab::Scene*>(s)->Flat();
@@ -107,6 +122,35 @@ void pbrhost_scene_flat(void* s, pbrhost_flat* o) {
 }
 
 void* pbrhost_scene_ctx(void* s) { return static_cast<pbrlab::Scene*>(s)->DeviceContext(); }
+
+// pbrlab::Render() into a RenderLayer that lives as long as the scene, the way the reference's GUI and CLI hold one
+// across frames (pc/pbrlab-gui.cc:207-238): *rgba / *count point INTO the layer (valid until the next call for this
+// scene or its destruction).  Returns seconds inside Render(), < 0 on failure.
+double pbrhost_render_layer(void* s, uint32_t w, uint32_t h, uint32_t spp, uint64_t seed, float** rgba, uint32_t** count) {
+  try {
+    pbrlab::SetRenderSeed(seed);
+    std::atomic_bool cancel(false);
+    std::atomic_size_t finish_pass(0);
+    pbrlab::RenderLayer* layer = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_layers_mutex);
+      std::unique_ptr<pbrlab::RenderLayer>& slot = g_layers[s];
+      if (!slot) slot.reset(new pbrlab::RenderLayer());
+      layer = slot.get();
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    const bool ok = pbrlab::Render(*static_cast<pbrlab::Scene*>(s), w, h, spp, cancel, layer, &finish_pass);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (!ok) { g_error = pbrlab::LastRenderError(); return -1.0; }
+    if (finish_pass.load() != spp) { g_error = "finish_pass != num_sample"; return -1.0; }
+    *rgba = layer->rgba.data();
+    *count = layer->count.data();
+    return std::chrono::duration<double>(t1 - t0).count();
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1.0;
+  }
+}
 
 // pbrlab::Render() through the public C++ entry point.  Returns seconds inside Render(), < 0 on failure.
 double pbrhost_render(void* s, uint32_t w, uint32_t h, uint32_t spp, uint64_t seed, float* rgba, uint32_t* count) {

@@ -1,11 +1,24 @@
 #!/bin/bash
-# multi-GPU bench line, as the driver launches it: scripts/gpu_scale.sh TAG N [extra bench args]
-TAG=${1:-scale}; N=${2:-2}; shift; shift
+# strong scaling of the fixed C2 frame on 1, 2, 4, 8 GPUs of one box as the driver launches it, + the multi-GPU tests
+TAG=${1:-r2x}; NS=${2:-"1 2 4 8"}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-  bench.py --gpus $N --steps 2 --warmup 3 "$@" > gpurun_out/${TAG}_n$N.json 2> gpurun_out/${TAG}_n$N.err
-echo "exit $?"; grep '^{' gpurun_out/${TAG}_n$N.json | cut -c1-1500; tail -5 gpurun_out/${TAG}_n$N.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
-  bench.py --impl reference --gpus $N --steps 1 --warmup 1 > gpurun_out/${TAG}_n${N}_ref.json 2>> gpurun_out/${TAG}_n$N.err
-grep '^{' gpurun_out/${TAG}_n${N}_ref.json | cut -c1-600
+nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/${TAG}_smi.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -k "multi_process or multi_device" > gpurun_out/${TAG}_tests.log 2>&1
+echo "tests exit $?" >> gpurun_out/${TAG}_tests.log
+tail -3 gpurun_out/${TAG}_tests.log
+for n in $NS; do
+  if [ "$n" = "1" ]; then
+    timeout 900 python bench.py --gpus 1 --steps 4 --warmup 3 --no-other-configs --no-cpu-baseline > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
+  else
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $n --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_n$n.json 2> gpurun_out/${TAG}_bench_n$n.err
+  fi
+  python - <<PY
+import json
+try:
+    d = json.loads([l for l in open("gpurun_out/${TAG}_bench_n$n.json") if l.startswith("{")][-1])
+    print("n=%d value %.1f e2e %.1f ms/step %.1f scaling %s spp/gpu %s" % (d["n_gpus"], d["value"], d["e2e"]["value"], d["ms_per_step"], d["scaling"], d["config"]["spp_per_gpu"]))
+except Exception as e:
+    print("n=$n: no line", e)
+PY
+done

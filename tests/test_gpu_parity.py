@@ -222,6 +222,26 @@ def test_live_material_edit(cornell_gpu):
     assert np.allclose(again, base, rtol=1e-4, atol=1e-4)
 
 
+def test_render_into_a_layer_kept_across_frames(cornell_gpu):
+    """pbrlab::Render() into ONE RenderLayer held across frames (how the reference's GUI / CLI call it, and what
+    bench.py's e2e times): same sums as a fresh layer, the buffers are reused, a smaller and a larger frame in between
+    resize it, and a live edit that shrinks the material table below an id in use is refused without a scan"""
+    scene, ctx = cornell_gpu
+    fresh, fcount, _ = scene.render(96, 64, 8, seed=9)
+    a, ac, _ = scene.render_layer(96, 64, 8, seed=9)
+    assert np.allclose(a, fresh, rtol=1e-4, atol=1e-5) and np.array_equal(ac, fcount)
+    addr = a.ctypes.data
+    small, sc_, _ = scene.render_layer(32, 32, 4, seed=9)
+    assert np.all(sc_ == 4) and np.all(small[..., 3] == 4.0)
+    b, bc, _ = scene.render_layer(96, 64, 8, seed=9)
+    assert b.ctypes.data == addr                                  # same host buffers
+    assert np.allclose(b, fresh, rtol=1e-4, atol=1e-5) and np.array_equal(bc, fcount)
+    words = scene.flat().materials.copy()
+    with pytest.raises(RuntimeError):
+        ctx.set_materials(words[:1])                              # ids up to len(words) - 1 are in use
+    ctx.set_materials(words)
+
+
 def test_edge_cases(built):
     """empty / degenerate inputs: errors, not crashes"""
     ctx = pb.Context()
