@@ -1,7 +1,6 @@
 // The small plain-data types of the reference's public API, kept field for field so that code written against
 // pbrlab compiles against this host layer unchanged: Ray (reference src/ray.h:9-14), RenderConfig
-// (src/render-config.h:9-18), Attribute / CurveAttribute (src/mesh/attribute.h:6-15).  One header here; ray.h,
-// render-config.h and mesh/attribute.h forward to it.
+// (src/render-config.h:9-18), Attribute / CurveAttribute (src/mesh/attribute.h:6-15), in one header.
 #ifndef PBRLAB_B200_API_TYPES_H_
 #define PBRLAB_B200_API_TYPES_H_
 #include <cstdint>

@@ -7,7 +7,7 @@
 #include <string>
 #include <vector>
 
-#include "attribute.h"
+#include "../api-types.h"
 
 namespace pbrlab {
 class CubicBezierCurveMesh {

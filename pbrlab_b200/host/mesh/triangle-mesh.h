@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../type.h"
-#include "attribute.h"
+#include "../api-types.h"
 
 namespace pbrlab {
 

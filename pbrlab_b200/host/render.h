@@ -12,7 +12,7 @@
 #include <cstdint>
 #include <string>
 
-#include "ray.h"
+#include "api-types.h"
 #include "render-layer.h"
 #include "scene.h"
 #include "type.h"

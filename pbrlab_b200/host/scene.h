@@ -11,7 +11,7 @@
 #include "light-manager.h"
 #include "material-param.h"
 #include "mesh-instance.h"
-#include "ray.h"
+#include "api-types.h"
 #include "texture.h"
 
 struct pbrgpu_ctx;
