@@ -12,7 +12,9 @@ w, h, spp = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 warm = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 files = sys.argv[5:] if len(sys.argv) > 5 else [scenes.cornell()]
 hair = dict(n_strands=50000, n_points=21, radius=1.2, length=2.5, thickness=0.008)
-if files == ["c3"]:
+if files in (["c1"], ["c2"]):
+    files = [scenes.cornell()]
+elif files == ["c3"]:
     files = [scenes.light_stage(), scenes.cyhair(center=(-2.5, 3.5, 0.0), **hair)]
 elif files == ["c4"]:
     files = [scenes.cornell(), scenes.cyhair(center=(-2.5, 6.0, 0.0), **hair)]
