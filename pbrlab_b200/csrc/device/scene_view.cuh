@@ -42,6 +42,7 @@ struct SceneView {
   const uint32_t* curve_sub;   // curve BVH leaf order: (slot << 2) | first quad; the BVH primitive is a PART of a segment
   uint32_t curve_part_quads;   // quads (quarter sub-segments) per part: 4 (whole segments), 2 or 1
   uint32_t ribbon_min_lanes;   // traversal engine: lanes holding a curve candidate that trigger a ribbon phase
+  uint32_t thin_spread;        // traversal engine: short launches spread their items over all warps (LanesFor)
   const float4* curve_cull;    // slot order, 2 per segment: (c0, capsule radius around the line c0c3), (c3 - c0, |c3 - c0|), see CurveMayHit; may be null
   uint32_t num_tris, num_curves;
   uint32_t bias_magic;         // kBiasMagic (traverse.cuh), as a run-time value on purpose

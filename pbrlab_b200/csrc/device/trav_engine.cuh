@@ -251,6 +251,22 @@ __device__ __forceinline__ void TravTrip(const SceneView& s, Trav& t, uint2* __r
   }
 }
 
+// Lanes of a warp that fetch work when a launch has `n` items for `gridDim.x * blockDim.x / 32` warps: all 32 as long
+// as there is more work than lanes; with less (the last iterations of a frame: a few thousand paths and walks, each a
+// long dependent chain) the items are spread over ALL warps, n / warps per warp.  A warp that carries one walk runs
+// only that walk's instructions; a warp that carries 32 runs the scatter step and seven traversal trips for every
+// bounce of any of them, and the frame ends when the slowest chain does.
+__device__ __forceinline__ uint32_t LanesFor(const SceneView& s, uint32_t n) {
+  if (!s.thin_spread) return 32u;
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  const uint32_t per_warp = (n + warps - 1u) / warps;
+  return per_warp < 1u ? 1u : (per_warp > 32u ? 32u : per_warp);
+}
+__device__ __forceinline__ uint32_t ThresholdFor(uint32_t lanes, uint32_t dflt) {
+  const uint32_t t = (lanes * 3u + 3u) / 4u;   // three quarters of the lanes in use
+  return t < dflt ? t : dflt;
+}
+
 // The engine loop.  `Client` supplies the converged section:
 //   bool Wants(const Trav& t, bool exhausted)  — per lane, for idle lanes: could a Refill give this lane work
 //        (a finished walk segment to continue, or a work source that is not dry yet)?
@@ -259,6 +275,8 @@ __device__ __forceinline__ void TravTrip(const SceneView& s, Trav& t, uint2* __r
 //        its next ray: on success it calls TravBegin (t.active == true).  Returns true when this lane found the
 //        work source empty.
 //   void End(const Trav& t)  — after the loop.
+//   uint32_t RefillThreshold(uint32_t dflt)  — idle lanes that trigger a Refill (dflt, or fewer when the client lets
+//        only some lanes of a warp fetch work, see LanesFor).
 // A Refill happens when at least `refill_min_idle` idle lanes want one, or when nobody is traversing.  The loop ends
 // when no lane is active after a Refill and the source is dry.
 // Between refills every trip runs a node phase (lanes without pending primitives) and, when at least
@@ -278,6 +296,7 @@ __device__ __forceinline__ void TravEngine(const SceneView& s, Client& client, u
   t.held = kInvalid;
   t.n_nodes = 0; t.n_prims = 0;
   bool exhausted = false;   // warp-uniform: the work source ran dry
+  refill_min_idle = client.RefillThreshold(refill_min_idle);
   for (;;) {
     const unsigned act = __ballot_sync(0xffffffffu, t.active);
     const unsigned want = __ballot_sync(0xffffffffu, !t.active && client.Wants(t, exhausted));

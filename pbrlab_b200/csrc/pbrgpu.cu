@@ -179,6 +179,7 @@ struct pbrgpu_ctx {
   int tune_sort_materials = 1;     // diffuse-only Principled materials get their own shading queue and kernel
   // longest paths first (FrameParams::order): probing passes per pixel before the order is built, pixels per block
   int tune_order = 1, tune_order_probe = 4, tune_order_block = 1 << 16;
+  int tune_thin_spread = 1;        // launches with fewer items than lanes give every warp n / warps of them (trav_engine.cuh: LanesFor)
   // Walk kernels on their own stream, beside closest hit + shading of the same iteration (they only share atomically
   // appended output streams).  Measured (profiles/r2r_tune_overlap.log): with the full launch shapes the two kernels
   // do not share an SM — the walk blocks fill the register file — but the closest-hit blocks move in as the walk
@@ -284,6 +285,7 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   v.curve_nodes = g_cn; v.curve_data = g_cd; v.curve_prim = d.curve_prim.ptr;
   v.curve_sub = d.curve_sub.ptr; v.curve_part_quads = h.curve_part_quads;
   v.ribbon_min_lanes = ctx->tune_ribbon_lanes;
+  v.thin_spread = ctx->tune_thin_spread ? 1u : 0u;
   v.curve_cull = h.curve_cull.empty() ? nullptr : reinterpret_cast<const float4*>(d.curve_cull.ptr);
   v.num_tris = h.num_tris(); v.num_curves = h.num_curves();
   v.bias_magic = pbr::kBiasMagic;
@@ -785,6 +787,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_trace_blocks_overlap = std::max(1, env_int("PBRGPU_TRACE_BLOCKS_OVERLAP", ctx->tune_trace_blocks_overlap));
   ctx->tune_walk_blocks_overlap = std::max(1, env_int("PBRGPU_WALK_BLOCKS_OVERLAP", ctx->tune_walk_blocks_overlap));
   ctx->tune_order = env_int("PBRGPU_ORDER", ctx->tune_order);
+  ctx->tune_thin_spread = env_int("PBRGPU_THIN", ctx->tune_thin_spread);
   ctx->tune_order_probe = std::max(1, env_int("PBRGPU_ORDER_PROBE", ctx->tune_order_probe));
   ctx->tune_order_block = std::max(1, env_int("PBRGPU_ORDER_BLOCK", ctx->tune_order_block));
   ctx->trace_iterations = env_int("PBRGPU_TRACE_ITERATIONS", 0) != 0;

@@ -462,7 +462,7 @@ struct ClosestClient {
   const FrameParams& frame;      // frame mode: how camera samples are numbered
   float4* rgba;                  // accumulator of retired paths (frame.rgba, or the hook's per-path buffer)
   const bool sort_materials;     // route diffuse-only materials to their own shading queue
-  uint32_t cur, n_active, n;
+  uint32_t cur, n_active, n, lanes;
   unsigned long long sample_base;
   uint32_t item = 0, pixel = kNoPixel;
   bool has_result = false, fresh = false;   // fresh: a camera ray (radiance 0, pixel known)
@@ -473,12 +473,15 @@ struct ClosestClient {
       : s(s_), w(w_), frame(frame_), rgba(rgba_), sort_materials(sort_), cur(cur_parity),
         n_active(w_.counters[kNumActive0 + cur_parity]),
         n(w_.counters[kNumActive0 + cur_parity] + w_.counters[kNumNew]),
+        lanes(LanesFor(s_, w_.counters[kNumActive0 + cur_parity] + w_.counters[kNumNew])),
         sample_base(w_.stats[kStatSampleBase]) {}
-  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
+  __device__ __forceinline__ bool Fetches() const { return (threadIdx.x & 31u) < lanes; }
+  __device__ __forceinline__ uint32_t RefillThreshold(uint32_t dflt) const { return ThresholdFor(lanes, dflt); }
+  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || (!exhausted && Fetches()); }
 
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     const bool finished = !t.active && has_result;
-    const bool need = !exhausted && !t.active;
+    const bool need = !exhausted && !t.active && Fetches();
     // ---- (1) finished rays: miss -> retire, else the shading queue of the material's class
     int kind = -1;   // -1 nothing, 0 miss, 1 general surface queue, 2 hair queue, 3 diffuse-only queue
     const HitT hit = t.hit;
@@ -781,7 +784,7 @@ __global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, Wave
 struct SssClient {
   const SceneView& s;
   const WaveState& w;
-  uint32_t cur, next, n, max_bounces;
+  uint32_t cur, next, n, max_bounces, lanes;
   uint32_t item = 0, budget = 0, pixel = 0;
   bool has_walk = false;
   bool skipped_seg = false;   // the current segment was answered by the clearance grid, not traced
@@ -791,8 +794,11 @@ struct SssClient {
   uint32_t rays = 0, skipped = 0;
 
   __device__ __forceinline__ SssClient(const SceneView& s_, const WaveState& w_, uint32_t cur_parity, uint32_t max_b)
-      : s(s_), w(w_), cur(cur_parity), next(cur_parity ^ 1u), n(w_.counters[kNumWalk0 + cur_parity]), max_bounces(max_b) {}
-  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_walk || !exhausted; }
+      : s(s_), w(w_), cur(cur_parity), next(cur_parity ^ 1u), n(w_.counters[kNumWalk0 + cur_parity]), max_bounces(max_b),
+        lanes(LanesFor(s_, w_.counters[kNumWalk0 + cur_parity])) {}
+  __device__ __forceinline__ bool Fetches() const { return (threadIdx.x & 31u) < lanes; }
+  __device__ __forceinline__ uint32_t RefillThreshold(uint32_t dflt) const { return ThresholdFor(lanes, dflt); }
+  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_walk || (!exhausted && Fetches()); }
 
   __device__ __forceinline__ void StartSegment(Trav& t) {
     SssPrepareSegment(&rng, &walk, &cpdf);
@@ -822,7 +828,7 @@ struct SssClient {
       has_walk = go_on;
     }
     // ---- (2) the three output streams and the work fetch (lanes without a walk): one atomic instruction
-    const bool need = !exhausted && !t.active && !has_walk;
+    const bool need = !exhausted && !t.active && !has_walk && Fetches();
     const Append5 app = Append5Issue(&w.counters[kNumExit], &w.counters[kNumDone0 + next],
                                      &w.counters[kNumWalk0 + next], &w.counters[kFetchWalk], nullptr, to_exit,
                                      to_done, to_park, need, false);
@@ -936,17 +942,19 @@ __global__ void __launch_bounds__(kShadeBlock) SssExitKernel(SceneView s, WaveSt
 struct ShadowClient {
   const SceneView& s;
   const WaveState& w;
-  uint32_t n, next;
+  uint32_t n, next, lanes;
   float4 c;
   bool has_result = false;
   uint32_t rays = 0;
 
   __device__ __forceinline__ ShadowClient(const SceneView& s_, const WaveState& w_, uint32_t next_parity)
-      : s(s_), w(w_), n(w_.counters[kNumShadow]), next(next_parity) {}
-  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
+      : s(s_), w(w_), n(w_.counters[kNumShadow]), next(next_parity), lanes(LanesFor(s_, w_.counters[kNumShadow])) {}
+  __device__ __forceinline__ bool Fetches() const { return (threadIdx.x & 31u) < lanes; }
+  __device__ __forceinline__ uint32_t RefillThreshold(uint32_t dflt) const { return ThresholdFor(lanes, dflt); }
+  __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || (!exhausted && Fetches()); }
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     const unsigned lane = threadIdx.x & 31u;
-    const bool need = !exhausted && !t.active;
+    const bool need = !exhausted && !t.active && Fetches();
     const unsigned m_need = __ballot_sync(0xffffffffu, need);
     uint32_t fetch_base = 0;
     if (lane == 0u && m_need) fetch_base = atomicAdd(&w.counters[kFetchShadow], uint32_t(__popc(m_need)));
@@ -1030,6 +1038,7 @@ struct BatchClient {
   __device__ __forceinline__ BatchClient(const SceneView& s_, const float4* r, uint64_t n_, float4* tuv, uint4* ids,
                                          float4* ng, uint8_t* occ, uint32_t* f, unsigned long long* st)
       : s(s_), rays(r), n(n_), hits_tuv(tuv), hits_ids(ids), hits_ng(ng), occluded(occ), fetch(f), stats(st) {}
+  __device__ __forceinline__ uint32_t RefillThreshold(uint32_t dflt) const { return dflt; }
   __device__ __forceinline__ bool Wants(const Trav&, bool exhausted) const { return has_result || !exhausted; }
   __device__ __forceinline__ bool Refill(Trav& t, bool exhausted) {
     if (!t.active && has_result) {
