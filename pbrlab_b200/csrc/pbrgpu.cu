@@ -168,7 +168,7 @@ struct pbrgpu_ctx {
   // that is only a few pool-fills long (strong scaling: 1/8 of the samples per GPU) spends a smaller share of its
   // time ramping up and draining with a smaller pool
   int tune_pool_div = 8, tune_pool_min_mi = 4;
-  int tune_drain_paths = 1 << 16, tune_drain_bounces = 256;    // fewer paths in flight than this: long walk slices (sweep: profiles/r2j_tune_drain_stages.log)
+  int tune_drain_paths = 1 << 16, tune_drain_bounces = 48;     // fewer paths in flight than this: longer walk slices (sweeps: profiles/r2j_tune_drain_stages.log; after the thin spreading 48 instead of 256, profiles/r3e_tune_*.log)
   int tune_drain2_paths = 0, tune_drain2_bounces = 64;          // an intermediate stage (off by default)
   int tune_clear_march = 4;        // sphere-tracing steps of the clearance test along a walk segment
   int tune_sss_skip = 1;           // clearance grid: random-walk segments that provably hit nothing are not traced
