@@ -53,7 +53,7 @@ WORKLOADS = {
     "c5": ("synthetic displaced 20M-triangle OBJ, GGX + SSS materials, 3840x2160 1024spp", 3840, 2160, 1024),
 }
 # (spp, cpu-reference spp) of the reduced runs in other_configs
-OTHER = {"c1": (64, 16), "c3": (64, 8), "c4": (64, 2), "c5": (64, 2)}
+OTHER = {"c1": (64, 16), "c3": (128, 8), "c4": (128, 2), "c5": (128, 2)}
 T_START = time.time()
 
 
@@ -445,7 +445,7 @@ def main():
     others = []
     if world == 1 and not args.no_other_configs and args.workload == "c2" and not args.spp:
         # rough cost of a reduced run incl. scene generation, parsing, commit and its CPU baseline (seconds)
-        cost = {"c1": 15, "c3": 40, "c4": 60, "c5": 240}
+        cost = {"c1": 15, "c3": 45, "c4": 90, "c5": 260}
         for name in ("c1", "c3", "c4", "c5"):
             if time.time() - T_START + cost[name] > args.budget_s:
                 others.append({"workload": name, "skipped": "time budget (%.0f s of --budget-s %.0f used)" % (time.time() - T_START, args.budget_s)})
