@@ -776,7 +776,7 @@ __global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, Wave
 //   * a walk gets at most `max_bounces` bounces per launch; if it is still inside the medium its record is appended
 //     to W[next] and the next iteration goes on with it.  A launch therefore never outlives its queue by more than
 //     max_bounces bounces (and the walks are re-balanced over the warps every time: larger budgets were measured and
-//     are slower, profiles/r2a_tune.log), and because the pool is kept full by new camera samples, long walks cost
+//     are slower, profiles/r2a_tune_diffuse_pipe_walk_budget_pool.log), and because the pool is kept full by new camera samples, long walks cost
 //     capacity, not idle SMs;
 //   * entering the medium is part of shade_surface, leaving it (exit vertex: NEE + diffuse bounce,
 //     cycles-principled-shader.cc:187-216) is sss_exit: both are rare per bounce and ran at 2-3 lanes per warp when

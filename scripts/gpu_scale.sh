@@ -22,3 +22,9 @@ except Exception as e:
     print("n=$n: no line", e)
 PY
 done
+# one process, one context over several devices (ncclCommInitAll inside the library)
+if [ -n "$MULTI_DEVICE" ]; then
+  for n in $MULTI_DEVICE; do
+    timeout 600 python scripts/time_multi_device.py $n 1024 2>&1 | grep "devices\|multi-device" | tee -a gpurun_out/${TAG}_multi_device.log
+  done
+fi
