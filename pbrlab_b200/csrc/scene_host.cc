@@ -392,7 +392,13 @@ bool HostScene::Commit(const float* bmin_in, const float* bmax_in) {
     {
       std::string which;
       const auto tcb = std::chrono::steady_clock::now();
-      if (!BuildBvh(boxes.data(), nparts, prm, &curve_bvh, &which, true)) return false;
+      // a curve candidate costs more than a triangle (rejection test, then now and again the ribbon test): smaller
+      // leaves.  Sweep (profiles/r3i_tune_curve_sah.log): prim_cost 0.6 -> 2.5 is +2.5 % on C4, neutral on C3.
+      pbrbvh::BuildParams cprm = prm;
+      cprm.prim_cost = 2.5f;
+      if (const char* e = getenv("PBRGPU_CURVE_PRIM_COST")) cprm.prim_cost = std::max(0.01f, float(atof(e)));
+      if (const char* e = getenv("PBRGPU_CURVE_LEAF")) cprm.max_leaf_prims = std::min(3, std::max(1, atoi(e)));
+      if (!BuildBvh(boxes.data(), nparts, cprm, &curve_bvh, &which, true)) return false;
       bvh_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - tcb).count();
       if (!nt) last_builder = which;
     }
