@@ -140,10 +140,11 @@ PBR_HD void KatEval(int op, const float* prm, const float* in, float* out, uint3
 // Reference-order megakernel form of GetRadiance (src/render.cc:24-90): one thread walks one path to the end,
 // tracing its own shadow rays.  It is the cross-check for the wavefront scheduling (same per-vertex functions, so
 // the two must agree to the last bit up to the order of the two NEE additions) and what the CPU tests run.
-PBR_HD vec3 PathRadiance(const SceneView& s, RayT ray, Pcg32* rng, uint64_t* ray_counts /* closest, shadow, sss */) {
-  vec3 L(0.f), throughput(1.f);
-  float pdf_prev = 0.f;
-  for (uint32_t depth = 0;; ++depth) {
+// `L`, `throughput`, `pdf_prev`, `depth`: the state a path carries from one vertex to the next (render.cc:79-86), so a
+// path can be taken up in the middle — the wavefront hands the last few paths of a frame to FinishPathsKernel.
+PBR_HD vec3 PathRadianceFrom(const SceneView& s, RayT ray, Pcg32* rng, vec3 L, vec3 throughput, float pdf_prev,
+                             uint32_t depth, uint64_t* ray_counts /* closest, shadow, sss */) {
+  for (;; ++depth) {
     if (IsBlack(throughput)) break;
     HitT hit;
     const bool found = TraceClosest<false>(s, ray, &hit, nullptr);
@@ -177,6 +178,10 @@ PBR_HD vec3 PathRadiance(const SceneView& s, RayT ray, Pcg32* rng, uint64_t* ray
     ray.tmax = kInf;
   }
   return L;
+}
+
+PBR_HD vec3 PathRadiance(const SceneView& s, RayT ray, Pcg32* rng, uint64_t* ray_counts /* closest, shadow, sss */) {
+  return PathRadianceFrom(s, ray, rng, vec3(0.f), vec3(1.f), 0.f, 0u, ray_counts);
 }
 
 }  // namespace pbr

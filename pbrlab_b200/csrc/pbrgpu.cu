@@ -179,6 +179,7 @@ struct pbrgpu_ctx {
   int tune_sort_materials = 1;     // diffuse-only Principled materials get their own shading queue and kernel
   // longest paths first (FrameParams::order): probing passes per pixel before the order is built, pixels per block
   int tune_order = 1, tune_order_probe = 4, tune_order_block = 1 << 16;
+  int tune_finish_paths = 8192;    // fewer paths + walks in flight than this at the end of a frame: FinishPathsKernel runs them to their end (0: off)
   int tune_thin_spread = 1;        // launches with fewer items than lanes give every warp n / warps of them (trav_engine.cuh: LanesFor)
   // Walk kernels on their own stream, beside closest hit + shading of the same iteration (they only share atomically
   // appended output streams).  Measured (profiles/r2r_tune_overlap.log): with the full launch shapes the two kernels
@@ -438,6 +439,36 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
     mark(0);
     pbr::BeginIterationKernel<<<1, 32, 0, st>>>(w.counters, w.stats, parity, regen, std::min(max_in_flight, w.capacity),
                                                 order_ready ? total : probe_samples);
+    if (frame && !single && !samples_left && in_flight < uint64_t(ctx->tune_finish_paths)) {
+      // the last paths of the frame: one thread each to the end instead of an iteration per vertex
+      pbr::RetireKernel<<<grid_shade, 256, 0, st>>>(w, parity, rgba);
+      mark(1);
+      pbr::FinishPathsKernel<<<grid_trace, kBlock, 0, st>>>(s, w, parity, rgba);
+      mark(2); mark(3); mark(4); mark(5);
+      tm->launches += 3;
+      CUDA_TRY(ctx, cudaMemcpyAsync(d.h_stats, w.stats, sizeof(unsigned long long) * pbr::kStatCount,
+                                    cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      if (prof) {
+        float ms[2] = {0, 0};
+        cudaEventElapsedTime(&ms[0], d.kev[0], d.kev[1]);
+        cudaEventElapsedTime(&ms[1], d.kev[1], d.kev[2]);
+        tm->regen_ms += ms[0]; tm->closest_ms += ms[1];
+      }
+      if (ctx->trace_iterations) {
+        const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        fprintf(stderr, "iter %u t %.3f ms: the last %llu paths and walks run to their end in one launch\n", it,
+                (now - trace_t0) * 1e3, (unsigned long long)in_flight);
+      }
+      have_active = have_walk = false;
+      if (finish_pass) {
+        const size_t passes = size_t(d.h_stats[pbr::kStatRetired] / frame->npix);
+        const size_t global = std::min(pass_cap, pass_offset + passes * pass_stride);
+        if (global > *finish_pass) *finish_pass = global;
+      }
+      parity = next;   // D[next] is empty (BeginIterationKernel): nothing left for the retire after the loop
+      break;
+    }
     // the walks in flight (W[cur]) do not depend on anything this iteration's closest-hit and shading kernels do
     const bool fork = overlap && have_walk;
     if (fork) {
@@ -788,6 +819,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_walk_blocks_overlap = std::max(1, env_int("PBRGPU_WALK_BLOCKS_OVERLAP", ctx->tune_walk_blocks_overlap));
   ctx->tune_order = env_int("PBRGPU_ORDER", ctx->tune_order);
   ctx->tune_thin_spread = env_int("PBRGPU_THIN", ctx->tune_thin_spread);
+  ctx->tune_finish_paths = std::max(0, env_int("PBRGPU_FINISH_PATHS", ctx->tune_finish_paths));
   ctx->tune_order_probe = std::max(1, env_int("PBRGPU_ORDER_PROBE", ctx->tune_order_probe));
   ctx->tune_order_block = std::max(1, env_int("PBRGPU_ORDER_BLOCK", ctx->tune_order_block));
   ctx->trace_iterations = env_int("PBRGPU_TRACE_ITERATIONS", 0) != 0;

@@ -39,6 +39,7 @@
 
 #include "device/shade.cuh"
 #include "device/trav_engine.cuh"
+#include "kat.cuh"
 
 namespace pbr {
 
@@ -934,6 +935,101 @@ __global__ void __launch_bounds__(kShadeBlock) SssExitKernel(SceneView s, WaveSt
     base = slots.next_fetch;
   }
   WarpTally(&w.stats[kStatVertices], shaded);
+}
+
+// ------------------------------------------------------------------------------------------------ the last paths
+// The end of a frame is a handful of paths, each a chain of dependent steps; an iteration of the wavefront moves every
+// one of them by ONE vertex (or one slice of a walk) and costs eight kernel launches and a host round trip — 80 to
+// 350 us for 16 us of work on a path's critical chain.  Once fewer than a few thousand paths and walks are in flight
+// the host launches this kernel instead of an iteration: every remaining path of S[cur] and every remaining walk of
+// W[cur] is taken up where it stands by ONE thread and run to its end with the megakernel form of the path loop
+// (kat.cuh: PathRadianceFrom — the same per-vertex functions, so the same radiance; the walk segments are answered
+// by the clearance field or traced exactly as in SssWalkKernel), items spread one per warp first (a warp runs the
+// union of its lanes' instruction streams).  The result goes straight into the frame (render.cc:175-183).
+__global__ void __launch_bounds__(128) FinishPathsKernel(SceneView s, WaveState w, uint32_t cur, float4* rgba) {
+  const uint32_t n_act = w.counters[kNumActive0 + cur], n_walk = w.counters[kNumWalk0 + cur];
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  uint64_t counts[3] = {0ull, 0ull, 0ull};
+  uint32_t skipped = 0, retired = 0;
+  for (uint32_t item = (threadIdx.x & 31u) * warps + warp; item < n_act + n_walk; item += 32u * warps) {
+    RayT ray;
+    vec3 L, thr;
+    float pdf_prev;
+    uint32_t depth, pixel;
+    Pcg32 rng;
+    bool alive = true;
+    if (item < n_act) {
+      ray = LoadRay(w, cur, item);
+      const float4 t4 = LdS(w, cur, item, kThr), r4 = LdS(w, cur, item, kRad);
+      thr = vec3(t4.x, t4.y, t4.z); pdf_prev = t4.w;
+      L = vec3(r4.x, r4.y, r4.z); depth = __float_as_uint(r4.w);
+      rng = RngFrom(LdS(w, cur, item, kRng));
+      pixel = __float_as_uint(LdS(w, cur, item, kPix).x);
+    } else {
+      // a walk: the rest of its bounces (random-walk-sss.h:281-383), then the exit vertex as in SssExitKernel
+      const uint32_t k = item - n_act;
+      const float4 a = LdW(w, cur, k, kWalkA), b = LdW(w, cur, k, kWalkB), c = LdW(w, cur, k, kWalkC),
+                   d = LdW(w, cur, k, kWalkD), nn = LdW(w, cur, k, kWalkN);
+      rng = RngFrom(LdW(w, cur, k, kWalkRng));
+      SssWalkState walk;
+      walk.sigma_t = vec3(a.x, a.y, a.z);
+      walk.sigma_s = vec3(b.x, b.y, b.z);
+      walk.throughput = vec3(a.w, b.w, c.w);
+      walk.ray.o = vec3(c.x, c.y, c.z);
+      walk.ray.d = vec3(d.x, d.y, d.z);
+      walk.ray.tmin = d.w;
+      walk.ray.tmax = kInf;
+      walk.bounce = __float_as_uint(nn.x);
+      pixel = __float_as_uint(nn.y);
+      const float4 t4 = LdW(w, cur, k, kWalkThr), r4 = LdW(w, cur, k, kWalkRad);
+      thr = vec3(t4.x, t4.y, t4.z); pdf_prev = t4.w;
+      L = vec3(r4.x, r4.y, r4.z); depth = __float_as_uint(r4.w);
+      HitT hit;
+      SssStep st;
+      do {
+        vec3 cpdf;
+        SssPrepareSegment(&rng, &walk, &cpdf);
+        bool is_hit = false;
+        if (SegmentIsClear(s, walk.ray.o, walk.ray.d, walk.ray.tmax * 1.001f)) {
+          ++skipped;
+        } else {
+          is_hit = TraceClosest<false>(s, walk.ray, &hit, nullptr);
+          ++counts[2];
+        }
+        st = SssFinishSegment(is_hit, hit.t, &rng, &walk, cpdf);
+      } while (st == kSssContinue);
+      if (st == kSssAbsorbed) {
+        alive = false;   // throughput 0: the path ends with the radiance it holds
+      } else {
+        const RayT entry_ray = RayFrom(LdW(w, cur, k, kWalkRayO), LdW(w, cur, k, kWalkRayD));
+        const HitT entry_hit = HitFrom(LdW(w, cur, k, kWalkHit));
+        const Surface entry_si = MakeSurface(s, entry_ray, entry_hit);
+        const Frame entry_frame = PrincipledFrame(entry_si);
+        VertexResult vr;
+        vr.P = entry_si.P;
+        vr.shadow[1].active = false;
+        SssFinish(s, entry_si, entry_frame, walk, hit, &rng, &vr);
+        if (vr.shadow[1].active) {
+          ++counts[1];
+          if (!TraceAny<false>(s, vr.shadow[1].ray, nullptr)) L = L + thr * vr.shadow[1].contribute;
+        }
+        thr = vr.throughput * thr;
+        pdf_prev = vr.pdf;
+        ray.o = vr.P; ray.d = vr.wi; ray.tmin = 1e-3f; ray.tmax = kInf;
+        depth += 1u;
+      }
+    }
+    if (alive) L = PathRadianceFrom(s, ray, &rng, L, thr, pdf_prev, depth, counts);
+    if (pixel != kNoPixel) {
+      atomicAdd(&rgba[pixel], make_float4(L.x, L.y, L.z, 1.0f));
+      ++retired;
+    }
+  }
+  WarpTally(&w.stats[kStatClosest], uint32_t(counts[0]));
+  WarpTally(&w.stats[kStatShadow], uint32_t(counts[1]));
+  WarpTally(&w.stats[kStatSss], uint32_t(counts[2]));
+  WarpTally(&w.stats[kStatSssSkipped], skipped);
+  WarpTally(&w.stats[kStatRetired], retired);
 }
 
 // ------------------------------------------------------------------------------------------------ shadow rays

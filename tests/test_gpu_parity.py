@@ -222,6 +222,31 @@ def test_live_material_edit(cornell_gpu):
     assert np.allclose(again, base, rtol=1e-4, atol=1e-4)
 
 
+def test_frame_schedule_switches_do_not_change_the_image(built, monkeypatch):
+    """what only changes WHEN a sample or a vertex runs leaves the frame as it is, up to the order of the float sums:
+    raster order vs longest paths first (PBRGPU_ORDER), the walk kernels beside closest hit + shading (PBRGPU_OVERLAP),
+    thin spreading of short launches (PBRGPU_THIN), and the last paths run to their end by one thread each
+    (PBRGPU_FINISH_PATHS: FinishPathsKernel takes paths and walks up in the middle) vs one iteration per vertex"""
+    frames = []
+    for env in ({}, {"PBRGPU_ORDER": "0"}, {"PBRGPU_OVERLAP": "0"}, {"PBRGPU_THIN": "0"}, {"PBRGPU_FINISH_PATHS": "0"},
+                {"PBRGPU_FINISH_PATHS": "1000000"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        sc = pb.Scene([scenes.cornell()])
+        rgba, count = sc.context().render(256, 192, 24, seed=77)
+        st = sc.context().stats()
+        assert np.all(count == 24) and st["paths"] == 256 * 192 * 24
+        frames.append(rgba)
+        sc.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    for f in frames[1:]:
+        # (one path in a few hundred thousand sums its two NEE terms in the other order: compare per-pixel sums loosely,
+        # the whole image tightly)
+        assert np.allclose(frames[0], f, rtol=2e-3, atol=1e-3), float(np.abs(frames[0] - f).max())
+        assert abs(float(f[..., :3].sum()) - float(frames[0][..., :3].sum())) <= 1e-5 * float(frames[0][..., :3].sum())
+
+
 def test_render_into_a_layer_kept_across_frames(cornell_gpu):
     """pbrlab::Render() into ONE RenderLayer held across frames (how the reference's GUI / CLI call it, and what
     bench.py's e2e times): same sums as a fresh layer, the buffers are reused, a smaller and a larger frame in between
