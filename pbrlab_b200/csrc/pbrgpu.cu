@@ -179,6 +179,7 @@ struct pbrgpu_ctx {
   int tune_sort_materials = 1;     // diffuse-only Principled materials get their own shading queue and kernel
   // longest paths first (FrameParams::order): probing passes per pixel before the order is built, pixels per block
   int tune_order = 1, tune_order_probe = 4, tune_order_block = 1 << 16;
+  int tune_finish_blocks = 4;      // its blocks per SM (128 registers per thread: four fit)
   int tune_finish_paths = 8192;    // fewer paths + walks in flight than this at the end of a frame: FinishPathsKernel runs them to their end (0: off)
   int tune_thin_spread = 1;        // launches with fewer items than lanes give every warp n / warps of them (trav_engine.cuh: LanesFor)
   // Walk kernels on their own stream, beside closest hit + shading of the same iteration (they only share atomically
@@ -443,7 +444,8 @@ int RunPool(pbrgpu_ctx* ctx, Device& d, const pbr::FrameParams* frame, float4* r
       // the last paths of the frame: one thread each to the end instead of an iteration per vertex
       pbr::RetireKernel<<<grid_shade, 256, 0, st>>>(w, parity, rgba);
       mark(1);
-      pbr::FinishPathsKernel<<<grid_trace, kBlock, 0, st>>>(s, w, parity, rgba);
+      // (every block resident at once: a chain that waits for a second wave of blocks is a longer frame)
+      pbr::FinishPathsKernel<<<PersistentGrid(d, ctx->tune_finish_blocks), kBlock, 0, st>>>(s, w, parity, rgba);
       mark(2); mark(3); mark(4); mark(5);
       tm->launches += 3;
       CUDA_TRY(ctx, cudaMemcpyAsync(d.h_stats, w.stats, sizeof(unsigned long long) * pbr::kStatCount,
@@ -820,6 +822,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_order = env_int("PBRGPU_ORDER", ctx->tune_order);
   ctx->tune_thin_spread = env_int("PBRGPU_THIN", ctx->tune_thin_spread);
   ctx->tune_finish_paths = std::max(0, env_int("PBRGPU_FINISH_PATHS", ctx->tune_finish_paths));
+  ctx->tune_finish_blocks = std::max(1, env_int("PBRGPU_FINISH_BLOCKS", ctx->tune_finish_blocks));
   ctx->tune_order_probe = std::max(1, env_int("PBRGPU_ORDER_PROBE", ctx->tune_order_probe));
   ctx->tune_order_block = std::max(1, env_int("PBRGPU_ORDER_BLOCK", ctx->tune_order_block));
   ctx->trace_iterations = env_int("PBRGPU_TRACE_ITERATIONS", 0) != 0;

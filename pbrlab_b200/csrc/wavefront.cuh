@@ -946,7 +946,7 @@ __global__ void __launch_bounds__(kShadeBlock) SssExitKernel(SceneView s, WaveSt
 // (kat.cuh: PathRadianceFrom — the same per-vertex functions, so the same radiance; the walk segments are answered
 // by the clearance field or traced exactly as in SssWalkKernel), items spread one per warp first (a warp runs the
 // union of its lanes' instruction streams).  The result goes straight into the frame (render.cc:175-183).
-__global__ void __launch_bounds__(128) FinishPathsKernel(SceneView s, WaveState w, uint32_t cur, float4* rgba) {
+__global__ void __launch_bounds__(128, 4) FinishPathsKernel(SceneView s, WaveState w, uint32_t cur, float4* rgba) {
   const uint32_t n_act = w.counters[kNumActive0 + cur], n_walk = w.counters[kNumWalk0 + cur];
   const uint32_t warps = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   uint64_t counts[3] = {0ull, 0ull, 0ull};

@@ -1,6 +1,7 @@
 #include "render.h"
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <exception>
 #include <mutex>
@@ -50,18 +51,25 @@ bool Render(const Scene& scene, const uint32_t width, const uint32_t height, con
   // The C ABI polls a plain int and reports progress through a plain size_t; a watcher mirrors the caller's atomics.
   volatile int cancel_int = cancel_render_flag.load() ? 1 : 0;
   size_t progress = 0;
-  std::atomic_bool done(false);
+  bool done = false;
+  std::mutex done_mutex;
+  std::condition_variable done_cv;
   std::thread watcher([&]() {
-    while (!done.load()) {
+    std::unique_lock<std::mutex> lock(done_mutex);
+    while (!done) {
       if (cancel_render_flag.load()) cancel_int = 1;
       const size_t p = *const_cast<volatile size_t*>(&progress);
       if (p > finish_pass->load()) finish_pass->store(p);
-      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+      done_cv.wait_for(lock, std::chrono::milliseconds(1));   // (woken at once when the frame is done)
     }
   });
   const int rc = pbrgpu_render(ctx, width, height, num_sample, g_render_seed.load(), 0, 1, &cancel_int,
                                layer->rgba.data(), layer->count.data(), &progress);
-  done = true;
+  {
+    std::lock_guard<std::mutex> lock(done_mutex);
+    done = true;
+  }
+  done_cv.notify_one();
   watcher.join();
   if (progress > finish_pass->load()) finish_pass->store(progress);
   if (rc != PBRGPU_OK) {
