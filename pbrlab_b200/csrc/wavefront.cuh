@@ -26,6 +26,11 @@
 //
 // One iteration:   begin -> retire D[cur] -> trace_closest (+ camera rays for the free capacity, misses retired in
 //                  place) -> shade_surface, shade_diffuse, shade_hair -> sss_walk -> sss_exit -> trace_any
+//                  (sss_walk + sss_exit on their own stream beside trace_closest + shading: they only share
+//                  atomically appended output streams; joined before trace_any)
+// The end of a frame: camera samples start longest paths first (FrameParams::order), launches with
+// fewer items than lanes spread them over all warps (trav_engine.cuh: LanesFor), and the last few thousand paths
+// and walks are run to their end by FinishPathsKernel instead of one iteration per vertex.
 // Every kernel is persistent — a grid that is a fixed multiple of the SM count, warps pulling work with an atomic
 // counter — and reads its queue length from device memory, so nothing but one small counter block crosses PCIe per
 // iteration.  The three ray kernels run in the warp traversal engine (device/trav_engine.cuh), which refills finished
@@ -39,6 +44,7 @@
 
 #include "device/shade.cuh"
 #include "device/trav_engine.cuh"
+#include "job_split.h"
 #include "kat.cuh"
 
 namespace pbr {
@@ -362,30 +368,11 @@ struct FrameParams {
   uint32_t probe_passes, rest_passes, order_block;
 };
 
-// camera sample id -> (pixel, local sample index)
-__device__ __forceinline__ void SampleOfId(const FrameParams& f, unsigned long long id, uint32_t* pixel, uint32_t* s_local) {
-  const unsigned long long probe = (unsigned long long)f.probe_passes * f.npix;
-  if (f.order == nullptr || f.rest_passes == 0u || id < probe) {
-    const uint32_t s = uint32_t(id / f.npix);
-    *s_local = s;
-    *pixel = uint32_t(id - (unsigned long long)s * f.npix);
-    return;
-  }
-  const unsigned long long r = id - probe;
-  const unsigned long long per_block = (unsigned long long)f.order_block * f.rest_passes;
-  const uint32_t block = uint32_t(r / per_block);
-  const uint32_t within = uint32_t(r - (unsigned long long)block * per_block);
-  const uint32_t first = block * f.order_block;
-  const uint32_t width = min(f.order_block, f.npix - first);
-  const uint32_t s = within / width;
-  *s_local = f.probe_passes + s;
-  *pixel = f.order[first + (within - s * width)];
-}
-
 __device__ __forceinline__ RayT StartCameraPath(const WaveState& w, const FrameParams& f, uint32_t parity, uint32_t i,
                                                 unsigned long long id, uint32_t* pixel_out) {
   uint32_t s_local, pixel;
-  SampleOfId(f, id, &pixel, &s_local);
+  const pbrjob::SampleOrder so = {f.order, f.npix, f.probe_passes, f.rest_passes, f.order_block};
+  pbrjob::SampleOfId(so, id, &pixel, &s_local);   // job_split.h
   const uint32_t x = pixel % f.cam.width, y = pixel / f.cam.width;
   Pcg32 rng;
   pcg32_srandom(&rng, f.seed + uint64_t(f.first_sample) + uint64_t(s_local) * f.sample_stride, uint64_t(pixel));

@@ -127,6 +127,15 @@ class Emul:
         assert ok
         return int(out[0]), int(out[1]), int(out[2])
 
+    def sample_order(self, order, npix, probe, rest, block):
+        """(pixel, local sample) of every camera sample id of a worker's frame (csrc/job_split.h: SampleOfId)"""
+        n = npix * (probe + rest)
+        pix = np.zeros(n, np.uint32); smp = np.zeros(n, np.uint32)
+        o = None if order is None else np.ascontiguousarray(order, np.uint32)
+        self.lib.emul_sample_order(_p(o), C.c_uint32(npix), C.c_uint32(probe), C.c_uint32(rest), C.c_uint32(block),
+                                   _p(pix), _p(smp))
+        return pix, smp
+
     def render(self, width, height, spp, seed=1234567890, sample_offset=0, sample_stride=1):
         rgba = np.zeros((height, width, 4), np.float32); count = np.zeros((height, width), np.uint32)
         c = np.zeros(3, np.uint64)

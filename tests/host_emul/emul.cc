@@ -251,6 +251,14 @@ int emul_eval_closure(int op, const float* params, const float* in, uint32_t in_
 }
 
 // the library's own job-split arithmetic (csrc/job_split.h, used by pbrgpu.cu: RenderImpl): out = {offset, stride, count}
+// pbrjob::SampleOfId over every id of a worker's frame: out_pixel / out_sample [npix * (probe + rest)]
+void emul_sample_order(const uint32_t* order, uint32_t npix, uint32_t probe, uint32_t rest, uint32_t block,
+                       uint32_t* out_pixel, uint32_t* out_sample) {
+  const pbrjob::SampleOrder so = {order, npix, probe, rest, block};
+  const uint64_t n = uint64_t(npix) * (probe + rest);
+  for (uint64_t id = 0; id < n; ++id) pbrjob::SampleOfId(so, id, &out_pixel[id], &out_sample[id]);
+}
+
 int emul_job_share(uint32_t job_offset, uint32_t job_stride, uint32_t rank, uint32_t world, uint32_t device,
                    uint32_t num_devices, uint32_t spp, uint32_t* out3) {
   const pbrjob::Share s = pbrjob::ShareOf(job_offset, job_stride, rank, world, device, num_devices);

@@ -69,6 +69,31 @@ def test_shares_partition_the_samples(cornell_emul):
             assert sorted(got) == want, (spp, job_off, job_stride, world, ndev)
 
 
+def test_sample_order_starts_every_sample_once(cornell_emul):
+    """longest paths first: whatever the pixel permutation, block size and number of probing passes, the
+    ids 0 .. npix * spp map onto every (pixel, sample) exactly once — probing samples first, in raster order — and a
+    block's samples come sample-major, so consecutive ids are different pixels"""
+    E = cornell_emul
+    rng = np.random.default_rng(3)
+    for npix, probe, rest, block in [(1000, 4, 12, 256), (1000, 1, 1, 1000), (777, 2, 5, 1024), (64, 4, 0, 16),
+                                     (4096, 3, 29, 4096), (10, 1, 7, 3)]:
+        order = rng.permutation(npix).astype(np.uint32)
+        pix, smp = E.sample_order(order, npix, probe, rest, block)
+        spp = probe + rest
+        key = pix.astype(np.int64) * spp + smp
+        assert len(np.unique(key)) == npix * spp and key.min() == 0 and key.max() == npix * spp - 1
+        n_probe = npix * probe
+        assert np.array_equal(pix[:n_probe], np.tile(np.arange(npix, dtype=np.uint32), probe))
+        assert np.array_equal(smp[:n_probe], np.repeat(np.arange(probe, dtype=np.uint32), npix))
+        if rest:
+            first_block = order[:min(block, npix)]
+            got = pix[n_probe:n_probe + len(first_block) * rest].reshape(rest, len(first_block))
+            assert np.all(got == first_block[None, :])            # the first block: all its samples, sample-major
+            assert np.all(smp[n_probe:] >= probe)
+    pix, smp = E.sample_order(None, 50, 0, 6, 16)                  # no order: raster throughout
+    assert np.array_equal(pix, np.tile(np.arange(50, dtype=np.uint32), 6))
+
+
 def test_nccl_entry_points_without_a_device(built):
     """the library loads without libnccl linked in; the job entry points validate their arguments and a unique id can
     be made on a host without a GPU (ncclGetUniqueId needs none)"""
