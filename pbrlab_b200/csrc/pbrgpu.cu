@@ -167,7 +167,7 @@ struct pbrgpu_ctx {
   // path slots in flight = clamp(samples of the frame / tune_pool_div, tune_pool_min_mi, tune_pool_mi): a frame
   // that is only a few pool-fills long (strong scaling: 1/8 of the samples per GPU) spends a smaller share of its
   // time ramping up and draining with a smaller pool
-  int tune_pool_div = 8, tune_pool_min_mi = 4;
+  int tune_pool_div = 2, tune_pool_min_mi = 4;   // (8 until the end of a frame got cheap, DESIGN §2.4: now a frame of two pool fills beats one of eight, profiles/r4u_tune_pool_short_frames.log)
   int tune_drain_paths = 1 << 16, tune_drain_bounces = 48;     // fewer paths in flight than this: longer walk slices (sweeps: profiles/r2j_tune_drain_stages.log; after the thin spreading 48 instead of 256, profiles/r3e_tune_*.log)
   int tune_drain2_paths = 0, tune_drain2_bounces = 64;          // an intermediate stage (off by default)
   int tune_clear_march = 4;        // sphere-tracing steps of the clearance test along a walk segment
