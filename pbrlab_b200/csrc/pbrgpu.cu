@@ -108,6 +108,11 @@ struct Device {
   DevBuf<uint8_t> srgb8;      // output stage (pbrgpu_resolve_srgb8)
   uint32_t frame_width = 0, frame_height = 0;   // size of the last rendered frame
   // pinned host mirror of the counters
+  // pinned staging of the frame read-back (pbrgpu_render with host buffers): the device writes it by DMA in chunks,
+  // host threads copy each chunk on to the caller's pageable buffers while the next one is in flight
+  uint8_t* h_frame = nullptr;
+  size_t h_frame_bytes = 0;
+  cudaEvent_t ev_chunk[8] = {};
   uint32_t* h_counters = nullptr;
   unsigned long long* h_stats = nullptr;
 
@@ -125,6 +130,9 @@ struct Device {
     if (h_counters) cudaFreeHost(h_counters);
     if (h_stats) cudaFreeHost(h_stats);
     h_counters = nullptr; h_stats = nullptr;
+    if (h_frame) cudaFreeHost(h_frame);
+    h_frame = nullptr; h_frame_bytes = 0;
+    for (auto& e : ev_chunk) { if (e) cudaEventDestroy(e); e = nullptr; }
     for (auto& e : ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     for (auto& e : kev) { if (e) cudaEventDestroy(e); e = nullptr; }
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -1107,6 +1115,53 @@ static int ReduceDevices(pbrgpu_ctx* ctx, uint32_t npix) {
   return PBRGPU_OK;
 }
 
+// The frame (20 B per pixel: float4 sums + u32 count) from the device into the caller's HOST buffers.  A copy to
+// pageable memory is staged by the driver through one thread (~10 GB/s: 4-5 ms for a 1080p frame, a fifth of the PCIe
+// rate); here the DMA goes to a pinned buffer of the context in eight chunks and one host thread per chunk copies it on
+// as soon as its event has fired.  Small frames take the plain path.
+static int ReadBackFrame(pbrgpu_ctx* ctx, Device& d, uint32_t npix, float* rgba_out, uint32_t* count_out) {
+  const size_t rgba_bytes = sizeof(float4) * size_t(npix), count_bytes = sizeof(uint32_t) * size_t(npix);
+  constexpr int kChunks = 8;   // 6 of the sums, 2 of the counts (4 : 1 in bytes)
+  static const bool plain = getenv("PBRGPU_PLAIN_READBACK") != nullptr;   // (A/B switch)
+  if (plain || rgba_bytes + count_bytes < (8u << 20)) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(rgba_out, d.rgba.ptr, rgba_bytes, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(count_out, d.count.ptr, count_bytes, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+    return PBRGPU_OK;
+  }
+  if (d.h_frame_bytes < rgba_bytes + count_bytes) {
+    if (d.h_frame) cudaFreeHost(d.h_frame);
+    d.h_frame = nullptr; d.h_frame_bytes = 0;
+    CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&d.h_frame), rgba_bytes + count_bytes));
+    d.h_frame_bytes = rgba_bytes + count_bytes;
+  }
+  for (auto& e : d.ev_chunk)
+    if (!e) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  struct Chunk { const uint8_t* src; uint8_t* stage; uint8_t* dst; size_t bytes; };
+  Chunk chunks[kChunks];
+  for (int c = 0; c < kChunks; ++c) {
+    const bool sums = c < 6;
+    const size_t total = sums ? rgba_bytes : count_bytes, parts = sums ? 6 : 2, k = sums ? size_t(c) : size_t(c - 6);
+    const size_t lo = (total * k / parts) & ~size_t(63), hi = (k + 1 == parts) ? total : ((total * (k + 1) / parts) & ~size_t(63));
+    chunks[c].src = reinterpret_cast<const uint8_t*>(sums ? static_cast<const void*>(d.rgba.ptr) : static_cast<const void*>(d.count.ptr)) + lo;
+    chunks[c].stage = d.h_frame + (sums ? 0 : rgba_bytes) + lo;
+    chunks[c].dst = reinterpret_cast<uint8_t*>(sums ? static_cast<void*>(rgba_out) : static_cast<void*>(count_out)) + lo;
+    chunks[c].bytes = hi - lo;
+    CUDA_TRY(ctx, cudaMemcpyAsync(chunks[c].stage, chunks[c].src, chunks[c].bytes, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(ctx, cudaEventRecord(d.ev_chunk[c], d.stream));
+  }
+  std::vector<std::thread> th;
+  std::vector<cudaError_t> err(kChunks, cudaSuccess);
+  for (int c = 0; c < kChunks; ++c)
+    th.emplace_back([&, c]() {
+      err[c] = cudaEventSynchronize(d.ev_chunk[c]);
+      if (err[c] == cudaSuccess) memcpy(chunks[c].dst, chunks[c].stage, chunks[c].bytes);
+    });
+  for (auto& t : th) t.join();
+  for (int c = 0; c < kChunks; ++c) CUDA_TRY(ctx, err[c]);
+  return PBRGPU_OK;
+}
+
 static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t spp, uint64_t seed,
                       uint32_t sample_offset, uint32_t sample_stride, const volatile int* cancel, float* rgba_out,
                       uint32_t* count_out, size_t* finish_pass, bool out_on_device) {
@@ -1162,10 +1217,14 @@ static int RenderImpl(pbrgpu_ctx* ctx, uint32_t width, uint32_t height, uint32_t
   }
   pbr::FinishFrameKernel<<<(npix + 255) / 256, 256, 0, d0.stream>>>(d0.rgba.ptr, d0.count.ptr, npix);
   tms[0].launches++;
-  const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  CUDA_TRY(ctx, cudaMemcpyAsync(rgba_out, d0.rgba.ptr, sizeof(float4) * npix, kind, d0.stream));
-  CUDA_TRY(ctx, cudaMemcpyAsync(count_out, d0.count.ptr, sizeof(uint32_t) * npix, kind, d0.stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(d0.stream));
+  if (out_on_device) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(rgba_out, d0.rgba.ptr, sizeof(float4) * npix, cudaMemcpyDeviceToDevice, d0.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(count_out, d0.count.ptr, sizeof(uint32_t) * npix, cudaMemcpyDeviceToDevice, d0.stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d0.stream));
+  } else {
+    rc = ReadBackFrame(ctx, d0, npix, rgba_out, count_out);
+    if (rc != PBRGPU_OK) return rc;
+  }
   CUDA_TRY(ctx, cudaGetLastError());
 
   pbrgpu_stats& s = ctx->stats;

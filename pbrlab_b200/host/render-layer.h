@@ -5,7 +5,9 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 namespace pbrlab {
 struct RenderLayer {
@@ -16,8 +18,23 @@ struct RenderLayer {
   }
   void Clear(void) {
     std::lock_guard<std::mutex> lock(mtx);
-    std::fill(rgba.begin(), rgba.end(), 0.0f);
-    std::fill(count.begin(), count.end(), uint32_t(0));
+    // (Render() clears the layer at the start of every frame, render.cc:99-100: a 4K layer is 166 MB, so large
+    // layers are zeroed by four threads)
+    const size_t n = rgba.size(), parts = n >= (size_t(1) << 22) ? 4 : 1;
+    if (parts == 1) {
+      std::fill(rgba.begin(), rgba.end(), 0.0f);
+      std::fill(count.begin(), count.end(), uint32_t(0));
+      return;
+    }
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < parts; ++k)
+      th.emplace_back([this, k, parts]() {
+        const size_t a = rgba.size() * k / parts, b = rgba.size() * (k + 1) / parts;
+        std::memset(rgba.data() + a, 0, (b - a) * sizeof(float));
+        const size_t c = count.size() * k / parts, d = count.size() * (k + 1) / parts;
+        std::memset(count.data() + c, 0, (d - c) * sizeof(uint32_t));
+      });
+    for (auto& t : th) t.join();
   }
   void Resize(const size_t w, const size_t h) {
     std::lock_guard<std::mutex> lock(mtx);
