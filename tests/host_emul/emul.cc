@@ -3,7 +3,9 @@
 // functions; this shim compiles them with g++ so their arithmetic can be checked against the compiled reference in
 // a container without a GPU.  It mirrors the pbrgpu_* entry points one to one (same argument meaning) but is never
 // built into, loaded by, or a fallback for the product: libpbrgpu.so has no CPU path.
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -137,6 +139,91 @@ int emul_trace(void* h, const pbrgpu_ray* rays, uint64_t n, pbrgpu_hit* hits, ui
     prims += st.prims;
   });
   if (stats2) { stats2[0] = nodes; stats2[1] = prims; }
+  return 0;
+}
+
+// MEASUREMENT ONLY: closest hit through the curve BVH with the children visited best-first — always the
+// box with the smallest entry distance next, over the whole tree (a priority queue) — instead of the static octant
+// order of TraverseBvh.  Same boxes, same leaf tests; stats2 = (inner nodes tested, curve candidates tested): the
+// lower bound any ordering of the visits could reach on this tree.
+int emul_trace_curves_best_first(void* h, const pbrgpu_ray* rays, uint64_t n, float* t_out, uint64_t* stats2, int mode) {
+  Emul* e = static_cast<Emul*>(h);
+  const SceneView& s = e->view;
+  if (!s.num_curves) return 1;
+  std::atomic<uint64_t> nodes(0), prims(0);
+  const uint32_t* nw = reinterpret_cast<const uint32_t*>(s.curve_nodes);
+  ParallelFor(n, [&](uint64_t i) {
+    const RayT ray = ToRay(rays[i]);
+    const CurveRaySpace rs = MakeCurveRaySpace(ray.d);
+    float tfar = ray.tmax;
+    uint64_t nn = 0, np = 0;
+    struct Item { float t; uint32_t id; uint32_t leaf_count; };   // leaf_count 0: inner node id; else first prim + count
+    std::vector<Item> heap;
+    auto push = [&](Item it) { heap.push_back(it); std::push_heap(heap.begin(), heap.end(), [](const Item& a, const Item& b) { return a.t > b.t; }); };
+    auto pop = [&]() { std::pop_heap(heap.begin(), heap.end(), [](const Item& a, const Item& b) { return a.t > b.t; }); Item it = heap.back(); heap.pop_back(); return it; };
+    // mode 1: depth-first, the hit children of a node in order of entry distance (a LIFO stack: pushed far to near)
+    std::vector<Item> batch;
+    if (mode >= 1) heap.push_back({ray.tmin, 0u, 0u}); else push({ray.tmin, 0u, 0u});
+    const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
+    while (!heap.empty()) {
+      Item it;
+      if (mode >= 1) { it = heap.back(); heap.pop_back(); if (it.t > tfar && !(mode == 3 && it.leaf_count == 0)) continue; }
+      else { it = pop(); if (it.t > tfar) break; }
+      if (it.leaf_count) {
+        for (uint32_t j = 0; j < it.leaf_count; ++j) {
+          ++np;
+          const uint32_t code = s.curve_sub[it.id + j], idx = code >> 2;
+          if (s.curve_cull && !CurveMayHit(ray.o, ray.d, s.curve_cull[idx * 2], s.curve_cull[idx * 2 + 1])) continue;
+          float t, u, v;
+          if (IntersectCurve(ray.o, rs, ray.tmin, tfar, s.curve_data[idx * 4], s.curve_data[idx * 4 + 1], s.curve_data[idx * 4 + 2],
+                             s.curve_data[idx * 4 + 3], code & 3u, s.curve_part_quads, &t, &u, &v))
+            tfar = t;
+        }
+        continue;
+      }
+      ++nn;
+      const uint32_t* w = nw + size_t(20) * it.id;
+      float p[3], step[3];
+      memcpy(p, w, 12);
+      for (int k = 0; k < 3; ++k) { const uint32_t eb = (w[3] >> (8 * k)) & 0xffu; const uint32_t bits = eb << 23; memcpy(&step[k], &bits, 4); }
+      const uint32_t imask = w[3] >> 24, child_base = w[4], prim_base = w[5];
+      uint32_t inner_rank = 0;
+      batch.clear();
+      for (int sl = 0; sl < 8; ++sl) {
+        const uint32_t meta = (w[6 + sl / 4] >> (8 * (sl % 4))) & 0xffu;
+        if (!meta) continue;
+        const bool inner = (imask >> sl) & 1u;
+        const uint32_t my_rank = inner_rank;
+        if (inner) ++inner_rank;
+        float tn = ray.tmin, tf = tfar;
+        for (int k = 0; k < 3; ++k) {
+          const uint32_t qlo = (w[8 + 2 * k + sl / 4] >> (8 * (sl % 4))) & 0xffu, qhi = (w[14 + 2 * k + sl / 4] >> (8 * (sl % 4))) & 0xffu;
+          const float lo = p[k] + float(qlo) * step[k], hi = p[k] + float(qhi) * step[k];
+          const float inv = 1.0f / (std::fabs(d[k]) < 1e-30f ? std::copysign(1e-30f, d[k]) : d[k]);
+          float t0 = (lo - o[k]) * inv, t1 = (hi - o[k]) * inv;
+          if (t0 > t1) std::swap(t0, t1);
+          tn = std::max(tn, t0 * 0.999999f - 1e-6f); tf = std::min(tf, t1 * 1.000001f + 1e-6f);
+        }
+        if (tn > tf) continue;
+        Item c;
+        if (inner) c = {tn, child_base + my_rank, 0u};
+        else {
+          const uint32_t unary = meta >> 5, cnt = unary == 1 ? 1u : (unary == 3 ? 2u : 3u);
+          c = {tn, prim_base + (meta & 0x1fu), cnt};
+        }
+        if (mode >= 1) batch.push_back(c); else push(c);
+      }
+      if (mode >= 1) {
+        std::sort(batch.begin(), batch.end(), [](const Item& a, const Item& b) { return a.t > b.t; });   // far first
+        if (mode >= 2)   // the node's leaf candidates first (as the traversal engine does), then its inner children near to far
+          std::stable_partition(batch.begin(), batch.end(), [](const Item& a) { return a.leaf_count == 0; });
+        for (const Item& c : batch) heap.push_back(c);
+      }
+    }
+    if (t_out) t_out[i] = tfar;
+    nodes += nn; prims += np;
+  });
+  stats2[0] = nodes; stats2[1] = prims;
   return 0;
 }
 
