@@ -43,6 +43,7 @@ struct SceneView {
   uint32_t curve_part_quads;   // quads (quarter sub-segments) per part: 4 (whole segments), 2 or 1
   uint32_t ribbon_min_lanes;   // traversal engine: lanes holding a curve candidate that trigger a ribbon phase
   uint32_t thin_spread;        // traversal engine: short launches spread their items over all warps (LanesFor)
+  uint32_t inside_first;       // traversal engine, curve BVH: children whose box holds the ray origin first (PopChild)
   const float4* curve_cull;    // slot order, 2 per segment: (c0, capsule radius around the line c0c3), (c3 - c0, |c3 - c0|), see CurveMayHit; may be null
   uint32_t num_tris, num_curves;
   uint32_t bias_magic;         // kBiasMagic (traverse.cuh), as a run-time value on purpose

@@ -59,13 +59,13 @@ __device__ __forceinline__ void TravBegin(const SceneView& s, const RayT& ray, T
 //   TravPrimStep   tests ONE pending primitive.
 // A lane always finishes the primitives of a node before its next node step, exactly like TraverseBvh, so tfar
 // shrinks in the same order and the reported hit is the same.
-template <bool HAS_CURVES, bool STATS, bool PREFETCH>
+template <bool HAS_CURVES, bool STATS, bool PREFETCH, bool ANY = false>
 __device__ __forceinline__ void TravNodeStep(const SceneView& s, Trav& t, uint2* __restrict__ stack) {
   const bool in_curves = HAS_CURVES && t.curves;
   const float4* __restrict__ nodes = in_curves ? s.curve_nodes : s.tri_nodes;
   const uint32_t hits_imask = t.group.y;
-  const uint32_t child_bit = msb(hits_imask);
-  t.group.y &= ~(1u << child_bit);
+  // (curve BVH: the children whose box holds the ray origin first, traverse.cuh: PopChild)
+  const uint32_t child_bit = in_curves ? PopChild<true>(&t.group.y) : PopChild<false>(&t.group.y);
   if (t.group.y & 0xff000000u) {
     if (t.sp < kStackSize) stack[t.sp++] = t.group;
   }
@@ -76,10 +76,14 @@ __device__ __forceinline__ void TravNodeStep(const SceneView& s, Trav& t, uint2*
   const float4 n3 = nodes[node * 5 + 3], n4 = nodes[node * 5 + 4];
   if (STATS) t.n_nodes++;
   const bool neg_x = !(t.oct_inv4 & 0x04u), neg_y = !(t.oct_inv4 & 0x02u), neg_z = !(t.oct_inv4 & 0x01u);
-  const uint32_t hitmask = NodeIntersect(t.ood, t.inv_d, t.oct_inv4, neg_x, neg_y, neg_z, t.tmin, t.tfar, n0, n1,
-                                         n2, n3, n4, s.bias_magic);
+  uint32_t inside = 0;
+  // (closest hit only: an any-hit ray gains nothing from the order and would pay for the extra mask, measured +2 %)
+  const uint32_t hitmask = (HAS_CURVES && !ANY) ? NodeIntersectT<true>(t.ood, t.inv_d, t.oct_inv4, neg_x, neg_y, neg_z, t.tmin, t.tfar, n0,
+                                                             n1, n2, n3, n4, s.bias_magic, &inside)
+                                      : NodeIntersectT<false>(t.ood, t.inv_d, t.oct_inv4, neg_x, neg_y, neg_z, t.tmin, t.tfar,
+                                                              n0, n1, n2, n3, n4, s.bias_magic, nullptr);
   t.group.x = f2u(n1.x);
-  t.group.y = (hitmask & 0xff000000u) | extract_byte(f2u(n0.w), 3);
+  t.group.y = (hitmask & 0xff000000u) | ((in_curves && !ANY && s.inside_first) ? inside : 0u) | extract_byte(f2u(n0.w), 3);
   t.pgroup.x = f2u(n1.y);
   t.pgroup.y = hitmask & 0x00ffffffu;
   t.checked = false;
@@ -216,7 +220,7 @@ __device__ __forceinline__ void TravTrip(const SceneView& s, Trav& t, uint2* __r
                                          uint32_t prim_min_lanes) {
   const bool node_work = t.active && t.pgroup.y == 0u && (!HAS_CURVES || t.held == kInvalid);
   if (node_work) {
-    TravNodeStep<HAS_CURVES, STATS, false>(s, t, stack);   // prefetching the next node was measured: 1.6x slower
+    TravNodeStep<HAS_CURVES, STATS, false, ANY>(s, t, stack);   // prefetching the next node was measured: 1.6x slower
     TravAdvance<HAS_CURVES>(s, t);
   }
   if (HAS_CURVES) {

@@ -189,6 +189,7 @@ struct pbrgpu_ctx {
   int tune_order = 1, tune_order_probe = 4, tune_order_block = 1 << 16;
   int tune_finish_blocks = 4;      // its blocks per SM (128 registers per thread: four fit)
   int tune_finish_paths = 8192;    // fewer paths + walks in flight than this at the end of a frame: FinishPathsKernel runs them to their end (0: off)
+  int tune_inside_first = 1;       // curve BVH: a ray visits the children whose box holds its origin first (traverse.cuh: PopChild)
   int tune_thin_spread = 1;        // launches with fewer items than lanes give every warp n / warps of them (trav_engine.cuh: LanesFor)
   // Walk kernels on their own stream, beside closest hit + shading of the same iteration (they only share atomically
   // appended output streams).  Measured (profiles/r2r_tune_overlap.log): with the full launch shapes the two kernels
@@ -296,6 +297,7 @@ int UploadScene(pbrgpu_ctx* ctx, Device& d) {
   v.curve_sub = d.curve_sub.ptr; v.curve_part_quads = h.curve_part_quads;
   v.ribbon_min_lanes = ctx->tune_ribbon_lanes;
   v.thin_spread = ctx->tune_thin_spread ? 1u : 0u;
+  v.inside_first = ctx->tune_inside_first ? 1u : 0u;
   v.curve_cull = h.curve_cull.empty() ? nullptr : reinterpret_cast<const float4*>(d.curve_cull.ptr);
   v.num_tris = h.num_tris(); v.num_curves = h.num_curves();
   v.bias_magic = pbr::kBiasMagic;
@@ -829,6 +831,7 @@ pbrgpu_ctx* pbrgpu_create(const int* device_ids, int n_devices) {
   ctx->tune_walk_blocks_overlap = std::max(1, env_int("PBRGPU_WALK_BLOCKS_OVERLAP", ctx->tune_walk_blocks_overlap));
   ctx->tune_order = env_int("PBRGPU_ORDER", ctx->tune_order);
   ctx->tune_thin_spread = env_int("PBRGPU_THIN", ctx->tune_thin_spread);
+  ctx->tune_inside_first = env_int("PBRGPU_INSIDE_FIRST", ctx->tune_inside_first);
   ctx->tune_finish_paths = std::max(0, env_int("PBRGPU_FINISH_PATHS", ctx->tune_finish_paths));
   ctx->tune_finish_blocks = std::max(1, env_int("PBRGPU_FINISH_BLOCKS", ctx->tune_finish_blocks));
   ctx->tune_order_probe = std::max(1, env_int("PBRGPU_ORDER_PROBE", ctx->tune_order_probe));

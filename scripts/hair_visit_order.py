@@ -30,6 +30,7 @@ h2, st2 = E.trace(sec, stats=True)
 m = len(sec)
 print("secondary rays from hair (%d): octant order nodes/ray %.2f prims/ray %.2f" % (m, st2[0]/m, st2[1]/m))
 st3 = np.zeros(2, np.uint64); t3 = np.zeros(m, np.float32)
-for mode, name in ((0, "best-first (global heap)"), (1, "depth-first, children sorted per node"), (2, "same, a node's leaves before its inner children"), (3, "same, but a child is only culled by its own boxes (no stored entry distance)")):
+for mode, name in ((0, "best-first (global heap)"), (1, "depth-first, children sorted per node"), (2, "same, a node's leaves before its inner children"), (3, "same, but a child is only culled by its own boxes (no stored entry distance)"),
+                   (4, "the static octant order (the engine's), this tool's count"), (5, "octant order, children whose box holds the ray origin first")):
     E.lib.emul_trace_curves_best_first(E.h, sec.ctypes.data_as(C.c_void_p), C.c_uint64(m), t3.ctypes.data_as(C.c_void_p), st3.ctypes.data_as(C.c_void_p), C.c_int(mode))
     print("   %-40s nodes/ray %.2f prims/ray %.2f" % (name, st3[0]/m, st3[1]/m))

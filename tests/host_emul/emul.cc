@@ -157,17 +157,17 @@ int emul_trace_curves_best_first(void* h, const pbrgpu_ray* rays, uint64_t n, fl
     const CurveRaySpace rs = MakeCurveRaySpace(ray.d);
     float tfar = ray.tmax;
     uint64_t nn = 0, np = 0;
-    struct Item { float t; uint32_t id; uint32_t leaf_count; };   // leaf_count 0: inner node id; else first prim + count
+    struct Item { float t; uint32_t id; uint32_t leaf_count; uint32_t key; };   // leaf_count 0: inner node id; else first prim + count; key: static visit rank
     std::vector<Item> heap;
     auto push = [&](Item it) { heap.push_back(it); std::push_heap(heap.begin(), heap.end(), [](const Item& a, const Item& b) { return a.t > b.t; }); };
     auto pop = [&]() { std::pop_heap(heap.begin(), heap.end(), [](const Item& a, const Item& b) { return a.t > b.t; }); Item it = heap.back(); heap.pop_back(); return it; };
     // mode 1: depth-first, the hit children of a node in order of entry distance (a LIFO stack: pushed far to near)
     std::vector<Item> batch;
-    if (mode >= 1) heap.push_back({ray.tmin, 0u, 0u}); else push({ray.tmin, 0u, 0u});
+    if (mode >= 1) heap.push_back({ray.tmin, 0u, 0u, 0u}); else push({ray.tmin, 0u, 0u, 0u});
     const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
     while (!heap.empty()) {
       Item it;
-      if (mode >= 1) { it = heap.back(); heap.pop_back(); if (it.t > tfar && !(mode == 3 && it.leaf_count == 0)) continue; }
+      if (mode >= 1) { it = heap.back(); heap.pop_back(); if (it.t > tfar && !(mode >= 3 && it.leaf_count == 0)) continue; }
       else { it = pop(); if (it.t > tfar) break; }
       if (it.leaf_count) {
         for (uint32_t j = 0; j < it.leaf_count; ++j) {
@@ -206,14 +206,25 @@ int emul_trace_curves_best_first(void* h, const pbrgpu_ray* rays, uint64_t n, fl
         }
         if (tn > tf) continue;
         Item c;
-        if (inner) c = {tn, child_base + my_rank, 0u};
+        const uint32_t oct_inv = (d[0] < 0.f ? 0u : 4u) | (d[1] < 0.f ? 0u : 2u) | (d[2] < 0.f ? 0u : 1u);
+        const uint32_t key = uint32_t(sl) ^ oct_inv;   // the engine visits the hit children by descending key
+        if (inner) c = {tn, child_base + my_rank, 0u, key};
         else {
           const uint32_t unary = meta >> 5, cnt = unary == 1 ? 1u : (unary == 3 ? 2u : 3u);
-          c = {tn, prim_base + (meta & 0x1fu), cnt};
+          c = {tn, prim_base + (meta & 0x1fu), cnt, key};
         }
         if (mode >= 1) batch.push_back(c); else push(c);
       }
       if (mode >= 1) {
+        if (mode >= 4) {
+          // modes 4 / 5: the static octant order (4), and the same with the children whose box holds the ray origin
+          // first (5); popped last-pushed first, so sort ascending by visit priority
+          const float t0 = ray.tmin;
+          std::sort(batch.begin(), batch.end(), [&](const Item& a, const Item& b) {
+            const uint32_t pa = ((mode == 5 && a.t <= t0) ? 8u : 0u) + a.key, pb = ((mode == 5 && b.t <= t0) ? 8u : 0u) + b.key;
+            return pa < pb;
+          });
+        } else
         std::sort(batch.begin(), batch.end(), [](const Item& a, const Item& b) { return a.t > b.t; });   // far first
         if (mode >= 2)   // the node's leaf candidates first (as the traversal engine does), then its inner children near to far
           std::stable_partition(batch.begin(), batch.end(), [](const Item& a) { return a.leaf_count == 0; });
