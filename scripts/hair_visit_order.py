@@ -28,7 +28,7 @@ d2 = rng.normal(size=P.shape).astype(np.float32); d2 /= np.linalg.norm(d2, axis=
 sec = pb.make_rays(P, d2, tmin=1e-3)
 h2, st2 = E.trace(sec, stats=True)
 m = len(sec)
-print("secondary rays from hair (%d): octant order nodes/ray %.2f prims/ray %.2f" % (m, st2[0]/m, st2[1]/m))
+print("secondary rays from hair (%d): the traversal as built (children around the origin first) nodes/ray %.2f prims/ray %.2f" % (m, st2[0]/m, st2[1]/m))
 st3 = np.zeros(2, np.uint64); t3 = np.zeros(m, np.float32)
 for mode, name in ((0, "best-first (global heap)"), (1, "depth-first, children sorted per node"), (2, "same, a node's leaves before its inner children"), (3, "same, but a child is only culled by its own boxes (no stored entry distance)"),
                    (4, "the static octant order (the engine's), this tool's count"), (5, "octant order, children whose box holds the ray origin first")):
