@@ -384,6 +384,11 @@ PBR_HD uint32_t PopChild(uint32_t* group_y) {
   return bit;
 }
 
+#ifdef PBR_TRI_INSIDE_FIRST   // measurement switch (tests/host_emul): the visit order of PopChild for triangle BVHs too
+constexpr bool kTriInsideFirst = true;
+#else
+constexpr bool kTriInsideFirst = false;
+#endif
 // Generic traversal of one BVH.  CURVES selects the leaf test, ANY the early-out.
 template <bool CURVES, bool ANY, bool STATS>
 PBR_HD bool TraverseBvh(const float4* __restrict__ nodes, const float4* __restrict__ prims,
@@ -412,7 +417,7 @@ PBR_HD bool TraverseBvh(const float4* __restrict__ nodes, const float4* __restri
     uint2 pgroup;
     if (group.y & 0xff000000u) {
       const uint32_t hits_imask = group.y;
-      const uint32_t child_bit = PopChild<CURVES>(&group.y);
+      const uint32_t child_bit = PopChild<CURVES || kTriInsideFirst>(&group.y);
       if (group.y & 0xff000000u) {
         if (sp < kStackSize) stack[sp++] = group;
       }
@@ -423,7 +428,7 @@ PBR_HD bool TraverseBvh(const float4* __restrict__ nodes, const float4* __restri
       const float4 n3 = nodes[node * 5 + 3], n4 = nodes[node * 5 + 4];
       if (STATS) st->nodes++;
       uint32_t inside = 0;
-      const uint32_t hitmask = NodeIntersectT<CURVES>(o_over_d, inv_d, oct_inv4, neg_x, neg_y, neg_z, ray.tmin, tfar, n0,
+      const uint32_t hitmask = NodeIntersectT<CURVES || kTriInsideFirst>(o_over_d, inv_d, oct_inv4, neg_x, neg_y, neg_z, ray.tmin, tfar, n0,
                                                       n1, n2, n3, n4, kBiasMagic, &inside);
       group.x = f2u(n1.x);
       group.y = (hitmask & 0xff000000u) | inside | extract_byte(f2u(n0.w), 3);
