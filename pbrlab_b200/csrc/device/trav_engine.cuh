@@ -59,7 +59,10 @@ __device__ __forceinline__ void TravBegin(const SceneView& s, const RayT& ray, T
 //   TravPrimStep   tests ONE pending primitive.
 // A lane always finishes the primitives of a node before its next node step, exactly like TraverseBvh, so tfar
 // shrinks in the same order and the reported hit is the same.
-template <bool HAS_CURVES, bool STATS, bool PREFETCH, bool ANY = false>
+// BY_ORIGIN: curve-BVH nodes hand the children whose box holds the ray origin to the ray first (PopChild); the engine
+// asks for it where the order pays, the closest-hit rays of a path (not for shadow rays: any hit ends them; not for
+// walk segments: they live inside triangle meshes and would only pay for the extra mask, measured +14 % walk time on C4)
+template <bool HAS_CURVES, bool STATS, bool PREFETCH, bool BY_ORIGIN = false>
 __device__ __forceinline__ void TravNodeStep(const SceneView& s, Trav& t, uint2* __restrict__ stack) {
   const bool in_curves = HAS_CURVES && t.curves;
   const float4* __restrict__ nodes = in_curves ? s.curve_nodes : s.tri_nodes;
@@ -77,13 +80,12 @@ __device__ __forceinline__ void TravNodeStep(const SceneView& s, Trav& t, uint2*
   if (STATS) t.n_nodes++;
   const bool neg_x = !(t.oct_inv4 & 0x04u), neg_y = !(t.oct_inv4 & 0x02u), neg_z = !(t.oct_inv4 & 0x01u);
   uint32_t inside = 0;
-  // (closest hit only: an any-hit ray gains nothing from the order and would pay for the extra mask, measured +2 %)
-  const uint32_t hitmask = (HAS_CURVES && !ANY) ? NodeIntersectT<true>(t.ood, t.inv_d, t.oct_inv4, neg_x, neg_y, neg_z, t.tmin, t.tfar, n0,
+  const uint32_t hitmask = (HAS_CURVES && BY_ORIGIN) ? NodeIntersectT<true>(t.ood, t.inv_d, t.oct_inv4, neg_x, neg_y, neg_z, t.tmin, t.tfar, n0,
                                                              n1, n2, n3, n4, s.bias_magic, &inside)
                                       : NodeIntersectT<false>(t.ood, t.inv_d, t.oct_inv4, neg_x, neg_y, neg_z, t.tmin, t.tfar,
                                                               n0, n1, n2, n3, n4, s.bias_magic, nullptr);
   t.group.x = f2u(n1.x);
-  t.group.y = (hitmask & 0xff000000u) | ((in_curves && !ANY && s.inside_first) ? inside : 0u) | extract_byte(f2u(n0.w), 3);
+  t.group.y = (hitmask & 0xff000000u) | ((in_curves && BY_ORIGIN && s.inside_first) ? inside : 0u) | extract_byte(f2u(n0.w), 3);
   t.pgroup.x = f2u(n1.y);
   t.pgroup.y = hitmask & 0x00ffffffu;
   t.checked = false;
@@ -215,12 +217,12 @@ __device__ __forceinline__ void TravRibbonStep(const SceneView& s, Trav& t) {
 
 // One trip of the engine between two converged sections: a node phase (lanes without pending primitives), the curve
 // candidate rejection, a primitive phase and the ribbon phase (see TravEngine).  Called by all 32 lanes.
-template <bool ANY, bool HAS_CURVES, bool STATS>
+template <bool ANY, bool HAS_CURVES, bool STATS, bool BY_ORIGIN = false>
 __device__ __forceinline__ void TravTrip(const SceneView& s, Trav& t, uint2* __restrict__ stack, uint32_t* pass_row,
                                          uint32_t prim_min_lanes) {
   const bool node_work = t.active && t.pgroup.y == 0u && (!HAS_CURVES || t.held == kInvalid);
   if (node_work) {
-    TravNodeStep<HAS_CURVES, STATS, false, ANY>(s, t, stack);   // prefetching the next node was measured: 1.6x slower
+    TravNodeStep<HAS_CURVES, STATS, false, BY_ORIGIN && !ANY>(s, t, stack);   // prefetching the next node was measured: 1.6x slower
     TravAdvance<HAS_CURVES>(s, t);
   }
   if (HAS_CURVES) {
@@ -279,6 +281,7 @@ __device__ __forceinline__ uint32_t ThresholdFor(uint32_t lanes, uint32_t dflt) 
 //        its next ray: on success it calls TravBegin (t.active == true).  Returns true when this lane found the
 //        work source empty.
 //   void End(const Trav& t)  — after the loop.
+//   static constexpr bool kOrderByOrigin  — see TravNodeStep.
 //   uint32_t RefillThreshold(uint32_t dflt)  — idle lanes that trigger a Refill (dflt, or fewer when the client lets
 //        only some lanes of a warp fetch work, see LanesFor).
 // A Refill happens when at least `refill_min_idle` idle lanes want one, or when nobody is traversing.  The loop ends
@@ -314,7 +317,7 @@ __device__ __forceinline__ void TravEngine(const SceneView& s, Client& client, u
         continue;
       }
     }
-    TravTrip<ANY, HAS_CURVES, STATS>(s, t, stack, pass_row, prim_min_lanes);
+    TravTrip<ANY, HAS_CURVES, STATS, Client::kOrderByOrigin>(s, t, stack, pass_row, prim_min_lanes);
   }
   client.End(t);
 }

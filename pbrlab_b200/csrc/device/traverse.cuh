@@ -339,7 +339,7 @@ PBR_HD uint32_t NodeIntersectT(const vec3& o_over_d, const vec3& inv_d, uint32_t
         if (tn <= tf) {
           const uint32_t c = extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
           hit_mask |= c;
-          if (m3 <= tmin) inside_mask |= (c >> 8) & 0x00ff0000u;   // (a leaf's bits lie below bit 24: nothing left of them here)
+          if (m3 <= tmin) inside_mask |= c;   // (one predicated OR; the leaves' bits, below bit 24, are masked off at the end)
         }
       } else {
         const float tn = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, tmin));
@@ -350,7 +350,7 @@ PBR_HD uint32_t NodeIntersectT(const vec3& o_over_d, const vec3& inv_d, uint32_t
       }
     }
   }
-  if (WANT_INSIDE) *inside = inside_mask;
+  if (WANT_INSIDE) *inside = (inside_mask & 0xff000000u) >> 8;
   return hit_mask;
 }
 

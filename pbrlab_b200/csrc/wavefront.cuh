@@ -445,6 +445,7 @@ __global__ void InitPathsFromRaysKernel(WaveState w, const float4* rays, const u
 // iteration's new camera samples: generated here, so a camera ray never makes a round trip through memory before its
 // first traversal.  Runs in the warp traversal engine: lanes are refilled while others traverse.
 struct ClosestClient {
+  static constexpr bool kOrderByOrigin = true;
   const SceneView& s;
   const WaveState& w;
   const FrameParams& frame;      // frame mode: how camera samples are numbered
@@ -770,6 +771,7 @@ __global__ void __launch_bounds__(kShadeBlock) ShadeHairKernel(SceneView s, Wave
 //     cycles-principled-shader.cc:187-216) is sss_exit: both are rare per bounce and ran at 2-3 lanes per warp when
 //     they were inlined here.
 struct SssClient {
+  static constexpr bool kOrderByOrigin = false;
   const SceneView& s;
   const WaveState& w;
   uint32_t cur, next, n, max_bounces, lanes;
@@ -1023,6 +1025,7 @@ __global__ void __launch_bounds__(128, 4) FinishPathsKernel(SceneView s, WaveSta
 // Scene::AnyHit1 for every NEE request of this iteration; an unoccluded contribution is added to the radiance of its
 // path wherever that path is now (S[next], D[next] or W[next]; the positions are nearly ascending).
 struct ShadowClient {
+  static constexpr bool kOrderByOrigin = false;
   const SceneView& s;
   const WaveState& w;
   uint32_t n, next, lanes;
@@ -1106,6 +1109,7 @@ __global__ void GatherVertexKernel(WaveState w, uint32_t parity, uint32_t n_path
 
 // pbrgpu_trace / pbrgpu_occluded: caller-supplied ray batches through the same engine as the render kernels
 struct BatchClient {
+  static constexpr bool kOrderByOrigin = true;
   const SceneView& s;
   const float4* __restrict__ rays;
   uint64_t n;
