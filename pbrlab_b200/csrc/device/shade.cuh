@@ -471,6 +471,9 @@ PBR_HD SssStep SssBounce(const SceneView& s, Pcg32* rng, SssWalkState* w, HitT* 
 #ifdef PBR_CLEARANCE_PROBE   // tests/host_emul only: every segment the field would skip must be a miss
   PBR_CLEARANCE_PROBE(SegmentIsClear(s, w->ray.o, w->ray.d, w->ray.tmax * 1.001f), is_hit);
 #endif
+#ifdef PBR_WALK_SEGMENT_PROBE   // tests/host_emul only: the walks' segments, for offline traversal statistics
+  PBR_WALK_SEGMENT_PROBE(w->ray, SegmentIsClear(s, w->ray.o, w->ray.d, w->ray.tmax * 1.001f));
+#endif
   if (rays) ++*rays;
   return SssFinishSegment(is_hit, hit->t, rng, w, channel_pdf);
 }

@@ -15,6 +15,23 @@ static std::atomic<uint64_t> g_clear_probe[3];
 #define PBR_CLEARANCE_PROBE(clear, hit) \
   do { const bool c_ = (clear); ++g_clear_probe[0]; if (c_) { ++g_clear_probe[1]; if (hit) ++g_clear_probe[2]; } } while (0)
 
+// walk segments of PathRadiance that the clearance field does NOT answer, recorded (up to a cap) while enabled:
+// 8 floats each (origin, tmin, direction, tmax) — scripts/walk_segment_stats.py
+#include <mutex>
+static std::mutex g_seg_mutex;
+static std::vector<float> g_segments;
+static std::atomic<uint64_t> g_seg_cap(0);
+#define PBR_WALK_SEGMENT_PROBE(ray, clear)                                                              \
+  do {                                                                                                  \
+    if (!(clear) && g_seg_cap.load(std::memory_order_relaxed)) {                                        \
+      std::lock_guard<std::mutex> lock_(g_seg_mutex);                                                   \
+      if (g_segments.size() / 8 < g_seg_cap.load()) {                                                   \
+        const float r_[8] = {(ray).o.x, (ray).o.y, (ray).o.z, (ray).tmin, (ray).d.x, (ray).d.y, (ray).d.z, (ray).tmax}; \
+        g_segments.insert(g_segments.end(), r_, r_ + 8);                                                \
+      }                                                                                                 \
+    }                                                                                                   \
+  } while (0)
+
 // curve leaf tests: [0] all, [1] those that pass CurveMayHit and run the full ribbon test
 static std::atomic<uint64_t> g_curve_probe[2];
 #define PBR_CURVE_PROBE(may) do { ++g_curve_probe[0]; if (may) ++g_curve_probe[1]; } while (0)
@@ -261,6 +278,88 @@ int emul_radiance(void* h, const pbrgpu_ray* rays, const uint64_t* seeds, uint64
 
 void emul_curve_probe(uint64_t* out2) {
   for (int k = 0; k < 2; ++k) out2[k] = g_curve_probe[k].exchange(0);
+}
+
+// start recording traced walk segments (cap > 0) / fetch what was recorded (returns the count, copies up to max_n)
+void emul_record_segments(uint64_t cap) {
+  std::lock_guard<std::mutex> lock(g_seg_mutex);
+  g_segments.clear();
+  g_seg_cap = cap;
+}
+uint64_t emul_fetch_segments(float* out8, uint64_t max_n) {
+  std::lock_guard<std::mutex> lock(g_seg_mutex);
+  const uint64_t n = std::min<uint64_t>(g_segments.size() / 8, max_n);
+  if (out8) memcpy(out8, g_segments.data(), sizeof(float) * 8 * n);
+  return g_segments.size() / 8;
+}
+
+// MEASUREMENT ONLY: for closest-hit queries through the TRIANGLE BVH, how many of the nodes a ray tests lie
+// on the chain from the root on which exactly one inner child (and no leaf) is hit — the nodes a traversal that
+// started at the end of that chain would not have to test.  out4 = (rays, nodes tested, nodes on the initial chain,
+// rays whose chain reaches a node with leaf hits only).  Depth-first in the static slot order, same boxes and
+// triangle test as TraverseBvh.
+int emul_tri_chain_stats(void* h, const pbrgpu_ray* rays, uint64_t n, uint64_t* out4) {
+  Emul* e = static_cast<Emul*>(h);
+  const SceneView& s = e->view;
+  if (!s.num_tris) return 1;
+  const uint32_t* nw = reinterpret_cast<const uint32_t*>(s.tri_nodes);
+  std::atomic<uint64_t> tot_nodes(0), tot_chain(0), tot_leafend(0);
+  ParallelFor(n, [&](uint64_t i) {
+    const RayT ray = ToRay(rays[i]);
+    float tfar = ray.tmax;
+    const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z};
+    std::vector<uint32_t> stack(1, 0u);
+    uint64_t nn = 0, chain = 0;
+    bool on_chain = true, leaf_end = false;
+    while (!stack.empty()) {
+      const uint32_t id = stack.back(); stack.pop_back();
+      ++nn;
+      const uint32_t* w = nw + size_t(20) * id;
+      float p[3], step[3];
+      memcpy(p, w, 12);
+      for (int k = 0; k < 3; ++k) { const uint32_t bits = ((w[3] >> (8 * k)) & 0xffu) << 23; memcpy(&step[k], &bits, 4); }
+      const uint32_t imask = w[3] >> 24, child_base = w[4], prim_base = w[5];
+      uint32_t inner_rank = 0, inner_hits = 0, leaf_hits = 0;
+      uint32_t hit_inner[8];
+      for (int sl = 0; sl < 8; ++sl) {
+        const uint32_t meta = (w[6 + sl / 4] >> (8 * (sl % 4))) & 0xffu;
+        if (!meta) continue;
+        const bool inner = (imask >> sl) & 1u;
+        const uint32_t my_rank = inner_rank;
+        if (inner) ++inner_rank;
+        float tn = ray.tmin, tf = tfar;
+        for (int k = 0; k < 3; ++k) {
+          const uint32_t qlo = (w[8 + 2 * k + sl / 4] >> (8 * (sl % 4))) & 0xffu, qhi = (w[14 + 2 * k + sl / 4] >> (8 * (sl % 4))) & 0xffu;
+          const float lo = p[k] + float(qlo) * step[k], hi = p[k] + float(qhi) * step[k];
+          const float inv = 1.0f / (std::fabs(d[k]) < 1e-30f ? std::copysign(1e-30f, d[k]) : d[k]);
+          float t0 = (lo - o[k]) * inv, t1 = (hi - o[k]) * inv;
+          if (t0 > t1) std::swap(t0, t1);
+          tn = std::max(tn, t0 * 0.999999f - 1e-6f); tf = std::min(tf, t1 * 1.000001f + 1e-6f);
+        }
+        if (tn > tf) continue;
+        if (inner) hit_inner[inner_hits++] = child_base + my_rank;
+        else {
+          ++leaf_hits;
+          const uint32_t unary = meta >> 5, cnt = unary == 1 ? 1u : (unary == 3 ? 2u : 3u);
+          for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t idx = prim_base + (meta & 0x1fu) + j;
+            float t, u, v;
+            if (IntersectTriangle(ray.o, ray.d, ray.tmin, tfar, from4(s.tri_data[idx * 3]), from4(s.tri_data[idx * 3 + 1]),
+                                  from4(s.tri_data[idx * 3 + 2]), &t, &u, &v))
+              tfar = t;
+          }
+        }
+      }
+      if (on_chain) {
+        if (inner_hits == 1 && leaf_hits == 0) ++chain;                 // this node could have been skipped
+        else { on_chain = false; leaf_end = (inner_hits == 0); }
+      }
+      for (uint32_t k = inner_hits; k > 0; --k) stack.push_back(hit_inner[k - 1]);
+    }
+    tot_nodes += nn; tot_chain += chain; tot_leafend += leaf_end ? 1 : 0;
+  });
+  out4[0] = n; out4[1] = tot_nodes; out4[2] = tot_chain; out4[3] = tot_leafend;
+  return 0;
 }
 
 // counters of PBR_CLEARANCE_PROBE since the last call (and reset)
