@@ -73,3 +73,18 @@ try:
             edge, spacing, margin, 100.0 * ok.mean(), 100.0 * miss.mean()))
 except ImportError:
     print("scipy not available: skipped the distance statistics")
+
+# ---- the same question for a concrete representation: bricks of F x F x F fine cells under the coarse cells, each fine
+# cell holding  (distance from its centre to the mesh) - (half its diagonal),  one sphere step from the segment's origin
+try:
+    cell = (hi[1] - lo[1]) / 501.0          # the clearance field's cell on this scene (505 cells incl. 4 spare layers)
+    O = seg[:, 0:3].astype(np.float64)
+    for F in (1, 2, 4, 8):
+        f = cell / F
+        centre = (np.floor(O / f) + 0.5) * f
+        dc, _ = tree.query(centre, workers=-1)
+        bound = dc - 0.866 * f - spacing
+        ok = L * 1.02 <= bound
+        print("fine cell = cell / %d (%.4f): one sphere step answers %.1f %% of the segments that are traced today" % (F, f, 100.0 * ok.mean()))
+except NameError:
+    pass
