@@ -385,6 +385,10 @@ def run_workload(name, args, rank, world, local_rank, steps, warmup, spp_overrid
             "workload": name, "value": samples_step * steps / (ms * 1e-3) * 1e-6, "unit": "Msamples/s",
             "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
             "Mrays_per_s": rays_step * steps / (ms * 1e-3) * 1e-6, "rays_per_sample": rays_step / samples_step,
+            # the reference issues one ray query per walk segment; here the clearance field answers most of them without a
+            # traversal (not counted as rays above): queries = rays + those
+            "Mray_queries_per_s": (rays_step + float(tally[3])) * steps / (ms * 1e-3) * 1e-6,
+            "ray_queries_per_sample": (rays_step + float(tally[3])) / samples_step,
             "e2e": {"value": samples_step * steps / (ms_e2e * 1e-3) * 1e-6, "unit": "Msamples/s",
                     "h2d_bytes_per_step": int(flat.materials.nbytes), "d2h_bytes_per_step": int(npix * 20)},
             "gpu_launches": int(launches),
@@ -467,6 +471,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32",
                 "data": "bundled OBJ (data/cornellbox_suzanne_lucy.obj)" if args.workload in ("c1", "c2") else "synthetic",
                 "config": head["config"], "Mrays_per_s": head["Mrays_per_s"], "rays_per_sample": head["rays_per_sample"],
+                "Mray_queries_per_s": head["Mray_queries_per_s"], "ray_queries_per_sample": head["ray_queries_per_sample"],
                 "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
                 "roofline_families": head["roofline_families"], "clocks": head.get("clocks")}
         if "cpu_baseline" in head:

@@ -80,6 +80,7 @@ struct HostScene {
   bool SetLights(const pbrgpu_light_tables* t);
   bool Commit(const float* bmin_in, const float* bmax_in);
   void BuildClearance();
+  void RefineClearanceNearSurface(float* scratch);
 
   uint32_t num_tris() const { return uint32_t(tri_vidx.size()); }
   uint32_t num_curves() const { return uint32_t(curve_ids.size()); }

@@ -81,6 +81,17 @@ class Emul:
         self.lib.emul_curve_probe(_p(o))
         return [int(x) for x in o]
 
+    def clearance_field(self):
+        """(bytes [dz, dy, dx], origin xyz, 1 / cell, quantum) of the committed scene's clearance field, or None"""
+        geo = np.zeros(7, np.float32); dims = np.zeros(3, np.uint32)
+        self.lib.emul_clearance_field.restype = C.c_uint64
+        n = self.lib.emul_clearance_field(self.h, _p(geo), _p(dims), None)
+        if not n:
+            return None
+        b = np.zeros(int(n), np.uint8)
+        self.lib.emul_clearance_field(self.h, _p(geo), _p(dims), _p(b))
+        return b.reshape(int(dims[2]), int(dims[1]), int(dims[0])), geo[:3].copy(), float(geo[3]), float(geo[4])
+
     def clearance_probe(self):
         """(walk segments, segments the clearance field skips, skipped segments that hit) since the last call"""
         o = np.zeros(3, np.uint64)

@@ -362,6 +362,16 @@ int emul_tri_chain_stats(void* h, const pbrgpu_ray* rays, uint64_t n, uint64_t* 
   return 0;
 }
 
+// the clearance field of the committed scene: geo7 = (org.xyz, inv_cell, quantum, -, -), dims3, and (bytes != null) the cells
+uint64_t emul_clearance_field(void* h, float* geo7, uint32_t* dims3, uint8_t* bytes) {
+  const pbrhost::HostScene& sc = static_cast<Emul*>(h)->scene;
+  for (int k = 0; k < 3; ++k) { geo7[k] = sc.clear_org[k]; dims3[k] = sc.clear_dims[k]; }
+  geo7[3] = sc.clear_inv_cell; geo7[4] = sc.clear_quantum;
+  const uint64_t n = uint64_t(sc.clear_dims[0]) * sc.clear_dims[1] * sc.clear_dims[2];
+  if (bytes && !sc.clear_dist.empty()) memcpy(bytes, sc.clear_dist.data(), n);
+  return sc.clear_dist.empty() ? 0 : n;
+}
+
 // counters of PBR_CLEARANCE_PROBE since the last call (and reset)
 void emul_clearance_probe(uint64_t* out3) {
   for (int k = 0; k < 3; ++k) out3[k] = g_clear_probe[k].exchange(0);

@@ -202,7 +202,11 @@ def test_render_properties_at_full_size(cornell_gpu):
     assert abs(m1 - m2) < 0.01 * m1                              # different streams, same estimator
     st = ctx.stats()
     assert st["paths"] == w * h * 64
-    assert 5.0 < (st["closest_rays"] + st["shadow_rays"] + st["sss_rays"]) / st["paths"] < 7.0   # reference: 5.995
+    # ray queries per path as the reference counts them (every walk segment is an rtcIntersect1 there; here the clearance
+    # field answers most of them without a traversal): reference 5.995
+    queries = st["closest_rays"] + st["shadow_rays"] + st["sss_rays"] + st["sss_skipped"]
+    assert 5.5 < queries / st["paths"] < 6.5, queries / st["paths"]
+    assert st["sss_rays"] > 0 and st["sss_skipped"] > 0.5 * st["sss_rays"]
 
 
 def test_live_material_edit(cornell_gpu):
