@@ -750,37 +750,54 @@ void HostScene::RefineClearanceNearSurface(float* scratch) {
   const int D[3] = {int(clear_dims[0]), int(clear_dims[1]), int(clear_dims[2])};
   const size_t ncell = size_t(D[0]) * D[1] * D[2];
   if (ncell == 0 || clear_dist.empty()) return;
-  // work of the pass for a radius: cells visited over all primitives (an upper bound: boxes are not clipped here)
+  // work of the pass for a radius: (cell, primitive) pairs it visits
   double budget = 3e8;
   if (const char* e = getenv("PBRGPU_CLEAR_EXACT_BUDGET")) budget = std::max(0.0, atof(e));
+  const double inv = double(clear_inv_cell);
+  // cells of the grid whose centre can be within `radius` cells of a box [lo, hi] (world units)
+  auto cell_range_r = [&](const double* blo, const double* bhi, double radius, int* a, int* b) {
+    for (int k = 0; k < 3; ++k) {
+      const double fa = (blo[k] - double(clear_org[k])) * inv - radius - 0.5, fb = (bhi[k] - double(clear_org[k])) * inv + radius - 0.5;
+      if (fb < 0.0 || fa > double(D[k] - 1)) return false;
+      a[k] = std::max(0, int(std::ceil(fa)));
+      b[k] = std::min(D[k] - 1, int(std::floor(fb)));
+      if (a[k] > b[k]) return false;
+    }
+    return true;
+  };
+  auto cells_of = [&](const double* blo, const double* bhi, double radius) -> uint64_t {
+    int a[3], b[3];
+    if (!cell_range_r(blo, bhi, radius, a, b)) return 0;
+    return uint64_t(b[0] - a[0] + 1) * uint64_t(b[1] - a[1] + 1) * uint64_t(b[2] - a[2] + 1);
+  };
   auto work_for = [&](double radius) {
     std::atomic<uint64_t> total(0);
     ParallelRanges(num_tris(), [&](uint64_t tb, uint64_t te) {
       uint64_t local = 0;
       for (uint64_t i = tb; i < te; ++i) {
         const F4 &A = verts[tri_vidx[i].x], &B = verts[tri_vidx[i].y], &C = verts[tri_vidx[i].z];
-        double cells = 1.0;
-        const float lo3[3] = {std::min(A.x, std::min(B.x, C.x)), std::min(A.y, std::min(B.y, C.y)), std::min(A.z, std::min(B.z, C.z))};
-        const float hi3[3] = {std::max(A.x, std::max(B.x, C.x)), std::max(A.y, std::max(B.y, C.y)), std::max(A.z, std::max(B.z, C.z))};
-        for (int k = 0; k < 3; ++k)
-          cells *= std::min(double(D[k]), double(hi3[k] - lo3[k]) * double(clear_inv_cell) + 2.0 * radius + 1.0);
-        local += uint64_t(cells);
+        const double lo3[3] = {std::min(A.x, std::min(B.x, C.x)), std::min(A.y, std::min(B.y, C.y)), std::min(A.z, std::min(B.z, C.z))};
+        const double hi3[3] = {std::max(A.x, std::max(B.x, C.x)), std::max(A.y, std::max(B.y, C.y)), std::max(A.z, std::max(B.z, C.z))};
+        local += cells_of(lo3, hi3, radius);
       }
       total += local;
     });
-    uint64_t curve_cells = 0;
-    for (uint32_t i = 0; i < num_curves(); ++i) {
-      const F4* cp = &curve_cps[4 * size_t(i)];
-      double cells = 1.0;
-      for (int k = 0; k < 3; ++k) {
-        const float* v0 = &cp[0].x;
-        float lo1 = v0[k], hi1 = v0[k];
-        for (int c = 1; c < 4; ++c) { lo1 = std::min(lo1, (&cp[c].x)[k]); hi1 = std::max(hi1, (&cp[c].x)[k]); }
-        cells *= std::min(double(D[k]), double(hi1 - lo1) * double(clear_inv_cell) + 2.0 * radius + 1.0);
+    ParallelRanges(num_curves(), [&](uint64_t cb, uint64_t ce) {
+      uint64_t local = 0;
+      for (uint64_t i = cb; i < ce; ++i) {
+        const F4* cp = &curve_cps[4 * size_t(i)];
+        double lo3[3] = {1e300, 1e300, 1e300}, hi3[3] = {-1e300, -1e300, -1e300}, r = 0.0;
+        for (int c = 0; c < 4; ++c) {
+          r = std::max(r, std::fabs(double(cp[c].w)));
+          const double v[3] = {cp[c].x, cp[c].y, cp[c].z};
+          for (int k = 0; k < 3; ++k) { lo3[k] = std::min(lo3[k], v[k]); hi3[k] = std::max(hi3[k], v[k]); }
+        }
+        for (int k = 0; k < 3; ++k) { lo3[k] -= r * 1.0001; hi3[k] += r * 1.0001; }
+        local += cells_of(lo3, hi3, radius);
       }
-      curve_cells += uint64_t(cells);
-    }
-    return double(total.load()) + double(curve_cells);
+      total += local;
+    });
+    return double(total.load());
   };
   double radius = 0.0;
   for (double r : {2.5, 1.5}) {
@@ -807,18 +824,7 @@ void HostScene::RefineClearanceNearSurface(float* scratch) {
     for (uint64_t i = b; i < e; ++i) dmin2[i].store(bits, std::memory_order_relaxed);
   });
   lap("cleared");
-  const double inv = double(clear_inv_cell);
-  // cells whose centre can be within kRefineCells of a box [lo, hi] (world units)
-  auto cell_range = [&](const double* blo, const double* bhi, int* a, int* b) {
-    for (int k = 0; k < 3; ++k) {
-      const double fa = (blo[k] - double(clear_org[k])) * inv - kRefineCells - 0.5, fb = (bhi[k] - double(clear_org[k])) * inv + kRefineCells - 0.5;
-      if (fb < 0.0 || fa > double(D[k] - 1)) return false;
-      a[k] = std::max(0, int(std::ceil(fa)));
-      b[k] = std::min(D[k] - 1, int(std::floor(fb)));
-      if (a[k] > b[k]) return false;
-    }
-    return true;
-  };
+  auto cell_range = [&](const double* blo, const double* bhi, int* a, int* b) { return cell_range_r(blo, bhi, kRefineCells, a, b); };
   const uint32_t nt = num_tris();
   ParallelRanges(nt, [&](uint64_t tb, uint64_t te) {
     for (uint64_t i = tb; i < te; ++i) {
